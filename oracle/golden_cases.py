@@ -1,0 +1,95 @@
+"""Golden-case definitions shared by oracle/make_golden.py (generator, needs /root/reference)
+and the tests (consumers, need only tests/golden/*.npz).  TEST INFRASTRUCTURE ONLY.
+
+Every case is fully determined by its entry here: weights come from
+``gcp_oracle.random_layer_params(cfg, seed)`` (or from a shipped checkpoint and are then stored
+in the fixture), inputs from ``build_inputs``.  The fixture stores the reference's outputs and
+gradients plus checksums of the regenerated weights/inputs so RNG drift is detected.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict
+
+import torch
+
+from . import gcp_oracle as O
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+CASES: Dict[str, dict] = {
+    # NMS hidden dims (configs/model/model_cfg/gcp_model_nms.yaml), 3 five-body graphs, positions updated
+    "nms_random": dict(cfg=dict(node_dims=(64, 16), edge_dims=(32, 4), updating_node_positions=True),
+                       graph=("nms", 3, 5), seed=11),
+    # same shapes, weights = interaction_layers.0 of checkpoints/NMS/NMS_Small (stored in fixture)
+    "nms_ckpt_layer0": dict(cfg=dict(node_dims=(64, 16), edge_dims=(32, 4), updating_node_positions=True),
+                            graph=("nms", 4, 5), seed=12,
+                            ckpt=("checkpoints/NMS/NMS_Small/model_epoch_9977_mse_0_0070.ckpt", 0)),
+    # LBA/CPD hidden dims, random multigraph with self loops, duplicates and isolated nodes
+    "lba_random_multigraph": dict(cfg=dict(node_dims=(100, 16), edge_dims=(32, 4)),
+                                  graph=("random", 40, 260), seed=13),
+    # small dims, 3 message layers, silu, vector residual, e3 on the edge path is not used (node path)
+    "tiny_silu_vres": dict(cfg=dict(node_dims=(8, 4), edge_dims=(4, 2), num_message_layers=3,
+                                    scalar_nonlinearity="silu", vector_residual=True, bottleneck=2,
+                                    default_bottleneck=2, updating_node_positions=True),
+                           graph=("random", 12, 50), seed=14),
+    # non-residual message stack, two message layers, kNN-like graph
+    "tiny_nonresidual": dict(cfg=dict(node_dims=(12, 4), edge_dims=(6, 2), num_message_layers=2,
+                                      use_residual_message_gcp=False, bottleneck=2, default_bottleneck=2),
+                             graph=("knn", 2, 9, 4), seed=15),
+    # single message layer (nonlinearities=None on G0, gcpnet.py:878)
+    "tiny_one_message_layer": dict(cfg=dict(node_dims=(8, 4), edge_dims=(4, 2), num_message_layers=1,
+                                             bottleneck=2, default_bottleneck=2),
+                                   graph=("random", 10, 30), seed=16),
+}
+
+
+def build_cfg(case: dict) -> O.OracleConfig:
+    return O.OracleConfig(**case["cfg"])
+
+
+def build_graph(case: dict):
+    g = case["graph"]
+    gen = torch.Generator().manual_seed(case["seed"])
+    if g[0] == "nms":
+        ei = O.nms_edge_index(g[1], g[2])
+        n = g[1] * g[2]
+        pos = None
+    elif g[0] == "random":
+        n, E = g[1], g[2]
+        # last two nodes never appear (isolated); self loops and duplicate edges occur
+        ei = torch.randint(0, n - 2, (2, E), generator=gen)
+        ei[:, 0] = ei[:, 1]  # guaranteed duplicate edge
+        ei[1, 2] = ei[0, 2]  # guaranteed self loop
+        pos = None
+    elif g[0] == "knn":
+        ei, pos = O.knn_like_edge_index(g[1], g[2], g[3], seed=case["seed"])
+        n = g[1] * g[2]
+    else:
+        raise ValueError(g)
+    return ei, n, pos
+
+
+def build_inputs(case: dict, dtype=torch.float32):
+    cfg = build_cfg(case)
+    ei, n, pos = build_graph(case)
+    return O.synthetic_layer_inputs(cfg, ei, n, seed=case["seed"], dtype=dtype, positions=pos)
+
+
+def loss_weights(case: dict, cfg: O.OracleConfig, n: int, dtype=torch.float32):
+    """Fixed random cotangents so the backward check is not the degenerate all-ones case."""
+    g = torch.Generator().manual_seed(case["seed"] + 1000)
+    s, v = cfg.node_dims
+    return (torch.randn(n, s, generator=g, dtype=torch.float64).to(dtype),
+            torch.randn(n, v, 3, generator=g, dtype=torch.float64).to(dtype),
+            torch.randn(n, 3, generator=g, dtype=torch.float64).to(dtype))
+
+
+def checksum(t: torch.Tensor) -> float:
+    t = t.detach().to(torch.float64).reshape(-1)
+    w = torch.arange(1, t.numel() + 1, dtype=torch.float64)
+    return float((t * torch.cos(w)).sum())
+
+
+def fixture_path(name: str) -> str:
+    return os.path.join(GOLDEN_DIR, f"{name}.npz")

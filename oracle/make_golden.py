@@ -1,0 +1,103 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from
+/root/reference through oracle/ref_shim.py) on the cases of oracle/golden_cases.py.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (the reference does not travel):
+
+    python -m oracle.make_golden
+
+Each fixture holds: the reference's fp32 outputs (h, chi[, pos]) in eval mode, the gradients
+of ``sum(out * cotangent)`` w.r.t. h, chi, e, xi and every parameter (large tensors are stored
+as every 7th element), and checksums of the regenerated weights and inputs.  For checkpoint
+cases the layer's trained weights are stored too.
+"""
+from __future__ import annotations
+
+import sys
+
+import numpy as np
+import torch
+
+from . import gcp_oracle as O
+from . import golden_cases as GC
+from . import ref_shim
+
+SAMPLE_STRIDE = 7
+SAMPLE_MIN = 2048
+
+
+def sample(t: torch.Tensor) -> np.ndarray:
+    a = t.detach().cpu().numpy()
+    if a.size > SAMPLE_MIN:
+        return a.reshape(-1)[::SAMPLE_STRIDE].copy()
+    return a
+
+
+def run_reference(name: str, case: dict):
+    ref = ref_shim.load_reference()
+    cfg = GC.build_cfg(case)
+    rcfg, rlayer = ref_shim.make_cfgs(
+        ref, num_message_layers=cfg.num_message_layers, pre_norm=cfg.pre_norm,
+        num_feedforward_layers=cfg.num_feedforward_layers,
+        scalar_nonlinearity=cfg.scalar_nonlinearity, vector_nonlinearity=cfg.vector_nonlinearity,
+        bottleneck=cfg.bottleneck, vector_residual=cfg.vector_residual,
+        enable_e3_equivariance=cfg.enable_e3_equivariance,
+        use_residual_message_gcp=cfg.use_residual_message_gcp)
+    rcfg.default_bottleneck = cfg.default_bottleneck
+    SV = ref.ScalarVector
+    layer = ref.GCPInteractions(SV(*cfg.node_dims), SV(*cfg.edge_dims), cfg=rcfg, layer_cfg=rlayer,
+                                dropout=0.1, updating_node_positions=cfg.updating_node_positions)
+    if "ckpt" in case:
+        sd = ref_shim.load_checkpoint_state_dict(case["ckpt"][0])
+        pre = f"interaction_layers.{case['ckpt'][1]}."
+        params = {k[len(pre):]: v.float() for k, v in sd.items() if k.startswith(pre)}
+    else:
+        params = O.random_layer_params(cfg, seed=case["seed"])
+    layer.load_state_dict(params, strict=True)  # names AND shapes must match the reference's
+    layer.eval()
+
+    inp = GC.build_inputs(case)
+    leaves = {k: inp[k].clone().requires_grad_(True) for k in ("h", "chi", "e", "xi")}
+    out = layer((leaves["h"], leaves["chi"]), (leaves["e"], leaves["xi"]), inp["edge_index"],
+                inp["frames"], node_pos=inp["node_pos"] if cfg.updating_node_positions else None)
+    n = inp["h"].shape[0]
+    ch, cchi, cpos = GC.loss_weights(case, cfg, n)
+    if cfg.updating_node_positions:
+        (oh, ochi), opos = out
+        loss = (oh * ch).sum() + (ochi * cchi).sum() + (opos * cpos).sum()
+    else:
+        oh, ochi = out
+        opos = None
+        loss = (oh * ch).sum() + (ochi * cchi).sum()
+    loss.backward()
+
+    rec = {"out_h": oh.detach().numpy(), "out_chi": ochi.detach().numpy(),
+           "loss": np.float64(loss.item())}
+    if opos is not None:
+        rec["out_pos"] = opos.detach().numpy()
+    for k, t in leaves.items():
+        rec["grad_" + k] = t.grad.numpy()
+    for k, p in layer.named_parameters():
+        rec["pgrad/" + k] = sample(p.grad if p.grad is not None else torch.zeros_like(p))
+    rec["checksum_params"] = np.float64(sum(GC.checksum(v) for v in params.values()))
+    rec["checksum_inputs"] = np.float64(sum(GC.checksum(inp[k]) for k in ("h", "chi", "e", "xi", "frames")))
+    if "ckpt" in case:
+        for k, v in params.items():
+            rec["param/" + k] = v.numpy()
+    np.savez_compressed(GC.fixture_path(name), **rec)
+    print(f"{name}: N={n} E={inp['edge_index'].shape[1]} loss={loss.item():.6f} -> {GC.fixture_path(name)}")
+
+
+def main(argv):
+    if not ref_shim.reference_available():
+        print("reference tree not available; nothing generated", file=sys.stderr)
+        return 1
+    torch.manual_seed(0)
+    torch.set_num_threads(1)  # bitwise reproducible reductions
+    names = argv[1:] or list(GC.CASES)
+    for name in names:
+        run_reference(name, GC.CASES[name])
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main(sys.argv))

@@ -1,0 +1,66 @@
+"""Live pin of the oracle against the imported, unmodified reference.  Runs only where
+/root/reference exists (the build container); skipped on the GPU box."""
+import pytest
+import torch
+
+from oracle import gcp_oracle as O
+from oracle import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not present")
+
+
+def _ref_layer(cfg: O.OracleConfig, params):
+    ref = ref_shim.load_reference()
+    rcfg, rlayer = ref_shim.make_cfgs(
+        ref, num_message_layers=cfg.num_message_layers, bottleneck=cfg.bottleneck,
+        scalar_nonlinearity=cfg.scalar_nonlinearity, vector_residual=cfg.vector_residual,
+        enable_e3_equivariance=cfg.enable_e3_equivariance,
+        use_residual_message_gcp=cfg.use_residual_message_gcp)
+    rcfg.default_bottleneck = cfg.default_bottleneck
+    SV = ref.ScalarVector
+    layer = ref.GCPInteractions(SV(*cfg.node_dims), SV(*cfg.edge_dims), cfg=rcfg, layer_cfg=rlayer,
+                                dropout=0.0, updating_node_positions=cfg.updating_node_positions)
+    layer.load_state_dict(params, strict=True)
+    return ref, layer.eval()
+
+
+@pytest.mark.parametrize("e3", [False, True])
+def test_equivariance_test_shapes(e3):
+    """Shapes of tests/test_gcpnet_equivariance.py:59-75: 300 nodes, 10 000 random edges, (100,16)/(32,4)."""
+    cfg = O.OracleConfig(node_dims=(100, 16), edge_dims=(32, 4), enable_e3_equivariance=e3)
+    params = O.random_layer_params(cfg, seed=3)
+    g = torch.Generator().manual_seed(1)
+    ei = torch.randint(0, 300, (2, 10000), generator=g)
+    inp = O.synthetic_layer_inputs(cfg, ei, 300, seed=5)
+    ref, layer = _ref_layer(cfg, params)
+    with torch.no_grad():
+        rh, rchi = layer((inp["h"], inp["chi"]), (inp["e"], inp["xi"]), ei, inp["frames"])
+        oh, ochi = O.interactions_forward(params, cfg, inp["h"], inp["chi"], inp["e"], inp["xi"], ei, inp["frames"])
+    assert torch.allclose(oh, rh, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(ochi, rchi, rtol=1e-4, atol=1e-5)
+
+
+def test_localize_matches_reference():
+    ref = ref_shim.load_reference()
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(50, 3, generator=g)
+    ei = torch.randint(0, 50, (2, 400), generator=g)
+    assert torch.allclose(O.localize(x, ei), ref.localize(x, ei), rtol=1e-6, atol=1e-7)
+
+
+def test_rotation_equivariance_of_oracle():
+    """The property tests/test_gcpnet_equivariance.py:1773-1881 asserts (atol 1e-5, rtol 1e-4)."""
+    cfg = O.OracleConfig(node_dims=(100, 16), edge_dims=(32, 4))
+    params = O.random_layer_params(cfg, seed=4, dtype=torch.float64)
+    g = torch.Generator().manual_seed(7)
+    ei = torch.randint(0, 60, (2, 600), generator=g)
+    x = torch.randn(60, 3, generator=g, dtype=torch.float64)
+    inp = O.synthetic_layer_inputs(cfg, ei, 60, seed=6, dtype=torch.float64, positions=x)
+    Q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g, dtype=torch.float64))
+    if torch.det(Q) < 0:
+        Q = -Q
+    oh, ochi = O.interactions_forward(params, cfg, inp["h"], inp["chi"], inp["e"], inp["xi"], ei, inp["frames"])
+    fr = O.localize(x @ Q, ei)
+    rh, rchi = O.interactions_forward(params, cfg, inp["h"], inp["chi"] @ Q, inp["e"], inp["xi"] @ Q, ei, fr)
+    assert torch.allclose(rh, oh, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(rchi, ochi @ Q, rtol=1e-4, atol=1e-5)
