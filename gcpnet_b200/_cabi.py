@@ -1,0 +1,248 @@
+"""ctypes mirror of include/gcpnet_b200.h (structures + prototypes).  No torch in here.
+
+The same structures are used by the product binding (gcpnet_b200/_lib.py, device pointers) and by
+the CPU emulation the non-GPU tests drive (tests/emul, host pointers).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+MAX_MESSAGE_LAYERS = 12
+ACT = {None: 0, "none": 0, "relu": 1, "leakyrelu": 2, "silu": 3, "sigmoid": 4, "selu": 5}
+
+c_float_p = C.POINTER(C.c_float)
+c_int32_p = C.POINTER(C.c_int32)
+c_int64_p = C.POINTER(C.c_int64)
+
+
+class Gcp2(C.Structure):
+    _fields_ = [
+        ("si", C.c_int32), ("vi", C.c_int32), ("so", C.c_int32), ("vo", C.c_int32), ("hd", C.c_int32),
+        ("act_s", C.c_int32), ("act_v", C.c_int32), ("vector_residual", C.c_int32),
+        ("vector_down", C.c_void_p), ("vector_down_frames", C.c_void_p), ("scalar_out_w", C.c_void_p),
+        ("scalar_out_b", C.c_void_p), ("vector_up", C.c_void_p), ("vector_out_scale_w", C.c_void_p),
+        ("vector_out_scale_b", C.c_void_p),
+        ("grad_off", C.c_int32 * 7), ("reserved", C.c_int32),
+    ]
+
+
+class Layer(C.Structure):
+    _fields_ = [
+        ("s", C.c_int32), ("v", C.c_int32), ("se", C.c_int32), ("ve", C.c_int32),
+        ("num_message_layers", C.c_int32), ("residual_messages", C.c_int32), ("reduce_mean", C.c_int32),
+        ("enable_e3", C.c_int32), ("has_pos", C.c_int32), ("training", C.c_int32),
+        ("slope", C.c_float), ("ln_eps", C.c_float), ("vn_eps", C.c_float), ("pos_weight", C.c_float),
+        ("p_drop", C.c_float),
+        ("seed", C.c_uint64), ("rng_counter", C.c_void_p),
+        ("message", Gcp2 * MAX_MESSAGE_LAYERS), ("ff0", Gcp2), ("ff1", Gcp2), ("pos_update", Gcp2),
+        ("ln0_w", C.c_void_p), ("ln0_b", C.c_void_p), ("ln1_w", C.c_void_p), ("ln1_b", C.c_void_p),
+        ("ln_grad_off", C.c_int32 * 4), ("n_edge_params", C.c_int32), ("n_node_params", C.c_int32),
+    ]
+
+
+class Graph(C.Structure):
+    _fields_ = [
+        ("num_nodes", C.c_int64), ("num_edges", C.c_int64),
+        ("perm", C.c_void_p), ("src", C.c_void_p), ("dst", C.c_void_p), ("dst_ptr", C.c_void_p),
+        ("src_pos", C.c_void_p), ("src_ptr", C.c_void_p), ("fbar", C.c_void_p),
+    ]
+
+
+class Plan(C.Structure):
+    _fields_ = [
+        ("edge_tile", C.c_int32), ("edge_grid_fwd", C.c_int32), ("edge_grid_bwd", C.c_int32),
+        ("node_tile", C.c_int32), ("node_grid_fwd", C.c_int32), ("node_grid_bwd", C.c_int32),
+        ("edge_smem_fwd_bytes", C.c_int32), ("edge_smem_bwd_bytes", C.c_int32),
+        ("node_smem_fwd_bytes", C.c_int32), ("node_smem_bwd_bytes", C.c_int32),
+        ("msg_floats", C.c_int64), ("saved_edge_floats", C.c_int64), ("saved_node_floats", C.c_int64),
+        ("edge_partial_floats", C.c_int64), ("node_partial_floats", C.c_int64),
+        ("edge_cotangent_floats", C.c_int64), ("agg_cotangent_floats", C.c_int64),
+    ]
+
+
+class ForwardIO(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("h", "chi", "e", "xi", "frames", "pos", "out_h", "out_chi", "out_pos", "msg", "saved_edge", "saved_node")]
+
+
+class BackwardIO(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("h", "chi", "e", "xi", "frames", "saved_edge", "saved_node", "g_out_h", "g_out_chi", "g_out_pos",
+                 "g_h", "g_chi", "g_e", "g_xi", "g_params", "ws_agg", "ws_edge", "ws_edge_partial", "ws_node_partial")]
+
+
+EXPORTS = (
+    "gcpnet_version", "gcpnet_last_error", "gcpnet_graph_workspace_bytes", "gcpnet_graph_build",
+    "gcpnet_localize", "gcpnet_layer_plan", "gcpnet_layer_forward", "gcpnet_layer_backward",
+    "gcpnet_message_passing_forward",
+)
+
+
+def declare(lib: C.CDLL) -> None:
+    """Attach argument / return types to every symbol include/gcpnet_b200.h declares."""
+    lib.gcpnet_version.restype = C.c_int
+    lib.gcpnet_version.argtypes = []
+    lib.gcpnet_last_error.restype = C.c_char_p
+    lib.gcpnet_last_error.argtypes = []
+    lib.gcpnet_graph_workspace_bytes.restype = C.c_size_t
+    lib.gcpnet_graph_workspace_bytes.argtypes = [C.c_int64, C.c_int64]
+    lib.gcpnet_graph_build.restype = C.c_int
+    lib.gcpnet_graph_build.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p] + [C.c_void_p] * 7 + \
+        [C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.gcpnet_localize.restype = C.c_int
+    lib.gcpnet_localize.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+    lib.gcpnet_layer_plan.restype = C.c_int
+    lib.gcpnet_layer_plan.argtypes = [C.POINTER(Layer), C.c_int64, C.c_int64, C.POINTER(Plan)]
+    lib.gcpnet_layer_forward.restype = C.c_int
+    lib.gcpnet_layer_forward.argtypes = [C.POINTER(Layer), C.POINTER(Graph), C.POINTER(Plan), C.POINTER(ForwardIO), C.c_void_p]
+    lib.gcpnet_layer_backward.restype = C.c_int
+    lib.gcpnet_layer_backward.argtypes = [C.POINTER(Layer), C.POINTER(Graph), C.POINTER(Plan), C.POINTER(BackwardIO), C.c_void_p]
+    lib.gcpnet_message_passing_forward.restype = C.c_int
+    lib.gcpnet_message_passing_forward.argtypes = [C.POINTER(Layer), C.POINTER(Graph), C.POINTER(Plan),
+                                                   C.POINTER(ForwardIO), C.c_void_p, C.c_void_p]
+
+
+# ------------------------------------------------------------------------------------------
+# layer description from a configuration + a name -> pointer map
+# ------------------------------------------------------------------------------------------
+GCP2_PARAM_ORDER = ("vector_down.weight", "scalar_out.weight", "scalar_out.bias", "vector_down_frames.weight",
+                    "vector_up.weight", "vector_out_scale.weight", "vector_out_scale.bias")  # state_dict order
+# index of each state_dict entry inside Gcp2.grad_off
+_GRAD_SLOT = {"vector_down.weight": 0, "vector_down_frames.weight": 1, "scalar_out.weight": 2, "scalar_out.bias": 3,
+              "vector_up.weight": 4, "vector_out_scale.weight": 5, "vector_out_scale.bias": 6}
+_PTR_FIELD = {"vector_down.weight": "vector_down", "vector_down_frames.weight": "vector_down_frames",
+              "scalar_out.weight": "scalar_out_w", "scalar_out.bias": "scalar_out_b", "vector_up.weight": "vector_up",
+              "vector_out_scale.weight": "vector_out_scale_w", "vector_out_scale.bias": "vector_out_scale_b"}
+
+
+def gcp2_hidden_dim(vi: int, vo: int, bottleneck: int) -> int:
+    """gcpnet.py:298-299."""
+    return vi // bottleneck if bottleneck > 1 else max(vi, vo)
+
+
+def gcp2_shapes(si: int, vi: int, so: int, vo: int, hd: int) -> Dict[str, Tuple[int, ...]]:
+    return {"vector_down.weight": (hd, vi), "scalar_out.weight": (so, si + hd + 9), "scalar_out.bias": (so,),
+            "vector_down_frames.weight": (3, vi), "vector_up.weight": (vo, hd),
+            "vector_out_scale.weight": (vo, so), "vector_out_scale.bias": (vo,)}
+
+
+class LayerSpec:
+    """Static description of one GCPInteractions layer: module list, dims, flags and the flat
+    parameter layout (names in the reference's state_dict order, gcpnet.py:963-1063)."""
+
+    def __init__(self, node_dims, edge_dims, *, num_message_layers=8, bottleneck=4, default_bottleneck=4,
+                 vector_residual=False, default_vector_residual=False, scalar_nonlinearity="relu",
+                 vector_nonlinearity=None, nonlinearity_slope=1e-2, use_residual_message_gcp=True,
+                 enable_e3_equivariance=False, reduce_function="mean", updating_node_positions=False,
+                 node_positions_weight=1.0):
+        self.s, self.v = int(node_dims[0]), int(node_dims[1])
+        self.se, self.ve = int(edge_dims[0]), int(edge_dims[1])
+        self.L = int(num_message_layers)
+        self.residual = bool(use_residual_message_gcp)
+        self.e3 = bool(enable_e3_equivariance)
+        self.reduce_mean = reduce_function == "mean"
+        self.has_pos = bool(updating_node_positions)
+        self.pos_weight = float(node_positions_weight)
+        self.slope = float(nonlinearity_slope)
+        a_s, a_v = ACT[_norm(scalar_nonlinearity)], ACT[_norm(vector_nonlinearity)]
+        s, v, se, ve, L = self.s, self.v, self.se, self.ve, self.L
+        # (prefix, si, vi, so, vo, hd, act_s, act_v, vres)
+        mods: List[tuple] = []
+        for k in range(L):
+            primary = k == 0 or k == L - 1
+            bn = default_bottleneck if primary else bottleneck
+            vres = default_vector_residual if primary else vector_residual
+            if k == 0:
+                acts = (a_s, a_v) if L > 1 else (0, 0)  # gcpnet.py:878
+                si, vi = 2 * s + se, 2 * v + ve
+            else:
+                acts = (0, 0) if k == L - 1 else (a_s, a_v)  # gcpnet.py:887
+                si, vi = s, v
+            if bn > 1 and vi % bn != 0:
+                raise AssertionError(f"Input channel of vector ({vi}) must be divisible with bottleneck factor ({bn})")
+            mods.append((f"interaction.message_fusion.{k}.", si, vi, s, v, gcp2_hidden_dim(vi, v, bn), acts[0], acts[1], int(vres)))
+        self.message_mods = mods
+        hs, hv = 4 * s, 2 * v  # gcpnet.py:1014 with num_feedforward_layers == 2
+        self.hs, self.hv = hs, hv
+        if bottleneck > 1 and (v % bottleneck != 0 or hv % bottleneck != 0):
+            raise AssertionError("vector channels must be divisible by the bottleneck factor")
+        self.ff_mods = [
+            ("feedforward_network.0.", s, v, hs, hv, gcp2_hidden_dim(v, hv, bottleneck), a_s, a_v, 0),
+            ("feedforward_network.1.", hs, hv, s, v, gcp2_hidden_dim(hv, v, bottleneck), 0, 0, 0),
+        ]
+        self.pos_mod = ("node_position_update_network.0.", s, v, s, 1, gcp2_hidden_dim(v, 1, bottleneck), a_s, a_v, 0) \
+            if self.has_pos else None
+        # flat parameter layout
+        self.names: List[str] = []
+        self.shapes: Dict[str, Tuple[int, ...]] = {}
+        self.offsets: Dict[str, int] = {}
+        off = 0
+
+        def add(name, shape):
+            nonlocal off
+            self.names.append(name)
+            self.shapes[name] = tuple(shape)
+            self.offsets[name] = off
+            n = 1
+            for d in shape:
+                n *= d
+            off += n
+
+        for m in mods:
+            for pn, shp in gcp2_shapes(*m[1:6]).items():
+                add(m[0] + pn, shp)
+        self.n_edge_params = off
+        for i in range(2):
+            add(f"gcp_norm.{i}.scalar_norm.weight", (s,))
+            add(f"gcp_norm.{i}.scalar_norm.bias", (s,))
+        for m in self.ff_mods + ([self.pos_mod] if self.pos_mod else []):
+            for pn, shp in gcp2_shapes(*m[1:6]).items():
+                add(m[0] + pn, shp)
+        self.n_params = off
+        self.n_node_params = off - self.n_edge_params
+
+    def fill_gcp2(self, dst: Gcp2, mod: tuple, ptr: Callable[[str], int]) -> None:
+        prefix, si, vi, so, vo, hd, act_s, act_v, vres = mod
+        dst.si, dst.vi, dst.so, dst.vo, dst.hd = si, vi, so, vo, hd
+        dst.act_s, dst.act_v, dst.vector_residual = act_s, act_v, vres
+        for pn in GCP2_PARAM_ORDER:
+            setattr(dst, _PTR_FIELD[pn], ptr(prefix + pn))
+            dst.grad_off[_GRAD_SLOT[pn]] = self.offsets[prefix + pn]
+
+    def make_layer(self, ptr: Callable[[str], int], *, training=False, p_drop=0.0, seed=0, rng_counter=0) -> Layer:
+        l = Layer()
+        l.s, l.v, l.se, l.ve = self.s, self.v, self.se, self.ve
+        l.num_message_layers = self.L
+        l.residual_messages = int(self.residual)
+        l.reduce_mean = int(self.reduce_mean)
+        l.enable_e3 = int(self.e3)
+        l.has_pos = int(self.has_pos)
+        l.training = int(bool(training) and p_drop > 0.0)
+        l.slope, l.ln_eps, l.vn_eps = self.slope, 1e-5, 1e-8
+        l.pos_weight = self.pos_weight
+        l.p_drop = float(p_drop)
+        l.seed = int(seed) & (2 ** 64 - 1)
+        l.rng_counter = rng_counter
+        for k, m in enumerate(self.message_mods):
+            self.fill_gcp2(l.message[k], m, ptr)
+        self.fill_gcp2(l.ff0, self.ff_mods[0], ptr)
+        self.fill_gcp2(l.ff1, self.ff_mods[1], ptr)
+        if self.pos_mod:
+            self.fill_gcp2(l.pos_update, self.pos_mod, ptr)
+        l.ln0_w, l.ln0_b = ptr("gcp_norm.0.scalar_norm.weight"), ptr("gcp_norm.0.scalar_norm.bias")
+        l.ln1_w, l.ln1_b = ptr("gcp_norm.1.scalar_norm.weight"), ptr("gcp_norm.1.scalar_norm.bias")
+        for i, n in enumerate(("gcp_norm.0.scalar_norm.weight", "gcp_norm.0.scalar_norm.bias",
+                               "gcp_norm.1.scalar_norm.weight", "gcp_norm.1.scalar_norm.bias")):
+            l.ln_grad_off[i] = self.offsets[n]
+        l.n_edge_params, l.n_node_params = self.n_edge_params, self.n_node_params
+        return l
+
+
+def _norm(name: Optional[str]) -> Optional[str]:
+    if name is None:
+        return None
+    n = str(name).lower().strip()
+    if n not in ACT:
+        raise NotImplementedError(f"The nonlinearity {name} is currently not implemented.")
+    return n

@@ -1,0 +1,147 @@
+/* gcpnet_b200.h -- C ABI of the B200-native GCPNet message-passing layer.
+ *
+ * The reference (BioinfoMachineLearning/GCPNet @ 172733b) is pure Python: its "operator interface"
+ * for this path is the nn.Module GCPInteractions (src/models/components/gcpnet.py:963-1262) and the
+ * torch_scatter.scatter calls under it (gcpnet.py:946; src/models/components/__init__.py:316).
+ * This header is the boundary a binding for that path links against: plain pointers and sizes,
+ * device memory owned by the caller, every call enqueues work on the caller's CUDA stream and
+ * returns immediately (no allocation, no synchronisation -> safe inside CUDA-graph capture).
+ * gcpnet_b200/interactions.py (ctypes) is the reference-facing binding; INTEGRATION.md shows it.
+ *
+ * All feature tensors are fp32, row-major, contiguous:
+ *   h[N][s]  chi[N][v][3]  e[E][se]  xi[E][ve][3]  frames[E][3][3]  pos[N][3]
+ *   edge_index int64 [2][E] exactly as the reference receives it (gcpnet.py:1165), any order,
+ *   self loops / duplicate edges / isolated nodes allowed.
+ * Return value: 0 on success, non-zero on error (message via gcpnet_last_error()).
+ */
+#ifndef GCPNET_B200_H
+#define GCPNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCPNET_MAX_MESSAGE_LAYERS 12
+
+/* scalar / vector nonlinearities: src/models/__init__.py:41-57 (get_nonlinearity) */
+enum gcpnet_act { GCPNET_ACT_NONE = 0, GCPNET_ACT_RELU = 1, GCPNET_ACT_LEAKYRELU = 2, GCPNET_ACT_SILU = 3,
+                  GCPNET_ACT_SIGMOID = 4, GCPNET_ACT_SELU = 5 };
+
+/* One GCP2 module (gcpnet.py:252-468, vector_gate path).  Weights keep the reference's nn.Linear
+ * layouts and state_dict names: vector_down.weight[hd][vi], vector_down_frames.weight[3][vi],
+ * scalar_out.weight[so][si+hd+9] (+bias[so]), vector_up.weight[vo][hd],
+ * vector_out_scale.weight[vo][so] (+bias[vo]).  grad_off[i] = offset (floats) of the i-th block's
+ * gradient inside the layer's flat gradient, in the order listed. */
+typedef struct gcpnet_gcp2 {
+  int32_t si, vi, so, vo, hd;
+  int32_t act_s, act_v, vector_residual;
+  const float* vector_down;
+  const float* vector_down_frames;
+  const float* scalar_out_w;
+  const float* scalar_out_b;
+  const float* vector_up;
+  const float* vector_out_scale_w;
+  const float* vector_out_scale_b;
+  int32_t grad_off[7]; /* vector_down, vector_down_frames, scalar_out_w, scalar_out_b, vector_up, vector_out_scale_w, vector_out_scale_b */
+  int32_t reserved;
+} gcpnet_gcp2;
+
+/* One GCPInteractions layer (gcpnet.py:963-1063): message stack, two LayerNorms, two feed-forward
+ * GCPs, optional position-update GCP.  Flat gradient layout = [message_fusion.* | everything else];
+ * n_edge_params / n_node_params are the two block sizes in floats. */
+typedef struct gcpnet_layer {
+  int32_t s, v, se, ve;            /* node (s, v) and edge (se, ve) hidden dims */
+  int32_t num_message_layers;      /* mp_cfg.num_message_layers */
+  int32_t residual_messages;       /* mp_cfg.use_residual_message_gcp */
+  int32_t reduce_mean;             /* 1: "mean" (default), 0: "add"/"sum" (gcpnet.py:984) */
+  int32_t enable_e3;               /* cfg.enable_e3_equivariance (edge path only) */
+  int32_t has_pos;                 /* updating_node_positions */
+  int32_t training;                /* 1: dropout active (GCPDropout, comp/__init__.py:97-135) */
+  float slope;                     /* leaky-relu slope */
+  float ln_eps, vn_eps;            /* nn.LayerNorm eps (1e-5), GCPLayerNorm vector eps (1e-8) */
+  float pos_weight;                /* cfg.node_positions_weight */
+  float p_drop;                    /* dropout probability */
+  uint64_t seed;                   /* dropout stream seed */
+  const int64_t* rng_counter;      /* device int64, advanced by the caller once per training forward */
+  gcpnet_gcp2 message[GCPNET_MAX_MESSAGE_LAYERS]; /* interaction.message_fusion.{k} */
+  gcpnet_gcp2 ff0, ff1;            /* feedforward_network.{0,1} */
+  gcpnet_gcp2 pos_update;          /* node_position_update_network.0 (if has_pos) */
+  const float *ln0_w, *ln0_b, *ln1_w, *ln1_b; /* gcp_norm.{0,1}.scalar_norm.{weight,bias} */
+  int32_t ln_grad_off[4];
+  int32_t n_edge_params, n_node_params;
+} gcpnet_layer;
+
+/* Destination- and source-sorted views of one graph batch, built by gcpnet_graph_build and shared
+ * by every layer that sees the same (edge_index, frames). */
+typedef struct gcpnet_graph {
+  int64_t num_nodes, num_edges;
+  const int32_t* perm;     /* [E] sorted position -> caller's edge id (stable sort by destination) */
+  const int32_t* src;      /* [E] source node of sorted position */
+  const int32_t* dst;      /* [E] destination node of sorted position (non-decreasing) */
+  const int32_t* dst_ptr;  /* [N+1] CSR pointer over `dst` */
+  const int32_t* src_pos;  /* [E] sorted positions grouped by source node (stable) */
+  const int32_t* src_ptr;  /* [N+1] CSR pointer over src_pos */
+  const float* fbar;       /* [N][9] mean frame over the edges leaving each node (0 if none) */
+} gcpnet_graph;
+
+/* Sizes the caller must allocate for one layer on one graph (all in floats unless noted). */
+typedef struct gcpnet_plan {
+  int32_t edge_tile, edge_grid_fwd, edge_grid_bwd, node_tile, node_grid_fwd, node_grid_bwd;
+  int32_t edge_smem_fwd_bytes, edge_smem_bwd_bytes, node_smem_fwd_bytes, node_smem_bwd_bytes;
+  int64_t msg_floats;            /* [E][s+3v] final messages */
+  int64_t saved_edge_floats;     /* activations kept for backward (0 in inference) */
+  int64_t saved_node_floats;
+  int64_t edge_partial_floats;   /* edge_grid_bwd * n_edge_params */
+  int64_t node_partial_floats;   /* node_grid_bwd * n_node_params */
+  int64_t edge_cotangent_floats; /* 2 * E * (s+3v): per-edge cotangents of the gathered node features */
+  int64_t agg_cotangent_floats;  /* N * (s+3v) */
+} gcpnet_plan;
+
+typedef struct gcpnet_forward_io {
+  const float *h, *chi, *e, *xi, *frames, *pos;  /* pos may be NULL when !has_pos */
+  float *out_h, *out_chi, *out_pos;
+  float* msg;          /* plan.msg_floats */
+  float* saved_edge;   /* plan.saved_edge_floats or NULL (inference) */
+  float* saved_node;   /* plan.saved_node_floats or NULL (inference) */
+} gcpnet_forward_io;
+
+typedef struct gcpnet_backward_io {
+  const float *h, *chi, *e, *xi, *frames;        /* the forward inputs */
+  const float *saved_edge, *saved_node;          /* written by gcpnet_layer_forward */
+  const float *g_out_h, *g_out_chi, *g_out_pos;  /* cotangents of the outputs (g_out_pos NULL when !has_pos) */
+  float *g_h, *g_chi, *g_e, *g_xi;               /* cotangents of the inputs */
+  float* g_params;                               /* [n_edge_params + n_node_params] flat parameter gradient (overwritten) */
+  float *ws_agg, *ws_edge, *ws_edge_partial, *ws_node_partial; /* workspaces sized by the plan */
+} gcpnet_backward_io;
+
+int gcpnet_version(void);
+const char* gcpnet_last_error(void);
+
+/* CSR build (replaces the index side of torch_scatter.scatter, gcpnet.py:946 and comp/__init__.py:316). */
+size_t gcpnet_graph_workspace_bytes(int64_t num_edges, int64_t num_nodes);
+int gcpnet_graph_build(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes, const float* frames,
+                       int32_t* perm, int32_t* src, int32_t* dst, int32_t* dst_ptr, int32_t* src_pos,
+                       int32_t* src_ptr, float* fbar, void* workspace, size_t workspace_bytes, void* stream);
+
+/* frames = localize(x, edge_index) without node mask (comp/__init__.py:220-269). */
+int gcpnet_localize(const float* pos, const int64_t* edge_index, int64_t num_edges, int norm_x_diff,
+                    float* frames, void* stream);
+
+/* GCPInteractions.forward / its backward (gcpnet.py:1160-1262). */
+int gcpnet_layer_plan(const gcpnet_layer* layer, int64_t num_nodes, int64_t num_edges, gcpnet_plan* plan);
+int gcpnet_layer_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, const gcpnet_plan* plan,
+                         const gcpnet_forward_io* io, void* stream);
+int gcpnet_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, const gcpnet_plan* plan,
+                          const gcpnet_backward_io* io, void* stream);
+
+/* GCPMessagePassing.forward alone (message + aggregate, gcpnet.py:949-960): out[N][s+3v]. */
+int gcpnet_message_passing_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, const gcpnet_plan* plan,
+                                   const gcpnet_forward_io* io, float* aggregate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCPNET_B200_H */

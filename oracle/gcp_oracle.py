@@ -202,10 +202,10 @@ def message_passing(p: Dict[str, Tensor], prefix: str, cfg: OracleConfig, h: Ten
         rs, rV = ms, mV
         for k in range(L):
             rs, rV = G(k, rs, rV)
-    flat = torch.cat((rs, rV.reshape(rV.shape[0], -1)), dim=-1)  # flatten (comp:61-63)
+    flat = torch.cat((rs, rV.reshape(rV.shape[0], 3 * rV.shape[1])), dim=-1)  # flatten (comp:61-63)
     agg = segment_reduce(flat, col, h.shape[0], reduce or cfg.reduce_function)  # (:946)
     so = rs.shape[1]
-    return agg[:, :so], agg[:, so:].reshape(agg.shape[0], -1, 3)  # recover (comp:65-69)
+    return agg[:, :so], agg[:, so:].reshape(agg.shape[0], (agg.shape[1] - so) // 3, 3)  # recover (comp:65-69)
 
 
 # --------------------------------------------------------------------------------------
