@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- edges/s of the fused GCP message+aggregate+node-update path, forward+backward.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one pass of the hot path over one synthetic batch: graph views (CSR sort + mean frames)
++ L x GCPInteractions forward + loss + L x backward.  Unit of work = one directed edge through one
+GCPInteractions layer (an "edge-layer"); a step processes L*E of them.
+
+One JSON line is printed by rank 0.  `value` = device-resident throughput (inputs in HBM, CUDA-event
+time, L2 flushed between steps); `e2e` = through the public module API with pinned-host inputs
+copied in and the loss read back every step; `roofline` = the dominant kernel (edge backward) timed
+live with CUDA events against its algorithmic bytes; `cpu_baseline` = the oracle port (plain torch
+on the host cores) on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# (graphs, nodes/graph, graph kind, k, layers, (s, v), (se, ve), positions)  -- BASELINE.json configs
+WORKLOADS = {
+    "cfg1": dict(desc="NMS-small 5-body, 500 graphs, 1 layer", graphs=500, n=5, kind="nms", layers=1,
+                 node_dims=(64, 16), edge_dims=(32, 4), pos=True),
+    "cfg2": dict(desc="NMS-small 5-body, batch 256 graphs, 4-layer GCPNet", graphs=256, n=5, kind="nms", layers=4,
+                 node_dims=(64, 16), edge_dims=(32, 4), pos=True),
+    "cfg3": dict(desc="LBA-like pockets, 32 graphs x 300 atoms, ~10 in-edges/atom, 6 layers", graphs=32, n=300,
+                 kind="knn", k=10, layers=6, node_dims=(100, 16), edge_dims=(32, 4), pos=False),
+    "cfg4": dict(desc="NMS 20-body, 128 graphs per GPU, 4 layers", graphs=128, n=20, kind="nms", layers=4,
+                 node_dims=(64, 16), edge_dims=(32, 4), pos=True),
+    "cfg5": dict(desc="CPD-like, 8 x 256 residues, kNN k=30, 6 encoder layers", graphs=8, n=256, kind="knn", k=30,
+                 layers=6, node_dims=(100, 16), edge_dims=(32, 4), pos=False),
+}
+
+
+def algorithmic_bytes_per_edge(s, v, se, ve, deg_in):
+    """compulsory HBM bytes per edge-layer with perfect on-chip reuse (fp32, int64 ids)."""
+    w = 4 * (s + 3 * v)
+    we = 4 * (se + 3 * ve)
+    fwd = 16 + 36 + we + 2 * w / deg_in
+    bwd = 16 + 36 + we + we + 3 * w / deg_in
+    return fwd, bwd
+
+
+def make_batch(w, seed, rank=0):
+    """Synthetic batch on the host (pinned): raw inputs of the layer stack."""
+    from oracle import gcp_oracle as O  # generators only (graph topology + N(0,1) features)
+    g = torch.Generator().manual_seed(1000 * seed + rank)
+    if w["kind"] == "nms":
+        ei = O.nms_edge_index(w["graphs"], w["n"])
+        N = w["graphs"] * w["n"]
+        pos = torch.randn(N, 3, generator=g) * (w["n"] / 5.0) ** (1.0 / 3.0)
+    else:
+        ei, pos = O.knn_like_edge_index(w["graphs"], w["n"], w["k"], seed=1000 * seed + rank)
+        N = w["graphs"] * w["n"]
+        pos = pos.float()
+    E = ei.shape[1]
+    s, v = w["node_dims"]
+    se, ve = w["edge_dims"]
+    b = dict(h=torch.randn(N, s, generator=g), chi=torch.randn(N, v, 3, generator=g), e=torch.randn(E, se, generator=g),
+             xi=torch.randn(E, ve, 3, generator=g), edge_index=ei.contiguous(), pos=pos.contiguous())
+    return {k: t.pin_memory() if torch.cuda.is_available() else t for k, t in b.items()}, N, E
+
+
+def oracle_cfg(w):
+    from oracle import gcp_oracle as O
+    return O.OracleConfig(node_dims=w["node_dims"], edge_dims=w["edge_dims"], updating_node_positions=w["pos"])
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md: clocks DURING the timed region)
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, val in zip(names, r[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_steps(w, steps, warmup, threads=None):
+    """Times `steps` full steps of workload `w` with the oracle (torch CPU, all host threads).
+    Returns (seconds per step, edge-layers per step, threads)."""
+    from oracle import gcp_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    cfg = oracle_cfg(w)
+    L = w["layers"]
+    params = [{k: t.requires_grad_(True) for k, t in O.random_layer_params(cfg, seed=10 + i).items()} for i in range(L)]
+    batch, N, E = make_batch(w, seed=0)
+    frames = O.localize(batch["pos"], batch["edge_index"])
+    p_drop = 0.1
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        h, chi = batch["h"].clone().requires_grad_(True), batch["chi"].clone().requires_grad_(True)
+        e, xi = batch["e"].clone().requires_grad_(True), batch["xi"].clone().requires_grad_(True)
+        pos = batch["pos"]
+        s, v = cfg.node_dims
+        for i in range(L):
+            masks = [((torch.rand(N, s) >= p_drop).float() / (1 - p_drop), (torch.rand(N, v) >= p_drop).float() / (1 - p_drop))
+                     for _ in range(2)]
+            out = O.interactions_forward(params[i], cfg, h, chi, e, xi, batch["edge_index"], frames,
+                                         node_pos=pos if w["pos"] else None, drop_masks=masks)
+            if w["pos"]:
+                (h, chi), pos = out
+            else:
+                h, chi = out
+        loss = h.sum() + chi.sum() + (pos.sum() if w["pos"] else 0.0)
+        loss.backward()
+        for p in params:
+            for t in p.values():
+                t.grad = None
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    times.sort()
+    return times[len(times) // 2], L * E, torch.get_num_threads()
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 20))
+    warm = max(1, min(args.warmup, 3))
+    sec, units, threads = cpu_steps(w, steps, warm)
+    val = units / sec
+    s, v = w["node_dims"]
+    print(json.dumps({
+        "impl": "reference", "metric": "edges/s (fused GCP msg+aggregate fwd+bwd)", "value": val, "unit": "edge-layers/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w['desc']}", "layers": w["layers"], "node_dims": [s, v],
+                   "edge_dims": list(w["edge_dims"]), "train_mode_dropout": 0.1},
+        "cpu_baseline": {"value": val, "unit": "edge-layers/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} full steps of the workload (median), oracle/gcp_oracle.py in torch CPU "
+                                   f"fp32 with {threads} threads; the Python reference cannot travel to the GPU box"},
+        "e2e": {"value": val, "unit": "edge-layers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def build_stack(w, device):
+    import gcpnet_b200
+    from tests.helpers import module_cfgs
+    cfg = oracle_cfg(w)
+    mcfg, lcfg = module_cfgs(cfg)
+    torch.manual_seed(0)
+    layers = torch.nn.ModuleList([
+        gcpnet_b200.GCPInteractions(cfg.node_dims, cfg.edge_dims, cfg=mcfg, layer_cfg=lcfg, dropout=0.1,
+                                    updating_node_positions=w["pos"]) for _ in range(w["layers"])]).to(device)
+    layers.train()
+    return layers
+
+
+def step_fn(layers, w, dev_batch):
+    """graph views + L x forward + loss + backward, everything on the current stream."""
+    import gcpnet_b200
+    b = dev_batch
+    frames = gcpnet_b200.localize(b["pos"], b["edge_index"])
+    h, chi, e, xi, pos = b["h"], b["chi"], b["e"], b["xi"], b["pos"]
+    for layer in layers:
+        if w["pos"]:
+            (h, chi), pos = layer((h, chi), (e, xi), b["edge_index"], frames, node_pos=pos)
+        else:
+            h, chi = layer((h, chi), (e, xi), b["edge_index"], frames)
+    loss = h.sum() + chi.sum() + (pos.sum() if w["pos"] else 0.0)
+    loss.backward()
+    return loss
+
+
+def run_ours(args, w):
+    import torch.distributed as dist
+    import gcpnet_b200
+    from gcpnet_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this path has no CPU implementation; use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    layers = build_stack(w, dev)
+    params = [p for p in layers.parameters()]
+    flat_grad_elems = sum(p.numel() for p in params)
+    host, N, E = make_batch(w, seed=1, rank=rank)
+    L = w["layers"]
+    units = L * E
+
+    def to_dev():
+        d = {k: t.to(dev, non_blocking=True) for k, t in host.items()}
+        for k in ("h", "chi", "e", "xi"):
+            d[k].requires_grad_(True)
+        return d
+
+    def allreduce_grads():
+        if world > 1:
+            # graph-sharded data parallelism: the only exchange is the parameter-gradient all-reduce
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+            flat.div_(world)
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    dbatch = to_dev()
+    torch.cuda.synchronize()
+
+    def one_step(batch):
+        for p in params:
+            p.grad = None
+        for k in ("h", "chi", "e", "xi"):
+            batch[k].grad = None
+        loss = step_fn(layers, w, batch)
+        allreduce_grads()
+        return loss
+
+    # ---- warm-up -------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        one_step(dbatch)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: L2 flushed before every step, CUDA events around each step ---
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    launches0 = lib.gcpnet_launch_count()
+    lib.gcpnet_profile_enable(1)  # per-kernel CUDA events on the launching stream, over this timed region
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        one_step(dbatch)
+        b.record()
+    barrier()
+    launches = lib.gcpnet_launch_count() - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    lib.gcpnet_profile_enable(0)
+    kernel_ms = {}
+    import ctypes as C
+    for which, name in enumerate(("edge_fwd", "node_fwd", "node_bwd", "edge_bwd", "cotangent_reduce", "partial_reduce",
+                                  "graph_build")):
+        tot, cnt = C.c_double(0), C.c_int64(0)
+        _lib.check(lib.gcpnet_profile_read(which, C.byref(tot), C.byref(cnt)), "gcpnet_profile_read")
+        kernel_ms[name] = (tot.value, cnt.value)
+
+    # ---- end to end: pinned host inputs -> device, step, loss -> host, every step ---------------
+    barrier()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    losses = []
+    for a, b in ev2:
+        flush.zero_()
+        a.record()
+        batch = to_dev()
+        loss = one_step(batch)
+        losses.append(float(loss))  # device -> host read of the step's result (synchronises)
+        b.record()
+    barrier()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    h2d = sum(t.numel() * t.element_size() for t in host.values())
+    if rank == 0:
+        s, v = w["node_dims"]
+        se, ve = w["edge_dims"]
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            sec, cu, threads = cpu_steps(w, steps=5, warmup=1)
+            cpu = {"value": cu / sec, "unit": "edge-layers/s", "cores": threads, "kind": "port",
+                   "sample": f"5 full steps (median) of the same workload ({L} layers, N={N}, E={E}) through "
+                             "oracle/gcp_oracle.py, torch CPU fp32"}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        deg_in = E / max(N, 1)
+        bf, bb = algorithmic_bytes_per_edge(s, v, se, ve, deg_in)
+        dom = max(("edge_fwd", "edge_bwd"), key=lambda k: kernel_ms[k][0])
+        tot_ms, cnt = kernel_ms[dom]
+        us = tot_ms * 1e3 / max(cnt, 1)
+        alg = (bb if dom == "edge_bwd" else bf) * E
+        gbs = alg / (us * 1e-6) / 1e9 if us > 0 else 0.0
+        roof_out = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                    "frac": gbs / peak, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured, burst copy)" if peaks else "of fallback 6.65 TB/s",
+                    "algorithmic_bytes_per_launch": alg, "us_per_launch": us, "launches_timed": cnt,
+                    "kernel_share_of_step": tot_ms / dev_ms,
+                    "kernel_ms_per_step": {k: t / args.steps for k, (t, _) in kernel_ms.items()},
+                    "note": "fused path is compute-bound (~350 FLOP/B, SURVEY 8d): HBM fraction reported as the "
+                            "contract asks; see DESIGN.md for the FLOP-side roofline"}
+        print(json.dumps({
+            "metric": "edges/s (fused GCP msg+aggregate fwd+bwd)", "value": world * units * args.steps / (dev_ms * 1e-3),
+            "unit": "edge-layers/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {w['desc']}", "layers": L, "nodes_per_gpu": N, "edges_per_gpu": E,
+                       "node_dims": [s, v], "edge_dims": [se, ve], "train_mode_dropout": 0.1,
+                       "l2": "flushed (256 MiB write) before every timed step", "timing": "CUDA events per step, summed",
+                       "parallelism": f"graph-sharded dp{world}, NCCL all-reduce of the {flat_grad_elems * 4} B gradient"},
+            "per_layer_edges_per_s": world * E * L * args.steps / (dev_ms * 1e-3) / 1.0,
+            "e2e": {"value": world * units * args.steps / (e2e_ms * 1e-3), "unit": "edge-layers/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roof_out, "cpu_baseline": cpu, "clocks": clocks, "loss": losses[-1],
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -73,7 +73,7 @@ class BackwardIO(C.Structure):
 
 
 EXPORTS = (
-    "gcpnet_version", "gcpnet_last_error", "gcpnet_graph_workspace_bytes", "gcpnet_graph_build",
+    "gcpnet_version", "gcpnet_last_error", "gcpnet_launch_count", "gcpnet_profile_enable", "gcpnet_profile_read", "gcpnet_graph_workspace_bytes", "gcpnet_graph_build",
     "gcpnet_localize", "gcpnet_layer_plan", "gcpnet_layer_forward", "gcpnet_layer_backward",
     "gcpnet_message_passing_forward",
 )
@@ -85,6 +85,12 @@ def declare(lib: C.CDLL) -> None:
     lib.gcpnet_version.argtypes = []
     lib.gcpnet_last_error.restype = C.c_char_p
     lib.gcpnet_last_error.argtypes = []
+    lib.gcpnet_launch_count.restype = C.c_uint64
+    lib.gcpnet_launch_count.argtypes = []
+    lib.gcpnet_profile_enable.restype = None
+    lib.gcpnet_profile_enable.argtypes = [C.c_int]
+    lib.gcpnet_profile_read.restype = C.c_int
+    lib.gcpnet_profile_read.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.gcpnet_graph_workspace_bytes.restype = C.c_size_t
     lib.gcpnet_graph_workspace_bytes.argtypes = [C.c_int64, C.c_int64]
     lib.gcpnet_graph_build.restype = C.c_int

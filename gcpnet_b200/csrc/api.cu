@@ -4,21 +4,36 @@
 // synchronisation, so the whole layer forward+backward can be captured into a CUDA graph.
 #include <cuda_runtime.h>
 
-#include <cub/device/device_radix_sort.cuh>
+#include <atomic>
 #include <cstdio>
+#include <map>
+#include <mutex>
+#include <vector>
 #include <string>
 
 #include "layer_setup.h"
 
 using namespace gcp;
 
+#include "common.h"
+
 static thread_local std::string g_last_error;
-static int fail(const std::string& msg) { g_last_error = msg; return 1; }
-#define CUDA_TRY(expr)                                                                         \
-  do {                                                                                         \
-    cudaError_t err__ = (expr);                                                                \
-    if (err__ != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(err__)); \
-  } while (0)
+int gcp_fail(const std::string& msg) { g_last_error = msg; return 1; }
+static std::atomic<unsigned long long> g_launches{0};
+void gcp_note_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+static std::atomic<bool> g_profile{false};
+static std::mutex g_profile_mu;
+static std::vector<cudaEvent_t> g_profile_ev[T_COUNT];  // begin, end, begin, end, ...
+bool gcp_profile_on() { return g_profile.load(std::memory_order_relaxed); }
+void gcp_profile_mark(int which, bool begin, cudaStream_t st) {
+  (void)begin;
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, st);
+  std::lock_guard<std::mutex> lock(g_profile_mu);
+  g_profile_ev[which].push_back(ev);
+}
 
 // ------------------------------------------------------------------------------------------
 // kernels
@@ -96,113 +111,76 @@ __global__ void partial_reduce_kernel(float* __restrict__ out, const float* __re
   out[idx] = acc;
 }
 
-// ---- graph build -------------------------------------------------------------------------------
-__global__ void edge_keys_kernel(const int64_t* __restrict__ edge_index, int E, int* __restrict__ row32,
-                                 int* __restrict__ col32, int* __restrict__ iota) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  row32[e] = (int)edge_index[e];
-  col32[e] = (int)edge_index[(size_t)E + e];
-  iota[e] = e;
-}
-__global__ void gather_src_kernel(const int* __restrict__ row32, const int* __restrict__ perm, int E,
-                                  int* __restrict__ src, int* __restrict__ iota) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= E) return;
-  src[p] = row32[perm[p]];
-  iota[p] = p;
-}
-// ptr[i] = first position whose key >= i  (keys sorted ascending), i in [0, N]
-__global__ void segment_ptr_kernel(const int* __restrict__ keys, int E, int N, int* __restrict__ ptr) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > N) return;
-  int lo = 0, hi = E;
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < i) lo = mid + 1; else hi = mid; }
-  ptr[i] = lo;
-}
-// fbar[i] = mean of frames over the edges leaving node i (comp/__init__.py:316-323), 0 if none
-__global__ void mean_frame_kernel(const float* __restrict__ frames, const int* __restrict__ perm,
-                                  const int* __restrict__ src_pos, const int* __restrict__ src_ptr, int N,
-                                  float* __restrict__ fbar) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= N * 9) return;
-  const int i = idx / 9, c = idx - 9 * i;
-  const int a = src_ptr[i], b = src_ptr[i + 1];
-  float acc = 0.f;
-  for (int q = a; q < b; ++q) acc += __ldg(frames + (size_t)perm[src_pos[q]] * 9 + c);
-  fbar[idx] = b > a ? acc / (float)(b - a) : 0.f;
-}
-
-// frames = [x_diff; x_cross; x_vertical] (comp/__init__.py:220-269, no node mask)
-__global__ void localize_kernel(const float* __restrict__ pos, const int64_t* __restrict__ edge_index, int E,
-                                int norm_x_diff, float* __restrict__ frames) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  const int64_t r = edge_index[e], c = edge_index[(size_t)E + e];
-  const float ax = pos[3 * r], ay = pos[3 * r + 1], az = pos[3 * r + 2];
-  const float bx = pos[3 * c], by = pos[3 * c + 1], bz = pos[3 * c + 2];
-  float dx = ax - bx, dy = ay - by, dz = az - bz;
-  float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
-  if (norm_x_diff) {
-    const float dn = sqrtf(dx * dx + dy * dy + dz * dz) + 1.f;
-    dx /= dn; dy /= dn; dz /= dn;
-    const float cn = sqrtf(cx * cx + cy * cy + cz * cz) + 1.f;
-    cx /= cn; cy /= cn; cz /= cn;
-  }
-  float* f = frames + (size_t)e * 9;
-  f[0] = dx; f[1] = dy; f[2] = dz; f[3] = cx; f[4] = cy; f[5] = cz;
-  f[6] = dy * cz - dz * cy; f[7] = dz * cx - dx * cz; f[8] = dx * cy - dy * cx;
-}
-
 // ------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------
+// opt in to > 48 KB of dynamic shared memory once per (kernel, device, size) -- not on every launch
 template <class K>
 static int set_smem(K kernel, int bytes) {
-  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> done;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  int& cur = done[{(const void*)kernel, dev}];
+  if (bytes > cur) {
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    cur = bytes;
+  }
   return 0;
 }
 
 static int launch_edge_fwd(const EdgeParams& p, int TE, int grid, cudaStream_t st) {
   const int bytes = p.sm.total * 4;
+  GcpTimedScope timed(T_EDGE_FWD, st);
   if (TE == 64) {
     if (set_smem(edge_fwd_kernel<64, EDGE_NT>, bytes)) return 1;
     edge_fwd_kernel<64, EDGE_NT><<<grid, EDGE_NT, bytes, st>>>(p);
+    gcp_note_launches(1);
   } else {
     if (set_smem(edge_fwd_kernel<32, EDGE_NT>, bytes)) return 1;
     edge_fwd_kernel<32, EDGE_NT><<<grid, EDGE_NT, bytes, st>>>(p);
+    gcp_note_launches(1);
   }
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 static int launch_edge_bwd(const EdgeParams& p, int TE, int grid, cudaStream_t st) {
   const int bytes = p.sm.total * 4;
+  GcpTimedScope timed(T_EDGE_BWD, st);
   if (TE != 32) return fail("edge backward tile must be 32");
   if (set_smem(edge_bwd_kernel<32, EDGE_NT>, bytes)) return 1;
   edge_bwd_kernel<32, EDGE_NT><<<grid, EDGE_NT, bytes, st>>>(p);
+  gcp_note_launches(1);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 static int launch_node_fwd(const NodeParams& p, int TE, int grid, cudaStream_t st) {
   const int bytes = p.sm.total * 4;
+  GcpTimedScope timed(T_NODE_FWD, st);
   if (TE == 32) {
     if (set_smem(node_fwd_kernel<32, NODE_NT>, bytes)) return 1;
     node_fwd_kernel<32, NODE_NT><<<grid, NODE_NT, bytes, st>>>(p);
+    gcp_note_launches(1);
   } else {
     if (set_smem(node_fwd_kernel<16, NODE_NT>, bytes)) return 1;
     node_fwd_kernel<16, NODE_NT><<<grid, NODE_NT, bytes, st>>>(p);
+    gcp_note_launches(1);
   }
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 static int launch_node_bwd(const NodeParams& p, int TE, int grid, cudaStream_t st) {
   const int bytes = p.sm.total * 4;
+  GcpTimedScope timed(T_NODE_BWD, st);
   if (TE == 32) {
     if (set_smem(node_bwd_kernel<32, NODE_NT>, bytes)) return 1;
     node_bwd_kernel<32, NODE_NT><<<grid, NODE_NT, bytes, st>>>(p);
+    gcp_note_launches(1);
   } else {
     if (set_smem(node_bwd_kernel<16, NODE_NT>, bytes)) return 1;
     node_bwd_kernel<16, NODE_NT><<<grid, NODE_NT, bytes, st>>>(p);
+    gcp_note_launches(1);
   }
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -215,57 +193,24 @@ extern "C" {
 
 int gcpnet_version(void) { return 100; }
 const char* gcpnet_last_error(void) { return g_last_error.c_str(); }
-
-static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
-
-size_t gcpnet_graph_workspace_bytes(int64_t E, int64_t N) {
-  (void)N;
-  size_t cub_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const int*)nullptr, (int*)nullptr, (const int*)nullptr,
-                                  (int*)nullptr, (int)E, 0, 32, (cudaStream_t)0);
-  // row32, col32, iota, sorted-src keys + cub temp
-  return 4 * align256((size_t)(E > 0 ? E : 1) * sizeof(int)) + align256(cub_bytes) + 256;
-}
-
-int gcpnet_graph_build(const int64_t* edge_index, int64_t E64, int64_t N64, const float* frames, int32_t* perm,
-                       int32_t* src, int32_t* dst, int32_t* dst_ptr, int32_t* src_pos, int32_t* src_ptr, float* fbar,
-                       void* workspace, size_t workspace_bytes, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  if (E64 < 0 || N64 <= 0 || E64 >= (1LL << 31) || N64 >= (1LL << 31)) return fail("graph_build: sizes out of range");
-  const int E = (int)E64, N = (int)N64;
-  if (workspace_bytes < gcpnet_graph_workspace_bytes(E64, N64)) return fail("graph_build: workspace too small");
-  const int T = 256;
-  if (E == 0) {
-    CUDA_TRY(cudaMemsetAsync(dst_ptr, 0, (size_t)(N + 1) * sizeof(int), st));
-    CUDA_TRY(cudaMemsetAsync(src_ptr, 0, (size_t)(N + 1) * sizeof(int), st));
-    CUDA_TRY(cudaMemsetAsync(fbar, 0, (size_t)N * 9 * sizeof(float), st));
-    return 0;
+void gcpnet_profile_enable(int on) { g_profile.store(on != 0); }
+int gcpnet_profile_read(int which, double* total_ms, int64_t* launches) {
+  if (which < 0 || which >= T_COUNT || !total_ms || !launches) return fail("profile_read: bad argument");
+  std::lock_guard<std::mutex> lock(g_profile_mu);
+  std::vector<cudaEvent_t>& v = g_profile_ev[which];
+  double tot = 0.0; int64_t n = 0;
+  for (size_t i = 0; i + 1 < v.size(); i += 2) {
+    CUDA_TRY(cudaEventSynchronize(v[i + 1]));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, v[i], v[i + 1]));
+    tot += ms; ++n;
   }
-  char* ws = (char*)workspace;
-  const size_t seg = align256((size_t)E * sizeof(int));
-  int* row32 = (int*)ws; int* col32 = (int*)(ws + seg); int* iota = (int*)(ws + 2 * seg); int* srckeys = (int*)(ws + 3 * seg);
-  void* cub_tmp = ws + 4 * seg;
-  size_t cub_bytes = workspace_bytes - 4 * seg;
-  int bits = 1;
-  while ((1LL << bits) < N64) ++bits;
-  edge_keys_kernel<<<(E + T - 1) / T, T, 0, st>>>(edge_index, E, row32, col32, iota);
-  // stable sort by destination: positions keep the caller's relative order inside a segment
-  CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, col32, dst, iota, perm, E, 0, bits, st));
-  gather_src_kernel<<<(E + T - 1) / T, T, 0, st>>>(row32, perm, E, src, iota);
-  segment_ptr_kernel<<<(N + 1 + T - 1) / T, T, 0, st>>>(dst, E, N, dst_ptr);
-  CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, src, srckeys, iota, src_pos, E, 0, bits, st));
-  segment_ptr_kernel<<<(N + 1 + T - 1) / T, T, 0, st>>>(srckeys, E, N, src_ptr);
-  mean_frame_kernel<<<(N * 9 + T - 1) / T, T, 0, st>>>(frames, perm, src_pos, src_ptr, N, fbar);
-  CUDA_TRY(cudaGetLastError());
+  for (cudaEvent_t e : v) cudaEventDestroy(e);
+  v.clear();
+  *total_ms = tot; *launches = n;
   return 0;
 }
-
-int gcpnet_localize(const float* pos, const int64_t* edge_index, int64_t E, int norm_x_diff, float* frames, void* stream) {
-  if (E <= 0) return 0;
-  localize_kernel<<<(int)((E + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pos, edge_index, (int)E, norm_x_diff, frames);
-  CUDA_TRY(cudaGetLastError());
-  return 0;
-}
+uint64_t gcpnet_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int gcpnet_layer_plan(const gcpnet_layer* layer, int64_t N, int64_t E, gcpnet_plan* plan) {
   if (!layer || !plan) return fail("layer_plan: null argument");
@@ -320,6 +265,7 @@ int gcpnet_message_passing_forward(const gcpnet_layer* layer, const gcpnet_graph
   const long long tot = graph->num_nodes * W;
   aggregate_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(io->msg, graph->dst_ptr, (int)graph->num_nodes, W,
                                                             layer->reduce_mean, aggregate);
+  gcp_note_launches(1);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -362,12 +308,16 @@ int gcpnet_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, 
     edge_grid = plan->edge_grid_bwd;
     if (launch_edge_bwd(ep, TE, edge_grid, st)) return 1;
     const long long tot = g.num_nodes * W;
+    GcpTimedScope timed(T_COT_REDUCE, st);
     node_cotangent_reduce_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(
         io->g_h, io->g_chi, ep.grow, ep.gcol, g.dst_ptr, g.src_ptr, g.src_pos, (int)g.num_nodes, l.s, 3 * l.v);
+    gcp_note_launches(1);
   }
   const int np_tot = l.n_edge_params + l.n_node_params;
+  GcpTimedScope timed(T_PARTIAL_REDUCE, st);
   partial_reduce_kernel<<<(np_tot + 255) / 256, 256, 0, st>>>(io->g_params, io->ws_edge_partial, l.n_edge_params, edge_grid,
                                                            io->ws_node_partial, l.n_node_params, plan->node_grid_bwd);
+  gcp_note_launches(1);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,132 @@
+// graph.cu -- per-batch graph preprocessing: destination/source CSR orders, mean frames, localize.
+// Replaces the index side of torch_scatter.scatter (gcpnet.py:946; comp/__init__.py:316) and
+// comp/__init__.py:220-269 (localize).  Entry points declared in include/gcpnet_b200.h.
+#include <cuda_runtime.h>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <string>
+
+#include "../../include/gcpnet_b200.h"
+#include "common.h"
+
+// ---- graph build -------------------------------------------------------------------------------
+__global__ void edge_keys_kernel(const int64_t* __restrict__ edge_index, int E, int* __restrict__ row32,
+                                 int* __restrict__ col32, int* __restrict__ iota) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  row32[e] = (int)edge_index[e];
+  col32[e] = (int)edge_index[(size_t)E + e];
+  iota[e] = e;
+}
+__global__ void gather_src_kernel(const int* __restrict__ row32, const int* __restrict__ perm, int E,
+                                  int* __restrict__ src, int* __restrict__ iota) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= E) return;
+  src[p] = row32[perm[p]];
+  iota[p] = p;
+}
+// ptr[i] = first position whose key >= i  (keys sorted ascending), i in [0, N]
+__global__ void segment_ptr_kernel(const int* __restrict__ keys, int E, int N, int* __restrict__ ptr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > N) return;
+  int lo = 0, hi = E;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < i) lo = mid + 1; else hi = mid; }
+  ptr[i] = lo;
+}
+// fbar[i] = mean of frames over the edges leaving node i (comp/__init__.py:316-323), 0 if none
+__global__ void mean_frame_kernel(const float* __restrict__ frames, const int* __restrict__ perm,
+                                  const int* __restrict__ src_pos, const int* __restrict__ src_ptr, int N,
+                                  float* __restrict__ fbar) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * 9) return;
+  const int i = idx / 9, c = idx - 9 * i;
+  const int a = src_ptr[i], b = src_ptr[i + 1];
+  float acc = 0.f;
+  for (int q = a; q < b; ++q) acc += __ldg(frames + (size_t)perm[src_pos[q]] * 9 + c);
+  fbar[idx] = b > a ? acc / (float)(b - a) : 0.f;
+}
+
+// frames = [x_diff; x_cross; x_vertical] (comp/__init__.py:220-269, no node mask)
+__global__ void localize_kernel(const float* __restrict__ pos, const int64_t* __restrict__ edge_index, int E,
+                                int norm_x_diff, float* __restrict__ frames) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int64_t r = edge_index[e], c = edge_index[(size_t)E + e];
+  const float ax = pos[3 * r], ay = pos[3 * r + 1], az = pos[3 * r + 2];
+  const float bx = pos[3 * c], by = pos[3 * c + 1], bz = pos[3 * c + 2];
+  float dx = ax - bx, dy = ay - by, dz = az - bz;
+  float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+  if (norm_x_diff) {
+    const float dn = sqrtf(dx * dx + dy * dy + dz * dz) + 1.f;
+    dx /= dn; dy /= dn; dz /= dn;
+    const float cn = sqrtf(cx * cx + cy * cy + cz * cz) + 1.f;
+    cx /= cn; cy /= cn; cz /= cn;
+  }
+  float* f = frames + (size_t)e * 9;
+  f[0] = dx; f[1] = dy; f[2] = dz; f[3] = cx; f[4] = cy; f[5] = cz;
+  f[6] = dy * cz - dz * cy; f[7] = dz * cx - dx * cz; f[8] = dx * cy - dy * cx;
+}
+
+extern "C" {
+
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+size_t gcpnet_graph_workspace_bytes(int64_t E, int64_t N) {
+  (void)N;
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const int*)nullptr, (int*)nullptr, (const int*)nullptr,
+                                  (int*)nullptr, (int)E, 0, 32, (cudaStream_t)0);
+  // row32, col32, iota, sorted-src keys + cub temp
+  return 4 * align256((size_t)(E > 0 ? E : 1) * sizeof(int)) + align256(cub_bytes) + 256;
+}
+
+int gcpnet_graph_build(const int64_t* edge_index, int64_t E64, int64_t N64, const float* frames, int32_t* perm,
+                       int32_t* src, int32_t* dst, int32_t* dst_ptr, int32_t* src_pos, int32_t* src_ptr, float* fbar,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (E64 < 0 || N64 <= 0 || E64 >= (1LL << 31) || N64 >= (1LL << 31)) return fail("graph_build: sizes out of range");
+  const int E = (int)E64, N = (int)N64;
+  if (workspace_bytes < gcpnet_graph_workspace_bytes(E64, N64)) return fail("graph_build: workspace too small");
+  const int T = 256;
+  if (E == 0) {
+    CUDA_TRY(cudaMemsetAsync(dst_ptr, 0, (size_t)(N + 1) * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(src_ptr, 0, (size_t)(N + 1) * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(fbar, 0, (size_t)N * 9 * sizeof(float), st));
+    return 0;
+  }
+  GcpTimedScope timed(T_GRAPH_BUILD, st);
+  char* ws = (char*)workspace;
+  const size_t seg = align256((size_t)E * sizeof(int));
+  int* row32 = (int*)ws; int* col32 = (int*)(ws + seg); int* iota = (int*)(ws + 2 * seg); int* srckeys = (int*)(ws + 3 * seg);
+  void* cub_tmp = ws + 4 * seg;
+  size_t cub_bytes = workspace_bytes - 4 * seg;
+  int bits = 1;
+  while ((1LL << bits) < N64) ++bits;
+  edge_keys_kernel<<<(E + T - 1) / T, T, 0, st>>>(edge_index, E, row32, col32, iota);
+  gcp_note_launches(1);
+  // stable sort by destination: positions keep the caller's relative order inside a segment
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, col32, dst, iota, perm, E, 0, bits, st));
+  gcp_note_launches(1);  // cub launches >= 1 kernel per sort; counted as one
+  gather_src_kernel<<<(E + T - 1) / T, T, 0, st>>>(row32, perm, E, src, iota);
+  gcp_note_launches(1);
+  segment_ptr_kernel<<<(N + 1 + T - 1) / T, T, 0, st>>>(dst, E, N, dst_ptr);
+  gcp_note_launches(1);
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, src, srckeys, iota, src_pos, E, 0, bits, st));
+  gcp_note_launches(1);
+  segment_ptr_kernel<<<(N + 1 + T - 1) / T, T, 0, st>>>(srckeys, E, N, src_ptr);
+  gcp_note_launches(1);
+  mean_frame_kernel<<<(N * 9 + T - 1) / T, T, 0, st>>>(frames, perm, src_pos, src_ptr, N, fbar);
+  gcp_note_launches(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int gcpnet_localize(const float* pos, const int64_t* edge_index, int64_t E, int norm_x_diff, float* frames, void* stream) {
+  if (E <= 0) return 0;
+  localize_kernel<<<(int)((E + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pos, edge_index, (int)E, norm_x_diff, frames);
+  gcp_note_launches(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -119,6 +119,14 @@ typedef struct gcpnet_backward_io {
 
 int gcpnet_version(void);
 const char* gcpnet_last_error(void);
+/* number of kernels this library has enqueued so far in this process (bench.py: gpu_launches) */
+uint64_t gcpnet_launch_count(void);
+/* Optional per-kernel timing with CUDA events on the launching stream (bench.py roofline leg).
+ * which: 0 edge forward, 1 node forward, 2 node backward, 3 edge backward, 4 cotangent reduce,
+ * 5 partial reduce, 6 graph build.  read() waits for the recorded events, returns their summed
+ * elapsed time and count, and clears them.  Keep disabled during CUDA-graph capture. */
+void gcpnet_profile_enable(int on);
+int gcpnet_profile_read(int which, double* total_ms, int64_t* launches);
 
 /* CSR build (replaces the index side of torch_scatter.scatter, gcpnet.py:946 and comp/__init__.py:316). */
 size_t gcpnet_graph_workspace_bytes(int64_t num_edges, int64_t num_nodes);

@@ -68,3 +68,81 @@ def oracle_forward_backward(case, cfg, params, inputs, dtype=torch.float32):
     for k, t in p.items():
         res["pgrad/" + k] = t.grad if t.grad is not None else torch.zeros_like(t)
     return res
+
+
+# ------------------------------------------------------------------------------------------
+# product-side helpers (used by the -m gpu tests, bench.py and smoke())
+# ------------------------------------------------------------------------------------------
+class AttrDict(dict):
+    """Minimal stand-in for an omegaconf.DictConfig (attribute access + copy)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as exc:
+            raise AttributeError(k) from exc
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+    def __copy__(self):
+        return AttrDict(self)
+
+
+def module_cfgs(cfg):
+    """(cfg, layer_cfg) in the shape of configs/model/module_cfg/gcp_module_nms.yaml and
+    layer_cfg/gcp_interaction_layer_nms.yaml, from an OracleConfig."""
+    mcfg = AttrDict(
+        norm_x_diff=True, scalar_gate=0, vector_gate=cfg.vector_gate, vector_residual=cfg.vector_residual,
+        vector_frame_residual=False, frame_gate=False, sigma_frame_gate=False,
+        scalar_nonlinearity=cfg.scalar_nonlinearity, vector_nonlinearity=cfg.vector_nonlinearity,
+        nonlinearities=[cfg.scalar_nonlinearity, cfg.vector_nonlinearity], bottleneck=cfg.bottleneck,
+        vector_linear=True, vector_identity=True, default_vector_residual=cfg.default_vector_residual,
+        default_bottleneck=cfg.default_bottleneck, node_positions_weight=cfg.node_positions_weight,
+        ablate_frame_updates=False, ablate_scalars=False, ablate_vectors=False, ablate_x_force_update=True,
+        enable_e3_equivariance=cfg.enable_e3_equivariance)
+    mp = AttrDict(edge_encoder=False, edge_gate=False, num_message_layers=cfg.num_message_layers, message_residual=0,
+                  message_ff_multiplier=1, self_message=True, use_residual_message_gcp=cfg.use_residual_message_gcp)
+    lcfg = AttrDict(pre_norm=cfg.pre_norm, num_feedforward_layers=cfg.num_feedforward_layers, dropout=0.1,
+                    nonlinearity_slope=cfg.nonlinearity_slope, mp_cfg=mp)
+    return mcfg, lcfg
+
+
+def build_module(cfg, params=None, dropout=0.0, device="cuda"):
+    """gcpnet_b200.GCPInteractions for an OracleConfig, optionally loaded with reference-named weights."""
+    import gcpnet_b200
+
+    mcfg, lcfg = module_cfgs(cfg)
+    layer = gcpnet_b200.GCPInteractions(cfg.node_dims, cfg.edge_dims, cfg=mcfg, layer_cfg=lcfg, dropout=dropout,
+                                        updating_node_positions=cfg.updating_node_positions)
+    if params is not None:
+        layer.load_state_dict({k: v.detach().clone().float() for k, v in params.items()}, strict=True)
+    return layer.to(device)
+
+
+def module_forward_backward(layer, case, cfg, inputs, device="cuda"):
+    """Mirror of oracle_forward_backward through the product module."""
+    dev = torch.device(device)
+    leaves = {k: inputs[k].to(dev, torch.float32).clone().requires_grad_(True) for k in ("h", "chi", "e", "xi")}
+    ei = inputs["edge_index"].to(dev)
+    frames = inputs["frames"].to(dev, torch.float32)
+    n = inputs["h"].shape[0]
+    ch, cchi, cpos = (t.to(dev) for t in GC.loss_weights(case, cfg, n))
+    if cfg.updating_node_positions:
+        (oh, ochi), opos = layer((leaves["h"], leaves["chi"]), (leaves["e"], leaves["xi"]), ei, frames,
+                                 node_pos=inputs["node_pos"].to(dev, torch.float32))
+        loss = (oh * ch).sum() + (ochi * cchi).sum() + (opos * cpos).sum()
+    else:
+        oh, ochi = layer((leaves["h"], leaves["chi"]), (leaves["e"], leaves["xi"]), ei, frames)
+        opos = None
+        loss = (oh * ch).sum() + (ochi * cchi).sum()
+    layer.zero_grad(set_to_none=True)
+    loss.backward()
+    res = {"out_h": oh.detach().cpu(), "out_chi": ochi.detach().cpu()}
+    if opos is not None:
+        res["out_pos"] = opos.detach().cpu()
+    for k, t in leaves.items():
+        res["grad_" + k] = t.grad.cpu()
+    for k, p in layer.named_parameters():
+        res["pgrad/" + k] = p.grad.cpu() if p.grad is not None else torch.zeros_like(p).cpu()
+    return res

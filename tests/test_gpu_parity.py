@@ -1,0 +1,239 @@
+"""Parity of the sm_100a path (through gcpnet_b200.GCPInteractions -> C ABI -> CUDA kernels) with
+the oracle and with the committed outputs of the unmodified reference (tests/golden/*.npz).
+
+Tolerance: 1e-4 relative to the tensor's max magnitude, fp32 (BASELINE.json north_star: "within
+1e-4 rel fp32").  Needs a GPU: run with -m gpu on the B200 box.  Nothing here reads /root/reference.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gcp_oracle as O
+from oracle import golden_cases as GC
+from tests.helpers import (build_module, load_case, module_forward_backward, oracle_forward_backward, rel_err,
+                           sample_like_fixture)
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _compare(res, want, names, tol=TOL):
+    for key in ("out_h", "out_chi", "out_pos", "grad_h", "grad_chi", "grad_e", "grad_xi"):
+        if key in want:
+            assert rel_err(res[key].numpy(), want[key].numpy()) < tol, key
+    for k in names:
+        assert rel_err(res["pgrad/" + k].numpy(), want["pgrad/" + k].numpy()) < tol, k
+
+
+@pytest.mark.parametrize("name", list(GC.CASES))
+def test_layer_matches_oracle_and_reference_fixture(name):
+    case, cfg, params, inputs, fx = load_case(name)
+    want = oracle_forward_backward(case, cfg, params, inputs)
+    layer = build_module(cfg, params).eval()
+    res = module_forward_backward(layer, case, cfg, inputs)
+    _compare(res, want, [k for k, _ in layer.named_parameters()])
+    # and against what the unmodified reference produced in the build container
+    for key in ("out_h", "out_chi", "out_pos", "grad_h", "grad_chi", "grad_e", "grad_xi"):
+        if key in fx.files:
+            assert rel_err(res[key].numpy(), fx[key]) < TOL, key
+    for key in fx.files:
+        if key.startswith("pgrad/"):
+            assert rel_err(sample_like_fixture(res[key]), fx[key]) < TOL, key
+
+
+def _random_case(cfg, n, E, seed, graph="random", k=0):
+    g = torch.Generator().manual_seed(seed)
+    pos = None
+    if graph == "random":
+        ei = torch.randint(0, n, (2, E), generator=g)
+    elif graph == "nms":
+        ei = O.nms_edge_index(n // k, k)
+        n = (n // k) * k
+    else:
+        ei, pos = O.knn_like_edge_index(n // 64, 64, k, seed=seed)
+        n = (n // 64) * 64
+    inputs = O.synthetic_layer_inputs(cfg, ei, n, seed=seed + 1, positions=pos)
+    return dict(seed=seed + 2), inputs
+
+
+@pytest.mark.parametrize("label,cfg,shape", [
+    # BASELINE.json configs[0]: NMS-small 5-body, 500 graphs -> N=2500, E=10000
+    ("cfg1_nms5", O.OracleConfig(node_dims=(64, 16), edge_dims=(32, 4), updating_node_positions=True),
+     dict(n=2500, E=0, graph="nms", k=5)),
+    # configs[3] shard shape scaled down: 20-body graphs (in-degree 19)
+    ("cfg4_nms20", O.OracleConfig(node_dims=(64, 16), edge_dims=(32, 4), updating_node_positions=True),
+     dict(n=640, E=0, graph="nms", k=20)),
+    # configs[2]/[4]-like: (100,16) hidden dims, kNN graph, k=30
+    ("cfg5_knn30", O.OracleConfig(node_dims=(100, 16), edge_dims=(32, 4)), dict(n=512, E=0, graph="knn", k=30)),
+    # tests/test_gcpnet_equivariance.py:59-75 shapes: 300 nodes, 10 000 random edges (self loops, duplicates)
+    ("equiv_shapes", O.OracleConfig(node_dims=(100, 16), edge_dims=(32, 4)), dict(n=300, E=10000, graph="random")),
+])
+def test_layer_matches_oracle_at_baseline_shapes(label, cfg, shape):
+    case, inputs = _random_case(cfg, seed=101, **shape)
+    params = O.random_layer_params(cfg, seed=100)
+    want = oracle_forward_backward(case, cfg, params, inputs)
+    layer = build_module(cfg, params).eval()
+    res = module_forward_backward(layer, case, cfg, inputs)
+    _compare(res, want, [k for k, _ in layer.named_parameters()])
+
+
+def test_reruns_are_bit_identical():
+    """Deterministic by construction (CSR segment reduce, per-CTA partials, no atomics)."""
+    cfg = O.OracleConfig(node_dims=(64, 16), edge_dims=(32, 4), updating_node_positions=True)
+    case, inputs = _random_case(cfg, n=400, E=3000, seed=7)
+    params = O.random_layer_params(cfg, seed=8)
+    layer = build_module(cfg, params).eval()
+    a = module_forward_backward(layer, case, cfg, inputs)
+    b = module_forward_backward(layer, case, cfg, inputs)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_edge_order_invariance():
+    """Permuting the edge list (with its features) must not change node outputs beyond fp32
+    re-association inside a destination segment; edge gradients permute along."""
+    cfg = O.OracleConfig(node_dims=(64, 16), edge_dims=(32, 4))
+    case, inputs = _random_case(cfg, n=200, E=1500, seed=17)
+    params = O.random_layer_params(cfg, seed=18)
+    layer = build_module(cfg, params).eval()
+    a = module_forward_backward(layer, case, cfg, inputs)
+    g = torch.Generator().manual_seed(3)
+    perm = torch.randperm(1500, generator=g)
+    inp2 = dict(inputs)
+    inp2["edge_index"] = inputs["edge_index"][:, perm]
+    for k in ("e", "xi", "frames"):
+        inp2[k] = inputs[k][perm]
+    b = module_forward_backward(layer, case, cfg, inp2)
+    assert rel_err(b["out_h"].numpy(), a["out_h"].numpy()) < 1e-5
+    assert rel_err(b["out_chi"].numpy(), a["out_chi"].numpy()) < 1e-5
+    assert rel_err(b["grad_e"].numpy(), a["grad_e"][perm].numpy()) < 1e-5
+    assert rel_err(b["grad_h"].numpy(), a["grad_h"].numpy()) < 1e-5
+
+
+def test_rotation_equivariance_full_size():
+    """Property of tests/test_gcpnet_equivariance.py:1773-1881 (atol 1e-5, rtol 1e-4) at its shapes."""
+    cfg = O.OracleConfig(node_dims=(100, 16), edge_dims=(32, 4))
+    g = torch.Generator().manual_seed(1)
+    n, E = 300, 10000
+    ei = torch.randint(0, n, (2, E), generator=g)
+    x = torch.randn(n, 3, generator=g, dtype=torch.float64) + torch.randint(1, 100, (1,), generator=g).double()
+    x = x - x.mean(0, keepdim=True)
+    inputs = O.synthetic_layer_inputs(cfg, ei, n, seed=5, positions=x)
+    Q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g, dtype=torch.float64))
+    if torch.det(Q) < 0:
+        Q = -Q
+    layer = build_module(cfg, O.random_layer_params(cfg, seed=4)).eval()
+    dev = torch.device("cuda")
+
+    def run(chi, xi, frames):
+        with torch.no_grad():
+            return layer((inputs["h"].to(dev), chi.float().to(dev)), (inputs["e"].to(dev), xi.float().to(dev)), ei.to(dev),
+                         frames.float().to(dev))
+    h0, chi0 = run(inputs["chi"], inputs["xi"], inputs["frames"])
+    fr = O.localize(x @ Q, ei)
+    h1, chi1 = run(inputs["chi"].double() @ Q, inputs["xi"].double() @ Q, fr)
+    assert torch.allclose(h1.cpu(), h0.cpu(), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(chi1.cpu().double(), chi0.cpu().double() @ Q, rtol=1e-4, atol=1e-5)
+
+
+def test_empty_and_degenerate_graphs():
+    cfg = O.OracleConfig(node_dims=(8, 4), edge_dims=(4, 2), num_message_layers=2, bottleneck=2, default_bottleneck=2,
+                         updating_node_positions=True)
+    params = O.random_layer_params(cfg, seed=41)
+    layer = build_module(cfg, params).eval()
+    # no edges at all; a single node with a self loop; many isolated nodes
+    for n, ei in ((5, torch.zeros((2, 0), dtype=torch.long)), (1, torch.zeros((2, 1), dtype=torch.long)),
+                  (70, torch.tensor([[0, 0, 3], [3, 3, 0]]))):
+        inputs = O.synthetic_layer_inputs(cfg, ei, n, seed=42)
+        case = dict(seed=43)
+        want = oracle_forward_backward(case, cfg, params, inputs)
+        res = module_forward_backward(layer, case, cfg, inputs)
+        _compare(res, want, [k for k, _ in layer.named_parameters()])
+
+
+def test_inference_mode_and_no_saved_activations():
+    cfg = O.OracleConfig(node_dims=(64, 16), edge_dims=(32, 4))
+    case, inputs = _random_case(cfg, n=100, E=700, seed=27)
+    params = O.random_layer_params(cfg, seed=28)
+    layer = build_module(cfg, params).eval()
+    dev = torch.device("cuda")
+    args = ((inputs["h"].to(dev), inputs["chi"].to(dev)), (inputs["e"].to(dev), inputs["xi"].to(dev)),
+            inputs["edge_index"].to(dev), inputs["frames"].to(dev))
+    with torch.no_grad():
+        h0, chi0 = layer(*args)
+    oh, ochi = O.interactions_forward(params, cfg, inputs["h"], inputs["chi"], inputs["e"], inputs["xi"],
+                                      inputs["edge_index"], inputs["frames"])
+    assert rel_err(h0.cpu().numpy(), oh.numpy()) < TOL and rel_err(chi0.cpu().numpy(), ochi.numpy()) < TOL
+    # all-true node mask is the unmasked path (gcpnet.py:1202-1206)
+    with torch.no_grad():
+        h1, _ = layer(*args, node_mask=torch.ones(100, dtype=torch.bool, device=dev))
+    assert torch.equal(h0, h1)
+    with pytest.raises(NotImplementedError):
+        m = torch.ones(100, dtype=torch.bool, device=dev)
+        m[3] = False
+        layer(*args, node_mask=m)
+
+
+def test_dropout_train_mode_statistics():
+    """GCPDropout (comp/__init__.py:97-135): p=0 in train mode equals eval; p>0 changes the output,
+    draws a new mask every call, and keeps E[output] close to eval for the first residual."""
+    cfg = O.OracleConfig(node_dims=(64, 16), edge_dims=(32, 4))
+    case, inputs = _random_case(cfg, n=300, E=2000, seed=37)
+    params = O.random_layer_params(cfg, seed=38)
+    dev = torch.device("cuda")
+    args = ((inputs["h"].to(dev), inputs["chi"].to(dev)), (inputs["e"].to(dev), inputs["xi"].to(dev)),
+            inputs["edge_index"].to(dev), inputs["frames"].to(dev))
+    ev = build_module(cfg, params, dropout=0.0).train()
+    with torch.no_grad():
+        a = ev(*args)
+        b = ev.eval()(*args)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    tr = build_module(cfg, params, dropout=0.3).train()
+    with torch.no_grad():
+        c = tr(*args)
+        d = tr(*args)
+    assert not torch.equal(c[0], d[0]) and not torch.equal(c[0], b[0])
+    assert torch.isfinite(c[0]).all() and torch.isfinite(c[1]).all()
+    # gradients flow in train mode and are finite
+    res = module_forward_backward(tr, case, cfg, inputs)
+    assert all(torch.isfinite(v).all() for v in res.values())
+
+
+def test_state_dict_roundtrip_and_reference_names():
+    cfg = O.OracleConfig(node_dims=(64, 16), edge_dims=(32, 4), updating_node_positions=True)
+    layer = build_module(cfg, None, device="cpu")
+    names = list(layer.state_dict().keys())
+    assert names == list(O.layer_param_shapes(cfg).keys())
+    for k, shp in O.layer_param_shapes(cfg).items():
+        assert tuple(layer.state_dict()[k].shape) == shp, k
+    assert sum(p.numel() for p in layer.parameters()) == 109445  # SURVEY 3.5, checkpoints/NMS
+
+
+def test_localize_matches_oracle():
+    import gcpnet_b200
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(500, 3, generator=g)
+    ei = torch.randint(0, 500, (2, 4000), generator=g)
+    got = gcpnet_b200.localize(x.cuda(), ei.cuda()).cpu()
+    assert torch.allclose(got, O.localize(x, ei), rtol=1e-5, atol=1e-6)
+
+
+def test_graph_build_matches_stable_sort():
+    """CSR views are index work: bit-exact against numpy stable argsort."""
+    import gcpnet_b200
+    g = torch.Generator().manual_seed(9)
+    n, E = 1000, 20000
+    ei = torch.randint(0, n - 5, (2, E), generator=g)
+    frames = torch.randn(E, 3, 3, generator=g)
+    gv = gcpnet_b200.graph_views(ei.cuda(), frames.cuda(), n)
+    row, col = ei[0].numpy(), ei[1].numpy()
+    perm = np.argsort(col, kind="stable")
+    assert np.array_equal(gv.perm.cpu().numpy(), perm.astype(np.int32))
+    assert np.array_equal(gv.dst.cpu().numpy(), col[perm].astype(np.int32))
+    assert np.array_equal(gv.src.cpu().numpy(), row[perm].astype(np.int32))
+    assert np.array_equal(gv.dst_ptr.cpu().numpy(), np.searchsorted(col[perm], np.arange(n + 1)).astype(np.int32))
+    spos = np.argsort(row[perm], kind="stable")
+    assert np.array_equal(gv.src_pos.cpu().numpy(), spos.astype(np.int32))
+    assert np.array_equal(gv.src_ptr.cpu().numpy(), np.searchsorted(row[perm][spos], np.arange(n + 1)).astype(np.int32))
+    want = O.segment_reduce(frames.reshape(E, 9), ei[0], n, "mean")
+    assert torch.allclose(gv.fbar.cpu(), want, rtol=1e-5, atol=1e-6)

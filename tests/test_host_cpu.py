@@ -1,0 +1,115 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports every symbol the header
+declares, the ctypes mirror matches the header's struct sizes, the module keeps the reference's
+state_dict, unsupported flags raise, CPU tensors are rejected (no fallback)."""
+import ctypes as C
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+import torch
+
+from gcpnet_b200 import _cabi
+from oracle import gcp_oracle as O
+from tests.helpers import build_module, module_cfgs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "gcpnet_b200.h")
+
+
+def test_header_symbols_match_exports_table():
+    text = open(HEADER).read()
+    declared = set(re.findall(r"\b(gcpnet_[a-z0-9_]+)\s*\(", text))
+    assert declared == set(_cabi.EXPORTS)
+
+
+def test_library_loads_and_exports_every_symbol():
+    from gcpnet_b200 import _lib, build
+    if not os.path.exists(_lib.lib_path()):
+        if shutil.which("nvcc") is None:
+            pytest.skip("library not built and no nvcc")
+        build.build()
+    lib = _lib.load()
+    for sym in _cabi.EXPORTS:
+        assert hasattr(lib, sym), sym
+    assert lib.gcpnet_version() >= 100
+    # plan is pure host code: callable without a GPU
+    cfg = O.OracleConfig(node_dims=(64, 16), edge_dims=(32, 4), updating_node_positions=True)
+    layer = build_module(cfg, None, device="cpu")
+    st = layer._layer_struct(layer._params_in_order(), False)
+    plan = _cabi.Plan()
+    assert lib.gcpnet_layer_plan(C.byref(st), 2500, 10000, C.byref(plan)) == 0
+    assert plan.msg_floats == 10000 * 112 and plan.edge_smem_fwd_bytes <= 227 * 1024
+    assert plan.edge_smem_bwd_bytes <= 227 * 1024 and plan.node_smem_bwd_bytes <= 227 * 1024
+    bad = _cabi.Layer()
+    assert lib.gcpnet_layer_plan(C.byref(bad), 10, 10, C.byref(plan)) != 0
+    assert b"num_message_layers" in lib.gcpnet_last_error()
+
+
+@pytest.mark.skipif(shutil.which("gcc") is None, reason="gcc needed")
+def test_ctypes_structs_match_header_sizes(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "gcpnet_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(gcpnet_gcp2),sizeof(gcpnet_layer),sizeof(gcpnet_graph),sizeof(gcpnet_plan),'
+                   'sizeof(gcpnet_forward_io),sizeof(gcpnet_backward_io));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert sizes == [C.sizeof(_cabi.Gcp2), C.sizeof(_cabi.Layer), C.sizeof(_cabi.Graph), C.sizeof(_cabi.Plan),
+                     C.sizeof(_cabi.ForwardIO), C.sizeof(_cabi.BackwardIO)]
+
+
+def test_state_dict_names_shapes_and_init_match_reference_layout():
+    cfg = O.OracleConfig(node_dims=(100, 16), edge_dims=(32, 4))
+    layer = build_module(cfg, None, device="cpu")
+    want = O.layer_param_shapes(cfg)
+    sd = layer.state_dict()
+    assert list(sd.keys()) == list(want.keys())
+    assert all(tuple(sd[k].shape) == want[k] for k in want)
+    assert sum(p.numel() for p in layer.parameters()) == 222604  # SURVEY 3.5 (checkpoints/CPD layer)
+    params = O.random_layer_params(cfg, seed=1)
+    layer.load_state_dict(params, strict=True)
+
+
+def test_unsupported_configurations_raise():
+    import gcpnet_b200
+    cfg = O.OracleConfig()
+    mcfg, lcfg = module_cfgs(cfg)
+    for key in ("frame_gate", "ablate_frame_updates", "enable_e3_equivariance", "ablate_scalars"):
+        bad = type(mcfg)(mcfg)
+        bad[key] = True
+        with pytest.raises(NotImplementedError):
+            gcpnet_b200.GCPInteractions((64, 16), (32, 4), cfg=bad, layer_cfg=lcfg)
+    with pytest.raises(NotImplementedError):
+        gcpnet_b200.GCPInteractions((64, 16), (32, 4), cfg=mcfg, layer_cfg=lcfg, autoregressive=True)
+    lbad = type(lcfg)(lcfg)
+    lbad["pre_norm"] = True
+    with pytest.raises(NotImplementedError):
+        gcpnet_b200.GCPInteractions((64, 16), (32, 4), cfg=mcfg, layer_cfg=lbad)
+    with pytest.raises(AssertionError):  # same assertion text as gcpnet.py:295-297
+        gcpnet_b200.GCPInteractions((64, 18), (32, 4), cfg=mcfg, layer_cfg=lcfg)
+
+
+def test_cpu_tensors_are_rejected_not_emulated():
+    cfg = O.OracleConfig(node_dims=(8, 4), edge_dims=(4, 2), num_message_layers=2, bottleneck=2, default_bottleneck=2)
+    layer = build_module(cfg, None, device="cpu")
+    ei = torch.randint(0, 6, (2, 10))
+    inp = O.synthetic_layer_inputs(cfg, ei, 6, seed=1)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        layer((inp["h"], inp["chi"]), (inp["e"], inp["xi"]), ei, inp["frames"])
+
+
+def test_scalar_vector_algebra():
+    from gcpnet_b200 import ScalarVector
+    a = ScalarVector(torch.ones(4, 3), torch.ones(4, 2, 3))
+    b = a + (torch.ones(4, 3), 2 * torch.ones(4, 2, 3))
+    assert float(b.scalar.sum()) == 24 and float(b.vector.sum()) == 72
+    flat = b.flatten()
+    assert flat.shape == (4, 9)
+    r = ScalarVector.recover(flat, 2)
+    assert torch.equal(r.scalar, b.scalar) and torch.equal(r.vector, b.vector)
+    s, v = a.concat((b,), dim=-1)
+    assert s.shape == (4, 6) and v.shape == (4, 4, 3)
+    h, chi = b
+    assert h is b.scalar and isinstance(b, tuple)
