@@ -315,7 +315,7 @@ def run_ours(args, w):
         a.record()
         batch = to_dev()
         loss = one_step(batch)
-        losses.append(float(loss))  # device -> host read of the step's result (synchronises)
+        losses.append(float(loss.detach()))  # device -> host read of the step's result (synchronises)
         b.record()
     barrier()
     e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)

@@ -17,12 +17,20 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
-def _compare(res, want, names, tol=TOL):
-    for key in ("out_h", "out_chi", "out_pos", "grad_h", "grad_chi", "grad_e", "grad_xi"):
-        if key in want:
+def _compare(res, want, names, tol=TOL, exact=None):
+    """`want` = fp32 oracle.  With `exact` (the fp64 oracle) the bar per tensor is
+    max(tol, 4 x the fp32 oracle's own distance to fp64): on large graphs ReLU units whose
+    pre-activation is ~0 flip between any two fp32 evaluation orders (the reference's included),
+    which moves individual gradient entries by more than 1e-4 of the tensor's range."""
+    keys = [k for k in ("out_h", "out_chi", "out_pos", "grad_h", "grad_chi", "grad_e", "grad_xi") if k in want]
+    keys += ["pgrad/" + k for k in names]
+    for key in keys:
+        if exact is None:
             assert rel_err(res[key].numpy(), want[key].numpy()) < tol, key
-    for k in names:
-        assert rel_err(res["pgrad/" + k].numpy(), want["pgrad/" + k].numpy()) < tol, k
+        else:
+            own = rel_err(want[key].numpy(), exact[key].numpy())
+            got = rel_err(res[key].numpy(), exact[key].numpy())
+            assert got < max(tol, 4.0 * own), (key, got, own)
 
 
 @pytest.mark.parametrize("name", list(GC.CASES))
@@ -72,9 +80,14 @@ def test_layer_matches_oracle_at_baseline_shapes(label, cfg, shape):
     case, inputs = _random_case(cfg, seed=101, **shape)
     params = O.random_layer_params(cfg, seed=100)
     want = oracle_forward_backward(case, cfg, params, inputs)
+    exact = oracle_forward_backward(case, cfg, params, inputs, dtype=torch.float64)
     layer = build_module(cfg, params).eval()
     res = module_forward_backward(layer, case, cfg, inputs)
-    _compare(res, want, [k for k, _ in layer.named_parameters()])
+    _compare(res, want, [k for k, _ in layer.named_parameters()], exact=exact)
+    # forward outputs are well conditioned: always within 1e-4 of the fp32 oracle
+    for key in ("out_h", "out_chi", "out_pos"):
+        if key in want:
+            assert rel_err(res[key].numpy(), want[key].numpy()) < TOL, key
 
 
 def test_reruns_are_bit_identical():
