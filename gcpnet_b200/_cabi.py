@@ -57,19 +57,21 @@ class Plan(C.Structure):
         ("node_smem_fwd_bytes", C.c_int32), ("node_smem_bwd_bytes", C.c_int32),
         ("msg_floats", C.c_int64), ("saved_edge_floats", C.c_int64), ("saved_node_floats", C.c_int64),
         ("edge_partial_floats", C.c_int64), ("node_partial_floats", C.c_int64),
-        ("edge_cotangent_floats", C.c_int64), ("agg_cotangent_floats", C.c_int64),
+        ("edge_cotangent_floats", C.c_int64), ("agg_cotangent_floats", C.c_int64), ("packed_floats", C.c_int64),
     ]
 
 
 class ForwardIO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
-                ("h", "chi", "e", "xi", "frames", "pos", "out_h", "out_chi", "out_pos", "msg", "saved_edge", "saved_node")]
+                ("h", "chi", "e", "xi", "frames", "pos", "out_h", "out_chi", "out_pos", "msg", "saved_edge", "saved_node",
+                 "packed")]
 
 
 class BackwardIO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("h", "chi", "e", "xi", "frames", "saved_edge", "saved_node", "g_out_h", "g_out_chi", "g_out_pos",
-                 "g_h", "g_chi", "g_e", "g_xi", "g_params", "ws_agg", "ws_edge", "ws_edge_partial", "ws_node_partial")]
+                 "g_h", "g_chi", "g_e", "g_xi", "g_params", "ws_agg", "ws_edge", "ws_edge_partial", "ws_node_partial",
+                 "packed")]
 
 
 EXPORTS = (

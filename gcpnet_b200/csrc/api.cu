@@ -1,4 +1,5 @@
-// api.cu -- CUDA kernels (sm_100a) and the extern "C" entry points declared in include/gcpnet_b200.h.
+// api.cu -- CUDA kernels (sm_100a) of the layer and the extern "C" entry points declared in
+// include/gcpnet_b200.h.
 //
 // Every entry point only enqueues kernels on the caller's stream: no allocation, no host
 // synchronisation, so the whole layer forward+backward can be captured into a CUDA graph.
@@ -8,14 +9,13 @@
 #include <cstdio>
 #include <map>
 #include <mutex>
-#include <vector>
 #include <string>
+#include <vector>
 
+#include "common.h"
 #include "layer_setup.h"
 
 using namespace gcp;
-
-#include "common.h"
 
 static thread_local std::string g_last_error;
 int gcp_fail(const std::string& msg) { g_last_error = msg; return 1; }
@@ -36,38 +36,60 @@ void gcp_profile_mark(int which, bool begin, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------
-// kernels
+// kernels: persistent, one CTA per SM, weights streamed through the shared-memory ring
 // ------------------------------------------------------------------------------------------
-template <int TE, int NT>
-__global__ void __launch_bounds__(NT) edge_fwd_kernel(const __grid_constant__ EdgeParams p) {
-  extern __shared__ __align__(16) float smem[];
+template <int TE, int NT, int SLF>
+__global__ void __launch_bounds__(NT, 1) edge_fwd_kernel(const __grid_constant__ EdgeParams p) {
+  extern __shared__ __align__(128) float smem[];
   const int ntiles = (p.E + TE - 1) / TE;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) edge_fwd_tile<TE, NT>(p, smem, tile);
+  const int mine = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (mine == 0) return;
+  WPipe wp = edge_pipe(p, smem, mine);
+  wpipe_start<NT>(wp);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+    edge_fwd_tile<TE, NT, SLF>(p, smem, tile, wp, tile == (int)blockIdx.x);
 }
 
-template <int TE, int NT>
-__global__ void __launch_bounds__(NT) edge_bwd_kernel(const __grid_constant__ EdgeParams p) {
-  extern __shared__ __align__(16) float smem[];
+template <int TE, int NT, int SLF, int SLD>
+__global__ void __launch_bounds__(NT, 1) edge_bwd_kernel(const __grid_constant__ EdgeParams p) {
+  extern __shared__ __align__(128) float smem[];
   const int ntiles = (p.E + TE - 1) / TE;
+  const int mine = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (mine == 0) return;
+  WPipe wp = edge_pipe(p, smem, mine);
+  wpipe_start<NT>(wp);
   float* prow = p.partial + (size_t)blockIdx.x * p.partial_stride;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-    edge_bwd_tile<TE, NT>(p, smem, tile, prow, tile != (int)blockIdx.x);
+    edge_bwd_tile<TE, NT, SLF, SLD>(p, smem, tile, wp, prow, tile != (int)blockIdx.x);
 }
 
-template <int TE, int NT>
-__global__ void __launch_bounds__(NT) node_fwd_kernel(const __grid_constant__ NodeParams p) {
-  extern __shared__ __align__(16) float smem[];
+template <int TE, int NT, int SLF>
+__global__ void __launch_bounds__(NT, 1) node_fwd_kernel(const __grid_constant__ NodeParams p) {
+  extern __shared__ __align__(128) float smem[];
   const int ntiles = (p.N + TE - 1) / TE;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) node_fwd_tile<TE, NT>(p, smem, tile);
+  const int mine = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (mine == 0) return;
+  WPipe wp = node_pipe(p, smem, mine);
+  wpipe_start<NT>(wp);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+    node_fwd_tile<TE, NT, SLF>(p, smem, tile, wp, tile == (int)blockIdx.x);
 }
 
-template <int TE, int NT>
-__global__ void __launch_bounds__(NT) node_bwd_kernel(const __grid_constant__ NodeParams p) {
-  extern __shared__ __align__(16) float smem[];
+template <int TE, int NT, int SLF, int SLD>
+__global__ void __launch_bounds__(NT, 1) node_bwd_kernel(const __grid_constant__ NodeParams p) {
+  extern __shared__ __align__(128) float smem[];
   const int ntiles = (p.N + TE - 1) / TE;
+  const int mine = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (mine == 0) return;
+  WPipe wp = node_pipe(p, smem, mine);
+  wpipe_start<NT>(wp);
   float* prow = p.partial + (size_t)blockIdx.x * p.partial_stride;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-    node_bwd_tile<TE, NT>(p, smem, tile, prow, tile != (int)blockIdx.x);
+    node_bwd_tile<TE, NT, SLF, SLD>(p, smem, tile, wp, prow, tile != (int)blockIdx.x);
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackParams p) {
+  pack_gcp<256>(p.ops[blockIdx.x], p.blob);
 }
 
 // aggregate only (GCPMessagePassing.forward): out[i] = mean/sum over the destination segment
@@ -130,58 +152,56 @@ static int set_smem(K kernel, int bytes) {
   return 0;
 }
 
-static int launch_edge_fwd(const EdgeParams& p, int TE, int grid, cudaStream_t st) {
-  const int bytes = p.sm.total * 4;
-  GcpTimedScope timed(T_EDGE_FWD, st);
-  if (TE == 64) {
-    if (set_smem(edge_fwd_kernel<64, EDGE_NT>, bytes)) return 1;
-    edge_fwd_kernel<64, EDGE_NT><<<grid, EDGE_NT, bytes, st>>>(p);
-    gcp_note_launches(1);
-  } else {
-    if (set_smem(edge_fwd_kernel<32, EDGE_NT>, bytes)) return 1;
-    edge_fwd_kernel<32, EDGE_NT><<<grid, EDGE_NT, bytes, st>>>(p);
-    gcp_note_launches(1);
-  }
-  CUDA_TRY(cudaGetLastError());
-  return 0;
-}
-static int launch_edge_bwd(const EdgeParams& p, int TE, int grid, cudaStream_t st) {
-  const int bytes = p.sm.total * 4;
-  GcpTimedScope timed(T_EDGE_BWD, st);
-  if (TE != 32) return fail("edge backward tile must be 32");
-  if (set_smem(edge_bwd_kernel<32, EDGE_NT>, bytes)) return 1;
-  edge_bwd_kernel<32, EDGE_NT><<<grid, EDGE_NT, bytes, st>>>(p);
+template <class K, class P>
+static int launch(K kernel, const P& p, int grid, int nt, int bytes, cudaStream_t st) {
+  if (set_smem(kernel, bytes)) return 1;
+  kernel<<<grid, nt, bytes, st>>>(p);
   gcp_note_launches(1);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
-static int launch_node_fwd(const NodeParams& p, int TE, int grid, cudaStream_t st) {
-  const int bytes = p.sm.total * 4;
-  GcpTimedScope timed(T_NODE_FWD, st);
-  if (TE == 32) {
-    if (set_smem(node_fwd_kernel<32, NODE_NT>, bytes)) return 1;
-    node_fwd_kernel<32, NODE_NT><<<grid, NODE_NT, bytes, st>>>(p);
-    gcp_note_launches(1);
-  } else {
-    if (set_smem(node_fwd_kernel<16, NODE_NT>, bytes)) return 1;
-    node_fwd_kernel<16, NODE_NT><<<grid, NODE_NT, bytes, st>>>(p);
-    gcp_note_launches(1);
-  }
-  CUDA_TRY(cudaGetLastError());
-  return 0;
+
+#define DISPATCH_EDGE(KERNEL, ...)                                                               \
+  do {                                                                                           \
+    const int bytes = p.sm.total * 4;                                                            \
+    if (tp.TE == 32 && tp.SLF == 1) return launch(KERNEL<32, 256, 1 __VA_ARGS__>, p, tp.grid, 256, bytes, st); \
+    if (tp.TE == 32 && tp.SLF == 2) return launch(KERNEL<32, 256, 2 __VA_ARGS__>, p, tp.grid, 256, bytes, st); \
+    if (tp.TE == 48 && tp.SLF == 1) return launch(KERNEL<48, 384, 1 __VA_ARGS__>, p, tp.grid, 384, bytes, st); \
+    if (tp.TE == 48 && tp.SLF == 2) return launch(KERNEL<48, 384, 2 __VA_ARGS__>, p, tp.grid, 384, bytes, st); \
+    if (tp.TE == 64 && tp.SLF == 1) return launch(KERNEL<64, 512, 1 __VA_ARGS__>, p, tp.grid, 512, bytes, st); \
+    if (tp.TE == 64 && tp.SLF == 2) return launch(KERNEL<64, 512, 2 __VA_ARGS__>, p, tp.grid, 512, bytes, st); \
+    return fail("no kernel instantiation for this edge tile plan");                              \
+  } while (0)
+#define COMMA_SLD , 2
+
+static int launch_edge_fwd(const EdgeParams& p, const EdgeTilePlan& tp, cudaStream_t st) {
+  GcpTimedScope timed(T_EDGE_FWD, st);
+  DISPATCH_EDGE(edge_fwd_kernel);
 }
-static int launch_node_bwd(const NodeParams& p, int TE, int grid, cudaStream_t st) {
+static int launch_edge_bwd(const EdgeParams& p, const EdgeTilePlan& tp, cudaStream_t st) {
+  GcpTimedScope timed(T_EDGE_BWD, st);
+  DISPATCH_EDGE(edge_bwd_kernel, COMMA_SLD);
+}
+static int launch_node_fwd(const NodeParams& p, const NodeTilePlan& tp, cudaStream_t st) {
+  GcpTimedScope timed(T_NODE_FWD, st);
   const int bytes = p.sm.total * 4;
+  if (tp.SLF == 1) return launch(node_fwd_kernel<NODE_TE, NODE_NT, 1>, p, tp.grid, NODE_NT, bytes, st);
+  if (tp.SLF == 2) return launch(node_fwd_kernel<NODE_TE, NODE_NT, 2>, p, tp.grid, NODE_NT, bytes, st);
+  if (tp.SLF == 4) return launch(node_fwd_kernel<NODE_TE, NODE_NT, 4>, p, tp.grid, NODE_NT, bytes, st);
+  return fail("no kernel instantiation for this node tile plan");
+}
+static int launch_node_bwd(const NodeParams& p, const NodeTilePlan& tp, cudaStream_t st) {
   GcpTimedScope timed(T_NODE_BWD, st);
-  if (TE == 32) {
-    if (set_smem(node_bwd_kernel<32, NODE_NT>, bytes)) return 1;
-    node_bwd_kernel<32, NODE_NT><<<grid, NODE_NT, bytes, st>>>(p);
-    gcp_note_launches(1);
-  } else {
-    if (set_smem(node_bwd_kernel<16, NODE_NT>, bytes)) return 1;
-    node_bwd_kernel<16, NODE_NT><<<grid, NODE_NT, bytes, st>>>(p);
-    gcp_note_launches(1);
-  }
+  const int bytes = p.sm.total * 4;
+  if (tp.SLF == 1) return launch(node_bwd_kernel<NODE_TE, NODE_NT, 1, NODE_SLD>, p, tp.grid, NODE_NT, bytes, st);
+  if (tp.SLF == 2) return launch(node_bwd_kernel<NODE_TE, NODE_NT, 2, NODE_SLD>, p, tp.grid, NODE_NT, bytes, st);
+  if (tp.SLF == 4) return launch(node_bwd_kernel<NODE_TE, NODE_NT, 4, NODE_SLD>, p, tp.grid, NODE_NT, bytes, st);
+  return fail("no kernel instantiation for this node tile plan");
+}
+static int launch_pack(const LayerOps& ops, float* blob, cudaStream_t st) {
+  const PackParams pp = make_pack_params(ops, blob);
+  pack_kernel<<<pp.n, 256, 0, st>>>(pp);
+  gcp_note_launches(1);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -191,7 +211,7 @@ static int launch_node_bwd(const NodeParams& p, int TE, int grid, cudaStream_t s
 // ------------------------------------------------------------------------------------------
 extern "C" {
 
-int gcpnet_version(void) { return 100; }
+int gcpnet_version(void) { return 200; }
 const char* gcpnet_last_error(void) { return g_last_error.c_str(); }
 void gcpnet_profile_enable(int on) { g_profile.store(on != 0); }
 int gcpnet_profile_read(int which, double* total_ms, int64_t* launches) {
@@ -214,23 +234,19 @@ uint64_t gcpnet_launch_count(void) { return g_launches.load(std::memory_order_re
 
 int gcpnet_layer_plan(const gcpnet_layer* layer, int64_t N, int64_t E, gcpnet_plan* plan) {
   if (!layer || !plan) return fail("layer_plan: null argument");
-  const std::string e = make_plan(*layer, N, E, plan);
+  LayerPlan lp;
+  const std::string e = make_layer_plan(*layer, N, E, &lp, plan);
   if (!e.empty()) return fail("layer_plan: " + e);
   return 0;
 }
 
-static int run_edge_forward(const gcpnet_layer& l, const gcpnet_graph& g, const gcpnet_forward_io& io, cudaStream_t st) {
+static int run_edge_forward(const gcpnet_layer& l, const gcpnet_graph& g, const LayerPlan& lp, const gcpnet_forward_io& io,
+                            cudaStream_t st) {
   if (g.num_edges == 0) return 0;
-  const LayerOps ops = layer_ops(l);
-  EdgeSmem sm;
-  const int TE = pick_edge_tile(l, ops, g.num_edges, false, &sm);
-  if (!TE) return fail("edge forward: no tile plan fits");
-  EdgeParams p = make_edge_params(l, g, ops, sm);
+  EdgeParams p = make_edge_params(l, g, lp.ops, lp.ef, false, io.packed);
   p.h = io.h; p.chi = io.chi; p.e = io.e; p.xi = io.xi; p.frames = io.frames;
   p.msg = io.msg; p.saved = io.saved_edge;
-  int grid = (int)((g.num_edges + TE - 1) / TE);
-  if (grid > MAX_PERSISTENT_CTAS) grid = MAX_PERSISTENT_CTAS;
-  return launch_edge_fwd(p, TE, grid, st);
+  return launch_edge_fwd(p, lp.ef, st);
 }
 
 int gcpnet_layer_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, const gcpnet_plan* plan,
@@ -238,29 +254,31 @@ int gcpnet_layer_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, c
   if (!layer || !graph || !plan || !io) return fail("layer_forward: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const gcpnet_layer& l = *layer;
-  const std::string e = check_layer(l);
-  if (!e.empty()) return fail("layer_forward: " + e);
   if (l.has_pos && (!io->pos || !io->out_pos)) return fail("layer_forward: node positions required");
+  if (!io->packed) return fail("layer_forward: packed-weight workspace required");
+  LayerPlan lp;
+  const std::string e = make_layer_plan(l, graph->num_nodes, graph->num_edges, &lp, nullptr);
+  if (!e.empty()) return fail("layer_forward: " + e);
   if (graph->num_nodes <= 0) return 0;
-  if (run_edge_forward(l, *graph, *io, st)) return 1;
-  const LayerOps ops = layer_ops(l);
-  NodeSmem sm;
-  const int TE = pick_node_tile(l, ops, graph->num_nodes, false, &sm);
-  if (!TE) return fail("node forward: no tile plan fits");
-  NodeParams p = make_node_params(l, *graph, ops, sm);
+  if (launch_pack(lp.ops, io->packed, st)) return 1;
+  if (run_edge_forward(l, *graph, lp, *io, st)) return 1;
+  NodeParams p = make_node_params(l, *graph, lp.ops, lp.nf, false, io->packed);
   p.h = io->h; p.chi = io->chi; p.msg = io->msg; p.pos = io->pos;
   p.out_h = io->out_h; p.out_chi = io->out_chi; p.out_pos = io->out_pos; p.saved = io->saved_node;
-  return launch_node_fwd(p, TE, plan->node_grid_fwd, st);
+  return launch_node_fwd(p, lp.nf, st);
 }
 
 int gcpnet_message_passing_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, const gcpnet_plan* plan,
                                    const gcpnet_forward_io* io, float* aggregate, void* stream) {
   if (!layer || !graph || !plan || !io || !aggregate) return fail("message_passing_forward: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  const std::string e = check_layer(*layer);
+  if (!io->packed) return fail("message_passing_forward: packed-weight workspace required");
+  LayerPlan lp;
+  const std::string e = make_layer_plan(*layer, graph->num_nodes, graph->num_edges, &lp, nullptr);
   if (!e.empty()) return fail("message_passing_forward: " + e);
   if (graph->num_nodes <= 0) return 0;
-  if (run_edge_forward(*layer, *graph, *io, st)) return 1;
+  if (launch_pack(lp.ops, io->packed, st)) return 1;
+  if (run_edge_forward(*layer, *graph, lp, *io, st)) return 1;
   const int W = layer->s + 3 * layer->v;
   const long long tot = graph->num_nodes * W;
   aggregate_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(io->msg, graph->dst_ptr, (int)graph->num_nodes, W,
@@ -276,37 +294,32 @@ int gcpnet_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, 
   cudaStream_t st = (cudaStream_t)stream;
   const gcpnet_layer& l = *layer;
   const gcpnet_graph& g = *graph;
-  const std::string e = check_layer(l);
-  if (!e.empty()) return fail("layer_backward: " + e);
   if (!io->saved_edge && g.num_edges > 0) return fail("layer_backward: forward ran without saved activations");
   if (!io->saved_node) return fail("layer_backward: forward ran without saved activations");
+  if (!io->packed) return fail("layer_backward: packed weights of the forward call required");
+  LayerPlan lp;
+  const std::string e = make_layer_plan(l, g.num_nodes, g.num_edges, &lp, nullptr);
+  if (!e.empty()) return fail("layer_backward: " + e);
   if (g.num_nodes <= 0) return 0;
-  const LayerOps ops = layer_ops(l);
   const int W = l.s + 3 * l.v;
   // node update backward -> direct cotangent of (h, chi) in g_h/g_chi, cotangent of the aggregate in ws_agg
-  NodeSmem nsm;
-  const int TN = pick_node_tile(l, ops, g.num_nodes, true, &nsm);
-  if (!TN) return fail("node backward: no tile plan fits");
-  NodeParams np = make_node_params(l, g, ops, nsm);
+  NodeParams np = make_node_params(l, g, lp.ops, lp.nb, true, io->packed);
   np.saved = const_cast<float*>(io->saved_node);
   np.g_out_h = io->g_out_h; np.g_out_chi = io->g_out_chi; np.g_out_pos = io->g_out_pos;
   np.g_x_h = io->g_h; np.g_x_chi = io->g_chi; np.g_agg = io->ws_agg;
   np.partial = io->ws_node_partial;
-  if (launch_node_bwd(np, TN, plan->node_grid_bwd, st)) return 1;
+  if (launch_node_bwd(np, lp.nb, st)) return 1;
   int edge_grid = 0;
   if (g.num_edges > 0) {
-    EdgeSmem esm;
-    const int TE = pick_edge_tile(l, ops, g.num_edges, true, &esm);
-    if (!TE) return fail("edge backward: no tile plan fits");
-    EdgeParams ep = make_edge_params(l, g, ops, esm);
+    EdgeParams ep = make_edge_params(l, g, lp.ops, lp.eb, true, io->packed);
     ep.h = io->h; ep.chi = io->chi; ep.e = io->e; ep.xi = io->xi; ep.frames = io->frames;
     ep.saved = const_cast<float*>(io->saved_edge);
     ep.gagg = io->ws_agg;
     ep.grow = io->ws_edge; ep.gcol = io->ws_edge + (size_t)g.num_edges * W;
     ep.ge = io->g_e; ep.gxi = io->g_xi;
     ep.partial = io->ws_edge_partial;
-    edge_grid = plan->edge_grid_bwd;
-    if (launch_edge_bwd(ep, TE, edge_grid, st)) return 1;
+    edge_grid = lp.eb.grid;
+    if (launch_edge_bwd(ep, lp.eb, st)) return 1;
     const long long tot = g.num_nodes * W;
     GcpTimedScope timed(T_COT_REDUCE, st);
     node_cotangent_reduce_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(
@@ -316,7 +329,7 @@ int gcpnet_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, 
   const int np_tot = l.n_edge_params + l.n_node_params;
   GcpTimedScope timed(T_PARTIAL_REDUCE, st);
   partial_reduce_kernel<<<(np_tot + 255) / 256, 256, 0, st>>>(io->g_params, io->ws_edge_partial, l.n_edge_params, edge_grid,
-                                                           io->ws_node_partial, l.n_node_params, plan->node_grid_bwd);
+                                                           io->ws_node_partial, l.n_node_params, lp.nb.grid);
   gcp_note_launches(1);
   CUDA_TRY(cudaGetLastError());
   return 0;

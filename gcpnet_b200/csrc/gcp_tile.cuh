@@ -1,16 +1,28 @@
-// gcp_tile.cuh -- CTA-tile building blocks of the GCP2 perceptron (forward and backward).
+// gcp_tile.cuh -- CTA-tile building blocks of the GCP2 perceptron (forward and backward), v2.
 //
 // Everything here works on a TILE of TE "entities" (edges in the message kernel, nodes in the
 // node-update kernel) whose features sit in shared memory, entity-major: X[e][f], row stride ld.
 // Reference semantics: GCP2.forward, src/models/components/gcpnet.py:393-468 (+ :353-391 for the
 // vector gate), scalarize src/models/components/__init__.py:272-325, safe_norm :381-392.
 //
+// Design (B200):
+//   * NT = 256..512 threads per CTA (8 threads per edge), one CTA per SM, persistent over tiles.
+//   * Weights never go through registers on their way in: the host-side pack kernel (pack.cuh) lays
+//     every GCP out as a few "chunks" in exactly the shared-memory layout the tile code wants, and the
+//     CTA streams them through a small ring of shared-memory slots with cp.async.bulk (TMA 1-D bulk
+//     copy, SASS UBLKCP) completing on mbarriers -- the next chunks land while the current GEMM runs.
+//   * Dense Linear layers are register-tiled fp32 FFMA GEMMs: a warp owns a 16 x 16 output tile
+//     (lane = 8 row groups x 4 column groups, 2 x 4 outputs per thread), operands are read with
+//     conflict-free 128-bit shared loads (1 wavefront per instruction).
+//   * All cooperative loops are "warp per row, lane per column" or use compile-time divisors: no
+//     runtime integer division in any inner loop.
+//
 // Code style: a routine is a sequence of PHASES.  A phase is a parallel-for over the CTA's NT
-// threads followed by a barrier; no value lives in a register across a phase boundary.  On the
-// device a phase is `{ tid = threadIdx.x; ... } __syncthreads();`.  The same source also compiles
-// for the host, where a phase runs the NT thread bodies one after another (optionally in reverse
-// order, to expose intra-phase hazards) -- that build is the CPU emulation used by the non-GPU
-// tests (tests/emul); it is never part of the product path.
+// threads followed by a barrier; no per-thread value lives across a phase boundary (CTA-uniform
+// values such as the pipeline position do).  The same source also compiles for the host, where a
+// phase runs the NT thread bodies one after another (optionally in reverse order, to expose
+// intra-phase hazards) -- that build is the CPU emulation used by the non-GPU tests (tests/emul);
+// it is never part of the product path.
 //
 // Bank-conflict rules used for the strides (floats):
 //   * arrays read with float4 along the feature axis by lanes that differ in the row:
@@ -20,6 +32,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace gcp {
 
@@ -27,12 +40,15 @@ namespace gcp {
 #define GCP_HDN __host__ __device__
 
 inline int g_emul_reverse = 0;  // host emulation only: run thread bodies in reverse order when set
+inline bool g_emul_first = false;  // host emulation only: true while the first-executed thread body of a phase runs
 #if defined(__CUDA_ARCH__)
+#define GCP_DEVICE_CODE 1
 #define GCP_PHASE_BEGIN(NT) { const int tid = (int)threadIdx.x; (void)tid;
 #define GCP_PHASE_END } __syncthreads();
 #define GCP_LDG(p) __ldg(p)
 #else
-#define GCP_PHASE_BEGIN(NT) for (int tid_ = 0; tid_ < (NT); ++tid_) { const int tid = ::gcp::g_emul_reverse ? (NT) - 1 - tid_ : tid_; (void)tid;
+#define GCP_DEVICE_CODE 0
+#define GCP_PHASE_BEGIN(NT) for (int tid_ = 0; tid_ < (NT); ++tid_) { const int tid = ::gcp::g_emul_reverse ? (NT) - 1 - tid_ : tid_; (void)tid; ::gcp::g_emul_first = (tid_ == 0);
 #define GCP_PHASE_END }
 #define GCP_LDG(p) (*(p))
 #endif
@@ -81,8 +97,30 @@ GCP_HD int ld_hd(int hd) { return ld_vec(3 * hd_cols(hd)); }
 GCP_HD float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 GCP_HD void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
-// One GCP2 module (device view).  Weight pointers use the nn.Linear layouts of the reference
-// (gcpnet.py:303-322): Wd[hd][vi], Wdf[3][vi], Ws[so][si+hd+9], bs[so], Wu[vo][hd], Wg[vo][so], bg[vo].
+// ------------------------------------------------------------------------------------------
+// packed weights (written by pack.cuh) and the shared-memory weight ring
+// ------------------------------------------------------------------------------------------
+struct WChunk { int off, floats; };  // offset (floats) into the layer's packed blob; size multiple of 4
+constexpr int MAX_WS_CHUNKS = 16;
+constexpr int MAX_WSEQ = 96;
+constexpr int MAX_WSLOTS = 3;
+
+// Packed layout of one GCP2 (all row strides padded, all padding zero):
+//   S  chunk: WdT[vi][cols]   WdT[c][k] = vector_down[k][c] (k < hd), WdT[c][hdp + cc] = vector_down_frames[cc][c]
+//   WS chunk c (c < nWS): W[NP][ldk], W[n][kk] = scalar_out.weight[n][c*kc + kk], followed by scalar_out.bias
+//             (NP floats; every chunk carries it so that all chunks have one size).  NP = round_up(so, 16):
+//             padding rows are zero.  Chunk c starts at ws_off + c * ws_stride.
+//   G  chunk: WG[round_up(vo,4)][ldg] = vector_out_scale.weight (zero rows beyond vo), then bias (round_up(vo,4)), then WU[vo][hdp] = vector_up.weight
+struct GcpW {
+  WChunk S, G;
+  int ws_off, ws_floats, ws_stride;
+  int nWS, kc, ldk, NP;
+  int ldg, o_bg, o_wu;  // offsets inside the G chunk
+  int cols, hdp;
+};
+
+// One GCP2 module (device view).  Raw weight pointers keep the nn.Linear layouts of the reference
+// (gcpnet.py:303-322) and are only read by the pack kernel; the tile code reads the packed chunks.
 // o_* = offsets (floats) of the matching gradient blocks inside a per-CTA partial-gradient row.
 struct GcpOp {
   int si, vi, so, vo, hd;
@@ -90,8 +128,87 @@ struct GcpOp {
   const float *Wd, *Wdf, *Ws, *bs, *Wu, *Wg, *bg;
   int o_Wd, o_Wdf, o_Ws, o_bs, o_Wu, o_Wg, o_bg;
   int pad_;
+  GcpW w;
 };
 GCP_HD int gcp_k(const GcpOp& op) { return op.si + op.hd + 9; }
+GCP_HD int gcp_kpad(const GcpOp& op) { return op.w.nWS * op.w.kc; }  // columns the GEMM reads from Z
+
+struct WSeq {  // the order in which one kernel consumes chunks, per tile
+  int n, nslot, slot_floats, pad_;
+  WChunk c[MAX_WSEQ];
+};
+
+struct WPipe {  // CTA-uniform state of the ring
+  float* slots;
+  unsigned long long* mbar;
+  const float* blob;
+  const WSeq* seq;
+  int head;   // position of the chunk the next wpipe_wait() returns
+  int total;  // positions this CTA consumes over its whole life
+};
+
+#if GCP_DEVICE_CODE
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+#endif
+
+// one thread: start the bulk copy of position `pos` into its slot
+GCP_HD void wpipe_issue(const WPipe& w, int pos) {
+  const WChunk ck = w.seq->c[pos % w.seq->n];
+  const int slot = pos % w.seq->nslot;
+  float* dst = w.slots + (size_t)slot * w.seq->slot_floats;
+  const float* src = w.blob + ck.off;
+#if GCP_DEVICE_CODE
+  const uint32_t bar = smem_u32(&w.mbar[slot]);
+  const uint32_t bytes = (uint32_t)ck.floats * 4u;
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+#else
+  memcpy(dst, src, (size_t)ck.floats * 4);
+#endif
+}
+// every thread, before reading the head chunk
+GCP_HD const float* wpipe_wait(const WPipe& w) {
+  const int slot = w.head % w.seq->nslot;
+#if GCP_DEVICE_CODE
+  const uint32_t bar = smem_u32(&w.mbar[slot]);
+  const uint32_t parity = (uint32_t)((w.head / w.seq->nslot) & 1);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  }
+#endif
+  return w.slots + (size_t)slot * w.seq->slot_floats;
+}
+// thread 0, at the START of the first phase after the barrier that ended the last read of the head
+// chunk (the caller then advances w.head in CTA-uniform code): refill the slot just freed
+GCP_HD void wpipe_refill(const WPipe& w, int released_pos, int tid) {
+#if GCP_DEVICE_CODE
+  const bool issuer = tid == 0;
+#else
+  // the emulated copy is instantaneous, so it has to happen before any thread body of this phase reads the
+  // slot (on the device the readers block on the mbarrier instead): the first-executed body issues it
+  const bool issuer = g_emul_first; (void)tid;
+#endif
+  if (issuer && released_pos + w.seq->nslot < w.total) wpipe_issue(w, released_pos + w.seq->nslot);
+}
+// kernel prologue (CTA-uniform): barrier init + first nslot copies.  NT-thread phase.
+template <int NT>
+GCP_HDN void wpipe_start(WPipe& w) {
+  GCP_PHASE_BEGIN(NT)
+  if (tid == 0) {
+#if GCP_DEVICE_CODE
+    for (int i = 0; i < w.seq->nslot; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&w.mbar[i])), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+    for (int i = 0; i < w.seq->nslot && i < w.total; ++i) wpipe_issue(w, i);
+  }
+  GCP_PHASE_END
+  w.head = 0;
+}
 
 // Shared-memory views used by one GCP2 evaluation on a tile.
 struct TileBufs {
@@ -101,301 +218,226 @@ struct TileBufs {
   float* F;              // [TE][9]    frames (a, xyz)
   float* T;   int ldt;   // [TE][ldt]  pre-activation scalar_out
   float* SG;  int ldsg;  // [TE][ldsg] sigmoid gate per output vector channel
-  float* WC;  int wc_cap;  // weight chunk staging
-  float* WS;             // small weights: WdT[vi][hd_cols], Wu[vo][hdp], biases
+  float* WSM;            // persistent copy of the current GCP's small weights (backward): WdT | WU
 };
 constexpr int LDF = 9;
 
 // ------------------------------------------------------------------------------------------
-// dense tile GEMMs, fp32 FFMA, register micro-tiles, weights staged through shared memory
+// GEMM thread map: warp = 16 rows x 16 columns of outputs, lane = (eg = lane>>2, og = lane&3),
+// thread rows {e0, e0+8}, 4 columns per 16-wide slice.
 // ------------------------------------------------------------------------------------------
+template <int TE, int NT>
+struct GemmMap {
+  static constexpr int NW = NT / 32, WE = TE / 16, WN = NW / WE;
+  static_assert(NT % 32 == 0 && TE % 16 == 0 && WE >= 1 && WN >= 1 && WE * WN == NW, "bad GEMM thread grid");
+  int e0, og, wn;
+  GCP_HD GemmMap(int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+    e0 = 16 * (warp % WE) + (lane >> 2);
+    og = lane & 3;
+    wn = warp / WE;
+  }
+};
+
+// acc[i][r][j] += sum_{kk<kc} xmap(X[e_r][k0+kk]) * Wc[n][kk],  n = 16*(wn + WN*i) + og + 4*j  (n-major weights)
+template <int TE, int NT, int SL, class XMap>
+GCP_HD void gemm_nmajor_chunk(float (&acc)[SL][2][4], const float* X, int ldx, int k0, int kc, const float* Wc, int ldk,
+                              int nslices, const GemmMap<TE, NT>& m, XMap xmap) {
+  constexpr int WN = GemmMap<TE, NT>::WN;
+  const float* x0 = X + m.e0 * ldx + k0;
+  const float* x1 = x0 + 8 * ldx;
+#pragma unroll
+  for (int i = 0; i < SL; ++i) {
+    const int sl = m.wn + WN * i;
+    if (sl < nslices) {
+      const float* w0 = Wc + (16 * sl + m.og) * ldk;
+#pragma unroll 2
+      for (int k4 = 0; k4 < kc; k4 += 4) {
+        float4 a = ld4(x0 + k4), b = ld4(x1 + k4);
+        a.x = xmap(a.x); a.y = xmap(a.y); a.z = xmap(a.z); a.w = xmap(a.w);
+        b.x = xmap(b.x); b.y = xmap(b.y); b.z = xmap(b.z); b.w = xmap(b.w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 wv = ld4(w0 + 4 * j * ldk + k4);
+          acc[i][0][j] = fmaf(a.x, wv.x, acc[i][0][j]); acc[i][0][j] = fmaf(a.y, wv.y, acc[i][0][j]);
+          acc[i][0][j] = fmaf(a.z, wv.z, acc[i][0][j]); acc[i][0][j] = fmaf(a.w, wv.w, acc[i][0][j]);
+          acc[i][1][j] = fmaf(b.x, wv.x, acc[i][1][j]); acc[i][1][j] = fmaf(b.y, wv.y, acc[i][1][j]);
+          acc[i][1][j] = fmaf(b.z, wv.z, acc[i][1][j]); acc[i][1][j] = fmaf(b.w, wv.w, acc[i][1][j]);
+        }
+      }
+    }
+  }
+}
+
+// acc[i][r][c] = sum_{k<K} X[e_r][k] * Wc[k][16*(wn+WN*i) + 4*og + c]   (k-major weights: the data
+// gradient through an nn.Linear whose packed weight is [K = out rows][ldw]).  K multiple of 4.
+template <int TE, int NT, int SL>
+GCP_HD void gemm_kmajor_chunk(float (&acc)[SL][2][4], const float* X, int ldx, int K, const float* Wc, int ldw,
+                              int nslices, const GemmMap<TE, NT>& m) {
+  constexpr int WN = GemmMap<TE, NT>::WN;
+  const float* x0 = X + m.e0 * ldx;
+  const float* x1 = x0 + 8 * ldx;
+#pragma unroll
+  for (int i = 0; i < SL; ++i) {
+    const int sl = m.wn + WN * i;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { acc[i][0][c] = 0.f; acc[i][1][c] = 0.f; }
+    if (sl < nslices) {
+      const float* w0 = Wc + 16 * sl + 4 * m.og;
+#pragma unroll 2
+      for (int k4 = 0; k4 < K; k4 += 4) {
+        const float4 a = ld4(x0 + k4), b = ld4(x1 + k4);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const float4 wv = ld4(w0 + (k4 + kk) * ldw);
+          acc[i][0][0] = fmaf(av[kk], wv.x, acc[i][0][0]); acc[i][0][1] = fmaf(av[kk], wv.y, acc[i][0][1]);
+          acc[i][0][2] = fmaf(av[kk], wv.z, acc[i][0][2]); acc[i][0][3] = fmaf(av[kk], wv.w, acc[i][0][3]);
+          acc[i][1][0] = fmaf(bv[kk], wv.x, acc[i][1][0]); acc[i][1][1] = fmaf(bv[kk], wv.y, acc[i][1][1]);
+          acc[i][1][2] = fmaf(bv[kk], wv.z, acc[i][1][2]); acc[i][1][3] = fmaf(bv[kk], wv.w, acc[i][1][3]);
+        }
+      }
+    }
+  }
+}
+
 struct XIdentity { GCP_HD float operator()(float x) const { return x; } };
 struct XAct { int a; float slope; GCP_HD float operator()(float x) const { return act_fwd(a, x, slope); } };
 
-// Y[e][n] = bias[n] + sum_k xmap(X[e][k]) * W[n][k]   (W global, nn.Linear layout [N][K]).
-// Thread (eg, og) owns rows e = eg + EG*i (i<ER) and outputs n = n0 + og + OG*j (j<NR).
-// K is split into chunks that fit WC; partial sums between chunks go through Yacc (smem, [TE][ldy]).
-template <int TE, int NT, int OG, int NR, class XMap, class Epi>
-GCP_HDN void tile_gemm_nmajor(const float* X, int ldx, int K, const float* W, int N, const float* bias,
-                              float* Wc, int wc_cap, float* Yacc, int ldy, XMap xmap, Epi epi) {
-  constexpr int EG = NT / OG;
-  constexpr int ER = TE / EG;
-  static_assert(EG * OG == NT && ER * EG == TE && ER >= 1, "bad gemm thread grid");
-  static_assert(NT % 32 == 0, "NT must be a multiple of the warp size");
-  constexpr int NCH = OG * NR;
-  const int K4 = round_up(K, 4);
-  const int kcmax = ((wc_cap / NCH) - 4) & ~3;
-  const int nkc = (K4 + kcmax - 1) / kcmax;
-  for (int kci = 0; kci < nkc; ++kci) {
-    const int k0 = kci * kcmax;
-    const int kc = (K4 - k0) < kcmax ? (K4 - k0) : kcmax;
-    const int ldw = ld_vec(kc);
-    for (int n0 = 0; n0 < N; n0 += NCH) {
-      GCP_PHASE_BEGIN(NT)
-      for (int n = tid >> 5; n < NCH; n += NT / 32) {
-        const int gn = n0 + n;
-        const float* wrow = W + (size_t)gn * K + k0;
-        for (int kk = tid & 31; kk < kc; kk += 32)
-          Wc[n * ldw + kk] = (gn < N && k0 + kk < K) ? GCP_LDG(wrow + kk) : 0.f;
-      }
-      GCP_PHASE_END
-      GCP_PHASE_BEGIN(NT)
-      const int og = tid % OG, eg = tid / OG;
-      float acc[ER][NR];
-#pragma unroll
-      for (int j = 0; j < NR; ++j) {
-        const int n = n0 + og + OG * j;
-#pragma unroll
-        for (int i = 0; i < ER; ++i) {
-          if (kci == 0) acc[i][j] = (bias != nullptr && n < N) ? GCP_LDG(bias + n) : 0.f;
-          else acc[i][j] = (n < N) ? Yacc[(eg + EG * i) * ldy + n] : 0.f;
-        }
-      }
-      const float* xbase = X + eg * ldx + k0;
-      const float* wbase = Wc + og * ldw;
-#pragma unroll 2
-      for (int k4 = 0; k4 < kc; k4 += 4) {
-        float4 xv[ER];
-#pragma unroll
-        for (int i = 0; i < ER; ++i) {
-          xv[i] = ld4(xbase + i * EG * ldx + k4);
-          xv[i].x = xmap(xv[i].x); xv[i].y = xmap(xv[i].y); xv[i].z = xmap(xv[i].z); xv[i].w = xmap(xv[i].w);
-        }
-#pragma unroll
-        for (int j = 0; j < NR; ++j) {
-          const float4 wv = ld4(wbase + j * OG * ldw + k4);
-#pragma unroll
-          for (int i = 0; i < ER; ++i) {
-            acc[i][j] = fmaf(xv[i].x, wv.x, acc[i][j]);
-            acc[i][j] = fmaf(xv[i].y, wv.y, acc[i][j]);
-            acc[i][j] = fmaf(xv[i].z, wv.z, acc[i][j]);
-            acc[i][j] = fmaf(xv[i].w, wv.w, acc[i][j]);
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < NR; ++j) {
-        const int n = n0 + og + OG * j;
-        if (n < N) {
-#pragma unroll
-          for (int i = 0; i < ER; ++i) {
-            const int e = eg + EG * i;
-            if (kci == nkc - 1) epi(e, n, acc[i][j]);
-            else Yacc[e * ldy + n] = acc[i][j];
-          }
-        }
-      }
-      GCP_PHASE_END
-    }
-  }
-}
-
-// Y[e][n] = sum_k X[e][k] * W[k][n]   (W global, row-major [K][N]: the transpose-free form of the
-// data-gradient through an nn.Linear whose weight is [K=out][N=in]).  NR multiple of 4.
-// Thread (eg, og) owns rows e = eg + EG*i and outputs n = n0 + 4*(og + OG*j4) + c.
-template <int TE, int NT, int OG, int NR, class Epi>
-GCP_HDN void tile_gemm_kmajor(const float* X, int ldx, int K, const float* W, int N,
-                              float* Wc, int wc_cap, float* Yacc, int ldy, Epi epi) {
-  constexpr int EG = NT / OG;
-  constexpr int ER = TE / EG;
-  static_assert(EG * OG == NT && ER * EG == TE && ER >= 1, "bad gemm thread grid");
-  static_assert(NR % 4 == 0, "NR must be a multiple of 4");
-  constexpr int NR4 = NR / 4;
-  constexpr int NCH = OG * NR;
-  const int K4 = round_up(K, 4);
-  const int kcmax = (wc_cap / NCH) & ~3;
-  const int nkc = (K4 + kcmax - 1) / kcmax;
-  for (int kci = 0; kci < nkc; ++kci) {
-    const int k0 = kci * kcmax;
-    const int kc = (K4 - k0) < kcmax ? (K4 - k0) : kcmax;
-    for (int n0 = 0; n0 < N; n0 += NCH) {
-      GCP_PHASE_BEGIN(NT)
-      for (int idx = tid; idx < kc * NCH; idx += NT) {
-        const int kk = idx / NCH, n = idx - kk * NCH;
-        Wc[idx] = (k0 + kk < K && n0 + n < N) ? GCP_LDG(W + (size_t)(k0 + kk) * N + n0 + n) : 0.f;
-      }
-      GCP_PHASE_END
-      GCP_PHASE_BEGIN(NT)
-      const int og = tid % OG, eg = tid / OG;
-      float acc[ER][NR];
-#pragma unroll
-      for (int j = 0; j < NR; ++j) {
-        const int n = n0 + 4 * (og + OG * (j >> 2)) + (j & 3);
-#pragma unroll
-        for (int i = 0; i < ER; ++i)
-          acc[i][j] = (kci > 0 && n < N) ? Yacc[(eg + EG * i) * ldy + n] : 0.f;
-      }
-      const float* xbase = X + eg * ldx + k0;
-#pragma unroll 1
-      for (int k4 = 0; k4 < kc; k4 += 4) {
-        float4 xv[ER];
-#pragma unroll
-        for (int i = 0; i < ER; ++i) xv[i] = ld4(xbase + i * EG * ldx + k4);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-          for (int j4 = 0; j4 < NR4; ++j4) {
-            const float4 wv = ld4(Wc + (k4 + kk) * NCH + 4 * (og + OG * j4));
-#pragma unroll
-            for (int i = 0; i < ER; ++i) {
-              const float x = kk == 0 ? xv[i].x : kk == 1 ? xv[i].y : kk == 2 ? xv[i].z : xv[i].w;
-              acc[i][4 * j4 + 0] = fmaf(x, wv.x, acc[i][4 * j4 + 0]);
-              acc[i][4 * j4 + 1] = fmaf(x, wv.y, acc[i][4 * j4 + 1]);
-              acc[i][4 * j4 + 2] = fmaf(x, wv.z, acc[i][4 * j4 + 2]);
-              acc[i][4 * j4 + 3] = fmaf(x, wv.w, acc[i][4 * j4 + 3]);
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < NR; ++j) {
-        const int n = n0 + 4 * (og + OG * (j >> 2)) + (j & 3);
-        if (n < N) {
-#pragma unroll
-          for (int i = 0; i < ER; ++i) {
-            const int e = eg + EG * i;
-            if (kci == nkc - 1) epi(e, n, acc[i][j]);
-            else Yacc[e * ldy + n] = acc[i][j];
-          }
-        }
-      }
-      GCP_PHASE_END
-    }
-  }
-}
-
 // Weight gradient of an nn.Linear on a tile:  P[j][i] (+)= sum_e G[e][j] * fmap(Zin[e][i]),
 // Pb[j] (+)= sum_e G[e][j].  P/Pb are this CTA's private rows in global memory (deterministic:
-// every element is owned by exactly one thread).  Rows e >= nrows of G must be zero.
-// G and Zin are read 4 resp. 8 columns at a time: their arrays carry >= 8 floats of slack.
-template <int TE, int NT, class FMap>
-GCP_HDN void tile_wgrad(const float* G, int ldg, int J, const float* Zin, int ldz, int I,
-                        float* P, float* Pb, bool accumulate, FMap fmap) {
-  const int JT = (J + 3) / 4, IT = (I + 7) / 8;
-  GCP_PHASE_BEGIN(NT)
+// every element is owned by exactly one thread; the previous partial is fetched BEFORE the
+// reduction loop so its latency overlaps the math).  Rows e >= nrows of G must be zero.
+// A thread owns a JW x IW block of P (JW in {1,4}, IW in {4,8}); G and Zin are read JW resp. IW columns
+// at a time: J % JW == 0 or zero padding, and Zin carries readable columns up to round_up(I, IW).
+template <int TE, int NT, int JW, int IW, class FMap>
+GCP_HD void tile_wgrad(const float* G, int ldg, int J, const float* Zin, int ldz, int I,
+                       float* P, float* Pb, bool accumulate, FMap fmap, int tid) {
+  static_assert((JW == 1 || JW == 4) && (IW == 4 || IW == 8), "tile shape");
+  const int JT = (J + JW - 1) / JW, IT = (I + IW - 1) / IW;
   for (int tile = tid; tile < JT * IT; tile += NT) {
-    const int jt = tile % JT, it = tile / JT;
-    float acc[4][8];
+    const int it = tile / JT, jt = tile - it * JT;  // consecutive lanes: consecutive j (contiguous G columns)
+    float acc[JW][IW], old[JW][IW];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < JW; ++a)
 #pragma unroll
-      for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
-    const float* gp = G + 4 * jt;
-    const float* zp = Zin + 8 * it;
+      for (int b = 0; b < IW; ++b) {
+        acc[a][b] = 0.f;
+        const int j = JW * jt + a, i = IW * it + b;
+        old[a][b] = (accumulate && j < J && i < I) ? P[(size_t)j * I + i] : 0.f;
+      }
+    const float* gp = G + JW * jt;
+    const float* zp = Zin + IW * it;
 #pragma unroll 2
     for (int e = 0; e < TE; ++e) {
-      const float4 g = ld4(gp + e * ldg);
-      float4 z0 = ld4(zp + e * ldz), z1 = ld4(zp + e * ldz + 4);
-      const float gv[4] = {g.x, g.y, g.z, g.w};
-      const float zv[8] = {fmap(z0.x), fmap(z0.y), fmap(z0.z), fmap(z0.w), fmap(z1.x), fmap(z1.y), fmap(z1.z), fmap(z1.w)};
+      float gv[JW], zv[IW];
+      if (JW == 4) {
+        const float4 g = ld4(gp + e * ldg);
+        const float t4[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < JW; ++a) gv[a] = t4[a];
+      } else {
+        gv[0] = gp[e * ldg];
+      }
+      const float4 z0 = ld4(zp + e * ldz);
+      zv[0] = fmap(z0.x); zv[1] = fmap(z0.y); zv[2] = fmap(z0.z); zv[3] = fmap(z0.w);
+      if (IW == 8) {
+        const float4 z1 = ld4(zp + e * ldz + 4);
+        zv[IW - 4] = fmap(z1.x); zv[IW - 3] = fmap(z1.y); zv[IW - 2] = fmap(z1.z); zv[IW - 1] = fmap(z1.w);
+      }
 #pragma unroll
-        for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(gv[a], zv[b], acc[a][b]);
+      for (int a = 0; a < JW; ++a)
+#pragma unroll
+        for (int b = 0; b < IW; ++b) acc[a][b] = fmaf(gv[a], zv[b], acc[a][b]);
     }
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int j = 4 * jt + a;
+    for (int a = 0; a < JW; ++a) {
+      const int j = JW * jt + a;
       if (j < J) {
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          const int i = 8 * it + b;
-          if (i < I) {
-            float* dst = P + (size_t)j * I + i;
-            *dst = (accumulate ? *dst : 0.f) + acc[a][b];
-          }
+        for (int b = 0; b < IW; ++b) {
+          const int i = IW * it + b;
+          if (i < I) P[(size_t)j * I + i] = old[a][b] + acc[a][b];
         }
       }
     }
   }
   if (Pb != nullptr) {
     for (int j = tid; j < J; j += NT) {
+      const float o = accumulate ? Pb[j] : 0.f;
       float s = 0.f;
       for (int e = 0; e < TE; ++e) s += G[e * ldg + j];
-      Pb[j] = (accumulate ? Pb[j] : 0.f) + s;
+      Pb[j] = o + s;
     }
   }
-  GCP_PHASE_END
 }
 
 // ------------------------------------------------------------------------------------------
-// GCP2 forward on a tile
+// cooperative row copies: warp per row, lane per column (coalesced, no integer division)
 // ------------------------------------------------------------------------------------------
-// Small-weight staging: WS = [ WdT: vi x hd_cols | Wu: vo x hdp ], zero padded.
-//   WdT[c][k] = Wd[k][c] (k<hd), WdT[c][hd_cols-4+cc] = Wdf[cc][c] (cc<3)
-template <int NT>
-GCP_HDN void gcp2_stage_small(const GcpOp& op, float* WS) {
-  const int cols = hd_cols(op.hd), hdp = cols - 4;
-  GCP_PHASE_BEGIN(NT)
-  for (int idx = tid; idx < op.vi * cols; idx += NT) {
-    const int c = idx / cols, k = idx - c * cols;
-    float w = 0.f;
-    if (k < op.hd) w = GCP_LDG(op.Wd + k * op.vi + c);
-    else if (k >= hdp && k < hdp + 3) w = GCP_LDG(op.Wdf + (k - hdp) * op.vi + c);
-    WS[idx] = w;
+// dst (smem, row stride ldd) <- rows of a global matrix with `len` contiguous floats per row,
+// row index given by rowidx(e) (< 0: zero fill).
+template <int TE, int NT, class RowIdx>
+GCP_HD void tile_load_rows(float* dst, int ldd, const float* src, int len, RowIdx rowidx, int tid) {
+  const int lane = tid & 31;
+  for (int e = tid >> 5; e < TE; e += NT / 32) {
+    const long long r = rowidx(e);
+    const float* sp = src + (size_t)(r < 0 ? 0 : r) * len;
+    float* dp = dst + e * ldd;
+    for (int f = lane; f < len; f += 32) dp[f] = r >= 0 ? GCP_LDG(sp + f) : 0.f;
   }
-  float* WU = WS + op.vi * cols;
-  for (int idx = tid; idx < op.vo * hdp; idx += NT) {
-    const int o = idx / hdp, k = idx - o * hdp;
-    WU[idx] = (k < op.hd) ? GCP_LDG(op.Wu + o * op.hd + k) : 0.f;
-  }
-  GCP_PHASE_END
 }
-GCP_HD int gcp2_small_floats(int vi, int vo, int hd) { return vi * hd_cols(hd) + vo * (hd_cols(hd) - 4); }
+// global rows [row0 + e] (dense, len floats) <- smem rows, for e < nrows
+template <int TE, int NT>
+GCP_HD void tile_store_rows(float* dst, long long row0, int len, const float* src, int lds, int nrows, int tid) {
+  const int lane = tid & 31;
+  for (int e = tid >> 5; e < nrows; e += NT / 32) {
+    float* dp = dst + (size_t)(row0 + e) * len;
+    const float* sp = src + e * lds;
+    for (int f = lane; f < len; f += 32) dp[f] = sp[f];
+  }
+}
 
-// HD[e][x][:] = sum_c V[e][c][x] * WdT[c][:]     (vector_down + vector_down_frames, gcpnet.py:420,426)
-template <int TE, int NT, int COLS>
-GCP_HDN void gcp2_vec_down_impl(const GcpOp& op, const TileBufs& b) {
-  GCP_PHASE_BEGIN(NT)
-  for (int item = tid; item < 3 * TE; item += NT) {
-    const int x = item / TE, e = item - x * TE;
-    float acc[COLS];
-#pragma unroll
-    for (int k = 0; k < COLS; ++k) acc[k] = 0.f;
+// ------------------------------------------------------------------------------------------
+// GCP2 forward pieces
+// ------------------------------------------------------------------------------------------
+// HD[e][x][:] = sum_c V[e][c][x] * WdT[c][:]   (vector_down + vector_down_frames, gcpnet.py:420,426)
+// item = (e, x, 4-column group); WdT read from `wdt` (the S chunk in its ring slot).
+template <int TE, int NT>
+GCP_HD void gcp2_vec_down(const GcpOp& op, const TileBufs& b, const float* wdt, int tid) {
+  const int cols = op.w.cols, ng = cols >> 2;
+  for (int item = tid; item < 3 * TE * ng; item += NT) {
+    const int e = item % TE, r = item / TE;  // compile-time divisor
+    const int x = r % 3, g = r / 3;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const float* vp = b.V + e * b.ldv + x;
+    const float* w = wdt + 4 * g;
     for (int c = 0; c < op.vi; ++c) {
       const float v = vp[3 * c];
-      const float* w = b.WS + c * COLS;
-#pragma unroll
-      for (int k4 = 0; k4 < COLS; k4 += 4) {
-        const float4 wv = ld4(w + k4);
-        acc[k4 + 0] = fmaf(v, wv.x, acc[k4 + 0]);
-        acc[k4 + 1] = fmaf(v, wv.y, acc[k4 + 1]);
-        acc[k4 + 2] = fmaf(v, wv.z, acc[k4 + 2]);
-        acc[k4 + 3] = fmaf(v, wv.w, acc[k4 + 3]);
-      }
+      const float4 wv = ld4(w + c * cols);
+      acc.x = fmaf(v, wv.x, acc.x); acc.y = fmaf(v, wv.y, acc.y); acc.z = fmaf(v, wv.z, acc.z); acc.w = fmaf(v, wv.w, acc.w);
     }
-    float* hp = b.HD + e * b.ldhd + x * COLS;
-#pragma unroll
-    for (int k4 = 0; k4 < COLS; k4 += 4) st4(hp + k4, make_float4(acc[k4], acc[k4 + 1], acc[k4 + 2], acc[k4 + 3]));
-  }
-  GCP_PHASE_END
-}
-template <int TE, int NT>
-GCP_HDN void gcp2_vec_down(const GcpOp& op, const TileBufs& b) {
-  switch (hd_cols(op.hd)) {
-    case 8: gcp2_vec_down_impl<TE, NT, 8>(op, b); break;
-    case 12: gcp2_vec_down_impl<TE, NT, 12>(op, b); break;
-    case 16: gcp2_vec_down_impl<TE, NT, 16>(op, b); break;
-    default: gcp2_vec_down_impl<TE, NT, 20>(op, b); break;  // hd <= 16 (checked on the host)
+    st4(b.HD + e * b.ldhd + x * cols + 4 * g, acc);
   }
 }
 
-// norms (safe_norm over xyz, gcpnet.py:421) and frame scalars (scalarize, comp:302-312) -> Z[:, si:K)
+// norms (safe_norm over xyz, gcpnet.py:421) and frame scalars (scalarize, comp:302-312) -> Z[:, si:K);
+// columns [K, kpad) are zeroed (the GEMM reads them against zero weights).
 template <int TE, int NT>
-GCP_HDN void gcp2_norm_scalarize(const GcpOp& op, const TileBufs& b, int e3) {
-  const int cols = hd_cols(op.hd), hdp = cols - 4;
-  const int nq = op.hd + 9;
-  GCP_PHASE_BEGIN(NT)
-  for (int item = tid; item < TE * nq; item += NT) {
-    const int j = item / TE, e = item - j * TE;
+GCP_HD void gcp2_norm_scalarize(const GcpOp& op, const TileBufs& b, int e3, int tid) {
+  const int cols = op.w.cols, hdp = op.w.hdp;
+  const int nq = op.hd + 9, kpad = gcp_kpad(op), K = op.si + nq;
+  const int ncol = kpad - op.si;  // nq real columns + zero padding
+  for (int item = tid; item < TE * ncol; item += NT) {
+    const int e = item % TE, j = item / TE;
     const float* hp = b.HD + e * b.ldhd;
-    float val;
+    float val = 0.f;
     if (j < op.hd) {
       const float a = hp[j], bb = hp[cols + j], c = hp[2 * cols + j];
       val = sqrtf(fmaf(a, a, fmaf(bb, bb, c * c)) + SAFE_NORM_EPS) + SAFE_NORM_EPS;
-    } else {
-      const int cc = (j - op.hd) / 3, a = (j - op.hd) - 3 * cc;  // q[3*cc + a]
+    } else if (j < nq) {
+      const int q = j - op.hd;
+      const int cc = q / 3, a = q - 3 * cc;  // q[3*cc + a]
       const float* f = b.F + e * LDF + 3 * a;
       val = f[0] * hp[hdp + cc];
       val = fmaf(f[1], hp[cols + hdp + cc], val);
@@ -404,46 +446,131 @@ GCP_HDN void gcp2_norm_scalarize(const GcpOp& op, const TileBufs& b, int e3) {
     }
     b.Z[e * b.ldz + op.si + j] = val;
   }
-  {  // zero the float4 padding columns [K, round_up(K,4)) (K differs between GCPs sharing Z)
-    const int K = op.si + nq, padn = round_up(K, 4) - K;
-    for (int item = tid; item < TE * padn; item += NT) {
-      const int e = item / padn;
-      b.Z[e * b.ldz + K + (item - e * padn)] = 0.f;
-    }
-  }
-  GCP_PHASE_END
-}
-
-// Full GCP2 forward up to (T, SG): caller then reads act_s(T) and gcp2_vec_out().
-// OGm/NRm: micro-tile grid of the scalar_out GEMM; the gate GEMM uses (OGg, 1).
-template <int TE, int NT, int OGm, int NRm, int OGg>
-GCP_HDN void gcp2_fwd_tile(const GcpOp& op, const TileBufs& b, int e3, float slope) {
-  gcp2_stage_small<NT>(op, b.WS);
-  gcp2_vec_down<TE, NT>(op, b);
-  gcp2_norm_scalarize<TE, NT>(op, b, e3);
-  float* T = b.T; const int ldt = b.ldt;
-  tile_gemm_nmajor<TE, NT, OGm, NRm>(b.Z, b.ldz, gcp_k(op), op.Ws, op.so, op.bs, b.WC, b.wc_cap, T, ldt, XIdentity(),
-                                     [=](int e, int n, float v) { T[e * ldt + n] = v; });
-  if (op.vo > 0) {
-    float* SG = b.SG; const int ldsg = b.ldsg;
-    // gate reads the PRE-activation scalars through act_v (gcpnet.py:386)
-    tile_gemm_nmajor<TE, NT, OGg, 1>(T, ldt, op.so, op.Wg, op.vo, op.bg, b.WC, b.wc_cap, SG, ldsg, XAct{op.act_v, slope},
-                                     [=](int e, int n, float v) { SG[e * ldsg + n] = sigmoidf_(v); });
-  }
+  (void)K;
 }
 
 // Ungated vector output U[e][o][x] = sum_k H[e][x][k] * Wu[o][k] (+ V_in[e][o][x] if vector_residual)
-GCP_HD float gcp2_vec_up(const GcpOp& op, const TileBufs& b, int e, int o, int x) {
-  const int cols = hd_cols(op.hd), hdp = cols - 4;
+GCP_HD float gcp2_vec_up(const GcpOp& op, const TileBufs& b, const float* wu, int e, int o, int x) {
+  const int cols = op.w.cols, hdp = op.w.hdp;
   const float* hp = b.HD + e * b.ldhd + x * cols;
-  const float* wu = b.WS + op.vi * cols + o * hdp;
+  const float* w = wu + o * hdp;
   float u = 0.f;
   for (int k4 = 0; k4 < hdp; k4 += 4) {
-    const float4 h = ld4(hp + k4), w = ld4(wu + k4);
-    u = fmaf(h.x, w.x, u); u = fmaf(h.y, w.y, u); u = fmaf(h.z, w.z, u); u = fmaf(h.w, w.w, u);
+    const float4 h = ld4(hp + k4), ww = ld4(w + k4);
+    u = fmaf(h.x, ww.x, u); u = fmaf(h.y, ww.y, u); u = fmaf(h.z, ww.z, u); u = fmaf(h.w, ww.w, u);
   }
   if (op.vres) u += b.V[e * b.ldv + 3 * o + x];
   return u;
+}
+
+// GCP2 forward up to (T, SG).  On return the G chunk is still the ring's head (the caller reads
+// WU from it in its update phase, then releases it with gcp2_fwd_finish()).
+// Phases: [vec_down] [norm+scalarize] [GEMM chunk]* [gate].
+template <int TE, int NT, int SL>
+GCP_HDN const float* gcp2_fwd_tile(const GcpOp& op, const TileBufs& b, WPipe& wp, int e3, float slope, bool refill_first) {
+  const GcpW& W = op.w;
+  // ---- S chunk: vector_down / vector_down_frames
+  GCP_PHASE_BEGIN(NT)
+  if (refill_first) wpipe_refill(wp, wp.head - 1, tid);  // slot freed by the caller's previous phase
+  const float* wdt = wpipe_wait(wp);
+  gcp2_vec_down<TE, NT>(op, b, wdt, tid);
+  GCP_PHASE_END
+  wp.head++;
+  GCP_PHASE_BEGIN(NT)
+  wpipe_refill(wp, wp.head - 1, tid);
+  gcp2_norm_scalarize<TE, NT>(op, b, e3, tid);
+  GCP_PHASE_END
+  // ---- scalar_out: T = Z * Ws^T + bs, K-chunked, accumulators stay in registers across chunks
+  {
+    float* T = b.T; const int ldt = b.ldt;
+    const int nslices = W.NP >> 4;
+#if GCP_DEVICE_CODE
+    float acc[SL][2][4];
+    const GemmMap<TE, NT> m((int)threadIdx.x);
+    for (int c = 0; c < W.nWS; ++c) {
+      if (c > 0) wpipe_refill(wp, wp.head - 1, (int)threadIdx.x);
+      const float* wc = wpipe_wait(wp);
+      if (c == 0) {
+        const float* bias = wc + W.NP * W.ldk;
+#pragma unroll
+        for (int i = 0; i < SL; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int n = 16 * (m.wn + GemmMap<TE, NT>::WN * i) + m.og + 4 * j;
+            acc[i][0][j] = acc[i][1][j] = (n < W.NP) ? bias[n] : 0.f;
+          }
+      }
+      gemm_nmajor_chunk<TE, NT, SL>(acc, b.Z, b.ldz, c * W.kc, W.kc, wc, W.ldk, nslices, m, XIdentity());
+      if (c == W.nWS - 1) {
+#pragma unroll
+        for (int i = 0; i < SL; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int n = 16 * (m.wn + GemmMap<TE, NT>::WN * i) + m.og + 4 * j;
+            if (n < op.so) { T[m.e0 * ldt + n] = acc[i][0][j]; T[(m.e0 + 8) * ldt + n] = acc[i][1][j]; }
+          }
+      }
+      __syncthreads();
+      wp.head++;
+    }
+#else
+    // host emulation: per-thread accumulators cannot live across phases -> park them in a scratch array
+    static thread_local float accs[1024][SL][2][4];
+    for (int c = 0; c < W.nWS; ++c) {
+      GCP_PHASE_BEGIN(NT)
+      if (c > 0) wpipe_refill(wp, wp.head - 1, tid);
+      const float* wc = wpipe_wait(wp);
+      const GemmMap<TE, NT> m(tid);
+      float (&acc)[SL][2][4] = accs[tid];
+      if (c == 0) {
+        const float* bias = wc + W.NP * W.ldk;
+        for (int i = 0; i < SL; ++i)
+          for (int j = 0; j < 4; ++j) {
+            const int n = 16 * (m.wn + GemmMap<TE, NT>::WN * i) + m.og + 4 * j;
+            acc[i][0][j] = acc[i][1][j] = (n < W.NP) ? bias[n] : 0.f;
+          }
+      }
+      gemm_nmajor_chunk<TE, NT, SL>(acc, b.Z, b.ldz, c * W.kc, W.kc, wc, W.ldk, nslices, m, XIdentity());
+      if (c == W.nWS - 1) {
+        for (int i = 0; i < SL; ++i)
+          for (int j = 0; j < 4; ++j) {
+            const int n = 16 * (m.wn + GemmMap<TE, NT>::WN * i) + m.og + 4 * j;
+            if (n < op.so) { T[m.e0 * ldt + n] = acc[i][0][j]; T[(m.e0 + 8) * ldt + n] = acc[i][1][j]; }
+          }
+      }
+      GCP_PHASE_END
+      wp.head++;
+    }
+#endif
+  }
+  // ---- gate: SG = sigmoid(act_v(T) * Wg^T + bg)   (reads the PRE-activation scalars, gcpnet.py:386)
+  const float* gch = nullptr;
+  GCP_PHASE_BEGIN(NT)
+  wpipe_refill(wp, wp.head - 1, tid);
+  const float* g = wpipe_wait(wp);
+  const XAct xa{op.act_v, slope};
+  // thread = (e, o-group): e = tid % TE, o = tid / TE + (NT/TE) * j
+  const int e = tid % TE;
+  const float* tp = b.T + e * b.ldt;
+  for (int o0 = tid / TE; o0 < op.vo; o0 += 2 * (NT / TE)) {
+    const int o1 = o0 + NT / TE;
+    const bool has1 = o1 < op.vo;
+    const float* w0 = g + o0 * W.ldg;
+    const float* w1 = g + (has1 ? o1 : o0) * W.ldg;
+    float a0 = g[W.o_bg + o0], a1 = has1 ? g[W.o_bg + o1] : 0.f;
+    for (int k4 = 0; k4 < op.so; k4 += 4) {
+      float4 t = ld4(tp + k4);
+      t.x = xa(t.x); t.y = xa(t.y); t.z = xa(t.z); t.w = xa(t.w);
+      const float4 u = ld4(w0 + k4), v = ld4(w1 + k4);
+      a0 = fmaf(t.x, u.x, a0); a0 = fmaf(t.y, u.y, a0); a0 = fmaf(t.z, u.z, a0); a0 = fmaf(t.w, u.w, a0);
+      a1 = fmaf(t.x, v.x, a1); a1 = fmaf(t.y, v.y, a1); a1 = fmaf(t.z, v.z, a1); a1 = fmaf(t.w, v.w, a1);
+    }
+    b.SG[e * b.ldsg + o0] = sigmoidf_(a0);
+    if (has1) b.SG[e * b.ldsg + o1] = sigmoidf_(a1);
+  }
+  GCP_PHASE_END
+  gch = wp.slots + (size_t)(wp.head % wp.seq->nslot) * wp.seq->slot_floats;
+  return gch;  // G chunk (WG | bg | WU), still held
 }
 
 // ------------------------------------------------------------------------------------------
@@ -461,123 +588,139 @@ struct BwdBufs {
 // Backward of one GCP2 on a tile.  On entry: b.Z[:, :si], b.V, b.F hold the forward inputs, b.T the
 // saved pre-activations, b.SG the saved gates, g.GS / g.GV the output cotangents (rows >= nrows zero).
 // The routine recomputes HD, norms and frame scalars, then produces
-//   * scalar input cotangent: emitted column by column through `emit_s(e, i, value)` (i < si)
+//   * scalar input cotangent: emitted through `emit_s(e, i, value)` (i < si)
 //   * vector input cotangent: emitted through `emit_v(e, c3, value)` (c3 < 3*vi)
 //   * weight-gradient partials into prow[op.o_*]  (accumulate: += instead of =)
-// b.T is overwritten with the cotangent of the pre-activation.
-template <int TE, int NT, int OGm, int NRm, int OGd, int NRd, class EmitS, class EmitV>
-GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g, int e3, float slope,
-                           float* prow, bool accumulate, EmitS emit_s, EmitV emit_v) {
-  const int cols = hd_cols(op.hd), hdp = cols - 4;
+// b.T is overwritten with the cotangent of the pre-activation.  Ring order: S, G, WS chunks.
+// `refill_first`: the caller's previous phase released the chunk at head-1.
+template <int TE, int NT, int SLF, int SLD, class EmitS, class EmitV>
+GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g, WPipe& wp, int e3, float slope,
+                           float* prow, bool accumulate, bool refill_first, EmitS emit_s, EmitV emit_v) {
+  const GcpW& W = op.w;
+  const int cols = W.cols, hdp = W.hdp;
   const int K = gcp_k(op);
-  gcp2_stage_small<NT>(op, b.WS);
-  gcp2_vec_down<TE, NT>(op, b);
-  gcp2_norm_scalarize<TE, NT>(op, b, e3);
-  float* T = b.T; const int ldt = b.ldt;
-  if (op.vo > 0) {
-    // gate backward: gU = gV' * sg ; gsig = sum_x gV' * U ; gg = gsig * sg * (1 - sg)
-    GCP_PHASE_BEGIN(NT)
-    for (int item = tid; item < TE * op.vo; item += NT) {
-      const int e = item / op.vo, o = item - e * op.vo;
-      const float sg = b.SG[e * b.ldsg + o];
-      float gsig = 0.f;
-#pragma unroll
-      for (int x = 0; x < 3; ++x) {
-        const float gv = g.GV[e * g.ldgv + 3 * o + x];
-        gsig = fmaf(gv, gcp2_vec_up(op, b, e, o, x), gsig);
-        g.GU[e * g.ldgu + 3 * o + x] = gv * sg;
-      }
-      g.GG[e * g.ldgg + o] = gsig * sg * (1.f - sg);
-    }
-    // zero the float4 padding columns of GG so the wgrad's 4-wide reads see zeros
-    for (int item = tid; item < TE * (round_up(op.vo, 4) - op.vo); item += NT) {
-      const int padn = round_up(op.vo, 4) - op.vo;
-      const int e = item / padn, o = op.vo + item - e * padn;
-      g.GG[e * g.ldgg + o] = 0.f;
-    }
-    GCP_PHASE_END
-    // vector_out_scale weight gradient (input of that Linear is act_v(T), T still pre-activation here)
-    tile_wgrad<TE, NT>(g.GG, g.ldgg, op.vo, T, ldt, op.so, prow + op.o_Wg, prow + op.o_bg, accumulate, XAct{op.act_v, slope});
-    // vector_up weight gradient: gWu[o][k] = sum_{e,x} gU[e][o][x] * H[e][x][k]
-    GCP_PHASE_BEGIN(NT)
-    for (int item = tid; item < op.vo * op.hd; item += NT) {
-      const int o = item / op.hd, k = item - o * op.hd;
-      float s = 0.f;
-      for (int e = 0; e < TE; ++e) {
-        const float* hp = b.HD + e * b.ldhd + k;
-        const float* gu = g.GU + e * g.ldgu + 3 * o;
-        s = fmaf(gu[0], hp[0], s); s = fmaf(gu[1], hp[cols], s); s = fmaf(gu[2], hp[2 * cols], s);
-      }
-      float* dst = prow + op.o_Wu + item;
-      *dst = (accumulate ? *dst : 0.f) + s;
-    }
-    GCP_PHASE_END
-  }
-  // cotangent of the pre-activation: gT = gS' * act_s'(T) + act_v'(T) * (Wg^T gg)
-  {
-    const int as = op.act_s, av = op.act_v;
-    float* GS = g.GS; const int ldgs = g.ldgs;
-    if (op.vo > 0) {
-      // T <- gT in place through the small k-major GEMM (K = vo)
-      // (each thread reads T[e][n] only for the (e, n) it then overwrites)
-      const int vo4 = round_up(op.vo, 4);
-      (void)vo4;
-      tile_gemm_kmajor<TE, NT, OGd, NRd>(g.GG, g.ldgg, op.vo, op.Wg, op.so, b.WC, b.wc_cap, nullptr, 0,
-                                         [=](int e, int n, float v) {
-                                           const float t = T[e * ldt + n];
-                                           T[e * ldt + n] = fmaf(GS[e * ldgs + n], act_grad(as, t, slope), v * act_grad(av, t, slope));
-                                         });
-    } else {
-      GCP_PHASE_BEGIN(NT)
-      for (int item = tid; item < TE * op.so; item += NT) {
-        const int e = item / op.so, n = item - e * op.so;
-        const float t = T[e * ldt + n];
-        T[e * ldt + n] = GS[e * ldgs + n] * act_grad(as, t, slope);
-      }
-      GCP_PHASE_END
-    }
-    // zero T's float4 padding columns for the wgrad reads
-    GCP_PHASE_BEGIN(NT)
-    const int padn = round_up(op.so, 4) - op.so;
-    for (int item = tid; item < TE * padn; item += NT) {
-      const int e = item / padn, n = op.so + item - e * padn;
-      T[e * ldt + n] = 0.f;
-    }
-    GCP_PHASE_END
-  }
-  // scalar_out weight gradient
-  tile_wgrad<TE, NT>(T, ldt, op.so, b.Z, b.ldz, K, prow + op.o_Ws, prow + op.o_bs, accumulate, XIdentity());
-  // data gradient through scalar_out: gz = gT * Ws ; columns < si go to the caller, the rest to GNQ
-  {
-    float* GNQ = g.GNQ; const int ldnq = g.ldnq; const int si = op.si;
-    tile_gemm_kmajor<TE, NT, OGd, NRd>(T, ldt, op.so, op.Ws, K, b.WC, b.wc_cap, nullptr, 0,
-                                       [=](int e, int n, float v) {
-                                         if (n < si) emit_s(e, n, v);
-                                         else GNQ[e * ldnq + (n - si)] = v;
-                                       });
-  }
-  // gHD: norms, vector_up and frame scalars back to the hidden vector channels
+  float* wdt_sm = b.WSM;                    // [vi][cols]
+  float* wu_sm = b.WSM + op.vi * cols;      // [vo][hdp]
+  constexpr int IW = (NT <= 256) ? 8 : 4;
+  (void)hdp;
+  // ---- recompute: vector_down (S chunk; keep WdT for the final phases)
   GCP_PHASE_BEGIN(NT)
-  for (int item = tid; item < 3 * TE; item += NT) {
-    const int x = item / TE, e = item - x * TE;
-    const float* hp = b.HD + e * b.ldhd;
-    float* ghp = g.GHD + e * g.ldghd + x * cols;
-    const float* gnq = g.GNQ + e * g.ldnq;
-    for (int k = 0; k < hdp; ++k) {
-      float acc = 0.f;
-      if (k < op.hd) {
-        // n = sqrt(sum_x H^2 + eps) + eps  ->  dn/dH[x] = H[x] / (n - eps)
-        const float a = hp[k], bb = hp[cols + k], c = hp[2 * cols + k];
-        const float root = sqrtf(fmaf(a, a, fmaf(bb, bb, c * c)) + SAFE_NORM_EPS);
-        acc = gnq[k] * hp[x * cols + k] / root;
-        for (int o = 0; o < op.vo; ++o)
-          acc = fmaf(g.GU[e * g.ldgu + 3 * o + x], b.WS[op.vi * cols + o * hdp + k], acc);
-      }
-      ghp[k] = acc;
+  if (refill_first) wpipe_refill(wp, wp.head - 1, tid);
+  const float* wdt = wpipe_wait(wp);
+  gcp2_vec_down<TE, NT>(op, b, wdt, tid);
+  for (int i = tid; i < op.vi * cols; i += NT) wdt_sm[i] = wdt[i];
+  GCP_PHASE_END
+  wp.head++;
+  GCP_PHASE_BEGIN(NT)
+  wpipe_refill(wp, wp.head - 1, tid);
+  gcp2_norm_scalarize<TE, NT>(op, b, e3, tid);
+  GCP_PHASE_END
+  float* T = b.T; const int ldt = b.ldt;
+  // ---- gate backward (G chunk): gU = gV' * sg ; gsig = sum_x gV' * U ; gg = gsig * sg * (1 - sg)
+  GCP_PHASE_BEGIN(NT)
+  const float* gc = wpipe_wait(wp);
+  const float* wu = gc + W.o_wu;
+  for (int i = tid; i < op.vo * hdp; i += NT) wu_sm[i] = wu[i];
+  const int e = tid % TE;
+  for (int o = tid / TE; o < op.vo; o += NT / TE) {
+    const float sg = b.SG[e * b.ldsg + o];
+    float gsig = 0.f;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+      const float gv = g.GV[e * g.ldgv + 3 * o + x];
+      gsig = fmaf(gv, gcp2_vec_up(op, b, wu, e, o, x), gsig);
+      g.GU[e * g.ldgu + 3 * o + x] = gv * sg;
     }
-    // frame scalars: q[3cc+a] = sum_x F[a][x] D[x][cc]  (|.| on a==1 when e3)
-    for (int cc = 0; cc < 3; ++cc) {
-      float acc = 0.f;
+    g.GG[e * g.ldgg + o] = gsig * sg * (1.f - sg);
+  }
+  // zero the float4 padding columns of GG so the 4-wide reads below see zeros
+  for (int o = op.vo + tid / TE; o < round_up(op.vo, 4); o += NT / TE) g.GG[e * g.ldgg + o] = 0.f;
+  GCP_PHASE_END
+  // ---- vector_out_scale / vector_up weight gradients (read ALL of T = pre-activations: own phase)
+  GCP_PHASE_BEGIN(NT)
+  tile_wgrad<TE, NT, 1, 4>(g.GG, g.ldgg, op.vo, T, ldt, op.so, prow + op.o_Wg, prow + op.o_bg, accumulate,
+                           XAct{op.act_v, slope}, tid);
+  // gWu[o][k] = sum_{e,x} gU[e][o][x] * H[e][x][k]
+  for (int item = tid; item < op.vo * op.hd; item += NT) {
+    const int o = item / op.hd, k = item - o * op.hd;
+    float s = 0.f;
+    for (int e = 0; e < TE; ++e) {
+      const float* hp = b.HD + e * b.ldhd + k;
+      const float* gu = g.GU + e * g.ldgu + 3 * o;
+      s = fmaf(gu[0], hp[0], s); s = fmaf(gu[1], hp[cols], s); s = fmaf(gu[2], hp[2 * cols], s);
+    }
+    float* dst = prow + op.o_Wu + item;
+    *dst = (accumulate ? *dst : 0.f) + s;
+  }
+  GCP_PHASE_END
+  // ---- cotangent of the pre-activation: gT = gS' * act_s'(T) + act_v'(T) * (gg * Wg)   (T <- gT in place;
+  //      every thread reads only the T entries it overwrites)
+  GCP_PHASE_BEGIN(NT)
+  const float* gc = wp.slots + (size_t)(wp.head % wp.seq->nslot) * wp.seq->slot_floats;
+  const GemmMap<TE, NT> m(tid);
+  float acc[SLF][2][4];
+  gemm_kmajor_chunk<TE, NT, SLF>(acc, g.GG, g.ldgg, round_up(op.vo, 4), gc, W.ldg, (op.so + 15) >> 4, m);
+  const int as = op.act_s, av = op.act_v;
+#pragma unroll
+  for (int i = 0; i < SLF; ++i)
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int n = 16 * (m.wn + GemmMap<TE, NT>::WN * i) + 4 * m.og + c;
+        const int e = m.e0 + 8 * r;
+        if (n < op.so) {
+          const float t = T[e * ldt + n];
+          T[e * ldt + n] = fmaf(g.GS[e * g.ldgs + n], act_grad(as, t, slope), acc[i][r][c] * act_grad(av, t, slope));
+        }
+      }
+  GCP_PHASE_END
+  wp.head++;  // G chunk released
+  // ---- scalar_out: weight gradient + data gradient gz = gT * Ws (WS chunks, k-major view)
+  for (int c = 0; c < W.nWS; ++c) {
+    GCP_PHASE_BEGIN(NT)
+    wpipe_refill(wp, wp.head - 1, tid);
+    const float* wc = wpipe_wait(wp);
+    if (c == 0)
+      tile_wgrad<TE, NT, 4, IW>(T, ldt, op.so, b.Z, b.ldz, K, prow + op.o_Ws, prow + op.o_bs, accumulate, XIdentity(), tid);
+    const GemmMap<TE, NT> m(tid);
+    float acc[SLD][2][4];
+    gemm_kmajor_chunk<TE, NT, SLD>(acc, T, ldt, round_up(op.so, 4), wc, W.ldk, W.kc >> 4, m);
+#pragma unroll
+    for (int i = 0; i < SLD; ++i)
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int il = 16 * (m.wn + GemmMap<TE, NT>::WN * i) + 4 * m.og + cc;
+          const int col = c * W.kc + il;
+          const int e = m.e0 + 8 * r;
+          if (il < W.kc && col < K) {
+            if (col < op.si) emit_s(e, col, acc[i][r][cc]);
+            else g.GNQ[e * g.ldnq + (col - op.si)] = acc[i][r][cc];
+          }
+        }
+    GCP_PHASE_END
+    wp.head++;
+  }
+  // ---- gHD: norms, vector_up and frame scalars back to the hidden vector channels
+  GCP_PHASE_BEGIN(NT)
+  wpipe_refill(wp, wp.head - 1, tid);
+  for (int item = tid; item < 3 * TE * cols; item += NT) {
+    const int e = item % TE, r = item / TE;  // compile-time divisors
+    const int x = r % 3, kk = r / 3;         // kk < cols: hidden column
+    const float* hp = b.HD + e * b.ldhd;
+    const float* gnq = g.GNQ + e * g.ldnq;
+    float acc = 0.f;
+    if (kk < op.hd) {
+      // n = sqrt(sum_x H^2 + eps) + eps  ->  dn/dH[x] = H[x] / (n - eps)
+      const float a = hp[kk], bb = hp[cols + kk], c = hp[2 * cols + kk];
+      const float root = sqrtf(fmaf(a, a, fmaf(bb, bb, c * c)) + SAFE_NORM_EPS);
+      acc = gnq[kk] * hp[x * cols + kk] / root;
+      for (int o = 0; o < op.vo; ++o) acc = fmaf(g.GU[e * g.ldgu + 3 * o + x], wu_sm[o * hdp + kk], acc);
+    } else if (kk >= hdp && kk < hdp + 3) {
+      // frame scalars: q[3cc+a] = sum_x F[a][x] D[x][cc]  (|.| on a==1 when e3)
+      const int cc = kk - hdp;
       for (int a = 0; a < 3; ++a) {
         float gq = gnq[op.hd + 3 * cc + a];
         if (e3 && a == 1) {
@@ -589,13 +732,13 @@ GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g,
         }
         acc = fmaf(b.F[e * LDF + 3 * a + x], gq, acc);
       }
-      ghp[hdp + cc] = acc;
     }
-    ghp[hdp + 3] = 0.f;
+    g.GHD[e * g.ldghd + x * cols + kk] = acc;
   }
   GCP_PHASE_END
-  // vector_down / vector_down_frames weight gradients: gWdT[c][k] = sum_{e,x} gHD[e][x][k] * V[e][c][x]
+  // ---- vector_down / vector_down_frames weight gradients; vector input cotangent
   GCP_PHASE_BEGIN(NT)
+  // gWdT[c][k] = sum_{e,x} gHD[e][x][k] * V[e][c][x]
   for (int item = tid; item < op.vi * (op.hd + 3); item += NT) {
     const int kk = item / op.vi, c = item - kk * op.vi;  // kk < hd: Wd row kk ; else Wdf row kk-hd
     const int col = kk < op.hd ? kk : hdp + (kk - op.hd);
@@ -608,45 +751,25 @@ GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g,
     float* dst = kk < op.hd ? prow + op.o_Wd + kk * op.vi + c : prow + op.o_Wdf + (kk - op.hd) * op.vi + c;
     *dst = (accumulate ? *dst : 0.f) + s;
   }
-  GCP_PHASE_END
-  // vector input cotangent: gV[e][c][x] = sum_k gHD[e][x][k] * WdT[c][k] (+ gU[e][c][x] if vector_residual)
-  GCP_PHASE_BEGIN(NT)
-  for (int item = tid; item < TE * op.vi; item += NT) {
-    const int e = item / op.vi, c = item - e * op.vi;
-    const float* w = b.WS + c * cols;
+  // gV[e][c][x] = sum_k gHD[e][x][k] * WdT[c][k] (+ gU[e][c][x] if vector_residual)
+  {
+    const int e = tid % TE;
+    for (int c = tid / TE; c < op.vi; c += NT / TE) {
+      const float* w = wdt_sm + c * cols;
 #pragma unroll
-    for (int x = 0; x < 3; ++x) {
-      const float* ghp = g.GHD + e * g.ldghd + x * cols;
-      float acc = 0.f;
-      for (int k4 = 0; k4 < cols; k4 += 4) {
-        const float4 gv = ld4(ghp + k4), wv = ld4(w + k4);
-        acc = fmaf(gv.x, wv.x, acc); acc = fmaf(gv.y, wv.y, acc); acc = fmaf(gv.z, wv.z, acc); acc = fmaf(gv.w, wv.w, acc);
+      for (int x = 0; x < 3; ++x) {
+        const float* ghp = g.GHD + e * g.ldghd + x * cols;
+        float acc = 0.f;
+        for (int k4 = 0; k4 < cols; k4 += 4) {
+          const float4 gv = ld4(ghp + k4), wv = ld4(w + k4);
+          acc = fmaf(gv.x, wv.x, acc); acc = fmaf(gv.y, wv.y, acc); acc = fmaf(gv.z, wv.z, acc); acc = fmaf(gv.w, wv.w, acc);
+        }
+        if (op.vres && op.vo > 0) acc += g.GU[e * g.ldgu + 3 * c + x];
+        emit_v(e, 3 * c + x, acc);
       }
-      if (op.vres && op.vo > 0) acc += g.GU[e * g.ldgu + 3 * c + x];
-      emit_v(e, 3 * c + x, acc);
     }
   }
   GCP_PHASE_END
-}
-
-// cooperative row copy helpers ----------------------------------------------------------------
-// dst (smem, row stride ldd) <- rows of a global matrix with `len` contiguous floats per row,
-// row index given by idx(e) (< 0: zero fill).
-template <int TE, int NT, class RowIdx>
-GCP_HD void tile_load_rows(float* dst, int ldd, const float* src, int len, RowIdx rowidx, int tid) {
-  for (int item = tid; item < TE * len; item += NT) {
-    const int e = item / len, f = item - e * len;
-    const long long r = rowidx(e);
-    dst[e * ldd + f] = r >= 0 ? GCP_LDG(src + (size_t)r * len + f) : 0.f;
-  }
-}
-// global rows [row0 + e] (dense, len floats) <- smem rows, for e < nrows
-template <int TE, int NT>
-GCP_HD void tile_store_rows(float* dst, long long row0, int len, const float* src, int lds, int nrows, int tid) {
-  for (int item = tid; item < nrows * len; item += NT) {
-    const int e = item / len, f = item - e * len;
-    dst[(size_t)(row0 + e) * len + f] = src[e * lds + f];
-  }
 }
 
 }  // namespace gcp

@@ -1,19 +1,23 @@
 // layer_setup.h -- host-side translation of the C-ABI descriptors (include/gcpnet_b200.h) into the
-// kernel parameter blocks, plus tile / shared-memory planning.  Shared by the CUDA launchers
-// (api.cu) and by the CPU emulation used in the non-GPU tests (tests/emul/emul.cu).
+// kernel parameter blocks: packed-weight layout, chunk sequences of the shared-memory weight ring,
+// tile / shared-memory planning.  Shared by the CUDA launchers (api.cu) and by the CPU emulation used
+// in the non-GPU tests (tests/emul/emul.cu).
 #pragma once
 #include <string>
 
 #include "../../include/gcpnet_b200.h"
 #include "edge_kernels.cuh"
 #include "node_kernels.cuh"
+#include "pack.cuh"
 
 namespace gcp {
 
-constexpr int EDGE_NT = 128;
-constexpr int NODE_NT = 128;
 constexpr int SMEM_LIMIT_BYTES = 227 * 1024;
-constexpr int MAX_PERSISTENT_CTAS = 148 * 2;
+constexpr int NUM_SMS = 148;                 // B200
+constexpr int EDGE_CAP_FLOATS = 8192;        // largest weight chunk of the edge kernels (32 KB ring slot)
+constexpr int NODE_CAP_FLOATS = 16384;       // node kernels: wide feed-forward layers (64 KB ring slot)
+constexpr int NODE_TE = 16, NODE_NT = 256;   // 16 threads per node
+constexpr int EDGE_SLD = 2, NODE_SLD = 2;
 
 inline GcpOp to_op(const gcpnet_gcp2& d, int grad_base) {
   GcpOp o{};
@@ -29,7 +33,8 @@ inline GcpOp to_op(const gcpnet_gcp2& d, int grad_base) {
 
 inline std::string check_gcp2(const gcpnet_gcp2& d, const char* name) {
   auto err = [&](const std::string& m) { return std::string(name) + ": " + m; };
-  if (d.si <= 0 || d.vi <= 0 || d.so <= 0 || d.vo < 0) return err("dims must be positive");
+  if (d.si <= 0 || d.vi <= 0 || d.so <= 0 || d.vo <= 0) return err("dims must be positive");
+  if (d.so % 4 != 0) return err("scalar output dims must be multiples of 4 in this build");
   if (d.hd <= 0 || d.hd > 16) return err("hidden vector dim must be in [1,16] (bottleneck too small for this build)");
   if (d.vector_residual && d.vi != d.vo) return err("vector_residual needs vi == vo");
   if (d.act_s < 0 || d.act_s > 5 || d.act_v < 0 || d.act_v > 5) return err("unknown nonlinearity");
@@ -39,6 +44,7 @@ inline std::string check_gcp2(const gcpnet_gcp2& d, const char* name) {
 inline std::string check_layer(const gcpnet_layer& l) {
   if (l.num_message_layers < 1 || l.num_message_layers > GCPNET_MAX_MESSAGE_LAYERS) return "num_message_layers out of range";
   if (l.s <= 0 || l.v <= 0 || l.se <= 0 || l.ve <= 0) return "layer dims must be positive";
+  if (l.s % 4 != 0) return "node scalar dim must be a multiple of 4 in this build";
   for (int k = 0; k < l.num_message_layers; ++k) {
     const gcpnet_gcp2& g = l.message[k];
     std::string e = check_gcp2(g, "message_fusion");
@@ -63,32 +69,86 @@ inline std::string check_layer(const gcpnet_layer& l) {
   return "";
 }
 
+// ---- packed-weight layout ------------------------------------------------------------------------
+// Fills op.w (chunk sizes and strides) and assigns blob offsets starting at *cursor.
+inline std::string plan_gcp_pack(GcpOp& op, int cap_floats, int* cursor) {
+  GcpW& W = op.w;
+  W.cols = hd_cols(op.hd); W.hdp = W.cols - 4;
+  W.NP = round_up(op.so, 16);
+  const int K = gcp_k(op);
+  int kc_max = 0;
+  for (int kc = 16; kc <= 128; kc += 16)
+    if (W.NP * ld_vec(kc) + W.NP <= cap_floats) kc_max = kc;
+  if (kc_max == 0) return "scalar_out is too wide for a weight-ring slot of this build";
+  W.nWS = (K + kc_max - 1) / kc_max;
+  if (W.nWS > MAX_WS_CHUNKS) return "scalar_out has too many input columns for this build";
+  W.kc = round_up((K + W.nWS - 1) / W.nWS, 16);
+  W.ldk = ld_vec(W.kc);
+  W.ldg = ld_vec(op.so);
+  W.o_bg = round_up(op.vo, 4) * W.ldg;  // zero rows up to a multiple of 4: read by the 4-deep k loop of the gT GEMM
+  W.o_wu = W.o_bg + round_up(op.vo, 4);
+  auto take = [&](int floats) { WChunk c; c.off = *cursor; c.floats = round_up(floats, 4); *cursor += round_up(c.floats, 32); return c; };
+  W.S = take(op.vi * W.cols);
+  W.ws_floats = round_up(W.NP * W.ldk + W.NP, 4);
+  W.ws_stride = round_up(W.ws_floats, 32);
+  W.ws_off = *cursor; *cursor += W.nWS * W.ws_stride;
+  W.G = take(W.o_wu + op.vo * W.hdp);
+  if (W.G.floats > cap_floats) return "vector_out_scale is too wide for a weight-ring slot of this build";
+  return "";
+}
+
+inline void seq_push(WSeq& q, const WChunk& c) { q.c[q.n++] = c; if (c.floats > q.slot_floats) q.slot_floats = c.floats; }
+inline WChunk ws_chunk(const GcpOp& op, int c) { WChunk k; k.off = op.w.ws_off + c * op.w.ws_stride; k.floats = op.w.ws_floats; return k; }
+inline void seq_fwd(WSeq& q, const GcpOp& op) {
+  seq_push(q, op.w.S);
+  for (int c = 0; c < op.w.nWS; ++c) seq_push(q, ws_chunk(op, c));
+  seq_push(q, op.w.G);
+}
+inline void seq_bwd(WSeq& q, const GcpOp& op) {
+  seq_push(q, op.w.S);
+  seq_push(q, op.w.G);
+  for (int c = 0; c < op.w.nWS; ++c) seq_push(q, ws_chunk(op, c));
+}
+
 struct LayerOps {
   GcpOp msg[MAX_MSG_LAYERS];
   GcpOp ff0, ff1, pu;
+  int L, has_pos;
+  int packed_floats;
+  WSeq edge_fwd, edge_bwd, node_fwd, node_bwd;
+  std::string error;
 };
-inline LayerOps layer_ops(const gcpnet_layer& l) {
+inline LayerOps layer_ops(const gcpnet_layer& l, int edge_cap = EDGE_CAP_FLOATS, int node_cap = NODE_CAP_FLOATS) {
   LayerOps o{};
-  for (int k = 0; k < l.num_message_layers; ++k) o.msg[k] = to_op(l.message[k], 0);
-  o.ff0 = to_op(l.ff0, l.n_edge_params);
-  o.ff1 = to_op(l.ff1, l.n_edge_params);
-  if (l.has_pos) o.pu = to_op(l.pos_update, l.n_edge_params);
+  o.L = l.num_message_layers; o.has_pos = l.has_pos;
+  int cursor = 0;
+  auto plan = [&](GcpOp& op, int cap) { if (o.error.empty()) o.error = plan_gcp_pack(op, cap, &cursor); };
+  for (int k = 0; k < o.L; ++k) { o.msg[k] = to_op(l.message[k], 0); plan(o.msg[k], edge_cap); }
+  o.ff0 = to_op(l.ff0, l.n_edge_params); plan(o.ff0, node_cap);
+  o.ff1 = to_op(l.ff1, l.n_edge_params); plan(o.ff1, node_cap);
+  if (l.has_pos) { o.pu = to_op(l.pos_update, l.n_edge_params); plan(o.pu, node_cap); }
+  o.packed_floats = cursor;
+  if (!o.error.empty()) return o;
+  int need = 0;
+  for (int k = 0; k < o.L; ++k) need += 2 + o.msg[k].w.nWS;
+  int need_n = 6 + o.ff0.w.nWS + o.ff1.w.nWS + (l.has_pos ? o.pu.w.nWS : 0);
+  if (need > MAX_WSEQ || need_n > MAX_WSEQ) { o.error = "layer needs too many weight chunks for this build"; return o; }
+  for (int k = 0; k < o.L; ++k) seq_fwd(o.edge_fwd, o.msg[k]);
+  for (int k = o.L - 1; k >= 0; --k) seq_bwd(o.edge_bwd, o.msg[k]);
+  seq_fwd(o.node_fwd, o.ff0); seq_fwd(o.node_fwd, o.ff1);
+  if (l.has_pos) { seq_fwd(o.node_fwd, o.pu); seq_bwd(o.node_bwd, o.pu); }
+  seq_bwd(o.node_bwd, o.ff1); seq_bwd(o.node_bwd, o.ff0);
+  for (WSeq* q : {&o.edge_fwd, &o.edge_bwd, &o.node_fwd, &o.node_bwd}) q->slot_floats = round_up(q->slot_floats, 32);
   return o;
 }
 
-inline int edge_wc_cap(const gcpnet_layer& l) {
-  // k-major data-gradient GEMM stages [K = s][64] in one chunk; n-major needs >= 64 x (8 + 4)
-  int cap = 12288;
-  const int need = E_OGD * E_NRD * round_up(l.s, 4);
-  if (need > cap) cap = need;
-  return cap;
-}
-inline int node_wc_cap(const gcpnet_layer& l) {
-  int cap = 12288;
-  int so = l.ff0.so > l.s ? l.ff0.so : l.s;
-  const int need = N_OGD * N_NRD * round_up(so, 4);
-  if (need > cap) cap = need;
-  return cap;
+inline PackParams make_pack_params(const LayerOps& o, float* blob) {
+  PackParams p{};
+  p.blob = blob;
+  for (int k = 0; k < o.L; ++k) p.ops[p.n++] = o.msg[k];
+  p.ops[p.n++] = o.ff0; p.ops[p.n++] = o.ff1;
+  if (o.has_pos) p.ops[p.n++] = o.pu;
+  return p;
 }
 
 inline void edge_saved_offsets(const gcpnet_layer& l, long long E, long long* offT, long long* offG, long long* offS,
@@ -105,79 +165,144 @@ inline void edge_saved_offsets(const gcpnet_layer& l, long long E, long long* of
   *total = off;
 }
 
-// Pick the largest edge tile whose shared-memory plan fits; small problems get the small tile so
-// that the tile count covers the 148 SMs.
-inline int pick_edge_tile(const gcpnet_layer& l, const LayerOps& ops, long long E, bool backward, EdgeSmem* out) {
-  const int cands[2] = {64, 32};
-  for (int ci = 0; ci < 2; ++ci) {
+// ---- tile planning ---------------------------------------------------------------------------------
+struct EdgeTilePlan { int TE, NT, SLF, nslot, grid; EdgeSmem sm; };
+struct NodeTilePlan { int TE, NT, SLF, nslot, grid; NodeSmem sm; };
+
+inline int edge_slf(const gcpnet_layer& l) { return (round_up(l.s, 16) / 16 + 3) / 4; }  // WN = 4 warps across the columns
+
+// Edge tiles: 8 threads per edge, TE in {32, 48, 64}.  Prefer the smallest tile whose tile count fits one
+// wave of one-CTA-per-SM (small graphs are latency bound: more CTAs in flight beat fatter tiles); large
+// graphs take the fattest tile that fits shared memory and loop persistently.
+inline bool pick_edge_tile(const gcpnet_layer& l, LayerOps& ops, long long E, bool backward, int force_te, EdgeTilePlan* out) {
+  WSeq& q = backward ? ops.edge_bwd : ops.edge_fwd;
+  const int slf = edge_slf(l);
+  if (slf > 2) return false;
+  const int cands[3] = {32, 48, 64};
+  bool have = false;
+  for (int ci = 0; ci < 3; ++ci) {
     const int TE = cands[ci];
-    if (TE == 64 && (backward || E < 64LL * 148 * 2)) continue;
-    EdgeSmem m = edge_plan_smem(TE, l.s, l.v, l.se, l.ve, ops.msg, l.num_message_layers, backward, edge_wc_cap(l));
-    if ((long long)m.total * 4 <= SMEM_LIMIT_BYTES) { *out = m; return TE; }
+    if (force_te && TE != force_te) continue;
+    EdgeTilePlan p{};
+    bool fits = false;
+    for (int nslot = 3; nslot >= 1 && !fits; --nslot) {
+      const EdgeSmem m = edge_plan_smem(TE, l.s, l.v, l.se, l.ve, ops.msg, l.num_message_layers, backward, nslot, q.slot_floats);
+      if ((long long)m.total * 4 <= SMEM_LIMIT_BYTES) { p.sm = m; p.nslot = nslot; fits = true; }
+    }
+    if (!fits) break;  // larger tiles need even more shared memory
+    p.TE = TE; p.NT = 8 * TE; p.SLF = slf;
+    const long long tiles = (E + TE - 1) / TE;
+    p.grid = (int)(tiles < 1 ? 1 : (tiles > NUM_SMS ? NUM_SMS : tiles));
+    *out = p; have = true;
+    if (tiles <= NUM_SMS) break;  // one wave: stop at the smallest such tile
   }
-  return 0;
-}
-inline int pick_node_tile(const gcpnet_layer& l, const LayerOps& ops, long long N, bool backward, NodeSmem* out) {
-  const int cands[2] = {32, 16};
-  for (int ci = 0; ci < 2; ++ci) {
-    const int TE = cands[ci];
-    if (TE == 32 && N < 32LL * 148 * 2) continue;
-    NodeSmem m = node_plan_smem(TE, l.s, l.v, l.ff0.so, l.ff0.vo, ops.ff0, ops.ff1, l.has_pos ? &ops.pu : nullptr, backward, node_wc_cap(l));
-    if ((long long)m.total * 4 <= SMEM_LIMIT_BYTES) { *out = m; return TE; }
-  }
-  return 0;
+  if (have) q.nslot = out->nslot;
+  return have;
 }
 
-inline std::string make_plan(const gcpnet_layer& l, long long N, long long E, gcpnet_plan* plan) {
+inline int node_slf(const gcpnet_layer& l) {
+  int np = round_up(l.ff0.so, 16);
+  if (round_up(l.s, 16) > np) np = round_up(l.s, 16);
+  const int wn = (NODE_NT / 32) / (NODE_TE / 16);
+  const int need = (np / 16 + wn - 1) / wn;
+  return need <= 1 ? 1 : (need <= 2 ? 2 : (need <= 4 ? 4 : 0));
+}
+inline bool pick_node_tile(const gcpnet_layer& l, LayerOps& ops, long long N, bool backward, NodeTilePlan* out) {
+  WSeq& q = backward ? ops.node_bwd : ops.node_fwd;
+  const int slf = node_slf(l);
+  if (slf == 0) return false;
+  for (int nslot = 3; nslot >= 1; --nslot) {  // 1 slot = no prefetch overlap, last resort for very wide layers
+    NodeSmem m = node_plan_smem(NODE_TE, NODE_NT, l.s, l.v, l.ff0.so, l.ff0.vo, ops.ff0, ops.ff1, l.has_pos ? &ops.pu : nullptr,
+                                backward, nslot, q.slot_floats);
+    if ((long long)m.total * 4 > SMEM_LIMIT_BYTES) continue;
+    NodeTilePlan p{};
+    p.TE = NODE_TE; p.NT = NODE_NT; p.SLF = slf; p.nslot = nslot; p.sm = m;
+    const long long tiles = (N + NODE_TE - 1) / NODE_TE;
+    p.grid = (int)(tiles < 1 ? 1 : (tiles > NUM_SMS ? NUM_SMS : tiles));
+    q.nslot = nslot;
+    *out = p;
+    return true;
+  }
+  return false;
+}
+
+struct LayerPlan {
+  LayerOps ops;
+  EdgeTilePlan ef, eb;
+  NodeTilePlan nf, nb;
+};
+
+inline std::string make_layer_plan(const gcpnet_layer& l, long long N, long long E, LayerPlan* lp, gcpnet_plan* plan) {
   std::string e = check_layer(l);
   if (!e.empty()) return e;
-  const LayerOps ops = layer_ops(l);
-  EdgeSmem ef, eb; NodeSmem nf, nb;
-  const int tef = pick_edge_tile(l, ops, E, false, &ef);
-  const int teb = pick_edge_tile(l, ops, E, true, &eb);
-  const int tnf = pick_node_tile(l, ops, N, false, &nf);
-  const int tnb = pick_node_tile(l, ops, N, true, &nb);
-  if (!tef || !teb || !tnf || !tnb) return "feature dims too large for the shared-memory tile plan of this build";
-  gcpnet_plan p{};
-  // forward and backward may use different tile sizes; saved activations are stored per sorted edge row
-  p.edge_tile = tef; p.node_tile = tnf;
-  auto tiles = [](long long n, int t) { return (int)((n + t - 1) / t); };
-  auto grid = [&](long long n, int t) { int g = tiles(n, t); return g > MAX_PERSISTENT_CTAS ? MAX_PERSISTENT_CTAS : (g < 1 ? 1 : g); };
-  p.edge_grid_fwd = grid(E, tef); p.edge_grid_bwd = grid(E, teb);
-  p.node_grid_fwd = grid(N, tnf); p.node_grid_bwd = grid(N, tnb);
-  p.edge_smem_fwd_bytes = ef.total * 4; p.edge_smem_bwd_bytes = eb.total * 4;
-  p.node_smem_fwd_bytes = nf.total * 4; p.node_smem_bwd_bytes = nb.total * 4;
-  const long long W = l.s + 3 * l.v;
-  p.msg_floats = E * W;
-  long long offT[MAX_MSG_LAYERS], offG[MAX_MSG_LAYERS], offS[MAX_MSG_LAYERS], offV[MAX_MSG_LAYERS], tot;
-  edge_saved_offsets(l, E, offT, offG, offS, offV, &tot);
-  p.saved_edge_floats = tot;
-  p.saved_node_floats = node_saved_layout((int)N, l.s, l.v, l.ff0.so, l.ff0.vo, l.has_pos != 0, l.training != 0).total;
-  p.edge_partial_floats = (long long)p.edge_grid_bwd * l.n_edge_params;
-  p.node_partial_floats = (long long)p.node_grid_bwd * l.n_node_params;
-  p.edge_cotangent_floats = 2 * E * W;
-  p.agg_cotangent_floats = N * W;
-  *plan = p;
+  // The packed layout (hence the ring-slot size) is shared by forward and backward: take the largest
+  // chunk caps for which BOTH directions fit shared memory.
+  const int edge_caps[3] = {EDGE_CAP_FLOATS, 6144, 4096};
+  const int node_caps[4] = {NODE_CAP_FLOATS, 10240, 8192, 6144};
+  bool okE = false, okN = false;
+  int ecap = 0, ncap = 0;
+  std::string last;
+  for (int i = 0; i < 3 && !okE; ++i) {
+    LayerOps o = layer_ops(l, edge_caps[i], node_caps[0]);
+    if (!o.error.empty()) { last = o.error; continue; }
+    EdgeTilePlan a, b;
+    if (pick_edge_tile(l, o, E, false, 0, &a) && pick_edge_tile(l, o, E, true, 0, &b)) { okE = true; ecap = edge_caps[i]; }
+  }
+  for (int i = 0; i < 4 && !okN; ++i) {
+    LayerOps o = layer_ops(l, edge_caps[0], node_caps[i]);
+    if (!o.error.empty()) { last = o.error; continue; }
+    NodeTilePlan a, b;
+    if (pick_node_tile(l, o, N, false, &a) && pick_node_tile(l, o, N, true, &b)) { okN = true; ncap = node_caps[i]; }
+  }
+  if (!okE || !okN) return last.empty() ? "feature dims too large for the shared-memory tile plan of this build" : last;
+  lp->ops = layer_ops(l, ecap, ncap);
+  if (!lp->ops.error.empty()) return lp->ops.error;
+  okE = pick_edge_tile(l, lp->ops, E, false, 0, &lp->ef) && pick_edge_tile(l, lp->ops, E, true, 0, &lp->eb);
+  okN = pick_node_tile(l, lp->ops, N, false, &lp->nf) && pick_node_tile(l, lp->ops, N, true, &lp->nb);
+  if (!okE || !okN) return "feature dims too large for the shared-memory tile plan of this build";
+  if (plan) {
+    gcpnet_plan p{};
+    p.edge_tile = lp->ef.TE; p.node_tile = lp->nf.TE;
+    p.edge_grid_fwd = lp->ef.grid; p.edge_grid_bwd = lp->eb.grid;
+    p.node_grid_fwd = lp->nf.grid; p.node_grid_bwd = lp->nb.grid;
+    p.edge_smem_fwd_bytes = lp->ef.sm.total * 4; p.edge_smem_bwd_bytes = lp->eb.sm.total * 4;
+    p.node_smem_fwd_bytes = lp->nf.sm.total * 4; p.node_smem_bwd_bytes = lp->nb.sm.total * 4;
+    const long long W = l.s + 3 * l.v;
+    p.msg_floats = E * W;
+    long long offT[MAX_MSG_LAYERS], offG[MAX_MSG_LAYERS], offS[MAX_MSG_LAYERS], offV[MAX_MSG_LAYERS], tot;
+    edge_saved_offsets(l, E, offT, offG, offS, offV, &tot);
+    p.saved_edge_floats = tot;
+    p.saved_node_floats = node_saved_layout((int)N, l.s, l.v, l.ff0.so, l.ff0.vo, l.has_pos != 0, l.training != 0).total;
+    p.edge_partial_floats = (long long)p.edge_grid_bwd * l.n_edge_params;
+    p.node_partial_floats = (long long)p.node_grid_bwd * l.n_node_params;
+    p.edge_cotangent_floats = 2 * E * W;
+    p.agg_cotangent_floats = N * W;
+    p.packed_floats = lp->ops.packed_floats;
+    *plan = p;
+  }
   return "";
 }
 
-inline int edge_tile_bwd(const gcpnet_layer& l, long long E, EdgeSmem* m) { return pick_edge_tile(l, layer_ops(l), E, true, m); }
-
-inline EdgeParams make_edge_params(const gcpnet_layer& l, const gcpnet_graph& g, const LayerOps& ops, const EdgeSmem& sm) {
+inline EdgeParams make_edge_params(const gcpnet_layer& l, const gcpnet_graph& g, const LayerOps& ops, const EdgeTilePlan& tp,
+                                   bool backward, const float* blob) {
   EdgeParams p{};
   p.N = (int)g.num_nodes; p.E = (int)g.num_edges; p.L = l.num_message_layers;
   p.s = l.s; p.v = l.v; p.se = l.se; p.ve = l.ve;
   p.residual = l.residual_messages; p.e3 = l.enable_e3; p.reduce_mean = l.reduce_mean; p.slope = l.slope;
   p.perm = g.perm; p.src = g.src; p.dst = g.dst; p.dst_ptr = g.dst_ptr;
+  p.blob = blob;
   for (int k = 0; k < p.L; ++k) p.ops[k] = ops.msg[k];
   long long tot;
   edge_saved_offsets(l, g.num_edges, p.offT, p.offG, p.offS, p.offV, &tot);
   p.partial_stride = l.n_edge_params;
-  p.sm = sm;
+  p.sm = tp.sm;
+  p.seq = backward ? ops.edge_bwd : ops.edge_fwd;
+  p.seq.nslot = tp.nslot;
   return p;
 }
 
-inline NodeParams make_node_params(const gcpnet_layer& l, const gcpnet_graph& g, const LayerOps& ops, const NodeSmem& sm) {
+inline NodeParams make_node_params(const gcpnet_layer& l, const gcpnet_graph& g, const LayerOps& ops, const NodeTilePlan& tp,
+                                   bool backward, const float* blob) {
   NodeParams p{};
   p.N = (int)g.num_nodes; p.s = l.s; p.v = l.v; p.hs = l.ff0.so; p.hv = l.ff0.vo;
   p.has_pos = l.has_pos; p.reduce_mean = l.reduce_mean; p.train = l.training;
@@ -185,12 +310,15 @@ inline NodeParams make_node_params(const gcpnet_layer& l, const gcpnet_graph& g,
   p.seed = l.seed; p.rng_ctr = (const long long*)l.rng_counter;
   p.fbar = g.fbar; p.dst_ptr = g.dst_ptr;
   p.ln0_w = l.ln0_w; p.ln0_b = l.ln0_b; p.ln1_w = l.ln1_w; p.ln1_b = l.ln1_b;
+  p.blob = blob;
   p.ff0 = ops.ff0; p.ff1 = ops.ff1; p.pu = ops.pu;
   p.sv = node_saved_layout(p.N, l.s, l.v, p.hs, p.hv, l.has_pos != 0, l.training != 0);
   p.partial_stride = l.n_node_params;
   p.o_ln0w = l.ln_grad_off[0] - l.n_edge_params; p.o_ln0b = l.ln_grad_off[1] - l.n_edge_params;
   p.o_ln1w = l.ln_grad_off[2] - l.n_edge_params; p.o_ln1b = l.ln_grad_off[3] - l.n_edge_params;
-  p.sm = sm;
+  p.sm = tp.sm;
+  p.seq = backward ? ops.node_bwd : ops.node_fwd;
+  p.seq.nslot = tp.nslot;
   return p;
 }
 

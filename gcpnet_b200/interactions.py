@@ -169,15 +169,16 @@ class _LayerFn(torch.autograd.Function):
         msg = f32(plan.msg_floats)
         saved_edge = f32(plan.saved_edge_floats) if need_grad else None
         saved_node = f32(plan.saved_node_floats) if need_grad else None
+        packed = f32(plan.packed_floats)
         io = _cabi.ForwardIO(_ptr(h), _ptr(chi), _ptr(e), _ptr(xi), _ptr(frames), _ptr(pos), _ptr(out_h), _ptr(out_chi),
-                             _ptr(out_pos), _ptr(msg), _ptr(saved_edge), _ptr(saved_node))
+                             _ptr(out_pos), _ptr(msg), _ptr(saved_edge), _ptr(saved_node), _ptr(packed))
         _lib.check(lib.gcpnet_layer_forward(C.byref(layer), C.byref(gv.struct), C.byref(plan), C.byref(io), _stream()),
                    "gcpnet_layer_forward")
         if training:
             mod._rng_counter.add_(1)
         ctx.mod, ctx.gv, ctx.plan, ctx.training = mod, gv, plan, training
         ctx.has_pos = spec.has_pos
-        ctx.save_for_backward(h, chi, e, xi, frames, saved_edge, saved_node, *params)
+        ctx.save_for_backward(h, chi, e, xi, frames, saved_edge, saved_node, packed, *params)
         if spec.has_pos:
             return out_h, out_chi, out_pos
         return out_h, out_chi
@@ -187,7 +188,7 @@ class _LayerFn(torch.autograd.Function):
         lib = _lib.load()
         mod, gv, plan = ctx.mod, ctx.gv, ctx.plan
         spec = mod.spec
-        h, chi, e, xi, frames, saved_edge, saved_node, *params = ctx.saved_tensors
+        h, chi, e, xi, frames, saved_edge, saved_node, packed, *params = ctx.saved_tensors
         if saved_node is None:
             raise RuntimeError("gcpnet_b200: backward called on a forward that ran without saved activations")
         dev = h.device
@@ -205,7 +206,7 @@ class _LayerFn(torch.autograd.Function):
         ws_ep, ws_np = f32(plan.edge_partial_floats), f32(plan.node_partial_floats)
         io = _cabi.BackwardIO(_ptr(h), _ptr(chi), _ptr(e), _ptr(xi), _ptr(frames), _ptr(saved_edge), _ptr(saved_node),
                               _ptr(g_out_h), _ptr(g_out_chi), _ptr(g_out_pos), _ptr(g_h), _ptr(g_chi), _ptr(g_e),
-                              _ptr(g_xi), _ptr(g_params), _ptr(ws_agg), _ptr(ws_edge), _ptr(ws_ep), _ptr(ws_np))
+                              _ptr(g_xi), _ptr(g_params), _ptr(ws_agg), _ptr(ws_edge), _ptr(ws_ep), _ptr(ws_np), _ptr(packed))
         _lib.check(lib.gcpnet_layer_backward(C.byref(layer), C.byref(gv.struct), C.byref(plan), C.byref(io), _stream()),
                    "gcpnet_layer_backward")
         if gv.E == 0:

@@ -98,6 +98,7 @@ typedef struct gcpnet_plan {
   int64_t node_partial_floats;   /* node_grid_bwd * n_node_params */
   int64_t edge_cotangent_floats; /* 2 * E * (s+3v): per-edge cotangents of the gathered node features */
   int64_t agg_cotangent_floats;  /* N * (s+3v) */
+  int64_t packed_floats;         /* packed (chunked, padded) copy of the layer's weights, rewritten by every forward */
 } gcpnet_plan;
 
 typedef struct gcpnet_forward_io {
@@ -106,6 +107,7 @@ typedef struct gcpnet_forward_io {
   float* msg;          /* plan.msg_floats */
   float* saved_edge;   /* plan.saved_edge_floats or NULL (inference) */
   float* saved_node;   /* plan.saved_node_floats or NULL (inference) */
+  float* packed;       /* plan.packed_floats: written by the forward call, read by the matching backward */
 } gcpnet_forward_io;
 
 typedef struct gcpnet_backward_io {
@@ -115,6 +117,7 @@ typedef struct gcpnet_backward_io {
   float *g_h, *g_chi, *g_e, *g_xi;               /* cotangents of the inputs */
   float* g_params;                               /* [n_edge_params + n_node_params] flat parameter gradient (overwritten) */
   float *ws_agg, *ws_edge, *ws_edge_partial, *ws_node_partial; /* workspaces sized by the plan */
+  const float* packed;                           /* the forward call's packed weights */
 } gcpnet_backward_io;
 
 int gcpnet_version(void);

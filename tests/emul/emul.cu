@@ -28,44 +28,67 @@ static float* alloc_smem(int floats) {
   return f;
 }
 
-template <int TE>
+template <int TE, int SLF>
 static void run_edge_fwd(const EdgeParams& p, int grid) {
+  constexpr int NT = 8 * TE;
   const int ntiles = (p.E + TE - 1) / TE;
   for (int cta = 0; cta < grid; ++cta) {
+    const int mine = cta < ntiles ? (ntiles - cta + grid - 1) / grid : 0;
+    if (!mine) continue;
     float* sm = alloc_smem(p.sm.total);
-    for (int tile = cta; tile < ntiles; tile += grid) edge_fwd_tile<TE, EDGE_NT>(p, sm, tile);
+    WPipe wp = edge_pipe(p, sm, mine);
+    wpipe_start<NT>(wp);
+    for (int tile = cta; tile < ntiles; tile += grid) edge_fwd_tile<TE, NT, SLF>(p, sm, tile, wp, tile == cta);
     free(sm);
   }
 }
-template <int TE>
+template <int TE, int SLF>
 static void run_edge_bwd(const EdgeParams& p, int grid) {
+  constexpr int NT = 8 * TE;
   const int ntiles = (p.E + TE - 1) / TE;
   for (int cta = 0; cta < grid; ++cta) {
+    const int mine = cta < ntiles ? (ntiles - cta + grid - 1) / grid : 0;
+    if (!mine) continue;
     float* sm = alloc_smem(p.sm.total);
+    WPipe wp = edge_pipe(p, sm, mine);
+    wpipe_start<NT>(wp);
     float* prow = p.partial + (size_t)cta * p.partial_stride;
-    for (int tile = cta; tile < ntiles; tile += grid) edge_bwd_tile<TE, EDGE_NT>(p, sm, tile, prow, tile != cta);
+    for (int tile = cta; tile < ntiles; tile += grid) edge_bwd_tile<TE, NT, SLF, EDGE_SLD>(p, sm, tile, wp, prow, tile != cta);
     free(sm);
   }
 }
-template <int TE>
+template <int SLF>
 static void run_node_fwd(const NodeParams& p, int grid) {
+  constexpr int TE = NODE_TE, NT = NODE_NT;
   const int ntiles = (p.N + TE - 1) / TE;
   for (int cta = 0; cta < grid; ++cta) {
+    const int mine = cta < ntiles ? (ntiles - cta + grid - 1) / grid : 0;
+    if (!mine) continue;
     float* sm = alloc_smem(p.sm.total);
-    for (int tile = cta; tile < ntiles; tile += grid) node_fwd_tile<TE, NODE_NT>(p, sm, tile);
+    WPipe wp = node_pipe(p, sm, mine);
+    wpipe_start<NT>(wp);
+    for (int tile = cta; tile < ntiles; tile += grid) node_fwd_tile<TE, NT, SLF>(p, sm, tile, wp, tile == cta);
     free(sm);
   }
 }
-template <int TE>
+template <int SLF>
 static void run_node_bwd(const NodeParams& p, int grid) {
+  constexpr int TE = NODE_TE, NT = NODE_NT;
   const int ntiles = (p.N + TE - 1) / TE;
   for (int cta = 0; cta < grid; ++cta) {
+    const int mine = cta < ntiles ? (ntiles - cta + grid - 1) / grid : 0;
+    if (!mine) continue;
     float* sm = alloc_smem(p.sm.total);
+    WPipe wp = node_pipe(p, sm, mine);
+    wpipe_start<NT>(wp);
     float* prow = p.partial + (size_t)cta * p.partial_stride;
-    for (int tile = cta; tile < ntiles; tile += grid) node_bwd_tile<TE, NODE_NT>(p, sm, tile, prow, tile != cta);
+    for (int tile = cta; tile < ntiles; tile += grid) node_bwd_tile<TE, NT, SLF, NODE_SLD>(p, sm, tile, wp, prow, tile != cta);
     free(sm);
   }
 }
+
+template <class F1, class F2>
+static int by_slf(int slf, F1 one, F2 two) { if (slf == 1) { one(); return 0; } if (slf == 2) { two(); return 0; } return 1; }
 
 extern "C" {
 
@@ -95,24 +118,33 @@ int emul_graph_build(const int64_t* edge_index, int64_t E, int64_t N, const floa
 }
 
 int emul_layer_plan(const gcpnet_layer* layer, int64_t N, int64_t E, gcpnet_plan* plan) {
-  const std::string e = make_plan(*layer, N, E, plan);
+  LayerPlan lp;
+  const std::string e = make_layer_plan(*layer, N, E, &lp, plan);
   return e.empty() ? 0 : fail(e);
 }
 
-// force_edge_tile / force_node_tile: 0 = planner's choice, else the tile size to emulate
+// force_edge_tile: 0 = planner's choice, else the edge tile size to emulate (32 / 48 / 64)
 int emul_layer_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, const gcpnet_plan* plan,
                        const gcpnet_forward_io* io, int force_edge_tile, int force_node_tile, int mp_only, float* aggregate) {
   const gcpnet_layer& l = *layer; const gcpnet_graph& g = *graph;
-  const std::string e = check_layer(l);
+  LayerPlan lp;
+  const std::string e = make_layer_plan(l, g.num_nodes, g.num_edges, &lp, nullptr);
   if (!e.empty()) return fail(e);
-  const LayerOps ops = layer_ops(l);
+  if (force_edge_tile && !pick_edge_tile(l, lp.ops, g.num_edges, false, force_edge_tile, &lp.ef)) return fail("forced edge tile does not fit");
+  (void)force_node_tile;
+  {  // pack kernel
+    const PackParams pp = make_pack_params(lp.ops, io->packed);
+    for (int b = 0; b < pp.n; ++b) pack_gcp<256>(pp.ops[b], pp.blob);
+  }
   if (g.num_edges > 0) {
-    EdgeSmem sm; int TE = pick_edge_tile(l, ops, g.num_edges, false, &sm);
-    if (force_edge_tile) { TE = force_edge_tile; sm = edge_plan_smem(TE, l.s, l.v, l.se, l.ve, ops.msg, l.num_message_layers, false, edge_wc_cap(l)); }
-    EdgeParams p = make_edge_params(l, g, ops, sm);
+    EdgeParams p = make_edge_params(l, g, lp.ops, lp.ef, false, io->packed);
     p.h = io->h; p.chi = io->chi; p.e = io->e; p.xi = io->xi; p.frames = io->frames; p.msg = io->msg; p.saved = io->saved_edge;
-    int grid = (int)((g.num_edges + TE - 1) / TE); if (grid > 3) grid = 3;  // exercise the persistent loop
-    if (TE == 64) run_edge_fwd<64>(p, grid); else if (TE == 32) run_edge_fwd<32>(p, grid); else return fail("bad edge tile");
+    int grid = lp.ef.grid; if (grid > 3) grid = 3;  // exercise the persistent loop
+    int bad = 1;
+    if (lp.ef.TE == 32) bad = by_slf(lp.ef.SLF, [&] { run_edge_fwd<32, 1>(p, grid); }, [&] { run_edge_fwd<32, 2>(p, grid); });
+    if (lp.ef.TE == 48) bad = by_slf(lp.ef.SLF, [&] { run_edge_fwd<48, 1>(p, grid); }, [&] { run_edge_fwd<48, 2>(p, grid); });
+    if (lp.ef.TE == 64) bad = by_slf(lp.ef.SLF, [&] { run_edge_fwd<64, 1>(p, grid); }, [&] { run_edge_fwd<64, 2>(p, grid); });
+    if (bad) return fail("bad edge tile");
   }
   const int W = l.s + 3 * l.v;
   if (mp_only) {
@@ -125,13 +157,12 @@ int emul_layer_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, con
       }
     return 0;
   }
-  NodeSmem sm; int TN = pick_node_tile(l, ops, g.num_nodes, false, &sm);
-  if (force_node_tile) { TN = force_node_tile; sm = node_plan_smem(TN, l.s, l.v, l.ff0.so, l.ff0.vo, ops.ff0, ops.ff1, l.has_pos ? &ops.pu : nullptr, false, node_wc_cap(l)); }
-  NodeParams p = make_node_params(l, g, ops, sm);
+  NodeParams p = make_node_params(l, g, lp.ops, lp.nf, false, io->packed);
   p.h = io->h; p.chi = io->chi; p.msg = io->msg; p.pos = io->pos;
   p.out_h = io->out_h; p.out_chi = io->out_chi; p.out_pos = io->out_pos; p.saved = io->saved_node;
-  int grid = (int)((g.num_nodes + TN - 1) / TN); if (grid > 2) grid = 2;
-  if (TN == 32) run_node_fwd<32>(p, grid); else if (TN == 16) run_node_fwd<16>(p, grid); else return fail("bad node tile");
+  int grid = lp.nf.grid; if (grid > 2) grid = 2;
+  if (lp.nf.SLF == 1) run_node_fwd<1>(p, grid); else if (lp.nf.SLF == 2) run_node_fwd<2>(p, grid);
+  else if (lp.nf.SLF == 4) run_node_fwd<4>(p, grid); else return fail("bad node tile");
   (void)plan;
   return 0;
 }
@@ -139,30 +170,32 @@ int emul_layer_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, con
 int emul_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, const gcpnet_plan* plan,
                         const gcpnet_backward_io* io, int force_node_tile, int edge_grid, int node_grid) {
   const gcpnet_layer& l = *layer; const gcpnet_graph& g = *graph;
-  const std::string e = check_layer(l);
+  LayerPlan lp;
+  const std::string e = make_layer_plan(l, g.num_nodes, g.num_edges, &lp, nullptr);
   if (!e.empty()) return fail(e);
-  const LayerOps ops = layer_ops(l);
+  (void)force_node_tile;
   const int W = l.s + 3 * l.v;
-  NodeSmem nsm; int TN = pick_node_tile(l, ops, g.num_nodes, true, &nsm);
-  if (force_node_tile) { TN = force_node_tile; nsm = node_plan_smem(TN, l.s, l.v, l.ff0.so, l.ff0.vo, ops.ff0, ops.ff1, l.has_pos ? &ops.pu : nullptr, true, node_wc_cap(l)); }
-  NodeParams np = make_node_params(l, g, ops, nsm);
+  NodeParams np = make_node_params(l, g, lp.ops, lp.nb, true, io->packed);
   np.saved = const_cast<float*>(io->saved_node);
   np.g_out_h = io->g_out_h; np.g_out_chi = io->g_out_chi; np.g_out_pos = io->g_out_pos;
   np.g_x_h = io->g_h; np.g_x_chi = io->g_chi; np.g_agg = io->ws_agg; np.partial = io->ws_node_partial;
-  const int ntn = (int)((g.num_nodes + TN - 1) / TN);
+  const int ntn = (int)((g.num_nodes + lp.nb.TE - 1) / lp.nb.TE);
   if (node_grid > ntn) node_grid = ntn;
-  if (TN == 32) run_node_bwd<32>(np, node_grid); else if (TN == 16) run_node_bwd<16>(np, node_grid); else return fail("bad node tile");
+  if (lp.nb.SLF == 1) run_node_bwd<1>(np, node_grid); else if (lp.nb.SLF == 2) run_node_bwd<2>(np, node_grid);
+  else if (lp.nb.SLF == 4) run_node_bwd<4>(np, node_grid); else return fail("bad node tile");
   if (g.num_edges > 0) {
-    EdgeSmem esm; const int TE = pick_edge_tile(l, ops, g.num_edges, true, &esm);
-    EdgeParams ep = make_edge_params(l, g, ops, esm);
+    EdgeParams ep = make_edge_params(l, g, lp.ops, lp.eb, true, io->packed);
     ep.h = io->h; ep.chi = io->chi; ep.e = io->e; ep.xi = io->xi; ep.frames = io->frames;
     ep.saved = const_cast<float*>(io->saved_edge); ep.gagg = io->ws_agg;
     ep.grow = io->ws_edge; ep.gcol = io->ws_edge + (size_t)g.num_edges * W; ep.ge = io->g_e; ep.gxi = io->g_xi;
     ep.partial = io->ws_edge_partial;
-    const int nte = (int)((g.num_edges + TE - 1) / TE);
+    const int nte = (int)((g.num_edges + lp.eb.TE - 1) / lp.eb.TE);
     if (edge_grid > nte) edge_grid = nte;
-    if (TE != 32) return fail("bad edge bwd tile");
-    run_edge_bwd<32>(ep, edge_grid);
+    int bad = 1;
+    if (lp.eb.TE == 32) bad = by_slf(lp.eb.SLF, [&] { run_edge_bwd<32, 1>(ep, edge_grid); }, [&] { run_edge_bwd<32, 2>(ep, edge_grid); });
+    if (lp.eb.TE == 48) bad = by_slf(lp.eb.SLF, [&] { run_edge_bwd<48, 1>(ep, edge_grid); }, [&] { run_edge_bwd<48, 2>(ep, edge_grid); });
+    if (lp.eb.TE == 64) bad = by_slf(lp.eb.SLF, [&] { run_edge_bwd<64, 1>(ep, edge_grid); }, [&] { run_edge_bwd<64, 2>(ep, edge_grid); });
+    if (bad) return fail("bad edge bwd tile");
     for (int64_t i = 0; i < g.num_nodes; ++i)
       for (int f = 0; f < W; ++f) {
         float* out = f < l.s ? io->g_h + i * l.s + f : io->g_chi + i * 3 * l.v + (f - l.s);

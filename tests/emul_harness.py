@@ -99,9 +99,11 @@ class EmulLayer:
         self.msg = nan(max(int(self.plan.msg_floats), 1))
         self.saved_edge = nan(max(int(self.plan.saved_edge_floats), 1)) if save else None
         self.saved_node = nan(max(int(self.plan.saved_node_floats), 1)) if save else None
+        self.packed = nan(max(int(self.plan.packed_floats), 1))
         io = _cabi.ForwardIO(_p(self.h), _p(self.chi), _p(self.e), _p(self.xi), _p(self.frames), _p(self.pos),
                              _p(self.out_h), _p(self.out_chi), _p(self.out_pos), _p(self.msg),
-                             _p(self.saved_edge) if save else None, _p(self.saved_node) if save else None)
+                             _p(self.saved_edge) if save else None, _p(self.saved_node) if save else None,
+                             _p(self.packed))
         agg = nan(N, s + 3 * v)
         rc = self.lib.emul_layer_forward(C.byref(self.layer), C.byref(self.graph), C.byref(self.plan), C.byref(io),
                                          edge_tile, node_tile, int(mp_only), _p(agg))
@@ -127,7 +129,7 @@ class EmulLayer:
         io = _cabi.BackwardIO(_p(self.h), _p(self.chi), _p(self.e), _p(self.xi), _p(self.frames), _p(self.saved_edge),
                               _p(self.saved_node), _p(g_h), _p(g_chi), _p(g_pos) if g_pos is not None else None,
                               _p(self.g_h), _p(self.g_chi), _p(self.g_e), _p(self.g_xi), _p(self.g_params),
-                              _p(ws_agg), _p(ws_edge), _p(ws_ep), _p(ws_np))
+                              _p(ws_agg), _p(ws_edge), _p(ws_ep), _p(ws_np), _p(self.packed))
         rc = self.lib.emul_layer_backward(C.byref(self.layer), C.byref(self.graph), C.byref(self.plan), C.byref(io),
                                           node_tile, edge_grid, node_grid)
         assert rc == 0, self.lib.emul_last_error().decode()
