@@ -29,6 +29,20 @@ def _deps():
     return [HEADER] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
 
 
+def _deps_of(src: str) -> list:
+    """Transitive closure of the quoted #includes of one source file (in-tree headers only)."""
+    import re
+    seen, todo = set(), [src]
+    while todo:
+        f = todo.pop()
+        if f in seen or not os.path.exists(f):
+            continue
+        seen.add(f)
+        for inc in re.findall(r'^\s*#include\s+"([^"]+)"', open(f).read(), flags=re.M):
+            todo.append(os.path.normpath(os.path.join(os.path.dirname(f), inc)))
+    return sorted(seen)
+
+
 def stale() -> bool:
     if not os.path.exists(LIB):
         return True
@@ -43,14 +57,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libgcpnet_b200.so")
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    objs = []
+    objs, jobs = [], []
     for src in sources():
         obj = os.path.join(PKG, "build", os.path.basename(src) + ".o")
         os.makedirs(os.path.dirname(obj), exist_ok=True)
-        if force or not os.path.exists(obj) or any(os.path.getmtime(d) > os.path.getmtime(obj) for d in _deps()):
+        if force or not os.path.exists(obj) or any(os.path.getmtime(d) > os.path.getmtime(obj) for d in _deps_of(src)):
             cmd = [nvcc] + [f for f in flags if f != "--shared"] + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
-            subprocess.check_call(cmd)
+            jobs.append((cmd, subprocess.Popen(cmd)))  # translation units compile concurrently
         objs.append(obj)
+    for cmd, proc in jobs:
+        if proc.wait() != 0:
+            raise subprocess.CalledProcessError(proc.returncode, cmd)
     subprocess.check_call([nvcc, "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs)
     return LIB
 

@@ -22,6 +22,7 @@ int gcp_fail(const std::string& msg) { g_last_error = msg; return 1; }
 static std::atomic<unsigned long long> g_launches{0};
 void gcp_note_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
+static std::atomic<int> g_opt_tc{1};
 static std::atomic<bool> g_profile{false};
 static std::mutex g_profile_mu;
 static std::vector<cudaEvent_t> g_profile_ev[T_COUNT];  // begin, end, begin, end, ...
@@ -205,6 +206,24 @@ static int launch_pack(const LayerOps& ops, float* blob, cudaStream_t st) {
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
+static bool use_tc(const LayerPlan& lp) { return lp.tc.ok && g_opt_tc.load(std::memory_order_relaxed) != 0; }
+int gcp_tc_launch_pack(const tc::TcPackProg& prog, cudaStream_t st);                      // tc_api.cu
+int gcp_tc_launch_edge_fwd(const tc::TcEdgeParams& p, int grid, cudaStream_t st);          // tc_api.cu
+static int launch_tc_pack(const LayerPlan& lp, float* packed, cudaStream_t st) {
+  tc::TcPackProg prog = lp.tc.pack;
+  prog.blob = packed + lp.v2_packed_floats;
+  return gcp_tc_launch_pack(prog, st);
+}
+static int launch_tc_edge_fwd(const gcpnet_graph& g, const LayerPlan& lp, const gcpnet_forward_io& io, float* saved, cudaStream_t st) {
+  GcpTimedScope timed(T_EDGE_FWD, st);
+  tc::TcEdgeParams p = lp.tc.proto;
+  p.N = (int)g.num_nodes; p.E = (int)g.num_edges;
+  p.h = io.h; p.chi = io.chi; p.e = io.e; p.xi = io.xi; p.frames = io.frames;
+  p.perm = g.perm; p.src = g.src; p.dst = g.dst;
+  p.blob = io.packed + lp.v2_packed_floats;
+  p.msg = io.msg; p.saved = saved;
+  return gcp_tc_launch_edge_fwd(p, lp.tc.grid, st);
+}
 
 // ------------------------------------------------------------------------------------------
 // C ABI
@@ -214,6 +233,10 @@ extern "C" {
 int gcpnet_version(void) { return 200; }
 const char* gcpnet_last_error(void) { return g_last_error.c_str(); }
 void gcpnet_profile_enable(int on) { g_profile.store(on != 0); }
+int gcpnet_set_option(const char* name, int value) {
+  if (name && std::string(name) == "tc") return g_opt_tc.exchange(value);
+  return -1;
+}
 int gcpnet_profile_read(int which, double* total_ms, int64_t* launches) {
   if (which < 0 || which >= T_COUNT || !total_ms || !launches) return fail("profile_read: bad argument");
   std::lock_guard<std::mutex> lock(g_profile_mu);
@@ -243,6 +266,10 @@ int gcpnet_layer_plan(const gcpnet_layer* layer, int64_t N, int64_t E, gcpnet_pl
 static int run_edge_forward(const gcpnet_layer& l, const gcpnet_graph& g, const LayerPlan& lp, const gcpnet_forward_io& io,
                             cudaStream_t st) {
   if (g.num_edges == 0) return 0;
+  if (use_tc(lp) && io.saved_edge == nullptr) {  // inference: tensor-core path (training joins once the backward is on it)
+    if (launch_tc_pack(lp, io.packed, st)) return 1;
+    return launch_tc_edge_fwd(g, lp, io, nullptr, st);
+  }
   EdgeParams p = make_edge_params(l, g, lp.ops, lp.ef, false, io.packed);
   p.h = io.h; p.chi = io.chi; p.e = io.e; p.xi = io.xi; p.frames = io.frames;
   p.msg = io.msg; p.saved = io.saved_edge;

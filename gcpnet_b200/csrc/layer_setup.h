@@ -9,6 +9,7 @@
 #include "edge_kernels.cuh"
 #include "node_kernels.cuh"
 #include "pack.cuh"
+#include "tc_setup.h"
 
 namespace gcp {
 
@@ -230,6 +231,8 @@ struct LayerPlan {
   LayerOps ops;
   EdgeTilePlan ef, eb;
   NodeTilePlan nf, nb;
+  tc::TcPlan tc;      // tensor-core edge path (tc_edge.cuh); tc.ok == false -> FFMA tiles only
+  int v2_packed_floats;
 };
 
 inline std::string make_layer_plan(const gcpnet_layer& l, long long N, long long E, LayerPlan* lp, gcpnet_plan* plan) {
@@ -260,6 +263,8 @@ inline std::string make_layer_plan(const gcpnet_layer& l, long long N, long long
   okE = pick_edge_tile(l, lp->ops, E, false, 0, &lp->ef) && pick_edge_tile(l, lp->ops, E, true, 0, &lp->eb);
   okN = pick_node_tile(l, lp->ops, N, false, &lp->nf) && pick_node_tile(l, lp->ops, N, true, &lp->nb);
   if (!okE || !okN) return "feature dims too large for the shared-memory tile plan of this build";
+  lp->tc = tc::make_tc_plan(l, E);
+  lp->v2_packed_floats = round_up(lp->ops.packed_floats, 32);
   if (plan) {
     gcpnet_plan p{};
     p.edge_tile = lp->ef.TE; p.node_tile = lp->nf.TE;
@@ -277,7 +282,8 @@ inline std::string make_layer_plan(const gcpnet_layer& l, long long N, long long
     p.node_partial_floats = (long long)p.node_grid_bwd * l.n_node_params;
     p.edge_cotangent_floats = 2 * E * W;
     p.agg_cotangent_floats = N * W;
-    p.packed_floats = lp->ops.packed_floats;
+    p.packed_floats = lp->v2_packed_floats + (lp->tc.ok ? lp->tc.blob_floats : 0);
+    p.tc_edge_path = lp->tc.ok ? 1 : 0;
     *plan = p;
   }
   return "";

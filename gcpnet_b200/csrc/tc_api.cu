@@ -1,0 +1,41 @@
+// tc_api.cu -- translation unit of the tensor-core (tcgen05) kernels: instantiations + launchers.
+#include <cuda_runtime.h>
+
+#include <map>
+#include <mutex>
+
+#include "common.h"
+#include "tc_setup.h"
+#include "tc_edge_dev.cuh"
+
+using namespace gcp;
+
+static int tc_set_smem(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> done;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  int& cur = done[{kernel, dev}];
+  if (bytes > cur) {
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    cur = bytes;
+  }
+  return 0;
+}
+
+int gcp_tc_launch_pack(const tc::TcPackProg& prog, cudaStream_t st) {
+  tc::tc_pack_kernel<<<prog.n, 256, 0, st>>>(prog);
+  gcp_note_launches(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int gcp_tc_launch_edge_fwd(const tc::TcEdgeParams& p, int grid, cudaStream_t st) {
+  const int bytes = p.smem_floats * 4;
+  if (tc_set_smem((const void*)tc::tc_edge_fwd_kernel<2>, bytes)) return 1;
+  tc::tc_edge_fwd_kernel<2><<<grid, 256, bytes, st>>>(p);
+  gcp_note_launches(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}

@@ -162,7 +162,7 @@ class _LayerFn(torch.autograd.Function):
         layer = mod._layer_struct(params, training)
         plan = _cabi.Plan()
         _lib.check(lib.gcpnet_layer_plan(C.byref(layer), N, E, C.byref(plan)), "gcpnet_layer_plan")
-        need_grad = any(ctx.needs_input_grad)  # all False under torch.no_grad()
+        need_grad = mod._grad_mode and any(ctx.needs_input_grad)
         f32 = lambda n: torch.empty(max(int(n), 1), dtype=torch.float32, device=dev)
         out_h, out_chi = torch.empty_like(h), torch.empty_like(chi)
         out_pos = torch.empty_like(pos) if spec.has_pos else None
@@ -366,6 +366,7 @@ class GCPInteractions(nn.Module):
             out = ScalarVector(h.clone(), chi.clone())
             return (out, node_pos.clone()) if self.updating_node_positions else out
         gv = graph_views(edge_index, frames, N)
+        self._grad_mode = torch.is_grad_enabled()  # Function.forward itself always runs with grad disabled
         outs = _LayerFn.apply(self, gv, h, chi, e, xi, frames, node_pos, *self._params_in_order())
         if self.updating_node_positions:
             return ScalarVector(outs[0], outs[1]), outs[2]

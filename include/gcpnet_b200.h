@@ -99,6 +99,8 @@ typedef struct gcpnet_plan {
   int64_t edge_cotangent_floats; /* 2 * E * (s+3v): per-edge cotangents of the gathered node features */
   int64_t agg_cotangent_floats;  /* N * (s+3v) */
   int64_t packed_floats;         /* packed (chunked, padded) copy of the layer's weights, rewritten by every forward */
+  int32_t tc_edge_path;          /* 1: this layer's edge kernels can run on the tcgen05 tensor-core path */
+  int32_t reserved;
 } gcpnet_plan;
 
 typedef struct gcpnet_forward_io {
@@ -129,6 +131,9 @@ uint64_t gcpnet_launch_count(void);
  * 5 partial reduce, 6 graph build.  read() waits for the recorded events, returns their summed
  * elapsed time and count, and clears them.  Keep disabled during CUDA-graph capture. */
 void gcpnet_profile_enable(int on);
+/* Runtime options: "tc" = 1/0 use / do not use the tensor-core (tcgen05, 3xTF32) edge kernels where the plan
+ * allows them (default 1).  Returns the previous value, -1 for an unknown option. */
+int gcpnet_set_option(const char* name, int value);
 int gcpnet_profile_read(int which, double* total_ms, int64_t* launches);
 
 /* CSR build (replaces the index side of torch_scatter.scatter, gcpnet.py:946 and comp/__init__.py:316). */
