@@ -23,6 +23,7 @@ static std::atomic<unsigned long long> g_launches{0};
 void gcp_note_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 static std::atomic<int> g_opt_tc{1};
+static std::atomic<long long*> g_tc_dbg{nullptr};
 static std::atomic<bool> g_profile{false};
 static std::mutex g_profile_mu;
 static std::vector<cudaEvent_t> g_profile_ev[T_COUNT];  // begin, end, begin, end, ...
@@ -222,6 +223,7 @@ static int launch_tc_edge_fwd(const gcpnet_graph& g, const LayerPlan& lp, const 
   p.perm = g.perm; p.src = g.src; p.dst = g.dst;
   p.blob = io.packed + lp.v2_packed_floats;
   p.msg = io.msg; p.saved = saved;
+  p.dbg = g_tc_dbg.load(std::memory_order_relaxed);
   return gcp_tc_launch_edge_fwd(p, lp.tc.grid, st);
 }
 
@@ -233,6 +235,7 @@ extern "C" {
 int gcpnet_version(void) { return 200; }
 const char* gcpnet_last_error(void) { return g_last_error.c_str(); }
 void gcpnet_profile_enable(int on) { g_profile.store(on != 0); }
+void gcpnet_debug_stamps(long long* device_buffer) { g_tc_dbg.store(device_buffer); }
 int gcpnet_set_option(const char* name, int value) {
   if (name && std::string(name) == "tc") return g_opt_tc.exchange(value);
   return -1;

@@ -10,6 +10,8 @@
 
 using namespace gcp;
 
+constexpr int TC_CS = 4;  // threads per tile row
+
 static int tc_set_smem(const void* kernel, int bytes) {
   static std::mutex mu;
   static std::map<std::pair<const void*, int>, int> done;
@@ -33,8 +35,8 @@ int gcp_tc_launch_pack(const tc::TcPackProg& prog, cudaStream_t st) {
 
 int gcp_tc_launch_edge_fwd(const tc::TcEdgeParams& p, int grid, cudaStream_t st) {
   const int bytes = p.smem_floats * 4;
-  if (tc_set_smem((const void*)tc::tc_edge_fwd_kernel<2>, bytes)) return 1;
-  tc::tc_edge_fwd_kernel<2><<<grid, 256, bytes, st>>>(p);
+  if (tc_set_smem((const void*)tc::tc_edge_fwd_kernel<TC_CS>, bytes)) return 1;
+  tc::tc_edge_fwd_kernel<TC_CS><<<grid, 128 * TC_CS, bytes, st>>>(p);
   gcp_note_launches(1);
   CUDA_TRY(cudaGetLastError());
   return 0;

@@ -147,6 +147,16 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, float a, float b, float
                ::"r"(taddr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)) : "memory");
 }
 
+// one lane of a converged warp (warp-uniform control flow around it keeps descriptor math on the uniform datapath)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// value of lane 0, provably warp-uniform for the compiler
+__device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ int uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // ---- mbarrier helpers (shared::cta) ---------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");

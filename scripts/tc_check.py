@@ -38,6 +38,20 @@ def run(cfg, ei, n, seed, label, timing=False):
         print(f"{label}: tc={tc} out_h rel {rel_err(res[tc][0].numpy(), wh.numpy()):.2e} out_chi rel {rel_err(res[tc][1].numpy(), wchi.numpy()):.2e}",
               flush=True)
     if timing:
+        import ctypes as C
+        lib.gcpnet_debug_stamps.argtypes = [C.c_void_p]
+        stamps = torch.zeros(12 * 16, dtype=torch.int64, device=dev)
+        lib.gcpnet_set_option(b"tc", 1)
+        lib.gcpnet_debug_stamps(stamps.data_ptr())
+        fwd(); fwd()
+        torch.cuda.synchronize()
+        lib.gcpnet_debug_stamps(None)
+        st = stamps.cpu().view(12, 16)
+        names = ["gather", "sync", "issue_v", "wait_v", "epiA", "sync", "issue_s", "wait_s", "epiB"]
+        for k in range(8):
+            row = st[k]
+            d = [int(row[i + 1] - row[i]) for i in range(8)]
+            print(f"  GCP{k} cycles: " + " ".join(f"{n}={v}" for n, v in zip(names[1:], d)) + f" | total {int(row[8] - row[0])}", flush=True)
         for tc in (0, 1):
             lib.gcpnet_set_option(b"tc", tc)
             for _ in range(3):
