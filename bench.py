@@ -207,8 +207,8 @@ def build_stack(w, device):
     return layers
 
 
-def step_fn(layers, w, dev_batch):
-    """graph views + L x forward + loss + backward, everything on the current stream."""
+def loss_fn(layers, w, dev_batch):
+    """frames + graph views + L x forward + loss, everything on the current stream."""
     import gcpnet_b200
     b = dev_batch
     frames = gcpnet_b200.localize(b["pos"], b["edge_index"])
@@ -218,7 +218,11 @@ def step_fn(layers, w, dev_batch):
             (h, chi), pos = layer((h, chi), (e, xi), b["edge_index"], frames, node_pos=pos)
         else:
             h, chi = layer((h, chi), (e, xi), b["edge_index"], frames)
-    loss = h.sum() + chi.sum() + (pos.sum() if w["pos"] else 0.0)
+    return h.sum() + chi.sum() + (pos.sum() if w["pos"] else 0.0)
+
+
+def step_fn(layers, w, dev_batch):
+    loss = loss_fn(layers, w, dev_batch)
     loss.backward()
     return loss
 
@@ -262,12 +266,28 @@ def run_ours(args, w):
     dbatch = to_dev()
     torch.cuda.synchronize()
 
-    def one_step(batch):
+    def eager_step(batch):
         for p in params:
             p.grad = None
         for k in ("h", "chi", "e", "xi"):
             batch[k].grad = None
         loss = step_fn(layers, w, batch)
+        allreduce_grads()
+        return loss
+
+    # The whole step (frames, CSR views, L x forward, loss, L x backward) is one CUDA graph: at 5 120 edges per
+    # batch the eager path is bound by Python/launch overhead, not by the kernels.
+    graphed = None
+    launches_per_step = None
+    if not args.no_graph:
+        l0 = lib.gcpnet_launch_count()
+        graphed = gcpnet_b200.GraphedStep(lambda b: loss_fn(layers, w, b), dbatch, params, warmup=max(args.warmup, 3))
+        launches_per_step = (lib.gcpnet_launch_count() - l0) // (max(args.warmup, 3) + 1)
+
+    def one_step(batch):
+        if graphed is None:
+            return eager_step(batch)
+        loss = graphed(batch if batch is not dbatch else None)
         allreduce_grads()
         return loss
 
@@ -287,7 +307,6 @@ def run_ours(args, w):
         sampler.start()
     barrier()
     launches0 = lib.gcpnet_launch_count()
-    lib.gcpnet_profile_enable(1)  # per-kernel CUDA events on the launching stream, over this timed region
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for a, b in ev:
         flush.zero_()
@@ -296,7 +315,35 @@ def run_ours(args, w):
         b.record()
     barrier()
     launches = lib.gcpnet_launch_count() - launches0
+    if graphed is not None:
+        launches = launches_per_step * args.steps  # replays re-launch the captured kernels
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    # ---- end to end: pinned host inputs -> device, step, loss -> host, every step ---------------
+    barrier()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    losses = []
+    for a, b in ev2:
+        flush.zero_()
+        a.record()
+        if graphed is not None:
+            loss = one_step(host)        # pinned host tensors -> the graph's static device buffers (async copies), replay
+        else:
+            loss = one_step(to_dev())
+        losses.append(float(loss.detach()))  # device -> host read of the step's result (synchronises)
+        b.record()
+    barrier()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
+    # ---- per-kernel CUDA events (same workload, same stream; eager launches because events inside a replayed graph
+    #      cannot bracket single kernels): the roofline leg
+    lib.gcpnet_profile_enable(1)
+    evk = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in evk:
+        flush.zero_()
+        a.record()
+        eager_step(dbatch)
+        b.record()
+    barrier()
+    eager_ms = sum(a.elapsed_time(b) for a, b in evk)
     lib.gcpnet_profile_enable(0)
     kernel_ms = {}
     import ctypes as C
@@ -306,19 +353,6 @@ def run_ours(args, w):
         _lib.check(lib.gcpnet_profile_read(which, C.byref(tot), C.byref(cnt)), "gcpnet_profile_read")
         kernel_ms[name] = (tot.value, cnt.value)
 
-    # ---- end to end: pinned host inputs -> device, step, loss -> host, every step ---------------
-    barrier()
-    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    losses = []
-    for a, b in ev2:
-        flush.zero_()
-        a.record()
-        batch = to_dev()
-        loss = one_step(batch)
-        losses.append(float(loss.detach()))  # device -> host read of the step's result (synchronises)
-        b.record()
-    barrier()
-    e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
     clocks = sampler.stop() if rank == 0 else None
 
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
@@ -352,7 +386,9 @@ def run_ours(args, w):
                     "frac": gbs / peak, "traffic": None,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured, burst copy)" if peaks else "of fallback 6.65 TB/s",
                     "algorithmic_bytes_per_launch": alg, "us_per_launch": us, "launches_timed": cnt,
-                    "kernel_share_of_step": tot_ms / dev_ms,
+                    "kernel_share_of_step": tot_ms / eager_ms,
+                    "kernel_timing": "CUDA events around every launch of the kernel in an eager pass of the same steps "
+                                     f"({eager_ms / args.steps:.3f} ms/step eager vs {dev_ms / args.steps:.3f} ms/step graph replay)",
                     "kernel_ms_per_step": {k: t / args.steps for k, (t, _) in kernel_ms.items()},
                     "note": "fused path is compute-bound (~350 FLOP/B, SURVEY 8d): HBM fraction reported as the "
                             "contract asks; see DESIGN.md for the FLOP-side roofline"}
@@ -364,6 +400,7 @@ def run_ours(args, w):
             "config": {"workload": f"{args.workload}: {w['desc']}", "layers": L, "nodes_per_gpu": N, "edges_per_gpu": E,
                        "node_dims": [s, v], "edge_dims": [se, ve], "train_mode_dropout": 0.1,
                        "l2": "flushed (256 MiB write) before every timed step", "timing": "CUDA events per step, summed",
+                       "launch": "whole step replayed as one CUDA graph" if graphed is not None else "eager launches",
                        "parallelism": f"graph-sharded dp{world}, NCCL all-reduce of the {flat_grad_elems * 4} B gradient"},
             "per_layer_edges_per_s": world * E * L * args.steps / (dev_ms * 1e-3) / 1.0,
             "e2e": {"value": world * units * args.steps / (e2e_ms * 1e-3), "unit": "edge-layers/s",
@@ -383,6 +420,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying one CUDA graph per step")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(NT, 1) node_bwd_kernel(const __grid_constant__
 }
 
 __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackParams p) {
-  pack_gcp<256>(p.ops[blockIdx.x], p.blob);
+  pack_gcp<256>(p.ops[blockIdx.x], p.blob, (int)blockIdx.y, (int)gridDim.y);
 }
 
 // aggregate only (GCPMessagePassing.forward): out[i] = mean/sum over the destination segment
@@ -202,7 +202,7 @@ static int launch_node_bwd(const NodeParams& p, const NodeTilePlan& tp, cudaStre
 }
 static int launch_pack(const LayerOps& ops, float* blob, cudaStream_t st) {
   const PackParams pp = make_pack_params(ops, blob);
-  pack_kernel<<<pp.n, 256, 0, st>>>(pp);
+  pack_kernel<<<dim3(pp.n, 16), 256, 0, st>>>(pp);
   gcp_note_launches(1);
   CUDA_TRY(cudaGetLastError());
   return 0;

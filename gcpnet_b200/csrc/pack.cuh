@@ -47,14 +47,15 @@ GCP_HD float pack_WS(const GcpOp& op, int c, int idx) {
   return n < op.so ? GCP_LDG(op.bs + n) : 0.f;
 }
 
-// one CTA (or one host call) packs one GCP
+// `nslices` CTAs (or one host call with nslices = 1) pack one GCP; slice = which CTA this is
 template <int NT>
-GCP_HDN void pack_gcp(const GcpOp& op, float* blob) {
+GCP_HDN void pack_gcp(const GcpOp& op, float* blob, int slice = 0, int nslices = 1) {
   GCP_PHASE_BEGIN(NT)
-  for (int i = tid; i < op.w.S.floats; i += NT) blob[op.w.S.off + i] = pack_S(op, i);
-  for (int i = tid; i < op.w.G.floats; i += NT) blob[op.w.G.off + i] = pack_G(op, i);
+  const int t0 = slice * NT + tid, step = nslices * NT;
+  for (int i = t0; i < op.w.S.floats; i += step) blob[op.w.S.off + i] = pack_S(op, i);
+  for (int i = t0; i < op.w.G.floats; i += step) blob[op.w.G.off + i] = pack_G(op, i);
   for (int c = 0; c < op.w.nWS; ++c)
-    for (int i = tid; i < op.w.ws_floats; i += NT) blob[op.w.ws_off + c * op.w.ws_stride + i] = pack_WS(op, c, i);
+    for (int i = t0; i < op.w.ws_floats; i += step) blob[op.w.ws_off + c * op.w.ws_stride + i] = pack_WS(op, c, i);
   GCP_PHASE_END
 }
 

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const __grid_constant__ Tc
   const TcPackItem& it = prog.it[blockIdx.x];
   float* blob = prog.blob;
   if (it.kind == PK_BIAS) {  // [bs (R) | composed gate bias (16)]
-    for (int i = threadIdx.x; i < it.R + 16; i += 256) {
+    for (int i = blockIdx.y * 256 + threadIdx.x; i < it.R + 16; i += 256 * gridDim.y) {
       float val = 0.f;
       if (i < it.R) { if (i < it.nreal) val = __ldg(it.w + i); }
       else if (i - it.R < it.vo) {
@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const __grid_constant__ Tc
     return;
   }
   const int total = it.R * it.C;
-  for (int idx = threadIdx.x; idx < total; idx += 256) {
+  for (int idx = blockIdx.y * 256 + threadIdx.x; idx < total; idx += 256 * gridDim.y) {
     const int n = idx % it.R, kk = idx / it.R;
     float val = 0.f;
     for (int rg = 0; rg < it.nrange; ++rg) {

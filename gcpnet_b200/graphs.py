@@ -1,0 +1,61 @@
+"""Whole-step CUDA-graph capture for models built from ``gcpnet_b200.GCPInteractions`` layers.
+
+Every C-ABI call of this package only enqueues kernels on the current stream (no allocation, no
+host synchronisation), so a complete training step -- frames, CSR views, L x layer forward, loss,
+L x backward -- can be recorded once and replayed with a single launch.  At NMS-small sizes
+(5 120 edges per batch) the step is launch-bound otherwise (hard part 3).
+
+    step = GraphedStep(lambda b: loss_fn(model(b)), static_batch)
+    loss = step(new_batch)        # copies new_batch into the static buffers, replays, returns the loss tensor
+
+The callable must be shape-stable (same N, E per replay: bucket / pad batches as the north-star
+prescribes) and must not synchronise.  Parameter gradients land in ``p.grad`` (static tensors that every
+replay overwrites), ready for an optimizer step or an NCCL all-reduce after the replay.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Iterable, Optional
+
+import torch
+
+from . import _lib
+from .interactions import clear_graph_cache
+
+
+class GraphedStep:
+    def __init__(self, fn: Callable[[Dict[str, torch.Tensor]], torch.Tensor], static_batch: Dict[str, torch.Tensor],
+                 params: Optional[Iterable[torch.nn.Parameter]] = None, warmup: int = 3):
+        self.fn = fn
+        self.batch = static_batch
+        self.params = list(params) if params is not None else []
+        lib = _lib.load()
+        lib.gcpnet_profile_enable(0)  # per-kernel events are not capturable
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                self._zero_grads()
+                fn(self.batch).backward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._zero_grads()
+        clear_graph_cache()  # CSR views must be rebuilt inside the capture (their memory has to come from the graph's pool)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = fn(self.batch)
+            self.loss.backward()
+        clear_graph_cache()
+
+    def _zero_grads(self):
+        for p in self.params:
+            p.grad = None
+        for t in self.batch.values():
+            if t.is_floating_point() and t.requires_grad:
+                t.grad = None
+
+    def __call__(self, new_batch: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+        if new_batch is not None:
+            for k, t in new_batch.items():
+                self.batch[k].detach().copy_(t, non_blocking=True)
+        self.graph.replay()
+        return self.loss
