@@ -210,6 +210,7 @@ static int launch_pack(const LayerOps& ops, float* blob, cudaStream_t st) {
 static bool use_tc(const LayerPlan& lp) { return lp.tc.ok && g_opt_tc.load(std::memory_order_relaxed) != 0; }
 int gcp_tc_launch_pack(const tc::TcPackProg& prog, cudaStream_t st);                      // tc_api.cu
 int gcp_tc_launch_edge_fwd(const tc::TcEdgeParams& p, int grid, cudaStream_t st);          // tc_api.cu
+int gcp_tc_launch_node_pre(const tc::TcEdgeParams& p, float* P, float* Q, cudaStream_t st);  // tc_api.cu
 static int launch_tc_pack(const LayerPlan& lp, float* packed, cudaStream_t st) {
   tc::TcPackProg prog = lp.tc.pack;
   prog.blob = packed + lp.v2_packed_floats;
@@ -224,6 +225,10 @@ static int launch_tc_edge_fwd(const gcpnet_graph& g, const LayerPlan& lp, const 
   p.blob = io.packed + lp.v2_packed_floats;
   p.msg = io.msg; p.saved = saved;
   p.dbg = g_tc_dbg.load(std::memory_order_relaxed);
+  float* pq = io.packed + lp.v2_packed_floats + tc::rup(lp.tc.blob_floats, 32);  // per-node products of message GCP 0
+  float* Pn = pq; float* Qn = pq + (size_t)p.N * 2 * p.pw;
+  p.P = Pn; p.Q = Qn;
+  if (gcp_tc_launch_node_pre(p, Pn, Qn, st)) return 1;
   return gcp_tc_launch_edge_fwd(p, lp.tc.grid, st);
 }
 

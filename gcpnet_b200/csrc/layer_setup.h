@@ -263,7 +263,7 @@ inline std::string make_layer_plan(const gcpnet_layer& l, long long N, long long
   okE = pick_edge_tile(l, lp->ops, E, false, 0, &lp->ef) && pick_edge_tile(l, lp->ops, E, true, 0, &lp->eb);
   okN = pick_node_tile(l, lp->ops, N, false, &lp->nf) && pick_node_tile(l, lp->ops, N, true, &lp->nb);
   if (!okE || !okN) return "feature dims too large for the shared-memory tile plan of this build";
-  lp->tc = tc::make_tc_plan(l, E);
+  lp->tc = tc::make_tc_plan(l, N, E);
   lp->v2_packed_floats = round_up(lp->ops.packed_floats, 32);
   if (plan) {
     gcpnet_plan p{};
@@ -282,7 +282,7 @@ inline std::string make_layer_plan(const gcpnet_layer& l, long long N, long long
     p.node_partial_floats = (long long)p.node_grid_bwd * l.n_node_params;
     p.edge_cotangent_floats = 2 * E * W;
     p.agg_cotangent_floats = N * W;
-    p.packed_floats = lp->v2_packed_floats + (lp->tc.ok ? lp->tc.blob_floats : 0);
+    p.packed_floats = lp->v2_packed_floats + (lp->tc.ok ? tc::rup(lp->tc.blob_floats, 32) + lp->tc.pq_floats : 0);
     p.tc_edge_path = lp->tc.ok ? 1 : 0;
     *plan = p;
   }

@@ -33,6 +33,15 @@ int gcp_tc_launch_pack(const tc::TcPackProg& prog, cudaStream_t st) {
   return 0;
 }
 
+int gcp_tc_launch_node_pre(const tc::TcEdgeParams& p, float* P, float* Q, cudaStream_t st) {
+  const long long total = (long long)p.N * (2 * p.pw + 192);
+  if (total <= 0) return 0;
+  tc::tc_node_pre_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(p.h, p.chi, p.blob, p.nt, p.N, p.s, p.v, p.pw, P, Q);
+  gcp_note_launches(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int gcp_tc_launch_edge_fwd(const tc::TcEdgeParams& p, int grid, cudaStream_t st) {
   const int bytes = p.smem_floats * 4;
   if (tc_set_smem((const void*)tc::tc_edge_fwd_kernel<TC_CS>, bytes)) return 1;

@@ -25,8 +25,9 @@
 //   * weights stream through two shared-memory rings filled by cp.async.bulk (small per-GCP tiles; scalar
 //     batch tiles); saved activations (the inputs S, V of every GCP = the shared-memory images) leave
 //     through cp.async.bulk stores.
-//   * message GCP 0 sees [h_row | e | h_col]: its scalar batch runs as three K-segments ([e | n | q], h_row,
-//     h_col) and its vector batch as three channel segments (chi_row, xi, chi_col) into the same accumulators.
+//   * message GCP 0 sees [h_row | e | h_col] and [chi_row | xi | chi_col]: the node-feature blocks are linear maps of
+//     per-NODE data, evaluated once per node by a small pre-kernel (P, Q below) and added in the epilogues; at edge
+//     level GCP 0 is an ordinary GCP over [e | n | q] and xi.
 #pragma once
 
 namespace gcp {
@@ -41,24 +42,25 @@ constexpr int DCOL = 13;         // vector batch accumulator: columns [0,hd) hid
 constexpr int UCOL = 16;         //                           columns [16,32) ungated vector outputs
 constexpr int VN = 32;           // N of the vector batch
 constexpr int NSLOT = 12;        // Z-tile tail: hd -> 4 norm slots (at most 12), then 9 frame scalars, then 3 zero columns
-constexpr int MAX_SEG = 4;
 constexpr int MAX_RSEQ = 64;
 
 struct TcChunk { int off, floats; };  // piece of the packed blob (floats; off multiple of 4)
-struct TcSeg {                        // one K-segment of a scalar batch = one commit
-  int a_tile;                         // 0: Z tile ([e | n | q] for GCP 0, [S | n | q] otherwise), 1: X tile = h_row, 2: X tile = h_col
-  int kc;                             // columns (multiple of 8), starting at column 0 of the tile
-};
 struct TcGcp {
   int si, vi, so, vo, hd, act_s, vres;
   int sop;                            // so -> 16; the scalar batch has N = sop + 16
-  int zc0, nslot;                     // first Z-tile column of the tail [n (nslot) | q (9) | 0 0 0]  (se for GCP 0, si otherwise)
-  int nseg; TcSeg seg[MAX_SEG];
-  int nvseg, vkc[3];                  // vector batch channel segments (multiples of 8)
-  int o_wd_hi[3], o_wd_lo[3];         // offsets (floats) inside the small chunk: B tiles [32][vkc] (slab pitch 32)
-  int o_bs, o_bg;                     // scalar_out bias [sop]; composed gate bias [16]
+  int zc0, nslot, kz;                 // Z tile: tail [n (nslot) | q (9) | 0 0 0] starts at zc0 (se for GCP 0, si otherwise); kz = GEMM K
+  int vkc;                            // K of the vector batch: channels of the V tile read (xi only for GCP 0)
+  // offsets (floats) inside the small chunk
+  int o_wv_hi, o_wv_lo;               // forward  B tile [32][vkc]   (slab pitch 32)
+  int o_wvt_hi, o_wvt_lo;             // backward B tile [vkc][32]   (slab pitch vkc): data gradient of the vector batch
+  int o_b;                            // composed bias [sop + 16]
 };
 struct RingDesc { int n, nslot, slot_floats, pad_; TcChunk c[MAX_RSEQ]; };
+
+// Per-node pre-products of message GCP 0: the h_row / h_col column blocks of scalar_out and
+// the chi_row / chi_col channel blocks of the vector batch do not depend on the edge, so they are evaluated once per
+// NODE and gathered:  P[i] = [src: T-part (sop) g-part (16) | dst: ...],  Q[i] = [src: 3 planes x 32 | dst: 3 planes x 32].
+struct TcNodeTiles { int ps, pd, qs, qd; };  // blob offsets of the B tiles [sop+16][s], [sop+16][s], [32][v8], [32][v8]
 
 struct TcEdgeParams {
   int N, E, L;
@@ -68,17 +70,18 @@ struct TcEdgeParams {
   const float *h, *chi, *e, *xi, *frames;
   const int *perm, *src, *dst;
   const float* blob;
+  const float *P, *Q;                 // [N][2 * (sop + 16)], [N][2 * 96]
+  int pw;                             // sop + 16
   float* msg;                         // [E][s + 3v]
   float* saved;                       // per tile: (L-1) x [S image | V image]; nullptr = inference
   long long* dbg;                     // optional [L][16] clock64 stamps of CTA 0's first tile (development aid)
   long long saved_tile_stride; int s_img, v_img;  // floats
-  int ZBUF, XBUF, VBUF, FBUF, RING_S, RING_W, BARS, smem_floats;   // shared-memory map (floats)
-  int ZLO, XLO, VLO, VACC, TACC, tmem_cols;                        // TMEM column map
+  int ZBUF, VBUF, FBUF, RING_S, RING_W, BARS, smem_floats;   // shared-memory map (floats)
+  int ZLO, VLO, VACC, TACC, tmem_cols;                       // TMEM column map
+  TcNodeTiles nt;
   TcGcp g[12];                        // GCPNET_MAX_MESSAGE_LAYERS
   RingDesc ring_s, ring_w;
 };
-
-
 
 }  // namespace tc
 }  // namespace gcp

@@ -54,9 +54,44 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const __grid_constant__ Tc
         }
       }
     }
-    const int off = ((kk >> 2) * it.R + n) * 4 + (kk & 3);
+    const int off = it.tr ? ((n >> 2) * it.Rt + kk) * 4 + (n & 3) : ((kk >> 2) * it.R + n) * 4 + (kk & 3);
     blob[it.dst_hi + off] = val;
-    blob[it.dst_lo + off] = umma::tf32_lo(val);
+    if (it.dst_lo >= 0) blob[it.dst_lo + off] = umma::tf32_lo(val);
+  }
+  if (it.tr) {  // zero rows [C, Rt) of the transposed tile
+    for (int idx = blockIdx.y * 256 + threadIdx.x; idx < (it.Rt - it.C) * it.R; idx += 256 * gridDim.y) {
+      const int n = idx % it.R, kk = it.C + idx / it.R;
+      const int off = ((n >> 2) * it.Rt + kk) * 4 + (n & 3);
+      blob[it.dst_hi + off] = 0.f;
+      if (it.dst_lo >= 0) blob[it.dst_lo + off] = 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-node pre-products of message GCP 0:  P[i] = [src | dst] x (T-part, g-part),  Q[i] = [src | dst] x 3 planes x 32
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tc_node_pre_kernel(const float* __restrict__ h, const float* __restrict__ chi,
+                                                          const float* __restrict__ blob, TcNodeTiles nt, int N, int s, int v, int pw,
+                                                          float* __restrict__ P, float* __restrict__ Q) {
+  const int per = 2 * pw + 192;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= (long long)N * per) return;
+  const int i = (int)(idx / per), o = (int)(idx - (long long)i * per);
+  float acc = 0.f;
+  if (o < 2 * pw) {
+    const int side = o / pw, c = o - side * pw;
+    const float* B = blob + (side ? nt.pd : nt.ps);  // [pw][s] slab, pitch pw
+    const float* hp = h + (size_t)i * s;
+    for (int j = 0; j < s; ++j) acc = fmaf(__ldg(B + ((j >> 2) * pw + c) * 4 + (j & 3)), __ldg(hp + j), acc);
+    P[(size_t)i * 2 * pw + o] = acc;
+  } else {
+    const int o2 = o - 2 * pw;
+    const int side = o2 / 96, x = (o2 - side * 96) / 32, c = o2 & 31;
+    const float* B = blob + (side ? nt.qd : nt.qs);  // [32][v8] slab, pitch 32
+    const float* cp = chi + (size_t)i * 3 * v + x;
+    for (int ch = 0; ch < v; ++ch) acc = fmaf(__ldg(B + ((ch >> 2) * 32 + c) * 4 + (ch & 3)), __ldg(cp + 3 * ch), acc);
+    Q[(size_t)i * 192 + o2] = acc;
   }
 }
 
@@ -167,8 +202,9 @@ __device__ __forceinline__ void mma3_planes(uint32_t d_tmem, uint32_t d_stride, 
 // ---- epilogue A: vector batch accumulator -> norms + frame scalars into the Z-tile tail ------------------------------
 // VACC: 3 planes x 32 columns; [0, hd) hidden channels H, [13, 16) frame-down vectors D, [16, 32) ungated outputs U.
 // Tail columns (from zc0): nslot norm slots | 9 frame scalars | 3 zeros.  Items: norm groups 0..2, frame scalars.
+// GCP 0: the accumulator only holds the xi part; the chi_row / chi_col parts come from the per-node products qs / qd.
 template <int CS>
-__device__ __forceinline__ void epilogue_a(const TcEdgeParams& p, const TcGcp& g, float* sm, const Who& w) {
+__device__ __forceinline__ void epilogue_a(const TcEdgeParams& p, const TcGcp& g, float* sm, const Who& w, const float* qs, const float* qd) {
   float* Z = sm + p.ZBUF;
   const uint32_t zlo = w.tl + (uint32_t)p.ZLO;
 #pragma unroll
@@ -182,6 +218,13 @@ __device__ __forceinline__ void epilogue_a(const TcEdgeParams& p, const TcGcp& g
 #pragma unroll
         for (int x = 0; x < 3; ++x) tmem_ld4(w.tl + (uint32_t)(p.VACC + VN * x + 4 * item), h[x]);
         wait_ld();
+        if (qs != nullptr) {
+#pragma unroll
+          for (int x = 0; x < 3; ++x) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(qs + 32 * x + 4 * item)), b = __ldg(reinterpret_cast<const float4*>(qd + 32 * x + 4 * item));
+            h[x][0] += a.x + b.x; h[x][1] += a.y + b.y; h[x][2] += a.z + b.z; h[x][3] += a.w + b.w;
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           if (4 * item + i < g.hd)
@@ -194,6 +237,13 @@ __device__ __forceinline__ void epilogue_a(const TcEdgeParams& p, const TcGcp& g
 #pragma unroll
       for (int x = 0; x < 3; ++x) tmem_ld4(w.tl + (uint32_t)(p.VACC + VN * x + 12), d[x]);  // columns 12..15: D at 13..15
       wait_ld();
+      if (qs != nullptr) {
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(qs + 32 * x + 12)), b = __ldg(reinterpret_cast<const float4*>(qd + 32 * x + 12));
+          d[x][0] += a.x + b.x; d[x][1] += a.y + b.y; d[x][2] += a.z + b.z; d[x][3] += a.w + b.w;
+        }
+      }
       const float* F = sm + p.FBUF + w.r * 9;
       float q[12];
 #pragma unroll
@@ -215,11 +265,12 @@ __device__ __forceinline__ void epilogue_a(const TcEdgeParams& p, const TcGcp& g
 // ---- epilogue B: scalar batch accumulator [T | g] + vector batch U -> new scalar state (Z tile), new vector state (V tile)
 template <int CS>
 __device__ __forceinline__ void epilogue_b(const TcEdgeParams& p, const TcGcp& g, float* sm, const Who& w, const float* smc,
-                                           bool add, bool last, long long q, bool live) {
+                                           bool add, bool last, long long q, bool live, const float* ps, const float* pd,
+                                           const float* qs, const float* qd) {
   float* Z = sm + p.ZBUF;
   float* V = sm + p.VBUF;
-  const float* bs = smc + g.o_bs;
-  const float* bg = smc + g.o_bg;
+  const float* bs = smc + g.o_b;
+  const float* bg = smc + g.o_b + g.sop;
   const int W = p.s + 3 * p.v;
   // scalars: S' = (S +) act_s(T + b)   (gcpnet.py:441,465; residual stack :920-924)
   for (int cg = w.part; 16 * cg < g.so; cg += CS) {
@@ -233,6 +284,10 @@ __device__ __forceinline__ void epilogue_b(const TcEdgeParams& p, const TcGcp& g
         const float4 old = add ? get4(Z, w.r, c) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 b4 = *reinterpret_cast<const float4*>(bs + c);
         float sv[4] = {t[4 * i4] + b4.x, t[4 * i4 + 1] + b4.y, t[4 * i4 + 2] + b4.z, t[4 * i4 + 3] + b4.w};
+        if (ps != nullptr) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(ps + c)), b = __ldg(reinterpret_cast<const float4*>(pd + c));
+          sv[0] += a.x + b.x; sv[1] += a.y + b.y; sv[2] += a.z + b.z; sv[3] += a.w + b.w;
+        }
         if (g.act_s == ACT_RELU) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) sv[i] = fmaxf(sv[i], 0.f);
@@ -253,6 +308,15 @@ __device__ __forceinline__ void epilogue_b(const TcEdgeParams& p, const TcGcp& g
 #pragma unroll
     for (int x = 0; x < 3; ++x) tmem_ld4(w.tl + (uint32_t)(p.VACC + VN * x + UCOL + 4 * gi), u[x]);
     wait_ld();
+    if (ps != nullptr) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(ps + g.sop + 4 * gi)), b = __ldg(reinterpret_cast<const float4*>(pd + g.sop + 4 * gi));
+      gt[0] += a.x + b.x; gt[1] += a.y + b.y; gt[2] += a.z + b.z; gt[3] += a.w + b.w;
+#pragma unroll
+      for (int x = 0; x < 3; ++x) {
+        const float4 c = __ldg(reinterpret_cast<const float4*>(qs + 32 * x + UCOL + 4 * gi)), d = __ldg(reinterpret_cast<const float4*>(qd + 32 * x + UCOL + 4 * gi));
+        u[x][0] += c.x + d.x; u[x][1] += c.y + d.y; u[x][2] += c.z + d.z; u[x][3] += c.w + d.w;
+      }
+    }
     float4 old[3];
 #pragma unroll
     for (int x = 0; x < 3; ++x) old[x] = (add || g.vres) ? get4(V + x * PLANE, w.r, 4 * gi) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -311,6 +375,93 @@ __device__ __forceinline__ void gather_planes(float* planes, uint32_t tlo, const
   }
 }
 
+// state every tile kernel carries around
+struct TileCtx {
+  float* sm;
+  Who w;
+  int uwarp;
+  uint32_t tbase;
+  unsigned long long* mma_bar;
+  uint32_t mma_n;   // commits on mma_bar so far (CTA-uniform)
+};
+__device__ __forceinline__ void wait_mma(TileCtx& c) {
+  mbar_wait(c.mma_bar, c.mma_n & 1u);
+  ++c.mma_n;
+  __syncwarp();
+  fence_after_sync();
+}
+
+// Forward of GCP k on the tile: the V tile (and for k > 0 the Z tile's first s columns) hold the inputs; on return they hold
+// the outputs.  `issue_extra` runs in the elected lane right after the vector batch is committed (bulk stores).
+template <int CS, class Extra>
+__device__ __forceinline__ void gcp_forward_tile(const TcEdgeParams& p, int k, TileCtx& c, Ring& rs, Ring& rw, bool add, bool write_state,
+                                                 bool last, long long q, bool live, int src, int dst, int orig, Extra issue_extra,
+                                                 const float** smc_out) {
+  const TcGcp& g = p.g[k];
+  float* sm = c.sm;
+  const Who& w = c.w;
+  float* Z = sm + p.ZBUF; float* V = sm + p.VBUF;
+  const uint32_t tbase = c.tbase;
+  auto stamp = [&](int i) { if (p.dbg != nullptr && blockIdx.x == 0 && w.tid == 0) p.dbg[k * 16 + i] = clock64(); };
+  const float* ps = nullptr; const float* pd = nullptr; const float* qs = nullptr; const float* qd = nullptr;
+  stamp(0);
+  if (k == 0) {
+    // edge vectors -> V tile; frames; per-node products of the two endpoints
+    gather_planes<CS>(V, w.tl + (uint32_t)p.VLO, w, p.xi + (size_t)orig * 3 * p.ve, p.ve, g.vkc, live);
+    if (w.part == CS - 1) {
+      float* F = sm + p.FBUF + w.r * 9;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) F[i] = live ? __ldg(p.frames + (size_t)orig * 9 + i) : 0.f;
+    }
+    ps = p.P + (size_t)src * 2 * p.pw; pd = p.P + (size_t)dst * 2 * p.pw + p.pw;
+    qs = p.Q + (size_t)src * 192; qd = p.Q + (size_t)dst * 192 + 96;
+  }
+  publish_and_sync();
+  stamp(1);
+  const float* smc = ring_wait(rs, uniform(rs.head));  // small chunk of this GCP (every thread reads the bias from it)
+  *smc_out = smc;
+  if (c.uwarp == 0) {
+    if (elect_one()) bulk_store_wait_read();
+    ring_fill(rs);  // every thread is past the previous GCP's last read of its small chunk (barrier above)
+    bool acc = false;
+    mma3_planes(tbase + (uint32_t)p.VACC, VN, V, PLANE, tbase + (uint32_t)p.VLO, PW, smc + g.o_wv_hi, smc + g.o_wv_lo, VN, g.vkc,
+                make_idesc(128, VN, 0, 0), acc);
+    if (elect_one()) {
+      commit(c.mma_bar);
+      issue_extra();
+    }
+    __syncwarp();
+  }
+  stamp(2);
+  wait_mma(c);
+  stamp(3);
+  // ---------------- epilogue A (+ GCP 0: edge scalars into the Z tile)
+  epilogue_a<CS>(p, g, sm, w, qs, qd);
+  if (k == 0) gather_row<CS>(Z, w.tl + (uint32_t)p.ZLO, w, p.e + (size_t)orig * p.se, p.se, p.se, live);
+  stamp(4);
+  publish_and_sync();
+  stamp(5);
+  // ---------------- scalar batch
+  if (c.uwarp == 0) {
+    if (elect_one()) bulk_store_wait_read();
+    ring_fill(rw);
+    const int wh = uniform(rw.head);
+    const float* bh = ring_wait(rw, wh);
+    const float* bl = ring_wait(rw, wh + 1);
+    bool acc = false;
+    mma3(tbase + (uint32_t)p.TACC, Z, tbase + (uint32_t)p.ZLO, bh, bl, g.sop + 16, g.kz, make_idesc(128, g.sop + 16, 0, 0), acc);
+    if (elect_one()) commit(c.mma_bar);
+    __syncwarp();
+  }
+  stamp(6);
+  wait_mma(c);
+  stamp(7);
+  rw.head += 2;
+  // ---------------- epilogue B
+  if (write_state) epilogue_b<CS>(p, g, sm, w, smc, add, last, q, live, ps, pd, qs, qd);
+  stamp(8);
+}
+
 template <int CS>
 __global__ void __launch_bounds__(128 * CS, 1) tc_edge_fwd_kernel(const __grid_constant__ TcEdgeParams p) {
   extern __shared__ __align__(128) float sm[];
@@ -318,20 +469,22 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_fwd_kernel(const __grid_c
   const int ntiles = (p.E + TE - 1) / TE;
   const int mine = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   if (mine == 0) return;
-  Who w;
-  w.tid = (int)threadIdx.x;
-  const int warp = w.tid >> 5, lane = w.tid & 31;
-  w.r = 32 * (warp & 3) + lane;
-  w.part = warp >> 2;
+  TileCtx c;
+  c.sm = sm;
+  c.w.tid = (int)threadIdx.x;
+  const int warp = c.w.tid >> 5, lane = c.w.tid & 31;
+  c.w.r = 32 * (warp & 3) + lane;
+  c.w.part = warp >> 2;
+  c.uwarp = uniform(warp);
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + p.BARS);
-  unsigned long long* mma_bar = bars;  // [0]; ring barriers follow
+  c.mma_bar = bars;  // [0]; ring barriers follow
+  c.mma_n = 0;
   Ring rs{sm + p.RING_S, bars + 1, &p.ring_s, p.blob, 0, 0, mine * p.ring_s.n};
   Ring rw{sm + p.RING_W, bars + 1 + p.ring_s.nslot, &p.ring_w, p.blob, 0, 0, mine * p.ring_w.n};
-  const int uwarp = uniform(warp);
-  if (uwarp == 0) {
+  if (c.uwarp == 0) {
     tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
     if (elect_one()) {
-      mbar_init(mma_bar, 1);
+      mbar_init(c.mma_bar, 1);
       for (int i = 0; i < p.ring_s.nslot; ++i) mbar_init(&rs.bar[i], 1);
       for (int i = 0; i < p.ring_w.nslot; ++i) mbar_init(&rw.bar[i], 1);
       mbar_fence_init();
@@ -344,115 +497,34 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_fwd_kernel(const __grid_c
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tbase = uniform(tmem_slot);
-  w.tl = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
-  uint32_t mma_n = 0;  // commits on mma_bar so far (CTA-uniform)
-  float* Z = sm + p.ZBUF; float* X = sm + p.XBUF; float* V = sm + p.VBUF;
-  const uint32_t idesc_v = make_idesc(128, VN, 0, 0);
-
-  auto stamp = [&](int k, int i) { if (p.dbg != nullptr && blockIdx.x == 0 && w.tid == 0) p.dbg[k * 16 + i] = clock64(); };
-  auto wait_mma = [&]() {
-    mbar_wait(mma_bar, mma_n & 1u);
-    ++mma_n;
-    __syncwarp();
-    fence_after_sync();
-  };
+  c.tbase = uniform(tmem_slot);
+  c.w.tl = c.tbase + ((uint32_t)(32 * (warp & 3)) << 16);
+  float* Z = sm + p.ZBUF; float* V = sm + p.VBUF;
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long q = (long long)tile * TE + w.r;
+    const long long q = (long long)tile * TE + c.w.r;
     const bool live = q < p.E;
     const int src = live ? p.src[q] : 0, dst = live ? p.dst[q] : 0, orig = live ? p.perm[q] : 0;
     float* saved_t = p.saved ? p.saved + (size_t)tile * p.saved_tile_stride : nullptr;
     // the gathers below overwrite tile columns other threads of the row still read in the previous tile's epilogue B
     if (tile != (int)blockIdx.x) { wait_st(); __syncthreads(); }
-
     for (int k = 0; k < p.L; ++k) {
-      const TcGcp& g = p.g[k];
-      const bool last = k == p.L - 1;
-      const bool add = k > 0 && p.residual;
-      stamp(k, 0);
-      // ---------------- vector batch operands (GCP 0: chi_row planes -> Z tile, xi -> V tile, chi_col -> X tile; frames)
-      if (k == 0) {
-        gather_planes<CS>(Z, w.tl + (uint32_t)p.ZLO, w, p.chi + (size_t)src * 3 * p.v, p.v, g.vkc[0], live);
-        gather_planes<CS>(V, w.tl + (uint32_t)p.VLO, w, p.xi + (size_t)orig * 3 * p.ve, p.ve, g.vkc[1], live);
-        gather_planes<CS>(X, w.tl + (uint32_t)p.XLO, w, p.chi + (size_t)dst * 3 * p.v, p.v, g.vkc[2], live);
-        if (w.part == CS - 1) {
-          float* F = sm + p.FBUF + w.r * 9;
-#pragma unroll
-          for (int i = 0; i < 9; ++i) F[i] = live ? __ldg(p.frames + (size_t)orig * 9 + i) : 0.f;
-        }
-      }
-      publish_and_sync();
-      stamp(k, 1);
-      const float* smc = ring_wait(rs, uniform(rs.head));  // small chunk of this GCP (every thread: biases are read in epilogue B)
-      if (uwarp == 0) {
-        if (elect_one()) bulk_store_wait_read();
-        ring_fill(rs);  // every thread is past the previous GCP's epilogue B (barrier above): that slot is free
-        {
-          bool acc = false;
-          const uint32_t d = tbase + (uint32_t)p.VACC;
-          if (k == 0) {
-            mma3_planes(d, VN, Z, PLANE, tbase + (uint32_t)p.ZLO, PW, smc + g.o_wd_hi[0], smc + g.o_wd_lo[0], VN, g.vkc[0], idesc_v, acc);
-            mma3_planes(d, VN, V, PLANE, tbase + (uint32_t)p.VLO, PW, smc + g.o_wd_hi[1], smc + g.o_wd_lo[1], VN, g.vkc[1], idesc_v, acc);
-            mma3_planes(d, VN, X, PLANE, tbase + (uint32_t)p.XLO, PW, smc + g.o_wd_hi[2], smc + g.o_wd_lo[2], VN, g.vkc[2], idesc_v, acc);
-          } else {
-            mma3_planes(d, VN, V, PLANE, tbase + (uint32_t)p.VLO, PW, smc + g.o_wd_hi[0], smc + g.o_wd_lo[0], VN, g.vkc[0], idesc_v, acc);
-          }
-        }
-        if (elect_one()) {
-          commit(mma_bar);
-          if (k > 0 && saved_t) {  // inputs of this GCP = outputs of the previous one
-            bulk_store(saved_t + (size_t)(k - 1) * (p.s_img + p.v_img), Z, p.s_img);
-            bulk_store(saved_t + (size_t)(k - 1) * (p.s_img + p.v_img) + p.s_img, V, p.v_img);
-          }
-        }
-        __syncwarp();
-      }
-      stamp(k, 2);
-      wait_mma();
-      stamp(k, 3);
-      // ---------------- epilogue A (+ GCP 0: edge scalars into the Z tile)
-      epilogue_a<CS>(p, g, sm, w);
-      if (k == 0) gather_row<CS>(Z, w.tl + (uint32_t)p.ZLO, w, p.e + (size_t)orig * p.se, p.se, p.se, live);
-      stamp(k, 4);
-      publish_and_sync();
-      stamp(k, 5);
-      // ---------------- scalar batch: one commit per K-segment
-      const uint32_t idesc_s = make_idesc(128, g.sop + 16, 0, 0);
-      bool tacc = false;
-      for (int sgi = 0; sgi < g.nseg; ++sgi) {
-        const TcSeg sg = g.seg[sgi];
-        if (sg.a_tile != 0) {  // GCP 0: the X tile takes h_row, then h_col
-          gather_row<CS>(X, w.tl + (uint32_t)p.XLO, w, p.h + (size_t)(sg.a_tile == 1 ? src : dst) * p.s, p.s, sg.kc, live);
-          publish_and_sync();
-        }
-        if (uwarp == 0) {
-          if (elect_one()) bulk_store_wait_read();
-          ring_fill(rw);
-          const int wh = uniform(rw.head);
-          const float* bh = ring_wait(rw, wh);
-          const float* bl = ring_wait(rw, wh + 1);
-          mma3(tbase + (uint32_t)p.TACC, sg.a_tile == 0 ? Z : X, tbase + (uint32_t)(sg.a_tile == 0 ? p.ZLO : p.XLO), bh, bl, g.sop + 16, sg.kc,
-               idesc_s, tacc);
-          if (elect_one()) commit(mma_bar);
-          __syncwarp();
-        }
-        tacc = true;
-        stamp(k, 6);
-        wait_mma();
-        stamp(k, 7);
-        rw.head += 2;
-      }
-      // ---------------- epilogue B
-      epilogue_b<CS>(p, g, sm, w, smc, add, last, q, live);
-      stamp(k, 8);
+      const float* smc;
+      gcp_forward_tile<CS>(p, k, c, rs, rw, k > 0 && p.residual, true, k == p.L - 1, q, live, src, dst, orig,
+                           [&]() {
+                             if (k > 0 && saved_t) {  // inputs of this GCP = outputs of the previous one (published by the barrier)
+                               bulk_store(saved_t + (size_t)(k - 1) * (p.s_img + p.v_img), Z, p.s_img);
+                               bulk_store(saved_t + (size_t)(k - 1) * (p.s_img + p.v_img) + p.s_img, V, p.v_img);
+                             }
+                           },
+                           &smc);
       rs.head += 1;
     }
   }
-  if (uwarp == 0 && elect_one()) bulk_store_wait_all();
+  if (c.uwarp == 0 && elect_one()) bulk_store_wait_all();
   fence_before_sync();
   __syncthreads();
-  if (uwarp == 0) tmem_dealloc(tbase, (uint32_t)p.tmem_cols);
+  if (c.uwarp == 0) tmem_dealloc(c.tbase, (uint32_t)p.tmem_cols);
 }
 
 }  // namespace tc
