@@ -207,7 +207,11 @@ static int launch_pack(const LayerOps& ops, float* blob, cudaStream_t st) {
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
-static bool use_tc(const LayerPlan& lp) { return lp.tc.ok && g_opt_tc.load(std::memory_order_relaxed) != 0; }
+static bool tc_option() { return g_opt_tc.load(std::memory_order_relaxed) != 0; }
+int gcp_tc_launch_edge_bwd(const tc::TcBwdParams& b, int grid, cudaStream_t st);           // tc_api.cu
+int gcp_tc_launch_post(const tc::TcPostParams& p, cudaStream_t st);                        // tc_api.cu
+int gcp_tc_launch_finalize(const float* partial, int rows, int stride, float* G, const float* npartial, int nrows, int nstride, float* Gn,
+                           const tc::TcFinalParams& fp, cudaStream_t st);                  // tc_api.cu
 int gcp_tc_launch_pack(const tc::TcPackProg& prog, cudaStream_t st);                      // tc_api.cu
 int gcp_tc_launch_edge_fwd(const tc::TcEdgeParams& p, int grid, cudaStream_t st);          // tc_api.cu
 int gcp_tc_launch_node_pre(const tc::TcEdgeParams& p, float* P, float* Q, cudaStream_t st);  // tc_api.cu
@@ -216,20 +220,64 @@ static int launch_tc_pack(const LayerPlan& lp, float* packed, cudaStream_t st) {
   prog.blob = packed + lp.v2_packed_floats;
   return gcp_tc_launch_pack(prog, st);
 }
+static void fill_tc_common(tc::TcEdgeParams& p, const gcpnet_graph& g, const LayerPlan& lp, const float* h, const float* chi, const float* e,
+                           const float* xi, const float* frames, const float* packed) {
+  p.N = (int)g.num_nodes; p.E = (int)g.num_edges;
+  p.h = h; p.chi = chi; p.e = e; p.xi = xi; p.frames = frames;
+  p.perm = g.perm; p.src = g.src; p.dst = g.dst;
+  p.blob = packed + lp.v2_packed_floats;
+  const float* pq = packed + lp.v2_packed_floats + tc::rup(lp.tc.blob_floats, 32);  // per-node products of message GCP 0
+  p.P = pq; p.Q = pq + (size_t)p.N * 2 * p.pw;
+}
 static int launch_tc_edge_fwd(const gcpnet_graph& g, const LayerPlan& lp, const gcpnet_forward_io& io, float* saved, cudaStream_t st) {
   GcpTimedScope timed(T_EDGE_FWD, st);
   tc::TcEdgeParams p = lp.tc.proto;
-  p.N = (int)g.num_nodes; p.E = (int)g.num_edges;
-  p.h = io.h; p.chi = io.chi; p.e = io.e; p.xi = io.xi; p.frames = io.frames;
-  p.perm = g.perm; p.src = g.src; p.dst = g.dst;
-  p.blob = io.packed + lp.v2_packed_floats;
+  fill_tc_common(p, g, lp, io.h, io.chi, io.e, io.xi, io.frames, io.packed);
   p.msg = io.msg; p.saved = saved;
   p.dbg = g_tc_dbg.load(std::memory_order_relaxed);
-  float* pq = io.packed + lp.v2_packed_floats + tc::rup(lp.tc.blob_floats, 32);  // per-node products of message GCP 0
-  float* Pn = pq; float* Qn = pq + (size_t)p.N * 2 * p.pw;
-  p.P = Pn; p.Q = Qn;
-  if (gcp_tc_launch_node_pre(p, Pn, Qn, st)) return 1;
+  if (gcp_tc_launch_node_pre(p, const_cast<float*>(p.P), const_cast<float*>(p.Q), st)) return 1;
   return gcp_tc_launch_edge_fwd(p, lp.tc.grid, st);
+}
+// tensor-core edge backward + node-level finish of message GCP 0 + chain rule to the reference's parameters
+static int run_tc_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, const LayerPlan& lp, const gcpnet_backward_io& io, cudaStream_t st) {
+  const tc::TcPlan& T = lp.tc;
+  float* Y = io.ws_edge;
+  float* A = Y + T.y_floats;
+  float* G = A + T.a_floats;
+  float* Gn = G + T.bproto.partial_stride;
+  float* npart = Gn + T.node_partial_stride;
+  {
+    GcpTimedScope timed(T_EDGE_BWD, st);
+    tc::TcBwdParams b = T.bproto;
+    fill_tc_common(b.f, g, lp, io.h, io.chi, io.e, io.xi, io.frames, io.packed);
+    b.f.saved = const_cast<float*>(io.saved_edge);
+    b.f.msg = nullptr; b.f.dbg = nullptr;
+    b.gagg = io.ws_agg; b.dst_ptr = g.dst_ptr;
+    b.ge = io.g_e; b.gxi = io.g_xi; b.Y = Y; b.partial = io.ws_edge_partial;
+    if (gcp_tc_launch_edge_bwd(b, T.grid, st)) return 1;
+  }
+  GcpTimedScope timed(T_COT_REDUCE, st);
+  tc::TcPostParams pp{};
+  pp.N = (int)g.num_nodes; pp.s = l.s; pp.v = l.v; pp.pw = T.proto.pw;
+  pp.Y = Y; pp.y_img_g = T.bproto.y_img_g; pp.y_img_v = T.bproto.y_img_v;
+  pp.dst_ptr = g.dst_ptr; pp.src_ptr = g.src_ptr; pp.src_pos = g.src_pos;
+  pp.h = io.h; pp.chi = io.chi; pp.blob = io.packed + lp.v2_packed_floats; pp.nt = T.proto.nt;
+  pp.A = A; pp.g_h = io.g_h; pp.g_chi = io.g_chi;
+  pp.npartial = npart; pp.npartial_stride = T.node_partial_stride; pp.nctas = T.node_partial_ctas;
+  if (gcp_tc_launch_post(pp, st)) return 1;
+  tc::TcFinalParams fp{};
+  fp.L = l.num_message_layers; fp.s = l.s; fp.v = l.v; fp.se = l.se; fp.ve = l.ve; fp.pw = T.proto.pw; fp.n_edge_params = l.n_edge_params;
+  fp.G = G; fp.Gn = Gn; fp.out = io.g_params;
+  for (int k = 0; k < fp.L; ++k) {
+    const gcpnet_gcp2& d = l.message[k];
+    const tc::TcGcp& tg = T.proto.g[k];
+    tc::TcFinalGcp& f = fp.g[k];
+    f.si = d.si; f.vi = d.vi; f.so = d.so; f.vo = d.vo; f.hd = d.hd; f.nslot = tg.nslot; f.zc0 = tg.zc0; f.kz = tg.kz;
+    f.off_tg = T.bproto.off_tg[k]; f.off_v = T.bproto.off_v[k];
+    for (int i = 0; i < 7; ++i) f.grad_off[i] = d.grad_off[i];
+    f.Wd = d.vector_down; f.Ws = d.scalar_out_w; f.bs = d.scalar_out_b; f.Wu = d.vector_up; f.Wg = d.vector_out_scale_w;
+  }
+  return gcp_tc_launch_finalize(io.ws_edge_partial, T.grid, T.bproto.partial_stride, G, npart, T.node_partial_ctas, T.node_partial_stride, Gn, fp, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -266,7 +314,7 @@ uint64_t gcpnet_launch_count(void) { return g_launches.load(std::memory_order_re
 int gcpnet_layer_plan(const gcpnet_layer* layer, int64_t N, int64_t E, gcpnet_plan* plan) {
   if (!layer || !plan) return fail("layer_plan: null argument");
   LayerPlan lp;
-  const std::string e = make_layer_plan(*layer, N, E, &lp, plan);
+  const std::string e = make_layer_plan(*layer, N, E, &lp, plan, tc_option());
   if (!e.empty()) return fail("layer_plan: " + e);
   return 0;
 }
@@ -274,9 +322,9 @@ int gcpnet_layer_plan(const gcpnet_layer* layer, int64_t N, int64_t E, gcpnet_pl
 static int run_edge_forward(const gcpnet_layer& l, const gcpnet_graph& g, const LayerPlan& lp, const gcpnet_forward_io& io,
                             cudaStream_t st) {
   if (g.num_edges == 0) return 0;
-  if (use_tc(lp) && io.saved_edge == nullptr) {  // inference: tensor-core path (training joins once the backward is on it)
+  if (lp.tc.ok) {  // tensor-core path (the plan decided; workspaces are sized for it)
     if (launch_tc_pack(lp, io.packed, st)) return 1;
-    return launch_tc_edge_fwd(g, lp, io, nullptr, st);
+    return launch_tc_edge_fwd(g, lp, io, io.saved_edge, st);
   }
   EdgeParams p = make_edge_params(l, g, lp.ops, lp.ef, false, io.packed);
   p.h = io.h; p.chi = io.chi; p.e = io.e; p.xi = io.xi; p.frames = io.frames;
@@ -292,7 +340,7 @@ int gcpnet_layer_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, c
   if (l.has_pos && (!io->pos || !io->out_pos)) return fail("layer_forward: node positions required");
   if (!io->packed) return fail("layer_forward: packed-weight workspace required");
   LayerPlan lp;
-  const std::string e = make_layer_plan(l, graph->num_nodes, graph->num_edges, &lp, nullptr);
+  const std::string e = make_layer_plan(l, graph->num_nodes, graph->num_edges, &lp, nullptr, plan->tc_edge_path != 0);
   if (!e.empty()) return fail("layer_forward: " + e);
   if (graph->num_nodes <= 0) return 0;
   if (launch_pack(lp.ops, io->packed, st)) return 1;
@@ -309,7 +357,7 @@ int gcpnet_message_passing_forward(const gcpnet_layer* layer, const gcpnet_graph
   cudaStream_t st = (cudaStream_t)stream;
   if (!io->packed) return fail("message_passing_forward: packed-weight workspace required");
   LayerPlan lp;
-  const std::string e = make_layer_plan(*layer, graph->num_nodes, graph->num_edges, &lp, nullptr);
+  const std::string e = make_layer_plan(*layer, graph->num_nodes, graph->num_edges, &lp, nullptr, plan->tc_edge_path != 0);
   if (!e.empty()) return fail("message_passing_forward: " + e);
   if (graph->num_nodes <= 0) return 0;
   if (launch_pack(lp.ops, io->packed, st)) return 1;
@@ -333,7 +381,7 @@ int gcpnet_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, 
   if (!io->saved_node) return fail("layer_backward: forward ran without saved activations");
   if (!io->packed) return fail("layer_backward: packed weights of the forward call required");
   LayerPlan lp;
-  const std::string e = make_layer_plan(l, g.num_nodes, g.num_edges, &lp, nullptr);
+  const std::string e = make_layer_plan(l, g.num_nodes, g.num_edges, &lp, nullptr, plan->tc_edge_path != 0);
   if (!e.empty()) return fail("layer_backward: " + e);
   if (g.num_nodes <= 0) return 0;
   const int W = l.s + 3 * l.v;
@@ -345,6 +393,15 @@ int gcpnet_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, 
   np.partial = io->ws_node_partial;
   if (launch_node_bwd(np, lp.nb, st)) return 1;
   int edge_grid = 0;
+  if (g.num_edges > 0 && lp.tc.ok) {
+    if (run_tc_edge_backward(l, g, lp, *io, st)) return 1;
+    GcpTimedScope timed(T_PARTIAL_REDUCE, st);
+    partial_reduce_kernel<<<(l.n_node_params + 255) / 256, 256, 0, st>>>(io->g_params + l.n_edge_params, nullptr, 0, 0, io->ws_node_partial,
+                                                                         l.n_node_params, lp.nb.grid);
+    gcp_note_launches(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
   if (g.num_edges > 0) {
     EdgeParams ep = make_edge_params(l, g, lp.ops, lp.eb, true, io->packed);
     ep.h = io->h; ep.chi = io->chi; ep.e = io->e; ep.xi = io->xi; ep.frames = io->frames;

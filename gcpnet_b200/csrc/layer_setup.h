@@ -235,7 +235,8 @@ struct LayerPlan {
   int v2_packed_floats;
 };
 
-inline std::string make_layer_plan(const gcpnet_layer& l, long long N, long long E, LayerPlan* lp, gcpnet_plan* plan) {
+inline std::string make_layer_plan(const gcpnet_layer& l, long long N, long long E, LayerPlan* lp, gcpnet_plan* plan,
+                                   bool tc_allowed = true) {
   std::string e = check_layer(l);
   if (!e.empty()) return e;
   // The packed layout (hence the ring-slot size) is shared by forward and backward: take the largest
@@ -264,6 +265,7 @@ inline std::string make_layer_plan(const gcpnet_layer& l, long long N, long long
   okN = pick_node_tile(l, lp->ops, N, false, &lp->nf) && pick_node_tile(l, lp->ops, N, true, &lp->nb);
   if (!okE || !okN) return "feature dims too large for the shared-memory tile plan of this build";
   lp->tc = tc::make_tc_plan(l, N, E);
+  if (!tc_allowed) lp->tc.ok = false;
   lp->v2_packed_floats = round_up(lp->ops.packed_floats, 32);
   if (plan) {
     gcpnet_plan p{};
@@ -277,10 +279,15 @@ inline std::string make_layer_plan(const gcpnet_layer& l, long long N, long long
     long long offT[MAX_MSG_LAYERS], offG[MAX_MSG_LAYERS], offS[MAX_MSG_LAYERS], offV[MAX_MSG_LAYERS], tot;
     edge_saved_offsets(l, E, offT, offG, offS, offV, &tot);
     p.saved_edge_floats = tot;
+    if (lp->tc.ok) p.saved_edge_floats = lp->tc.saved_floats;
     p.saved_node_floats = node_saved_layout((int)N, l.s, l.v, l.ff0.so, l.ff0.vo, l.has_pos != 0, l.training != 0).total;
     p.edge_partial_floats = (long long)p.edge_grid_bwd * l.n_edge_params;
+    if (lp->tc.ok) p.edge_partial_floats = lp->tc.partial_floats;
     p.node_partial_floats = (long long)p.node_grid_bwd * l.n_node_params;
     p.edge_cotangent_floats = 2 * E * W;
+    if (lp->tc.ok)  // [Y | A | G | Gn | node partials]
+      p.edge_cotangent_floats = lp->tc.y_floats + lp->tc.a_floats + lp->tc.bproto.partial_stride + lp->tc.node_partial_stride +
+                                (long long)lp->tc.node_partial_ctas * lp->tc.node_partial_stride;
     p.agg_cotangent_floats = N * W;
     p.packed_floats = lp->v2_packed_floats + (lp->tc.ok ? tc::rup(lp->tc.blob_floats, 32) + lp->tc.pq_floats : 0);
     p.tc_edge_path = lp->tc.ok ? 1 : 0;

@@ -50,3 +50,32 @@ int gcp_tc_launch_edge_fwd(const tc::TcEdgeParams& p, int grid, cudaStream_t st)
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
+
+int gcp_tc_launch_edge_bwd(const tc::TcBwdParams& b, int grid, cudaStream_t st) {
+  const int bytes = b.f.smem_floats * 4;
+  if (tc_set_smem((const void*)tc::tc_edge_bwd_kernel<TC_CS>, bytes)) return 1;
+  tc::tc_edge_bwd_kernel<TC_CS><<<grid, 128 * TC_CS, bytes, st>>>(b);
+  gcp_note_launches(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// node-level finish of message GCP 0 + reduction of the partials + chain rule to the reference's parameters
+int gcp_tc_launch_post(const tc::TcPostParams& p, cudaStream_t st) {
+  const long long n1 = (long long)p.N * 2 * (p.pw + 96), n2 = (long long)p.N * (p.s + 3 * p.v);
+  tc::tc_post_sum_kernel<<<(int)((n1 + 255) / 256), 256, 0, st>>>(p);
+  tc::tc_post_data_kernel<<<(int)((n2 + 255) / 256), 256, 0, st>>>(p);
+  tc::tc_post_wgrad_kernel<<<p.nctas, 256, 0, st>>>(p);
+  gcp_note_launches(3);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int gcp_tc_launch_finalize(const float* partial, int rows, int stride, float* G, const float* npartial, int nrows, int nstride, float* Gn,
+                           const tc::TcFinalParams& fp, cudaStream_t st) {
+  tc::tc_reduce_kernel<<<(stride + 255) / 256, 256, 0, st>>>(partial, rows, stride, stride, G);
+  tc::tc_reduce_kernel<<<(nstride + 255) / 256, 256, 0, st>>>(npartial, nrows, nstride, nstride, Gn);
+  tc::tc_finalize_kernel<<<(fp.n_edge_params + 255) / 256, 256, 0, st>>>(fp);
+  gcp_note_launches(3);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}

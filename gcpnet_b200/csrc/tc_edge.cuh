@@ -83,5 +83,55 @@ struct TcEdgeParams {
   RingDesc ring_s, ring_w;
 };
 
+// ---- backward -------------------------------------------------------------------------------------------------------
+// Gradients are taken with respect to the COMPOSED matrices the forward uses (chain rule back to the reference's
+// parameters happens once per layer in tc_finalize_kernel):
+//   G_tg[k]  [pw][kz]   = sum_e [gT | gg][e] (x) Z[e]        gT = gS' . act'(T), gg = gate pre-activation cotangent
+//                         (the Z tile's last padding column is set to 1, so column kz-1 of G_tg is the bias gradient)
+//   G_v[k]   [32][16]   = sum_{e,xyz} [gH | gD | gU][e] (x) V_in[e]
+// Data gradients: gZ = [gT | gg] . W_tg (one GEMM, N = kz), gV_in = [gH | gD | gU] . W_v (N = channels).
+struct TcBwdParams {
+  TcEdgeParams f;                     // forward view (recompute): tiles, rings are the BACKWARD ones
+  const float* gagg;                  // [N][s + 3v] cotangent of the aggregated messages
+  const int* dst_ptr;                 // [N+1] (mean reduce: 1 / in-degree)
+  int reduce_mean;
+  float *ge, *gxi;                    // [E][se], [E][3 ve]  caller's edge order
+  float* Y;                           // per tile: [GTG image (pw/4 slabs) | GHDU image (3 planes x 8 slabs)] of message GCP 0
+  int y_img_g, y_img_v;               // floats
+  float* partial;                     // [grid][partial_stride]
+  int partial_stride;
+  int off_tg[12], off_v[12];          // offsets inside a partial row
+  int GTG, GHDU;                      // shared-memory offsets (floats) of the cotangent tiles
+  int GS, GV, GHDULO;                 // TMEM columns; GTG lo aliases f.ZLO, GZACC aliases f.TACC, GVACC aliases f.VLO
+  int kzn[12];                        // N of the scalar data-gradient GEMM (kz -> 16)
+  TcChunk wt_hi[12], wt_lo[12];       // (informational) transposed scalar tiles
+};
+
+struct TcPostParams {
+  int N, s, v, pw;
+  const float* Y; int y_img_g, y_img_v;
+  const int *dst_ptr, *src_ptr, *src_pos;
+  const float *h, *chi, *blob;
+  TcNodeTiles nt;
+  float* A;                 // [N][2][pw + 96]
+  float *g_h, *g_chi;       // accumulated into
+  float* npartial; int npartial_stride, nctas;
+};
+
+// Chain rule from the composed matrices back to the reference's parameters (see TcBwdParams):
+//   W_tg = [Ws ; Wg Ws],  b' = [bs ; Wg bs + bg],  W_v = [Wd ; Wdf (rows 13..15) ; Wu Wd (rows 16..)]
+struct TcFinalGcp {
+  int si, vi, so, vo, hd, nslot, zc0, kz, off_tg, off_v;
+  int grad_off[7];  // vector_down, vector_down_frames, scalar_out_w, scalar_out_b, vector_up, vector_out_scale_w, vector_out_scale_b
+  const float *Wd, *Ws, *bs, *Wu, *Wg;
+};
+struct TcFinalParams {
+  int L, s, v, se, ve, pw, n_edge_params;
+  const float* G;      // reduced edge-level composed gradients (partial row layout)
+  const float* Gn;     // reduced node-level composed gradients of GCP 0: [src: pw x s | dst: pw x s | src: 32 x 16 | dst: 32 x 16]
+  float* out;          // flat parameter gradient (message_fusion part)
+  TcFinalGcp g[12];
+};
+
 }  // namespace tc
 }  // namespace gcp

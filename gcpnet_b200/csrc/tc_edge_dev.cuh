@@ -204,7 +204,8 @@ __device__ __forceinline__ void mma3_planes(uint32_t d_tmem, uint32_t d_stride, 
 // Tail columns (from zc0): nslot norm slots | 9 frame scalars | 3 zeros.  Items: norm groups 0..2, frame scalars.
 // GCP 0: the accumulator only holds the xi part; the chi_row / chi_col parts come from the per-node products qs / qd.
 template <int CS>
-__device__ __forceinline__ void epilogue_a(const TcEdgeParams& p, const TcGcp& g, float* sm, const Who& w, const float* qs, const float* qd) {
+__device__ __forceinline__ void epilogue_a(const TcEdgeParams& p, const TcGcp& g, float* sm, const Who& w, const float* qs, const float* qd,
+                                           bool pad_one = false) {
   float* Z = sm + p.ZBUF;
   const uint32_t zlo = w.tl + (uint32_t)p.ZLO;
 #pragma unroll
@@ -255,7 +256,8 @@ __device__ __forceinline__ void epilogue_a(const TcEdgeParams& p, const TcGcp& g
         if (p.e3 && a == 1) v = fabsf(v);
         q[t] = v;
       }
-      q[9] = q[10] = q[11] = 0.f;
+      q[9] = q[10] = 0.f;
+      q[11] = pad_one ? 1.f : 0.f;  // backward: a column of ones turns the weight-gradient GEMM's last column into the bias gradient
 #pragma unroll
       for (int j = 0; j < 3; ++j) put4(Z, zlo, w.r, g.zc0 + g.nslot + 4 * j, q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
     }
@@ -396,7 +398,7 @@ __device__ __forceinline__ void wait_mma(TileCtx& c) {
 template <int CS, class Extra>
 __device__ __forceinline__ void gcp_forward_tile(const TcEdgeParams& p, int k, TileCtx& c, Ring& rs, Ring& rw, bool add, bool write_state,
                                                  bool last, long long q, bool live, int src, int dst, int orig, Extra issue_extra,
-                                                 const float** smc_out) {
+                                                 const float** smc_out, bool pad_one = false) {
   const TcGcp& g = p.g[k];
   float* sm = c.sm;
   const Who& w = c.w;
@@ -436,7 +438,7 @@ __device__ __forceinline__ void gcp_forward_tile(const TcEdgeParams& p, int k, T
   wait_mma(c);
   stamp(3);
   // ---------------- epilogue A (+ GCP 0: edge scalars into the Z tile)
-  epilogue_a<CS>(p, g, sm, w, qs, qd);
+  epilogue_a<CS>(p, g, sm, w, qs, qd, pad_one);
   if (k == 0) gather_row<CS>(Z, w.tl + (uint32_t)p.ZLO, w, p.e + (size_t)orig * p.se, p.se, p.se, live);
   stamp(4);
   publish_and_sync();
@@ -457,6 +459,7 @@ __device__ __forceinline__ void gcp_forward_tile(const TcEdgeParams& p, int k, T
   wait_mma(c);
   stamp(7);
   rw.head += 2;
+  if (c.uwarp == 0) ring_fill(rw);  // the two slots just released: prefetch while the epilogue runs
   // ---------------- epilogue B
   if (write_state) epilogue_b<CS>(p, g, sm, w, smc, add, last, q, live, ps, pd, qs, qd);
   stamp(8);
@@ -525,6 +528,557 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_fwd_kernel(const __grid_c
   fence_before_sync();
   __syncthreads();
   if (c.uwarp == 0) tmem_dealloc(c.tbase, (uint32_t)p.tmem_cols);
+}
+
+// =====================================================================================================================
+// backward
+// =====================================================================================================================
+constexpr int GPLANE = (VN / 4) * SLAB;  // floats per plane of the [gH | gD | gU] tile (32 columns)
+
+// Legacy-path tensor-core MMA (m16n8k8, tf32) for the weight-gradient products: their reduction runs over the tile's
+// ROWS, an operand orientation tcgen05 only accepts in the 128B-swizzled MN-major layout; the register-fragment MMA reads
+// the slab tiles directly.  3xTF32 with the split done in registers.
+__device__ __forceinline__ void hmma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// c[16 x 8 block at (m0, n0)] += sum over the 128 tile rows e of A[e][m0 + .] * B[e][n0 + .]   (A, B slab tiles)
+__device__ __forceinline__ void wgrad_block(float (&c)[4], const float* A, const float* B, int m0, int n0, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const float* a_lo_row = A + slab_off(RP, t, m0 + g);
+  const float* a_hi_row = A + slab_off(RP, t, m0 + g + 8);
+  const float* b_row = B + slab_off(RP, t, n0 + g);
+#pragma unroll 4
+  for (int k0 = 0; k0 < TE; k0 += 8) {
+    const float fa[4] = {a_lo_row[4 * k0], a_hi_row[4 * k0], a_lo_row[4 * (k0 + 4)], a_hi_row[4 * (k0 + 4)]};
+    const float fb[2] = {b_row[4 * k0], b_row[4 * (k0 + 4)]};
+    uint32_t ah[4], al[4], bh[2], bl[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ah[i] = __float_as_uint(fa[i]) & TF32_MASK; al[i] = __float_as_uint(fa[i] - __uint_as_float(ah[i])); }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { bh[i] = __float_as_uint(fb[i]) & TF32_MASK; bl[i] = __float_as_uint(fb[i] - __uint_as_float(bh[i])); }
+    hmma_tf32(c, ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
+    hmma_tf32(c, al[0], al[1], al[2], al[3], bh[0], bh[1]);
+    hmma_tf32(c, ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
+  }
+}
+// fragment -> this CTA's partial block G[ld columns] at (m0, n0); rows >= mrows / columns >= ncols are dropped
+__device__ __forceinline__ void wgrad_store(const float (&c)[4], float* G, int ld, int m0, int n0, int mrows, int ncols, bool accumulate, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int m = m0 + g + 8 * hh, n = n0 + 2 * t;
+    if (m < mrows && n < ncols) {  // ncols even
+      float2* dp = reinterpret_cast<float2*>(G + (size_t)m * ld + n);
+      float2 v = make_float2(c[2 * hh], c[2 * hh + 1]);
+      if (accumulate) { const float2 o = *dp; v.x += o.x; v.y += o.y; }
+      *dp = v;
+    }
+  }
+}
+
+template <int CS>
+__global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_constant__ TcBwdParams b) {
+  extern __shared__ __align__(128) float sm[];
+  __shared__ uint32_t tmem_slot;
+  const TcEdgeParams& p = b.f;
+  const int ntiles = (p.E + TE - 1) / TE;
+  const int mine = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (mine == 0) return;
+  TileCtx c;
+  c.sm = sm;
+  c.w.tid = (int)threadIdx.x;
+  const int warp = c.w.tid >> 5, lane = c.w.tid & 31;
+  c.w.r = 32 * (warp & 3) + lane;
+  c.w.part = warp >> 2;
+  c.uwarp = uniform(warp);
+  const Who& w = c.w;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + p.BARS);
+  c.mma_bar = bars;
+  unsigned long long* ld_bar = bars + 1;
+  c.mma_n = 0;
+  uint32_t ld_n = 0;
+  Ring rs{sm + p.RING_S, bars + 2, &p.ring_s, p.blob, 0, 0, mine * p.ring_s.n};
+  Ring rw{sm + p.RING_W, bars + 2 + p.ring_s.nslot, &p.ring_w, p.blob, 0, 0, mine * p.ring_w.n};
+  if (c.uwarp == 0) {
+    tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
+    if (elect_one()) {
+      mbar_init(c.mma_bar, 1);
+      mbar_init(ld_bar, 1);
+      for (int i = 0; i < p.ring_s.nslot; ++i) mbar_init(&rs.bar[i], 1);
+      for (int i = 0; i < p.ring_w.nslot; ++i) mbar_init(&rw.bar[i], 1);
+      mbar_fence_init();
+      fence_async_smem();
+    }
+    __syncwarp();
+    ring_fill(rs);
+    ring_fill(rw);
+  }
+  float* Z = sm + p.ZBUF; float* V = sm + p.VBUF; float* GTG = sm + b.GTG; float* GHDU = sm + b.GHDU;
+  // [gH | gD | gU] tile: columns hd..12 are never written below and meet zero weights -- they only have to be finite
+  for (int i = c.w.tid; i < 3 * GPLANE; i += 128 * CS) GHDU[i] = 0.f;
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  c.tbase = uniform(tmem_slot);
+  c.w.tl = c.tbase + ((uint32_t)(32 * (warp & 3)) << 16);
+  const uint32_t tbase = c.tbase;
+  for (int cc = 4 * w.part; cc < 3 * VN; cc += 4 * CS) tmem_st4(w.tl + (uint32_t)(b.GHDULO + cc), 0.f, 0.f, 0.f, 0.f);
+  const int W = p.s + 3 * p.v;
+  float* prow = b.partial + (size_t)blockIdx.x * b.partial_stride;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const bool accumulate = tile != (int)blockIdx.x;
+    const long long q = (long long)tile * TE + w.r;
+    const bool live = q < p.E;
+    const int src = live ? p.src[q] : 0, dst = live ? p.dst[q] : 0, orig = live ? p.perm[q] : 0;
+    const float* saved_t = p.saved + (size_t)tile * p.saved_tile_stride;
+    // ---- cotangent of the final message: gagg[dst] (/ in-degree for the mean reduce, gcpnet.py:946) -> GS, GV (TMEM)
+    {
+      float scale = 0.f;
+      if (live) {
+        scale = 1.f;
+        if (b.reduce_mean) { const int deg = b.dst_ptr[dst + 1] - b.dst_ptr[dst]; scale = 1.f / (float)(deg > 1 ? deg : 1); }
+      }
+      const float* gp = b.gagg + (size_t)dst * W;
+      for (int cc = 4 * w.part; cc < p.s; cc += 4 * CS) {
+        const float4 v = live ? __ldg(reinterpret_cast<const float4*>(gp + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        tmem_st4(w.tl + (uint32_t)(b.GS + cc), v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+      }
+      for (int gi = w.part; gi < (PW >> 2); gi += CS) {
+        float f[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) f[j] = 0.f;
+        if (live && 4 * gi < p.v) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(gp + p.s + 12 * gi + 4 * j));
+            f[4 * j] = v.x * scale; f[4 * j + 1] = v.y * scale; f[4 * j + 2] = v.z * scale; f[4 * j + 3] = v.w * scale;
+          }
+        }
+#pragma unroll
+        for (int x = 0; x < 3; ++x) tmem_st4(w.tl + (uint32_t)(b.GV + PW * x + 4 * gi), f[x], f[3 + x], f[6 + x], f[9 + x]);
+      }
+    }
+    if (w.part == CS - 1) {  // frames of the tile's edges (the forward loads them with GCP 0, which comes LAST here)
+      float* F = sm + p.FBUF + w.r * 9;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) F[i] = live ? __ldg(p.frames + (size_t)orig * 9 + i) : 0.f;
+    }
+    for (int k = p.L - 1; k >= 0; --k) {
+      const TcGcp& g = p.g[k];
+      const bool res = k > 0 && p.residual;
+      // every reader of the Z / V / cotangent tiles of the previous GCP (weight-gradient products) is done
+      wait_st();
+      __syncthreads();
+      // ---- inputs of GCP k: saved images (k > 0) -> Z[:, :s], V; their lo parts -> TMEM
+      if (k > 0) {
+        if (c.uwarp == 0 && elect_one()) {
+          const uint32_t bar = smem_addr(ld_bar);
+          const uint32_t bytes = (uint32_t)(p.s_img + p.v_img) * 4u;
+          const float* sp = saved_t + (size_t)(k - 1) * (p.s_img + p.v_img);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(smem_addr(Z)), "l"(sp), "r"((uint32_t)p.s_img * 4u), "r"(bar) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(smem_addr(V)), "l"(sp + p.s_img), "r"((uint32_t)p.v_img * 4u), "r"(bar) : "memory");
+        }
+        mbar_wait(ld_bar, ld_n & 1u);
+        ++ld_n;
+        __syncwarp();
+        for (int cc = 4 * w.part; cc < p.s; cc += 4 * CS) {
+          const float4 v = get4(Z, w.r, cc);
+          tmem_st4(w.tl + (uint32_t)(p.ZLO + cc), lo_part(v.x), lo_part(v.y), lo_part(v.z), lo_part(v.w));
+        }
+        for (int gi = w.part; gi < (PW >> 2); gi += CS)
+#pragma unroll
+          for (int x = 0; x < 3; ++x) {
+            const float4 v = get4(V + x * PLANE, w.r, 4 * gi);
+            tmem_st4(w.tl + (uint32_t)(p.VLO + PW * x + 4 * gi), lo_part(v.x), lo_part(v.y), lo_part(v.z), lo_part(v.w));
+          }
+      }
+      // ---- recompute the forward of GCP k up to [H | D | U] and [T | g]
+      const float* smc;
+      gcp_forward_tile<CS>(p, k, c, rs, rw, false, false, false, q, live, src, dst, orig, [] {}, &smc, true);
+      const float* ps = nullptr; const float* pd = nullptr; const float* qs = nullptr; const float* qd = nullptr;
+      if (k == 0) {
+        ps = p.P + (size_t)src * 2 * p.pw; pd = p.P + (size_t)dst * 2 * p.pw + p.pw;
+        qs = p.Q + (size_t)src * 192; qd = p.Q + (size_t)dst * 192 + 96;
+      }
+      const float* bs = smc + g.o_b;
+      const float* bg = smc + g.o_b + g.sop;
+      // ---- epilogue 1: cotangents of the two batches' outputs: [gT | gg] (GTG tile), gU (GHDU tile columns 16..31)
+      for (int cg = w.part; 16 * cg < g.so; cg += CS) {
+        float t[16], gs[16];
+        tmem_ld16(w.tl + (uint32_t)(p.TACC + 16 * cg), t);
+        tmem_ld16(w.tl + (uint32_t)(b.GS + 16 * cg), gs);
+        wait_ld();
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int cc = 16 * cg + 4 * i4;
+          if (cc < g.so) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bs + cc);
+            float tv[4] = {t[4 * i4] + b4.x, t[4 * i4 + 1] + b4.y, t[4 * i4 + 2] + b4.z, t[4 * i4 + 3] + b4.w};
+            if (ps != nullptr) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(ps + cc)), d4 = __ldg(reinterpret_cast<const float4*>(pd + cc));
+              tv[0] += a.x + d4.x; tv[1] += a.y + d4.y; tv[2] += a.z + d4.z; tv[3] += a.w + d4.w;
+            }
+            float gt[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) gt[i] = gs[4 * i4 + i] * act_grad(g.act_s, tv[i], p.slope);
+            put4(GTG, w.tl + (uint32_t)p.ZLO, w.r, cc, gt[0], gt[1], gt[2], gt[3]);
+          }
+        }
+      }
+      for (int gi = w.part; gi < (PW >> 2); gi += CS) {
+        float gt[4], u[3][4], gv[3][4];
+        tmem_ld4(w.tl + (uint32_t)(p.TACC + g.sop + 4 * gi), gt);
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+          tmem_ld4(w.tl + (uint32_t)(p.VACC + VN * x + UCOL + 4 * gi), u[x]);
+          tmem_ld4(w.tl + (uint32_t)(b.GV + PW * x + 4 * gi), gv[x]);
+        }
+        wait_ld();
+        if (ps != nullptr) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(ps + g.sop + 4 * gi)), d4 = __ldg(reinterpret_cast<const float4*>(pd + g.sop + 4 * gi));
+          gt[0] += a.x + d4.x; gt[1] += a.y + d4.y; gt[2] += a.z + d4.z; gt[3] += a.w + d4.w;
+#pragma unroll
+          for (int x = 0; x < 3; ++x) {
+            const float4 e4 = __ldg(reinterpret_cast<const float4*>(qs + 32 * x + UCOL + 4 * gi)), f4 = __ldg(reinterpret_cast<const float4*>(qd + 32 * x + UCOL + 4 * gi));
+            u[x][0] += e4.x + f4.x; u[x][1] += e4.y + f4.y; u[x][2] += e4.z + f4.z; u[x][3] += e4.w + f4.w;
+          }
+        }
+        float4 vin[3];
+#pragma unroll
+        for (int x = 0; x < 3; ++x) vin[x] = g.vres ? get4(V + x * PLANE, w.r, 4 * gi) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float gu[3][4], gg[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int o = 4 * gi + i;
+          const float sg = o < g.vo ? sigmoidf_(gt[i] + bg[o]) : 0.f;
+          float gsig = 0.f;
+#pragma unroll
+          for (int x = 0; x < 3; ++x) {
+            const float vi = i == 0 ? vin[x].x : (i == 1 ? vin[x].y : (i == 2 ? vin[x].z : vin[x].w));
+            gsig = fmaf(gv[x][i], u[x][i] + vi, gsig);
+            gu[x][i] = gv[x][i] * sg;
+          }
+          gg[i] = gsig * sg * (1.f - sg);
+        }
+#pragma unroll
+        for (int x = 0; x < 3; ++x) put4(GHDU + x * GPLANE, w.tl + (uint32_t)(b.GHDULO + VN * x), w.r, UCOL + 4 * gi, gu[x][0], gu[x][1], gu[x][2], gu[x][3]);
+        put4(GTG, w.tl + (uint32_t)p.ZLO, w.r, g.sop + 4 * gi, gg[0], gg[1], gg[2], gg[3]);
+      }
+      publish_and_sync();
+      // ---- scalar data gradient: gZ = [gT | gg] . W_tg   (accumulator aliases [T | g])
+      if (c.uwarp == 0) {
+        ring_fill(rw);
+        const int wh = uniform(rw.head);
+        const float* bh = ring_wait(rw, wh);
+        const float* bl = ring_wait(rw, wh + 1);
+        bool acc = false;
+        mma3(tbase + (uint32_t)p.TACC, GTG, tbase + (uint32_t)p.ZLO, bh, bl, b.kzn[k], p.pw, make_idesc(128, b.kzn[k], 0, 0), acc);
+        if (elect_one()) commit(c.mma_bar);
+        __syncwarp();
+      }
+      // ---- meanwhile: weight-gradient product G_tg += [gT | gg]^T . Z  (CUDA cores' tensor path, all warps)
+      {
+        const int mt = p.pw >> 4, nt = (g.kz + 7) >> 3;
+        for (int pr = warp; pr < mt * nt; pr += 4 * CS) {
+          const int m0 = 16 * (pr % mt), n0 = 8 * (pr / mt);
+          float cf[4] = {0.f, 0.f, 0.f, 0.f};
+          wgrad_block(cf, GTG, Z, m0, n0, lane);
+          wgrad_store(cf, prow + b.off_tg[k], g.kz, m0, n0, p.pw, g.kz, accumulate, lane);
+        }
+      }
+      wait_mma(c);
+      rw.head += 2;
+      if (c.uwarp == 0) ring_fill(rw);
+      // ---- epilogue 3: gS (residual + gZ[:, :s]) -> GS; tail of gZ -> [gH | gD] (GHDU tile columns 0..15)
+      if (k > 0) {
+        for (int cg = w.part; 16 * cg < p.s; cg += CS) {
+          float gz[16], gs[16];
+          tmem_ld16(w.tl + (uint32_t)(p.TACC + 16 * cg), gz);
+          if (res) tmem_ld16(w.tl + (uint32_t)(b.GS + 16 * cg), gs);
+          wait_ld();
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = gz[4 * i4 + i] + (res ? gs[4 * i4 + i] : 0.f);
+            tmem_st4(w.tl + (uint32_t)(b.GS + 16 * cg + 4 * i4), o[0], o[1], o[2], o[3]);
+          }
+        }
+      } else {
+        for (int cg = w.part; 16 * cg < p.se; cg += CS) {  // cotangent of the edge scalars
+          float gz[16];
+          tmem_ld16(w.tl + (uint32_t)(p.TACC + 16 * cg), gz);
+          wait_ld();
+          if (live) {
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4)
+              if (16 * cg + 4 * i4 < p.se)
+                *reinterpret_cast<float4*>(b.ge + (size_t)orig * p.se + 16 * cg + 4 * i4) = make_float4(gz[4 * i4], gz[4 * i4 + 1], gz[4 * i4 + 2], gz[4 * i4 + 3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int item = 0; item < 4; ++item) {
+        if ((item % CS) != w.part) continue;
+        if (item < 3) {
+          if (4 * item < g.nslot) {
+            float gn[4], h[3][4];
+            tmem_ld4(w.tl + (uint32_t)(p.TACC + g.zc0 + 4 * item), gn);
+#pragma unroll
+            for (int x = 0; x < 3; ++x) tmem_ld4(w.tl + (uint32_t)(p.VACC + VN * x + 4 * item), h[x]);
+            wait_ld();
+            if (qs != nullptr) {
+#pragma unroll
+              for (int x = 0; x < 3; ++x) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(qs + 32 * x + 4 * item)), d4 = __ldg(reinterpret_cast<const float4*>(qd + 32 * x + 4 * item));
+                h[x][0] += a.x + d4.x; h[x][1] += a.y + d4.y; h[x][2] += a.z + d4.z; h[x][3] += a.w + d4.w;
+              }
+            }
+            float gh[3][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              // n = sqrt(sum_x H^2 + eps) + eps  ->  dn/dH[x] = H[x] / sqrt(sum_x H^2 + eps)
+              const float root = sqrtf(fmaf(h[0][i], h[0][i], fmaf(h[1][i], h[1][i], h[2][i] * h[2][i])) + SAFE_NORM_EPS);
+              const float f = (4 * item + i < g.hd) ? gn[i] / root : 0.f;
+#pragma unroll
+              for (int x = 0; x < 3; ++x) gh[x][i] = f * h[x][i];
+            }
+#pragma unroll
+            for (int x = 0; x < 3; ++x) put4(GHDU + x * GPLANE, w.tl + (uint32_t)(b.GHDULO + VN * x), w.r, 4 * item, gh[x][0], gh[x][1], gh[x][2], gh[x][3]);
+          }
+        } else {
+          float gq[12];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            float t4[4];
+            tmem_ld4(w.tl + (uint32_t)(p.TACC + g.zc0 + g.nslot + 4 * j), t4);
+            gq[4 * j] = t4[0]; gq[4 * j + 1] = t4[1]; gq[4 * j + 2] = t4[2]; gq[4 * j + 3] = t4[3];
+          }
+          wait_ld();
+          const float* F = sm + p.FBUF + w.r * 9;
+          // q[3c + a] = sum_x F[a][x] D[x][c]  ->  gD[x][c] = sum_a F[a][x] gq[3c + a]
+#pragma unroll
+          for (int x = 0; x < 3; ++x) {
+            float gd[3];
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) gd[cc] = fmaf(F[x], gq[3 * cc], fmaf(F[3 + x], gq[3 * cc + 1], F[6 + x] * gq[3 * cc + 2]));
+            put4(GHDU + x * GPLANE, w.tl + (uint32_t)(b.GHDULO + VN * x), w.r, 12, 0.f, gd[0], gd[1], gd[2]);
+          }
+        }
+      }
+      publish_and_sync();
+      // ---- vector data gradient: gV_in = [gH | gD | gU] . W_v   (accumulator aliases the V lo region)
+      if (c.uwarp == 0) {
+        bool acc = false;
+        mma3_planes(tbase + (uint32_t)p.VLO, PW, GHDU, GPLANE, tbase + (uint32_t)b.GHDULO, VN, smc + g.o_wvt_hi, smc + g.o_wvt_lo, 16, VN,
+                    make_idesc(128, 16, 0, 0), acc);
+        if (elect_one()) {
+          commit(c.mma_bar);
+          if (k == 0) {  // per-edge cotangents of message GCP 0's per-node products, for the node-level finish
+            float* yp = b.Y + (size_t)tile * (b.y_img_g + b.y_img_v);
+            bulk_store(yp, GTG, b.y_img_g);
+            bulk_store(yp + b.y_img_g, GHDU, b.y_img_v);
+          }
+        }
+        __syncwarp();
+      }
+      // ---- meanwhile: G_v += sum_xyz [gH | gD | gU]^T . V_in
+      if (warp >= 4 * CS - 4) {
+        const int pr = warp - (4 * CS - 4);  // 2 x 2 blocks of 16 x 8
+        const int m0 = 16 * (pr & 1), n0 = 8 * (pr >> 1);
+        float cf[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int x = 0; x < 3; ++x) wgrad_block(cf, GHDU + x * GPLANE, V + x * PLANE, m0, n0, lane);
+        wgrad_store(cf, prow + b.off_v[k], 16, m0, n0, VN, 16, accumulate, lane);
+      }
+      wait_mma(c);
+      // ---- epilogue 4: gV (residual (+ gU with vector_residual) + gV_in) -> GV; GCP 0: cotangent of the edge vectors
+      for (int gi = w.part; gi < (PW >> 2); gi += CS) {
+        float a[3][4], gv[3][4];
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+          tmem_ld4(w.tl + (uint32_t)(p.VLO + PW * x + 4 * gi), a[x]);
+          if (res) tmem_ld4(w.tl + (uint32_t)(b.GV + PW * x + 4 * gi), gv[x]);
+        }
+        wait_ld();
+        if (k > 0) {
+#pragma unroll
+          for (int x = 0; x < 3; ++x) {
+            float o[4];
+            const float4 gu = g.vres ? get4(GHDU + x * GPLANE, w.r, UCOL + 4 * gi) : make_float4(0.f, 0.f, 0.f, 0.f);
+            o[0] = a[x][0] + gu.x; o[1] = a[x][1] + gu.y; o[2] = a[x][2] + gu.z; o[3] = a[x][3] + gu.w;
+            if (res) { o[0] += gv[x][0]; o[1] += gv[x][1]; o[2] += gv[x][2]; o[3] += gv[x][3]; }
+            tmem_st4(w.tl + (uint32_t)(b.GV + PW * x + 4 * gi), o[0], o[1], o[2], o[3]);
+          }
+        } else if (live && 4 * gi < p.ve) {
+          float f[12];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int x = 0; x < 3; ++x) f[3 * i + x] = a[x][i];
+          float* gp = b.gxi + (size_t)orig * 3 * p.ve + 12 * gi;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) *reinterpret_cast<float4*>(gp + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        }
+      }
+      rs.head += 1;
+    }
+    if (c.uwarp == 0 && elect_one()) bulk_store_wait_read();  // the Y images of this tile have left shared memory
+  }
+  if (c.uwarp == 0 && elect_one()) bulk_store_wait_all();
+  wait_st();
+  fence_before_sync();
+  __syncthreads();
+  if (c.uwarp == 0) tmem_dealloc(c.tbase, (uint32_t)p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// node-level finish of message GCP 0 (backward): Y[e] = [gT | gg | (gH | gD | gU) x 3] are the
+// cotangents of the gathered per-node products; sum them per node over outgoing / incoming edges (fixed order, no
+// atomics), push them through the node tiles (data gradient) and against h / chi (weight gradient).
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float y_at(const TcPostParams& p, int q, int c) {
+  const int tile = q >> 7, r = q & 127;
+  const float* yp = p.Y + (size_t)tile * (p.y_img_g + p.y_img_v);
+  if (c < p.pw) return __ldg(yp + ((c >> 2) * RP + r) * 4 + (c & 3));
+  const int c2 = c - p.pw, x = c2 >> 5, cc = c2 & 31;
+  return __ldg(yp + p.y_img_g + x * GPLANE + ((cc >> 2) * RP + r) * 4 + (cc & 3));
+}
+__global__ void __launch_bounds__(256) tc_post_sum_kernel(const TcPostParams p) {
+  const int per = p.pw + 96;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= (long long)p.N * 2 * per) return;
+  const int i = (int)(idx / (2 * per)), rem = (int)(idx - (long long)i * 2 * per);
+  const int side = rem / per, c = rem - side * per;
+  float acc = 0.f;
+  if (side == 0) { for (int j = p.src_ptr[i]; j < p.src_ptr[i + 1]; ++j) acc += y_at(p, __ldg(p.src_pos + j), c); }
+  else { for (int q = p.dst_ptr[i]; q < p.dst_ptr[i + 1]; ++q) acc += y_at(p, q, c); }
+  p.A[idx] = acc;
+}
+__global__ void __launch_bounds__(256) tc_post_data_kernel(const TcPostParams p) {
+  const int W = p.s + 3 * p.v, per = p.pw + 96;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= (long long)p.N * W) return;
+  const int i = (int)(idx / W), o = (int)(idx - (long long)i * W);
+  const float* As = p.A + (size_t)i * 2 * per;
+  const float* Ad = As + per;
+  float acc = 0.f;
+  if (o < p.s) {
+    const float* Bs = p.blob + p.nt.ps; const float* Bd = p.blob + p.nt.pd;  // [pw][s] slab, pitch pw
+    for (int c = 0; c < p.pw; ++c) {
+      const int off = ((o >> 2) * p.pw + c) * 4 + (o & 3);
+      acc = fmaf(As[c], __ldg(Bs + off), fmaf(Ad[c], __ldg(Bd + off), acc));
+    }
+    p.g_h[(size_t)i * p.s + o] += acc;
+  } else {
+    const int ch = (o - p.s) / 3, x = (o - p.s) - 3 * ch;
+    const float* Bs = p.blob + p.nt.qs; const float* Bd = p.blob + p.nt.qd;  // [32][v8] slab, pitch 32
+    for (int c = 0; c < VN; ++c) {
+      const int off = ((ch >> 2) * VN + c) * 4 + (ch & 3);
+      acc = fmaf(As[p.pw + 32 * x + c], __ldg(Bs + off), fmaf(Ad[p.pw + 32 * x + c], __ldg(Bd + off), acc));
+    }
+    p.g_chi[(size_t)i * 3 * p.v + (o - p.s)] += acc;
+  }
+}
+// per-CTA partials [src: pw x s | dst: pw x s | src: 32 x 16 | dst: 32 x 16]
+__global__ void __launch_bounds__(256) tc_post_wgrad_kernel(const TcPostParams p) {
+  const int per = p.pw + 96, chunk = (p.N + gridDim.x - 1) / gridDim.x;
+  const int i0 = blockIdx.x * chunk, i1 = min(p.N, i0 + chunk);
+  float* out = p.npartial + (size_t)blockIdx.x * p.npartial_stride;
+  const int ns = p.pw * p.s, nv = VN * 16;
+  for (int o = threadIdx.x; o < 2 * ns + 2 * nv; o += 256) {
+    float acc = 0.f;
+    if (o < 2 * ns) {
+      const int side = o / ns, r = o - side * ns, n = r / p.s, j = r - n * p.s;
+      for (int i = i0; i < i1; ++i) acc = fmaf(p.A[((size_t)i * 2 + side) * per + n], __ldg(p.h + (size_t)i * p.s + j), acc);
+    } else {
+      const int o2 = o - 2 * ns, side = o2 / nv, r = o2 - side * nv, jj = r / 16, ch = r - jj * 16;
+      if (ch < p.v)
+        for (int i = i0; i < i1; ++i)
+#pragma unroll
+          for (int x = 0; x < 3; ++x) acc = fmaf(p.A[((size_t)i * 2 + side) * per + p.pw + 32 * x + jj], __ldg(p.chi + (size_t)i * 3 * p.v + 3 * ch + x), acc);
+    }
+    out[o] = acc;
+  }
+}
+// out[idx] = sum over rows of partial[row][idx]
+__global__ void __launch_bounds__(256) tc_reduce_kernel(const float* __restrict__ partial, int rows, int stride, int n, float* __restrict__ out) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= n) return;
+  float acc = 0.f;
+  for (int r = 0; r < rows; ++r) acc += __ldg(partial + (size_t)r * stride + idx);
+  out[idx] = acc;
+}
+
+__device__ __forceinline__ float fin_gtg(const TcFinalParams& p, int k, int n, int r) {  // composed scalar gradient at (row n, reference column r)
+  const TcFinalGcp& g = p.g[k];
+  if (k == 0) {
+    if (r < p.s) return p.Gn[(size_t)n * p.s + r];
+    if (r < p.s + p.se) return p.G[g.off_tg + (size_t)n * g.kz + (r - p.s)];
+    if (r < 2 * p.s + p.se) return p.Gn[(size_t)p.pw * p.s + (size_t)n * p.s + (r - p.s - p.se)];
+  } else if (r < g.si) return p.G[g.off_tg + (size_t)n * g.kz + r];
+  const int t = r - g.si;  // n | q
+  const int col = t < g.hd ? g.zc0 + t : g.zc0 + g.nslot + (t - g.hd);
+  return p.G[g.off_tg + (size_t)n * g.kz + col];
+}
+__device__ __forceinline__ float fin_gb(const TcFinalParams& p, int k, int n) { return p.G[p.g[k].off_tg + (size_t)n * p.g[k].kz + p.g[k].kz - 1]; }
+__device__ __forceinline__ float fin_gv(const TcFinalParams& p, int k, int j, int c) {  // composed vector gradient at (row j, reference channel c)
+  const TcFinalGcp& g = p.g[k];
+  if (k == 0) {
+    const float* gn = p.Gn + 2 * (size_t)p.pw * p.s;
+    if (c < p.v) return gn[j * 16 + c];
+    if (c < p.v + p.ve) return p.G[g.off_v + j * 16 + (c - p.v)];
+    return gn[VN * 16 + j * 16 + (c - p.v - p.ve)];
+  }
+  return p.G[g.off_v + j * 16 + c];
+}
+__global__ void __launch_bounds__(256) tc_finalize_kernel(const __grid_constant__ TcFinalParams p) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= p.n_edge_params) return;
+  // which GCP / tensor
+  int k = 0, t = 0, base = 0;
+  bool found = false;
+  for (int kk = 0; kk < p.L && !found; ++kk) {
+    const TcFinalGcp& g = p.g[kk];
+    const int K = g.si + g.hd + 9;
+    const int sizes[7] = {g.hd * g.vi, 3 * g.vi, g.so * K, g.so, g.vo * g.hd, g.vo * g.so, g.vo};
+    for (int tt = 0; tt < 7; ++tt)
+      if (idx >= g.grad_off[tt] && idx < g.grad_off[tt] + sizes[tt]) { k = kk; t = tt; base = g.grad_off[tt]; found = true; break; }
+  }
+  if (!found) return;
+  const TcFinalGcp& g = p.g[k];
+  const int i = idx - base, K = g.si + g.hd + 9, so = g.so;
+  float val = 0.f;
+  if (t == 2) {          // scalar_out.weight[n][r] = G(n, r) + sum_o Wg[o][n] G(so + o, r)
+    const int n = i / K, r = i - n * K;
+    val = fin_gtg(p, k, n, r);
+    for (int o = 0; o < g.vo; ++o) val = fmaf(__ldg(g.Wg + o * so + n), fin_gtg(p, k, so + o, r), val);
+  } else if (t == 3) {   // scalar_out.bias
+    val = fin_gb(p, k, i);
+    for (int o = 0; o < g.vo; ++o) val = fmaf(__ldg(g.Wg + o * so + i), fin_gb(p, k, so + o), val);
+  } else if (t == 5) {   // vector_out_scale.weight[o][n] = sum_r G(so + o, r) Ws[n][r] + Gb(so + o) bs[n]
+    const int o = i / so, n = i - o * so;
+    val = fin_gb(p, k, so + o) * __ldg(g.bs + n);
+    for (int r = 0; r < K; ++r) val = fmaf(fin_gtg(p, k, so + o, r), __ldg(g.Ws + (size_t)n * K + r), val);
+  } else if (t == 6) {   // vector_out_scale.bias
+    val = fin_gb(p, k, so + i);
+  } else if (t == 0) {   // vector_down.weight[j][c] = Gv(j, c) + sum_o Wu[o][j] Gv(16 + o, c)
+    const int j = i / g.vi, c = i - j * g.vi;
+    val = fin_gv(p, k, j, c);
+    for (int o = 0; o < g.vo; ++o) val = fmaf(__ldg(g.Wu + o * g.hd + j), fin_gv(p, k, UCOL + o, c), val);
+  } else if (t == 1) {   // vector_down_frames.weight[cc][c]
+    const int cc = i / g.vi, c = i - cc * g.vi;
+    val = fin_gv(p, k, DCOL + cc, c);
+  } else {               // vector_up.weight[o][j] = sum_c Gv(16 + o, c) Wd[j][c]
+    const int o = i / g.hd, j = i - o * g.hd;
+    for (int c = 0; c < g.vi; ++c) val = fmaf(fin_gv(p, k, UCOL + o, c), __ldg(g.Wd + j * g.vi + c), val);
+  }
+  p.out[idx] = val;
 }
 
 }  // namespace tc

@@ -39,7 +39,15 @@ struct TcPlan {
   int grid = 0;
   long long saved_floats = 0; // training: tiles * (L-1) * (s_img + v_img)
   long long pq_floats = 0;    // N * (2 * pw + 192)
+  // backward
+  TcBwdParams bproto{};
+  long long y_floats = 0;       // tiles * (y_img_g + y_img_v): per-edge cotangents of message GCP 0's per-node products
+  long long partial_floats = 0; // grid * partial_stride
+  long long a_floats = 0;       // N * 2 * (pw + 96): per-node sums of Y over outgoing / incoming edges
+  int node_partial_ctas = 0, node_partial_stride = 0;  // node-level weight-gradient partials of message GCP 0
+  int wt_off_hi[12] = {0}, wt_off_lo[12] = {0};
 };
+constexpr int TC_POST_CTAS = 32;
 
 inline int rup(int x, int m) { return (x + m - 1) / m * m; }
 
@@ -109,6 +117,15 @@ inline TcPlan make_tc_plan(const gcpnet_layer& l, long long N, long long E) {
       p.ring_w.c[p.ring_w.n++] = TcChunk{ohi, fl};
       p.ring_w.c[p.ring_w.n++] = TcChunk{olo, fl};
       if (fl > max_w) max_w = fl;
+      // transposed tile [kz -> 16][pw] for the data-gradient GEMM
+      const int rt = rup(g.kz, 16), flt = rt * R;
+      const int thi = take(flt), tlo = take(flt);
+      TcPackItem& tt = item();
+      tt = it;
+      tt.dst_hi = thi; tt.dst_lo = tlo; tt.tr = 1; tt.Rt = rt;
+      P.wt_off_hi[k] = thi; P.wt_off_lo[k] = tlo;
+      P.bproto.kzn[k] = rt;
+      if (flt > max_w) max_w = flt;
     }
     if (k == 0) {
       // node-level tiles of GCP 0 (hi parts only): h_row / h_col column blocks, chi_row / chi_col channel blocks
@@ -155,6 +172,58 @@ inline TcPlan make_tc_plan(const gcpnet_layer& l, long long N, long long E) {
   P.saved_floats = tiles * p.saved_tile_stride;
   P.pq_floats = N * (2 * p.pw + 192);
   P.grid = (int)(tiles < 1 ? 1 : (tiles > 148 ? 148 : tiles));
+  // ======================== backward ========================
+  {
+    TcBwdParams& b = P.bproto;
+    b.f = p;
+    TcEdgeParams& f = b.f;
+    // rings in reverse GCP order; per GCP: forward tile (recompute) then transposed tile (data gradient)
+    f.ring_s.n = 0; f.ring_w.n = 0;
+    for (int k = L - 1; k >= 0; --k) {
+      f.ring_s.c[f.ring_s.n++] = p.ring_s.c[k];
+      const int R = s + 16;
+      f.ring_w.c[f.ring_w.n++] = p.ring_w.c[2 * k];
+      f.ring_w.c[f.ring_w.n++] = p.ring_w.c[2 * k + 1];
+      f.ring_w.c[f.ring_w.n++] = TcChunk{P.wt_off_hi[k], b.kzn[k] * R};
+      f.ring_w.c[f.ring_w.n++] = TcChunk{P.wt_off_lo[k], b.kzn[k] * R};
+    }
+    f.ring_w.nslot = 2;
+    // shared memory
+    int o2 = 0;
+    auto carve2 = [&](int floats) { const int o = o2; o2 += rup(floats, 32); return o; };
+    const int zc = zcols > p.pw ? zcols : p.pw;
+    f.ZBUF = carve2((zc / 4) * SLAB);
+    f.VBUF = carve2(3 * PLANE);
+    b.GTG = carve2((p.pw / 4) * SLAB);
+    b.GHDU = carve2(3 * (VN / 4) * SLAB);
+    f.FBUF = carve2(TE * 9);
+    f.RING_S = carve2(f.ring_s.nslot * f.ring_s.slot_floats);
+    f.RING_W = carve2(f.ring_w.nslot * f.ring_w.slot_floats);
+    f.BARS = carve2(2 * (2 + f.ring_s.nslot + f.ring_w.nslot));
+    f.smem_floats = o2;
+    if ((long long)o2 * 4 > TC_SMEM_LIMIT_BYTES) return no("backward tile does not fit shared memory");
+    // TMEM: GS | GV | R1 = Z lo / [gT|gg] lo | R2 = V lo / gV accumulator | vector accumulator | R3 = [T|g] / gZ accumulator | [gH|gD|gU] lo
+    int c2 = 0;
+    auto tc2 = [&](int n) { const int o = c2; c2 += n; return o; };
+    int r3 = p.pw;
+    for (int k = 0; k < L; ++k) if (b.kzn[k] > r3) r3 = b.kzn[k];
+    b.GS = tc2(s); b.GV = tc2(3 * PW);
+    f.ZLO = tc2(zc); f.VLO = tc2(3 * PW); f.VACC = tc2(3 * VN); f.TACC = tc2(r3); b.GHDULO = tc2(3 * VN);
+    if (c2 > 512) return no("backward tile does not fit tensor memory");
+    f.tmem_cols = 512;
+    // partial rows
+    int po = 0;
+    for (int k = 0; k < L; ++k) { b.off_tg[k] = po; po += p.pw * p.g[k].kz; b.off_v[k] = po; po += VN * 16; }
+    b.partial_stride = rup(po, 32);
+    b.y_img_g = (p.pw / 4) * SLAB; b.y_img_v = 3 * (VN / 4) * SLAB;
+    b.reduce_mean = l.reduce_mean;
+    P.y_floats = tiles * (long long)(b.y_img_g + b.y_img_v);
+    P.partial_floats = (long long)P.grid * b.partial_stride;
+    P.a_floats = N * 2LL * (p.pw + 96);
+    P.node_partial_ctas = TC_POST_CTAS;
+    P.node_partial_stride = 2 * (p.pw * s + VN * 16);
+    if (l.enable_e3) return no("e3 frames not covered by the tensor-core backward");
+  }
   P.ok = true;
   return P;
 }
