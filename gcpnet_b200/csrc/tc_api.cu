@@ -65,7 +65,7 @@ int gcp_tc_launch_post(const tc::TcPostParams& p, cudaStream_t st) {
   const long long n1 = (long long)p.N * 2 * (p.pw + 96), n2 = (long long)p.N * (p.s + 3 * p.v);
   tc::tc_post_sum_kernel<<<(int)((n1 + 255) / 256), 256, 0, st>>>(p);
   tc::tc_post_data_kernel<<<(int)((n2 + 255) / 256), 256, 0, st>>>(p);
-  tc::tc_post_wgrad_kernel<<<p.nctas, 256, 0, st>>>(p);
+  tc::tc_post_wgrad_kernel<<<dim3((p.npartial_stride + 255) / 256, p.nctas), 256, 0, st>>>(p);
   gcp_note_launches(3);
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -75,7 +75,8 @@ int gcp_tc_launch_finalize(const float* partial, int rows, int stride, float* G,
   tc::tc_reduce_kernel<<<(stride + 255) / 256, 256, 0, st>>>(partial, rows, stride, stride, G);
   tc::tc_reduce_kernel<<<(nstride + 255) / 256, 256, 0, st>>>(npartial, nrows, nstride, nstride, Gn);
   tc::tc_finalize_kernel<<<(fp.n_edge_params + 255) / 256, 256, 0, st>>>(fp);
-  gcp_note_launches(3);
+  tc::tc_finalize_wg_kernel<<<(fp.L * fp.g[0].vo * fp.g[0].so * 32 + 255) / 256, 256, 0, st>>>(fp);
+  gcp_note_launches(4);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

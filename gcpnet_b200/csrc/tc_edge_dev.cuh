@@ -533,6 +533,7 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_fwd_kernel(const __grid_c
 // =====================================================================================================================
 // backward
 // =====================================================================================================================
+
 constexpr int GPLANE = (VN / 4) * SLAB;  // floats per plane of the [gH | gD | gU] tile (32 columns)
 
 // Legacy-path tensor-core MMA (m16n8k8, tf32) for the weight-gradient products: their reduction runs over the tile's
@@ -985,26 +986,29 @@ __global__ void __launch_bounds__(256) tc_post_data_kernel(const TcPostParams p)
     p.g_chi[(size_t)i * 3 * p.v + (o - p.s)] += acc;
   }
 }
-// per-CTA partials [src: pw x s | dst: pw x s | src: 32 x 16 | dst: 32 x 16]
+// partial rows (one per node chunk = blockIdx.y) [src: pw x s | dst: pw x s | src: 32 x 16 | dst: 32 x 16]; thread = one output
 __global__ void __launch_bounds__(256) tc_post_wgrad_kernel(const TcPostParams p) {
-  const int per = p.pw + 96, chunk = (p.N + gridDim.x - 1) / gridDim.x;
-  const int i0 = blockIdx.x * chunk, i1 = min(p.N, i0 + chunk);
-  float* out = p.npartial + (size_t)blockIdx.x * p.npartial_stride;
+  const int per = p.pw + 96, chunk = (p.N + gridDim.y - 1) / gridDim.y;
+  const int i0 = blockIdx.y * chunk, i1 = min(p.N, i0 + chunk);
+  float* out = p.npartial + (size_t)blockIdx.y * p.npartial_stride;
   const int ns = p.pw * p.s, nv = VN * 16;
-  for (int o = threadIdx.x; o < 2 * ns + 2 * nv; o += 256) {
-    float acc = 0.f;
-    if (o < 2 * ns) {
-      const int side = o / ns, r = o - side * ns, n = r / p.s, j = r - n * p.s;
-      for (int i = i0; i < i1; ++i) acc = fmaf(p.A[((size_t)i * 2 + side) * per + n], __ldg(p.h + (size_t)i * p.s + j), acc);
-    } else {
-      const int o2 = o - 2 * ns, side = o2 / nv, r = o2 - side * nv, jj = r / 16, ch = r - jj * 16;
-      if (ch < p.v)
-        for (int i = i0; i < i1; ++i)
+  const int o = blockIdx.x * 256 + threadIdx.x;
+  if (o >= 2 * ns + 2 * nv) return;
+  float acc = 0.f;
+  if (o < 2 * ns) {
+    const int side = o / ns, r = o - side * ns, n = r / p.s, j = r - n * p.s;
+    const float* ap = p.A + (size_t)side * per + n;
+    const float* hp = p.h + j;
+#pragma unroll 4
+    for (int i = i0; i < i1; ++i) acc = fmaf(__ldg(ap + (size_t)i * 2 * per), __ldg(hp + (size_t)i * p.s), acc);
+  } else {
+    const int o2 = o - 2 * ns, side = o2 / nv, r = o2 - side * nv, jj = r / 16, ch = r - jj * 16;
+    if (ch < p.v)
+      for (int i = i0; i < i1; ++i)
 #pragma unroll
-          for (int x = 0; x < 3; ++x) acc = fmaf(p.A[((size_t)i * 2 + side) * per + p.pw + 32 * x + jj], __ldg(p.chi + (size_t)i * 3 * p.v + 3 * ch + x), acc);
-    }
-    out[o] = acc;
+        for (int x = 0; x < 3; ++x) acc = fmaf(__ldg(p.A + ((size_t)i * 2 + side) * per + p.pw + 32 * x + jj), __ldg(p.chi + (size_t)i * 3 * p.v + 3 * ch + x), acc);
   }
+  out[o] = acc;
 }
 // out[idx] = sum over rows of partial[row][idx]
 __global__ void __launch_bounds__(256) tc_reduce_kernel(const float* __restrict__ partial, int rows, int stride, int n, float* __restrict__ out) {
@@ -1061,10 +1065,8 @@ __global__ void __launch_bounds__(256) tc_finalize_kernel(const __grid_constant_
   } else if (t == 3) {   // scalar_out.bias
     val = fin_gb(p, k, i);
     for (int o = 0; o < g.vo; ++o) val = fmaf(__ldg(g.Wg + o * so + i), fin_gb(p, k, so + o), val);
-  } else if (t == 5) {   // vector_out_scale.weight[o][n] = sum_r G(so + o, r) Ws[n][r] + Gb(so + o) bs[n]
-    const int o = i / so, n = i - o * so;
-    val = fin_gb(p, k, so + o) * __ldg(g.bs + n);
-    for (int r = 0; r < K; ++r) val = fmaf(fin_gtg(p, k, so + o, r), __ldg(g.Ws + (size_t)n * K + r), val);
+  } else if (t == 5) {   // vector_out_scale.weight: tc_finalize_wg_kernel
+    return;
   } else if (t == 6) {   // vector_out_scale.bias
     val = fin_gb(p, k, so + i);
   } else if (t == 0) {   // vector_down.weight[j][c] = Gv(j, c) + sum_o Wu[o][j] Gv(16 + o, c)
@@ -1079,6 +1081,21 @@ __global__ void __launch_bounds__(256) tc_finalize_kernel(const __grid_constant_
     for (int c = 0; c < g.vi; ++c) val = fmaf(fin_gv(p, k, UCOL + o, c), __ldg(g.Wd + j * g.vi + c), val);
   }
   p.out[idx] = val;
+}
+
+// vector_out_scale.weight[o][n] = sum_r G(so + o, r) Ws[n][r] + Gb(so + o) bs[n]: one warp per element, lanes split r
+__global__ void __launch_bounds__(256) tc_finalize_wg_kernel(const __grid_constant__ TcFinalParams p) {
+  const int wid = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int per = p.g[0].vo * p.g[0].so;  // same (vo, so) for every message GCP
+  if (wid >= p.L * per) return;
+  const int k = wid / per, i = wid - k * per;
+  const TcFinalGcp& g = p.g[k];
+  const int K = g.si + g.hd + 9, so = g.so, o = i / so, n = i - o * so;
+  float val = 0.f;
+  for (int r = lane; r < K; r += 32) val = fmaf(fin_gtg(p, k, so + o, r), __ldg(g.Ws + (size_t)n * K + r), val);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+  if (lane == 0) p.out[g.grad_off[5] + i] = val + fin_gb(p, k, so + o) * __ldg(g.bs + n);
 }
 
 }  // namespace tc

@@ -47,7 +47,7 @@ struct TcPlan {
   int node_partial_ctas = 0, node_partial_stride = 0;  // node-level weight-gradient partials of message GCP 0
   int wt_off_hi[12] = {0}, wt_off_lo[12] = {0};
 };
-constexpr int TC_POST_CTAS = 32;
+constexpr int TC_POST_CTAS = 16;  // node chunks of the node-level weight-gradient partials
 
 inline int rup(int x, int m) { return (x + m - 1) / m * m; }
 
