@@ -119,7 +119,7 @@ int emul_graph_build(const int64_t* edge_index, int64_t E, int64_t N, const floa
 
 int emul_layer_plan(const gcpnet_layer* layer, int64_t N, int64_t E, gcpnet_plan* plan) {
   LayerPlan lp;
-  const std::string e = make_layer_plan(*layer, N, E, &lp, plan);
+  const std::string e = make_layer_plan(*layer, N, E, &lp, plan, false);  // the emulation covers the FFMA tile path
   return e.empty() ? 0 : fail(e);
 }
 
@@ -128,7 +128,7 @@ int emul_layer_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, con
                        const gcpnet_forward_io* io, int force_edge_tile, int force_node_tile, int mp_only, float* aggregate) {
   const gcpnet_layer& l = *layer; const gcpnet_graph& g = *graph;
   LayerPlan lp;
-  const std::string e = make_layer_plan(l, g.num_nodes, g.num_edges, &lp, nullptr);
+  const std::string e = make_layer_plan(l, g.num_nodes, g.num_edges, &lp, nullptr, false);
   if (!e.empty()) return fail(e);
   if (force_edge_tile && !pick_edge_tile(l, lp.ops, g.num_edges, false, force_edge_tile, &lp.ef)) return fail("forced edge tile does not fit");
   (void)force_node_tile;
@@ -171,7 +171,7 @@ int emul_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, co
                         const gcpnet_backward_io* io, int force_node_tile, int edge_grid, int node_grid) {
   const gcpnet_layer& l = *layer; const gcpnet_graph& g = *graph;
   LayerPlan lp;
-  const std::string e = make_layer_plan(l, g.num_nodes, g.num_edges, &lp, nullptr);
+  const std::string e = make_layer_plan(l, g.num_nodes, g.num_edges, &lp, nullptr, false);
   if (!e.empty()) return fail(e);
   (void)force_node_tile;
   const int W = l.s + 3 * l.v;
