@@ -310,6 +310,61 @@ struct XAct { int a; float slope; GCP_HD float operator()(float x) const { retur
 // reduction loop so its latency overlaps the math).  Rows e >= nrows of G must be zero.
 // A thread owns a JW x IW block of P (JW in {1,4}, IW in {4,8}); G and Zin are read JW resp. IW columns
 // at a time: J % JW == 0 or zero padding, and Zin carries readable columns up to round_up(I, IW).
+#if GCP_DEVICE_CODE
+// Device version: the products run on the register-fragment tensor-core MMA (mma.sync m16n8k8, tf32 inputs, fp32
+// accumulation) as 3xTF32 (hi*hi + lo*hi + hi*lo, split in registers): the reduction index is the tile ROW, so the
+// A / B fragments are read straight out of the row-major tiles.  One warp per 16 (j) x 8 (i) block of P.
+__device__ __forceinline__ void wg_hmma(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+template <int TE, int NT, int JW, int IW, class FMap>
+__device__ __forceinline__ void tile_wgrad(const float* G, int ldg, int J, const float* Zin, int ldz, int I,
+                                           float* P, float* Pb, bool accumulate, FMap fmap, int tid) {
+  static_assert(TE % 8 == 0, "tile rows");
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int JB = (J + 15) >> 4, IB = (I + 7) >> 3;
+  for (int blk = warp; blk < JB * IB; blk += NT / 32) {
+    const int ib = blk / JB, jb = blk - ib * JB;
+    const int j0 = 16 * jb + g, j1 = j0 + 8, i0 = 8 * ib + g;
+    const int ja = j0 < J ? j0 : J - 1, jc = j1 < J ? j1 : J - 1, ii = i0 < I ? i0 : I - 1;  // clamped loads; results dropped below
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k0 = 0; k0 < TE; k0 += 8) {
+      const float fa[4] = {G[(k0 + t) * ldg + ja], G[(k0 + t) * ldg + jc], G[(k0 + t + 4) * ldg + ja], G[(k0 + t + 4) * ldg + jc]};
+      const float fb[2] = {fmap(Zin[(k0 + t) * ldz + ii]), fmap(Zin[(k0 + t + 4) * ldz + ii])};
+      uint32_t ah[4], al[4], bh[2], bl[2];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { ah[q] = __float_as_uint(fa[q]) & 0xffffe000u; al[q] = __float_as_uint(fa[q] - __uint_as_float(ah[q])); }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) { bh[q] = __float_as_uint(fb[q]) & 0xffffe000u; bl[q] = __float_as_uint(fb[q] - __uint_as_float(bh[q])); }
+      wg_hmma(c, ah, bh);
+      wg_hmma(c, al, bh);
+      wg_hmma(c, ah, bl);
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int j = 16 * jb + g + 8 * hh;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int i = 8 * ib + 2 * t + q;
+        if (j < J && i < I) {
+          float* dp = P + (size_t)j * I + i;
+          *dp = (accumulate ? *dp : 0.f) + c[2 * hh + q];
+        }
+      }
+    }
+  }
+  if (Pb != nullptr) {
+    for (int j = tid; j < J; j += NT) {
+      const float o = accumulate ? Pb[j] : 0.f;
+      float s = 0.f;
+      for (int e = 0; e < TE; ++e) s += G[e * ldg + j];
+      Pb[j] = o + s;
+    }
+  }
+}
+#else
 template <int TE, int NT, int JW, int IW, class FMap>
 GCP_HD void tile_wgrad(const float* G, int ldg, int J, const float* Zin, int ldz, int I,
                        float* P, float* Pb, bool accumulate, FMap fmap, int tid) {
@@ -371,6 +426,8 @@ GCP_HD void tile_wgrad(const float* G, int ldg, int J, const float* Zin, int ldz
     }
   }
 }
+
+#endif
 
 // ------------------------------------------------------------------------------------------
 // cooperative row copies: warp per row, lane per column (coalesced, no integer division)
