@@ -251,7 +251,7 @@ static int run_tc_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, co
     tc::TcBwdParams b = T.bproto;
     fill_tc_common(b.f, g, lp, io.h, io.chi, io.e, io.xi, io.frames, io.packed);
     b.f.saved = const_cast<float*>(io.saved_edge);
-    b.f.msg = nullptr; b.f.dbg = nullptr;
+    b.f.msg = nullptr; b.f.dbg = g_tc_dbg.load(std::memory_order_relaxed);
     b.gagg = io.ws_agg; b.dst_ptr = g.dst_ptr;
     b.ge = io.g_e; b.gxi = io.g_xi; b.Y = Y; b.partial = io.ws_edge_partial;
     if (gcp_tc_launch_edge_bwd(b, T.grid, st)) return 1;

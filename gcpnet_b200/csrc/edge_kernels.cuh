@@ -201,9 +201,7 @@ GCP_HDN void edge_bwd_tile(const EdgeParams& p, float* sm, int tile, WPipe& wp, 
       const bool add = p.residual != 0;
       float* GS = g.GS; const int ldgs = g.ldgs; float* GV = g.GV; const int ldgv = g.ldgv;
       gcp2_bwd_tile<TE, NT, SLF, SLD>(
-          op, b, g, wp, p.e3, p.slope, prow, accumulate, refill_first,
-          [=](int e, int i, float val) { float* d = GS + e * ldgs + i; *d = add ? *d + val : val; },
-          [=](int e, int c3, float val) { float* d = GV + e * ldgv + c3; *d = add ? *d + val : val; });
+          op, b, g, wp, p.e3, p.slope, prow, accumulate, refill_first, EmitTile{GS, ldgs, add}, EmitTile{GV, ldgv, add});
     } else {
       float* grow = p.grow; float* gcol = p.gcol; float* ge = p.ge; float* gxi = p.gxi;
       const int* perm = p.perm;

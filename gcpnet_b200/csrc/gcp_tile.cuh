@@ -38,6 +38,7 @@ namespace gcp {
 
 #define GCP_HD __host__ __device__ __forceinline__
 #define GCP_HDN __host__ __device__
+#define GCP_HDN_NOINLINE __host__ __device__ __noinline__
 
 inline int g_emul_reverse = 0;  // host emulation only: run thread bodies in reverse order when set
 inline bool g_emul_first = false;  // host emulation only: true while the first-executed thread body of a phase runs
@@ -60,8 +61,22 @@ enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKYRELU = 2, ACT_SILU = 3, AC
 
 GCP_HD float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-// src/models/__init__.py:41-57
+// src/models/__init__.py:41-57.  The shipped configs use relu / identity: those two stay inline, the transcendental
+// ones live behind a call (inlining them at every call site of the unrolled tile loops bloats the kernels past the
+// instruction cache: 30 % of the node-update kernel's SASS was activation bodies).
+__host__ __device__ __noinline__ float act_fwd_slow(int a, float x, float slope);
+__host__ __device__ __noinline__ float act_grad_slow(int a, float x, float slope);
 GCP_HD float act_fwd(int a, float x, float slope) {
+  if (a == ACT_NONE) return x;
+  if (a == ACT_RELU) return x > 0.f ? x : 0.f;
+  return act_fwd_slow(a, x, slope);
+}
+GCP_HD float act_grad(int a, float x, float slope) {
+  if (a == ACT_NONE) return 1.f;
+  if (a == ACT_RELU) return x > 0.f ? 1.f : 0.f;
+  return act_grad_slow(a, x, slope);
+}
+__host__ __device__ __noinline__ inline float act_fwd_slow(int a, float x, float slope) {
   switch (a) {
     case ACT_RELU: return x > 0.f ? x : 0.f;
     case ACT_LEAKYRELU: return x > 0.f ? x : slope * x;
@@ -74,7 +89,7 @@ GCP_HD float act_fwd(int a, float x, float slope) {
     default: return x;
   }
 }
-GCP_HD float act_grad(int a, float x, float slope) {
+__host__ __device__ __noinline__ inline float act_grad_slow(int a, float x, float slope) {
   switch (a) {
     case ACT_RELU: return x > 0.f ? 1.f : 0.f;
     case ACT_LEAKYRELU: return x > 0.f ? 1.f : slope;
@@ -524,7 +539,7 @@ GCP_HD float gcp2_vec_up(const GcpOp& op, const TileBufs& b, const float* wu, in
 // WU from it in its update phase, then releases it with gcp2_fwd_finish()).
 // Phases: [vec_down] [norm+scalarize] [GEMM chunk]* [gate].
 template <int TE, int NT, int SL>
-GCP_HDN const float* gcp2_fwd_tile(const GcpOp& op, const TileBufs& b, WPipe& wp, int e3, float slope, bool refill_first) {
+GCP_HDN_NOINLINE const float* gcp2_fwd_tile(const GcpOp& op, const TileBufs& b, WPipe& wp, int e3, float slope, bool refill_first) {
   const GcpW& W = op.w;
   // ---- S chunk: vector_down / vector_down_frames
   GCP_PHASE_BEGIN(NT)
@@ -650,8 +665,14 @@ struct BwdBufs {
 //   * weight-gradient partials into prow[op.o_*]  (accumulate: += instead of =)
 // b.T is overwritten with the cotangent of the pre-activation.  Ring order: S, G, WS chunks.
 // `refill_first`: the caller's previous phase released the chunk at head-1.
+// accumulate-or-assign into a shared-memory tile: the emit functor of every caller that keeps the cotangent on chip
+// (one functor TYPE -> one instantiation of gcp2_bwd_tile, called several times instead of inlined several times)
+struct EmitTile {
+  float* p; int ld; bool add;
+  GCP_HD void operator()(int e, int i, float val) const { float* d = p + e * ld + i; *d = add ? *d + val : val; }
+};
 template <int TE, int NT, int SLF, int SLD, class EmitS, class EmitV>
-GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g, WPipe& wp, int e3, float slope,
+GCP_HDN_NOINLINE void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g, WPipe& wp, int e3, float slope,
                            float* prow, bool accumulate, bool refill_first, EmitS emit_s, EmitV emit_v) {
   const GcpW& W = op.w;
   const int cols = W.cols, hdp = W.hdp;

@@ -68,7 +68,7 @@ constexpr int RED_W = 6;
 
 // GCPLayerNorm forward, in place on (S, V) (comp/__init__.py:138-167).  3 phases.
 template <int TE, int NT>
-GCP_HDN void tile_layernorm_fwd(float* S, int lds, float* V, int ldv, int s, int v, const float* w, const float* bb,
+GCP_HDN_NOINLINE void tile_layernorm_fwd(float* S, int lds, float* V, int ldv, int s, int v, const float* w, const float* bb,
                                 float ln_eps, float vn_eps, float* RED) {
   constexpr int PARTS = NT / TE;
   GCP_PHASE_BEGIN(NT)
@@ -114,7 +114,7 @@ GCP_HDN void tile_layernorm_fwd(float* S, int lds, float* V, int ldv, int s, int
 // GCPLayerNorm backward: (S, V) = the layer-norm INPUT, (GS, GV) = cotangent of the output, replaced by the
 // cotangent of the input; weight/bias gradients go to this CTA's partial row.  4 phases.
 template <int TE, int NT>
-GCP_HDN void tile_layernorm_bwd(const float* S, int lds, const float* V, int ldv, float* GS, int ldgs, float* GV, int ldgv,
+GCP_HDN_NOINLINE void tile_layernorm_bwd(const float* S, int lds, const float* V, int ldv, float* GS, int ldgs, float* GV, int ldgv,
                                 int s, int v, const float* w, float ln_eps, float vn_eps, float* RED,
                                 float* pw, float* pb, bool accumulate) {
   constexpr int PARTS = NT / TE;
@@ -434,9 +434,7 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
     }
     GCP_PHASE_END
     gcp2_bwd_tile<TE, NT, SLF, SLD>(
-        p.pu, b, g, wp, 0, p.slope, prow, accumulate, false,
-        [=](int e, int i, float val) { GXS[e * ldgxs + i] += val; },
-        [=](int e, int c3, float val) { GXV[e * ldgxv + c3] += val; });
+        p.pu, b, g, wp, 0, p.slope, prow, accumulate, false, EmitTile{GXS, ldgxs, true}, EmitTile{GXV, ldgxv, true});
   }
   // ---- LayerNorm1 backward (input x2)
   tile_layernorm_bwd<TE, NT>(X2S, L.ldx2s, X2V, L.ldx2v, GXS, ldgxs, GXV, ldgxv, s, v, p.ln1_w, p.ln_eps, p.vn_eps, RED,
@@ -478,17 +476,13 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
     g.GS = GS1; g.ldgs = L.ldgs1; g.GV = GV1; g.ldgv = L.ldgv1;
     const int ldgs0 = L.ldgs0, ldgv0 = L.ldgv0;
     gcp2_bwd_tile<TE, NT, SLF, SLD>(
-        p.ff1, b1, g, wp, 0, p.slope, prow, accumulate, false,
-        [=](int e, int i, float val) { GS0[e * ldgs0 + i] = val; },
-        [=](int e, int c3, float val) { GV0[e * ldgv0 + c3] = val; });
+        p.ff1, b1, g, wp, 0, p.slope, prow, accumulate, false, EmitTile{GS0, ldgs0, false}, EmitTile{GV0, ldgv0, false});
   }
   // ---- FF0 backward: cotangents (GS0, GV0) -> accumulated into the cotangent of x1n
   {
     g.GS = GS0; g.ldgs = L.ldgs0; g.GV = GV0; g.ldgv = L.ldgv0;
     gcp2_bwd_tile<TE, NT, SLF, SLD>(
-        p.ff0, b0, g, wp, 0, p.slope, prow, accumulate, false,
-        [=](int e, int i, float val) { GXS[e * ldgxs + i] += val; },
-        [=](int e, int c3, float val) { GXV[e * ldgxv + c3] += val; });
+        p.ff0, b0, g, wp, 0, p.slope, prow, accumulate, false, EmitTile{GXS, ldgxs, true}, EmitTile{GXV, ldgxv, true});
   }
   // ---- LayerNorm0 backward (input x1, kept raw in X2S/X2V)
   tile_layernorm_bwd<TE, NT>(X2S, L.ldx2s, X2V, L.ldx2v, GXS, ldgxs, GXV, ldgxv, s, v, p.ln0_w, p.ln_eps, p.vn_eps, RED,

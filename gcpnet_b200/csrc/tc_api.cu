@@ -27,7 +27,7 @@ static int tc_set_smem(const void* kernel, int bytes) {
 }
 
 int gcp_tc_launch_pack(const tc::TcPackProg& prog, cudaStream_t st) {
-  tc::tc_pack_kernel<<<dim3(prog.n, 8), 256, 0, st>>>(prog);
+  tc::tc_pack_kernel<<<dim3(prog.n, 32), 256, 0, st>>>(prog);
   gcp_note_launches(1);
   CUDA_TRY(cudaGetLastError());
   return 0;

@@ -543,25 +543,43 @@ __device__ __forceinline__ void hmma_tf32(float (&c)[4], uint32_t a0, uint32_t a
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-// c[16 x 8 block at (m0, n0)] += sum over the 128 tile rows e of A[e][m0 + .] * B[e][n0 + .]   (A, B slab tiles)
-__device__ __forceinline__ void wgrad_block(float (&c)[4], const float* A, const float* B, int m0, int n0, int lane) {
+// c[b][16 x 8 block at (m0, n0 + 8 b)] += sum over the 128 tile rows e of A[e][m0 + .] * B[e][n0 + 8 b + .]   (A, B slab tiles)
+// NB column blocks share the A fragments; the three 3xTF32 terms keep separate accumulators (short dependency chains).
+template <int NB>
+__device__ __forceinline__ void wgrad_blocks(float (&c)[NB][4], const float* A, const float* B, int m0, int n0, int nb, int lane) {
   const int g = lane >> 2, t = lane & 3;
-  const float* a_lo_row = A + slab_off(RP, t, m0 + g);
-  const float* a_hi_row = A + slab_off(RP, t, m0 + g + 8);
-  const float* b_row = B + slab_off(RP, t, n0 + g);
-#pragma unroll 4
+  const float* a_row0 = A + slab_off(RP, t, m0 + g);
+  const float* a_row1 = A + slab_off(RP, t, m0 + g + 8);
+  const float* b_row[NB];
+#pragma unroll
+  for (int bb = 0; bb < NB; ++bb) b_row[bb] = B + slab_off(RP, t, n0 + 8 * (bb < nb ? bb : 0) + g);
+  float c1[NB][4], c2[NB][4];
+#pragma unroll
+  for (int bb = 0; bb < NB; ++bb)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { c1[bb][q] = 0.f; c2[bb][q] = 0.f; }
+#pragma unroll 2
   for (int k0 = 0; k0 < TE; k0 += 8) {
-    const float fa[4] = {a_lo_row[4 * k0], a_hi_row[4 * k0], a_lo_row[4 * (k0 + 4)], a_hi_row[4 * (k0 + 4)]};
-    const float fb[2] = {b_row[4 * k0], b_row[4 * (k0 + 4)]};
-    uint32_t ah[4], al[4], bh[2], bl[2];
+    const float fa[4] = {a_row0[4 * k0], a_row1[4 * k0], a_row0[4 * (k0 + 4)], a_row1[4 * (k0 + 4)]};
+    uint32_t ah[4], al[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { ah[i] = __float_as_uint(fa[i]) & TF32_MASK; al[i] = __float_as_uint(fa[i] - __uint_as_float(ah[i])); }
+    for (int q = 0; q < 4; ++q) { ah[q] = __float_as_uint(fa[q]) & TF32_MASK; al[q] = __float_as_uint(fa[q] - __uint_as_float(ah[q])); }
 #pragma unroll
-    for (int i = 0; i < 2; ++i) { bh[i] = __float_as_uint(fb[i]) & TF32_MASK; bl[i] = __float_as_uint(fb[i] - __uint_as_float(bh[i])); }
-    hmma_tf32(c, ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
-    hmma_tf32(c, al[0], al[1], al[2], al[3], bh[0], bh[1]);
-    hmma_tf32(c, ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
+    for (int bb = 0; bb < NB; ++bb) {
+      if (bb < nb) {  // warp-uniform
+        const float fb0 = b_row[bb][4 * k0], fb1 = b_row[bb][4 * (k0 + 4)];
+        const uint32_t bh0 = __float_as_uint(fb0) & TF32_MASK, bh1 = __float_as_uint(fb1) & TF32_MASK;
+        const uint32_t bl0 = __float_as_uint(fb0 - __uint_as_float(bh0)), bl1 = __float_as_uint(fb1 - __uint_as_float(bh1));
+        hmma_tf32(c[bb], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+        hmma_tf32(c1[bb], al[0], al[1], al[2], al[3], bh0, bh1);
+        hmma_tf32(c2[bb], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
+      }
+    }
   }
+#pragma unroll
+  for (int bb = 0; bb < NB; ++bb)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) c[bb][q] += c1[bb][q] + c2[bb][q];
 }
 // fragment -> this CTA's partial block G[ld columns] at (m0, n0); rows >= mrows / columns >= ncols are dropped
 __device__ __forceinline__ void wgrad_store(const float (&c)[4], float* G, int ld, int m0, int n0, int mrows, int ncols, bool accumulate, int lane) {
@@ -596,16 +614,18 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_c
   const Who& w = c.w;
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + p.BARS);
   c.mma_bar = bars;
-  unsigned long long* ld_bar = bars + 1;
+  unsigned long long* ld_bar = bars + 1;   // V image of the GCP about to run
+  unsigned long long* ldz_bar = bars + 2;  // S image (issued one GCP ahead, as soon as the Z tile's last reader is done)
   c.mma_n = 0;
-  uint32_t ld_n = 0;
-  Ring rs{sm + p.RING_S, bars + 2, &p.ring_s, p.blob, 0, 0, mine * p.ring_s.n};
-  Ring rw{sm + p.RING_W, bars + 2 + p.ring_s.nslot, &p.ring_w, p.blob, 0, 0, mine * p.ring_w.n};
+  uint32_t ld_n = 0, ldz_n = 0;
+  Ring rs{sm + p.RING_S, bars + 3, &p.ring_s, p.blob, 0, 0, mine * p.ring_s.n};
+  Ring rw{sm + p.RING_W, bars + 3 + p.ring_s.nslot, &p.ring_w, p.blob, 0, 0, mine * p.ring_w.n};
   if (c.uwarp == 0) {
     tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
     if (elect_one()) {
       mbar_init(c.mma_bar, 1);
       mbar_init(ld_bar, 1);
+      mbar_init(ldz_bar, 1);
       for (int i = 0; i < p.ring_s.nslot; ++i) mbar_init(&rs.bar[i], 1);
       for (int i = 0; i < p.ring_w.nslot; ++i) mbar_init(&rw.bar[i], 1);
       mbar_fence_init();
@@ -669,21 +689,28 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_c
     for (int k = p.L - 1; k >= 0; --k) {
       const TcGcp& g = p.g[k];
       const bool res = k > 0 && p.residual;
+      auto bstamp = [&](int i) { if (p.dbg != nullptr && blockIdx.x == 0 && w.tid == 0) p.dbg[(12 + k) * 16 + i] = clock64(); };
+      bstamp(0);
       // every reader of the Z / V / cotangent tiles of the previous GCP (weight-gradient products) is done
       wait_st();
       __syncthreads();
       // ---- inputs of GCP k: saved images (k > 0) -> Z[:, :s], V; their lo parts -> TMEM
       if (k > 0) {
         if (c.uwarp == 0 && elect_one()) {
-          const uint32_t bar = smem_addr(ld_bar);
-          const uint32_t bytes = (uint32_t)(p.s_img + p.v_img) * 4u;
           const float* sp = saved_t + (size_t)(k - 1) * (p.s_img + p.v_img);
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(smem_addr(Z)), "l"(sp), "r"((uint32_t)p.s_img * 4u), "r"(bar) : "memory");
+          const uint32_t bar = smem_addr(ld_bar);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)p.v_img * 4u) : "memory");
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                        ::"r"(smem_addr(V)), "l"(sp + p.s_img), "r"((uint32_t)p.v_img * 4u), "r"(bar) : "memory");
+          if (k == p.L - 1) {  // first GCP of the tile: nobody prefetched its S image
+            const uint32_t zbar = smem_addr(ldz_bar);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(zbar), "r"((uint32_t)p.s_img * 4u) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_addr(Z)), "l"(sp), "r"((uint32_t)p.s_img * 4u), "r"(zbar) : "memory");
+          }
         }
+        mbar_wait(ldz_bar, ldz_n & 1u);
+        ++ldz_n;
         mbar_wait(ld_bar, ld_n & 1u);
         ++ld_n;
         __syncwarp();
@@ -698,6 +725,7 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_c
             tmem_st4(w.tl + (uint32_t)(p.VLO + PW * x + 4 * gi), lo_part(v.x), lo_part(v.y), lo_part(v.z), lo_part(v.w));
           }
       }
+      bstamp(1);
       // ---- recompute the forward of GCP k up to [H | D | U] and [T | g]
       const float* smc;
       gcp_forward_tile<CS>(p, k, c, rs, rw, false, false, false, q, live, src, dst, orig, [] {}, &smc, true);
@@ -708,6 +736,7 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_c
       }
       const float* bs = smc + g.o_b;
       const float* bg = smc + g.o_b + g.sop;
+      bstamp(2);
       // ---- epilogue 1: cotangents of the two batches' outputs: [gT | gg] (GTG tile), gU (GHDU tile columns 16..31)
       for (int cg = w.part; 16 * cg < g.so; cg += CS) {
         float t[16], gs[16];
@@ -771,6 +800,7 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_c
         put4(GTG, w.tl + (uint32_t)p.ZLO, w.r, g.sop + 4 * gi, gg[0], gg[1], gg[2], gg[3]);
       }
       publish_and_sync();
+      bstamp(3);
       // ---- scalar data gradient: gZ = [gT | gg] . W_tg   (accumulator aliases [T | g])
       if (c.uwarp == 0) {
         ring_fill(rw);
@@ -782,17 +812,28 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_c
         if (elect_one()) commit(c.mma_bar);
         __syncwarp();
       }
+      bstamp(4);
       // ---- meanwhile: weight-gradient product G_tg += [gT | gg]^T . Z  (CUDA cores' tensor path, all warps)
       {
-        const int mt = p.pw >> 4, nt = (g.kz + 7) >> 3;
-        for (int pr = warp; pr < mt * nt; pr += 4 * CS) {
-          const int m0 = 16 * (pr % mt), n0 = 8 * (pr / mt);
-          float cf[4] = {0.f, 0.f, 0.f, 0.f};
-          wgrad_block(cf, GTG, Z, m0, n0, lane);
-          wgrad_store(cf, prow + b.off_tg[k], g.kz, m0, n0, p.pw, g.kz, accumulate, lane);
+        constexpr int NB = 4;
+        const int mt = p.pw >> 4, nt = (g.kz + 7) >> 3, ng = (nt + NB - 1) / NB;
+        for (int pr = warp; pr < mt * ng; pr += 4 * CS) {
+          const int m0 = 16 * (pr % mt), nb0 = NB * (pr / mt);
+          const int nb = nt - nb0 < NB ? nt - nb0 : NB;
+          float cf[NB][4];
+#pragma unroll
+          for (int bb = 0; bb < NB; ++bb)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cf[bb][q] = 0.f;
+          wgrad_blocks<NB>(cf, GTG, Z, m0, 8 * nb0, nb, lane);
+#pragma unroll
+          for (int bb = 0; bb < NB; ++bb)
+            if (bb < nb) wgrad_store(cf[bb], prow + b.off_tg[k], g.kz, m0, 8 * (nb0 + bb), p.pw, g.kz, accumulate, lane);
         }
       }
+      bstamp(5);
       wait_mma(c);
+      bstamp(6);
       rw.head += 2;
       if (c.uwarp == 0) ring_fill(rw);
       // ---- epilogue 3: gS (residual + gZ[:, :s]) -> GS; tail of gZ -> [gH | gD] (GHDU tile columns 0..15)
@@ -873,6 +914,7 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_c
         }
       }
       publish_and_sync();
+      bstamp(7);
       // ---- vector data gradient: gV_in = [gH | gD | gU] . W_v   (accumulator aliases the V lo region)
       if (c.uwarp == 0) {
         bool acc = false;
@@ -880,6 +922,13 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_c
                     make_idesc(128, 16, 0, 0), acc);
         if (elect_one()) {
           commit(c.mma_bar);
+          if (k > 1) {  // S image of the next GCP: the Z tile's readers (scalar batches, weight-gradient product) are done
+            const float* sp = saved_t + (size_t)(k - 2) * (p.s_img + p.v_img);
+            const uint32_t zbar = smem_addr(ldz_bar);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(zbar), "r"((uint32_t)p.s_img * 4u) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_addr(Z)), "l"(sp), "r"((uint32_t)p.s_img * 4u), "r"(zbar) : "memory");
+          }
           if (k == 0) {  // per-edge cotangents of message GCP 0's per-node products, for the node-level finish
             float* yp = b.Y + (size_t)tile * (b.y_img_g + b.y_img_v);
             bulk_store(yp, GTG, b.y_img_g);
@@ -888,16 +937,19 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_c
         }
         __syncwarp();
       }
+      bstamp(8);
       // ---- meanwhile: G_v += sum_xyz [gH | gD | gU]^T . V_in
       if (warp >= 4 * CS - 4) {
         const int pr = warp - (4 * CS - 4);  // 2 x 2 blocks of 16 x 8
         const int m0 = 16 * (pr & 1), n0 = 8 * (pr >> 1);
-        float cf[4] = {0.f, 0.f, 0.f, 0.f};
+        float cf[1][4] = {{0.f, 0.f, 0.f, 0.f}};
 #pragma unroll 1
-        for (int x = 0; x < 3; ++x) wgrad_block(cf, GHDU + x * GPLANE, V + x * PLANE, m0, n0, lane);
-        wgrad_store(cf, prow + b.off_v[k], 16, m0, n0, VN, 16, accumulate, lane);
+        for (int x = 0; x < 3; ++x) wgrad_blocks<1>(cf, GHDU + x * GPLANE, V + x * PLANE, m0, n0, 1, lane);
+        wgrad_store(cf[0], prow + b.off_v[k], 16, m0, n0, VN, 16, accumulate, lane);
       }
+      bstamp(9);
       wait_mma(c);
+      bstamp(10);
       // ---- epilogue 4: gV (residual (+ gU with vector_residual) + gV_in) -> GV; GCP 0: cotangent of the edge vectors
       for (int gi = w.part; gi < (PW >> 2); gi += CS) {
         float a[3][4], gv[3][4];
@@ -927,6 +979,7 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_c
           for (int j = 0; j < 3; ++j) *reinterpret_cast<float4*>(gp + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
         }
       }
+      bstamp(11);
       rs.head += 1;
     }
     if (c.uwarp == 0 && elect_one()) bulk_store_wait_read();  // the Y images of this tile have left shared memory

@@ -47,7 +47,7 @@ struct TcPlan {
   int node_partial_ctas = 0, node_partial_stride = 0;  // node-level weight-gradient partials of message GCP 0
   int wt_off_hi[12] = {0}, wt_off_lo[12] = {0};
 };
-constexpr int TC_POST_CTAS = 16;  // node chunks of the node-level weight-gradient partials
+constexpr int TC_POST_CTAS = 64;  // node chunks of the node-level weight-gradient partials
 
 inline int rup(int x, int m) { return (x + m - 1) / m * m; }
 
@@ -199,7 +199,7 @@ inline TcPlan make_tc_plan(const gcpnet_layer& l, long long N, long long E) {
     f.FBUF = carve2(TE * 9);
     f.RING_S = carve2(f.ring_s.nslot * f.ring_s.slot_floats);
     f.RING_W = carve2(f.ring_w.nslot * f.ring_w.slot_floats);
-    f.BARS = carve2(2 * (2 + f.ring_s.nslot + f.ring_w.nslot));
+    f.BARS = carve2(2 * (3 + f.ring_s.nslot + f.ring_w.nslot));
     f.smem_floats = o2;
     if ((long long)o2 * 4 > TC_SMEM_LIMIT_BYTES) return no("backward tile does not fit shared memory");
     // TMEM: GS | GV | R1 = Z lo / [gT|gg] lo | R2 = V lo / gV accumulator | vector accumulator | R3 = [T|g] / gZ accumulator | [gH|gD|gU] lo
