@@ -334,9 +334,15 @@ __device__ __forceinline__ void wg_hmma(float (&c)[4], const uint32_t (&a)[4], c
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 template <int TE, int NT, int JW, int IW, class FMap>
+__device__ __forceinline__ void tile_wgrad_ffma(const float* G, int ldg, int J, const float* Zin, int ldz, int I,
+                                                float* P, float* Pb, bool accumulate, FMap fmap, int tid);
+template <int TE, int NT, int JW, int IW, class FMap>
 __device__ __forceinline__ void tile_wgrad(const float* G, int ldg, int J, const float* Zin, int ldz, int I,
                                            float* P, float* Pb, bool accumulate, FMap fmap, int tid) {
   static_assert(TE % 8 == 0, "tile rows");
+  // The legacy tensor path only pays for short reductions (node tiles, 16 rows: the FFMA version is bound by its
+  // per-output overhead there); on the wide edge tiles the FFMA blocks win (mma.sync tf32 runs at ~2x FFMA rate, 3xTF32).
+  if (TE > 16) { tile_wgrad_ffma<TE, NT, JW, IW>(G, ldg, J, Zin, ldz, I, P, Pb, accumulate, fmap, tid); return; }
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int JB = (J + 15) >> 4, IB = (I + 7) >> 3;
   for (int blk = warp; blk < JB * IB; blk += NT / 32) {
@@ -379,9 +385,12 @@ __device__ __forceinline__ void tile_wgrad(const float* G, int ldg, int J, const
     }
   }
 }
+#define GCP_WGRAD_NAME tile_wgrad_ffma
 #else
+#define GCP_WGRAD_NAME tile_wgrad
+#endif
 template <int TE, int NT, int JW, int IW, class FMap>
-GCP_HD void tile_wgrad(const float* G, int ldg, int J, const float* Zin, int ldz, int I,
+GCP_HD void GCP_WGRAD_NAME(const float* G, int ldg, int J, const float* Zin, int ldz, int I,
                        float* P, float* Pb, bool accumulate, FMap fmap, int tid) {
   static_assert((JW == 1 || JW == 4) && (IW == 4 || IW == 8), "tile shape");
   const int JT = (J + JW - 1) / JW, IT = (I + IW - 1) / IW;
@@ -441,8 +450,6 @@ GCP_HD void tile_wgrad(const float* G, int ldg, int J, const float* Zin, int ldz
     }
   }
 }
-
-#endif
 
 // ------------------------------------------------------------------------------------------
 // cooperative row copies: warp per row, lane per column (coalesced, no integer division)
@@ -539,7 +546,7 @@ GCP_HD float gcp2_vec_up(const GcpOp& op, const TileBufs& b, const float* wu, in
 // WU from it in its update phase, then releases it with gcp2_fwd_finish()).
 // Phases: [vec_down] [norm+scalarize] [GEMM chunk]* [gate].
 template <int TE, int NT, int SL>
-GCP_HDN_NOINLINE const float* gcp2_fwd_tile(const GcpOp& op, const TileBufs& b, WPipe& wp, int e3, float slope, bool refill_first) {
+GCP_HDN const float* gcp2_fwd_tile(const GcpOp& op, const TileBufs& b, WPipe& wp, int e3, float slope, bool refill_first) {
   const GcpW& W = op.w;
   // ---- S chunk: vector_down / vector_down_frames
   GCP_PHASE_BEGIN(NT)
@@ -672,7 +679,7 @@ struct EmitTile {
   GCP_HD void operator()(int e, int i, float val) const { float* d = p + e * ld + i; *d = add ? *d + val : val; }
 };
 template <int TE, int NT, int SLF, int SLD, class EmitS, class EmitV>
-GCP_HDN_NOINLINE void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g, WPipe& wp, int e3, float slope,
+GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g, WPipe& wp, int e3, float slope,
                            float* prow, bool accumulate, bool refill_first, EmitS emit_s, EmitV emit_v) {
   const GcpW& W = op.w;
   const int cols = W.cols, hdp = W.hdp;
@@ -848,6 +855,18 @@ GCP_HDN_NOINLINE void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const Bw
     }
   }
   GCP_PHASE_END
+}
+
+// Out-of-line entry points for kernels that run each GCP ONCE per tile (node update): three inlined copies of these
+// routines do not fit the instruction cache, one shared copy does.  The edge kernels loop over their GCPs and inline.
+template <int TE, int NT, int SL>
+GCP_HDN_NOINLINE const float* gcp2_fwd_tile_call(const GcpOp& op, const TileBufs& b, WPipe& wp, int e3, float slope, bool refill_first) {
+  return gcp2_fwd_tile<TE, NT, SL>(op, b, wp, e3, slope, refill_first);
+}
+template <int TE, int NT, int SLF, int SLD>
+GCP_HDN_NOINLINE void gcp2_bwd_tile_call(const GcpOp& op, const TileBufs& b, const BwdBufs& g, WPipe& wp, int e3, float slope,
+                                         float* prow, bool accumulate, bool refill_first, EmitTile emit_s, EmitTile emit_v) {
+  gcp2_bwd_tile<TE, NT, SLF, SLD>(op, b, g, wp, e3, slope, prow, accumulate, refill_first, emit_s, emit_v);
 }
 
 }  // namespace gcp

@@ -278,7 +278,7 @@ GCP_HDN void node_fwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
   // FF0: (s, v) -> (hs, hv)
   {
     const TileBufs b = node_bufs(p, sm, 0);
-    const float* gch = gcp2_fwd_tile<TE, NT, SLF>(p.ff0, b, wp, 0, p.slope, false);
+    const float* gch = gcp2_fwd_tile_call<TE, NT, SLF>(p.ff0, b, wp, 0, p.slope, false);
     const float* wu = gch + p.ff0.w.o_wu;
     float* ZB = sm + L.ZB; float* VB = sm + L.VB;
     GCP_PHASE_BEGIN(NT)
@@ -312,7 +312,7 @@ GCP_HDN void node_fwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
   // FF1: (hs, hv) -> (s, v), then x2 = x1n + Dropout1(f)
   {
     const TileBufs b = node_bufs(p, sm, 1);
-    const float* gch = gcp2_fwd_tile<TE, NT, SLF>(p.ff1, b, wp, 0, p.slope, true);
+    const float* gch = gcp2_fwd_tile_call<TE, NT, SLF>(p.ff1, b, wp, 0, p.slope, true);
     const float* wu = gch + p.ff1.w.o_wu;
     GCP_PHASE_BEGIN(NT)
     const int lane = tid & 31;
@@ -362,7 +362,7 @@ GCP_HDN void node_fwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
   GCP_PHASE_END
   if (p.has_pos) {
     const TileBufs b = node_bufs(p, sm, 2);
-    const float* gch = gcp2_fwd_tile<TE, NT, SLF>(p.pu, b, wp, 0, p.slope, false);
+    const float* gch = gcp2_fwd_tile_call<TE, NT, SLF>(p.pu, b, wp, 0, p.slope, false);
     const float* wu = gch + p.pu.w.o_wu;
     GCP_PHASE_BEGIN(NT)
     if (p.saved != nullptr) {
@@ -433,7 +433,7 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
       }
     }
     GCP_PHASE_END
-    gcp2_bwd_tile<TE, NT, SLF, SLD>(
+    gcp2_bwd_tile_call<TE, NT, SLF, SLD>(
         p.pu, b, g, wp, 0, p.slope, prow, accumulate, false, EmitTile{GXS, ldgxs, true}, EmitTile{GXV, ldgxv, true});
   }
   // ---- LayerNorm1 backward (input x2)
@@ -475,13 +475,13 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
   {
     g.GS = GS1; g.ldgs = L.ldgs1; g.GV = GV1; g.ldgv = L.ldgv1;
     const int ldgs0 = L.ldgs0, ldgv0 = L.ldgv0;
-    gcp2_bwd_tile<TE, NT, SLF, SLD>(
+    gcp2_bwd_tile_call<TE, NT, SLF, SLD>(
         p.ff1, b1, g, wp, 0, p.slope, prow, accumulate, false, EmitTile{GS0, ldgs0, false}, EmitTile{GV0, ldgv0, false});
   }
   // ---- FF0 backward: cotangents (GS0, GV0) -> accumulated into the cotangent of x1n
   {
     g.GS = GS0; g.ldgs = L.ldgs0; g.GV = GV0; g.ldgv = L.ldgv0;
-    gcp2_bwd_tile<TE, NT, SLF, SLD>(
+    gcp2_bwd_tile_call<TE, NT, SLF, SLD>(
         p.ff0, b0, g, wp, 0, p.slope, prow, accumulate, false, EmitTile{GXS, ldgxs, true}, EmitTile{GXV, ldgxv, true});
   }
   // ---- LayerNorm0 backward (input x1, kept raw in X2S/X2V)
