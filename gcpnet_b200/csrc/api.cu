@@ -200,8 +200,8 @@ static int launch_node_bwd(const NodeParams& p, const NodeTilePlan& tp, cudaStre
   if (tp.SLF == 4) return launch(node_bwd_kernel<NODE_TE, NODE_NT, 4, NODE_SLD>, p, tp.grid, NODE_NT, bytes, st);
   return fail("no kernel instantiation for this node tile plan");
 }
-static int launch_pack(const LayerOps& ops, float* blob, cudaStream_t st) {
-  const PackParams pp = make_pack_params(ops, blob);
+static int launch_pack(const LayerOps& ops, float* blob, cudaStream_t st, bool skip_messages = false) {
+  const PackParams pp = make_pack_params(ops, blob, skip_messages);
   pack_kernel<<<dim3(pp.n, 16), 256, 0, st>>>(pp);
   gcp_note_launches(1);
   CUDA_TRY(cudaGetLastError());
@@ -343,7 +343,7 @@ int gcpnet_layer_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, c
   const std::string e = make_layer_plan(l, graph->num_nodes, graph->num_edges, &lp, nullptr, plan->tc_edge_path != 0);
   if (!e.empty()) return fail("layer_forward: " + e);
   if (graph->num_nodes <= 0) return 0;
-  if (launch_pack(lp.ops, io->packed, st)) return 1;
+  if (launch_pack(lp.ops, io->packed, st, lp.tc.ok)) return 1;
   if (run_edge_forward(l, *graph, lp, *io, st)) return 1;
   NodeParams p = make_node_params(l, *graph, lp.ops, lp.nf, false, io->packed);
   p.h = io->h; p.chi = io->chi; p.msg = io->msg; p.pos = io->pos;

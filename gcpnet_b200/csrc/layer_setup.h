@@ -143,10 +143,10 @@ inline LayerOps layer_ops(const gcpnet_layer& l, int edge_cap = EDGE_CAP_FLOATS,
   return o;
 }
 
-inline PackParams make_pack_params(const LayerOps& o, float* blob) {
+inline PackParams make_pack_params(const LayerOps& o, float* blob, bool skip_messages = false) {
   PackParams p{};
   p.blob = blob;
-  for (int k = 0; k < o.L; ++k) p.ops[p.n++] = o.msg[k];
+  for (int k = 0; k < o.L && !skip_messages; ++k) p.ops[p.n++] = o.msg[k];  // the tensor-core path packs its own message tiles
   p.ops[p.n++] = o.ff0; p.ops[p.n++] = o.ff1;
   if (o.has_pos) p.ops[p.n++] = o.pu;
   return p;

@@ -1024,10 +1024,16 @@ __global__ void __launch_bounds__(256) tc_post_data_kernel(const TcPostParams p)
   float acc = 0.f;
   if (o < p.s) {
     const float* Bs = p.blob + p.nt.ps; const float* Bd = p.blob + p.nt.pd;  // [pw][s] slab, pitch pw
-    for (int c = 0; c < p.pw; ++c) {
-      const int off = ((o >> 2) * p.pw + c) * 4 + (o & 3);
-      acc = fmaf(As[c], __ldg(Bs + off), fmaf(Ad[c], __ldg(Bd + off), acc));
+    const float* bs0 = Bs + (o >> 2) * p.pw * 4 + (o & 3);
+    const float* bd0 = Bd + (o >> 2) * p.pw * 4 + (o & 3);
+    float acc2 = 0.f;
+#pragma unroll 2
+    for (int c = 0; c < p.pw; c += 4) {  // pw % 4 == 0; A rows are 16-byte aligned
+      const float4 a = *reinterpret_cast<const float4*>(As + c), d = *reinterpret_cast<const float4*>(Ad + c);
+      acc = fmaf(a.x, __ldg(bs0 + 4 * c), fmaf(a.y, __ldg(bs0 + 4 * c + 4), fmaf(a.z, __ldg(bs0 + 4 * c + 8), fmaf(a.w, __ldg(bs0 + 4 * c + 12), acc))));
+      acc2 = fmaf(d.x, __ldg(bd0 + 4 * c), fmaf(d.y, __ldg(bd0 + 4 * c + 4), fmaf(d.z, __ldg(bd0 + 4 * c + 8), fmaf(d.w, __ldg(bd0 + 4 * c + 12), acc2))));
     }
+    acc += acc2;
     p.g_h[(size_t)i * p.s + o] += acc;
   } else {
     const int ch = (o - p.s) / 3, x = (o - p.s) - 3 * ch;

@@ -134,6 +134,9 @@ void gcpnet_profile_enable(int on);
 /* Runtime options: "tc" = 1/0 use / do not use the tensor-core (tcgen05, 3xTF32) edge kernels where the plan
  * allows them (default 1).  Returns the previous value, -1 for an unknown option. */
 int gcpnet_set_option(const char* name, int value);
+/* Development aid: when non-NULL, CTA 0 of the tensor-core edge kernels writes clock64() stamps of its first tile's
+ * stages into this device buffer of 24 x 16 int64 (scripts/tc_bwd_stamps.py decodes them).  NULL switches it off. */
+void gcpnet_debug_stamps(long long* device_buffer);
 int gcpnet_profile_read(int which, double* total_ms, int64_t* launches);
 
 /* CSR build (replaces the index side of torch_scatter.scatter, gcpnet.py:946 and comp/__init__.py:316). */

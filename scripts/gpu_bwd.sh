@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 300 python scripts/tc_bwd_stamps.py > gpurun_out/tc_bwd.log 2>&1; echo "rc=$?" >> gpurun_out/tc_bwd.log
+timeout 300 python scripts/tc_bwd_check.py test51 > gpurun_out/tc_bwd.log 2>&1; echo "rc=$?" >> gpurun_out/tc_bwd.log
 cat gpurun_out/tc_bwd.log

@@ -256,3 +256,113 @@ def test_graph_build_matches_stable_sort():
     assert np.array_equal(gv.src_ptr.cpu().numpy(), np.searchsorted(row[perm][spos], np.arange(n + 1)).astype(np.int32))
     want = O.segment_reduce(frames.reshape(E, 9), ei[0], n, "mean")
     assert torch.allclose(gv.fbar.cpu(), want, rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------
+# tensor-core (tcgen05, 3xTF32) edge path vs the FFMA tile path; whole-step CUDA graph
+# ------------------------------------------------------------------------------------------
+def _with_tc(flag, fn):
+    from gcpnet_b200 import _lib
+    lib = _lib.load()
+    prev = lib.gcpnet_set_option(b"tc", int(flag))
+    try:
+        return fn()
+    finally:
+        lib.gcpnet_set_option(b"tc", prev)
+
+
+def test_plan_reports_tensor_core_path_for_nms_dims_only():
+    import ctypes as C
+    from gcpnet_b200 import _cabi, _lib
+    lib = _lib.load()
+    for dims, want in (((64, 16), 1), ((100, 16), 0), ((8, 4), 0)):
+        cfg = O.OracleConfig(node_dims=dims, edge_dims=(32, 4) if dims[0] >= 64 else (4, 2), bottleneck=4 if dims[0] >= 64 else 2,
+                             default_bottleneck=4 if dims[0] >= 64 else 2)
+        layer = build_module(cfg, O.random_layer_params(cfg, seed=1))
+        struct = layer._layer_struct(layer._params_in_order(), False)
+        plan = _cabi.Plan()
+        _lib.check(lib.gcpnet_layer_plan(C.byref(struct), 256, 1024, C.byref(plan)), "plan")
+        assert plan.tc_edge_path == want, dims
+        prev = lib.gcpnet_set_option(b"tc", 0)
+        try:
+            _lib.check(lib.gcpnet_layer_plan(C.byref(struct), 256, 1024, C.byref(plan)), "plan")
+            assert plan.tc_edge_path == 0
+        finally:
+            lib.gcpnet_set_option(b"tc", prev)
+
+
+@pytest.mark.parametrize("graph", ["nms20", "ragged_multigraph"])
+def test_tensor_core_and_ffma_paths_agree_and_match_oracle(graph):
+    """Same module, same inputs, both kernel families (several 128-edge tiles per CTA, ragged last tile, isolated nodes,
+    duplicates): each within 1e-4 of the oracle, and within 2e-5 of each other.  The 24 320-edge case uses a smooth
+    scalar nonlinearity: with ReLU, 12 M pre-activations guarantee a few units within rounding of the kink, any two fp32
+    evaluation orders then differ by whole per-edge gradient rows (measured: both kernel families AND the fp32 oracle sit
+    5e-2 from the fp64 oracle on grad_e there), which says nothing about the kernels."""
+    cfg = O.OracleConfig(node_dims=(64, 16), edge_dims=(32, 4), updating_node_positions=True,
+                         scalar_nonlinearity="silu" if graph == "nms20" else "relu")
+    if graph == "nms20":
+        case, inputs = _random_case(cfg, n=1280, E=0, seed=51, graph="nms", k=20)   # 24 320 edges = 190 tiles > 148 CTAs
+    else:
+        case, inputs = _random_case(cfg, n=333, E=1901, seed=53)
+    params = O.random_layer_params(cfg, seed=50)
+    want = oracle_forward_backward(case, cfg, params, inputs)
+    exact = oracle_forward_backward(case, cfg, params, inputs, dtype=torch.float64)
+    layer = build_module(cfg, params).eval()
+    res = {tc: _with_tc(tc, lambda: module_forward_backward(layer, case, cfg, inputs)) for tc in (0, 1)}
+    names = [k for k, _ in layer.named_parameters()]
+    for tc in (0, 1):
+        _compare(res[tc], want, names, exact=exact)
+    for key in ("out_h", "out_chi", "out_pos"):
+        assert rel_err(res[1][key].numpy(), res[0][key].numpy()) < 2e-5, key
+
+
+def test_tensor_core_path_nonresidual_vector_residual_and_silu():
+    """Flag combinations of the message stack on the tensor-core path (NMS dims)."""
+    for kw in (dict(use_residual_message_gcp=False), dict(vector_residual=True), dict(scalar_nonlinearity="silu"),
+               dict(num_message_layers=1), dict(num_message_layers=3, reduce_function="mean")):
+        cfg = O.OracleConfig(node_dims=(64, 16), edge_dims=(32, 4), **kw)
+        case, inputs = _random_case(cfg, n=150, E=700, seed=61)
+        params = O.random_layer_params(cfg, seed=60)
+        want = oracle_forward_backward(case, cfg, params, inputs)
+        exact = oracle_forward_backward(case, cfg, params, inputs, dtype=torch.float64)
+        layer = build_module(cfg, params).eval()
+        res = _with_tc(1, lambda: module_forward_backward(layer, case, cfg, inputs))
+        _compare(res, want, [k for k, _ in layer.named_parameters()], exact=exact)
+
+
+def test_graphed_step_replays_the_eager_step():
+    """gcpnet_b200.GraphedStep: one CUDA graph per training step; replay with new inputs == eager on those inputs."""
+    import gcpnet_b200
+    cfg = O.OracleConfig(node_dims=(64, 16), edge_dims=(32, 4), updating_node_positions=True)
+    params = O.random_layer_params(cfg, seed=70)
+    layer = build_module(cfg, params).eval()
+    dev = torch.device("cuda")
+    ei = O.nms_edge_index(40, 5)
+
+    def batch(seed):
+        inp = O.synthetic_layer_inputs(cfg, ei, 200, seed=seed)
+        b = {k: inp[k].to(dev) for k in ("h", "chi", "e", "xi", "frames", "node_pos")}
+        b["edge_index"] = inp["edge_index"].to(dev)
+        for k in ("h", "chi", "e", "xi"):
+            b[k].requires_grad_(True)
+        return b
+
+    def loss_fn(b):
+        (oh, ochi), opos = layer((b["h"], b["chi"]), (b["e"], b["xi"]), b["edge_index"], b["frames"], node_pos=b["node_pos"])
+        return (oh * oh).sum() + ochi.sum() + opos.sum()
+
+    plist = list(layer.parameters())
+    static = batch(71)
+    step = gcpnet_b200.GraphedStep(loss_fn, static, plist)
+    new = batch(72)
+    loss_g = step({k: v.detach() for k, v in new.items()}).detach().clone()
+    grads_g = [p.grad.detach().clone() for p in plist]
+    gh_g = static["h"].grad.detach().clone()
+    for p in plist:
+        p.grad = None
+    loss_e = loss_fn(new)
+    loss_e.backward()
+    assert rel_err(loss_g.cpu().numpy(), loss_e.detach().cpu().numpy()) < 1e-6
+    assert rel_err(gh_g.cpu().numpy(), new["h"].grad.cpu().numpy()) < 1e-6
+    for a, p in zip(grads_g, plist):
+        assert rel_err(a.cpu().numpy(), p.grad.cpu().numpy()) < 1e-6
