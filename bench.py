@@ -384,8 +384,14 @@ def run_ours(args, w):
         us = tot_ms * 1e3 / max(cnt, 1)
         alg = (bb if dom == "edge_bwd" else bf) * E
         gbs = alg / (us * 1e-6) / 1e9 if us > 0 else 0.0
+        traffic = None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed `ncu --set full` capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            traffic = tr.get(args.workload, {}).get(dom)
+        except Exception:
+            pass
         roof_out = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": gbs, "peak": peak, "unit": "GB/s",
-                    "frac": gbs / peak, "traffic": None,
+                    "frac": gbs / peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured, burst copy)" if peaks else "of fallback 6.65 TB/s",
                     "algorithmic_bytes_per_launch": alg, "us_per_launch": us, "launches_timed": cnt,
                     "kernel_share_of_step": tot_ms / eager_ms,
