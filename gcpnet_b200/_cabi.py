@@ -76,7 +76,7 @@ class BackwardIO(C.Structure):
 
 
 EXPORTS = (
-    "gcpnet_version", "gcpnet_last_error", "gcpnet_launch_count", "gcpnet_profile_enable", "gcpnet_profile_read", "gcpnet_set_option", "gcpnet_debug_stamps", "gcpnet_graph_workspace_bytes", "gcpnet_graph_build",
+    "gcpnet_version", "gcpnet_last_error", "gcpnet_launch_count", "gcpnet_profile_enable", "gcpnet_profile_read", "gcpnet_set_option", "gcpnet_debug_stamps", "gcpnet_set_side_stream", "gcpnet_join", "gcpnet_graph_workspace_bytes", "gcpnet_graph_build",
     "gcpnet_localize", "gcpnet_layer_plan", "gcpnet_layer_forward", "gcpnet_layer_backward",
     "gcpnet_message_passing_forward",
 )
@@ -96,6 +96,10 @@ def declare(lib: C.CDLL) -> None:
     lib.gcpnet_profile_read.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.gcpnet_set_option.restype = C.c_int
     lib.gcpnet_set_option.argtypes = [C.c_char_p, C.c_int]
+    lib.gcpnet_set_side_stream.restype = C.c_int
+    lib.gcpnet_set_side_stream.argtypes = [C.c_void_p]
+    lib.gcpnet_join.restype = C.c_int
+    lib.gcpnet_join.argtypes = [C.c_void_p]
     lib.gcpnet_debug_stamps.restype = None
     lib.gcpnet_debug_stamps.argtypes = [C.c_void_p]
     lib.gcpnet_graph_workspace_bytes.restype = C.c_size_t

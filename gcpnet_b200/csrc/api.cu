@@ -209,7 +209,23 @@ static int launch_pack(const LayerOps& ops, float* blob, cudaStream_t st, bool s
 }
 static bool tc_option() { return g_opt_tc.load(std::memory_order_relaxed) != 0; }
 int gcp_tc_launch_edge_bwd(const tc::TcBwdParams& b, int grid, cudaStream_t st);           // tc_api.cu
-int gcp_tc_launch_post(const tc::TcPostParams& p, cudaStream_t st);                        // tc_api.cu
+int gcp_tc_launch_post(const tc::TcPostParams& p, int which, cudaStream_t st);             // tc_api.cu
+
+// ---- side stream: parameter-gradient post-processing off the critical path ---------------------------------------------
+// The next layer's backward only needs dh / dchi; reducing the partials and the chain rule to the reference's parameters
+// can overlap with it.  The caller owns the side stream (gcpnet_set_side_stream) and joins it with gcpnet_join() before
+// anything consumes the parameter gradients.  Events are created once, outside any stream capture.
+static std::mutex g_side_mu;
+static cudaStream_t g_side = nullptr;
+static std::vector<cudaEvent_t> g_side_events;      // pool
+static size_t g_side_next = 0;
+static std::vector<cudaEvent_t> g_side_pending;     // recorded on the side stream, not yet joined
+static cudaEvent_t side_event() {
+  if (g_side_events.empty()) return nullptr;
+  cudaEvent_t e = g_side_events[g_side_next % g_side_events.size()];
+  ++g_side_next;
+  return e;
+}
 int gcp_tc_launch_finalize(const float* partial, int rows, int stride, float* G, const float* npartial, int nrows, int nstride, float* Gn,
                            const tc::TcFinalParams& fp, cudaStream_t st);                  // tc_api.cu
 int gcp_tc_launch_pack(const tc::TcPackProg& prog, cudaStream_t st);                      // tc_api.cu
@@ -256,7 +272,6 @@ static int run_tc_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, co
     b.ge = io.g_e; b.gxi = io.g_xi; b.Y = Y; b.partial = io.ws_edge_partial;
     if (gcp_tc_launch_edge_bwd(b, T.grid, st)) return 1;
   }
-  GcpTimedScope timed(T_COT_REDUCE, st);
   tc::TcPostParams pp{};
   pp.N = (int)g.num_nodes; pp.s = l.s; pp.v = l.v; pp.pw = T.proto.pw;
   pp.Y = Y; pp.y_img_g = T.bproto.y_img_g; pp.y_img_v = T.bproto.y_img_v;
@@ -264,7 +279,27 @@ static int run_tc_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, co
   pp.h = io.h; pp.chi = io.chi; pp.blob = io.packed + lp.v2_packed_floats; pp.nt = T.proto.nt;
   pp.A = A; pp.g_h = io.g_h; pp.g_chi = io.g_chi;
   pp.npartial = npart; pp.npartial_stride = T.node_partial_stride; pp.nctas = T.node_partial_ctas;
-  if (gcp_tc_launch_post(pp, st)) return 1;
+  {
+    GcpTimedScope timed(T_COT_REDUCE, st);
+    if (gcp_tc_launch_post(pp, 1, st)) return 1;   // per-node sums of the per-edge cotangents
+  }
+  // fork: everything that only feeds the PARAMETER gradient runs on the side stream (if the caller gave one)
+  cudaStream_t ps = st;
+  cudaEvent_t ev_fork = nullptr, ev_done = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_side_mu);
+    if (g_side != nullptr && !gcp_profile_on()) { ev_fork = side_event(); ev_done = side_event(); }
+    if (ev_fork && ev_done) {
+      ps = g_side;
+      CUDA_TRY(cudaEventRecord(ev_fork, st));
+      CUDA_TRY(cudaStreamWaitEvent(ps, ev_fork, 0));
+    }
+  }
+  {
+    GcpTimedScope timed(T_COT_REDUCE, st);
+    if (gcp_tc_launch_post(pp, 2, st)) return 1;   // dh, dchi: the next layer's backward waits for these
+  }
+  if (gcp_tc_launch_post(pp, 4, ps)) return 1;
   tc::TcFinalParams fp{};
   fp.L = l.num_message_layers; fp.s = l.s; fp.v = l.v; fp.se = l.se; fp.ve = l.ve; fp.pw = T.proto.pw; fp.n_edge_params = l.n_edge_params;
   fp.G = G; fp.Gn = Gn; fp.out = io.g_params;
@@ -277,7 +312,21 @@ static int run_tc_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, co
     for (int i = 0; i < 7; ++i) f.grad_off[i] = d.grad_off[i];
     f.Wd = d.vector_down; f.Ws = d.scalar_out_w; f.bs = d.scalar_out_b; f.Wu = d.vector_up; f.Wg = d.vector_out_scale_w;
   }
-  return gcp_tc_launch_finalize(io.ws_edge_partial, T.grid, T.bproto.partial_stride, G, npart, T.node_partial_ctas, T.node_partial_stride, Gn, fp, st);
+  {
+    GcpTimedScope timed(T_PARTIAL_REDUCE, ps);
+    if (gcp_tc_launch_finalize(io.ws_edge_partial, T.grid, T.bproto.partial_stride, G, npart, T.node_partial_ctas, T.node_partial_stride, Gn, fp, ps))
+      return 1;
+    partial_reduce_kernel<<<(l.n_node_params + 255) / 256, 256, 0, ps>>>(io.g_params + l.n_edge_params, nullptr, 0, 0, io.ws_node_partial,
+                                                                          l.n_node_params, lp.nb.grid);
+    gcp_note_launches(1);
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (ps != st) {
+    std::lock_guard<std::mutex> lock(g_side_mu);
+    CUDA_TRY(cudaEventRecord(ev_done, ps));
+    g_side_pending.push_back(ev_done);
+  }
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -289,6 +338,24 @@ int gcpnet_version(void) { return 200; }
 const char* gcpnet_last_error(void) { return g_last_error.c_str(); }
 void gcpnet_profile_enable(int on) { g_profile.store(on != 0); }
 void gcpnet_debug_stamps(long long* device_buffer) { g_tc_dbg.store(device_buffer); }
+int gcpnet_set_side_stream(void* stream) {
+  std::lock_guard<std::mutex> lock(g_side_mu);
+  g_side = (cudaStream_t)stream;
+  if (g_side != nullptr && g_side_events.empty()) {
+    for (int i = 0; i < 64; ++i) {
+      cudaEvent_t e;
+      CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      g_side_events.push_back(e);
+    }
+  }
+  return 0;
+}
+int gcpnet_join(void* stream) {
+  std::lock_guard<std::mutex> lock(g_side_mu);
+  for (cudaEvent_t e : g_side_pending) CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, e, 0));
+  g_side_pending.clear();
+  return 0;
+}
 int gcpnet_set_option(const char* name, int value) {
   if (name && std::string(name) == "tc") return g_opt_tc.exchange(value);
   return -1;
@@ -394,13 +461,7 @@ int gcpnet_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, 
   if (launch_node_bwd(np, lp.nb, st)) return 1;
   int edge_grid = 0;
   if (g.num_edges > 0 && lp.tc.ok) {
-    if (run_tc_edge_backward(l, g, lp, *io, st)) return 1;
-    GcpTimedScope timed(T_PARTIAL_REDUCE, st);
-    partial_reduce_kernel<<<(l.n_node_params + 255) / 256, 256, 0, st>>>(io->g_params + l.n_edge_params, nullptr, 0, 0, io->ws_node_partial,
-                                                                         l.n_node_params, lp.nb.grid);
-    gcp_note_launches(1);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
+    return run_tc_edge_backward(l, g, lp, *io, st);
   }
   if (g.num_edges > 0) {
     EdgeParams ep = make_edge_params(l, g, lp.ops, lp.eb, true, io->packed);

@@ -61,12 +61,14 @@ int gcp_tc_launch_edge_bwd(const tc::TcBwdParams& b, int grid, cudaStream_t st) 
 }
 
 // node-level finish of message GCP 0 + reduction of the partials + chain rule to the reference's parameters
-int gcp_tc_launch_post(const tc::TcPostParams& p, cudaStream_t st) {
+// which: 1 = per-node sums, 2 = data gradient (dh, dchi), 4 = node-level weight-gradient partials
+int gcp_tc_launch_post(const tc::TcPostParams& p, int which, cudaStream_t st) {
   const long long n1 = (long long)p.N * 2 * (p.pw + 96), n2 = (long long)p.N * (p.s + 3 * p.v);
-  tc::tc_post_sum_kernel<<<(int)((n1 + 255) / 256), 256, 0, st>>>(p);
-  tc::tc_post_data_kernel<<<(int)((n2 + 255) / 256), 256, 0, st>>>(p);
-  tc::tc_post_wgrad_kernel<<<dim3((p.npartial_stride + 255) / 256, p.nctas), 256, 0, st>>>(p);
-  gcp_note_launches(3);
+  int n = 0;
+  if (which & 1) { tc::tc_post_sum_kernel<<<(int)((n1 + 255) / 256), 256, 0, st>>>(p); ++n; }
+  if (which & 2) { tc::tc_post_data_kernel<<<(int)((n2 + 255) / 256), 256, 0, st>>>(p); ++n; }
+  if (which & 4) { tc::tc_post_wgrad_kernel<<<dim3((p.npartial_stride + 255) / 256, p.nctas), 256, 0, st>>>(p); ++n; }
+  gcp_note_launches(n);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -149,6 +149,41 @@ class _LayerNormParams(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------
+# side stream: parameter-gradient post-processing overlaps with the next layer's backward
+# ------------------------------------------------------------------------------------------
+_SIDE = {"stream": None, "keep": [], "queued": False, "enabled": True}
+
+
+def _side_stream_setup() -> None:
+    """Create the side stream once (outside any CUDA-graph capture: the first backward of a process is a warm-up)."""
+    if _SIDE["stream"] is None and _SIDE["enabled"] and not torch.cuda.is_current_stream_capturing():
+        st = torch.cuda.Stream()
+        _lib.check(_lib.load().gcpnet_set_side_stream(st.cuda_stream), "gcpnet_set_side_stream")
+        _SIDE["stream"] = st
+
+
+def _join_side() -> None:
+    """End of a backward pass: the current stream waits for everything forked to the side stream."""
+    _SIDE["queued"] = False
+    if _SIDE["stream"] is not None:
+        _lib.check(_lib.load().gcpnet_join(_stream()), "gcpnet_join")
+    _SIDE["keep"].clear()
+
+
+def _after_backward_call(tensors) -> None:
+    """Keep the workspaces the side stream still reads alive until the join; make sure the join is queued."""
+    if _SIDE["stream"] is None:
+        return
+    _SIDE["keep"].extend(tensors)
+    if not _SIDE["queued"]:
+        try:
+            torch.autograd.Variable._execution_engine.queue_callback(_join_side)
+            _SIDE["queued"] = True
+        except RuntimeError:  # not inside an autograd backward pass (direct call): join right away
+            _join_side()
+
+
+# ------------------------------------------------------------------------------------------
 # autograd bridge
 # ------------------------------------------------------------------------------------------
 class _LayerFn(torch.autograd.Function):
@@ -186,6 +221,7 @@ class _LayerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         lib = _lib.load()
+        _side_stream_setup()
         mod, gv, plan = ctx.mod, ctx.gv, ctx.plan
         spec = mod.spec
         h, chi, e, xi, frames, saved_edge, saved_node, packed, *params = ctx.saved_tensors
@@ -209,6 +245,7 @@ class _LayerFn(torch.autograd.Function):
                               _ptr(g_xi), _ptr(g_params), _ptr(ws_agg), _ptr(ws_edge), _ptr(ws_ep), _ptr(ws_np), _ptr(packed))
         _lib.check(lib.gcpnet_layer_backward(C.byref(layer), C.byref(gv.struct), C.byref(plan), C.byref(io), _stream()),
                    "gcpnet_layer_backward")
+        _after_backward_call((ws_agg, ws_edge, ws_ep, ws_np, saved_edge, saved_node, packed, h, chi, g_params))
         if gv.E == 0:
             g_e.zero_()
             g_xi.zero_()

@@ -134,6 +134,14 @@ void gcpnet_profile_enable(int on);
 /* Runtime options: "tc" = 1/0 use / do not use the tensor-core (tcgen05, 3xTF32) edge kernels where the plan
  * allows them (default 1).  Returns the previous value, -1 for an unknown option. */
 int gcpnet_set_option(const char* name, int value);
+/* Optional side stream.  When set, gcpnet_layer_backward enqueues the work that only feeds the PARAMETER gradient
+ * (node-level weight-gradient partials, reduction of the per-CTA partials, chain rule to the reference's tensors) on
+ * this stream, forked from / ordered after the caller's stream by events, so it overlaps with the next layer's
+ * backward.  The caller must call gcpnet_join(stream) -- `stream` then waits for everything forked so far -- before
+ * reading g_params, and must keep the backward workspaces alive until then.  NULL (default): everything runs in
+ * order on the caller's stream.  At most 32 backward calls may be pending between two joins. */
+int gcpnet_set_side_stream(void* stream);
+int gcpnet_join(void* stream);
 /* Development aid: when non-NULL, CTA 0 of the tensor-core edge kernels writes clock64() stamps of its first tile's
  * stages into this device buffer of 24 x 16 int64 (scripts/tc_bwd_stamps.py decodes them).  NULL switches it off. */
 void gcpnet_debug_stamps(long long* device_buffer);
