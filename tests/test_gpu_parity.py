@@ -366,3 +366,33 @@ def test_graphed_step_replays_the_eager_step():
     assert rel_err(gh_g.cpu().numpy(), new["h"].grad.cpu().numpy()) < 1e-6
     for a, p in zip(grads_g, plist):
         assert rel_err(a.cpu().numpy(), p.grad.cpu().numpy()) < 1e-6
+
+
+def test_tensor_core_path_degenerate_graphs():
+    """NMS dims (tensor-core path): no edges, one self loop, 129 edges (one full tile + one row), isolated nodes."""
+    cfg = O.OracleConfig(node_dims=(64, 16), edge_dims=(32, 4), updating_node_positions=True)
+    params = O.random_layer_params(cfg, seed=81)
+    layer = build_module(cfg, params).eval()
+    g = torch.Generator().manual_seed(82)
+    for n, ei in ((4, torch.zeros((2, 0), dtype=torch.long)), (1, torch.zeros((2, 1), dtype=torch.long)),
+                  (40, torch.randint(0, 30, (2, 129), generator=g)), (300, torch.tensor([[0, 0, 7], [7, 7, 0]]))):
+        inputs = O.synthetic_layer_inputs(cfg, ei, n, seed=83)
+        case = dict(seed=84)
+        want = oracle_forward_backward(case, cfg, params, inputs)
+        res = _with_tc(1, lambda: module_forward_backward(layer, case, cfg, inputs))
+        _compare(res, want, [k for k, _ in layer.named_parameters()])
+
+
+def test_tensor_core_path_reruns_are_bit_identical_and_train_mode_runs():
+    cfg = O.OracleConfig(node_dims=(64, 16), edge_dims=(32, 4), updating_node_positions=True)
+    case, inputs = _random_case(cfg, n=500, E=4000, seed=91)
+    params = O.random_layer_params(cfg, seed=90)
+    layer = build_module(cfg, params).eval()
+    a = _with_tc(1, lambda: module_forward_backward(layer, case, cfg, inputs))
+    b = _with_tc(1, lambda: module_forward_backward(layer, case, cfg, inputs))
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    train = build_module(cfg, params, dropout=0.1).train()
+    c = _with_tc(1, lambda: module_forward_backward(train, case, cfg, inputs))
+    assert all(torch.isfinite(t).all() for t in c.values())
+    assert not torch.equal(c["out_h"], a["out_h"])
