@@ -273,7 +273,7 @@ static int run_tc_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, co
     if (gcp_tc_launch_edge_bwd(b, T.grid, st)) return 1;
   }
   tc::TcPostParams pp{};
-  pp.N = (int)g.num_nodes; pp.s = l.s; pp.v = l.v; pp.pw = T.proto.pw;
+  pp.N = (int)g.num_nodes; pp.s = l.s; pp.v = l.v; pp.pw = T.proto.pw; pp.rows = T.proto.rows;
   pp.Y = Y; pp.y_img_g = T.bproto.y_img_g; pp.y_img_v = T.bproto.y_img_v;
   pp.dst_ptr = g.dst_ptr; pp.src_ptr = g.src_ptr; pp.src_pos = g.src_pos;
   pp.h = io.h; pp.chi = io.chi; pp.blob = io.packed + lp.v2_packed_floats; pp.nt = T.proto.nt;

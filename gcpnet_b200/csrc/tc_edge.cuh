@@ -64,6 +64,7 @@ struct TcNodeTiles { int ps, pd, qs, qd; };  // blob offsets of the B tiles [sop
 
 struct TcEdgeParams {
   int N, E, L;
+  int rows;                           // edges per tile: 128, or fewer (multiple of 8) so that small graphs still give every SM a tile
   int s, v, se, ve;
   int residual, e3;
   float slope;
@@ -108,7 +109,7 @@ struct TcBwdParams {
 };
 
 struct TcPostParams {
-  int N, s, v, pw;
+  int N, s, v, pw, rows;
   const float* Y; int y_img_g, y_img_v;
   const int *dst_ptr, *src_ptr, *src_pos;
   const float *h, *chi, *blob;

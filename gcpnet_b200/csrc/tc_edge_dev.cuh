@@ -469,7 +469,7 @@ template <int CS>
 __global__ void __launch_bounds__(128 * CS, 1) tc_edge_fwd_kernel(const __grid_constant__ TcEdgeParams p) {
   extern __shared__ __align__(128) float sm[];
   __shared__ uint32_t tmem_slot;
-  const int ntiles = (p.E + TE - 1) / TE;
+  const int ntiles = (p.E + p.rows - 1) / p.rows;
   const int mine = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   if (mine == 0) return;
   TileCtx c;
@@ -505,8 +505,8 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_fwd_kernel(const __grid_c
   float* Z = sm + p.ZBUF; float* V = sm + p.VBUF;
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long q = (long long)tile * TE + c.w.r;
-    const bool live = q < p.E;
+    const long long q = (long long)tile * p.rows + c.w.r;
+    const bool live = c.w.r < p.rows && q < p.E;
     const int src = live ? p.src[q] : 0, dst = live ? p.dst[q] : 0, orig = live ? p.perm[q] : 0;
     float* saved_t = p.saved ? p.saved + (size_t)tile * p.saved_tile_stride : nullptr;
     // the gathers below overwrite tile columns other threads of the row still read in the previous tile's epilogue B
@@ -546,7 +546,7 @@ __device__ __forceinline__ void hmma_tf32(float (&c)[4], uint32_t a0, uint32_t a
 // c[b][16 x 8 block at (m0, n0 + 8 b)] += sum over the 128 tile rows e of A[e][m0 + .] * B[e][n0 + 8 b + .]   (A, B slab tiles)
 // NB column blocks share the A fragments; the three 3xTF32 terms keep separate accumulators (short dependency chains).
 template <int NB>
-__device__ __forceinline__ void wgrad_blocks(float (&c)[NB][4], const float* A, const float* B, int m0, int n0, int nb, int lane) {
+__device__ __forceinline__ void wgrad_blocks(float (&c)[NB][4], const float* A, const float* B, int m0, int n0, int nb, int lane, int rows) {
   const int g = lane >> 2, t = lane & 3;
   const float* a_row0 = A + slab_off(RP, t, m0 + g);
   const float* a_row1 = A + slab_off(RP, t, m0 + g + 8);
@@ -559,7 +559,7 @@ __device__ __forceinline__ void wgrad_blocks(float (&c)[NB][4], const float* A, 
 #pragma unroll
     for (int q = 0; q < 4; ++q) { c1[bb][q] = 0.f; c2[bb][q] = 0.f; }
 #pragma unroll 2
-  for (int k0 = 0; k0 < TE; k0 += 8) {
+  for (int k0 = 0; k0 < rows; k0 += 8) {  // rows beyond the tile hold zeros anyway
     const float fa[4] = {a_row0[4 * k0], a_row1[4 * k0], a_row0[4 * (k0 + 4)], a_row1[4 * (k0 + 4)]};
     uint32_t ah[4], al[4];
 #pragma unroll
@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_c
   extern __shared__ __align__(128) float sm[];
   __shared__ uint32_t tmem_slot;
   const TcEdgeParams& p = b.f;
-  const int ntiles = (p.E + TE - 1) / TE;
+  const int ntiles = (p.E + p.rows - 1) / p.rows;
   const int mine = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   if (mine == 0) return;
   TileCtx c;
@@ -650,8 +650,8 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_c
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const bool accumulate = tile != (int)blockIdx.x;
-    const long long q = (long long)tile * TE + w.r;
-    const bool live = q < p.E;
+    const long long q = (long long)tile * p.rows + w.r;
+    const bool live = w.r < p.rows && q < p.E;
     const int src = live ? p.src[q] : 0, dst = live ? p.dst[q] : 0, orig = live ? p.perm[q] : 0;
     const float* saved_t = p.saved + (size_t)tile * p.saved_tile_stride;
     // ---- cotangent of the final message: gagg[dst] (/ in-degree for the mean reduce, gcpnet.py:946) -> GS, GV (TMEM)
@@ -825,7 +825,7 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_c
           for (int bb = 0; bb < NB; ++bb)
 #pragma unroll
             for (int q = 0; q < 4; ++q) cf[bb][q] = 0.f;
-          wgrad_blocks<NB>(cf, GTG, Z, m0, 8 * nb0, nb, lane);
+          wgrad_blocks<NB>(cf, GTG, Z, m0, 8 * nb0, nb, lane, p.rows);
 #pragma unroll
           for (int bb = 0; bb < NB; ++bb)
             if (bb < nb) wgrad_store(cf[bb], prow + b.off_tg[k], g.kz, m0, 8 * (nb0 + bb), p.pw, g.kz, accumulate, lane);
@@ -944,7 +944,7 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_c
         const int m0 = 16 * (pr & 1), n0 = 8 * (pr >> 1);
         float cf[1][4] = {{0.f, 0.f, 0.f, 0.f}};
 #pragma unroll 1
-        for (int x = 0; x < 3; ++x) wgrad_blocks<1>(cf, GHDU + x * GPLANE, V + x * PLANE, m0, n0, 1, lane);
+        for (int x = 0; x < 3; ++x) wgrad_blocks<1>(cf, GHDU + x * GPLANE, V + x * PLANE, m0, n0, 1, lane, p.rows);
         wgrad_store(cf[0], prow + b.off_v[k], 16, m0, n0, VN, 16, accumulate, lane);
       }
       bstamp(9);
@@ -997,7 +997,7 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_c
 // atomics), push them through the node tiles (data gradient) and against h / chi (weight gradient).
 // ---------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float y_at(const TcPostParams& p, int q, int c) {
-  const int tile = q >> 7, r = q & 127;
+  const int tile = q / p.rows, r = q - tile * p.rows;
   const float* yp = p.Y + (size_t)tile * (p.y_img_g + p.y_img_v);
   if (c < p.pw) return __ldg(yp + ((c >> 2) * RP + r) * 4 + (c & 3));
   const int c2 = c - p.pw, x = c2 >> 5, cc = c2 & 31;

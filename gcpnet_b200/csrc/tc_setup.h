@@ -168,7 +168,17 @@ inline TcPlan make_tc_plan(const gcpnet_layer& l, long long N, long long E) {
   // ---- saved activations: per tile, per GCP k < L-1: S image (s/4 slabs) + V image (3 planes)
   p.s_img = (s / 4) * SLAB; p.v_img = 3 * PLANE;
   p.saved_tile_stride = (long long)(L - 1) * (p.s_img + p.v_img);
-  const long long tiles = (E + TE - 1) / TE;
+  // tile height: 128 rows, or the smallest multiple of 8 (>= 32) that still gives one tile per SM on small graphs (the
+  // per-tile latency chain does not depend on the row count, the row-proportional stages -- weight-gradient products,
+  // TMEM / shared-memory traffic -- shrink with it)
+  int rows = TE;
+  if (E < 148LL * TE) {
+    rows = rup((int)((E + 147) / 148), 8);
+    if (rows < 32) rows = 32;
+    if (rows > TE) rows = TE;
+  }
+  p.rows = rows;
+  const long long tiles = (E + rows - 1) / rows;
   P.saved_floats = tiles * p.saved_tile_stride;
   P.pq_floats = N * (2 * p.pw + 192);
   P.grid = (int)(tiles < 1 ? 1 : (tiles > 148 ? 148 : tiles));
