@@ -46,6 +46,81 @@ __global__ void mean_frame_kernel(const float* __restrict__ frames, const int* _
   fbar[idx] = b > a ? acc / (float)(b - a) : 0.f;
 }
 
+// ---- small graphs: the whole build in ONE CTA --------------------------------------------------------------------
+// At NMS-small sizes (E = 5 120) the radix-sort pipeline above is 13 launches of mostly idle kernels.  One CTA does the
+// same job: counting sort by destination / by source with shared-memory cursors, then every node orders its own segment
+// by edge id (destination view) / by sorted position (source view), which reproduces the stable order of the radix sort
+// exactly -- the result does not depend on the order in which the atomics land.
+constexpr int SMALL_MAX_NODES = 12287, SMALL_MAX_EDGES = 65536, SMALL_NT = 1024;
+__global__ void __launch_bounds__(SMALL_NT) graph_build_small_kernel(const int64_t* __restrict__ edge_index, int E, int N,
+                                                                     const float* __restrict__ frames, int* __restrict__ perm,
+                                                                     int* __restrict__ src, int* __restrict__ dst, int* __restrict__ dst_ptr,
+                                                                     int* __restrict__ src_pos, int* __restrict__ src_ptr, float* __restrict__ fbar) {
+  extern __shared__ int sh[];
+  int* cd = sh;            // [N + 1] counts -> cursors (destination)
+  int* cs = sh + (N + 1);  // [N + 1] (source)
+  __shared__ int carry[2];
+  const int tid = threadIdx.x;
+  for (int i = tid; i <= N; i += SMALL_NT) { cd[i] = 0; cs[i] = 0; }
+  __syncthreads();
+  for (int e = tid; e < E; e += SMALL_NT) {
+    atomicAdd(&cd[(int)edge_index[(size_t)E + e]], 1);
+    atomicAdd(&cs[(int)edge_index[e]], 1);
+  }
+  __syncthreads();
+  // exclusive scans (one warp each, chunks of 32 with a running carry): ptr arrays to global, cursors stay in shared memory
+  if (tid < 64) {
+    int* c = tid < 32 ? cd : cs;
+    int* ptr = tid < 32 ? dst_ptr : src_ptr;
+    const int lane = tid & 31;
+    int run = 0;
+    for (int base = 0; base <= N; base += 32) {
+      const int i = base + lane;
+      const int v = i < N ? c[i] : 0;
+      int x = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+      const int excl = run + x - v;
+      if (i <= N) { ptr[i] = excl; c[i] = excl; }
+      run += __shfl_sync(0xffffffffu, x, 31);
+    }
+    (void)carry;
+  }
+  __syncthreads();
+  for (int e = tid; e < E; e += SMALL_NT) perm[atomicAdd(&cd[(int)edge_index[(size_t)E + e]], 1)] = e;
+  __syncthreads();
+  for (int i = tid; i < N; i += SMALL_NT) {  // order every destination segment by edge id (insertion sort: segments are short)
+    const int a = dst_ptr[i], b = dst_ptr[i + 1];
+    for (int p = a + 1; p < b; ++p) {
+      const int key = perm[p];
+      int q = p - 1;
+      while (q >= a && perm[q] > key) { perm[q + 1] = perm[q]; --q; }
+      perm[q + 1] = key;
+    }
+    for (int p = a; p < b; ++p) { dst[p] = i; src[p] = (int)edge_index[perm[p]]; }
+  }
+  __syncthreads();
+  for (int p = tid; p < E; p += SMALL_NT) src_pos[atomicAdd(&cs[src[p]], 1)] = p;
+  __syncthreads();
+  for (int i = tid; i < N; i += SMALL_NT) {
+    const int a = src_ptr[i], b = src_ptr[i + 1];
+    for (int p = a + 1; p < b; ++p) {
+      const int key = src_pos[p];
+      int q = p - 1;
+      while (q >= a && src_pos[q] > key) { src_pos[q + 1] = src_pos[q]; --q; }
+      src_pos[q + 1] = key;
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < N * 9; idx += SMALL_NT) {  // mean frame over the edges leaving each node
+    const int i = idx / 9, c = idx - 9 * i;
+    const int a = src_ptr[i], b = src_ptr[i + 1];
+    float acc = 0.f;
+    for (int q = a; q < b; ++q) acc += __ldg(frames + (size_t)perm[src_pos[q]] * 9 + c);
+    fbar[idx] = b > a ? acc / (float)(b - a) : 0.f;
+  }
+}
+
 // frames = [x_diff; x_cross; x_vertical] (comp/__init__.py:220-269, no node mask)
 __global__ void localize_kernel(const float* __restrict__ pos, const int64_t* __restrict__ edge_index, int E,
                                 int norm_x_diff, float* __restrict__ frames) {
@@ -95,6 +170,18 @@ int gcpnet_graph_build(const int64_t* edge_index, int64_t E64, int64_t N64, cons
     return 0;
   }
   GcpTimedScope timed(T_GRAPH_BUILD, st);
+  if (N <= SMALL_MAX_NODES && E <= SMALL_MAX_EDGES) {
+    const int bytes = 2 * (N + 1) * (int)sizeof(int);
+    static bool attr_set = false;
+    if (!attr_set) {
+      CUDA_TRY(cudaFuncSetAttribute(graph_build_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (SMALL_MAX_NODES + 1) * (int)sizeof(int)));
+      attr_set = true;
+    }
+    graph_build_small_kernel<<<1, SMALL_NT, bytes, st>>>(edge_index, E, N, frames, perm, src, dst, dst_ptr, src_pos, src_ptr, fbar);
+    gcp_note_launches(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
   char* ws = (char*)workspace;
   const size_t seg = align256((size_t)E * sizeof(int));
   int* row32 = (int*)ws; int* col32 = (int*)(ws + seg); int* iota = (int*)(ws + 2 * seg); int* srckeys = (int*)(ws + 3 * seg);
