@@ -211,6 +211,7 @@ def loss_fn(layers, w, dev_batch):
     """frames + graph views + L x forward + loss, everything on the current stream."""
     import gcpnet_b200
     b = dev_batch
+    gcpnet_b200.prepack(layers, b["h"].shape[0], b["edge_index"].shape[1])  # all layers' weight packing, on a side stream
     frames = gcpnet_b200.localize(b["pos"], b["edge_index"])
     h, chi, e, xi, pos = b["h"], b["chi"], b["e"], b["xi"], b["pos"]
     for layer in layers:

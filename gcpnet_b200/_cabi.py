@@ -65,7 +65,7 @@ class Plan(C.Structure):
 class ForwardIO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("h", "chi", "e", "xi", "frames", "pos", "out_h", "out_chi", "out_pos", "msg", "saved_edge", "saved_node",
-                 "packed")]
+                 "packed")] + [("packed_ready", C.c_int32), ("reserved", C.c_int32)]
 
 
 class BackwardIO(C.Structure):
@@ -77,7 +77,7 @@ class BackwardIO(C.Structure):
 
 EXPORTS = (
     "gcpnet_version", "gcpnet_last_error", "gcpnet_launch_count", "gcpnet_profile_enable", "gcpnet_profile_read", "gcpnet_set_option", "gcpnet_debug_stamps", "gcpnet_set_side_stream", "gcpnet_join", "gcpnet_graph_workspace_bytes", "gcpnet_graph_build",
-    "gcpnet_localize", "gcpnet_layer_plan", "gcpnet_layer_forward", "gcpnet_layer_backward",
+    "gcpnet_localize", "gcpnet_layer_plan", "gcpnet_layer_pack", "gcpnet_layer_forward", "gcpnet_layer_backward",
     "gcpnet_message_passing_forward",
 )
 
@@ -111,6 +111,8 @@ def declare(lib: C.CDLL) -> None:
     lib.gcpnet_localize.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
     lib.gcpnet_layer_plan.restype = C.c_int
     lib.gcpnet_layer_plan.argtypes = [C.POINTER(Layer), C.c_int64, C.c_int64, C.POINTER(Plan)]
+    lib.gcpnet_layer_pack.restype = C.c_int
+    lib.gcpnet_layer_pack.argtypes = [C.POINTER(Layer), C.POINTER(Plan), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     lib.gcpnet_layer_forward.restype = C.c_int
     lib.gcpnet_layer_forward.argtypes = [C.POINTER(Layer), C.POINTER(Graph), C.POINTER(Plan), C.POINTER(ForwardIO), C.c_void_p]
     lib.gcpnet_layer_backward.restype = C.c_int

@@ -390,13 +390,24 @@ static int run_edge_forward(const gcpnet_layer& l, const gcpnet_graph& g, const 
                             cudaStream_t st) {
   if (g.num_edges == 0) return 0;
   if (lp.tc.ok) {  // tensor-core path (the plan decided; workspaces are sized for it)
-    if (launch_tc_pack(lp, io.packed, st)) return 1;
+    if (!io.packed_ready && launch_tc_pack(lp, io.packed, st)) return 1;
     return launch_tc_edge_fwd(g, lp, io, io.saved_edge, st);
   }
   EdgeParams p = make_edge_params(l, g, lp.ops, lp.ef, false, io.packed);
   p.h = io.h; p.chi = io.chi; p.e = io.e; p.xi = io.xi; p.frames = io.frames;
   p.msg = io.msg; p.saved = io.saved_edge;
   return launch_edge_fwd(p, lp.ef, st);
+}
+
+int gcpnet_layer_pack(const gcpnet_layer* layer, const gcpnet_plan* plan, int64_t N, int64_t E, float* packed, void* stream) {
+  if (!layer || !plan || !packed) return fail("layer_pack: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  LayerPlan lp;
+  const std::string e = make_layer_plan(*layer, N, E, &lp, nullptr, plan->tc_edge_path != 0);
+  if (!e.empty()) return fail("layer_pack: " + e);
+  if (launch_pack(lp.ops, packed, st, lp.tc.ok)) return 1;
+  if (lp.tc.ok && E > 0 && launch_tc_pack(lp, packed, st)) return 1;
+  return 0;
 }
 
 int gcpnet_layer_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, const gcpnet_plan* plan,
@@ -410,7 +421,7 @@ int gcpnet_layer_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, c
   const std::string e = make_layer_plan(l, graph->num_nodes, graph->num_edges, &lp, nullptr, plan->tc_edge_path != 0);
   if (!e.empty()) return fail("layer_forward: " + e);
   if (graph->num_nodes <= 0) return 0;
-  if (launch_pack(lp.ops, io->packed, st, lp.tc.ok)) return 1;
+  if (!io->packed_ready && launch_pack(lp.ops, io->packed, st, lp.tc.ok)) return 1;
   if (run_edge_forward(l, *graph, lp, *io, st)) return 1;
   NodeParams p = make_node_params(l, *graph, lp.ops, lp.nf, false, io->packed);
   p.h = io->h; p.chi = io->chi; p.msg = io->msg; p.pos = io->pos;

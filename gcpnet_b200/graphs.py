@@ -22,6 +22,19 @@ from . import _lib
 from .interactions import clear_graph_cache
 
 
+_PACK_STREAM = {}
+
+
+def prepack(layers, num_nodes: int, num_edges: int) -> None:
+    """Pack the weights of all `layers` (gcpnet_b200.GCPInteractions) on a side stream at the start of a step."""
+    dev = torch.cuda.current_device()
+    st = _PACK_STREAM.get(dev)
+    if st is None and not torch.cuda.is_current_stream_capturing():
+        st = _PACK_STREAM[dev] = torch.cuda.Stream()
+    for layer in layers:
+        layer.prepack(num_nodes, num_edges, st)
+
+
 class GraphedStep:
     def __init__(self, fn: Callable[[Dict[str, torch.Tensor]], torch.Tensor], static_batch: Dict[str, torch.Tensor],
                  params: Optional[Iterable[torch.nn.Parameter]] = None, warmup: int = 3):

@@ -204,9 +204,15 @@ class _LayerFn(torch.autograd.Function):
         msg = f32(plan.msg_floats)
         saved_edge = f32(plan.saved_edge_floats) if need_grad else None
         saved_node = f32(plan.saved_node_floats) if need_grad else None
-        packed = f32(plan.packed_floats)
+        pre = mod._prepacked
+        mod._prepacked = None
+        if pre is not None and pre[0] == (N, E, training, tuple(p.data_ptr() for p in params)) and pre[1].device == dev:
+            packed, ready = pre[1], 1
+            torch.cuda.current_stream().wait_event(pre[2])  # packed on the side stream at the start of the step
+        else:
+            packed, ready = f32(plan.packed_floats), 0
         io = _cabi.ForwardIO(_ptr(h), _ptr(chi), _ptr(e), _ptr(xi), _ptr(frames), _ptr(pos), _ptr(out_h), _ptr(out_chi),
-                             _ptr(out_pos), _ptr(msg), _ptr(saved_edge), _ptr(saved_node), _ptr(packed))
+                             _ptr(out_pos), _ptr(msg), _ptr(saved_edge), _ptr(saved_node), _ptr(packed), ready, 0)
         _lib.check(lib.gcpnet_layer_forward(C.byref(layer), C.byref(gv.struct), C.byref(plan), C.byref(io), _stream()),
                    "gcpnet_layer_forward")
         if training:
@@ -332,6 +338,7 @@ class GCPInteractions(nn.Module):
             self.node_position_update_network = nn.ModuleList([GCP2Params(*spec.pos_mod[1:6])])
         self._param_list = None
         self._struct_cache = None
+        self._prepacked = None
         self.register_buffer("_rng_counter", torch.zeros(1, dtype=torch.int64), persistent=False)
         _LAYER_SERIAL[0] += 1  # distinct dropout streams per layer, reproducible under torch.manual_seed
         self._seed = (int(torch.initial_seed()) * 0x9E3779B1 + _LAYER_SERIAL[0]) & 0x7FFFFFFFFFFFFFFF
@@ -358,6 +365,31 @@ class GCPInteractions(nn.Module):
                                      rng_counter=self._rng_counter.data_ptr())
         self._struct_cache = (key, layer)
         return layer
+
+    def prepack(self, num_nodes: int, num_edges: int, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Pack this layer's weights for a (num_nodes, num_edges) batch ahead of its forward call, on `stream` (forked from
+        the current stream).  A step can call this for every layer first: the packing of layers 1..L-1 then overlaps with
+        layer 0's kernels instead of sitting on each layer's critical path.  Consumed by the next forward call; repeat after
+        every optimizer step."""
+        lib = _lib.load()
+        params = self._params_in_order()
+        if not params[0].is_cuda:
+            raise RuntimeError("gcpnet_b200: prepack needs the module on a CUDA device")
+        training = bool(self.training and self.dropout_p > 0.0)
+        layer = self._layer_struct(params, training)
+        plan = _cabi.Plan()
+        _lib.check(lib.gcpnet_layer_plan(C.byref(layer), int(num_nodes), int(num_edges), C.byref(plan)), "gcpnet_layer_plan")
+        packed = torch.empty(max(int(plan.packed_floats), 1), dtype=torch.float32, device=params[0].device)
+        cur = torch.cuda.current_stream()
+        side = stream if stream is not None else cur
+        if side is not cur:
+            side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            _lib.check(lib.gcpnet_layer_pack(C.byref(layer), C.byref(plan), int(num_nodes), int(num_edges), _ptr(packed),
+                                             side.cuda_stream), "gcpnet_layer_pack")
+            ev = torch.cuda.Event()
+            ev.record(side)
+        self._prepacked = ((int(num_nodes), int(num_edges), training, tuple(p.data_ptr() for p in params)), packed, ev)
 
     # -- forward ----------------------------------------------------------------------------
     def forward(self, node_rep, edge_rep, edge_index, frames, node_rep_regressive=None, node_mask=None, node_pos=None):

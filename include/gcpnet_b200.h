@@ -110,6 +110,8 @@ typedef struct gcpnet_forward_io {
   float* saved_edge;   /* plan.saved_edge_floats or NULL (inference) */
   float* saved_node;   /* plan.saved_node_floats or NULL (inference) */
   float* packed;       /* plan.packed_floats: written by the forward call, read by the matching backward */
+  int32_t packed_ready; /* 1: `packed` already holds this layer's packed weights (gcpnet_layer_pack): skip the pack kernels */
+  int32_t reserved;
 } gcpnet_forward_io;
 
 typedef struct gcpnet_backward_io {
@@ -156,6 +158,12 @@ int gcpnet_graph_build(const int64_t* edge_index, int64_t num_edges, int64_t num
 /* frames = localize(x, edge_index) without node mask (comp/__init__.py:220-269). */
 int gcpnet_localize(const float* pos, const int64_t* edge_index, int64_t num_edges, int norm_x_diff,
                     float* frames, void* stream);
+
+/* Pack this layer's weights into `packed` (plan.packed_floats) ahead of time -- the weights are known at the start of a
+ * step, so a caller can run all layers' packing on a side stream while the first layers compute, then pass
+ * packed_ready = 1 to gcpnet_layer_forward.  Must be repeated whenever the parameters change. */
+int gcpnet_layer_pack(const gcpnet_layer* layer, const gcpnet_plan* plan, int64_t num_nodes, int64_t num_edges, float* packed,
+                      void* stream);
 
 /* GCPInteractions.forward / its backward (gcpnet.py:1160-1262). */
 int gcpnet_layer_plan(const gcpnet_layer* layer, int64_t num_nodes, int64_t num_edges, gcpnet_plan* plan);

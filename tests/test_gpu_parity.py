@@ -396,3 +396,23 @@ def test_tensor_core_path_reruns_are_bit_identical_and_train_mode_runs():
     c = _with_tc(1, lambda: module_forward_backward(train, case, cfg, inputs))
     assert all(torch.isfinite(t).all() for t in c.values())
     assert not torch.equal(c["out_h"], a["out_h"])
+
+
+def test_prepacked_weights_give_the_same_step():
+    """layer.prepack (weights packed ahead of the forward, on a side stream) must not change anything."""
+    cfg = O.OracleConfig(node_dims=(64, 16), edge_dims=(32, 4), updating_node_positions=True)
+    case, inputs = _random_case(cfg, n=200, E=1100, seed=95)
+    params = O.random_layer_params(cfg, seed=94)
+    layer = build_module(cfg, params).eval()
+    a = module_forward_backward(layer, case, cfg, inputs)
+    side = torch.cuda.Stream()
+    layer.prepack(200, 1100, side)
+    assert layer._prepacked is not None
+    b = module_forward_backward(layer, case, cfg, inputs)
+    assert layer._prepacked is None  # consumed
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    layer.prepack(123, 77, side)     # stale sizes: ignored, the forward packs by itself
+    c = module_forward_backward(layer, case, cfg, inputs)
+    for k in a:
+        assert torch.equal(a[k], c[k]), k
