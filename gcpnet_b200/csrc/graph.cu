@@ -51,7 +51,7 @@ __global__ void mean_frame_kernel(const float* __restrict__ frames, const int* _
 // same job: counting sort by destination / by source with shared-memory cursors, then every node orders its own segment
 // by edge id (destination view) / by sorted position (source view), which reproduces the stable order of the radix sort
 // exactly -- the result does not depend on the order in which the atomics land.
-constexpr int SMALL_MAX_NODES = 12287, SMALL_MAX_EDGES = 65536, SMALL_NT = 1024;
+constexpr int SMALL_MAX_NODES = 12287, SMALL_MAX_EDGES = 16384, SMALL_NT = 1024;  // beyond that the radix-sort pipeline wins (measured)
 __global__ void __launch_bounds__(SMALL_NT) graph_build_small_kernel(const int64_t* __restrict__ edge_index, int E, int N,
                                                                      const float* __restrict__ frames, int* __restrict__ perm,
                                                                      int* __restrict__ src, int* __restrict__ dst, int* __restrict__ dst_ptr,
