@@ -168,12 +168,13 @@ inline TcPlan make_tc_plan(const gcpnet_layer& l, long long N, long long E) {
   // ---- saved activations: per tile, per GCP k < L-1: S image (s/4 slabs) + V image (3 planes)
   p.s_img = (s / 4) * SLAB; p.v_img = 3 * PLANE;
   p.saved_tile_stride = (long long)(L - 1) * (p.s_img + p.v_img);
-  // tile height: 128 rows, or the smallest multiple of 8 (>= 32) that still gives one tile per SM on small graphs (the
-  // per-tile latency chain does not depend on the row count, the row-proportional stages -- weight-gradient products,
-  // TMEM / shared-memory traffic -- shrink with it)
+  // tile height: at most 128 rows, chosen so that the persistent CTAs (one per SM) all run the same number of tiles: w =
+  // waves at full height, rows = E / (148 w) rounded up to 8 (>= 32).  The per-tile latency chain does not depend on the
+  // row count; the row-proportional stages (weight-gradient products, TMEM / shared-memory traffic) shrink with it.
   int rows = TE;
-  if (E < 148LL * TE) {
-    rows = rup((int)((E + 147) / 148), 8);
+  if (E > 0) {
+    const long long t128 = (E + TE - 1) / TE, w = (t128 + 147) / 148;
+    rows = rup((int)((E + 148 * w - 1) / (148 * w)), 8);
     if (rows < 32) rows = 32;
     if (rows > TE) rows = TE;
   }
