@@ -709,15 +709,16 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_c
                          ::"r"(smem_addr(Z)), "l"(sp), "r"((uint32_t)p.s_img * 4u), "r"(zbar) : "memory");
           }
         }
-        mbar_wait(ldz_bar, ldz_n & 1u);
+        mbar_wait(ldz_bar, ldz_n & 1u);  // prefetched one GCP ahead: normally complete
         ++ldz_n;
-        mbar_wait(ld_bar, ld_n & 1u);
-        ++ld_n;
         __syncwarp();
-        for (int cc = 4 * w.part; cc < p.s; cc += 4 * CS) {
+        for (int cc = 4 * w.part; cc < p.s; cc += 4 * CS) {  // ... so its lo split overlaps with the V image still in flight
           const float4 v = get4(Z, w.r, cc);
           tmem_st4(w.tl + (uint32_t)(p.ZLO + cc), lo_part(v.x), lo_part(v.y), lo_part(v.z), lo_part(v.w));
         }
+        mbar_wait(ld_bar, ld_n & 1u);
+        ++ld_n;
+        __syncwarp();
         for (int gi = w.part; gi < (PW >> 2); gi += CS)
 #pragma unroll
           for (int x = 0; x < 3; ++x) {
