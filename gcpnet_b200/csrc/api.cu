@@ -465,6 +465,7 @@ int gcpnet_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, 
   const int W = l.s + 3 * l.v;
   // node update backward -> direct cotangent of (h, chi) in g_h/g_chi, cotangent of the aggregate in ws_agg
   NodeParams np = make_node_params(l, g, lp.ops, lp.nb, true, io->packed);
+  np.dbg = g_tc_dbg.load(std::memory_order_relaxed);
   np.saved = const_cast<float*>(io->saved_node);
   np.g_out_h = io->g_out_h; np.g_out_chi = io->g_out_chi; np.g_out_pos = io->g_out_pos;
   np.g_x_h = io->g_h; np.g_x_chi = io->g_chi; np.g_agg = io->ws_agg;

@@ -237,6 +237,14 @@ struct TileBufs {
 };
 constexpr int LDF = 9;
 
+#if GCP_DEVICE_CODE
+// Register-fragment tensor-core MMA (m16n8k8, tf32 inputs, fp32 accumulation); used as 3xTF32 (hi*hi + lo*hi + hi*lo).
+__device__ __forceinline__ void wg_hmma(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+#endif
+
 // ------------------------------------------------------------------------------------------
 // GEMM thread map: warp = 16 rows x 16 columns of outputs, lane = (eg = lane>>2, og = lane&3),
 // thread rows {e0, e0+8}, 4 columns per 16-wide slice.
@@ -252,6 +260,16 @@ struct GemmMap {
     og = lane & 3;
     wn = warp / WE;
   }
+  // Column (inside the 16-wide slice) of accumulator element j of this thread.  Node tiles (16 rows) run their GEMMs on
+  // the register-fragment tensor-core MMA on the device (column pairs {2 og, 2 og + 1} of the two 8-column halves); the
+  // FFMA loops (edge tiles; host emulation) own columns og + 4 j (n-major weights) resp. 4 og + j (k-major weights).
+#if GCP_DEVICE_CODE
+  static constexpr bool kMma = TE <= 16;
+#else
+  static constexpr bool kMma = false;
+#endif
+  GCP_HD int col_n(int j) const { return kMma ? 2 * og + (j & 1) + 8 * (j >> 1) : og + 4 * j; }
+  GCP_HD int col_k(int j) const { return kMma ? 2 * og + (j & 1) + 8 * (j >> 1) : 4 * og + j; }
 };
 
 // acc[i][r][j] += sum_{kk<kc} xmap(X[e_r][k0+kk]) * Wc[n][kk],  n = 16*(wn + WN*i) + og + 4*j  (n-major weights)
@@ -261,6 +279,37 @@ GCP_HD void gemm_nmajor_chunk(float (&acc)[SL][2][4], const float* X, int ldx, i
   constexpr int WN = GemmMap<TE, NT>::WN;
   const float* x0 = X + m.e0 * ldx + k0;
   const float* x1 = x0 + 8 * ldx;
+#if GCP_DEVICE_CODE
+  if (GemmMap<TE, NT>::kMma) {  // 3xTF32 on mma.sync m16n8k8: A = X rows {e0, e0 + 8}, B = n-major weights
+    const int g = m.e0 & 7, t = m.og;
+    for (int k8 = 0; k8 < kc; k8 += 8) {  // kc is a multiple of 4: the last step may be half empty
+      const bool tail = k8 + 4 >= kc;
+      const float fa[4] = {xmap(x0[k8 + t]), xmap(x1[k8 + t]), tail ? 0.f : xmap(x0[k8 + t + 4]), tail ? 0.f : xmap(x1[k8 + t + 4])};
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { ah[q] = __float_as_uint(fa[q]) & 0xffffe000u; al[q] = __float_as_uint(fa[q] - __uint_as_float(ah[q])); }
+#pragma unroll
+      for (int i = 0; i < SL; ++i) {
+        const int sl = m.wn + WN * i;
+        if (sl < nslices) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const float* wp = Wc + (16 * sl + 8 * hh + g) * ldk + k8 + t;
+            const float fb0 = wp[0], fb1 = tail ? 0.f : wp[4];
+            uint32_t bh[2] = {__float_as_uint(fb0) & 0xffffe000u, __float_as_uint(fb1) & 0xffffe000u};
+            uint32_t bl[2] = {__float_as_uint(fb0 - __uint_as_float(bh[0])), __float_as_uint(fb1 - __uint_as_float(bh[1]))};
+            float c[4] = {acc[i][0][2 * hh], acc[i][0][2 * hh + 1], acc[i][1][2 * hh], acc[i][1][2 * hh + 1]};
+            wg_hmma(c, ah, bh);
+            wg_hmma(c, al, bh);
+            wg_hmma(c, ah, bl);
+            acc[i][0][2 * hh] = c[0]; acc[i][0][2 * hh + 1] = c[1]; acc[i][1][2 * hh] = c[2]; acc[i][1][2 * hh + 1] = c[3];
+          }
+        }
+      }
+    }
+    return;
+  }
+#endif
 #pragma unroll
   for (int i = 0; i < SL; ++i) {
     const int sl = m.wn + WN * i;
@@ -292,6 +341,41 @@ GCP_HD void gemm_kmajor_chunk(float (&acc)[SL][2][4], const float* X, int ldx, i
   constexpr int WN = GemmMap<TE, NT>::WN;
   const float* x0 = X + m.e0 * ldx;
   const float* x1 = x0 + 8 * ldx;
+#if GCP_DEVICE_CODE
+  if (GemmMap<TE, NT>::kMma) {  // 3xTF32 on mma.sync m16n8k8: B = k-major weights Wc[k][n]
+    const int g = m.e0 & 7, t = m.og;
+#pragma unroll
+    for (int i = 0; i < SL; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { acc[i][0][c] = 0.f; acc[i][1][c] = 0.f; }
+    for (int k8 = 0; k8 < K; k8 += 8) {  // K is a multiple of 4; the last half step reads zero-padded rows / columns
+      const bool tail = k8 + 4 >= K;
+      const float fa[4] = {x0[k8 + t], x1[k8 + t], tail ? 0.f : x0[k8 + t + 4], tail ? 0.f : x1[k8 + t + 4]};
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { ah[q] = __float_as_uint(fa[q]) & 0xffffe000u; al[q] = __float_as_uint(fa[q] - __uint_as_float(ah[q])); }
+#pragma unroll
+      for (int i = 0; i < SL; ++i) {
+        const int sl = m.wn + WN * i;
+        if (sl < nslices) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const float* wp = Wc + (k8 + t) * ldw + 16 * sl + 8 * hh + g;
+            const float fb0 = wp[0], fb1 = tail ? 0.f : wp[4 * ldw];
+            uint32_t bh[2] = {__float_as_uint(fb0) & 0xffffe000u, __float_as_uint(fb1) & 0xffffe000u};
+            uint32_t bl[2] = {__float_as_uint(fb0 - __uint_as_float(bh[0])), __float_as_uint(fb1 - __uint_as_float(bh[1]))};
+            float c[4] = {acc[i][0][2 * hh], acc[i][0][2 * hh + 1], acc[i][1][2 * hh], acc[i][1][2 * hh + 1]};
+            wg_hmma(c, ah, bh);
+            wg_hmma(c, al, bh);
+            wg_hmma(c, ah, bl);
+            acc[i][0][2 * hh] = c[0]; acc[i][0][2 * hh + 1] = c[1]; acc[i][1][2 * hh] = c[2]; acc[i][1][2 * hh + 1] = c[3];
+          }
+        }
+      }
+    }
+    return;
+  }
+#endif
 #pragma unroll
   for (int i = 0; i < SL; ++i) {
     const int sl = m.wn + WN * i;
@@ -329,10 +413,6 @@ struct XAct { int a; float slope; GCP_HD float operator()(float x) const { retur
 // Device version: the products run on the register-fragment tensor-core MMA (mma.sync m16n8k8, tf32 inputs, fp32
 // accumulation) as 3xTF32 (hi*hi + lo*hi + hi*lo, split in registers): the reduction index is the tile ROW, so the
 // A / B fragments are read straight out of the row-major tiles.  One warp per 16 (j) x 8 (i) block of P.
-__device__ __forceinline__ void wg_hmma(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
 template <int TE, int NT, int JW, int IW, class FMap>
 __device__ __forceinline__ void tile_wgrad_ffma(const float* G, int ldg, int J, const float* Zin, int ldz, int I,
                                                 float* P, float* Pb, bool accumulate, FMap fmap, int tid);
@@ -463,6 +543,13 @@ GCP_HD void tile_load_rows(float* dst, int ldd, const float* src, int len, RowId
     const long long r = rowidx(e);
     const float* sp = src + (size_t)(r < 0 ? 0 : r) * len;
     float* dp = dst + e * ldd;
+#if GCP_DEVICE_CODE
+    if ((((unsigned)len | (unsigned)ldd) & 3u) == 0 && ((((size_t)src) | ((size_t)dst)) & 15u) == 0) {  // 16-byte path
+      for (int f = 4 * lane; f < len; f += 128)
+        *reinterpret_cast<float4*>(dp + f) = r >= 0 ? __ldg(reinterpret_cast<const float4*>(sp + f)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+#endif
     for (int f = lane; f < len; f += 32) dp[f] = r >= 0 ? GCP_LDG(sp + f) : 0.f;
   }
 }
@@ -575,7 +662,7 @@ GCP_HDN const float* gcp2_fwd_tile(const GcpOp& op, const TileBufs& b, WPipe& wp
         for (int i = 0; i < SL; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int n = 16 * (m.wn + GemmMap<TE, NT>::WN * i) + m.og + 4 * j;
+            const int n = 16 * (m.wn + GemmMap<TE, NT>::WN * i) + m.col_n(j);
             acc[i][0][j] = acc[i][1][j] = (n < W.NP) ? bias[n] : 0.f;
           }
       }
@@ -585,7 +672,7 @@ GCP_HDN const float* gcp2_fwd_tile(const GcpOp& op, const TileBufs& b, WPipe& wp
         for (int i = 0; i < SL; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int n = 16 * (m.wn + GemmMap<TE, NT>::WN * i) + m.og + 4 * j;
+            const int n = 16 * (m.wn + GemmMap<TE, NT>::WN * i) + m.col_n(j);
             if (n < op.so) { T[m.e0 * ldt + n] = acc[i][0][j]; T[(m.e0 + 8) * ldt + n] = acc[i][1][j]; }
           }
       }
@@ -605,7 +692,7 @@ GCP_HDN const float* gcp2_fwd_tile(const GcpOp& op, const TileBufs& b, WPipe& wp
         const float* bias = wc + W.NP * W.ldk;
         for (int i = 0; i < SL; ++i)
           for (int j = 0; j < 4; ++j) {
-            const int n = 16 * (m.wn + GemmMap<TE, NT>::WN * i) + m.og + 4 * j;
+            const int n = 16 * (m.wn + GemmMap<TE, NT>::WN * i) + m.col_n(j);
             acc[i][0][j] = acc[i][1][j] = (n < W.NP) ? bias[n] : 0.f;
           }
       }
@@ -613,7 +700,7 @@ GCP_HDN const float* gcp2_fwd_tile(const GcpOp& op, const TileBufs& b, WPipe& wp
       if (c == W.nWS - 1) {
         for (int i = 0; i < SL; ++i)
           for (int j = 0; j < 4; ++j) {
-            const int n = 16 * (m.wn + GemmMap<TE, NT>::WN * i) + m.og + 4 * j;
+            const int n = 16 * (m.wn + GemmMap<TE, NT>::WN * i) + m.col_n(j);
             if (n < op.so) { T[m.e0 * ldt + n] = acc[i][0][j]; T[(m.e0 + 8) * ldt + n] = acc[i][1][j]; }
           }
       }
@@ -752,7 +839,7 @@ GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g,
     for (int r = 0; r < 2; ++r)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const int n = 16 * (m.wn + GemmMap<TE, NT>::WN * i) + 4 * m.og + c;
+        const int n = 16 * (m.wn + GemmMap<TE, NT>::WN * i) + m.col_k(c);
         const int e = m.e0 + 8 * r;
         if (n < op.so) {
           const float t = T[e * ldt + n];
@@ -777,7 +864,7 @@ GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g,
       for (int r = 0; r < 2; ++r)
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-          const int il = 16 * (m.wn + GemmMap<TE, NT>::WN * i) + 4 * m.og + cc;
+          const int il = 16 * (m.wn + GemmMap<TE, NT>::WN * i) + m.col_k(cc);
           const int col = c * W.kc + il;
           const int e = m.e0 + 8 * r;
           if (il < W.kc && col < K) {

@@ -51,6 +51,7 @@ struct NodeParams {
   NodeSmem sm;
   GcpOp ff0, ff1, pu;
   WSeq seq;
+  long long* dbg;                // optional clock64 stamps of CTA 0 (development aid), entries [320 + i]
 };
 
 // counter-based uniform in [0,1): splitmix64 of (seed, counter, element)
@@ -66,11 +67,46 @@ GCP_HD float rng_uniform(unsigned long long seed, unsigned long long ctr, unsign
 // RED layout: [TE][PARTS][4] floats
 constexpr int RED_W = 6;
 
+#if GCP_DEVICE_CODE
+template <int PARTS>
+__device__ __forceinline__ float part_sum(float x) {  // butterfly over PARTS neighbouring lanes: same bits in every lane
+#pragma unroll
+  for (int o = PARTS / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+#endif
+
 // GCPLayerNorm forward, in place on (S, V) (comp/__init__.py:138-167).  3 phases.
 template <int TE, int NT>
 GCP_HDN_NOINLINE void tile_layernorm_fwd(float* S, int lds, float* V, int ldv, int s, int v, const float* w, const float* bb,
                                 float ln_eps, float vn_eps, float* RED) {
   constexpr int PARTS = NT / TE;
+#if GCP_DEVICE_CODE
+  // Device: the PARTS threads of a row are neighbouring lanes of one warp, row statistics by shuffles (one barrier).
+  static_assert(PARTS <= 32 && (PARTS & (PARTS - 1)) == 0, "row parts must tile a warp");
+  {
+    const int tid = (int)threadIdx.x, e = tid / PARTS, part = tid % PARTS;
+    float* sp = S + e * lds;
+    float* vp = V + e * ldv;
+    float sum = 0.f, m = 0.f;
+    for (int j = part; j < s; j += PARTS) sum += sp[j];
+    for (int c = part; c < v; c += PARTS) {
+      const float n2 = fmaf(vp[3 * c], vp[3 * c], fmaf(vp[3 * c + 1], vp[3 * c + 1], vp[3 * c + 2] * vp[3 * c + 2]));
+      m += n2 > vn_eps ? n2 : vn_eps;
+    }
+    sum = part_sum<PARTS>(sum); m = part_sum<PARTS>(m);
+    const float mean = sum / (float)s;
+    float var = 0.f;
+    for (int j = part; j < s; j += PARTS) { const float d = sp[j] - mean; var = fmaf(d, d, var); }
+    var = part_sum<PARTS>(var);
+    const float rstd = 1.f / sqrtf(var / (float)s + ln_eps);
+    for (int j = part; j < s; j += PARTS) sp[j] = fmaf((sp[j] - mean) * rstd, GCP_LDG(w + j), GCP_LDG(bb + j));
+    const float inv = 1.f / sqrtf(m / (float)v);
+    for (int c = part; c < 3 * v; c += PARTS) vp[c] *= inv;
+    __syncthreads();
+    return;
+  }
+#endif
   GCP_PHASE_BEGIN(NT)
   const int e = tid % TE, part = tid / TE;
   const float* sp = S + e * lds;
@@ -118,6 +154,66 @@ GCP_HDN_NOINLINE void tile_layernorm_bwd(const float* S, int lds, const float* V
                                 int s, int v, const float* w, float ln_eps, float vn_eps, float* RED,
                                 float* pw, float* pb, bool accumulate) {
   constexpr int PARTS = NT / TE;
+#if GCP_DEVICE_CODE
+  {
+    const int tid = (int)threadIdx.x, e = tid / PARTS, part = tid % PARTS;
+    const float* sp = S + e * lds;
+    const float* vp = V + e * ldv;
+    float* gp = GS + e * ldgs;
+    float* gv = GV + e * ldgv;
+    float sum = 0.f, m = 0.f, dot = 0.f;
+    for (int j = part; j < s; j += PARTS) sum += sp[j];
+    for (int c = part; c < v; c += PARTS) {
+      const float n2 = fmaf(vp[3 * c], vp[3 * c], fmaf(vp[3 * c + 1], vp[3 * c + 1], vp[3 * c + 2] * vp[3 * c + 2]));
+      m += n2 > vn_eps ? n2 : vn_eps;
+      dot = fmaf(gv[3 * c], vp[3 * c], fmaf(gv[3 * c + 1], vp[3 * c + 1], fmaf(gv[3 * c + 2], vp[3 * c + 2], dot)));
+    }
+    sum = part_sum<PARTS>(sum); m = part_sum<PARTS>(m); dot = part_sum<PARTS>(dot);
+    const float mean = sum / (float)s;
+    float var = 0.f;
+    for (int j = part; j < s; j += PARTS) { const float d = sp[j] - mean; var = fmaf(d, d, var); }
+    var = part_sum<PARTS>(var);
+    const float rstd = 1.f / sqrtf(var / (float)s + ln_eps);
+    if (part == 0) { RED[2 * e] = mean; RED[2 * e + 1] = rstd; }
+    // vectors: y = V / r, r = sqrt(mean_c max(|V_c|^2, eps))   (row-local, in place)
+    {
+      const float rr = sqrtf(m / (float)v);
+      const float coef = dot / ((float)v * rr * rr * rr);
+      for (int c = part; c < v; c += PARTS) {
+        const float n2 = fmaf(vp[3 * c], vp[3 * c], fmaf(vp[3 * c + 1], vp[3 * c + 1], vp[3 * c + 2] * vp[3 * c + 2]));
+        const float ind = n2 > vn_eps ? 1.f : 0.f;
+#pragma unroll
+        for (int x = 0; x < 3; ++x) gv[3 * c + x] = gv[3 * c + x] / rr - coef * ind * vp[3 * c + x];
+      }
+    }
+    float m1 = 0.f, m2 = 0.f;
+    for (int j = part; j < s; j += PARTS) {
+      const float gxh = gp[j] * GCP_LDG(w + j);
+      m1 += gxh; m2 = fmaf(gxh, (sp[j] - mean) * rstd, m2);
+    }
+    m1 = part_sum<PARTS>(m1) / (float)s; m2 = part_sum<PARTS>(m2) / (float)s;
+    __syncthreads();
+    // scalar_norm.weight / .bias gradients: thread per column, fixed row order (reads GS before it is replaced)
+    for (int j = tid; j < s; j += NT) {
+      float gw = 0.f, gb = 0.f;
+#pragma unroll 4
+      for (int r = 0; r < TE; ++r) {
+        const float gy = GS[r * ldgs + j];
+        gw = fmaf(gy, (S[r * lds + j] - RED[2 * r]) * RED[2 * r + 1], gw);
+        gb += gy;
+      }
+      pw[j] = (accumulate ? pw[j] : 0.f) + gw;
+      pb[j] = (accumulate ? pb[j] : 0.f) + gb;
+    }
+    __syncthreads();
+    for (int j = part; j < s; j += PARTS) {
+      const float xhat = (sp[j] - mean) * rstd;
+      gp[j] = rstd * (gp[j] * GCP_LDG(w + j) - m1 - xhat * m2);
+    }
+    __syncthreads();
+    return;
+  }
+#endif
   GCP_PHASE_BEGIN(NT)
   const int e = tid % TE, part = tid / TE;
   const float* sp = S + e * lds;
@@ -381,6 +477,11 @@ GCP_HDN void node_fwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
   }
 }
 
+#if GCP_DEVICE_CODE
+#define GCP_NSTAMP(i) do { if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[320 + (i)] = clock64(); } while (0)
+#else
+#define GCP_NSTAMP(i) do { } while (0)
+#endif
 template <int TE, int NT, int SLF, int SLD>
 GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, float* prow, bool accumulate) {
   const NodeSmem& L = p.sm;
@@ -394,6 +495,7 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
   BwdBufs g;
   g.GU = sm + L.GU; g.ldgu = L.ldgu; g.GG = sm + L.GG; g.ldgg = L.ldgg; g.GNQ = sm + L.GNQ; g.ldnq = L.ldnq;
   g.GHD = sm + L.GHD; g.ldghd = L.ldghd;
+  GCP_NSTAMP(0);
   // load x2 (raw copy + a copy that becomes out = LN1(x2)), the output cotangents, the mean frames
   GCP_PHASE_BEGIN(NT)
   const int lane = tid & 31;
@@ -412,6 +514,7 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
     if (lane < 9) sm[L.F + e * LDF + lane] = live ? GCP_LDG(p.fbar + i * 9 + lane) : 0.f;
   }
   GCP_PHASE_END
+  GCP_NSTAMP(1);
   // ---- position update backward: only the vector output of P carries a cotangent (gcpnet.py:1129-1137,1156)
   if (p.has_pos) {
     tile_layernorm_fwd<TE, NT>(XS, L.ldxs, XV, L.ldxv, s, v, p.ln1_w, p.ln1_b, p.ln_eps, p.vn_eps, RED);
@@ -436,9 +539,11 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
     gcp2_bwd_tile_call<TE, NT, SLF, SLD>(
         p.pu, b, g, wp, 0, p.slope, prow, accumulate, false, EmitTile{GXS, ldgxs, true}, EmitTile{GXV, ldgxv, true});
   }
+  GCP_NSTAMP(2);
   // ---- LayerNorm1 backward (input x2)
   tile_layernorm_bwd<TE, NT>(X2S, L.ldx2s, X2V, L.ldx2v, GXS, ldgxs, GXV, ldgxv, s, v, p.ln1_w, p.ln_eps, p.vn_eps, RED,
                              prow + p.o_ln1w, prow + p.o_ln1b, accumulate);
+  GCP_NSTAMP(3);
   // ---- x2 = x1n + Dropout1(f): cotangent of f, reload x1 (raw copy + copy that becomes x1n), FF inputs
   const TileBufs b1 = node_bufs(p, sm, 1);
   const TileBufs b0 = node_bufs(p, sm, 0);
@@ -465,12 +570,14 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
   tile_load_rows<TE, NT>(b1.T, b1.ldt, p.saved + p.sv.T1, s, rr, tid);
   tile_load_rows<TE, NT>(b1.SG, b1.ldsg, p.saved + p.sv.SG1, v, rr, tid);
   GCP_PHASE_END
+  GCP_NSTAMP(4);
   tile_layernorm_fwd<TE, NT>(XS, L.ldxs, XV, L.ldxv, s, v, p.ln0_w, p.ln0_b, p.ln_eps, p.vn_eps, RED);
   GCP_PHASE_BEGIN(NT)
   const int lane = tid & 31;
   for (int e = tid >> 5; e < TE; e += NT / 32)
     for (int j = lane; j < hs; j += 32) b1.Z[e * b1.ldz + j] = act_fwd(p.ff0.act_s, b0.T[e * b0.ldt + j], p.slope);
   GCP_PHASE_END
+  GCP_NSTAMP(5);
   // ---- FF1 backward: cotangents (GS1, GV1) -> cotangents of FF0's outputs (GS0, GV0)
   {
     g.GS = GS1; g.ldgs = L.ldgs1; g.GV = GV1; g.ldgv = L.ldgv1;
@@ -478,15 +585,18 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
     gcp2_bwd_tile_call<TE, NT, SLF, SLD>(
         p.ff1, b1, g, wp, 0, p.slope, prow, accumulate, false, EmitTile{GS0, ldgs0, false}, EmitTile{GV0, ldgv0, false});
   }
+  GCP_NSTAMP(6);
   // ---- FF0 backward: cotangents (GS0, GV0) -> accumulated into the cotangent of x1n
   {
     g.GS = GS0; g.ldgs = L.ldgs0; g.GV = GV0; g.ldgv = L.ldgv0;
     gcp2_bwd_tile_call<TE, NT, SLF, SLD>(
         p.ff0, b0, g, wp, 0, p.slope, prow, accumulate, false, EmitTile{GXS, ldgxs, true}, EmitTile{GXV, ldgxv, true});
   }
+  GCP_NSTAMP(7);
   // ---- LayerNorm0 backward (input x1, kept raw in X2S/X2V)
   tile_layernorm_bwd<TE, NT>(X2S, L.ldx2s, X2V, L.ldx2v, GXS, ldgxs, GXV, ldgxv, s, v, p.ln0_w, p.ln_eps, p.vn_eps, RED,
                              prow + p.o_ln0w, prow + p.o_ln0b, accumulate);
+  GCP_NSTAMP(8);
   // ---- x1 = x + Dropout0(m): direct cotangent of the layer input, cotangent of the aggregate
   GCP_PHASE_BEGIN(NT)
   const int lane = tid & 31;
@@ -501,6 +611,7 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
     }
   }
   GCP_PHASE_END
+  GCP_NSTAMP(9);
 }
 
 // host-side planning -------------------------------------------------------------------------

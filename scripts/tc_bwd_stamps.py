@@ -33,3 +33,6 @@ bn = ["sync", "load+lo", "recompute", "epi1+sync", "issue_B3", "wgrad_tg", "wait
 for k in range(7, -1, -1):
     r = st[12 + k]
     print(f"bwd GCP{k}: " + " ".join(f"{n}={int(r[i+1]-r[i])}" for i, n in enumerate(bn[:11])) + f" | total {int(r[11]-r[0])}")
+nn = ["load", "pos_bwd", "ln1_bwd", "reload", "ln0_fwd+act", "ff1_bwd", "ff0_bwd", "ln0_bwd", "store"]
+r = stamps.cpu()[320:330]
+print("node_bwd: " + " ".join(f"{n}={int(r[i+1]-r[i])}" for i, n in enumerate(nn)) + f" | total {int(r[9]-r[0])}")
