@@ -17,7 +17,7 @@ constexpr int SMEM_LIMIT_BYTES = 227 * 1024;
 constexpr int NUM_SMS = 148;                 // B200
 constexpr int EDGE_CAP_FLOATS = 8192;        // largest weight chunk of the edge kernels (32 KB ring slot)
 constexpr int NODE_CAP_FLOATS = 16384;       // node kernels: wide feed-forward layers (64 KB ring slot)
-constexpr int NODE_TE = 16, NODE_NT = 256;   // 16 threads per node
+constexpr int NODE_TE = 16, NODE_NT = 512;   // 32 threads per node
 constexpr int EDGE_SLD = 2, NODE_SLD = 2;
 
 inline GcpOp to_op(const gcpnet_gcp2& d, int grad_base) {
