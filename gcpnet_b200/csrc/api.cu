@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(NT, 1) node_bwd_kernel(const __grid_constant__
   const int mine = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   if (mine == 0) return;
   WPipe wp = node_pipe(p, smem, mine);
+  if (p.dbg != nullptr && blockIdx.x == 0) wp.dbg = p.dbg + 336;
   wpipe_start<NT>(wp);
   float* prow = p.partial + (size_t)blockIdx.x * p.partial_stride;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)

@@ -160,6 +160,7 @@ struct WPipe {  // CTA-uniform state of the ring
   const WSeq* seq;
   int head;   // position of the chunk the next wpipe_wait() returns
   int total;  // positions this CTA consumes over its whole life
+  long long* dbg = nullptr;  // development aid: clock64 stamps of the backward phases (thread 0 of CTA 0), 16 per call
 };
 
 #if GCP_DEVICE_CODE
@@ -775,6 +776,16 @@ GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g,
   float* wu_sm = b.WSM + op.vi * cols;      // [vo][hdp]
   constexpr int IW = (NT <= 256) ? 8 : 4;
   (void)hdp;
+  // development aid: stamps 0..8 = phase boundaries, 9..14 = inside the first scalar_out chunk
+#if GCP_DEVICE_CODE
+  int dbg_i = 0;
+#define GCP_BSTAMP() do { if (wp.dbg != nullptr && threadIdx.x == 0) wp.dbg[dbg_i] = clock64(); ++dbg_i; } while (0)
+#define GCP_BSTAMP_AT(i) do { if (wp.dbg != nullptr && threadIdx.x == 0 && c == 0) wp.dbg[i] = clock64(); } while (0)
+#else
+#define GCP_BSTAMP() do { } while (0)
+#define GCP_BSTAMP_AT(i) do { } while (0)
+#endif
+  GCP_BSTAMP();
   // ---- recompute: vector_down (S chunk; keep WdT for the final phases)
   GCP_PHASE_BEGIN(NT)
   if (refill_first) wpipe_refill(wp, wp.head - 1, tid);
@@ -782,11 +793,13 @@ GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g,
   gcp2_vec_down<TE, NT>(op, b, wdt, tid);
   for (int i = tid; i < op.vi * cols; i += NT) wdt_sm[i] = wdt[i];
   GCP_PHASE_END
+  GCP_BSTAMP();
   wp.head++;
   GCP_PHASE_BEGIN(NT)
   wpipe_refill(wp, wp.head - 1, tid);
   gcp2_norm_scalarize<TE, NT>(op, b, e3, tid);
   GCP_PHASE_END
+  GCP_BSTAMP();
   float* T = b.T; const int ldt = b.ldt;
   // ---- gate backward (G chunk): gU = gV' * sg ; gsig = sum_x gV' * U ; gg = gsig * sg * (1 - sg)
   GCP_PHASE_BEGIN(NT)
@@ -808,6 +821,7 @@ GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g,
   // zero the float4 padding columns of GG so the 4-wide reads below see zeros
   for (int o = op.vo + tid / TE; o < round_up(op.vo, 4); o += NT / TE) g.GG[e * g.ldgg + o] = 0.f;
   GCP_PHASE_END
+  GCP_BSTAMP();
   // ---- vector_out_scale / vector_up weight gradients (read ALL of T = pre-activations: own phase)
   GCP_PHASE_BEGIN(NT)
   tile_wgrad<TE, NT, 1, 4>(g.GG, g.ldgg, op.vo, T, ldt, op.so, prow + op.o_Wg, prow + op.o_bg, accumulate,
@@ -825,6 +839,7 @@ GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g,
     *dst = (accumulate ? *dst : 0.f) + s;
   }
   GCP_PHASE_END
+  GCP_BSTAMP();
   // ---- cotangent of the pre-activation: gT = gS' * act_s'(T) + act_v'(T) * (gg * Wg)   (T <- gT in place;
   //      every thread reads only the T entries it overwrites)
   GCP_PHASE_BEGIN(NT)
@@ -847,17 +862,22 @@ GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g,
         }
       }
   GCP_PHASE_END
+  GCP_BSTAMP();
   wp.head++;  // G chunk released
   // ---- scalar_out: weight gradient + data gradient gz = gT * Ws (WS chunks, k-major view)
   for (int c = 0; c < W.nWS; ++c) {
     GCP_PHASE_BEGIN(NT)
+    GCP_BSTAMP_AT(9);
     wpipe_refill(wp, wp.head - 1, tid);
     const float* wc = wpipe_wait(wp);
+    GCP_BSTAMP_AT(10);
     if (c == 0)
       tile_wgrad<TE, NT, 4, IW>(T, ldt, op.so, b.Z, b.ldz, K, prow + op.o_Ws, prow + op.o_bs, accumulate, XIdentity(), tid);
+    GCP_BSTAMP_AT(11);
     const GemmMap<TE, NT> m(tid);
     float acc[SLD][2][4];
     gemm_kmajor_chunk<TE, NT, SLD>(acc, T, ldt, round_up(op.so, 4), wc, W.ldk, W.kc >> 4, m);
+    GCP_BSTAMP_AT(12);
 #pragma unroll
     for (int i = 0; i < SLD; ++i)
 #pragma unroll
@@ -872,9 +892,12 @@ GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g,
             else g.GNQ[e * g.ldnq + (col - op.si)] = acc[i][r][cc];
           }
         }
+    GCP_BSTAMP_AT(13);
     GCP_PHASE_END
+    GCP_BSTAMP_AT(14);
     wp.head++;
   }
+  GCP_BSTAMP();
   // ---- gHD: norms, vector_up and frame scalars back to the hidden vector channels
   GCP_PHASE_BEGIN(NT)
   wpipe_refill(wp, wp.head - 1, tid);
@@ -908,6 +931,7 @@ GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g,
     g.GHD[e * g.ldghd + x * cols + kk] = acc;
   }
   GCP_PHASE_END
+  GCP_BSTAMP();
   // ---- vector_down / vector_down_frames weight gradients; vector input cotangent
   GCP_PHASE_BEGIN(NT)
   // gWdT[c][k] = sum_{e,x} gHD[e][x][k] * V[e][c][x]
@@ -942,6 +966,10 @@ GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g,
     }
   }
   GCP_PHASE_END
+  GCP_BSTAMP();
+#if GCP_DEVICE_CODE
+  if (wp.dbg != nullptr) wp.dbg += 16;
+#endif
 }
 
 // Out-of-line entry points for kernels that run each GCP ONCE per tile (node update): three inlined copies of these

@@ -16,7 +16,7 @@ layer = build_module(cfg, params).train()
 dev = "cuda"
 leaves = {k: inputs[k].to(dev).requires_grad_(True) for k in ("h", "chi", "e", "xi")}
 ei_d, fr, pos = inputs["edge_index"].to(dev), inputs["frames"].to(dev), inputs["node_pos"].to(dev)
-stamps = torch.zeros(24 * 16, dtype=torch.int64, device=dev)
+stamps = torch.zeros(32 * 16, dtype=torch.int64, device=dev)
 for it in range(3):
     if it == 2:
         lib.gcpnet_debug_stamps(stamps.data_ptr())
@@ -24,7 +24,7 @@ for it in range(3):
     (oh.sum() + ochi.sum() + opos.sum()).backward()
 torch.cuda.synchronize()
 lib.gcpnet_debug_stamps(None)
-st = stamps.cpu().view(24, 16)
+st = stamps.cpu().view(32, 16)
 fn = ["gather+sync", "issue_v", "wait_v", "epiA", "sync", "issue_s", "wait_s", "epiB"]
 for k in range(8):
     r = st[k]
@@ -36,3 +36,11 @@ for k in range(7, -1, -1):
 nn = ["load", "pos_bwd", "ln1_bwd", "reload", "ln0_fwd+act", "ff1_bwd", "ff0_bwd", "ln0_bwd", "store"]
 r = stamps.cpu()[320:330]
 print("node_bwd: " + " ".join(f"{n}={int(r[i+1]-r[i])}" for i, n in enumerate(nn)) + f" | total {int(r[9]-r[0])}")
+pn = ["vec_down", "norm_q", "gate", "wgrad_g_u", "gT", "ws_chunks(wgrad+dgrad)", "gHD", "wd_wgrad+gV"]
+for j, name in enumerate(["pos", "ff1", "ff0"]):
+    r = stamps.cpu()[336 + 16 * j: 336 + 16 * j + 9]
+    print(f"  {name}_bwd: " + " ".join(f"{n}={int(r[i+1]-r[i])}" for i, n in enumerate(pn)) + f" | total {int(r[8]-r[0])}")
+cn = ["refill+wait", "wgrad", "dgrad_gemm", "emit", "barrier"]
+for j, name in enumerate(["pos", "ff1", "ff0"]):
+    r = stamps.cpu()[336 + 16 * j + 9: 336 + 16 * j + 15]
+    print(f"  {name}_bwd chunk 0: " + " ".join(f"{n}={int(r[i+1]-r[i])}" for i, n in enumerate(cn)))
