@@ -29,10 +29,10 @@ fn = ["gather+sync", "issue_v", "wait_v", "epiA", "sync", "issue_s", "wait_s", "
 for k in range(8):
     r = st[k]
     print(f"fwd GCP{k}: " + " ".join(f"{n}={int(r[i+1]-r[i])}" for i, n in enumerate(fn)) + f" | total {int(r[8]-r[0])}")
-bn = ["sync", "load+lo", "recompute", "epi1+sync", "issue_B3", "wgrad_tg", "wait_B3", "epi3+sync", "issue_B4", "wgrad_v", "wait_B4", "epi4"]
+bn = ["sync+load+lo", "recompute", "epi1+sync", "issue_B3", "wgrad_tg", "wait_B3", "epi3+sync", "issue_B4", "wgrad_v", "wait_B4", "epi4"]
 for k in range(7, -1, -1):
     r = st[12 + k]
-    print(f"bwd GCP{k}: " + " ".join(f"{n}={int(r[i+1]-r[i])}" for i, n in enumerate(bn[:11])) + f" | total {int(r[11]-r[0])}")
+    print(f"bwd GCP{k}: " + " ".join(f"{n}={int(r[i+1]-r[i])}" for i, n in enumerate(bn)) + f" | total {int(r[11]-r[0])}")
 nn = ["load", "pos_bwd", "ln1_bwd", "reload", "ln0_fwd+act", "ff1_bwd", "ff0_bwd", "ln0_bwd", "store"]
 r = stamps.cpu()[320:330]
 print("node_bwd: " + " ".join(f"{n}={int(r[i+1]-r[i])}" for i, n in enumerate(nn)) + f" | total {int(r[9]-r[0])}")
