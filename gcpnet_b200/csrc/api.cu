@@ -14,6 +14,7 @@
 
 #include "common.h"
 #include "layer_setup.h"
+#include "node_wgrad.cuh"
 
 using namespace gcp;
 
@@ -255,6 +256,39 @@ static int launch_tc_edge_fwd(const gcpnet_graph& g, const LayerPlan& lp, const 
   if (gcp_tc_launch_node_pre(p, const_cast<float*>(p.P), const_cast<float*>(p.Q), st)) return 1;
   return gcp_tc_launch_edge_fwd(p, lp.tc.grid, st);
 }
+// weight gradients of the node GCPs' scalar_out / vector_out_scale from the rows the node backward spilled: one
+// output-parallel kernel over all nodes; OVERWRITES those regions of the flat gradient (after the partial-row reduction,
+// whose sums over the never-written regions of the partial rows are meaningless)
+static int launch_node_wgrad(const gcpnet_layer& l, const gcpnet_graph& g, const LayerPlan& lp, const float* ws_node_partial,
+                             const float* saved_node, float* g_node_params, cudaStream_t st) {
+  const long long N = g.num_nodes;
+  const NodeSpill sp = node_spill_layout(N, lp.ops, l.has_pos != 0);
+  const float* spill = ws_node_partial + (size_t)lp.nb.grid * l.n_node_params;
+  const NodeSavedLayout sv = node_saved_layout((int)N, l.s, l.v, l.ff0.so, l.ff0.vo, l.has_pos != 0, l.training != 0);
+  const GcpOp* op[3] = {&lp.ops.ff0, &lp.ops.ff1, l.has_pos ? &lp.ops.pu : nullptr};
+  const long long tsaved[3] = {sv.T0, sv.T1, sv.TP};
+  NodeWgradParams p{};
+  p.N = (int)N; p.slope = l.slope;
+  int cta = 0;
+  auto add = [&](const float* G, int ldg, int J, const float* Z, int ldz, int I, int act, float* outW, float* outb) {
+    NodeWgradJob& j = p.job[p.njobs++];
+    j.G = G; j.ldg = ldg; j.J = J; j.Z = Z; j.ldz = ldz; j.I = I; j.act = act; j.outW = outW; j.outb = outb;
+    j.JB = (J + 15) / 16; j.IG = ((I + 7) / 8 + 3) / 4; j.cta0 = cta;
+    cta += j.JB * j.IG;
+  };
+  for (int k = 0; k < 3; ++k) {
+    if (op[k] == nullptr) continue;
+    const GcpOp& o = *op[k];
+    add(spill + sp.gT[k], sp.ldg[k], o.so, spill + sp.Z[k], sp.ldz[k], gcp_k(o), ACT_NONE, g_node_params + o.o_Ws, g_node_params + o.o_bs);
+    if (o.vo > 0)
+      add(spill + sp.GG[k], sp.ldgg[k], o.vo, saved_node + tsaved[k], o.so, o.so, o.act_v, g_node_params + o.o_Wg, g_node_params + o.o_bg);
+  }
+  node_wgrad_kernel<<<cta, 256, 0, st>>>(p);
+  gcp_note_launches(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 // tensor-core edge backward + node-level finish of message GCP 0 + chain rule to the reference's parameters
 static int run_tc_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, const LayerPlan& lp, const gcpnet_backward_io& io, cudaStream_t st) {
   const tc::TcPlan& T = lp.tc;
@@ -321,6 +355,7 @@ static int run_tc_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, co
                                                                           l.n_node_params, lp.nb.grid);
     gcp_note_launches(1);
     CUDA_TRY(cudaGetLastError());
+    if (launch_node_wgrad(l, g, lp, io.ws_node_partial, io.saved_node, io.g_params + l.n_edge_params, ps)) return 1;
   }
   if (ps != st) {
     std::lock_guard<std::mutex> lock(g_side_mu);
@@ -471,6 +506,11 @@ int gcpnet_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, 
   np.g_out_h = io->g_out_h; np.g_out_chi = io->g_out_chi; np.g_out_pos = io->g_out_pos;
   np.g_x_h = io->g_h; np.g_x_chi = io->g_chi; np.g_agg = io->ws_agg;
   np.partial = io->ws_node_partial;
+  {
+    const NodeSpill sp = node_spill_layout(g.num_nodes, lp.ops, l.has_pos != 0);
+    np.spill = io->ws_node_partial + (size_t)lp.nb.grid * l.n_node_params;
+    for (int k = 0; k < 3; ++k) { np.sp_gT[k] = sp.gT[k]; np.sp_Z[k] = sp.Z[k]; np.sp_GG[k] = sp.GG[k]; }
+  }
   if (launch_node_bwd(np, lp.nb, st)) return 1;
   int edge_grid = 0;
   if (g.num_edges > 0 && lp.tc.ok) {
@@ -498,6 +538,7 @@ int gcpnet_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, 
                                                            io->ws_node_partial, l.n_node_params, lp.nb.grid);
   gcp_note_launches(1);
   CUDA_TRY(cudaGetLastError());
+  if (launch_node_wgrad(l, g, lp, io->ws_node_partial, io->saved_node, io->g_params + l.n_edge_params, st)) return 1;
   return 0;
 }
 

@@ -750,6 +750,11 @@ struct BwdBufs {
   float* GG;  int ldgg;   // [TE][ldgg]  scratch: grad wrt gate pre-activation (vo), float4-read by wgrad
   float* GNQ; int ldnq;   // [TE][ldnq]  scratch: grad wrt [norms | frame scalars] (hd+9)
   float* GHD; int ldghd;  // [TE][ldghd] scratch: grad wrt HD (same layout as HD)
+  // Optional spill of the operands of the two large weight-gradient products (scalar_out, vector_out_scale): when set,
+  // the tile stores its rows of gT [so -> 4], Z [K -> 4] and gg [vo -> 4] (dense rows, node index = sp_row0 + e) and one
+  // output-parallel kernel over ALL rows forms the products (node_wgrad.cuh) instead of a 16-row partial per CTA.
+  float* sp_gT = nullptr; float* sp_Z = nullptr; float* sp_GG = nullptr;
+  long long sp_row0 = 0; int sp_nrows = 0;
 };
 
 // Backward of one GCP2 on a tile.  On entry: b.Z[:, :si], b.V, b.F hold the forward inputs, b.T the
@@ -824,8 +829,11 @@ GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g,
   GCP_BSTAMP();
   // ---- vector_out_scale / vector_up weight gradients (read ALL of T = pre-activations: own phase)
   GCP_PHASE_BEGIN(NT)
-  tile_wgrad<TE, NT, 1, 4>(g.GG, g.ldgg, op.vo, T, ldt, op.so, prow + op.o_Wg, prow + op.o_bg, accumulate,
-                           XAct{op.act_v, slope}, tid);
+  if (g.sp_GG != nullptr)
+    tile_store_rows<TE, NT>(g.sp_GG, g.sp_row0, round_up(op.vo, 4), g.GG, g.ldgg, g.sp_nrows, tid);
+  else
+    tile_wgrad<TE, NT, 1, 4>(g.GG, g.ldgg, op.vo, T, ldt, op.so, prow + op.o_Wg, prow + op.o_bg, accumulate,
+                             XAct{op.act_v, slope}, tid);
   // gWu[o][k] = sum_{e,x} gU[e][o][x] * H[e][x][k]
   for (int item = tid; item < op.vo * op.hd; item += NT) {
     const int o = item / op.hd, k = item - o * op.hd;
@@ -871,8 +879,14 @@ GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g,
     wpipe_refill(wp, wp.head - 1, tid);
     const float* wc = wpipe_wait(wp);
     GCP_BSTAMP_AT(10);
-    if (c == 0)
-      tile_wgrad<TE, NT, 4, IW>(T, ldt, op.so, b.Z, b.ldz, K, prow + op.o_Ws, prow + op.o_bs, accumulate, XIdentity(), tid);
+    if (c == 0) {
+      if (g.sp_gT != nullptr) {
+        tile_store_rows<TE, NT>(g.sp_gT, g.sp_row0, round_up(op.so, 4), T, ldt, g.sp_nrows, tid);
+        tile_store_rows<TE, NT>(g.sp_Z, g.sp_row0, round_up(K, 4), b.Z, b.ldz, g.sp_nrows, tid);
+      } else {
+        tile_wgrad<TE, NT, 4, IW>(T, ldt, op.so, b.Z, b.ldz, K, prow + op.o_Ws, prow + op.o_bs, accumulate, XIdentity(), tid);
+      }
+    }
     GCP_BSTAMP_AT(11);
     const GemmMap<TE, NT> m(tid);
     float acc[SLD][2][4];

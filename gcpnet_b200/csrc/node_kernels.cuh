@@ -51,6 +51,8 @@ struct NodeParams {
   NodeSmem sm;
   GcpOp ff0, ff1, pu;
   WSeq seq;
+  float* spill;                  // backward: operands of the large weight-gradient products (nullptr: per-CTA partials)
+  long long sp_gT[3], sp_Z[3], sp_GG[3];   // float offsets in spill, per GCP (0: FF0, 1: FF1, 2: position update)
   long long* dbg;                // optional clock64 stamps of CTA 0 (development aid), entries [320 + i]
 };
 
@@ -495,6 +497,11 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
   BwdBufs g;
   g.GU = sm + L.GU; g.ldgu = L.ldgu; g.GG = sm + L.GG; g.ldgg = L.ldgg; g.GNQ = sm + L.GNQ; g.ldnq = L.ldnq;
   g.GHD = sm + L.GHD; g.ldghd = L.ldghd;
+  auto set_spill = [&](int which) {
+    if (p.spill == nullptr) return;
+    g.sp_gT = p.spill + p.sp_gT[which]; g.sp_Z = p.spill + p.sp_Z[which]; g.sp_GG = p.spill + p.sp_GG[which];
+    g.sp_row0 = row0; g.sp_nrows = nrows;
+  };
   GCP_NSTAMP(0);
   // load x2 (raw copy + a copy that becomes out = LN1(x2)), the output cotangents, the mean frames
   GCP_PHASE_BEGIN(NT)
@@ -536,6 +543,7 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
       }
     }
     GCP_PHASE_END
+    set_spill(2);
     gcp2_bwd_tile_call<TE, NT, SLF, SLD>(
         p.pu, b, g, wp, 0, p.slope, prow, accumulate, false, EmitTile{GXS, ldgxs, true}, EmitTile{GXV, ldgxv, true});
   }
@@ -582,6 +590,7 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
   {
     g.GS = GS1; g.ldgs = L.ldgs1; g.GV = GV1; g.ldgv = L.ldgv1;
     const int ldgs0 = L.ldgs0, ldgv0 = L.ldgv0;
+    set_spill(1);
     gcp2_bwd_tile_call<TE, NT, SLF, SLD>(
         p.ff1, b1, g, wp, 0, p.slope, prow, accumulate, false, EmitTile{GS0, ldgs0, false}, EmitTile{GV0, ldgv0, false});
   }
@@ -589,6 +598,7 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
   // ---- FF0 backward: cotangents (GS0, GV0) -> accumulated into the cotangent of x1n
   {
     g.GS = GS0; g.ldgs = L.ldgs0; g.GV = GV0; g.ldgv = L.ldgv0;
+    set_spill(0);
     gcp2_bwd_tile_call<TE, NT, SLF, SLD>(
         p.ff0, b0, g, wp, 0, p.slope, prow, accumulate, false, EmitTile{GXS, ldgxs, true}, EmitTile{GXV, ldgxv, true});
   }
