@@ -263,7 +263,7 @@ static int launch_node_wgrad(const gcpnet_layer& l, const gcpnet_graph& g, const
                              const float* saved_node, float* g_node_params, cudaStream_t st) {
   const long long N = g.num_nodes;
   const NodeSpill sp = node_spill_layout(N, lp.ops, l.has_pos != 0);
-  const float* spill = ws_node_partial + (size_t)lp.nb.grid * l.n_node_params;
+  const float* spill = ws_node_partial + (size_t)node_spill_offset(lp.nb.grid, l.n_node_params);
   const NodeSavedLayout sv = node_saved_layout((int)N, l.s, l.v, l.ff0.so, l.ff0.vo, l.has_pos != 0, l.training != 0);
   const GcpOp* op[3] = {&lp.ops.ff0, &lp.ops.ff1, l.has_pos ? &lp.ops.pu : nullptr};
   const long long tsaved[3] = {sv.T0, sv.T1, sv.TP};
@@ -508,7 +508,7 @@ int gcpnet_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, 
   np.partial = io->ws_node_partial;
   {
     const NodeSpill sp = node_spill_layout(g.num_nodes, lp.ops, l.has_pos != 0);
-    np.spill = io->ws_node_partial + (size_t)lp.nb.grid * l.n_node_params;
+    np.spill = io->ws_node_partial + (size_t)node_spill_offset(lp.nb.grid, l.n_node_params);
     for (int k = 0; k < 3; ++k) { np.sp_gT[k] = sp.gT[k]; np.sp_Z[k] = sp.Z[k]; np.sp_GG[k] = sp.GG[k]; }
   }
   if (launch_node_bwd(np, lp.nb, st)) return 1;

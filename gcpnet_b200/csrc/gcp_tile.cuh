@@ -561,6 +561,12 @@ GCP_HD void tile_store_rows(float* dst, long long row0, int len, const float* sr
   for (int e = tid >> 5; e < nrows; e += NT / 32) {
     float* dp = dst + (size_t)(row0 + e) * len;
     const float* sp = src + e * lds;
+#if GCP_DEVICE_CODE
+    if ((((unsigned)len | (unsigned)lds) & 3u) == 0 && ((((size_t)src) | ((size_t)dst)) & 15u) == 0) {  // 16-byte path
+      for (int f = 4 * lane; f < len; f += 128) *reinterpret_cast<float4*>(dp + f) = *reinterpret_cast<const float4*>(sp + f);
+      continue;
+    }
+#endif
     for (int f = lane; f < len; f += 32) dp[f] = sp[f];
   }
 }

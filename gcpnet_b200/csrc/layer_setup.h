@@ -238,6 +238,7 @@ struct LayerPlan {
 // Spill area of the node backward (behind the per-CTA partial rows in ws_node_partial): per GCP dense row matrices
 // gT [N][so -> 4], Z [N][K -> 4], gg [N][vo -> 4]  (BwdBufs::sp_*, node_wgrad.cuh).
 struct NodeSpill { long long gT[3], Z[3], GG[3], total; int ldg[3], ldz[3], ldgg[3]; };
+inline long long node_spill_offset(int grid, int n_node_params) { return ((long long)grid * n_node_params + 3) / 4 * 4; }  // 16-byte aligned rows
 inline NodeSpill node_spill_layout(long long N, const LayerOps& ops, bool has_pos) {
   NodeSpill sp{};
   const GcpOp* op[3] = {&ops.ff0, &ops.ff1, has_pos ? &ops.pu : nullptr};
@@ -301,7 +302,7 @@ inline std::string make_layer_plan(const gcpnet_layer& l, long long N, long long
     p.saved_node_floats = node_saved_layout((int)N, l.s, l.v, l.ff0.so, l.ff0.vo, l.has_pos != 0, l.training != 0).total;
     p.edge_partial_floats = (long long)p.edge_grid_bwd * l.n_edge_params;
     if (lp->tc.ok) p.edge_partial_floats = lp->tc.partial_floats;
-    p.node_partial_floats = (long long)p.node_grid_bwd * l.n_node_params + node_spill_layout(N, lp->ops, l.has_pos != 0).total;
+    p.node_partial_floats = node_spill_offset(p.node_grid_bwd, l.n_node_params) + node_spill_layout(N, lp->ops, l.has_pos != 0).total;
     p.edge_cotangent_floats = 2 * E * W;
     if (lp->tc.ok)  // [Y | A | G | Gn | node partials]
       p.edge_cotangent_floats = lp->tc.y_floats + lp->tc.a_floats + lp->tc.bproto.partial_stride + lp->tc.node_partial_stride +
