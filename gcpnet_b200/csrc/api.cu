@@ -256,6 +256,26 @@ static int launch_tc_edge_fwd(const gcpnet_graph& g, const LayerPlan& lp, const 
   if (gcp_tc_launch_node_pre(p, const_cast<float*>(p.P), const_cast<float*>(p.Q), st)) return 1;
   return gcp_tc_launch_edge_fwd(p, lp.tc.grid, st);
 }
+// fork: work that only feeds the PARAMETER gradient runs on the side stream (if the caller gave one and nobody is timing
+// kernels); returns the stream to use (st itself when there is no side stream)
+static cudaStream_t fork_side(cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(g_side_mu);
+  if (g_side == nullptr || gcp_profile_on()) return st;
+  cudaEvent_t ev = side_event();
+  if (ev == nullptr) return st;
+  if (cudaEventRecord(ev, st) != cudaSuccess || cudaStreamWaitEvent(g_side, ev, 0) != cudaSuccess) return st;
+  return g_side;
+}
+static int side_done(cudaStream_t ps, cudaStream_t st) {
+  if (ps == st) return 0;
+  std::lock_guard<std::mutex> lock(g_side_mu);
+  cudaEvent_t ev = side_event();
+  if (ev == nullptr) return fail("side stream: out of events");
+  CUDA_TRY(cudaEventRecord(ev, ps));
+  g_side_pending.push_back(ev);
+  return 0;
+}
+
 // weight gradients of the node GCPs' scalar_out / vector_out_scale from the rows the node backward spilled: one
 // output-parallel kernel over all nodes; OVERWRITES those regions of the flat gradient (after the partial-row reduction,
 // whose sums over the never-written regions of the partial rows are meaningless)
@@ -319,17 +339,7 @@ static int run_tc_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, co
     if (gcp_tc_launch_post(pp, 1, st)) return 1;   // per-node sums of the per-edge cotangents
   }
   // fork: everything that only feeds the PARAMETER gradient runs on the side stream (if the caller gave one)
-  cudaStream_t ps = st;
-  cudaEvent_t ev_fork = nullptr, ev_done = nullptr;
-  {
-    std::lock_guard<std::mutex> lock(g_side_mu);
-    if (g_side != nullptr && !gcp_profile_on()) { ev_fork = side_event(); ev_done = side_event(); }
-    if (ev_fork && ev_done) {
-      ps = g_side;
-      CUDA_TRY(cudaEventRecord(ev_fork, st));
-      CUDA_TRY(cudaStreamWaitEvent(ps, ev_fork, 0));
-    }
-  }
+  const cudaStream_t ps = fork_side(st);
   {
     GcpTimedScope timed(T_COT_REDUCE, st);
     if (gcp_tc_launch_post(pp, 2, st)) return 1;   // dh, dchi: the next layer's backward waits for these
@@ -351,18 +361,8 @@ static int run_tc_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, co
     GcpTimedScope timed(T_PARTIAL_REDUCE, ps);
     if (gcp_tc_launch_finalize(io.ws_edge_partial, T.grid, T.bproto.partial_stride, G, npart, T.node_partial_ctas, T.node_partial_stride, Gn, fp, ps))
       return 1;
-    partial_reduce_kernel<<<(l.n_node_params + 255) / 256, 256, 0, ps>>>(io.g_params + l.n_edge_params, nullptr, 0, 0, io.ws_node_partial,
-                                                                          l.n_node_params, lp.nb.grid);
-    gcp_note_launches(1);
-    CUDA_TRY(cudaGetLastError());
-    if (launch_node_wgrad(l, g, lp, io.ws_node_partial, io.saved_node, io.g_params + l.n_edge_params, ps)) return 1;
   }
-  if (ps != st) {
-    std::lock_guard<std::mutex> lock(g_side_mu);
-    CUDA_TRY(cudaEventRecord(ev_done, ps));
-    g_side_pending.push_back(ev_done);
-  }
-  return 0;
+  return side_done(ps, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -514,6 +514,16 @@ int gcpnet_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, 
   if (launch_node_bwd(np, lp.nb, st)) return 1;
   int edge_grid = 0;
   if (g.num_edges > 0 && lp.tc.ok) {
+    {  // node parameter gradients: ready as soon as the node backward is done -> overlap with the edge backward
+      const cudaStream_t ps = fork_side(st);
+      GcpTimedScope timed(T_PARTIAL_REDUCE, ps);
+      partial_reduce_kernel<<<(l.n_node_params + 255) / 256, 256, 0, ps>>>(io->g_params + l.n_edge_params, nullptr, 0, 0, io->ws_node_partial,
+                                                                            l.n_node_params, lp.nb.grid);
+      gcp_note_launches(1);
+      CUDA_TRY(cudaGetLastError());
+      if (launch_node_wgrad(l, g, lp, io->ws_node_partial, io->saved_node, io->g_params + l.n_edge_params, ps)) return 1;
+      if (side_done(ps, st)) return 1;
+    }
     return run_tc_edge_backward(l, g, lp, *io, st);
   }
   if (g.num_edges > 0) {
