@@ -245,6 +245,10 @@ def run_ours(args, w):
             os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    for kv in getattr(args, "option", []):
+        name, _, val = kv.partition("=")
+        if lib.gcpnet_set_option(name.encode(), int(val)) < 0:
+            raise SystemExit(f"unknown library option {name!r}")
     layers = build_stack(w, dev)
     params = [p for p in layers.parameters()]
     flat_grad_elems = sum(p.numel() for p in params)
@@ -430,6 +434,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying one CUDA graph per step")
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=0|1",
+                    help="library switch for A/B runs (gcpnet_set_option): tc, post_fused, early_fork")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -24,6 +24,8 @@ static std::atomic<unsigned long long> g_launches{0};
 void gcp_note_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 static std::atomic<int> g_opt_tc{1};
+static std::atomic<int> g_opt_post_fused{0};   // fused per-node cotangent sums + dh/dchi kernel
+static std::atomic<int> g_opt_early_fork{1};   // node parameter-gradient work forks right after the node backward
 static std::atomic<long long*> g_tc_dbg{nullptr};
 static std::atomic<bool> g_profile{false};
 static std::mutex g_profile_mu;
@@ -229,7 +231,7 @@ static cudaEvent_t side_event() {
   return e;
 }
 int gcp_tc_launch_finalize(const float* partial, int rows, int stride, float* G, const float* npartial, int nrows, int nstride, float* Gn,
-                           const tc::TcFinalParams& fp, cudaStream_t st);                  // tc_api.cu
+                           const tc::TcFinalParams& fp, int which, cudaStream_t st);       // tc_api.cu
 int gcp_tc_launch_pack(const tc::TcPackProg& prog, cudaStream_t st);                      // tc_api.cu
 int gcp_tc_launch_edge_fwd(const tc::TcEdgeParams& p, int grid, cudaStream_t st);          // tc_api.cu
 int gcp_tc_launch_node_pre(const tc::TcEdgeParams& p, float* P, float* Q, cudaStream_t st);  // tc_api.cu
@@ -334,17 +336,20 @@ static int run_tc_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, co
   pp.h = io.h; pp.chi = io.chi; pp.blob = io.packed + lp.v2_packed_floats; pp.nt = T.proto.nt;
   pp.A = A; pp.g_h = io.g_h; pp.g_chi = io.g_chi;
   pp.npartial = npart; pp.npartial_stride = T.node_partial_stride; pp.nctas = T.node_partial_ctas;
+  // The per-node sums of the per-edge cotangents come first; then everything that only feeds the PARAMETER gradient forks
+  // to the side stream (if the caller gave one) while dh, dchi -- which the next layer's backward waits for -- finish here.
+  // (Measured at cfg2: side-stream work that overlaps the per-node sums slows the critical path; one fused sum + dh/dchi
+  // kernel is faster by itself but delays the fork, 1.4 % slower per step -- kept as option "post_fused".)
+  const bool fused = g_opt_post_fused.load(std::memory_order_relaxed) != 0;
   {
     GcpTimedScope timed(T_COT_REDUCE, st);
-    if (gcp_tc_launch_post(pp, 1, st)) return 1;   // per-node sums of the per-edge cotangents
+    if (gcp_tc_launch_post(pp, fused ? 3 : 1, st)) return 1;
   }
-  // fork: everything that only feeds the PARAMETER gradient runs on the side stream (if the caller gave one)
   const cudaStream_t ps = fork_side(st);
-  {
+  if (!fused) {
     GcpTimedScope timed(T_COT_REDUCE, st);
-    if (gcp_tc_launch_post(pp, 2, st)) return 1;   // dh, dchi: the next layer's backward waits for these
+    if (gcp_tc_launch_post(pp, 2, st)) return 1;
   }
-  if (gcp_tc_launch_post(pp, 4, ps)) return 1;
   tc::TcFinalParams fp{};
   fp.L = l.num_message_layers; fp.s = l.s; fp.v = l.v; fp.se = l.se; fp.ve = l.ve; fp.pw = T.proto.pw; fp.n_edge_params = l.n_edge_params;
   fp.G = G; fp.Gn = Gn; fp.out = io.g_params;
@@ -359,7 +364,8 @@ static int run_tc_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, co
   }
   {
     GcpTimedScope timed(T_PARTIAL_REDUCE, ps);
-    if (gcp_tc_launch_finalize(io.ws_edge_partial, T.grid, T.bproto.partial_stride, G, npart, T.node_partial_ctas, T.node_partial_stride, Gn, fp, ps))
+    if (gcp_tc_launch_post(pp, 4, ps)) return 1;
+    if (gcp_tc_launch_finalize(io.ws_edge_partial, T.grid, T.bproto.partial_stride, G, npart, T.node_partial_ctas, T.node_partial_stride, Gn, fp, 3, ps))
       return 1;
   }
   return side_done(ps, st);
@@ -394,6 +400,8 @@ int gcpnet_join(void* stream) {
 }
 int gcpnet_set_option(const char* name, int value) {
   if (name && std::string(name) == "tc") return g_opt_tc.exchange(value);
+  if (name && std::string(name) == "post_fused") return g_opt_post_fused.exchange(value);
+  if (name && std::string(name) == "early_fork") return g_opt_early_fork.exchange(value);
   return -1;
 }
 int gcpnet_profile_read(int which, double* total_ms, int64_t* launches) {
@@ -515,7 +523,7 @@ int gcpnet_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, 
   int edge_grid = 0;
   if (g.num_edges > 0 && lp.tc.ok) {
     {  // node parameter gradients: ready as soon as the node backward is done -> overlap with the edge backward
-      const cudaStream_t ps = fork_side(st);
+      const cudaStream_t ps = g_opt_early_fork.load(std::memory_order_relaxed) ? fork_side(st) : st;
       GcpTimedScope timed(T_PARTIAL_REDUCE, ps);
       partial_reduce_kernel<<<(l.n_node_params + 255) / 256, 256, 0, ps>>>(io->g_params + l.n_edge_params, nullptr, 0, 0, io->ws_node_partial,
                                                                             l.n_node_params, lp.nb.grid);

@@ -65,20 +65,30 @@ int gcp_tc_launch_edge_bwd(const tc::TcBwdParams& b, int grid, cudaStream_t st) 
 int gcp_tc_launch_post(const tc::TcPostParams& p, int which, cudaStream_t st) {
   const long long n1 = (long long)p.N * 2 * (p.pw + 96), n2 = (long long)p.N * (p.s + 3 * p.v);
   int n = 0;
-  if (which & 1) { tc::tc_post_sum_kernel<<<(int)((n1 + 255) / 256), 256, 0, st>>>(p); ++n; }
-  if (which & 2) { tc::tc_post_data_kernel<<<(int)((n2 + 255) / 256), 256, 0, st>>>(p); ++n; }
+  if ((which & 3) == 3 && p.s + 3 * p.v >= 48 && p.pw + 96 <= tc::POST_PER) {  // fused: sums in shared memory
+    tc::tc_post_fused_kernel<<<(int)((n2 + 255) / 256), 256, 0, st>>>(p); ++n;
+  } else {
+    if (which & 1) { tc::tc_post_sum_kernel<<<(int)((n1 + 255) / 256), 256, 0, st>>>(p); ++n; }
+    if (which & 2) { tc::tc_post_data_kernel<<<(int)((n2 + 255) / 256), 256, 0, st>>>(p); ++n; }
+  }
   if (which & 4) { tc::tc_post_wgrad_kernel<<<dim3((p.npartial_stride + 255) / 256, p.nctas), 256, 0, st>>>(p); ++n; }
   gcp_note_launches(n);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
+// which: 1 = reduce the per-CTA partial rows of the edge backward (needs only that kernel), 2 = reduce the node-level
+// partial rows (tc_post_wgrad_kernel) and apply the chain rule
 int gcp_tc_launch_finalize(const float* partial, int rows, int stride, float* G, const float* npartial, int nrows, int nstride, float* Gn,
-                           const tc::TcFinalParams& fp, cudaStream_t st) {
-  tc::tc_reduce_kernel<<<(stride + 255) / 256, 256, 0, st>>>(partial, rows, stride, stride, G);
-  tc::tc_reduce_kernel<<<(nstride + 255) / 256, 256, 0, st>>>(npartial, nrows, nstride, nstride, Gn);
-  tc::tc_finalize_kernel<<<(fp.n_edge_params + 255) / 256, 256, 0, st>>>(fp);
-  tc::tc_finalize_wg_kernel<<<(fp.L * fp.g[0].vo * fp.g[0].so * 32 + 255) / 256, 256, 0, st>>>(fp);
-  gcp_note_launches(4);
+                           const tc::TcFinalParams& fp, int which, cudaStream_t st) {
+  int n = 0;
+  if (which & 1) { tc::tc_reduce_kernel<<<(stride + 255) / 256, 256, 0, st>>>(partial, rows, stride, stride, G); ++n; }
+  if (which & 2) {
+    tc::tc_reduce_kernel<<<(nstride + 255) / 256, 256, 0, st>>>(npartial, nrows, nstride, nstride, Gn);
+    tc::tc_finalize_kernel<<<(fp.n_edge_params + 255) / 256, 256, 0, st>>>(fp);
+    tc::tc_finalize_wg_kernel<<<(fp.L * fp.g[0].vo * fp.g[0].so * 32 + 255) / 256, 256, 0, st>>>(fp);
+    n += 3;
+  }
+  gcp_note_launches(n);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

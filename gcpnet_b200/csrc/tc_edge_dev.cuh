@@ -1046,6 +1046,62 @@ __global__ void __launch_bounds__(256) tc_post_data_kernel(const TcPostParams p)
     p.g_chi[(size_t)i * 3 * p.v + (o - p.s)] += acc;
   }
 }
+// Fused version of the two kernels above (the layer below waits for dh / dchi): the CTA first forms the per-node sums of
+// the nodes its 256 outputs touch (shared memory + the global copy the weight-gradient kernel reads; a node shared with
+// the neighbouring CTA is summed by both, same bits), then pushes them through the node tiles.  Launch condition:
+// s + 3v >= 48 (at most POST_ROWS nodes per CTA) and pw + 96 <= POST_PER.
+constexpr int POST_ROWS = 8, POST_PER = 240;
+__global__ void __launch_bounds__(256) tc_post_fused_kernel(const TcPostParams p) {
+  __shared__ __align__(16) float As_sm[POST_ROWS][2 * POST_PER];
+  const int W = p.s + 3 * p.v, per = p.pw + 96;
+  const long long idx0 = (long long)blockIdx.x * 256;
+  const int i_first = (int)(idx0 / W);
+  const long long last = idx0 + 255 < (long long)p.N * W - 1 ? idx0 + 255 : (long long)p.N * W - 1;
+  const int nrow = (int)(last / W) - i_first + 1;
+  for (int t = threadIdx.x; t < nrow * 2 * per; t += 256) {
+    const int r = t / (2 * per), rem = t - r * 2 * per;
+    const int i = i_first + r, side = rem / per, c = rem - side * per;
+    float acc = 0.f;
+    if (side == 0) { for (int j = p.src_ptr[i]; j < p.src_ptr[i + 1]; ++j) acc += y_at(p, __ldg(p.src_pos + j), c); }
+    else { for (int q = p.dst_ptr[i]; q < p.dst_ptr[i + 1]; ++q) acc += y_at(p, q, c); }
+    As_sm[r][rem] = acc;
+    p.A[(size_t)i * 2 * per + rem] = acc;
+  }
+  __syncthreads();
+  const long long idx = idx0 + threadIdx.x;
+  if (idx >= (long long)p.N * W) return;
+  const int i = (int)(idx / W), o = (int)(idx - (long long)i * W);
+  const float* As = As_sm[i - i_first];
+  const float* Ad = As + per;
+  float acc = 0.f;
+  if (o < p.s) {
+    const float* Bs = p.blob + p.nt.ps; const float* Bd = p.blob + p.nt.pd;  // [pw][s] slab, pitch pw
+    const float* bs0 = Bs + (o >> 2) * p.pw * 4 + (o & 3);
+    const float* bd0 = Bd + (o >> 2) * p.pw * 4 + (o & 3);
+    float acc2 = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < p.pw; c += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(As + c);
+      acc = fmaf(a.x, __ldg(bs0 + 4 * c), fmaf(a.y, __ldg(bs0 + 4 * c + 4), fmaf(a.z, __ldg(bs0 + 4 * c + 8), fmaf(a.w, __ldg(bs0 + 4 * c + 12), acc))));
+    }
+#pragma unroll 4
+    for (int c = 0; c < p.pw; c += 4) {
+      const float4 d = *reinterpret_cast<const float4*>(Ad + c);  // per % 4 == 0 (pw = sop + 16)
+      acc2 = fmaf(d.x, __ldg(bd0 + 4 * c), fmaf(d.y, __ldg(bd0 + 4 * c + 4), fmaf(d.z, __ldg(bd0 + 4 * c + 8), fmaf(d.w, __ldg(bd0 + 4 * c + 12), acc2))));
+    }
+    acc += acc2;
+    p.g_h[(size_t)i * p.s + o] += acc;
+  } else {
+    const int ch = (o - p.s) / 3, x = (o - p.s) - 3 * ch;
+    const float* Bs = p.blob + p.nt.qs; const float* Bd = p.blob + p.nt.qd;  // [32][v8] slab, pitch 32
+#pragma unroll 4
+    for (int c = 0; c < VN; ++c) {
+      const int off = ((ch >> 2) * VN + c) * 4 + (ch & 3);
+      acc = fmaf(As[p.pw + 32 * x + c], __ldg(Bs + off), fmaf(Ad[p.pw + 32 * x + c], __ldg(Bd + off), acc));
+    }
+    p.g_chi[(size_t)i * 3 * p.v + (o - p.s)] += acc;
+  }
+}
 // partial rows (one per node chunk = blockIdx.y) [src: pw x s | dst: pw x s | src: 32 x 16 | dst: 32 x 16]; thread = one output
 __global__ void __launch_bounds__(256) tc_post_wgrad_kernel(const TcPostParams p) {
   const int per = p.pw + 96, chunk = (p.N + gridDim.y - 1) / gridDim.y;

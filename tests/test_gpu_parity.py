@@ -416,3 +416,33 @@ def test_prepacked_weights_give_the_same_step():
     c = module_forward_backward(layer, case, cfg, inputs)
     for k in a:
         assert torch.equal(a[k], c[k]), k
+
+
+def test_library_switches_give_the_same_gradients():
+    """`gcpnet_set_option` switches of the backward's node-level finish (fused per-node cotangent sums + dh/dchi kernel;
+    early fork of the node parameter-gradient work): every combination within tolerance of the oracle and bit-identical
+    outputs / input gradients between combinations (the switches only re-order independent kernels)."""
+    from gcpnet_b200 import _lib
+    lib = _lib.load()
+    cfg = O.OracleConfig(node_dims=(64, 16), edge_dims=(32, 4), updating_node_positions=True, scalar_nonlinearity="silu")
+    case, inputs = _random_case(cfg, n=257, E=1500, seed=71)
+    params = O.random_layer_params(cfg, seed=70)
+    want = oracle_forward_backward(case, cfg, params, inputs)
+    exact = oracle_forward_backward(case, cfg, params, inputs, dtype=torch.float64)
+    layer = build_module(cfg, params).eval()
+    names = [k for k, _ in layer.named_parameters()]
+    res = {}
+    for fused in (0, 1):
+        for early in (0, 1):
+            prev = (lib.gcpnet_set_option(b"post_fused", fused), lib.gcpnet_set_option(b"early_fork", early))
+            try:
+                res[fused, early] = module_forward_backward(layer, case, cfg, inputs)
+            finally:
+                lib.gcpnet_set_option(b"post_fused", prev[0]); lib.gcpnet_set_option(b"early_fork", prev[1])
+            _compare(res[fused, early], want, names, exact=exact)
+    base = res[0, 0]
+    for key, r in res.items():
+        for k in ("out_h", "out_chi", "out_pos", "grad_h", "grad_chi", "grad_e", "grad_xi"):
+            if k in base:
+                assert torch.equal(r[k], base[k]), (key, k)
+    assert lib.gcpnet_set_option(b"no_such_option", 1) == -1
