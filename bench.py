@@ -133,8 +133,10 @@ def cpu_steps(w, steps, warmup, threads=None):
     """Times `steps` full steps of workload `w` with the oracle (torch CPU, all host threads).
     Returns (seconds per step, edge-layers per step, threads)."""
     from oracle import gcp_oracle as O
-    if threads:
-        torch.set_num_threads(threads)
+    # all the host cores this process may use -- torchrun exports OMP_NUM_THREADS=1, which would cripple the CPU arm
+    if not threads:
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(threads)
     cfg = oracle_cfg(w)
     L = w["layers"]
     params = [{k: t.requires_grad_(True) for k, t in O.random_layer_params(cfg, seed=10 + i).items()} for i in range(L)]
@@ -177,7 +179,7 @@ def run_reference(args, w):
     sec, units, threads = cpu_steps(w, steps, warm)
     val = units / sec
     s, v = w["node_dims"]
-    print(json.dumps({
+    _emit({
         "impl": "reference", "metric": "edges/s (fused GCP msg+aggregate fwd+bwd)", "value": val, "unit": "edge-layers/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -188,7 +190,7 @@ def run_reference(args, w):
                                    f"fp32 with {threads} threads; the Python reference cannot travel to the GPU box"},
         "e2e": {"value": val, "unit": "edge-layers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------
@@ -263,7 +265,7 @@ def run_ours(args, w):
         return d
 
     def allreduce_grads():
-        if world > 1:
+        if world > 1 and not os.environ.get("GCPNET_BENCH_SKIP_ALLREDUCE"):  # (diagnostic switch; such a run is not a bench line)
             # graph-sharded data parallelism: the only exchange is the parameter-gradient all-reduce
             flat = torch.cat([p.grad.reshape(-1) for p in params])
             dist.all_reduce(flat)
@@ -405,7 +407,7 @@ def run_ours(args, w):
                     "kernel_ms_per_step": {k: t / args.steps for k, (t, _) in kernel_ms.items()},
                     "note": "fused path is compute-bound (~350 FLOP/B, SURVEY 8d): HBM fraction reported as the "
                             "contract asks; see DESIGN.md for the FLOP-side roofline"}
-        print(json.dumps({
+        _emit({
             "metric": "edges/s (fused GCP msg+aggregate fwd+bwd)", "value": world * units * args.steps / (dev_ms * 1e-3),
             "unit": "edge-layers/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -420,12 +422,35 @@ def run_ours(args, w):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "roofline": roof_out, "cpu_baseline": cpu, "clocks": clocks, "loss": losses[-1],
-        }))
+        })
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def _protect_stdout():
+    """Rank 0 must print exactly ONE line on stdout.  Libraries write there too (NCCL prints its version banner from C
+    when NCCL_DEBUG >= VERSION), so fd 1 is pointed at stderr for the whole run and the result line goes to a private
+    duplicate of the original stdout."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
