@@ -40,6 +40,8 @@ class GraphedStep:
                  params: Optional[Iterable[torch.nn.Parameter]] = None, warmup: int = 3):
         self.fn = fn
         self.batch = static_batch
+        self._copy_stream = None
+        self._staged = False
         self.params = list(params) if params is not None else []
         lib = _lib.load()
         lib.gcpnet_profile_enable(0)  # per-kernel events are not capturable
@@ -66,9 +68,34 @@ class GraphedStep:
             if t.is_floating_point() and t.requires_grad:
                 t.grad = None
 
+    def prefetch(self, host_batch: Dict[str, torch.Tensor]) -> None:
+        """Start copying the NEXT step's inputs (pinned host tensors) into device staging buffers on a copy stream, so the
+        transfer overlaps with the step that is running; the next ``__call__()`` without arguments consumes them (one
+        device-to-device copy per tensor into the graph's static buffers)."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._stage = {k: torch.empty_like(t.detach()) for k, t in self.batch.items()}
+            self._stage_ready = torch.cuda.Event()
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record(torch.cuda.current_stream())
+        cs = self._copy_stream
+        cs.wait_event(self._stage_free)  # the previous step has drained the staging buffers
+        with torch.cuda.stream(cs):
+            for k, t in host_batch.items():
+                self._stage[k].copy_(t, non_blocking=True)
+            self._stage_ready.record(cs)
+        self._staged = True
+
     def __call__(self, new_batch: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
         if new_batch is not None:
             for k, t in new_batch.items():
                 self.batch[k].detach().copy_(t, non_blocking=True)
+        elif self._staged:
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self._stage_ready)
+            for k, t in self._stage.items():
+                self.batch[k].detach().copy_(t, non_blocking=True)
+            self._stage_free.record(cur)
+            self._staged = False
         self.graph.replay()
         return self.loss

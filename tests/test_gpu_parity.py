@@ -366,6 +366,16 @@ def test_graphed_step_replays_the_eager_step():
     assert rel_err(gh_g.cpu().numpy(), new["h"].grad.cpu().numpy()) < 1e-6
     for a, p in zip(grads_g, plist):
         assert rel_err(a.cpu().numpy(), p.grad.cpu().numpy()) < 1e-6
+    # staged inputs: pinned host tensors -> copy stream -> static buffers; two steps back to back, each with its own data
+    third = batch(73)
+    hosts = [{k: v.detach().cpu().pin_memory() for k, v in b.items()} for b in (third, new)]
+    step.prefetch(hosts[0])
+    loss_a = step().detach().clone()
+    step.prefetch(hosts[1])
+    loss_b = step().detach().clone()
+    torch.cuda.synchronize()
+    assert torch.equal(loss_b, loss_g)
+    assert rel_err(loss_a.cpu().numpy(), loss_fn(third).detach().cpu().numpy()) < 1e-6
 
 
 def test_tensor_core_path_degenerate_graphs():
