@@ -12,6 +12,7 @@ Anything the kernels do not cover raises ``NotImplementedError`` -- there is no 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from collections import OrderedDict
 from typing import Any, Optional, Tuple
 
@@ -157,7 +158,7 @@ _SIDE = {"stream": None, "keep": [], "queued": False, "enabled": True}
 def _side_stream_setup() -> None:
     """Create the side stream once (outside any CUDA-graph capture: the first backward of a process is a warm-up)."""
     if _SIDE["stream"] is None and _SIDE["enabled"] and not torch.cuda.is_current_stream_capturing():
-        st = torch.cuda.Stream()
+        st = torch.cuda.Stream(priority=int(os.environ.get("GCPNET_SIDE_PRIORITY", "0")))
         _lib.check(_lib.load().gcpnet_set_side_stream(st.cuda_stream), "gcpnet_set_side_stream")
         _SIDE["stream"] = st
 
