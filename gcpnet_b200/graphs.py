@@ -14,6 +14,7 @@ replay overwrites), ready for an optimizer step or an NCCL all-reduce after the 
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, Iterable, Optional
 
 import torch
@@ -56,7 +57,10 @@ class GraphedStep:
         self._zero_grads()
         clear_graph_cache()  # CSR views must be rebuilt inside the capture (their memory has to come from the graph's pool)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # capture stream priority (A/B aid): with -1 the critical chain's kernel nodes outrank the parameter-gradient
+        # work forked to the (default-priority) side stream when both are ready
+        cap = torch.cuda.Stream(priority=int(os.environ.get("GCPNET_MAIN_PRIORITY", "0")))
+        with torch.cuda.graph(self.graph, stream=cap):
             self.loss = fn(self.batch)
             self.loss.backward()
         clear_graph_cache()
