@@ -24,7 +24,7 @@ static std::atomic<unsigned long long> g_launches{0};
 void gcp_note_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 static std::atomic<int> g_opt_tc{1};
-static std::atomic<int> g_opt_post_fused{0};   // fused per-node cotangent sums + dh/dchi kernel
+static std::atomic<int> g_opt_post_fused{2};   // ordering of the backward's node-level finish (run_tc_edge_backward)
 static std::atomic<int> g_opt_early_fork{1};   // node parameter-gradient work forks right after the node backward
 static std::atomic<long long*> g_tc_dbg{nullptr};
 static std::atomic<bool> g_profile{false};
@@ -336,17 +336,21 @@ static int run_tc_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, co
   pp.h = io.h; pp.chi = io.chi; pp.blob = io.packed + lp.v2_packed_floats; pp.nt = T.proto.nt;
   pp.A = A; pp.g_h = io.g_h; pp.g_chi = io.g_chi;
   pp.npartial = npart; pp.npartial_stride = T.node_partial_stride; pp.nctas = T.node_partial_ctas;
-  // The per-node sums of the per-edge cotangents come first; then everything that only feeds the PARAMETER gradient forks
-  // to the side stream (if the caller gave one) while dh, dchi -- which the next layer's backward waits for -- finish here.
-  // (Measured at cfg2: side-stream work that overlaps the per-node sums slows the critical path; one fused sum + dh/dchi
-  // kernel is faster by itself but delays the fork, 1.4 % slower per step -- kept as option "post_fused".)
-  const bool fused = g_opt_post_fused.load(std::memory_order_relaxed) != 0;
+  // Node-level finish: per-node sums of the per-edge cotangents, then dh / dchi (the next layer's backward waits for
+  // these) on the caller's stream; everything that only feeds the PARAMETER gradient on the side stream (if the caller
+  // gave one).  Measured at cfg2 with the main chain on a high-priority stream (GraphedStep): mode 2 is 0.7 % faster per
+  // step than modes 0 / 1; with equal priorities side work that overlaps the sums slows the critical path and mode 0 wins.
+  // option "post_fused": 0 = sums -> fork -> dh/dchi || side work;  1 = fused sums + dh/dchi -> fork;
+  //                      2 = fork -> fused sums + dh/dchi || reduction of the edge partial rows, rest of the side work after the sums
+  const int mode = g_opt_post_fused.load(std::memory_order_relaxed);
+  cudaStream_t ps = st;
+  if (mode == 2) ps = fork_side(st);
   {
     GcpTimedScope timed(T_COT_REDUCE, st);
-    if (gcp_tc_launch_post(pp, fused ? 3 : 1, st)) return 1;
+    if (gcp_tc_launch_post(pp, mode == 0 ? 1 : 3, st)) return 1;
   }
-  const cudaStream_t ps = fork_side(st);
-  if (!fused) {
+  if (mode != 2) ps = fork_side(st);
+  if (mode == 0) {
     GcpTimedScope timed(T_COT_REDUCE, st);
     if (gcp_tc_launch_post(pp, 2, st)) return 1;
   }
@@ -364,8 +368,19 @@ static int run_tc_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, co
   }
   {
     GcpTimedScope timed(T_PARTIAL_REDUCE, ps);
+    if (mode == 2) {
+      if (gcp_tc_launch_finalize(io.ws_edge_partial, T.grid, T.bproto.partial_stride, G, npart, T.node_partial_ctas, T.node_partial_stride, Gn, fp, 1, ps))
+        return 1;
+      if (ps != st) {  // the per-node sums (main stream) feed the node-level products
+        std::lock_guard<std::mutex> lock(g_side_mu);
+        cudaEvent_t ev = side_event();
+        if (ev == nullptr) return fail("side stream: out of events");
+        CUDA_TRY(cudaEventRecord(ev, st));
+        CUDA_TRY(cudaStreamWaitEvent(ps, ev, 0));
+      }
+    }
     if (gcp_tc_launch_post(pp, 4, ps)) return 1;
-    if (gcp_tc_launch_finalize(io.ws_edge_partial, T.grid, T.bproto.partial_stride, G, npart, T.node_partial_ctas, T.node_partial_stride, Gn, fp, 3, ps))
+    if (gcp_tc_launch_finalize(io.ws_edge_partial, T.grid, T.bproto.partial_stride, G, npart, T.node_partial_ctas, T.node_partial_stride, Gn, fp, mode == 2 ? 2 : 3, ps))
       return 1;
   }
   return side_done(ps, st);

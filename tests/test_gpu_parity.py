@@ -442,7 +442,7 @@ def test_library_switches_give_the_same_gradients():
     layer = build_module(cfg, params).eval()
     names = [k for k, _ in layer.named_parameters()]
     res = {}
-    for fused in (0, 1):
+    for fused in (0, 1, 2):
         for early in (0, 1):
             prev = (lib.gcpnet_set_option(b"post_fused", fused), lib.gcpnet_set_option(b"early_fork", early))
             try:
