@@ -83,14 +83,27 @@ __global__ void __launch_bounds__(256) tc_node_pre_kernel(const float* __restric
     const int side = o / pw, c = o - side * pw;
     const float* B = blob + (side ? nt.pd : nt.ps);  // [pw][s] slab, pitch pw
     const float* hp = h + (size_t)i * s;
-    for (int j = 0; j < s; ++j) acc = fmaf(__ldg(B + ((j >> 2) * pw + c) * 4 + (j & 3)), __ldg(hp + j), acc);
+    // s % 16 == 0 on this path: 16-byte loads, four columns per step; ONE accumulator in column order (the summation
+    // order is part of the pinned numerics: ReLU units at ~0 flip with it, tests/test_gpu_parity.py)
+#pragma unroll 4
+    for (int j4 = 0; j4 < (s >> 2); ++j4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(B + (j4 * pw + c) * 4));
+      const float4 x = __ldg(reinterpret_cast<const float4*>(hp) + j4);
+      acc = fmaf(b.x, x.x, acc); acc = fmaf(b.y, x.y, acc); acc = fmaf(b.z, x.z, acc); acc = fmaf(b.w, x.w, acc);
+    }
     P[(size_t)i * 2 * pw + o] = acc;
   } else {
     const int o2 = o - 2 * pw;
     const int side = o2 / 96, x = (o2 - side * 96) / 32, c = o2 & 31;
     const float* B = blob + (side ? nt.qd : nt.qs);  // [32][v8] slab, pitch 32
     const float* cp = chi + (size_t)i * 3 * v + x;
-    for (int ch = 0; ch < v; ++ch) acc = fmaf(__ldg(B + ((ch >> 2) * 32 + c) * 4 + (ch & 3)), __ldg(cp + 3 * ch), acc);
+    int ch = 0;
+    for (; ch + 4 <= v; ch += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(B + ((ch >> 2) * 32 + c) * 4));
+      acc = fmaf(b.x, __ldg(cp + 3 * ch), acc); acc = fmaf(b.y, __ldg(cp + 3 * ch + 3), acc);
+      acc = fmaf(b.z, __ldg(cp + 3 * ch + 6), acc); acc = fmaf(b.w, __ldg(cp + 3 * ch + 9), acc);
+    }
+    for (; ch < v; ++ch) acc = fmaf(__ldg(B + ((ch >> 2) * 32 + c) * 4 + (ch & 3)), __ldg(cp + 3 * ch), acc);
     Q[(size_t)i * 192 + o2] = acc;
   }
 }
@@ -1004,16 +1017,31 @@ __device__ __forceinline__ float y_at(const TcPostParams& p, int q, int c) {
   const int c2 = c - p.pw, x = c2 >> 5, cc = c2 & 31;
   return __ldg(yp + p.y_img_g + x * GPLANE + ((cc >> 2) * RP + r) * 4 + (cc & 3));
 }
+// sum of column c of the Y rows of node i's outgoing (side 0) / incoming (side 1) edges, in CSR order; four edges are
+// fetched at a time so that their (dependent index -> value) loads overlap
+__device__ __forceinline__ float y_node_sum(const TcPostParams& p, int i, int side, int c) {
+  const int* ptr = side == 0 ? p.src_ptr : p.dst_ptr;
+  const int e0 = __ldg(ptr + i), e1 = __ldg(ptr + i + 1);
+  float acc = 0.f;
+  for (int j = e0; j < e1; j += 4) {
+    int q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) q[u] = j + u < e1 ? (side == 0 ? __ldg(p.src_pos + j + u) : j + u) : -1;
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = q[u] >= 0 ? y_at(p, q[u], c) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (q[u] >= 0) acc += v[u];
+  }
+  return acc;
+}
 __global__ void __launch_bounds__(256) tc_post_sum_kernel(const TcPostParams p) {
   const int per = p.pw + 96;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= (long long)p.N * 2 * per) return;
   const int i = (int)(idx / (2 * per)), rem = (int)(idx - (long long)i * 2 * per);
   const int side = rem / per, c = rem - side * per;
-  float acc = 0.f;
-  if (side == 0) { for (int j = p.src_ptr[i]; j < p.src_ptr[i + 1]; ++j) acc += y_at(p, __ldg(p.src_pos + j), c); }
-  else { for (int q = p.dst_ptr[i]; q < p.dst_ptr[i + 1]; ++q) acc += y_at(p, q, c); }
-  p.A[idx] = acc;
+  p.A[idx] = y_node_sum(p, i, side, c);
 }
 __global__ void __launch_bounds__(256) tc_post_data_kernel(const TcPostParams p) {
   const int W = p.s + 3 * p.v, per = p.pw + 96;
@@ -1061,9 +1089,7 @@ __global__ void __launch_bounds__(256) tc_post_fused_kernel(const TcPostParams p
   for (int t = threadIdx.x; t < nrow * 2 * per; t += 256) {
     const int r = t / (2 * per), rem = t - r * 2 * per;
     const int i = i_first + r, side = rem / per, c = rem - side * per;
-    float acc = 0.f;
-    if (side == 0) { for (int j = p.src_ptr[i]; j < p.src_ptr[i + 1]; ++j) acc += y_at(p, __ldg(p.src_pos + j), c); }
-    else { for (int q = p.dst_ptr[i]; q < p.dst_ptr[i + 1]; ++q) acc += y_at(p, q, c); }
+    const float acc = y_node_sum(p, i, side, c);
     As_sm[r][rem] = acc;
     p.A[(size_t)i * 2 * per + rem] = acc;
   }
