@@ -129,14 +129,38 @@ __global__ void node_cotangent_reduce_kernel(float* __restrict__ g_h, float* __r
 }
 
 // flat parameter gradient = fixed-order sum of the per-CTA partial rows
+// `skip`: ranges of the NODE part that the tiles did not produce (their operands were spilled for node_wgrad_kernel, which
+// writes those gradients itself): neither read nor written here
+struct SkipRanges { int n; int off[12], len[12]; };
 __global__ void partial_reduce_kernel(float* __restrict__ out, const float* __restrict__ pe, int ne, int ge,
-                                      const float* __restrict__ pn, int nn, int gn) {
+                                      const float* __restrict__ pn, int nn, int gn, const SkipRanges skip) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= ne + nn) return;
   float acc = 0.f;
   if (idx < ne) { for (int g = 0; g < ge; ++g) acc += __ldg(pe + (size_t)g * ne + idx); }
-  else { const int j = idx - ne; for (int g = 0; g < gn; ++g) acc += __ldg(pn + (size_t)g * nn + j); }
+  else {
+    const int j = idx - ne;
+    for (int r = 0; r < skip.n; ++r)
+      if (j >= skip.off[r] && j < skip.off[r] + skip.len[r]) return;
+    for (int g = 0; g < gn; ++g) acc += __ldg(pn + (size_t)g * nn + j);
+  }
   out[idx] = acc;
+}
+// the regions of the node parameter gradient that launch_node_wgrad() produces (scalar_out / vector_out_scale, weight + bias)
+static SkipRanges node_wgrad_ranges(const gcpnet_layer& l, const LayerPlan& lp) {
+  SkipRanges s{};
+  const GcpOp* op[3] = {&lp.ops.ff0, &lp.ops.ff1, l.has_pos ? &lp.ops.pu : nullptr};
+  auto add = [&](int off, int len) {  // merge with the previous range when contiguous (weight followed by its bias)
+    if (s.n > 0 && s.off[s.n - 1] + s.len[s.n - 1] == off) { s.len[s.n - 1] += len; return; }
+    if (s.n < 12) { s.off[s.n] = off; s.len[s.n] = len; ++s.n; }
+  };
+  for (int k = 0; k < 3; ++k) {
+    if (op[k] == nullptr) continue;
+    const GcpOp& o = *op[k];
+    add(o.o_Ws, o.so * gcp_k(o)); add(o.o_bs, o.so);
+    if (o.vo > 0) { add(o.o_Wg, o.vo * o.so); add(o.o_bg, o.vo); }
+  }
+  return s;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -279,8 +303,8 @@ static int side_done(cudaStream_t ps, cudaStream_t st) {
 }
 
 // weight gradients of the node GCPs' scalar_out / vector_out_scale from the rows the node backward spilled: one
-// output-parallel kernel over all nodes; OVERWRITES those regions of the flat gradient (after the partial-row reduction,
-// whose sums over the never-written regions of the partial rows are meaningless)
+// output-parallel kernel over all nodes; it writes exactly the regions of the flat gradient that partial_reduce_kernel
+// skips (node_wgrad_ranges)
 static int launch_node_wgrad(const gcpnet_layer& l, const gcpnet_graph& g, const LayerPlan& lp, const float* ws_node_partial,
                              const float* saved_node, float* g_node_params, cudaStream_t st) {
   const long long N = g.num_nodes;
@@ -541,7 +565,7 @@ int gcpnet_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, 
       const cudaStream_t ps = g_opt_early_fork.load(std::memory_order_relaxed) ? fork_side(st) : st;
       GcpTimedScope timed(T_PARTIAL_REDUCE, ps);
       partial_reduce_kernel<<<(l.n_node_params + 255) / 256, 256, 0, ps>>>(io->g_params + l.n_edge_params, nullptr, 0, 0, io->ws_node_partial,
-                                                                            l.n_node_params, lp.nb.grid);
+                                                                            l.n_node_params, lp.nb.grid, node_wgrad_ranges(l, lp));
       gcp_note_launches(1);
       CUDA_TRY(cudaGetLastError());
       if (launch_node_wgrad(l, g, lp, io->ws_node_partial, io->saved_node, io->g_params + l.n_edge_params, ps)) return 1;
@@ -568,7 +592,7 @@ int gcpnet_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, 
   const int np_tot = l.n_edge_params + l.n_node_params;
   GcpTimedScope timed(T_PARTIAL_REDUCE, st);
   partial_reduce_kernel<<<(np_tot + 255) / 256, 256, 0, st>>>(io->g_params, io->ws_edge_partial, l.n_edge_params, edge_grid,
-                                                           io->ws_node_partial, l.n_node_params, lp.nb.grid);
+                                                           io->ws_node_partial, l.n_node_params, lp.nb.grid, node_wgrad_ranges(l, lp));
   gcp_note_launches(1);
   CUDA_TRY(cudaGetLastError());
   if (launch_node_wgrad(l, g, lp, io->ws_node_partial, io->saved_node, io->g_params + l.n_edge_params, st)) return 1;
