@@ -54,16 +54,37 @@ def algorithmic_bytes_per_edge(s, v, se, ve, deg_in):
     return fwd, bwd
 
 
+def nms_edge_index(num_graphs, n):
+    """Fully connected directed graphs without self loops, row-major (i, j != i) per graph (nms_dataset.py:159-165)."""
+    i = torch.arange(n).repeat_interleave(n)
+    j = torch.arange(n).repeat(n)
+    keep = i != j
+    base = torch.stack((i[keep], j[keep]))
+    off = (torch.arange(num_graphs) * n).repeat_interleave(base.shape[1])
+    return base.repeat(1, num_graphs) + off
+
+
+def knn_edge_index(num_graphs, n, k, seed):
+    """Random points in a box per graph; every node receives edges from its k nearest neighbours (destination-major)."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(num_graphs, n, 3, generator=g) * (n ** (1.0 / 3.0)) * 3.8
+    d = torch.cdist(x, x) + torch.eye(n).unsqueeze(0) * 1e9
+    kk = min(k, n - 1)
+    nbr = d.topk(kk, dim=-1, largest=False).indices
+    col = torch.arange(n).view(1, n, 1).expand(num_graphs, n, kk)
+    off = (torch.arange(num_graphs) * n).view(-1, 1, 1)
+    return torch.stack(((nbr + off).reshape(-1), (col + off).reshape(-1))), x.reshape(-1, 3)
+
+
 def make_batch(w, seed, rank=0):
     """Synthetic batch on the host (pinned): raw inputs of the layer stack."""
-    from oracle import gcp_oracle as O  # generators only (graph topology + N(0,1) features)
     g = torch.Generator().manual_seed(1000 * seed + rank)
     if w["kind"] == "nms":
-        ei = O.nms_edge_index(w["graphs"], w["n"])
+        ei = nms_edge_index(w["graphs"], w["n"])
         N = w["graphs"] * w["n"]
         pos = torch.randn(N, 3, generator=g) * (w["n"] / 5.0) ** (1.0 / 3.0)
     else:
-        ei, pos = O.knn_like_edge_index(w["graphs"], w["n"], w["k"], seed=1000 * seed + rank)
+        ei, pos = knn_edge_index(w["graphs"], w["n"], w["k"], seed=1000 * seed + rank)
         N = w["graphs"] * w["n"]
         pos = pos.float()
     E = ei.shape[1]
@@ -75,8 +96,38 @@ def make_batch(w, seed, rank=0):
 
 
 def oracle_cfg(w):
-    from oracle import gcp_oracle as O
+    from oracle import gcp_oracle as O  # CPU arm only
     return O.OracleConfig(node_dims=w["node_dims"], edge_dims=w["edge_dims"], updating_node_positions=w["pos"])
+
+
+class AttrDict(dict):
+    """Stand-in for the reference's omegaconf.DictConfig (attribute access, survives copy())."""
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+    def __copy__(self):
+        return AttrDict(self)
+
+
+def module_cfgs():
+    """configs/model/module_cfg/gcp_module_nms.yaml + layer_cfg/gcp_interaction_layer_nms.yaml + mp_cfg/gcp_mp_nms.yaml."""
+    mcfg = AttrDict(norm_x_diff=True, scalar_gate=0, vector_gate=True, vector_residual=False, vector_frame_residual=False,
+                    frame_gate=False, sigma_frame_gate=False, scalar_nonlinearity="relu", vector_nonlinearity=None,
+                    nonlinearities=["relu", None], bottleneck=4, vector_linear=True, vector_identity=True,
+                    default_vector_residual=False, default_bottleneck=4, node_positions_weight=1.0, ablate_frame_updates=False,
+                    ablate_scalars=False, ablate_vectors=False, ablate_x_force_update=True, enable_e3_equivariance=False)
+    mp = AttrDict(edge_encoder=False, edge_gate=False, num_message_layers=8, message_residual=0, message_ff_multiplier=1,
+                  self_message=True, use_residual_message_gcp=True)
+    lcfg = AttrDict(pre_norm=False, num_feedforward_layers=2, dropout=0.1, nonlinearity_slope=1e-2, mp_cfg=mp)
+    return mcfg, lcfg
+
+
+def config_of(args, w, N, E, world):
+    """The `config` object both arms print (identical keys and values for the same invocation)."""
+    s, v = w["node_dims"]
+    return {"workload": f"{args.workload}: {w['desc']}", "layers": w["layers"], "nodes_per_gpu": N, "edges_per_gpu": E,
+            "node_dims": [s, v], "edge_dims": list(w["edge_dims"]), "train_mode_dropout": 0.1,
+            "parallelism": f"graph-sharded dp{world}"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -174,17 +225,15 @@ def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 20))
-    warm = max(1, min(args.warmup, 3))
+    steps, warm = args.steps, max(args.warmup, 3)  # the same K / W our arm reports (a CPU step is ~0.1 s at cfg2)
     sec, units, threads = cpu_steps(w, steps, warm)
     val = units / sec
-    s, v = w["node_dims"]
+    N, E = w["graphs"] * w["n"], units // w["layers"]
     _emit({
         "impl": "reference", "metric": "edges/s (fused GCP msg+aggregate fwd+bwd)", "value": val, "unit": "edge-layers/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {w['desc']}", "layers": w["layers"], "node_dims": [s, v],
-                   "edge_dims": list(w["edge_dims"]), "train_mode_dropout": 0.1},
+        "config": config_of(args, w, N, E, int(os.environ.get("WORLD_SIZE", "1"))),
         "cpu_baseline": {"value": val, "unit": "edge-layers/s", "cores": threads, "kind": "port",
                          "sample": f"{steps} full steps of the workload (median), oracle/gcp_oracle.py in torch CPU "
                                    f"fp32 with {threads} threads; the Python reference cannot travel to the GPU box"},
@@ -198,12 +247,10 @@ def run_reference(args, w):
 # ------------------------------------------------------------------------------------------
 def build_stack(w, device):
     import gcpnet_b200
-    from tests.helpers import module_cfgs
-    cfg = oracle_cfg(w)
-    mcfg, lcfg = module_cfgs(cfg)
+    mcfg, lcfg = module_cfgs()
     torch.manual_seed(0)
     layers = torch.nn.ModuleList([
-        gcpnet_b200.GCPInteractions(cfg.node_dims, cfg.edge_dims, cfg=mcfg, layer_cfg=lcfg, dropout=0.1,
+        gcpnet_b200.GCPInteractions(w["node_dims"], w["edge_dims"], cfg=mcfg, layer_cfg=lcfg, dropout=0.1,
                                     updating_node_positions=w["pos"]) for _ in range(w["layers"])]).to(device)
     layers.train()
     return layers
@@ -286,40 +333,60 @@ def run_ours(args, w):
             d[k].requires_grad_(True)
         return d, dflat
 
-    def allreduce_grads():
-        if world > 1 and not os.environ.get("GCPNET_BENCH_SKIP_ALLREDUCE"):  # (diagnostic switch; such a run is not a bench line)
-            # graph-sharded data parallelism: the only exchange is the parameter-gradient all-reduce
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)
-            flat.div_(world)
-
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     dbatch, dflat = to_dev_packed()
     torch.cuda.synchronize()
+    group = dist.group.WORLD if world > 1 else None
+
+    # Gradients of all layers live in ONE flat buffer (gcpnet_b200.ddp.FlatGradients): the layers write into it directly.
+    # With several ranks the per-layer NCCL all-reduces (mean) are captured INSIDE the step's CUDA graph on the library's
+    # side stream, each issued as soon as its layer's parameter-gradient work is enqueued.
+    # The whole step (frames, CSR views, L x forward, loss, L x backward[, all-reduces]) is one CUDA graph: at 5 120 edges
+    # per batch the eager path is bound by Python/launch overhead, not by the kernels.
+    graphed = None
+    launches_per_step = None
+    allreduce_mode = "none (1 rank)" if world == 1 else "per-layer NCCL all-reduce (mean) captured in the step graph, side stream"
+    if not args.no_graph:
+        l0 = lib.gcpnet_launch_count()
+        try:
+            if os.environ.get("GCPNET_BENCH_EAGER_ALLREDUCE"):
+                raise RuntimeError("eager all-reduce requested")
+            graphed = gcpnet_b200.GraphedStep(lambda b: loss_fn(layers, w, b), dbatch, params, warmup=max(args.warmup, 3),
+                                              model=layers, process_group=group)
+        except Exception as exc:  # NCCL capture unavailable: all-reduce the flat buffer after the replay instead
+            if world == 1:
+                raise
+            print(f"[bench] captured all-reduce unavailable ({exc}); using one eager flat all-reduce per step", file=sys.stderr)
+            torch.cuda.synchronize()
+            l0 = lib.gcpnet_launch_count()
+            graphed = gcpnet_b200.GraphedStep(lambda b: loss_fn(layers, w, b), dbatch, params, warmup=max(args.warmup, 3),
+                                              model=layers, process_group=None)
+            graphed.flat.group, graphed.flat.overlap = group, False
+            allreduce_mode = "one eager NCCL all-reduce (mean) of the flat gradient buffer after the graph replay"
+        launches_per_step = (lib.gcpnet_launch_count() - l0) // (max(args.warmup, 3) + 1)
+    eager_flat = None
 
     def eager_step(batch):
         for p in params:
-            p.grad = None
+            if graphed is None or graphed.flat is None:
+                p.grad = None
         for k in ("h", "chi", "e", "xi"):
             batch[k].grad = None
         loss = step_fn(layers, w, batch)
-        allreduce_grads()
         return loss
-
-    # The whole step (frames, CSR views, L x forward, loss, L x backward) is one CUDA graph: at 5 120 edges per
-    # batch the eager path is bound by Python/launch overhead, not by the kernels.
-    graphed = None
-    launches_per_step = None
-    if not args.no_graph:
-        l0 = lib.gcpnet_launch_count()
-        graphed = gcpnet_b200.GraphedStep(lambda b: loss_fn(layers, w, b), dbatch, params, warmup=max(args.warmup, 3))
-        launches_per_step = (lib.gcpnet_launch_count() - l0) // (max(args.warmup, 3) + 1)
 
     def one_step(batch):
         if graphed is None:
-            return eager_step(batch)
+            loss = eager_step(batch)
+            if world > 1:
+                nonlocal eager_flat
+                if eager_flat is None:
+                    eager_flat = gcpnet_b200.FlatGradients(layers, process_group=group, overlap=False)
+                eager_flat.all_reduce()
+            return loss
         loss = graphed(batch if batch is not dbatch else None)
-        allreduce_grads()
+        if world > 1 and not graphed.flat.overlap:
+            graphed.flat.all_reduce()
         return loss
 
     # ---- warm-up -------------------------------------------------------------------------
@@ -369,6 +436,10 @@ def run_ours(args, w):
     e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
     # ---- per-kernel CUDA events (same workload, same stream; eager launches because events inside a replayed graph
     #      cannot bracket single kernels): the roofline leg
+    if graphed is not None and graphed.flat is not None:
+        graphed.flat.group = None  # the per-kernel leg below is a single-rank diagnostic: no collectives
+        for l in layers:
+            l._grad_hook = None
     lib.gcpnet_profile_enable(1)
     evk = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for a, b in evk:
@@ -426,7 +497,8 @@ def run_ours(args, w):
                     "frac": gbs / peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured, burst copy)" if peaks else "of fallback 6.65 TB/s",
                     "algorithmic_bytes_per_launch": alg, "us_per_launch": us, "launches_timed": cnt,
-                    "kernel_share_of_step": tot_ms / eager_ms,
+                    "kernel_share_of_step": tot_ms / dev_ms,
+                    "kernel_share_of_kernel_time": tot_ms / max(sum(t for t, _ in kernel_ms.values()), 1e-9),
                     "kernel_timing": "CUDA events around every launch of the kernel in an eager pass of the same steps "
                                      f"({eager_ms / args.steps:.3f} ms/step eager vs {dev_ms / args.steps:.3f} ms/step graph replay)",
                     "kernel_ms_per_step": {k: t / args.steps for k, (t, _) in kernel_ms.items()},
@@ -437,11 +509,10 @@ def run_ours(args, w):
             "unit": "edge-layers/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {w['desc']}", "layers": L, "nodes_per_gpu": N, "edges_per_gpu": E,
-                       "node_dims": [s, v], "edge_dims": [se, ve], "train_mode_dropout": 0.1,
-                       "l2": "flushed (256 MiB write) before every timed step", "timing": "CUDA events per step, summed",
+            "config": config_of(args, w, N, E, world),
+            "method": {"l2": "flushed (256 MiB write) before every timed step", "timing": "CUDA events per step, summed, max over ranks",
                        "launch": "whole step replayed as one CUDA graph" if graphed is not None else "eager launches",
-                       "parallelism": f"graph-sharded dp{world}, NCCL all-reduce of the {flat_grad_elems * 4} B gradient"},
+                       "gradient_exchange": allreduce_mode, "gradient_bytes": flat_grad_elems * 4},
             "per_layer_edges_per_s": world * E * L * args.steps / (dev_ms * 1e-3) / 1.0,
             "e2e": {"value": world * units * args.steps / (e2e_ms * 1e-3), "unit": "edge-layers/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},

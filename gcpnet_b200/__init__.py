@@ -3,7 +3,9 @@
 Python host code over hand-written sm_100a kernels behind the C ABI of include/gcpnet_b200.h.
 """
 from .scalar_vector import ScalarVector  # noqa: F401
-from .interactions import GCPInteractions, GCP2Params, localize, graph_views, clear_graph_cache  # noqa: F401
+from .interactions import GCPInteractions, GCPMessagePassing, GCP2Params, localize, graph_views, clear_graph_cache  # noqa: F401
 from .graphs import GraphedStep, prepack  # noqa: F401
+from . import ddp  # noqa: F401
+from .ddp import FlatGradients  # noqa: F401
 
-__all__ = ["GCPInteractions", "GCP2Params", "ScalarVector", "localize", "graph_views", "clear_graph_cache", "GraphedStep", "prepack"]
+__all__ = ["GCPInteractions", "GCPMessagePassing", "GCP2Params", "ScalarVector", "localize", "graph_views", "clear_graph_cache", "GraphedStep", "prepack", "FlatGradients", "ddp"]

@@ -78,7 +78,7 @@ class BackwardIO(C.Structure):
 EXPORTS = (
     "gcpnet_version", "gcpnet_last_error", "gcpnet_launch_count", "gcpnet_profile_enable", "gcpnet_profile_read", "gcpnet_set_option", "gcpnet_debug_stamps", "gcpnet_set_side_stream", "gcpnet_join", "gcpnet_graph_workspace_bytes", "gcpnet_graph_build",
     "gcpnet_localize", "gcpnet_layer_plan", "gcpnet_layer_pack", "gcpnet_layer_forward", "gcpnet_layer_backward",
-    "gcpnet_message_passing_forward",
+    "gcpnet_message_passing_forward", "gcpnet_message_passing_backward",
 )
 
 
@@ -120,6 +120,9 @@ def declare(lib: C.CDLL) -> None:
     lib.gcpnet_message_passing_forward.restype = C.c_int
     lib.gcpnet_message_passing_forward.argtypes = [C.POINTER(Layer), C.POINTER(Graph), C.POINTER(Plan),
                                                    C.POINTER(ForwardIO), C.c_void_p, C.c_void_p]
+    lib.gcpnet_message_passing_backward.restype = C.c_int
+    lib.gcpnet_message_passing_backward.argtypes = [C.POINTER(Layer), C.POINTER(Graph), C.POINTER(Plan),
+                                                    C.POINTER(BackwardIO), C.c_void_p, C.c_void_p]
 
 
 # ------------------------------------------------------------------------------------------

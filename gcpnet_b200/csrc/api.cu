@@ -228,8 +228,9 @@ static int launch_node_bwd(const NodeParams& p, const NodeTilePlan& tp, cudaStre
   if (tp.SLF == 4) return launch(node_bwd_kernel<NODE_TE, NODE_NT, 4, NODE_SLD>, p, tp.grid, NODE_NT, bytes, st);
   return fail("no kernel instantiation for this node tile plan");
 }
-static int launch_pack(const LayerOps& ops, float* blob, cudaStream_t st, bool skip_messages = false) {
-  const PackParams pp = make_pack_params(ops, blob, skip_messages);
+static int launch_pack(const LayerOps& ops, float* blob, cudaStream_t st, bool skip_messages = false, bool skip_node = false) {
+  const PackParams pp = make_pack_params(ops, blob, skip_messages, skip_node);
+  if (pp.n == 0) return 0;
   pack_kernel<<<dim3(pp.n, 16), 256, 0, st>>>(pp);
   gcp_note_launches(1);
   CUDA_TRY(cudaGetLastError());
@@ -243,15 +244,24 @@ int gcp_tc_launch_post(const tc::TcPostParams& p, int which, cudaStream_t st);  
 // The next layer's backward only needs dh / dchi; reducing the partials and the chain rule to the reference's parameters
 // can overlap with it.  The caller owns the side stream (gcpnet_set_side_stream) and joins it with gcpnet_join() before
 // anything consumes the parameter gradients.  Events are created once, outside any stream capture.
+// State is kept per device (one process normally drives one GPU; a process that drives several gets one side stream each).
+struct SideState {
+  cudaStream_t stream = nullptr;
+  std::vector<cudaEvent_t> events;       // pool, created once outside any stream capture
+  size_t next = 0;
+  std::vector<cudaEvent_t> pending;      // recorded on the side stream, not yet joined
+};
 static std::mutex g_side_mu;
-static cudaStream_t g_side = nullptr;
-static std::vector<cudaEvent_t> g_side_events;      // pool
-static size_t g_side_next = 0;
-static std::vector<cudaEvent_t> g_side_pending;     // recorded on the side stream, not yet joined
-static cudaEvent_t side_event() {
-  if (g_side_events.empty()) return nullptr;
-  cudaEvent_t e = g_side_events[g_side_next % g_side_events.size()];
-  ++g_side_next;
+static std::map<int, SideState> g_side_by_dev;
+static SideState* side_state() {         // call with g_side_mu held
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  return &g_side_by_dev[dev];
+}
+static cudaEvent_t side_event(SideState& s) {
+  if (s.events.empty()) return nullptr;
+  cudaEvent_t e = s.events[s.next % s.events.size()];
+  ++s.next;
   return e;
 }
 int gcp_tc_launch_finalize(const float* partial, int rows, int stride, float* G, const float* npartial, int nrows, int nstride, float* Gn,
@@ -286,19 +296,32 @@ static int launch_tc_edge_fwd(const gcpnet_graph& g, const LayerPlan& lp, const 
 // kernels); returns the stream to use (st itself when there is no side stream)
 static cudaStream_t fork_side(cudaStream_t st) {
   std::lock_guard<std::mutex> lock(g_side_mu);
-  if (g_side == nullptr || gcp_profile_on()) return st;
-  cudaEvent_t ev = side_event();
+  SideState* s = side_state();
+  if (s == nullptr || s->stream == nullptr || gcp_profile_on()) return st;
+  cudaEvent_t ev = side_event(*s);
   if (ev == nullptr) return st;
-  if (cudaEventRecord(ev, st) != cudaSuccess || cudaStreamWaitEvent(g_side, ev, 0) != cudaSuccess) return st;
-  return g_side;
+  if (cudaEventRecord(ev, st) != cudaSuccess || cudaStreamWaitEvent(s->stream, ev, 0) != cudaSuccess) return st;
+  return s->stream;
+}
+// the side stream `ps` additionally waits for what has been enqueued on `st` so far
+static int side_wait_main(cudaStream_t ps, cudaStream_t st) {
+  if (ps == st) return 0;
+  std::lock_guard<std::mutex> lock(g_side_mu);
+  SideState* s = side_state();
+  cudaEvent_t ev = s ? side_event(*s) : nullptr;
+  if (ev == nullptr) return fail("side stream: out of events");
+  CUDA_TRY(cudaEventRecord(ev, st));
+  CUDA_TRY(cudaStreamWaitEvent(ps, ev, 0));
+  return 0;
 }
 static int side_done(cudaStream_t ps, cudaStream_t st) {
   if (ps == st) return 0;
   std::lock_guard<std::mutex> lock(g_side_mu);
-  cudaEvent_t ev = side_event();
+  SideState* s = side_state();
+  cudaEvent_t ev = s ? side_event(*s) : nullptr;
   if (ev == nullptr) return fail("side stream: out of events");
   CUDA_TRY(cudaEventRecord(ev, ps));
-  g_side_pending.push_back(ev);
+  s->pending.push_back(ev);
   return 0;
 }
 
@@ -336,7 +359,8 @@ static int launch_node_wgrad(const gcpnet_layer& l, const gcpnet_graph& g, const
 }
 
 // tensor-core edge backward + node-level finish of message GCP 0 + chain rule to the reference's parameters
-static int run_tc_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, const LayerPlan& lp, const gcpnet_backward_io& io, cudaStream_t st) {
+static int run_tc_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, const LayerPlan& lp, const gcpnet_backward_io& io, const float* gagg,
+                                cudaStream_t st) {
   const tc::TcPlan& T = lp.tc;
   float* Y = io.ws_edge;
   float* A = Y + T.y_floats;
@@ -349,7 +373,7 @@ static int run_tc_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, co
     fill_tc_common(b.f, g, lp, io.h, io.chi, io.e, io.xi, io.frames, io.packed);
     b.f.saved = const_cast<float*>(io.saved_edge);
     b.f.msg = nullptr; b.f.dbg = g_tc_dbg.load(std::memory_order_relaxed);
-    b.gagg = io.ws_agg; b.dst_ptr = g.dst_ptr;
+    b.gagg = gagg; b.dst_ptr = g.dst_ptr;
     b.ge = io.g_e; b.gxi = io.g_xi; b.Y = Y; b.partial = io.ws_edge_partial;
     if (gcp_tc_launch_edge_bwd(b, T.grid, st)) return 1;
   }
@@ -395,13 +419,7 @@ static int run_tc_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, co
     if (mode == 2) {
       if (gcp_tc_launch_finalize(io.ws_edge_partial, T.grid, T.bproto.partial_stride, G, npart, T.node_partial_ctas, T.node_partial_stride, Gn, fp, 1, ps))
         return 1;
-      if (ps != st) {  // the per-node sums (main stream) feed the node-level products
-        std::lock_guard<std::mutex> lock(g_side_mu);
-        cudaEvent_t ev = side_event();
-        if (ev == nullptr) return fail("side stream: out of events");
-        CUDA_TRY(cudaEventRecord(ev, st));
-        CUDA_TRY(cudaStreamWaitEvent(ps, ev, 0));
-      }
+      if (side_wait_main(ps, st)) return 1;  // the per-node sums (main stream) feed the node-level products
     }
     if (gcp_tc_launch_post(pp, 4, ps)) return 1;
     if (gcp_tc_launch_finalize(io.ws_edge_partial, T.grid, T.bproto.partial_stride, G, npart, T.node_partial_ctas, T.node_partial_stride, Gn, fp, mode == 2 ? 2 : 3, ps))
@@ -421,20 +439,24 @@ void gcpnet_profile_enable(int on) { g_profile.store(on != 0); }
 void gcpnet_debug_stamps(long long* device_buffer) { g_tc_dbg.store(device_buffer); }
 int gcpnet_set_side_stream(void* stream) {
   std::lock_guard<std::mutex> lock(g_side_mu);
-  g_side = (cudaStream_t)stream;
-  if (g_side != nullptr && g_side_events.empty()) {
-    for (int i = 0; i < 64; ++i) {
+  SideState* s = side_state();
+  if (s == nullptr) return fail("set_side_stream: no current device");
+  s->stream = (cudaStream_t)stream;
+  if (s->stream != nullptr && s->events.empty()) {
+    for (int i = 0; i < 256; ++i) {
       cudaEvent_t e;
       CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      g_side_events.push_back(e);
+      s->events.push_back(e);
     }
   }
   return 0;
 }
 int gcpnet_join(void* stream) {
   std::lock_guard<std::mutex> lock(g_side_mu);
-  for (cudaEvent_t e : g_side_pending) CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, e, 0));
-  g_side_pending.clear();
+  SideState* s = side_state();
+  if (s == nullptr) return 0;
+  for (cudaEvent_t e : s->pending) CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, e, 0));
+  s->pending.clear();
   return 0;
 }
 int gcpnet_set_option(const char* name, int value) {
@@ -521,12 +543,36 @@ int gcpnet_message_passing_forward(const gcpnet_layer* layer, const gcpnet_graph
   const std::string e = make_layer_plan(*layer, graph->num_nodes, graph->num_edges, &lp, nullptr, plan->tc_edge_path != 0);
   if (!e.empty()) return fail("message_passing_forward: " + e);
   if (graph->num_nodes <= 0) return 0;
-  if (launch_pack(lp.ops, io->packed, st)) return 1;
+  if (launch_pack(lp.ops, io->packed, st, lp.tc.ok, true)) return 1;
   if (run_edge_forward(*layer, *graph, lp, *io, st)) return 1;
   const int W = layer->s + 3 * layer->v;
   const long long tot = graph->num_nodes * W;
   aggregate_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(io->msg, graph->dst_ptr, (int)graph->num_nodes, W,
                                                             layer->reduce_mean, aggregate);
+  gcp_note_launches(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// FFMA-tile edge backward + per-node sums of the gathered cotangents (accumulated into g_h / g_chi)
+static int run_ffma_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, const LayerPlan& lp, const gcpnet_backward_io& io,
+                                  const float* gagg, cudaStream_t st, int* edge_grid) {
+  *edge_grid = 0;
+  if (g.num_edges <= 0) return 0;
+  const int W = l.s + 3 * l.v;
+  EdgeParams ep = make_edge_params(l, g, lp.ops, lp.eb, true, io.packed);
+  ep.h = io.h; ep.chi = io.chi; ep.e = io.e; ep.xi = io.xi; ep.frames = io.frames;
+  ep.saved = const_cast<float*>(io.saved_edge);
+  ep.gagg = gagg;
+  ep.grow = io.ws_edge; ep.gcol = io.ws_edge + (size_t)g.num_edges * W;
+  ep.ge = io.g_e; ep.gxi = io.g_xi;
+  ep.partial = io.ws_edge_partial;
+  *edge_grid = lp.eb.grid;
+  if (launch_edge_bwd(ep, lp.eb, st)) return 1;
+  const long long tot = g.num_nodes * W;
+  GcpTimedScope timed(T_COT_REDUCE, st);
+  node_cotangent_reduce_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(
+      io.g_h, io.g_chi, ep.grow, ep.gcol, g.dst_ptr, g.src_ptr, g.src_pos, (int)g.num_nodes, l.s, 3 * l.v);
   gcp_note_launches(1);
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -559,7 +605,6 @@ int gcpnet_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, 
     for (int k = 0; k < 3; ++k) { np.sp_gT[k] = sp.gT[k]; np.sp_Z[k] = sp.Z[k]; np.sp_GG[k] = sp.GG[k]; }
   }
   if (launch_node_bwd(np, lp.nb, st)) return 1;
-  int edge_grid = 0;
   if (g.num_edges > 0 && lp.tc.ok) {
     {  // node parameter gradients: ready as soon as the node backward is done -> overlap with the edge backward
       const cudaStream_t ps = g_opt_early_fork.load(std::memory_order_relaxed) ? fork_side(st) : st;
@@ -571,24 +616,10 @@ int gcpnet_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, 
       if (launch_node_wgrad(l, g, lp, io->ws_node_partial, io->saved_node, io->g_params + l.n_edge_params, ps)) return 1;
       if (side_done(ps, st)) return 1;
     }
-    return run_tc_edge_backward(l, g, lp, *io, st);
+    return run_tc_edge_backward(l, g, lp, *io, io->ws_agg, st);
   }
-  if (g.num_edges > 0) {
-    EdgeParams ep = make_edge_params(l, g, lp.ops, lp.eb, true, io->packed);
-    ep.h = io->h; ep.chi = io->chi; ep.e = io->e; ep.xi = io->xi; ep.frames = io->frames;
-    ep.saved = const_cast<float*>(io->saved_edge);
-    ep.gagg = io->ws_agg;
-    ep.grow = io->ws_edge; ep.gcol = io->ws_edge + (size_t)g.num_edges * W;
-    ep.ge = io->g_e; ep.gxi = io->g_xi;
-    ep.partial = io->ws_edge_partial;
-    edge_grid = lp.eb.grid;
-    if (launch_edge_bwd(ep, lp.eb, st)) return 1;
-    const long long tot = g.num_nodes * W;
-    GcpTimedScope timed(T_COT_REDUCE, st);
-    node_cotangent_reduce_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(
-        io->g_h, io->g_chi, ep.grow, ep.gcol, g.dst_ptr, g.src_ptr, g.src_pos, (int)g.num_nodes, l.s, 3 * l.v);
-    gcp_note_launches(1);
-  }
+  int edge_grid = 0;
+  if (run_ffma_edge_backward(l, g, lp, *io, io->ws_agg, st, &edge_grid)) return 1;
   const int np_tot = l.n_edge_params + l.n_node_params;
   GcpTimedScope timed(T_PARTIAL_REDUCE, st);
   partial_reduce_kernel<<<(np_tot + 255) / 256, 256, 0, st>>>(io->g_params, io->ws_edge_partial, l.n_edge_params, edge_grid,
@@ -596,6 +627,37 @@ int gcpnet_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, 
   gcp_note_launches(1);
   CUDA_TRY(cudaGetLastError());
   if (launch_node_wgrad(l, g, lp, io->ws_node_partial, io->saved_node, io->g_params + l.n_edge_params, st)) return 1;
+  return 0;
+}
+
+int gcpnet_message_passing_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, const gcpnet_plan* plan,
+                                    const gcpnet_backward_io* io, const float* g_aggregate, void* stream) {
+  if (!layer || !graph || !plan || !io || !g_aggregate) return fail("message_passing_backward: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const gcpnet_layer& l = *layer;
+  const gcpnet_graph& g = *graph;
+  if (!io->saved_edge && g.num_edges > 0) return fail("message_passing_backward: forward ran without saved activations");
+  if (!io->packed) return fail("message_passing_backward: packed weights of the forward call required");
+  LayerPlan lp;
+  const std::string e = make_layer_plan(l, g.num_nodes, g.num_edges, &lp, nullptr, plan->tc_edge_path != 0);
+  if (!e.empty()) return fail("message_passing_backward: " + e);
+  if (g.num_nodes <= 0) return 0;
+  // the edge backward ACCUMULATES the gathered cotangents into g_h / g_chi (the layer's node backward writes the direct
+  // part first): standalone, the direct part is zero
+  CUDA_TRY(cudaMemsetAsync(io->g_h, 0, (size_t)g.num_nodes * l.s * sizeof(float), st));
+  CUDA_TRY(cudaMemsetAsync(io->g_chi, 0, (size_t)g.num_nodes * 3 * l.v * sizeof(float), st));
+  if (g.num_edges == 0) {
+    CUDA_TRY(cudaMemsetAsync(io->g_params, 0, (size_t)l.n_edge_params * sizeof(float), st));
+    return 0;
+  }
+  if (lp.tc.ok) return run_tc_edge_backward(l, g, lp, *io, g_aggregate, st);
+  int edge_grid = 0;
+  if (run_ffma_edge_backward(l, g, lp, *io, g_aggregate, st, &edge_grid)) return 1;
+  GcpTimedScope timed(T_PARTIAL_REDUCE, st);
+  partial_reduce_kernel<<<(l.n_edge_params + 255) / 256, 256, 0, st>>>(io->g_params, io->ws_edge_partial, l.n_edge_params, edge_grid,
+                                                                        nullptr, 0, 0, SkipRanges{});
+  gcp_note_launches(1);
+  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 

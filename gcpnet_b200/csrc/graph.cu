@@ -3,19 +3,30 @@
 // comp/__init__.py:220-269 (localize).  Entry points declared in include/gcpnet_b200.h.
 #include <cuda_runtime.h>
 
+#include <cstdio>
 #include <cub/device/device_radix_sort.cuh>
+#include <mutex>
+#include <set>
 #include <string>
 
 #include "../../include/gcpnet_b200.h"
 #include "common.h"
 
 // ---- graph build -------------------------------------------------------------------------------
-__global__ void edge_keys_kernel(const int64_t* __restrict__ edge_index, int E, int* __restrict__ row32,
+// An edge_index entry outside [0, N) is the reference's IndexError / device-side assert (fancy indexing h[row], scatter);
+// here it would silently corrupt the CSR build and every gather after it, so the build kernels stop the context instead.
+__device__ __noinline__ void bad_edge_index(long long e, long long r, long long c, int N) {
+  printf("gcpnet_graph_build: edge %lld = (%lld, %lld) is outside [0, %d)\n", e, r, c, N);
+  asm volatile("trap;");
+}
+__global__ void edge_keys_kernel(const int64_t* __restrict__ edge_index, int E, int N, int* __restrict__ row32,
                                  int* __restrict__ col32, int* __restrict__ iota) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
-  row32[e] = (int)edge_index[e];
-  col32[e] = (int)edge_index[(size_t)E + e];
+  const int64_t r = edge_index[e], c = edge_index[(size_t)E + e];
+  if (r < 0 || r >= N || c < 0 || c >= N) bad_edge_index(e, r, c, N);
+  row32[e] = (int)r;
+  col32[e] = (int)c;
   iota[e] = e;
 }
 __global__ void gather_src_kernel(const int* __restrict__ row32, const int* __restrict__ perm, int E,
@@ -52,20 +63,39 @@ __global__ void mean_frame_kernel(const float* __restrict__ frames, const int* _
 // by edge id (destination view) / by sorted position (source view), which reproduces the stable order of the radix sort
 // exactly -- the result does not depend on the order in which the atomics land.
 constexpr int SMALL_MAX_NODES = 12287, SMALL_MAX_EDGES = 16384, SMALL_NT = 1024;  // beyond that the radix-sort pipeline wins (measured)
+constexpr int SMALL_LONG_SEG = 48;    // segments longer than this are ranked by the whole CTA instead of one thread's insertion sort
+constexpr int SMALL_MAX_LONG = SMALL_MAX_EDGES / SMALL_LONG_SEG + 1;
+// order the entries of arr[a, b) ascending (distinct keys), whole CTA: rank by counting, through `scratch`
+__device__ __forceinline__ void cta_rank_sort(int* arr, int* scratch, int a, int b, int tid) {
+  for (int p = a + tid; p < b; p += SMALL_NT) {
+    const int key = arr[p];
+    int rank = 0;
+    for (int q = a; q < b; ++q) rank += arr[q] < key;
+    scratch[a + rank] = key;
+  }
+  __syncthreads();
+  for (int p = a + tid; p < b; p += SMALL_NT) arr[p] = scratch[p];
+  __syncthreads();
+}
 __global__ void __launch_bounds__(SMALL_NT) graph_build_small_kernel(const int64_t* __restrict__ edge_index, int E, int N,
                                                                      const float* __restrict__ frames, int* __restrict__ perm,
                                                                      int* __restrict__ src, int* __restrict__ dst, int* __restrict__ dst_ptr,
-                                                                     int* __restrict__ src_pos, int* __restrict__ src_ptr, float* __restrict__ fbar) {
+                                                                     int* __restrict__ src_pos, int* __restrict__ src_ptr, float* __restrict__ fbar,
+                                                                     int* __restrict__ scratch) {
   extern __shared__ int sh[];
   int* cd = sh;            // [N + 1] counts -> cursors (destination)
   int* cs = sh + (N + 1);  // [N + 1] (source)
   __shared__ int carry[2];
+  __shared__ int long_n, long_seg[SMALL_MAX_LONG];
   const int tid = threadIdx.x;
   for (int i = tid; i <= N; i += SMALL_NT) { cd[i] = 0; cs[i] = 0; }
+  if (tid == 0) long_n = 0;
   __syncthreads();
   for (int e = tid; e < E; e += SMALL_NT) {
-    atomicAdd(&cd[(int)edge_index[(size_t)E + e]], 1);
-    atomicAdd(&cs[(int)edge_index[e]], 1);
+    const int64_t r = edge_index[e], c = edge_index[(size_t)E + e];
+    if (r < 0 || r >= N || c < 0 || c >= N) bad_edge_index(e, r, c, N);
+    atomicAdd(&cd[(int)c], 1);
+    atomicAdd(&cs[(int)r], 1);
   }
   __syncthreads();
   // exclusive scans (one warp each, chunks of 32 with a running carry): ptr arrays to global, cursors stay in shared memory
@@ -89,21 +119,31 @@ __global__ void __launch_bounds__(SMALL_NT) graph_build_small_kernel(const int64
   __syncthreads();
   for (int e = tid; e < E; e += SMALL_NT) perm[atomicAdd(&cd[(int)edge_index[(size_t)E + e]], 1)] = e;
   __syncthreads();
-  for (int i = tid; i < N; i += SMALL_NT) {  // order every destination segment by edge id (insertion sort: segments are short)
+  // order every destination segment by edge id: short segments by one thread's insertion sort, hub nodes' long
+  // segments (O(deg^2) in one thread otherwise) by the whole CTA
+  for (int i = tid; i < N; i += SMALL_NT) {
     const int a = dst_ptr[i], b = dst_ptr[i + 1];
+    if (b - a > SMALL_LONG_SEG) { long_seg[atomicAdd(&long_n, 1)] = i; continue; }
     for (int p = a + 1; p < b; ++p) {
       const int key = perm[p];
       int q = p - 1;
       while (q >= a && perm[q] > key) { perm[q + 1] = perm[q]; --q; }
       perm[q + 1] = key;
     }
+  }
+  __syncthreads();
+  for (int j = 0; j < long_n; ++j) { const int i = long_seg[j]; cta_rank_sort(perm, scratch, dst_ptr[i], dst_ptr[i + 1], tid); }
+  for (int i = tid; i < N; i += SMALL_NT) {
+    const int a = dst_ptr[i], b = dst_ptr[i + 1];
     for (int p = a; p < b; ++p) { dst[p] = i; src[p] = (int)edge_index[perm[p]]; }
   }
   __syncthreads();
+  if (tid == 0) long_n = 0;
   for (int p = tid; p < E; p += SMALL_NT) src_pos[atomicAdd(&cs[src[p]], 1)] = p;
   __syncthreads();
   for (int i = tid; i < N; i += SMALL_NT) {
     const int a = src_ptr[i], b = src_ptr[i + 1];
+    if (b - a > SMALL_LONG_SEG) { long_seg[atomicAdd(&long_n, 1)] = i; continue; }
     for (int p = a + 1; p < b; ++p) {
       const int key = src_pos[p];
       int q = p - 1;
@@ -112,6 +152,7 @@ __global__ void __launch_bounds__(SMALL_NT) graph_build_small_kernel(const int64
     }
   }
   __syncthreads();
+  for (int j = 0; j < long_n; ++j) { const int i = long_seg[j]; cta_rank_sort(src_pos, scratch, src_ptr[i], src_ptr[i + 1], tid); }
   for (int idx = tid; idx < N * 9; idx += SMALL_NT) {  // mean frame over the edges leaving each node
     const int i = idx / 9, c = idx - 9 * i;
     const int a = src_ptr[i], b = src_ptr[i + 1];
@@ -172,12 +213,18 @@ int gcpnet_graph_build(const int64_t* edge_index, int64_t E64, int64_t N64, cons
   GcpTimedScope timed(T_GRAPH_BUILD, st);
   if (N <= SMALL_MAX_NODES && E <= SMALL_MAX_EDGES) {
     const int bytes = 2 * (N + 1) * (int)sizeof(int);
-    static bool attr_set = false;
-    if (!attr_set) {
-      CUDA_TRY(cudaFuncSetAttribute(graph_build_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (SMALL_MAX_NODES + 1) * (int)sizeof(int)));
-      attr_set = true;
+    {  // opt in to the large dynamic shared memory once per device
+      static std::mutex mu;
+      static std::set<int> done;
+      int dev = 0;
+      CUDA_TRY(cudaGetDevice(&dev));
+      std::lock_guard<std::mutex> lock(mu);
+      if (!done.count(dev)) {
+        CUDA_TRY(cudaFuncSetAttribute(graph_build_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (SMALL_MAX_NODES + 1) * (int)sizeof(int)));
+        done.insert(dev);
+      }
     }
-    graph_build_small_kernel<<<1, SMALL_NT, bytes, st>>>(edge_index, E, N, frames, perm, src, dst, dst_ptr, src_pos, src_ptr, fbar);
+    graph_build_small_kernel<<<1, SMALL_NT, bytes, st>>>(edge_index, E, N, frames, perm, src, dst, dst_ptr, src_pos, src_ptr, fbar, (int*)workspace);
     gcp_note_launches(1);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -189,7 +236,7 @@ int gcpnet_graph_build(const int64_t* edge_index, int64_t E64, int64_t N64, cons
   size_t cub_bytes = workspace_bytes - 4 * seg;
   int bits = 1;
   while ((1LL << bits) < N64) ++bits;
-  edge_keys_kernel<<<(E + T - 1) / T, T, 0, st>>>(edge_index, E, row32, col32, iota);
+  edge_keys_kernel<<<(E + T - 1) / T, T, 0, st>>>(edge_index, E, N, row32, col32, iota);
   gcp_note_launches(1);
   // stable sort by destination: positions keep the caller's relative order inside a segment
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, col32, dst, iota, perm, E, 0, bits, st));

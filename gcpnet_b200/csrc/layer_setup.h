@@ -143,10 +143,11 @@ inline LayerOps layer_ops(const gcpnet_layer& l, int edge_cap = EDGE_CAP_FLOATS,
   return o;
 }
 
-inline PackParams make_pack_params(const LayerOps& o, float* blob, bool skip_messages = false) {
+inline PackParams make_pack_params(const LayerOps& o, float* blob, bool skip_messages = false, bool skip_node = false) {
   PackParams p{};
   p.blob = blob;
   for (int k = 0; k < o.L && !skip_messages; ++k) p.ops[p.n++] = o.msg[k];  // the tensor-core path packs its own message tiles
+  if (skip_node) return p;  // GCPMessagePassing alone: no feed-forward / position-update weights
   p.ops[p.n++] = o.ff0; p.ops[p.n++] = o.ff1;
   if (o.has_pos) p.ops[p.n++] = o.pu;
   return p;

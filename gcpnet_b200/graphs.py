@@ -8,9 +8,13 @@ L x backward -- can be recorded once and replayed with a single launch.  At NMS-
     step = GraphedStep(lambda b: loss_fn(model(b)), static_batch)
     loss = step(new_batch)        # copies new_batch into the static buffers, replays, returns the loss tensor
 
-The callable must be shape-stable (same N, E per replay: bucket / pad batches as the north-star
-prescribes) and must not synchronise.  Parameter gradients land in ``p.grad`` (static tensors that every
-replay overwrites), ready for an optimizer step or an NCCL all-reduce after the replay.
+The callable must be shape-stable (same N, E per replay: bucket / pad batches with ``gcpnet_b200.bucketing``
+as the north-star prescribes) and must not synchronise.  Parameter gradients land in ``p.grad`` (static tensors
+that every replay overwrites).  With ``model=`` the gradients of all fused layers live in ONE flat buffer
+(``gcpnet_b200.ddp.FlatGradients``): the layers write into it directly, ``p.grad`` are views, and with a process group
+the per-layer NCCL all-reduces are captured inside the graph on the library's side stream, overlapping with the
+backward of the layers below.  ``optimizer.zero_grad(set_to_none=True)`` between replays is tolerated: every call
+re-attaches the captured gradient tensors.
 """
 from __future__ import annotations
 
@@ -38,12 +42,18 @@ def prepack(layers, num_nodes: int, num_edges: int) -> None:
 
 class GraphedStep:
     def __init__(self, fn: Callable[[Dict[str, torch.Tensor]], torch.Tensor], static_batch: Dict[str, torch.Tensor],
-                 params: Optional[Iterable[torch.nn.Parameter]] = None, warmup: int = 3):
+                 params: Optional[Iterable[torch.nn.Parameter]] = None, warmup: int = 3, model=None, process_group=None):
         self.fn = fn
         self.batch = static_batch
         self._copy_stream = None
         self._staged = False
         self.params = list(params) if params is not None else []
+        self.flat = None
+        if model is not None:
+            from .ddp import FlatGradients
+            self.flat = FlatGradients(model, process_group=process_group)
+            if not self.params:
+                self.params = [p for p, _ in self.flat._views]
         lib = _lib.load()
         lib.gcpnet_profile_enable(0)  # per-kernel events are not capturable
         side = torch.cuda.Stream()
@@ -62,11 +72,20 @@ class GraphedStep:
         # (GCPNET_MAIN_PRIORITY=0 restores equal priorities for A/B runs)
         cap = torch.cuda.Stream(priority=int(os.environ.get("GCPNET_MAIN_PRIORITY", "-1")))
         with torch.cuda.graph(self.graph, stream=cap):
+            if self.flat is not None:
+                self.flat.zero_others()
             self.loss = fn(self.batch)
             self.loss.backward()
+            if self.flat is not None:
+                self.flat.all_reduce()  # parameters outside the fused layers (the layers' slices went per layer)
         clear_graph_cache()
+        # the tensors every replay writes the gradients into: re-attached in __call__ if a caller dropped them
+        self._grads = [(p, p.grad) for p in self.params]
 
     def _zero_grads(self):
+        if self.flat is not None:
+            self.flat.attach()
+            return
         for p in self.params:
             p.grad = None
         for t in self.batch.values():
@@ -102,5 +121,8 @@ class GraphedStep:
                 self.batch[k].detach().copy_(t, non_blocking=True)
             self._stage_free.record(cur)
             self._staged = False
+        for p, g in self._grads:  # optimizer.zero_grad(set_to_none=True) between replays: put the static tensors back
+            if p.grad is not g:
+                p.grad = g
         self.graph.replay()
         return self.loss

@@ -75,13 +75,21 @@ class GraphViews:
 
 _GRAPH_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
 _GRAPH_CACHE_SIZE = 8
+_GRAPH_CACHE_MODE = [False]  # True while the entries were built under CUDA-graph capture
 
 
 def graph_views(edge_index: torch.Tensor, frames: torch.Tensor, num_nodes: int) -> GraphViews:
     """Build (or fetch) the graph views.  Frames are computed once per batch in the reference
     (gcpnet_nms_module.py:132) and every layer of the model sees the same tensors, so the key is
     the identity + version of the two tensors; entries hold references to them so a pointer
-    cannot be recycled while its entry lives."""
+    cannot be recycled while its entry lives.  The key relies on ``Tensor._version``: writes that do not bump it
+    (``.data.copy_``, DLPack consumers, custom kernels) need ``clear_graph_cache()``.  Entries never cross a CUDA-graph
+    capture boundary: views built under capture live in the graph's memory pool and are only valid inside that graph,
+    and a capture must rebuild its views as graph nodes (replays re-run them on the new contents of the static inputs)."""
+    capturing = torch.cuda.is_current_stream_capturing()
+    if capturing != _GRAPH_CACHE_MODE[0]:
+        _GRAPH_CACHE.clear()
+        _GRAPH_CACHE_MODE[0] = capturing
     key = (edge_index.data_ptr(), edge_index._version, frames.data_ptr(), frames._version, int(num_nodes),
            int(edge_index.shape[1]), edge_index.device.index, _stream())
     hit = _GRAPH_CACHE.get(key)
@@ -137,7 +145,9 @@ class GCP2Params(nn.Module):
         raise RuntimeError("GCP2Params only holds parameters; the fused layer kernels evaluate it")
 
 
-class _MessagePassingParams(nn.Module):
+class _MessageParams(nn.Module):
+    """``interaction.message_fusion.{k}`` of a GCPInteractions layer (the fused layer kernels evaluate the stack)."""
+
     def __init__(self, mods):
         super().__init__()
         self.message_fusion = nn.ModuleList([GCP2Params(*m[1:6]) for m in mods])
@@ -152,34 +162,63 @@ class _LayerNormParams(nn.Module):
 # ------------------------------------------------------------------------------------------
 # side stream: parameter-gradient post-processing overlaps with the next layer's backward
 # ------------------------------------------------------------------------------------------
-_SIDE = {"stream": None, "keep": [], "queued": False, "enabled": True}
+# One record per device.  The library forks the work that only feeds the PARAMETER gradient to this stream
+# (include/gcpnet_b200.h, gcpnet_set_side_stream).  Who may read those gradients when:
+#   * default: `_LayerFn.backward` makes the caller's stream wait for the layer's side work (gcpnet_join) BEFORE it hands
+#     the gradients to autograd -- AccumulateGrad, hooks and DDP reducers may read them at once;
+#   * gradient sink (`gcpnet_b200.ddp.FlatGradients`, used by GraphedStep): the layer writes its gradients straight into
+#     the caller's flat buffer and returns nothing to autograd, so nobody reads them during the backward pass; the join is
+#     deferred to one end-of-backward callback and the side work overlaps with the next layer's backward.
+_SIDE = {}
+
+
+def _side(dev: Optional[int] = None) -> dict:
+    dev = torch.cuda.current_device() if dev is None else dev
+    st = _SIDE.get(dev)
+    if st is None:
+        st = _SIDE[dev] = {"stream": None, "keep": [], "queued": False, "after_join": []}
+    return st
+
+
+def side_stream() -> Optional["torch.cuda.Stream"]:
+    """The library's side stream of the current device (None before the first backward pass)."""
+    return _side()["stream"]
 
 
 def _side_stream_setup() -> None:
     """Create the side stream once (outside any CUDA-graph capture: the first backward of a process is a warm-up)."""
-    if _SIDE["stream"] is None and _SIDE["enabled"] and not torch.cuda.is_current_stream_capturing():
-        st = torch.cuda.Stream(priority=int(os.environ.get("GCPNET_SIDE_PRIORITY", "0")))
-        _lib.check(_lib.load().gcpnet_set_side_stream(st.cuda_stream), "gcpnet_set_side_stream")
-        _SIDE["stream"] = st
+    st = _side()
+    if st["stream"] is None and not torch.cuda.is_current_stream_capturing():
+        stream = torch.cuda.Stream(priority=int(os.environ.get("GCPNET_SIDE_PRIORITY", "0")))
+        _lib.check(_lib.load().gcpnet_set_side_stream(stream.cuda_stream), "gcpnet_set_side_stream")
+        st["stream"] = stream
 
 
 def _join_side() -> None:
-    """End of a backward pass: the current stream waits for everything forked to the side stream."""
-    _SIDE["queued"] = False
-    if _SIDE["stream"] is not None:
-        _lib.check(_lib.load().gcpnet_join(_stream()), "gcpnet_join")
-    _SIDE["keep"].clear()
+    """The current stream waits for everything forked to the side stream so far; deferred callbacks run after it."""
+    st = _side()
+    st["queued"] = False
+    try:
+        if st["stream"] is not None:
+            _lib.check(_lib.load().gcpnet_join(_stream()), "gcpnet_join")
+        for fn in st["after_join"]:
+            fn()
+    finally:
+        st["after_join"].clear()
+        st["keep"].clear()
 
 
-def _after_backward_call(tensors) -> None:
-    """Keep the workspaces the side stream still reads alive until the join; make sure the join is queued."""
-    if _SIDE["stream"] is None:
-        return
-    _SIDE["keep"].extend(tensors)
-    if not _SIDE["queued"]:
+def _defer_join(tensors, after_join=None) -> None:
+    """Keep the workspaces the side stream still reads alive until the join; make sure ONE join is queued at the end of the
+    running backward pass (or join right away when called outside of one)."""
+    st = _side()
+    st["keep"].extend(tensors)
+    if after_join is not None:
+        st["after_join"].append(after_join)
+    if not st["queued"]:
         try:
             torch.autograd.Variable._execution_engine.queue_callback(_join_side)
-            _SIDE["queued"] = True
+            st["queued"] = True
         except RuntimeError:  # not inside an autograd backward pass (direct call): join right away
             _join_side()
 
@@ -207,7 +246,7 @@ class _LayerFn(torch.autograd.Function):
         saved_node = f32(plan.saved_node_floats) if need_grad else None
         pre = mod._prepacked
         mod._prepacked = None
-        if pre is not None and pre[0] == (N, E, training, tuple(p.data_ptr() for p in params)) and pre[1].device == dev:
+        if pre is not None and pre[0] == (N, E, training, tuple((p.data_ptr(), p._version) for p in params)) and pre[1].device == dev:
             packed, ready = pre[1], 1
             torch.cuda.current_stream().wait_event(pre[2])  # packed on the side stream at the start of the step
         else:
@@ -244,7 +283,11 @@ class _LayerFn(torch.autograd.Function):
         layer = mod._layer_struct(params, ctx.training)
         f32 = lambda n: torch.empty(max(int(n), 1), dtype=torch.float32, device=dev)
         g_h, g_chi, g_e, g_xi = torch.empty_like(h), torch.empty_like(chi), torch.empty_like(e), torch.empty_like(xi)
-        g_params = f32(spec.n_params)
+        sink = mod._grad_sink
+        if sink is not None and (sink.numel() != spec.n_params or sink.device != dev or sink.dtype != torch.float32
+                                 or not sink.is_contiguous()):
+            raise RuntimeError("gcpnet_b200: gradient sink does not match this layer's flat parameter layout")
+        g_params = sink if sink is not None else f32(spec.n_params)
         ws_agg, ws_edge = f32(plan.agg_cotangent_floats), f32(plan.edge_cotangent_floats)
         ws_ep, ws_np = f32(plan.edge_partial_floats), f32(plan.node_partial_floats)
         io = _cabi.BackwardIO(_ptr(h), _ptr(chi), _ptr(e), _ptr(xi), _ptr(frames), _ptr(saved_edge), _ptr(saved_node),
@@ -252,10 +295,19 @@ class _LayerFn(torch.autograd.Function):
                               _ptr(g_xi), _ptr(g_params), _ptr(ws_agg), _ptr(ws_edge), _ptr(ws_ep), _ptr(ws_np), _ptr(packed))
         _lib.check(lib.gcpnet_layer_backward(C.byref(layer), C.byref(gv.struct), C.byref(plan), C.byref(io), _stream()),
                    "gcpnet_layer_backward")
-        _after_backward_call((ws_agg, ws_edge, ws_ep, ws_np, saved_edge, saved_node, packed, h, chi, g_params))
         if gv.E == 0:
             g_e.zero_()
             g_xi.zero_()
+        g_pos = g_out_pos if ctx.has_pos else None  # node_pos' = node_pos + update (gcpnet.py:1258)
+        if sink is not None:
+            # nobody reads the parameter gradients during this backward pass: deferred join, side work overlaps
+            hook = mod._grad_hook
+            _defer_join((ws_agg, ws_edge, ws_ep, ws_np, saved_edge, saved_node, packed, h, chi),
+                        None if hook is None else hook(mod, sink))
+            return (None, None, g_h, g_chi, g_e, g_xi, None, g_pos) + (None,) * len(params)
+        # autograd (AccumulateGrad, tensor hooks, DDP reducer) may read the gradients as soon as this returns
+        if _side()["stream"] is not None:
+            _lib.check(lib.gcpnet_join(_stream()), "gcpnet_join")
         pgrads = []
         for name in spec.names:
             o = spec.offsets[name]
@@ -264,8 +316,173 @@ class _LayerFn(torch.autograd.Function):
             for d in shp:
                 n *= d
             pgrads.append(g_params[o:o + n].view(shp))
-        g_pos = g_out_pos if ctx.has_pos else None  # node_pos' = node_pos + update (gcpnet.py:1258)
         return (None, None, g_h, g_chi, g_e, g_xi, None, g_pos, *pgrads)
+
+
+# ------------------------------------------------------------------------------------------
+# GCPMessagePassing on its own (message + aggregate)
+# ------------------------------------------------------------------------------------------
+def _nonlinearities(cfg):
+    nl = _get(cfg, "nonlinearities", None)
+    if nl is None:
+        nl = (_get(cfg, "scalar_nonlinearity", "relu"), _get(cfg, "vector_nonlinearity", None))
+    return nl
+
+
+def _check_gcp_flags(cfg, who: str) -> None:
+    """Flag combinations of the reference's GCP2 the kernels do not cover raise (no eager fallback)."""
+    def unsupported(what):
+        raise NotImplementedError(f"gcpnet_b200.{who}: {what} is not covered by the sm_100a kernels "
+                                  "(and there is no eager fallback)")
+    sel = _get(cfg, "selected_GCP", None)
+    sel_name = getattr(getattr(sel, "func", sel), "__name__", None) or str(_get(sel, "_target_", "") or "")
+    if sel is not None and sel_name and not sel_name.endswith("GCP2"):
+        unsupported(f"selected_GCP={sel_name} (only GCP2)")
+    if not bool(_get(cfg, "vector_gate", True)):
+        unsupported("vector_gate=False")
+    if int(_get(cfg, "scalar_gate", 0) or 0) > 0:
+        unsupported("scalar_gate > 0")
+    for flag in ("frame_gate", "sigma_frame_gate", "vector_frame_residual", "ablate_frame_updates", "ablate_scalars",
+                 "ablate_vectors"):
+        if bool(_get(cfg, flag, False)):
+            unsupported(f"cfg.{flag}=True")
+
+
+class _MPFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod: "GCPMessagePassing", gv: GraphViews, h, chi, e, xi, frames, *params):
+        lib = _lib.load()
+        spec = mod.spec
+        N, E, dev = gv.N, gv.E, h.device
+        layer = mod._layer_struct(params)
+        plan = _cabi.Plan()
+        _lib.check(lib.gcpnet_layer_plan(C.byref(layer), N, E, C.byref(plan)), "gcpnet_layer_plan")
+        need_grad = mod._grad_mode and any(ctx.needs_input_grad)
+        f32 = lambda n: torch.empty(max(int(n), 1), dtype=torch.float32, device=dev)
+        W = spec.s + 3 * spec.v
+        agg = torch.empty((N, W), dtype=torch.float32, device=dev)
+        msg, packed = f32(plan.msg_floats), f32(plan.packed_floats)
+        saved_edge = f32(plan.saved_edge_floats) if need_grad else None
+        io = _cabi.ForwardIO(_ptr(h), _ptr(chi), _ptr(e), _ptr(xi), _ptr(frames), None, None, None, None, _ptr(msg),
+                             _ptr(saved_edge), None, _ptr(packed), 0, 0)
+        _lib.check(lib.gcpnet_message_passing_forward(C.byref(layer), C.byref(gv.struct), C.byref(plan), C.byref(io), _ptr(agg),
+                                                      _stream()), "gcpnet_message_passing_forward")
+        ctx.mod, ctx.gv, ctx.plan = mod, gv, plan
+        ctx.save_for_backward(h, chi, e, xi, frames, saved_edge, packed, *params)
+        return agg
+
+    @staticmethod
+    def backward(ctx, g_agg):
+        lib = _lib.load()
+        _side_stream_setup()
+        mod, gv, plan = ctx.mod, ctx.gv, ctx.plan
+        spec = mod.spec
+        h, chi, e, xi, frames, saved_edge, packed, *params = ctx.saved_tensors
+        if saved_edge is None:
+            raise RuntimeError("gcpnet_b200: backward called on a forward that ran without saved activations")
+        dev = h.device
+        layer = mod._layer_struct(params)
+        f32 = lambda n: torch.empty(max(int(n), 1), dtype=torch.float32, device=dev)
+        g_h, g_chi, g_e, g_xi = torch.empty_like(h), torch.empty_like(chi), torch.zeros_like(e), torch.zeros_like(xi)
+        g_params = f32(spec.n_edge_params)
+        ws_edge, ws_ep = f32(plan.edge_cotangent_floats), f32(plan.edge_partial_floats)
+        io = _cabi.BackwardIO(_ptr(h), _ptr(chi), _ptr(e), _ptr(xi), _ptr(frames), _ptr(saved_edge), None, None, None, None,
+                              _ptr(g_h), _ptr(g_chi), _ptr(g_e), _ptr(g_xi), _ptr(g_params), None, _ptr(ws_edge), _ptr(ws_ep),
+                              None, _ptr(packed))
+        _lib.check(lib.gcpnet_message_passing_backward(C.byref(layer), C.byref(gv.struct), C.byref(plan), C.byref(io),
+                                                       _ptr(g_agg.contiguous()), _stream()), "gcpnet_message_passing_backward")
+        if _side()["stream"] is not None:
+            _lib.check(lib.gcpnet_join(_stream()), "gcpnet_join")
+        pgrads = []
+        for name in spec.names[:len(params)]:
+            o, shp = spec.offsets[name], spec.shapes[name]
+            n = 1
+            for d in shp:
+                n *= d
+            pgrads.append(g_params[o:o + n].view(shp))
+        return (None, None, g_h, g_chi, g_e, g_xi, None, *pgrads)
+
+
+class GCPMessagePassing(nn.Module):
+    """``GCPMessagePassing`` (gcpnet.py:838-960): the residual stack of message GCPs over ``[h_row | e | h_col]`` and the
+    per-destination reduction.  Reference constructor; ``input_dims`` must equal ``output_dims`` (what every caller in the
+    reference passes, gcpnet.py:991-998)."""
+
+    def __init__(self, input_dims, output_dims, edge_dims, cfg, mp_cfg, reduce_function: str = "mean",
+                 use_scalar_message_attention: bool = False, aggregate_with_row: bool = False, nonlinearity_slope: float = 1e-2):
+        super().__init__()
+        node_dims = ScalarVector(int(input_dims[0]), int(input_dims[1]))
+        if tuple(int(d) for d in output_dims) != tuple(node_dims):
+            raise NotImplementedError("gcpnet_b200.GCPMessagePassing: output_dims != input_dims is not covered")
+        if use_scalar_message_attention or aggregate_with_row:
+            raise NotImplementedError("gcpnet_b200.GCPMessagePassing: use_scalar_message_attention / aggregate_with_row "
+                                      "(GCPInteractions2 only) are not covered")
+        if reduce_function not in ("mean", "add", "sum"):
+            raise NotImplementedError(f"gcpnet_b200.GCPMessagePassing: reduce_function={reduce_function!r}")
+        _check_gcp_flags(cfg, "GCPMessagePassing")
+        self.node_dims = node_dims
+        self.edge_dims = ScalarVector(int(edge_dims[0]), int(edge_dims[1]))
+        self.reduce_function = reduce_function
+        nl = _nonlinearities(cfg)
+        self.spec = _cabi.LayerSpec(
+            node_dims, self.edge_dims, num_message_layers=int(_get(mp_cfg, "num_message_layers", 8)),
+            bottleneck=int(_get(cfg, "bottleneck", 1)), default_bottleneck=int(_get(cfg, "default_bottleneck", 1)),
+            vector_residual=bool(_get(cfg, "vector_residual", False)),
+            default_vector_residual=bool(_get(cfg, "default_vector_residual", False)),
+            scalar_nonlinearity=nl[0], vector_nonlinearity=nl[1], nonlinearity_slope=float(nonlinearity_slope),
+            use_residual_message_gcp=bool(_get(mp_cfg, "use_residual_message_gcp", True)),
+            enable_e3_equivariance=bool(_get(cfg, "enable_e3_equivariance", False)), reduce_function=reduce_function)
+        for m in self.spec.message_mods:
+            if not 1 <= m[5] <= 16:
+                raise NotImplementedError(f"gcpnet_b200.GCPMessagePassing: hidden vector dim {m[5]} (supported: 1..16)")
+        self.message_fusion = nn.ModuleList([GCP2Params(*m[1:6]) for m in self.spec.message_mods])
+        self._names = [n[len("interaction."):] for n in self.spec.names[:7 * self.spec.L]]
+        self._param_list = None
+        self._struct_cache = None
+
+    def _params_in_order(self):
+        if self._param_list is None:
+            table = dict(self.named_parameters())
+            self._param_list = [table[n] for n in self._names]
+        return self._param_list
+
+    def _apply(self, fn, *a, **k):
+        self._param_list = None
+        self._struct_cache = None
+        return super()._apply(fn, *a, **k)
+
+    def _layer_struct(self, params) -> _cabi.Layer:
+        ptrs = tuple(p.data_ptr() for p in params)
+        if self._struct_cache is not None and self._struct_cache[0] == ptrs:
+            return self._struct_cache[1]
+        table = dict(zip(self.spec.names, ptrs))  # message_fusion.* come first in the flat layout
+        layer = self.spec.make_layer(lambda n: table.get(n, 0))
+        self._struct_cache = (ptrs, layer)
+        return layer
+
+    def forward(self, node_rep, edge_rep, edge_index, frames, node_mask=None):
+        if node_mask is not None:
+            raise NotImplementedError("gcpnet_b200.GCPMessagePassing: node_mask goes through GCPInteractions")
+        h, chi, e, xi = node_rep[0].contiguous(), node_rep[1].contiguous(), edge_rep[0].contiguous(), edge_rep[1].contiguous()
+        for t, name in ((h, "node scalars"), (chi, "node vectors"), (e, "edge scalars"), (xi, "edge vectors"),
+                        (edge_index, "edge_index"), (frames, "frames")):
+            _check_cuda(t, name)
+        N, E = int(h.shape[0]), int(edge_index.shape[1])
+        s, v = self.node_dims
+        se, ve = self.edge_dims
+        for t, want, name in ((h, (N, s), "node scalars"), (chi, (N, v, 3), "node vectors"), (e, (E, se), "edge scalars"),
+                              (xi, (E, ve, 3), "edge vectors"), (frames, (E, 3, 3), "frames")):
+            if tuple(t.shape) != want or t.dtype != torch.float32:
+                raise TypeError(f"gcpnet_b200.GCPMessagePassing: {name} must be float32 {want}, got {t.dtype} {tuple(t.shape)}")
+        if edge_index.dtype != torch.int64 or tuple(edge_index.shape) != (2, E):
+            raise TypeError("gcpnet_b200.GCPMessagePassing: edge_index must be int64 [2, E]")
+        if N == 0:
+            return ScalarVector(h.clone(), chi.clone())
+        edge_index, frames = edge_index.contiguous(), frames.contiguous()
+        gv = graph_views(edge_index, frames, N)
+        self._grad_mode = torch.is_grad_enabled()
+        agg = _MPFn.apply(self, gv, h, chi, e, xi, frames, *self._params_in_order())
+        return ScalarVector.recover(agg, v)
 
 
 # ------------------------------------------------------------------------------------------
@@ -332,7 +549,7 @@ class GCPInteractions(nn.Module):
                 unsupported(f"hidden vector dim {m[5]} of {m[0]} (supported: 1..16)")
 
         # parameters, in the reference's registration order and under its names
-        self.interaction = _MessagePassingParams(spec.message_mods)
+        self.interaction = _MessageParams(spec.message_mods)
         self.gcp_norm = nn.ModuleList([_LayerNormParams(node_dims.scalar) for _ in range(2)])
         self.feedforward_network = nn.ModuleList([GCP2Params(*m[1:6]) for m in spec.ff_mods])
         if spec.pos_mod:
@@ -340,6 +557,8 @@ class GCPInteractions(nn.Module):
         self._param_list = None
         self._struct_cache = None
         self._prepacked = None
+        self._grad_sink = None   # flat fp32 view the backward writes the parameter gradients into (gcpnet_b200.ddp)
+        self._grad_hook = None   # hook(layer, sink) -> callable run after the end-of-backward join (or None)
         self.register_buffer("_rng_counter", torch.zeros(1, dtype=torch.int64), persistent=False)
         _LAYER_SERIAL[0] += 1  # distinct dropout streams per layer, reproducible under torch.manual_seed
         self._seed = (int(torch.initial_seed()) * 0x9E3779B1 + _LAYER_SERIAL[0]) & 0x7FFFFFFFFFFFFFFF
@@ -390,7 +609,10 @@ class GCPInteractions(nn.Module):
                                              side.cuda_stream), "gcpnet_layer_pack")
             ev = torch.cuda.Event()
             ev.record(side)
-        self._prepacked = ((int(num_nodes), int(num_edges), training, tuple(p.data_ptr() for p in params)), packed, ev)
+        if side is not cur and not torch.cuda.is_current_stream_capturing():
+            packed.record_stream(side)  # allocated on the caller's stream, written on `side`
+        self._prepacked = ((int(num_nodes), int(num_edges), training, tuple((p.data_ptr(), p._version) for p in params)),
+                           packed, ev)
 
     # -- forward ----------------------------------------------------------------------------
     def forward(self, node_rep, edge_rep, edge_index, frames, node_rep_regressive=None, node_mask=None, node_pos=None):

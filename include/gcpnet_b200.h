@@ -176,6 +176,12 @@ int gcpnet_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, 
 int gcpnet_message_passing_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, const gcpnet_plan* plan,
                                    const gcpnet_forward_io* io, float* aggregate, void* stream);
 
+/* Backward of GCPMessagePassing.forward alone: g_aggregate[N][s+3v] = cotangent of the aggregate.  Uses of `io`:
+ * h, chi, e, xi, frames, saved_edge, packed (inputs); g_h, g_chi, g_e, g_xi (overwritten); g_params[0 .. n_edge_params)
+ * (the message_fusion.* gradients); ws_edge, ws_edge_partial (workspaces).  The node-side fields are ignored. */
+int gcpnet_message_passing_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, const gcpnet_plan* plan,
+                                    const gcpnet_backward_io* io, const float* g_aggregate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -146,3 +146,98 @@ def module_forward_backward(layer, case, cfg, inputs, device="cuda"):
     for k, p in layer.named_parameters():
         res["pgrad/" + k] = p.grad.cpu() if p.grad is not None else torch.zeros_like(p).cpu()
     return res
+
+
+# ------------------------------------------------------------------------------------------
+# train mode: the dropout masks the kernels draw, restated on the host
+# ------------------------------------------------------------------------------------------
+def device_uniform(seed: int, counter: int, idx: np.ndarray) -> np.ndarray:
+    """The counter-based uniform of the node kernels (rng_uniform, gcpnet_b200/csrc/node_kernels.cuh): splitmix64 of
+    (seed, counter, element) -> top 24 bits / 2^24, restated with numpy uint64 arithmetic (wraps mod 2^64)."""
+    with np.errstate(over="ignore"):
+        z = (np.uint64(seed & (2 ** 64 - 1)) + np.uint64(0x9E3779B97F4A7C15) * np.uint64(counter + 1)
+             + np.uint64(0xBF58476D1CE4E5B9) * (idx.astype(np.uint64) + np.uint64(1)))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+
+
+def dropout_masks(layer, num_nodes: int, counter: int):
+    """[(scalar_mask[N,s], vector_mask[N,v]) x 2] of already-scaled keep masks (0 or 1/(1-p)) that a TRAINING forward of
+    `layer` (gcpnet_b200.GCPInteractions) draws when its counter reads `counter`: GCPDropout semantics (comp/__init__.py:
+    97-135) -- scalars elementwise, vectors one draw per (node, channel) -- with the layer's seed."""
+    s, v = layer.node_dims
+    p = np.float32(layer.dropout_p)
+    keep = np.float32(1.0) / (np.float32(1.0) - p)
+    i = np.arange(num_nodes, dtype=np.uint64)[:, None]
+    ch = np.arange(s + v, dtype=np.uint64)[None, :]
+    out = []
+    for which in (0, 1):
+        u = device_uniform(layer._seed, counter, (i * np.uint64(s + v) + ch) * np.uint64(2) + np.uint64(which))
+        m = np.where(u >= p, keep, np.float32(0.0)).astype(np.float32)
+        out.append((torch.from_numpy(m[:, :s].copy()), torch.from_numpy(m[:, s:].copy())))
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# layer stacks (what bench.py times): L layers chained through (h, chi[, node_pos])
+# ------------------------------------------------------------------------------------------
+def stack_loss(h, chi, pos, cots):
+    ch, cchi, cpos = cots
+    loss = (h * ch).sum() + (chi * cchi).sum()
+    if pos is not None:
+        loss = loss + (pos * cpos).sum()
+    return loss
+
+
+def oracle_stack(cfg, params_list, inputs, cots, masks_list=None, dtype=torch.float32):
+    """L oracle layers; returns outputs, input gradients and per-layer parameter gradients."""
+    P = [{k: v.to(dtype).clone().requires_grad_(True) for k, v in p.items()} for p in params_list]
+    lv = {k: inputs[k].to(dtype).clone().requires_grad_(True) for k in ("h", "chi", "e", "xi")}
+    h, chi = lv["h"], lv["chi"]
+    pos = inputs["node_pos"].to(dtype) if cfg.updating_node_positions else None
+    frames = inputs["frames"].to(dtype)
+    for li, p in enumerate(P):
+        masks = None if masks_list is None else [(a.to(dtype), b.to(dtype)) for a, b in masks_list[li]]
+        out = O.interactions_forward(p, cfg, h, chi, lv["e"], lv["xi"], inputs["edge_index"], frames, node_pos=pos,
+                                     drop_masks=masks)
+        if cfg.updating_node_positions:
+            (h, chi), pos = out
+        else:
+            h, chi = out
+    stack_loss(h, chi, pos, [c.to(dtype) for c in cots]).backward()
+    res = {"out_h": h.detach(), "out_chi": chi.detach()}
+    if pos is not None:
+        res["out_pos"] = pos.detach()
+    for k, t in lv.items():
+        res["grad_" + k] = t.grad
+    for li, p in enumerate(P):
+        for k, t in p.items():
+            res[f"pgrad/{li}/{k}"] = t.grad if t.grad is not None else torch.zeros_like(t)
+    return res
+
+
+def module_stack(layers, cfg, inputs, cots, device="cuda"):
+    dev = torch.device(device)
+    lv = {k: inputs[k].to(dev, torch.float32).clone().requires_grad_(True) for k in ("h", "chi", "e", "xi")}
+    ei, frames = inputs["edge_index"].to(dev), inputs["frames"].to(dev, torch.float32)
+    h, chi = lv["h"], lv["chi"]
+    pos = inputs["node_pos"].to(dev, torch.float32) if cfg.updating_node_positions else None
+    for layer in layers:
+        if cfg.updating_node_positions:
+            (h, chi), pos = layer((h, chi), (lv["e"], lv["xi"]), ei, frames, node_pos=pos)
+        else:
+            h, chi = layer((h, chi), (lv["e"], lv["xi"]), ei, frames)
+    for layer in layers:
+        layer.zero_grad(set_to_none=True)
+    stack_loss(h, chi, pos, [c.to(dev) for c in cots]).backward()
+    res = {"out_h": h.detach().cpu(), "out_chi": chi.detach().cpu()}
+    if pos is not None:
+        res["out_pos"] = pos.detach().cpu()
+    for k, t in lv.items():
+        res["grad_" + k] = t.grad.cpu()
+    for li, layer in enumerate(layers):
+        for k, p in layer.named_parameters():
+            res[f"pgrad/{li}/{k}"] = p.grad.cpu() if p.grad is not None else torch.zeros_like(p).cpu()
+    return res

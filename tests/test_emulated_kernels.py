@@ -148,3 +148,30 @@ def test_emulated_dropout_masks_are_consistent(lib):
     assert rel_err(gh, lv["h"].grad.numpy()) < TOL and rel_err(ge, lv["e"].grad.numpy()) < TOL
     for k in L.spec.names:
         assert rel_err(L.param_grad(k), p[k].grad.numpy()) < TOL, k
+
+
+def test_host_restatement_of_the_dropout_generator_matches_the_kernels(lib):
+    """tests/helpers.dropout_masks (numpy splitmix64) == the masks the node tile code draws: the GPU train-mode parity
+    tests feed the restated masks to the oracle."""
+    from types import SimpleNamespace
+    from tests import emul_harness as EH
+    from tests.helpers import dropout_masks
+    cfg = O.OracleConfig(node_dims=(16, 4), edge_dims=(8, 2), num_message_layers=2, updating_node_positions=True,
+                         bottleneck=2, default_bottleneck=2)
+    params = O.random_layer_params(cfg, seed=61)
+    g = torch.Generator().manual_seed(8)
+    n = 37
+    ei = torch.randint(0, n, (2, 120), generator=g)
+    inputs = O.synthetic_layer_inputs(cfg, ei, n, seed=62)
+    seed = 0x7123456789ABCDEF
+    L = EH.EmulLayer(lib, cfg, params, inputs, training=True, p_drop=0.1, seed=seed)
+    L.ctr[0] = 5
+    L.forward()
+    s, v = cfg.node_dims
+    W, hs, hv = s + 3 * v, 4 * s, 2 * v
+    off = n * (2 * W + hs + hv + 3 * hv + s + v + s + 1 + 3)
+    m0 = L.saved_node[off: off + n * (s + v)].reshape(n, s + v)
+    m1 = L.saved_node[off + n * (s + v): off + 2 * n * (s + v)].reshape(n, s + v)
+    want = dropout_masks(SimpleNamespace(node_dims=(s, v), dropout_p=0.1, _seed=seed), n, 5)
+    assert np.array_equal(m0[:, :s], want[0][0].numpy()) and np.array_equal(m0[:, s:], want[0][1].numpy())
+    assert np.array_equal(m1[:, :s], want[1][0].numpy()) and np.array_equal(m1[:, s:], want[1][1].numpy())

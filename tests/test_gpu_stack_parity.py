@@ -1,0 +1,223 @@
+"""Parity of what bench.py times: train mode (dropout active) with the kernels' masks restated on the host, stacks of
+layers chained through (h, chi, node_pos) at the BASELINE shapes, the standalone GCPMessagePassing entry points, the
+sum/add reduction and the non-default nonlinearities.  Oracle = oracle/gcp_oracle.py; tolerance 1e-4 relative to the
+tensor's max magnitude (BASELINE.json north_star), gradients of deep ReLU stacks against the fp64 oracle with the fp32
+oracle's own distance as slack (tests/test_gpu_parity.py::_compare).  Needs a GPU (-m gpu)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gcp_oracle as O
+from oracle import golden_cases as GC
+from tests.helpers import (build_module, dropout_masks, module_forward_backward, module_stack, oracle_forward_backward,
+                           oracle_stack, rel_err)
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _with_tc(flag, fn):
+    from gcpnet_b200 import _lib
+    lib = _lib.load()
+    prev = lib.gcpnet_set_option(b"tc", int(flag))
+    try:
+        return fn()
+    finally:
+        lib.gcpnet_set_option(b"tc", prev)
+
+
+def _check(res, want, exact=None, tol=TOL, slack=4.0, keys=None):
+    for key in (keys or want.keys()):
+        if exact is None:
+            assert rel_err(res[key].numpy(), want[key].numpy()) < tol, key
+        else:
+            own = rel_err(want[key].numpy(), exact[key].numpy())
+            got = rel_err(res[key].numpy(), exact[key].numpy())
+            assert got < max(tol, slack * own), (key, got, own)
+
+
+def _cots(n, s, v, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(n, s, generator=g), torch.randn(n, v, 3, generator=g), torch.randn(n, 3, generator=g))
+
+
+def _nms_inputs(cfg, graphs, n, seed):
+    ei = O.nms_edge_index(graphs, n)
+    g = torch.Generator().manual_seed(seed)
+    pos = torch.randn(graphs * n, 3, generator=g, dtype=torch.float64) * (n / 5.0) ** (1.0 / 3.0)
+    return O.synthetic_layer_inputs(cfg, ei, graphs * n, seed=seed + 1, positions=pos)
+
+
+@pytest.mark.parametrize("tc", [1, 0])
+def test_train_mode_single_layer_matches_oracle_with_the_kernels_masks(tc):
+    """GCPDropout in train mode (comp/__init__.py:97-135): the masks the node kernels draw (counter-based generator,
+    restated in tests/helpers.py) fed to the oracle reproduce outputs AND all gradients, on both edge-kernel families."""
+    cfg = O.OracleConfig(node_dims=(64, 16), edge_dims=(32, 4), updating_node_positions=True, scalar_nonlinearity="silu")
+    inputs = _nms_inputs(cfg, 60, 5, seed=300)
+    n = 300
+    params = O.random_layer_params(cfg, seed=301)
+    layer = build_module(cfg, params, dropout=0.25).train()
+    for rep in range(2):  # the counter advances: a fresh mask every call, still reproducible
+        counter = int(layer._rng_counter.item())
+        masks = dropout_masks(layer, n, counter)
+        for m in masks:
+            frac = float((m[0] == 0).float().mean())
+            assert 0.2 < frac < 0.3
+        cots = _cots(n, 64, 16, 302 + rep)
+        res = _with_tc(tc, lambda: module_stack([layer], cfg, inputs, cots))
+        assert int(layer._rng_counter.item()) == counter + 1
+        want = oracle_stack(cfg, [params], inputs, cots, masks_list=[masks])
+        exact = oracle_stack(cfg, [params], inputs, cots, masks_list=[masks], dtype=torch.float64)
+        _check(res, want, exact)
+        for key in ("out_h", "out_chi", "out_pos"):
+            assert rel_err(res[key].numpy(), want[key].numpy()) < TOL, key
+
+
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_cfg2_four_layer_stack_matches_oracle(mode):
+    """BASELINE configs[1] (what bench.py times): 256 five-body graphs, 4 layers chained through node_pos, dropout 0.1."""
+    cfg = O.OracleConfig(node_dims=(64, 16), edge_dims=(32, 4), updating_node_positions=True)
+    inputs = _nms_inputs(cfg, 256, 5, seed=310)
+    n = 1280
+    plist = [O.random_layer_params(cfg, seed=311 + i) for i in range(4)]
+    layers = [build_module(cfg, p, dropout=0.1) for p in plist]
+    masks = None
+    if mode == "train":
+        for l in layers:
+            l.train()
+        masks = [dropout_masks(l, n, int(l._rng_counter.item())) for l in layers]
+    else:
+        for l in layers:
+            l.eval()
+    cots = _cots(n, 64, 16, 319)
+    res = module_stack(layers, cfg, inputs, cots)
+    want = oracle_stack(cfg, plist, inputs, cots, masks_list=masks)
+    exact = oracle_stack(cfg, plist, inputs, cots, masks_list=masks, dtype=torch.float64)
+    _check(res, want, exact, slack=6.0)
+    for key in ("out_h", "out_chi", "out_pos"):  # forward: always within 1e-4 of the fp32 oracle
+        assert rel_err(res[key].numpy(), want[key].numpy()) < TOL, key
+
+
+def test_cfg3_six_layer_stack_matches_oracle():
+    """BASELINE configs[2] shape: (100,16) hidden dims, ~10 in-edges per node with a radius-graph-like degree spread
+    (kNN sources, a third of the edges dropped at random), 6 layers, no positions."""
+    cfg = O.OracleConfig(node_dims=(100, 16), edge_dims=(32, 4), scalar_nonlinearity="silu")
+    ei, pos = O.knn_like_edge_index(8, 300, 15, seed=320)
+    g = torch.Generator().manual_seed(321)
+    ei = ei[:, torch.rand(ei.shape[1], generator=g) < 0.67]
+    n = 2400
+    inputs = O.synthetic_layer_inputs(cfg, ei, n, seed=322, positions=pos)
+    plist = [O.random_layer_params(cfg, seed=323 + i) for i in range(6)]
+    layers = [build_module(cfg, p).eval() for p in plist]
+    cots = _cots(n, 100, 16, 329)
+    res = module_stack(layers, cfg, inputs, cots)
+    want = oracle_stack(cfg, plist, inputs, cots)
+    exact = oracle_stack(cfg, plist, inputs, cots, dtype=torch.float64)
+    _check(res, want, exact, slack=6.0)
+    for key in ("out_h", "out_chi"):
+        assert rel_err(res[key].numpy(), want[key].numpy()) < TOL, key
+
+
+@pytest.mark.parametrize("dims,tc", [((64, 16), 1), ((64, 16), 0), ((100, 16), 0)])
+@pytest.mark.parametrize("reduce", ["add", "mean"])
+def test_message_passing_alone_forward_and_backward(dims, tc, reduce):
+    """gcpnet_message_passing_forward / _backward (GCPMessagePassing.forward, gcpnet.py:949-960) with reduce 'add'
+    (autoregressive layers, :984) and 'mean', against the oracle."""
+    import gcpnet_b200
+    from tests.helpers import module_cfgs
+    cfg = O.OracleConfig(node_dims=dims, edge_dims=(32, 4), reduce_function=reduce, scalar_nonlinearity="silu")
+    g = torch.Generator().manual_seed(330)
+    n, E = 150, 1100
+    ei = torch.randint(0, n - 3, (2, E), generator=g)
+    inputs = O.synthetic_layer_inputs(cfg, ei, n, seed=331)
+    params = {k: v for k, v in O.random_layer_params(cfg, seed=332).items() if k.startswith("interaction.")}
+    mcfg, lcfg = module_cfgs(cfg)
+    mp = gcpnet_b200.GCPMessagePassing(dims, dims, (32, 4), cfg=mcfg, mp_cfg=lcfg.mp_cfg, reduce_function=reduce)
+    mp.load_state_dict({k[len("interaction."):]: v for k, v in params.items()}, strict=True)
+    mp = mp.cuda()
+    cots = _cots(n, dims[0], dims[1], 333)
+    # oracle
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    lv = {k: inputs[k].clone().requires_grad_(True) for k in ("h", "chi", "e", "xi")}
+    ws, wV = O.message_passing(p, "interaction.", cfg, lv["h"], lv["chi"], lv["e"], lv["xi"], ei, inputs["frames"])
+    ((ws * cots[0]).sum() + (wV * cots[1]).sum()).backward()
+    # product
+    dv = {k: inputs[k].cuda().requires_grad_(True) for k in ("h", "chi", "e", "xi")}
+
+    def run():
+        out = mp((dv["h"], dv["chi"]), (dv["e"], dv["xi"]), ei.cuda(), inputs["frames"].cuda())
+        ((out[0] * cots[0].cuda()).sum() + (out[1] * cots[1].cuda()).sum()).backward()
+        return out
+    out = _with_tc(tc, run)
+    assert rel_err(out[0].detach().cpu().numpy(), ws.detach().numpy()) < TOL
+    assert rel_err(out[1].detach().cpu().numpy(), wV.detach().numpy()) < TOL
+    for k in ("h", "chi", "e", "xi"):
+        assert rel_err(dv[k].grad.cpu().numpy(), lv[k].grad.numpy()) < TOL, k
+    for k, t in mp.named_parameters():
+        assert rel_err(t.grad.cpu().numpy(), p["interaction." + k].grad.numpy()) < TOL, k
+
+
+@pytest.mark.parametrize("act", ["leakyrelu", "selu", "sigmoid", "silu"])
+@pytest.mark.parametrize("dims", [(64, 16), (100, 16)])
+def test_other_scalar_nonlinearities(act, dims):
+    """get_nonlinearity (src/models/__init__.py:41-57): every scalar activation on both kernel families."""
+    cfg = O.OracleConfig(node_dims=dims, edge_dims=(32, 4), scalar_nonlinearity=act, nonlinearity_slope=0.05,
+                         updating_node_positions=dims[0] == 64)
+    g = torch.Generator().manual_seed(340)
+    n, E = 120, 800
+    ei = torch.randint(0, n, (2, E), generator=g)
+    inputs = O.synthetic_layer_inputs(cfg, ei, n, seed=341)
+    params = O.random_layer_params(cfg, seed=342)
+    case = dict(seed=343)
+    want = oracle_forward_backward(case, cfg, params, inputs)
+    exact = oracle_forward_backward(case, cfg, params, inputs, dtype=torch.float64)
+    layer = build_module(cfg, params).eval()
+    res = module_forward_backward(layer, case, cfg, inputs)
+    keys = [k for k in want if k != "loss"]
+    _check(res, want, exact, keys=keys)
+
+
+def test_vector_nonlinearity_runs_on_the_ffma_path():
+    """A non-identity vector nonlinearity (the gate reads act_v(T), gcpnet.py:386) is not composable into the tensor-core
+    batches: the plan falls back to the FFMA tiles, results still match."""
+    cfg = O.OracleConfig(node_dims=(64, 16), edge_dims=(32, 4), scalar_nonlinearity="silu", vector_nonlinearity="sigmoid")
+    g = torch.Generator().manual_seed(350)
+    n, E = 90, 500
+    ei = torch.randint(0, n, (2, E), generator=g)
+    inputs = O.synthetic_layer_inputs(cfg, ei, n, seed=351)
+    params = O.random_layer_params(cfg, seed=352)
+    case = dict(seed=353)
+    want = oracle_forward_backward(case, cfg, params, inputs)
+    layer = build_module(cfg, params).eval()
+    res = module_forward_backward(layer, case, cfg, inputs)
+    _check(res, want, keys=[k for k in want if k != "loss"])
+
+
+def test_gradient_accumulation_and_hooks_see_finished_gradients():
+    """Two backward passes accumulated into p.grad (AccumulateGrad reads the layer's gradient while the library's side
+    stream may still be working unless the layer joins it first) == the sum of two separate passes; a tensor hook on a
+    parameter reads the final value."""
+    cfg = O.OracleConfig(node_dims=(64, 16), edge_dims=(32, 4), updating_node_positions=True, scalar_nonlinearity="silu")
+    inputs = _nms_inputs(cfg, 200, 5, seed=360)
+    n = 1000
+    params = O.random_layer_params(cfg, seed=361)
+    layer = build_module(cfg, params).eval()
+    c1, c2 = _cots(n, 64, 16, 362), _cots(n, 64, 16, 363)
+    a = module_stack([layer], cfg, inputs, c1)
+    b = module_stack([layer], cfg, inputs, c2)
+    seen = {}
+    name0 = "interaction.message_fusion.3.scalar_out.weight"
+    hook = dict(layer.named_parameters())[name0].register_hook(lambda g: seen.setdefault("g", g.detach().clone()))
+    dev = torch.device("cuda")
+    layer.zero_grad(set_to_none=True)
+    for cots in (c1, c2):
+        lv = {k: inputs[k].to(dev).requires_grad_(True) for k in ("h", "chi", "e", "xi")}
+        (h, chi), pos = layer((lv["h"], lv["chi"]), (lv["e"], lv["xi"]), inputs["edge_index"].to(dev), inputs["frames"].to(dev),
+                              node_pos=inputs["node_pos"].to(dev))
+        ((h * cots[0].to(dev)).sum() + (chi * cots[1].to(dev)).sum() + (pos * cots[2].to(dev)).sum()).backward()
+    hook.remove()
+    torch.cuda.synchronize()
+    for k, p in layer.named_parameters():
+        want = a[f"pgrad/0/{k}"] + b[f"pgrad/0/{k}"]
+        assert rel_err(p.grad.cpu().numpy(), want.numpy()) < 1e-5, k
+    assert torch.equal(seen["g"].cpu(), a[f"pgrad/0/{name0}"])
