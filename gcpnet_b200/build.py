@@ -57,6 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libgcpnet_b200.so")
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("GCPNET_NVCC_FLAGS", "").split()  # e.g. -DGCP_STAMPS=1 for the stage-timing scripts
     objs, jobs = [], []
     for src in sources():
         obj = os.path.join(PKG, "build", os.path.basename(src) + ".o")

@@ -34,6 +34,11 @@
 #include <stdint.h>
 #include <string.h>
 
+// Development aid (clock64 stage stamps, scripts/tc_bwd_stamps.py): compiled out unless built with -DGCP_STAMPS=1.
+#ifndef GCP_STAMPS
+#define GCP_STAMPS 0
+#endif
+
 namespace gcp {
 
 #define GCP_HD __host__ __device__ __forceinline__
@@ -788,7 +793,7 @@ GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g,
   constexpr int IW = (NT <= 256) ? 8 : 4;
   (void)hdp;
   // development aid: stamps 0..8 = phase boundaries, 9..14 = inside the first scalar_out chunk
-#if GCP_DEVICE_CODE
+#if GCP_DEVICE_CODE && GCP_STAMPS
   int dbg_i = 0;
 #define GCP_BSTAMP() do { if (wp.dbg != nullptr && threadIdx.x == 0) wp.dbg[dbg_i] = clock64(); ++dbg_i; } while (0)
 #define GCP_BSTAMP_AT(i) do { if (wp.dbg != nullptr && threadIdx.x == 0 && c == 0) wp.dbg[i] = clock64(); } while (0)
@@ -987,7 +992,7 @@ GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g,
   }
   GCP_PHASE_END
   GCP_BSTAMP();
-#if GCP_DEVICE_CODE
+#if GCP_DEVICE_CODE && GCP_STAMPS
   if (wp.dbg != nullptr) wp.dbg += 16;
 #endif
 }

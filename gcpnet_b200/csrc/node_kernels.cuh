@@ -479,7 +479,7 @@ GCP_HDN void node_fwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
   }
 }
 
-#if GCP_DEVICE_CODE
+#if GCP_DEVICE_CODE && GCP_STAMPS
 #define GCP_NSTAMP(i) do { if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[320 + (i)] = clock64(); } while (0)
 #else
 #define GCP_NSTAMP(i) do { } while (0)

@@ -6,6 +6,12 @@
 #include "tc_edge.cuh"
 #include "tc_setup.h"
 
+// Development aid: clock64 stamps of CTA 0's stages (scripts/tc_bwd_stamps.py).  Compiled out of the shipped library
+// (they cost 4-8 % of the executed instructions); build with GCPNET_NVCC_FLAGS=-DGCP_STAMPS=1 to get them.
+#ifndef GCP_STAMPS
+#define GCP_STAMPS 0
+#endif
+
 namespace gcp {
 namespace tc {
 
@@ -140,6 +146,22 @@ __device__ __forceinline__ const float* ring_wait(const Ring& r, int pos) {
 __device__ __forceinline__ void bulk_store(float* gdst, const float* ssrc, int floats) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr(ssrc)), "r"((uint32_t)floats * 4u) : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// Tile images in global memory are COMPACT: of every 4-column slab (RP rows x 16 bytes in shared memory) only the first
+// `rows` rows -- the rows the tile really has -- are stored / loaded (small graphs run 32..48-row tiles: 3 x less traffic
+// than whole slabs).  One elected thread issues `nslab` bulk copies; stores form one bulk group.
+__device__ __forceinline__ void image_store(float* gdst, const float* ssrc, int nslab, int rows) {
+  const uint32_t bytes = (uint32_t)rows * 16u;
+  for (int j = 0; j < nslab; ++j)
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst + (size_t)j * rows * 4), "r"(smem_addr(ssrc + (size_t)j * SLAB)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void image_load(float* sdst, const float* gsrc, int nslab, int rows, unsigned long long* bar) {
+  const uint32_t b = smem_addr(bar), bytes = (uint32_t)rows * 16u;
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes * (uint32_t)nslab) : "memory");
+  for (int j = 0; j < nslab; ++j)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(sdst + (size_t)j * SLAB)), "l"(gsrc + (size_t)j * rows * 4), "r"(bytes), "r"(b) : "memory");
 }
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -417,7 +439,11 @@ __device__ __forceinline__ void gcp_forward_tile(const TcEdgeParams& p, int k, T
   const Who& w = c.w;
   float* Z = sm + p.ZBUF; float* V = sm + p.VBUF;
   const uint32_t tbase = c.tbase;
+#if GCP_STAMPS
   auto stamp = [&](int i) { if (p.dbg != nullptr && blockIdx.x == 0 && w.tid == 0) p.dbg[k * 16 + i] = clock64(); };
+#else
+  auto stamp = [](int) {};
+#endif
   const float* ps = nullptr; const float* pd = nullptr; const float* qs = nullptr; const float* qd = nullptr;
   stamp(0);
   if (k == 0) {
@@ -529,8 +555,8 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_fwd_kernel(const __grid_c
       gcp_forward_tile<CS>(p, k, c, rs, rw, k > 0 && p.residual, true, k == p.L - 1, q, live, src, dst, orig,
                            [&]() {
                              if (k > 0 && saved_t) {  // inputs of this GCP = outputs of the previous one (published by the barrier)
-                               bulk_store(saved_t + (size_t)(k - 1) * (p.s_img + p.v_img), Z, p.s_img);
-                               bulk_store(saved_t + (size_t)(k - 1) * (p.s_img + p.v_img) + p.s_img, V, p.v_img);
+                               image_store(saved_t + (size_t)(k - 1) * (p.s_img + p.v_img), Z, p.s >> 2, p.rows);
+                               image_store(saved_t + (size_t)(k - 1) * (p.s_img + p.v_img) + p.s_img, V, 3 * (PW >> 2), p.rows);
                              }
                            },
                            &smc);
@@ -556,37 +582,46 @@ __device__ __forceinline__ void hmma_tf32(float (&c)[4], uint32_t a0, uint32_t a
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-// c[b][16 x 8 block at (m0, n0 + 8 b)] += sum over the 128 tile rows e of A[e][m0 + .] * B[e][n0 + 8 b + .]   (A, B slab tiles)
+// c[b][16 x 8 block at (m0, n0 + 8 b)] += sum over the tile rows e < rows of A[e][m0 + .] * B[e][n0 + 8 b + .]   (A, B slab tiles)
 // NB column blocks share the A fragments; the three 3xTF32 terms keep separate accumulators (short dependency chains).
+// Straight-line body: explicit 32-bit shared addresses with immediate offsets, no branch between the fragment loads and
+// the MMAs (blocks beyond `nb` recompute block 0 and are dropped by the caller) -- with a per-block branch the compiler
+// re-derives the shared window and re-converges the warp before every mma.sync, which made the product latency-bound
+// (5.7 k cycles for 5 row steps, r2 stage stamps).
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
 template <int NB>
 __device__ __forceinline__ void wgrad_blocks(float (&c)[NB][4], const float* A, const float* B, int m0, int n0, int nb, int lane, int rows) {
   const int g = lane >> 2, t = lane & 3;
-  const float* a_row0 = A + slab_off(RP, t, m0 + g);
-  const float* a_row1 = A + slab_off(RP, t, m0 + g + 8);
-  const float* b_row[NB];
+  const uint32_t a0 = smem_addr(A + slab_off(RP, t, m0 + g)), a1 = smem_addr(A + slab_off(RP, t, m0 + g + 8));
+  uint32_t bb0[NB];
 #pragma unroll
-  for (int bb = 0; bb < NB; ++bb) b_row[bb] = B + slab_off(RP, t, n0 + 8 * (bb < nb ? bb : 0) + g);
+  for (int bb = 0; bb < NB; ++bb) bb0[bb] = smem_addr(B + slab_off(RP, t, n0 + 8 * (bb < nb ? bb : 0) + g));
   float c1[NB][4], c2[NB][4];
 #pragma unroll
   for (int bb = 0; bb < NB; ++bb)
 #pragma unroll
     for (int q = 0; q < 4; ++q) { c1[bb][q] = 0.f; c2[bb][q] = 0.f; }
-#pragma unroll 2
-  for (int k0 = 0; k0 < rows; k0 += 8) {  // rows beyond the tile hold zeros anyway
-    const float fa[4] = {a_row0[4 * k0], a_row1[4 * k0], a_row0[4 * (k0 + 4)], a_row1[4 * (k0 + 4)]};
+#pragma unroll 1
+  for (int k0 = 0; k0 < rows; k0 += 8) {  // 8 tile rows per step = 128 bytes inside a slab
+    const uint32_t ko = (uint32_t)k0 * 16u;
+    const float fa[4] = {lds_f32(a0 + ko), lds_f32(a1 + ko), lds_f32(a0 + ko + 64u), lds_f32(a1 + ko + 64u)};
+    float fb[NB][2];
+#pragma unroll
+    for (int bb = 0; bb < NB; ++bb) { fb[bb][0] = lds_f32(bb0[bb] + ko); fb[bb][1] = lds_f32(bb0[bb] + ko + 64u); }
     uint32_t ah[4], al[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) { ah[q] = __float_as_uint(fa[q]) & TF32_MASK; al[q] = __float_as_uint(fa[q] - __uint_as_float(ah[q])); }
 #pragma unroll
     for (int bb = 0; bb < NB; ++bb) {
-      if (bb < nb) {  // warp-uniform
-        const float fb0 = b_row[bb][4 * k0], fb1 = b_row[bb][4 * (k0 + 4)];
-        const uint32_t bh0 = __float_as_uint(fb0) & TF32_MASK, bh1 = __float_as_uint(fb1) & TF32_MASK;
-        const uint32_t bl0 = __float_as_uint(fb0 - __uint_as_float(bh0)), bl1 = __float_as_uint(fb1 - __uint_as_float(bh1));
-        hmma_tf32(c[bb], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
-        hmma_tf32(c1[bb], al[0], al[1], al[2], al[3], bh0, bh1);
-        hmma_tf32(c2[bb], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
-      }
+      const uint32_t bh0 = __float_as_uint(fb[bb][0]) & TF32_MASK, bh1 = __float_as_uint(fb[bb][1]) & TF32_MASK;
+      const uint32_t bl0 = __float_as_uint(fb[bb][0] - __uint_as_float(bh0)), bl1 = __float_as_uint(fb[bb][1] - __uint_as_float(bh1));
+      hmma_tf32(c[bb], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+      hmma_tf32(c1[bb], al[0], al[1], al[2], al[3], bh0, bh1);
+      hmma_tf32(c2[bb], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
     }
   }
 #pragma unroll
@@ -594,18 +629,25 @@ __device__ __forceinline__ void wgrad_blocks(float (&c)[NB][4], const float* A, 
 #pragma unroll
     for (int q = 0; q < 4; ++q) c[bb][q] += c1[bb][q] + c2[bb][q];
 }
-// fragment -> this CTA's partial block G[ld columns] at (m0, n0); rows >= mrows / columns >= ncols are dropped
-__device__ __forceinline__ void wgrad_store(const float (&c)[4], float* G, int ld, int m0, int n0, int mrows, int ncols, bool accumulate, int lane) {
+// previous partial of a 16 x 8 block (multi-tile CTAs accumulate)
+__device__ __forceinline__ void wgrad_fetch(float (&o)[4], const float* G, int ld, int m0, int n0, int mrows, int ncols, bool accumulate, int lane) {
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
     const int m = m0 + g + 8 * hh, n = n0 + 2 * t;
-    if (m < mrows && n < ncols) {  // ncols even
-      float2* dp = reinterpret_cast<float2*>(G + (size_t)m * ld + n);
-      float2 v = make_float2(c[2 * hh], c[2 * hh + 1]);
-      if (accumulate) { const float2 o = *dp; v.x += o.x; v.y += o.y; }
-      *dp = v;
-    }
+    float2 v = make_float2(0.f, 0.f);
+    if (accumulate && m < mrows && n < ncols) v = *reinterpret_cast<const float2*>(G + (size_t)m * ld + n);
+    o[2 * hh] = v.x; o[2 * hh + 1] = v.y;
+  }
+}
+// fragment (+ the previous partial `o`) -> this CTA's partial block G[ld columns] at (m0, n0); rows >= mrows / columns >= ncols are dropped
+__device__ __forceinline__ void wgrad_store(const float (&c)[4], const float (&o)[4], float* G, int ld, int m0, int n0, int mrows, int ncols, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int m = m0 + g + 8 * hh, n = n0 + 2 * t;
+    if (m < mrows && n < ncols)  // ncols even
+      *reinterpret_cast<float2*>(G + (size_t)m * ld + n) = make_float2(c[2 * hh] + o[2 * hh], c[2 * hh + 1] + o[2 * hh + 1]);
   }
 }
 
@@ -702,7 +744,11 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_c
     for (int k = p.L - 1; k >= 0; --k) {
       const TcGcp& g = p.g[k];
       const bool res = k > 0 && p.residual;
+#if GCP_STAMPS
       auto bstamp = [&](int i) { if (p.dbg != nullptr && blockIdx.x == 0 && w.tid == 0) p.dbg[(12 + k) * 16 + i] = clock64(); };
+#else
+      auto bstamp = [](int) {};
+#endif
       bstamp(0);
       // every reader of the Z / V / cotangent tiles of the previous GCP (weight-gradient products) is done
       wait_st();
@@ -711,16 +757,8 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_c
       if (k > 0) {
         if (c.uwarp == 0 && elect_one()) {
           const float* sp = saved_t + (size_t)(k - 1) * (p.s_img + p.v_img);
-          const uint32_t bar = smem_addr(ld_bar);
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)p.v_img * 4u) : "memory");
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(smem_addr(V)), "l"(sp + p.s_img), "r"((uint32_t)p.v_img * 4u), "r"(bar) : "memory");
-          if (k == p.L - 1) {  // first GCP of the tile: nobody prefetched its S image
-            const uint32_t zbar = smem_addr(ldz_bar);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(zbar), "r"((uint32_t)p.s_img * 4u) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_addr(Z)), "l"(sp), "r"((uint32_t)p.s_img * 4u), "r"(zbar) : "memory");
-          }
+          image_load(V, sp + p.s_img, 3 * (PW >> 2), p.rows, ld_bar);
+          if (k == p.L - 1) image_load(Z, sp, p.s >> 2, p.rows, ldz_bar);  // first GCP of the tile: nobody prefetched its S image
         }
         mbar_wait(ldz_bar, ldz_n & 1u);  // prefetched one GCP ahead: normally complete
         ++ldz_n;
@@ -831,19 +869,34 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_c
       {
         constexpr int NB = 4;
         const int mt = p.pw >> 4, nt = (g.kz + 7) >> 3, ng = (nt + NB - 1) / NB;
-        for (int pr = warp; pr < mt * ng; pr += 4 * CS) {
+        // warp 0 has just issued the data-gradient batch: when the other warps cover all blocks in one round it takes none
+        const int nw = 4 * CS, skip0 = (mt * ng <= nw - 1) ? 1 : 0;
+#if GCP_STAMPS
+        if (p.dbg != nullptr && blockIdx.x == 0 && w.tid == 32) p.dbg[(12 + k) * 16 + 12] = clock64();
+#endif
+        for (int pr = warp - skip0; pr >= 0 && pr < mt * ng; pr += nw) {
           const int m0 = 16 * (pr % mt), nb0 = NB * (pr / mt);
           const int nb = nt - nb0 < NB ? nt - nb0 : NB;
-          float cf[NB][4];
+          float cf[NB][4], old[NB][4];
 #pragma unroll
           for (int bb = 0; bb < NB; ++bb)
 #pragma unroll
             for (int q = 0; q < 4; ++q) cf[bb][q] = 0.f;
           wgrad_blocks<NB>(cf, GTG, Z, m0, 8 * nb0, nb, lane, p.rows);
+          // multi-tile CTAs accumulate: ALL previous partials are fetched before the first store (one L2 round trip, not one per block)
 #pragma unroll
           for (int bb = 0; bb < NB; ++bb)
-            if (bb < nb) wgrad_store(cf[bb], prow + b.off_tg[k], g.kz, m0, 8 * (nb0 + bb), p.pw, g.kz, accumulate, lane);
+            wgrad_fetch(old[bb], prow + b.off_tg[k], g.kz, m0, 8 * (nb0 + bb), p.pw, bb < nb ? g.kz : 0, accumulate, lane);
+#if GCP_STAMPS
+          if (p.dbg != nullptr && blockIdx.x == 0 && w.tid == 32) p.dbg[(12 + k) * 16 + 13] = clock64();
+#endif
+#pragma unroll
+          for (int bb = 0; bb < NB; ++bb)
+            if (bb < nb) wgrad_store(cf[bb], old[bb], prow + b.off_tg[k], g.kz, m0, 8 * (nb0 + bb), p.pw, g.kz, lane);
         }
+#if GCP_STAMPS
+        if (p.dbg != nullptr && blockIdx.x == 0 && w.tid == 32) p.dbg[(12 + k) * 16 + 14] = clock64();
+#endif
       }
       bstamp(5);
       wait_mma(c);
@@ -936,17 +989,12 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_c
                     make_idesc(128, 16, 0, 0), acc);
         if (elect_one()) {
           commit(c.mma_bar);
-          if (k > 1) {  // S image of the next GCP: the Z tile's readers (scalar batches, weight-gradient product) are done
-            const float* sp = saved_t + (size_t)(k - 2) * (p.s_img + p.v_img);
-            const uint32_t zbar = smem_addr(ldz_bar);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(zbar), "r"((uint32_t)p.s_img * 4u) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_addr(Z)), "l"(sp), "r"((uint32_t)p.s_img * 4u), "r"(zbar) : "memory");
-          }
+          if (k > 1)  // S image of the next GCP: the Z tile's readers (scalar batches, weight-gradient product) are done
+            image_load(Z, saved_t + (size_t)(k - 2) * (p.s_img + p.v_img), p.s >> 2, p.rows, ldz_bar);
           if (k == 0) {  // per-edge cotangents of message GCP 0's per-node products, for the node-level finish
             float* yp = b.Y + (size_t)tile * (b.y_img_g + b.y_img_v);
-            bulk_store(yp, GTG, b.y_img_g);
-            bulk_store(yp + b.y_img_g, GHDU, b.y_img_v);
+            image_store(yp, GTG, p.pw >> 2, p.rows);
+            image_store(yp + b.y_img_g, GHDU, 3 * (VN >> 2), p.rows);
           }
         }
         __syncwarp();
@@ -956,10 +1004,11 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_c
       if (warp >= 4 * CS - 4) {
         const int pr = warp - (4 * CS - 4);  // 2 x 2 blocks of 16 x 8
         const int m0 = 16 * (pr & 1), n0 = 8 * (pr >> 1);
-        float cf[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+        float cf[1][4] = {{0.f, 0.f, 0.f, 0.f}}, old[4];
 #pragma unroll 1
         for (int x = 0; x < 3; ++x) wgrad_blocks<1>(cf, GHDU + x * GPLANE, V + x * PLANE, m0, n0, 1, lane, p.rows);
-        wgrad_store(cf[0], prow + b.off_v[k], 16, m0, n0, VN, 16, accumulate, lane);
+        wgrad_fetch(old, prow + b.off_v[k], 16, m0, n0, VN, 16, accumulate, lane);
+        wgrad_store(cf[0], old, prow + b.off_v[k], 16, m0, n0, VN, 16, lane);
       }
       bstamp(9);
       wait_mma(c);
@@ -1013,9 +1062,9 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_bwd_kernel(const __grid_c
 __device__ __forceinline__ float y_at(const TcPostParams& p, int q, int c) {
   const int tile = q / p.rows, r = q - tile * p.rows;
   const float* yp = p.Y + (size_t)tile * (p.y_img_g + p.y_img_v);
-  if (c < p.pw) return __ldg(yp + ((c >> 2) * RP + r) * 4 + (c & 3));
+  if (c < p.pw) return __ldg(yp + ((c >> 2) * p.rows + r) * 4 + (c & 3));  // compact images: slab pitch = rows
   const int c2 = c - p.pw, x = c2 >> 5, cc = c2 & 31;
-  return __ldg(yp + p.y_img_g + x * GPLANE + ((cc >> 2) * RP + r) * 4 + (cc & 3));
+  return __ldg(yp + p.y_img_g + ((x * (VN >> 2) + (cc >> 2)) * p.rows + r) * 4 + (cc & 3));
 }
 // sum of column c of the Y rows of node i's outgoing (side 0) / incoming (side 1) edges, in CSR order; four edges are
 // fetched at a time so that their (dependent index -> value) loads overlap

@@ -166,8 +166,7 @@ inline TcPlan make_tc_plan(const gcpnet_layer& l, long long N, long long E) {
   if (col > 512) return no("tile does not fit tensor memory");
   p.tmem_cols = col <= 32 ? 32 : (col <= 64 ? 64 : (col <= 128 ? 128 : (col <= 256 ? 256 : 512)));
   // ---- saved activations: per tile, per GCP k < L-1: S image (s/4 slabs) + V image (3 planes)
-  p.s_img = (s / 4) * SLAB; p.v_img = 3 * PLANE;
-  p.saved_tile_stride = (long long)(L - 1) * (p.s_img + p.v_img);
+  // (sizes depend on the tile height: set below, once `rows` is known)
   // tile height: at most 128 rows, chosen so that the persistent CTAs (one per SM) all run the same number of tiles: w =
   // waves at full height, rows = E / (148 w) rounded up to 8 (>= 32).  The per-tile latency chain does not depend on the
   // row count; the row-proportional stages (weight-gradient products, TMEM / shared-memory traffic) shrink with it.
@@ -179,6 +178,9 @@ inline TcPlan make_tc_plan(const gcpnet_layer& l, long long N, long long E) {
     if (rows > TE) rows = TE;
   }
   p.rows = rows;
+  // compact images: only the tile's `rows` rows of every 4-column slab are stored (image_store / image_load)
+  p.s_img = (s / 4) * rows * 4; p.v_img = 3 * (PW / 4) * rows * 4;
+  p.saved_tile_stride = (long long)(L - 1) * (p.s_img + p.v_img);
   const long long tiles = (E + rows - 1) / rows;
   P.saved_floats = tiles * p.saved_tile_stride;
   P.pq_floats = N * (2 * p.pw + 192);
@@ -226,7 +228,7 @@ inline TcPlan make_tc_plan(const gcpnet_layer& l, long long N, long long E) {
     int po = 0;
     for (int k = 0; k < L; ++k) { b.off_tg[k] = po; po += p.pw * p.g[k].kz; b.off_v[k] = po; po += VN * 16; }
     b.partial_stride = rup(po, 32);
-    b.y_img_g = (p.pw / 4) * SLAB; b.y_img_v = 3 * (VN / 4) * SLAB;
+    b.y_img_g = (p.pw / 4) * rows * 4; b.y_img_v = 3 * (VN / 4) * rows * 4;
     b.reduce_mean = l.reduce_mean;
     P.y_floats = tiles * (long long)(b.y_img_g + b.y_img_v);
     P.partial_floats = (long long)P.grid * b.partial_stride;

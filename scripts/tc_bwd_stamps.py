@@ -32,7 +32,8 @@ for k in range(8):
 bn = ["sync+load+lo", "recompute", "epi1+sync", "issue_B3", "wgrad_tg", "wait_B3", "epi3+sync", "issue_B4", "wgrad_v", "wait_B4", "epi4"]
 for k in range(7, -1, -1):
     r = st[12 + k]
-    print(f"bwd GCP{k}: " + " ".join(f"{n}={int(r[i+1]-r[i])}" for i, n in enumerate(bn)) + f" | total {int(r[11]-r[0])}")
+    print(f"bwd GCP{k}: " + " ".join(f"{n}={int(r[i+1]-r[i])}" for i, n in enumerate(bn)) + f" | total {int(r[11]-r[0])}"
+          + f" | warp1 wgrad: start+{int(r[12]-r[3])} after epi1, blocks={int(r[13]-r[12])} store={int(r[14]-r[13])}")
 nn = ["load", "pos_bwd", "ln1_bwd", "reload", "ln0_fwd+act", "ff1_bwd", "ff0_bwd", "ln0_bwd", "store"]
 r = stamps.cpu()[320:330]
 print("node_bwd: " + " ".join(f"{n}={int(r[i+1]-r[i])}" for i, n in enumerate(nn)) + f" | total {int(r[9]-r[0])}")
