@@ -38,6 +38,7 @@ class Layer(C.Structure):
         ("message", Gcp2 * MAX_MESSAGE_LAYERS), ("ff0", Gcp2), ("ff1", Gcp2), ("pos_update", Gcp2),
         ("ln0_w", C.c_void_p), ("ln0_b", C.c_void_p), ("ln1_w", C.c_void_p), ("ln1_b", C.c_void_p),
         ("ln_grad_off", C.c_int32 * 4), ("n_edge_params", C.c_int32), ("n_node_params", C.c_int32),
+        ("pre_norm", C.c_int32), ("autoregressive", C.c_int32),
     ]
 
 
@@ -46,6 +47,8 @@ class Graph(C.Structure):
         ("num_nodes", C.c_int64), ("num_edges", C.c_int64),
         ("perm", C.c_void_p), ("src", C.c_void_p), ("dst", C.c_void_p), ("dst_ptr", C.c_void_p),
         ("src_pos", C.c_void_p), ("src_ptr", C.c_void_p), ("fbar", C.c_void_p),
+        ("fbar_pos", C.c_void_p), ("node_mask", C.c_void_p), ("gsrc", C.c_void_p), ("gdst", C.c_void_p),
+        ("vdst_ptr", C.c_void_p), ("vsrc_ptr", C.c_void_p), ("vsrc_pos", C.c_void_p), ("num_gather_rows", C.c_int64),
     ]
 
 
@@ -59,25 +62,28 @@ class Plan(C.Structure):
         ("edge_partial_floats", C.c_int64), ("node_partial_floats", C.c_int64),
         ("edge_cotangent_floats", C.c_int64), ("agg_cotangent_floats", C.c_int64), ("packed_floats", C.c_int64),
         ("tc_edge_path", C.c_int32), ("reserved", C.c_int32),
+        ("prenorm_floats", C.c_int64), ("prenorm_ws_floats", C.c_int64),
     ]
 
 
 class ForwardIO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("h", "chi", "e", "xi", "frames", "pos", "out_h", "out_chi", "out_pos", "msg", "saved_edge", "saved_node",
-                 "packed")] + [("packed_ready", C.c_int32), ("reserved", C.c_int32)]
+                 "packed")] + [("packed_ready", C.c_int32), ("reserved", C.c_int32)] + \
+        [(n, C.c_void_p) for n in ("h_gather", "chi_gather", "prenorm")]
 
 
 class BackwardIO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("h", "chi", "e", "xi", "frames", "saved_edge", "saved_node", "g_out_h", "g_out_chi", "g_out_pos",
                  "g_h", "g_chi", "g_e", "g_xi", "g_params", "ws_agg", "ws_edge", "ws_edge_partial", "ws_node_partial",
-                 "packed")]
+                 "packed", "h_gather", "chi_gather", "g_h_gather", "g_chi_gather", "prenorm", "ws_prenorm")]
 
 
 EXPORTS = (
     "gcpnet_version", "gcpnet_last_error", "gcpnet_launch_count", "gcpnet_profile_enable", "gcpnet_profile_read", "gcpnet_set_option", "gcpnet_debug_stamps", "gcpnet_set_side_stream", "gcpnet_join", "gcpnet_graph_workspace_bytes", "gcpnet_graph_build",
-    "gcpnet_localize", "gcpnet_layer_plan", "gcpnet_layer_pack", "gcpnet_layer_forward", "gcpnet_layer_backward",
+    "gcpnet_localize", "gcpnet_localize_masked", "gcpnet_graph_ar_workspace_bytes", "gcpnet_graph_build_autoregressive",
+    "gcpnet_graph_mask", "gcpnet_centralize", "gcpnet_decentralize", "gcpnet_layer_plan", "gcpnet_layer_pack", "gcpnet_layer_forward", "gcpnet_layer_backward",
     "gcpnet_message_passing_forward", "gcpnet_message_passing_backward",
 )
 
@@ -109,6 +115,20 @@ def declare(lib: C.CDLL) -> None:
         [C.c_void_p, C.c_size_t, C.c_void_p]
     lib.gcpnet_localize.restype = C.c_int
     lib.gcpnet_localize.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+    lib.gcpnet_localize_masked.restype = C.c_int
+    lib.gcpnet_localize_masked.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gcpnet_graph_ar_workspace_bytes.restype = C.c_size_t
+    lib.gcpnet_graph_ar_workspace_bytes.argtypes = [C.c_int64, C.c_int64]
+    lib.gcpnet_graph_build_autoregressive.restype = C.c_int
+    lib.gcpnet_graph_build_autoregressive.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p] + [C.c_void_p] * 11 + \
+        [C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.gcpnet_graph_mask.restype = C.c_int
+    lib.gcpnet_graph_mask.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(Graph),
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.gcpnet_centralize.restype = C.c_int
+    lib.gcpnet_centralize.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gcpnet_decentralize.restype = C.c_int
+    lib.gcpnet_decentralize.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gcpnet_layer_plan.restype = C.c_int
     lib.gcpnet_layer_plan.argtypes = [C.POINTER(Layer), C.c_int64, C.c_int64, C.POINTER(Plan)]
     lib.gcpnet_layer_pack.restype = C.c_int
@@ -157,7 +177,7 @@ class LayerSpec:
                  vector_residual=False, default_vector_residual=False, scalar_nonlinearity="relu",
                  vector_nonlinearity=None, nonlinearity_slope=1e-2, use_residual_message_gcp=True,
                  enable_e3_equivariance=False, reduce_function="mean", updating_node_positions=False,
-                 node_positions_weight=1.0):
+                 node_positions_weight=1.0, pre_norm=False, autoregressive=False):
         self.s, self.v = int(node_dims[0]), int(node_dims[1])
         self.se, self.ve = int(edge_dims[0]), int(edge_dims[1])
         self.L = int(num_message_layers)
@@ -165,6 +185,8 @@ class LayerSpec:
         self.e3 = bool(enable_e3_equivariance)
         self.reduce_mean = reduce_function == "mean"
         self.has_pos = bool(updating_node_positions)
+        self.pre_norm = bool(pre_norm)
+        self.autoregressive = bool(autoregressive)
         self.pos_weight = float(node_positions_weight)
         self.slope = float(nonlinearity_slope)
         a_s, a_v = ACT[_norm(scalar_nonlinearity)], ACT[_norm(vector_nonlinearity)]
@@ -258,6 +280,7 @@ class LayerSpec:
                                "gcp_norm.1.scalar_norm.weight", "gcp_norm.1.scalar_norm.bias")):
             l.ln_grad_off[i] = self.offsets[n]
         l.n_edge_params, l.n_node_params = self.n_edge_params, self.n_node_params
+        l.pre_norm, l.autoregressive = int(self.pre_norm), int(self.autoregressive)
         return l
 
 

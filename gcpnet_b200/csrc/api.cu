@@ -15,6 +15,7 @@
 #include "common.h"
 #include "layer_setup.h"
 #include "node_wgrad.cuh"
+#include "layernorm.cuh"
 
 using namespace gcp;
 
@@ -128,10 +129,27 @@ __global__ void node_cotangent_reduce_kernel(float* __restrict__ g_h, float* __r
   *out = acc;
 }
 
+// Autoregressive layers: the same sums over the rows of the [2N] gather table (row 2i = node_rep[i], row 2i+1 =
+// node_rep_regressive[i]); the direct cotangent of node i (node update, in dir_h / dir_chi) joins row 2i.
+__global__ void ar_cotangent_reduce_kernel(float* __restrict__ g_hg, float* __restrict__ g_chig, const float* __restrict__ dir_h,
+                                           const float* __restrict__ dir_chi, const float* __restrict__ grow, const float* __restrict__ gcol,
+                                           const int* __restrict__ vdst_ptr, const int* __restrict__ vsrc_ptr, const int* __restrict__ vsrc_pos,
+                                           int R, int s, int v3) {
+  const int W = s + v3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)R * W) return;
+  const int u = (int)(idx / W), f = (int)(idx - (long long)u * W);
+  float acc = 0.f;
+  if ((u & 1) == 0) acc = f < s ? dir_h[(size_t)(u >> 1) * s + f] : dir_chi[(size_t)(u >> 1) * v3 + (f - s)];
+  for (int q = vdst_ptr[u]; q < vdst_ptr[u + 1]; ++q) acc += __ldg(gcol + (size_t)q * W + f);
+  for (int q = vsrc_ptr[u]; q < vsrc_ptr[u + 1]; ++q) acc += __ldg(grow + (size_t)__ldg(vsrc_pos + q) * W + f);
+  if (f < s) g_hg[(size_t)u * s + f] = acc; else g_chig[(size_t)u * v3 + (f - s)] = acc;
+}
+
 // flat parameter gradient = fixed-order sum of the per-CTA partial rows
 // `skip`: ranges of the NODE part that the tiles did not produce (their operands were spilled for node_wgrad_kernel, which
 // writes those gradients itself): neither read nor written here
-struct SkipRanges { int n; int off[12], len[12]; };
+struct SkipRanges { int n; int off[14], len[14]; };
 __global__ void partial_reduce_kernel(float* __restrict__ out, const float* __restrict__ pe, int ne, int ge,
                                       const float* __restrict__ pn, int nn, int gn, const SkipRanges skip) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,8 +170,11 @@ static SkipRanges node_wgrad_ranges(const gcpnet_layer& l, const LayerPlan& lp) 
   const GcpOp* op[3] = {&lp.ops.ff0, &lp.ops.ff1, l.has_pos ? &lp.ops.pu : nullptr};
   auto add = [&](int off, int len) {  // merge with the previous range when contiguous (weight followed by its bias)
     if (s.n > 0 && s.off[s.n - 1] + s.len[s.n - 1] == off) { s.len[s.n - 1] += len; return; }
-    if (s.n < 12) { s.off[s.n] = off; s.len[s.n] = len; ++s.n; }
+    if (s.n < 14) { s.off[s.n] = off; s.len[s.n] = len; ++s.n; }
   };
+  if (l.pre_norm) {  // gcp_norm.0 belongs to the standalone normalisation in front of the layer (run_prenorm_backward)
+    add(l.ln_grad_off[0] - l.n_edge_params, l.s); add(l.ln_grad_off[1] - l.n_edge_params, l.s);
+  }
   for (int k = 0; k < 3; ++k) {
     if (op[k] == nullptr) continue;
     const GcpOp& o = *op[k];
@@ -428,6 +449,17 @@ static int run_tc_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, co
   return side_done(ps, st);
 }
 
+// consistency of the optional variants (autoregressive gather views, pre_norm workspace)
+static const char* check_variant(const gcpnet_layer& l, const gcpnet_graph& g, const float* h_gather, const float* chi_gather, const float* prenorm) {
+  const bool ar = g.gsrc != nullptr;
+  if (ar != (l.autoregressive != 0)) return "autoregressive layers need the views of gcpnet_graph_build_autoregressive (and only they)";
+  if (ar && (!g.gdst || !g.vdst_ptr || !g.vsrc_ptr || !g.vsrc_pos || g.num_gather_rows != 2 * g.num_nodes)) return "incomplete autoregressive graph views";
+  if (ar && (!h_gather || !chi_gather)) return "autoregressive layers need the [2N] gather table";
+  if (ar && l.pre_norm) return "pre_norm with an autoregressive gather table is not covered";
+  if (l.pre_norm && !prenorm) return "pre_norm layers need the prenorm workspace";
+  return nullptr;
+}
+
 // ------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------
@@ -499,7 +531,8 @@ static int run_edge_forward(const gcpnet_layer& l, const gcpnet_graph& g, const 
     return launch_tc_edge_fwd(g, lp, io, io.saved_edge, st);
   }
   EdgeParams p = make_edge_params(l, g, lp.ops, lp.ef, false, io.packed);
-  p.h = io.h; p.chi = io.chi; p.e = io.e; p.xi = io.xi; p.frames = io.frames;
+  p.h = io.h_gather ? io.h_gather : io.h; p.chi = io.chi_gather ? io.chi_gather : io.chi;
+  p.e = io.e; p.xi = io.xi; p.frames = io.frames;
   p.msg = io.msg; p.saved = io.saved_edge;
   return launch_edge_fwd(p, lp.ef, st);
 }
@@ -526,11 +559,21 @@ int gcpnet_layer_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, c
   const std::string e = make_layer_plan(l, graph->num_nodes, graph->num_edges, &lp, nullptr, plan->tc_edge_path != 0);
   if (!e.empty()) return fail("layer_forward: " + e);
   if (graph->num_nodes <= 0) return 0;
+  if (const char* m = check_variant(l, *graph, io->h_gather, io->chi_gather, io->prenorm)) return fail(std::string("layer_forward: ") + m);
   if (!io->packed_ready && launch_pack(lp.ops, io->packed, st, lp.tc.ok)) return 1;
-  if (run_edge_forward(l, *graph, lp, *io, st)) return 1;
-  NodeParams p = make_node_params(l, *graph, lp.ops, lp.nf, false, io->packed);
-  p.h = io->h; p.chi = io->chi; p.msg = io->msg; p.pos = io->pos;
-  p.out_h = io->out_h; p.out_chi = io->out_chi; p.out_pos = io->out_pos; p.saved = io->saved_node;
+  gcpnet_forward_io f = *io;
+  if (l.pre_norm) {  // gcp_norm.0 on the layer input (gcpnet.py:1188-1189); everything below reads the normalised copy
+    const long long N = graph->num_nodes;
+    float* hn = io->prenorm; float* chin = io->prenorm + N * l.s;
+    gcp_layernorm_fwd_kernel<<<(int)((N * 32 + 255) / 256), 256, 0, st>>>(io->h, io->chi, (int)N, l.s, l.v, l.ln0_w, l.ln0_b, l.ln_eps, l.vn_eps, hn, chin);
+    gcp_note_launches(1);
+    CUDA_TRY(cudaGetLastError());
+    f.h = hn; f.chi = chin;
+  }
+  if (run_edge_forward(l, *graph, lp, f, st)) return 1;
+  NodeParams p = make_node_params(l, *graph, lp.ops, lp.nf, false, f.packed);
+  p.h = f.h; p.chi = f.chi; p.msg = f.msg; p.pos = f.pos;
+  p.out_h = f.out_h; p.out_chi = f.out_chi; p.out_pos = f.out_pos; p.saved = f.saved_node;
   return launch_node_fwd(p, lp.nf, st);
 }
 
@@ -558,10 +601,20 @@ int gcpnet_message_passing_forward(const gcpnet_layer* layer, const gcpnet_graph
 static int run_ffma_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, const LayerPlan& lp, const gcpnet_backward_io& io,
                                   const float* gagg, cudaStream_t st, int* edge_grid) {
   *edge_grid = 0;
-  if (g.num_edges <= 0) return 0;
   const int W = l.s + 3 * l.v;
+  if (g.num_edges <= 0) {
+    if (g.gsrc != nullptr) {  // no edges: the gather-table cotangent is the direct part on the even rows
+      const long long tot = g.num_gather_rows * W;
+      ar_cotangent_reduce_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(
+          io.g_h_gather, io.g_chi_gather, io.g_h, io.g_chi, nullptr, nullptr, g.vdst_ptr, g.vsrc_ptr, g.vsrc_pos, (int)g.num_gather_rows, l.s, 3 * l.v);
+      gcp_note_launches(1);
+      CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+  }
   EdgeParams ep = make_edge_params(l, g, lp.ops, lp.eb, true, io.packed);
-  ep.h = io.h; ep.chi = io.chi; ep.e = io.e; ep.xi = io.xi; ep.frames = io.frames;
+  ep.h = io.h_gather ? io.h_gather : io.h; ep.chi = io.chi_gather ? io.chi_gather : io.chi;
+  ep.e = io.e; ep.xi = io.xi; ep.frames = io.frames;
   ep.saved = const_cast<float*>(io.saved_edge);
   ep.gagg = gagg;
   ep.grow = io.ws_edge; ep.gcol = io.ws_edge + (size_t)g.num_edges * W;
@@ -569,18 +622,52 @@ static int run_ffma_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, 
   ep.partial = io.ws_edge_partial;
   *edge_grid = lp.eb.grid;
   if (launch_edge_bwd(ep, lp.eb, st)) return 1;
-  const long long tot = g.num_nodes * W;
   GcpTimedScope timed(T_COT_REDUCE, st);
-  node_cotangent_reduce_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(
-      io.g_h, io.g_chi, ep.grow, ep.gcol, g.dst_ptr, g.src_ptr, g.src_pos, (int)g.num_nodes, l.s, 3 * l.v);
+  if (g.gsrc != nullptr) {
+    const long long tot = g.num_gather_rows * W;
+    ar_cotangent_reduce_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(
+        io.g_h_gather, io.g_chi_gather, io.g_h, io.g_chi, ep.grow, ep.gcol, g.vdst_ptr, g.vsrc_ptr, g.vsrc_pos, (int)g.num_gather_rows, l.s, 3 * l.v);
+  } else {
+    const long long tot = g.num_nodes * W;
+    node_cotangent_reduce_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(
+        io.g_h, io.g_chi, ep.grow, ep.gcol, g.dst_ptr, g.src_ptr, g.src_pos, (int)g.num_nodes, l.s, 3 * l.v);
+  }
   gcp_note_launches(1);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
+static int layer_backward_body(const gcpnet_layer* layer, const gcpnet_graph* graph, const gcpnet_plan* plan,
+                               const gcpnet_backward_io* io, void* stream);
 int gcpnet_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, const gcpnet_plan* plan,
                           const gcpnet_backward_io* io, void* stream) {
   if (!layer || !graph || !plan || !io) return fail("layer_backward: null argument");
+  const gcpnet_layer& l = *layer;
+  if (graph->num_nodes > 0)
+    if (const char* m = check_variant(l, *graph, io->h_gather, io->chi_gather, io->prenorm)) return fail(std::string("layer_backward: ") + m);
+  if (graph->gsrc != nullptr && (!io->g_h_gather || !io->g_chi_gather)) return fail("layer_backward: autoregressive layers need g_h_gather / g_chi_gather");
+  if (!l.pre_norm || graph->num_nodes <= 0) return layer_backward_body(layer, graph, plan, io, stream);
+  // pre_norm: the layer proper ran on the normalised input; its input cotangent lands in the workspace, then the
+  // standalone gcp_norm.0 backward produces the caller's g_h / g_chi and the gcp_norm.0 parameter gradients
+  if (!io->ws_prenorm) return fail("layer_backward: pre_norm layers need ws_prenorm");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long N = graph->num_nodes, W = l.s + 3 * l.v;
+  gcpnet_backward_io b = *io;
+  b.h = io->prenorm; b.chi = io->prenorm + N * l.s;
+  b.g_h = io->ws_prenorm; b.g_chi = io->ws_prenorm + N * l.s;
+  if (layer_backward_body(layer, graph, plan, &b, stream)) return 1;
+  float* stats = io->ws_prenorm + N * W;
+  float* partial = stats + 2 * N;
+  gcp_layernorm_bwd_kernel<<<(int)((N * 32 + 255) / 256), 256, 0, st>>>(io->h, io->chi, (int)N, l.s, l.v, l.ln0_w, l.ln_eps, l.vn_eps, b.g_h, b.g_chi,
+                                                                       io->g_h, io->g_chi, stats);
+  gcp_layernorm_wgrad_kernel<<<LN_PARTS, 128, 0, st>>>(io->h, b.g_h, stats, (int)N, l.s, partial);
+  gcp_layernorm_wreduce_kernel<<<(2 * l.s + 127) / 128, 128, 0, st>>>(partial, LN_PARTS, l.s, io->g_params + l.ln_grad_off[0], io->g_params + l.ln_grad_off[1]);
+  gcp_note_launches(3);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+static int layer_backward_body(const gcpnet_layer* layer, const gcpnet_graph* graph, const gcpnet_plan* plan,
+                               const gcpnet_backward_io* io, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const gcpnet_layer& l = *layer;
   const gcpnet_graph& g = *graph;
@@ -596,6 +683,7 @@ int gcpnet_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, 
   NodeParams np = make_node_params(l, g, lp.ops, lp.nb, true, io->packed);
   np.dbg = g_tc_dbg.load(std::memory_order_relaxed);
   np.saved = const_cast<float*>(io->saved_node);
+  np.h = io->h; np.chi = io->chi;  // node mask: masked-out nodes fed the layer input to the position GCP
   np.g_out_h = io->g_out_h; np.g_out_chi = io->g_out_chi; np.g_out_pos = io->g_out_pos;
   np.g_x_h = io->g_h; np.g_x_chi = io->g_chi; np.g_agg = io->ws_agg;
   np.partial = io->ws_node_partial;

@@ -26,6 +26,8 @@ struct EdgeParams {
   float slope;
   const float *h, *chi, *e, *xi, *frames;  // h[N][s] chi[N][3v] e[E][se] xi[E][3ve] frames[E][9] (caller's edge order)
   const int *perm, *src, *dst;             // sorted position p -> original edge id / source node / destination node
+  const int *gsrc, *gdst;                  // rows of (h, chi) gathered for the two ends (= src, dst; autoregressive layers:
+                                           // rows of the [2N] gather table, gcpnet.py:1065-1116)
   const int* dst_ptr;                      // [N+1] CSR row pointer of the destination-sorted order
   const float* blob;                       // packed weights of the layer (pack.cuh)
   float* msg;                              // [E][s+3v] final messages, sorted order
@@ -71,7 +73,7 @@ GCP_HD void edge_gather_inputs(const EdgeParams& p, float* sm, int row0, int nro
     float* zp = ZA + e * L.ldza; float* vp = VA + e * L.ldva; float* fp = F + e * LDF;
     if (e < nrows) {
       const int q = row0 + e;
-      const size_t rs = (size_t)p.src[q], rd = (size_t)p.dst[q], rp = (size_t)p.perm[q];
+      const size_t rs = (size_t)p.gsrc[q], rd = (size_t)p.gdst[q], rp = (size_t)p.perm[q];
       for (int f = lane; f < s; f += 32) { zp[f] = GCP_LDG(p.h + rs * s + f); zp[s + se + f] = GCP_LDG(p.h + rd * s + f); }
       for (int f = lane; f < se; f += 32) zp[s + f] = GCP_LDG(p.e + rp * se + f);
       for (int f = lane; f < v3; f += 32) { vp[f] = GCP_LDG(p.chi + rs * v3 + f); vp[v3 + ve3 + f] = GCP_LDG(p.chi + rd * v3 + f); }

@@ -162,12 +162,129 @@ __global__ void __launch_bounds__(SMALL_NT) graph_build_small_kernel(const int64
   }
 }
 
-// frames = [x_diff; x_cross; x_vertical] (comp/__init__.py:220-269, no node mask)
-__global__ void localize_kernel(const float* __restrict__ pos, const int64_t* __restrict__ edge_index, int E,
-                                int norm_x_diff, float* __restrict__ frames) {
+
+// ---- autoregressive views (gcpnet.py:1065-1116) ----------------------------------------------------------------------------
+// gather-row ids: node i reads row 2i (node_rep) on edges with row < col and row 2i+1 (node_rep_regressive) on the others,
+// at BOTH ends of the edge (each of the reference's two passes feeds one table to both ends)
+__global__ void ar_keys_kernel(const int64_t* __restrict__ edge_index, int E, int N, int64_t* __restrict__ keys) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   const int64_t r = edge_index[e], c = edge_index[(size_t)E + e];
+  if (r < 0 || r >= N || c < 0 || c >= N) bad_edge_index(e, r, c, N);
+  const int64_t flag = r < c ? 0 : 1;
+  keys[e] = 2 * r + flag;
+  keys[(size_t)E + e] = 2 * c + flag;
+}
+__global__ void ar_derive_kernel(const int* __restrict__ gsrc, const int* __restrict__ gdst, const int* __restrict__ vdst_ptr,
+                                 const int* __restrict__ vsrc_ptr, int E, int N, int* __restrict__ src, int* __restrict__ dst,
+                                 int* __restrict__ dst_ptr, int* __restrict__ src_ptr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < E) { src[i] = gsrc[i] >> 1; dst[i] = gdst[i] >> 1; }
+  if (i <= N) { dst_ptr[i] = vdst_ptr[2 * i]; src_ptr[i] = vsrc_ptr[2 * i]; }
+}
+
+// ---- node mask (gcpnet.py:1202-1217; comp/__init__.py:294-300) ----------------------------------------------------------
+// relabel[i] = number of unmasked nodes before i (torch_geometric.utils.subgraph relabels in subset order); one CTA
+__global__ void __launch_bounds__(1024) mask_scan_kernel(const unsigned char* __restrict__ mask, int N, int* __restrict__ relabel) {
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < N; base += 1024) {
+    const int i = base + tid;
+    const int v = (i < N && mask[i]) ? 1 : 0;
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int w = wsum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += y; }
+      wsum[lane] = w;  // inclusive
+    }
+    __syncthreads();
+    const int excl = carry + (warp > 0 ? wsum[warp - 1] : 0) + x - v;
+    if (i < N) relabel[i] = excl;
+    __syncthreads();
+    if (tid == 0) carry += wsum[31];
+    __syncthreads();
+  }
+  if (tid == 0) relabel[N] = carry;
+}
+__global__ void mask_frames_kernel(const int64_t* __restrict__ edge_index, int E, const float* __restrict__ frames,
+                                   const unsigned char* __restrict__ mask, float* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const bool m = mask[edge_index[e]] && mask[edge_index[(size_t)E + e]];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) out[(size_t)e * 9 + i] = m ? frames[(size_t)e * 9 + i] : 0.f;  // predicated, never inf * 0
+}
+__global__ void mask_mean_frames_kernel(const float* __restrict__ frames, const unsigned char* __restrict__ mask,
+                                        const int* __restrict__ relabel, const int* __restrict__ perm, const int* __restrict__ dst,
+                                        const int* __restrict__ src_pos, const int* __restrict__ src_ptr, int N,
+                                        float* __restrict__ fbar_ff, float* __restrict__ fbar_pos) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * 9) return;
+  const int i = idx / 9, c = idx - 9 * i;
+  const int a = src_ptr[i], b = src_ptr[i + 1];
+  const bool mi = mask[i] != 0;
+  float sum_pos = 0.f, sum_ff = 0.f;
+  int cnt_ff = 0;
+  for (int q = a; q < b; ++q) {
+    const int p = src_pos[q], j = dst[p];
+    if (!(mi && mask[j])) continue;  // the only edges whose frames are read (others may hold inf)
+    const float f = __ldg(frames + (size_t)perm[p] * 9 + c);
+    sum_pos += f;
+    // feed-forward GCPs run on the subgraph of the mask with RELABELLED node ids, and the reference hands scalarize the
+    // original [N] mask: the subgraph edge (i', j') contributes iff mask[i'] & mask[j']  (gcpnet.py:1232-1239)
+    ++cnt_ff;
+    if (mask[relabel[i]] && mask[relabel[j]]) sum_ff += f;
+  }
+  fbar_pos[idx] = b > a ? sum_pos / (float)(b - a) : 0.f;
+  fbar_ff[idx] = cnt_ff > 0 ? sum_ff / (float)cnt_ff : 0.f;
+}
+
+// ---- centroids -------------------------------------------------------------------------------------------------------------
+__global__ void centroid_kernel(const float* __restrict__ pos, const int64_t* __restrict__ batch, int N, int G,
+                                const unsigned char* __restrict__ mask, float* __restrict__ centroid) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= G * 3) return;
+  const int g = idx / 3, c = idx - 3 * g;
+  int lo = 0, hi = N;  // batch_index is non-decreasing: [first, last) of graph g by bisection
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (batch[mid] < g) lo = mid + 1; else hi = mid; }
+  const int first = lo;
+  hi = N;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (batch[mid] <= g) lo = mid + 1; else hi = mid; }
+  float acc = 0.f;
+  int cnt = 0;
+  for (int i = first; i < lo; ++i)
+    if (mask == nullptr || mask[i]) { acc += pos[(size_t)i * 3 + c]; ++cnt; }
+  centroid[idx] = cnt > 0 ? acc / (float)cnt : 0.f;
+}
+__global__ void shift_kernel(const float* __restrict__ pos, const int64_t* __restrict__ batch, int N, const float* __restrict__ centroid,
+                             const unsigned char* __restrict__ mask, float sign, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * 3) return;
+  const int i = idx / 3, c = idx - 3 * i;
+  if (mask != nullptr && !mask[i]) { out[idx] = __int_as_float(0x7f800000); return; }  // comp/__init__.py:187-193,208-211
+  out[idx] = pos[idx] + sign * centroid[batch[i] * 3 + c];
+}
+
+// frames = [x_diff; x_cross; x_vertical] (comp/__init__.py:220-269)
+__global__ void localize_kernel(const float* __restrict__ pos, const int64_t* __restrict__ edge_index, int E,
+                                int norm_x_diff, const unsigned char* __restrict__ mask, float* __restrict__ frames) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int64_t r = edge_index[e], c = edge_index[(size_t)E + e];
+  if (mask != nullptr && !(mask[r] && mask[c])) {  // comp/__init__.py:229-236,262-264: masked edges carry +inf frames
+    float* f = frames + (size_t)e * 9;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) f[i] = __int_as_float(0x7f800000);
+    return;
+  }
   const float ax = pos[3 * r], ay = pos[3 * r + 1], az = pos[3 * r + 2];
   const float bx = pos[3 * c], by = pos[3 * c + 1], bz = pos[3 * c + 2];
   float dx = ax - bx, dy = ay - by, dz = az - bz;
@@ -255,9 +372,93 @@ int gcpnet_graph_build(const int64_t* edge_index, int64_t E64, int64_t N64, cons
   return 0;
 }
 
-int gcpnet_localize(const float* pos, const int64_t* edge_index, int64_t E, int norm_x_diff, float* frames, void* stream) {
+int gcpnet_localize_masked(const float* pos, const int64_t* edge_index, int64_t E, int norm_x_diff, const uint8_t* node_mask,
+                           float* frames, void* stream) {
   if (E <= 0) return 0;
-  localize_kernel<<<(int)((E + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pos, edge_index, (int)E, norm_x_diff, frames);
+  localize_kernel<<<(int)((E + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pos, edge_index, (int)E, norm_x_diff, node_mask, frames);
+  gcp_note_launches(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int gcpnet_localize(const float* pos, const int64_t* edge_index, int64_t E, int norm_x_diff, float* frames, void* stream) {
+  return gcpnet_localize_masked(pos, edge_index, E, norm_x_diff, nullptr, frames, stream);
+}
+
+// ---- autoregressive views ------------------------------------------------------------------------------------------------
+size_t gcpnet_graph_ar_workspace_bytes(int64_t E, int64_t N) {
+  return align256((size_t)(E > 0 ? E : 1) * 2 * sizeof(int64_t)) + align256((size_t)2 * N * 9 * sizeof(float)) +
+         gcpnet_graph_workspace_bytes(E, 2 * N);
+}
+int gcpnet_graph_build_autoregressive(const int64_t* edge_index, int64_t E64, int64_t N64, const float* frames, int32_t* perm,
+                                      int32_t* src, int32_t* dst, int32_t* dst_ptr, int32_t* src_pos, int32_t* src_ptr, float* fbar,
+                                      int32_t* gsrc, int32_t* gdst, int32_t* vdst_ptr, int32_t* vsrc_ptr, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (E64 < 0 || N64 <= 0 || E64 >= (1LL << 31) || N64 >= (1LL << 30)) return fail("graph_build_autoregressive: sizes out of range");
+  if (workspace_bytes < gcpnet_graph_ar_workspace_bytes(E64, N64)) return fail("graph_build_autoregressive: workspace too small");
+  const int E = (int)E64, N = (int)N64, T = 256;
+  char* ws = (char*)workspace;
+  int64_t* keys = (int64_t*)ws;
+  const size_t o1 = align256((size_t)(E > 0 ? E : 1) * 2 * sizeof(int64_t));
+  float* fbar2 = (float*)(ws + o1);
+  const size_t o2 = o1 + align256((size_t)2 * N * 9 * sizeof(float));
+  if (E > 0) {
+    ar_keys_kernel<<<(E + T - 1) / T, T, 0, st>>>(edge_index, E, N, keys);
+    gcp_note_launches(1);
+  }
+  // the ordinary build over the 2N gather rows: sorted by (destination, flag); its CSRs are the gather-row CSRs
+  if (gcpnet_graph_build(keys, E64, 2 * N64, frames, perm, gsrc, gdst, vdst_ptr, src_pos, vsrc_ptr, fbar2, ws + o2, workspace_bytes - o2, stream))
+    return 1;
+  ar_derive_kernel<<<((E > N + 1 ? E : N + 1) + T - 1) / T, T, 0, st>>>(gsrc, gdst, vdst_ptr, vsrc_ptr, E, N, src, dst, dst_ptr, src_ptr);
+  gcp_note_launches(1);
+  if (E > 0) {
+    mean_frame_kernel<<<(N * 9 + T - 1) / T, T, 0, st>>>(frames, perm, src_pos, src_ptr, N, fbar);
+    gcp_note_launches(1);
+  } else {
+    CUDA_TRY(cudaMemsetAsync(fbar, 0, (size_t)N * 9 * sizeof(float), st));
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---- node mask ---------------------------------------------------------------------------------------------------------------
+int gcpnet_graph_mask(const int64_t* edge_index, int64_t E64, int64_t N64, const float* frames, const uint8_t* node_mask,
+                      const gcpnet_graph* graph, float* frames_eff, float* fbar_ff, float* fbar_pos, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!node_mask || !graph || !frames_eff || !fbar_ff || !fbar_pos) return fail("graph_mask: null argument");
+  if (E64 < 0 || N64 <= 0 || E64 >= (1LL << 31) || N64 >= (1LL << 31)) return fail("graph_mask: sizes out of range");
+  if (workspace_bytes < (size_t)(N64 + 1) * sizeof(int)) return fail("graph_mask: workspace too small");
+  const int E = (int)E64, N = (int)N64, T = 256;
+  int* relabel = (int*)workspace;
+  mask_scan_kernel<<<1, 1024, 0, st>>>(node_mask, N, relabel);
+  gcp_note_launches(1);
+  if (E > 0) {
+    mask_frames_kernel<<<(E + T - 1) / T, T, 0, st>>>(edge_index, E, frames, node_mask, frames_eff);
+    gcp_note_launches(1);
+  }
+  mask_mean_frames_kernel<<<(N * 9 + T - 1) / T, T, 0, st>>>(frames, node_mask, relabel, graph->perm, graph->dst, graph->src_pos,
+                                                             graph->src_ptr, N, fbar_ff, fbar_pos);
+  gcp_note_launches(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---- centralize / decentralize (comp/__init__.py:170-217) ----------------------------------------------------------------
+int gcpnet_centralize(const float* pos, const int64_t* batch_index, int64_t N, int64_t G, const uint8_t* node_mask, float* centroid,
+                      float* centered, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N <= 0 || G <= 0) return 0;
+  centroid_kernel<<<(int)((G * 3 + 127) / 128), 128, 0, st>>>(pos, batch_index, (int)N, (int)G, node_mask, centroid);
+  shift_kernel<<<(int)((N * 3 + 255) / 256), 256, 0, st>>>(pos, batch_index, (int)N, centroid, node_mask, -1.f, centered);
+  gcp_note_launches(2);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int gcpnet_decentralize(const float* pos, const int64_t* batch_index, int64_t N, const float* centroid, const uint8_t* node_mask,
+                        float* out, void* stream) {
+  if (N <= 0) return 0;
+  shift_kernel<<<(int)((N * 3 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pos, batch_index, (int)N, centroid, node_mask, 1.f, out);
   gcp_note_launches(1);
   CUDA_TRY(cudaGetLastError());
   return 0;

@@ -19,6 +19,7 @@ constexpr int EDGE_CAP_FLOATS = 8192;        // largest weight chunk of the edge
 constexpr int NODE_CAP_FLOATS = 16384;       // node kernels: wide feed-forward layers (64 KB ring slot)
 constexpr int NODE_TE = 16, NODE_NT = 512;   // 32 threads per node
 constexpr int EDGE_SLD = 2, NODE_SLD = 2;
+constexpr int LN_PARTS = 64;                // node chunks of the standalone GCPLayerNorm backward (weight / bias partials)
 
 inline GcpOp to_op(const gcpnet_gcp2& d, int grad_base) {
   GcpOp o{};
@@ -311,6 +312,10 @@ inline std::string make_layer_plan(const gcpnet_layer& l, long long N, long long
     p.agg_cotangent_floats = N * W;
     p.packed_floats = lp->v2_packed_floats + (lp->tc.ok ? tc::rup(lp->tc.blob_floats, 32) + lp->tc.pq_floats : 0);
     p.tc_edge_path = lp->tc.ok ? 1 : 0;
+    if (l.pre_norm) {  // [normalised input] ; backward: [cotangent of it | per-node (mean, rstd) | LN_PARTS x 2s partials]
+      p.prenorm_floats = N * W;
+      p.prenorm_ws_floats = N * W + 2 * N + (long long)LN_PARTS * 2 * l.s;
+    }
     *plan = p;
   }
   return "";
@@ -323,6 +328,7 @@ inline EdgeParams make_edge_params(const gcpnet_layer& l, const gcpnet_graph& g,
   p.s = l.s; p.v = l.v; p.se = l.se; p.ve = l.ve;
   p.residual = l.residual_messages; p.e3 = l.enable_e3; p.reduce_mean = l.reduce_mean; p.slope = l.slope;
   p.perm = g.perm; p.src = g.src; p.dst = g.dst; p.dst_ptr = g.dst_ptr;
+  p.gsrc = g.gsrc != nullptr ? g.gsrc : g.src; p.gdst = g.gdst != nullptr ? g.gdst : g.dst;
   p.blob = blob;
   for (int k = 0; k < p.L; ++k) p.ops[k] = ops.msg[k];
   long long tot;
@@ -342,6 +348,7 @@ inline NodeParams make_node_params(const gcpnet_layer& l, const gcpnet_graph& g,
   p.slope = l.slope; p.ln_eps = l.ln_eps; p.vn_eps = l.vn_eps; p.pos_weight = l.pos_weight; p.p_drop = l.training ? l.p_drop : 0.f;
   p.seed = l.seed; p.rng_ctr = (const long long*)l.rng_counter;
   p.fbar = g.fbar; p.dst_ptr = g.dst_ptr;
+  p.fbar_pos = g.fbar_pos; p.mask = g.node_mask; p.pre_norm = l.pre_norm;
   p.ln0_w = l.ln0_w; p.ln0_b = l.ln0_b; p.ln1_w = l.ln1_w; p.ln1_b = l.ln1_b;
   p.blob = blob;
   p.ff0 = ops.ff0; p.ff1 = ops.ff1; p.pu = ops.pu;

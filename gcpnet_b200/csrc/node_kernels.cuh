@@ -37,6 +37,9 @@ struct NodeParams {
   unsigned long long seed;
   const long long* rng_ctr;     // device counter, advanced by the host side once per training forward
   const float *h, *chi, *msg, *fbar, *pos;
+  const float* fbar_pos;        // node mask: mean frames of the position-update GCP (nullptr: fbar)
+  const unsigned char* mask;    // node mask (nullptr: every node takes part): masked-out rows keep the layer input
+  int pre_norm;                 // gcp_norm.1 after the first residual, no normalisation at the end (gcpnet.py:1223-1224,1245)
   const int* dst_ptr;
   const float *ln0_w, *ln0_b, *ln1_w, *ln1_b;
   const float* blob;
@@ -372,7 +375,10 @@ GCP_HDN void node_fwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
     }
   }
   GCP_PHASE_END
-  tile_layernorm_fwd<TE, NT>(XS, L.ldxs, XV, L.ldxv, s, v, p.ln0_w, p.ln0_b, p.ln_eps, p.vn_eps, RED);
+  // normalisation after the first residual: gcp_norm.0, or gcp_norm.1 when pre_norm (gcpnet.py:1223-1226)
+  const float* lnA_w = p.pre_norm ? p.ln1_w : p.ln0_w;
+  const float* lnA_b = p.pre_norm ? p.ln1_b : p.ln0_b;
+  tile_layernorm_fwd<TE, NT>(XS, L.ldxs, XV, L.ldxv, s, v, lnA_w, lnA_b, p.ln_eps, p.vn_eps, RED);
   // FF0: (s, v) -> (hs, hv)
   {
     const TileBufs b = node_bufs(p, sm, 0);
@@ -452,7 +458,23 @@ GCP_HDN void node_fwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
     GCP_PHASE_END
     wp.head++;
   }
-  tile_layernorm_fwd<TE, NT>(XS, L.ldxs, XV, L.ldxv, s, v, p.ln1_w, p.ln1_b, p.ln_eps, p.vn_eps, RED);
+  if (!p.pre_norm) tile_layernorm_fwd<TE, NT>(XS, L.ldxs, XV, L.ldxv, s, v, p.ln1_w, p.ln1_b, p.ln_eps, p.vn_eps, RED);
+  const bool pos_frames = p.has_pos && p.fbar_pos != nullptr && p.fbar_pos != p.fbar;
+  if (p.mask != nullptr || pos_frames) {
+    // node mask: masked-out nodes keep the layer input (gcpnet.py:1249-1251); the position GCP sees all nodes with its own
+    // mean frames (derive_x_update runs on the full graph, gcpnet.py:1258)
+    GCP_PHASE_BEGIN(NT)
+    const int lane = tid & 31;
+    for (int e = tid >> 5; e < nrows; e += NT / 32) {
+      const size_t i = (size_t)(row0 + e);
+      if (p.mask != nullptr && !p.mask[i])
+        for (int f = lane; f < W; f += 32) {
+          if (f < s) XS[e * L.ldxs + f] = GCP_LDG(p.h + i * s + f); else XV[e * L.ldxv + (f - s)] = GCP_LDG(p.chi + i * v3 + (f - s));
+        }
+      if (pos_frames && lane < 9) sm[L.F + e * LDF + lane] = GCP_LDG(p.fbar_pos + i * 9 + lane);
+    }
+    GCP_PHASE_END
+  }
   GCP_PHASE_BEGIN(NT)
   wpipe_refill(wp, wp.head - 1, tid);  // G chunk of FF1 (the LayerNorm phases do not touch the ring)
   tile_store_rows<TE, NT>(p.out_h, row0, s, XS, L.ldxs, nrows, tid);
@@ -502,6 +524,7 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
     g.sp_gT = p.spill + p.sp_gT[which]; g.sp_Z = p.spill + p.sp_Z[which]; g.sp_GG = p.spill + p.sp_GG[which];
     g.sp_row0 = row0; g.sp_nrows = nrows;
   };
+  const bool pos_frames = p.has_pos && p.fbar_pos != nullptr && p.fbar_pos != p.fbar;
   GCP_NSTAMP(0);
   // load x2 (raw copy + a copy that becomes out = LN1(x2)), the output cotangents, the mean frames
   GCP_PHASE_BEGIN(NT)
@@ -518,13 +541,25 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
       if (f < s) { X2S[e * L.ldx2s + f] = x2; XS[e * L.ldxs + f] = x2; GXS[e * ldgxs + f] = gx; }
       else { X2V[e * L.ldx2v + (f - s)] = x2; XV[e * L.ldxv + (f - s)] = x2; GXV[e * ldgxv + (f - s)] = gx; }
     }
-    if (lane < 9) sm[L.F + e * LDF + lane] = live ? GCP_LDG(p.fbar + i * 9 + lane) : 0.f;
+    if (lane < 9) sm[L.F + e * LDF + lane] = live ? GCP_LDG((pos_frames ? p.fbar_pos : p.fbar) + i * 9 + lane) : 0.f;
   }
   GCP_PHASE_END
   GCP_NSTAMP(1);
   // ---- position update backward: only the vector output of P carries a cotangent (gcpnet.py:1129-1137,1156)
   if (p.has_pos) {
-    tile_layernorm_fwd<TE, NT>(XS, L.ldxs, XV, L.ldxv, s, v, p.ln1_w, p.ln1_b, p.ln_eps, p.vn_eps, RED);
+    if (!p.pre_norm) tile_layernorm_fwd<TE, NT>(XS, L.ldxs, XV, L.ldxv, s, v, p.ln1_w, p.ln1_b, p.ln_eps, p.vn_eps, RED);
+    if (p.mask != nullptr) {  // the position GCP of a masked-out node read the layer input
+      GCP_PHASE_BEGIN(NT)
+      const int lane = tid & 31;
+      for (int e = tid >> 5; e < nrows; e += NT / 32) {
+        const size_t i = (size_t)(row0 + e);
+        if (!p.mask[i])
+          for (int f = lane; f < W; f += 32) {
+            if (f < s) XS[e * L.ldxs + f] = GCP_LDG(p.h + i * s + f); else XV[e * L.ldxv + (f - s)] = GCP_LDG(p.chi + i * v3 + (f - s));
+          }
+      }
+      GCP_PHASE_END
+    }
     const TileBufs b = node_bufs(p, sm, 2);
     g.GS = sm + L.GS1; g.ldgs = L.ldgs1; g.GV = sm + L.GV1; g.ldgv = L.ldgv1;
     GCP_PHASE_BEGIN(NT)
@@ -548,9 +583,30 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
         p.pu, b, g, wp, 0, p.slope, prow, accumulate, false, EmitTile{GXS, ldgxs, true}, EmitTile{GXV, ldgxv, true});
   }
   GCP_NSTAMP(2);
-  // ---- LayerNorm1 backward (input x2)
-  tile_layernorm_bwd<TE, NT>(X2S, L.ldx2s, X2V, L.ldx2v, GXS, ldgxs, GXV, ldgxv, s, v, p.ln1_w, p.ln_eps, p.vn_eps, RED,
-                             prow + p.o_ln1w, prow + p.o_ln1b, accumulate);
+  if (p.mask != nullptr || pos_frames) {
+    // node mask: for a masked-out node the output IS the layer input -> its cotangent leaves here and nothing flows into
+    // the update chain (zero cotangents give zero data and weight gradients row by row); frames of the feed-forward GCPs
+    GCP_PHASE_BEGIN(NT)
+    const int lane = tid & 31;
+    for (int e = tid >> 5; e < nrows; e += NT / 32) {
+      const size_t i = (size_t)(row0 + e);
+      if (p.mask != nullptr && !p.mask[i])
+        for (int f = lane; f < W; f += 32) {
+          if (f < s) { p.g_x_h[i * s + f] = GXS[e * ldgxs + f]; GXS[e * ldgxs + f] = 0.f; }
+          else { p.g_x_chi[i * v3 + (f - s)] = GXV[e * ldgxv + (f - s)]; GXV[e * ldgxv + (f - s)] = 0.f; }
+          p.g_agg[i * W + f] = 0.f;
+        }
+      if (pos_frames && lane < 9) sm[L.F + e * LDF + lane] = GCP_LDG(p.fbar + i * 9 + lane);
+    }
+    GCP_PHASE_END
+  }
+  // ---- LayerNorm1 backward (input x2); pre_norm: there is no normalisation at the end
+  const float* lnA_w = p.pre_norm ? p.ln1_w : p.ln0_w;
+  const float* lnA_b = p.pre_norm ? p.ln1_b : p.ln0_b;
+  const int o_lnAw = p.pre_norm ? p.o_ln1w : p.o_ln0w, o_lnAb = p.pre_norm ? p.o_ln1b : p.o_ln0b;
+  if (!p.pre_norm)
+    tile_layernorm_bwd<TE, NT>(X2S, L.ldx2s, X2V, L.ldx2v, GXS, ldgxs, GXV, ldgxv, s, v, p.ln1_w, p.ln_eps, p.vn_eps, RED,
+                               prow + p.o_ln1w, prow + p.o_ln1b, accumulate);
   GCP_NSTAMP(3);
   // ---- x2 = x1n + Dropout1(f): cotangent of f, reload x1 (raw copy + copy that becomes x1n), FF inputs
   const TileBufs b1 = node_bufs(p, sm, 1);
@@ -579,7 +635,7 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
   tile_load_rows<TE, NT>(b1.SG, b1.ldsg, p.saved + p.sv.SG1, v, rr, tid);
   GCP_PHASE_END
   GCP_NSTAMP(4);
-  tile_layernorm_fwd<TE, NT>(XS, L.ldxs, XV, L.ldxv, s, v, p.ln0_w, p.ln0_b, p.ln_eps, p.vn_eps, RED);
+  tile_layernorm_fwd<TE, NT>(XS, L.ldxs, XV, L.ldxv, s, v, lnA_w, lnA_b, p.ln_eps, p.vn_eps, RED);
   GCP_PHASE_BEGIN(NT)
   const int lane = tid & 31;
   for (int e = tid >> 5; e < TE; e += NT / 32)
@@ -603,15 +659,16 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
         p.ff0, b0, g, wp, 0, p.slope, prow, accumulate, false, EmitTile{GXS, ldgxs, true}, EmitTile{GXV, ldgxv, true});
   }
   GCP_NSTAMP(7);
-  // ---- LayerNorm0 backward (input x1, kept raw in X2S/X2V)
-  tile_layernorm_bwd<TE, NT>(X2S, L.ldx2s, X2V, L.ldx2v, GXS, ldgxs, GXV, ldgxv, s, v, p.ln0_w, p.ln_eps, p.vn_eps, RED,
-                             prow + p.o_ln0w, prow + p.o_ln0b, accumulate);
+  // ---- backward of the normalisation after the first residual (input x1, kept raw in X2S/X2V)
+  tile_layernorm_bwd<TE, NT>(X2S, L.ldx2s, X2V, L.ldx2v, GXS, ldgxs, GXV, ldgxv, s, v, lnA_w, p.ln_eps, p.vn_eps, RED,
+                             prow + o_lnAw, prow + o_lnAb, accumulate);
   GCP_NSTAMP(8);
   // ---- x1 = x + Dropout0(m): direct cotangent of the layer input, cotangent of the aggregate
   GCP_PHASE_BEGIN(NT)
   const int lane = tid & 31;
   for (int e = tid >> 5; e < nrows; e += NT / 32) {
     const size_t i = (size_t)(row0 + e);
+    if (p.mask != nullptr && !p.mask[i]) continue;  // masked-out node: cotangents written above
     for (int f = lane; f < W; f += 32) {
       const float gx = f < s ? GXS[e * ldgxs + f] : GXV[e * ldgxv + (f - s)];
       float mk = 1.f;

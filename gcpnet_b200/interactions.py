@@ -51,26 +51,73 @@ def _stream() -> int:
 # ------------------------------------------------------------------------------------------
 # per-batch graph views (CSR by destination and by source, mean frames), shared by all layers
 # ------------------------------------------------------------------------------------------
-class GraphViews:
-    """Device arrays built by ``gcpnet_graph_build`` for one (edge_index, frames) pair."""
+def _mask_u8(node_mask: Optional[torch.Tensor], num_nodes: int, device) -> Optional[torch.Tensor]:
+    """bool[N] (or anything truthy per node) -> contiguous uint8[N] the kernels read; no host synchronisation."""
+    if node_mask is None:
+        return None
+    if tuple(node_mask.shape) != (num_nodes,):
+        raise TypeError(f"gcpnet_b200: node_mask has shape {tuple(node_mask.shape)}, expected ({num_nodes},)")
+    _check_cuda(node_mask, "node_mask")
+    m = node_mask.contiguous()
+    return m.view(torch.uint8) if m.dtype == torch.bool else (m != 0).view(torch.uint8)
 
-    def __init__(self, edge_index: torch.Tensor, frames: torch.Tensor, num_nodes: int):
+
+class GraphViews:
+    """Device arrays built by ``gcpnet_graph_build`` for one (edge_index, frames) pair; with ``autoregressive`` the gather
+    views of ``gcpnet_graph_build_autoregressive`` (gcpnet.py:1065-1116), with ``node_mask`` the masked frames and mean
+    frames of ``gcpnet_graph_mask`` (gcpnet.py:1202-1217; comp/__init__.py:294-300)."""
+
+    def __init__(self, edge_index: torch.Tensor, frames: torch.Tensor, num_nodes: int, autoregressive: bool = False,
+                 node_mask: Optional[torch.Tensor] = None):
         lib = _lib.load()
         dev = edge_index.device
         E = int(edge_index.shape[1])
         self.N, self.E = int(num_nodes), E
+        N = self.N
         i32 = lambda n: torch.empty(max(n, 1), dtype=torch.int32, device=dev)
         self.perm, self.src, self.dst, self.src_pos = i32(E), i32(E), i32(E), i32(E)
-        self.dst_ptr, self.src_ptr = i32(self.N + 1), i32(self.N + 1)
-        self.fbar = torch.empty((self.N, 9), dtype=torch.float32, device=dev)
-        ws_bytes = int(lib.gcpnet_graph_workspace_bytes(E, self.N))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        _lib.check(lib.gcpnet_graph_build(_ptr(edge_index), E, self.N, _ptr(frames), _ptr(self.perm), _ptr(self.src),
-                                          _ptr(self.dst), _ptr(self.dst_ptr), _ptr(self.src_pos), _ptr(self.src_ptr),
-                                          _ptr(self.fbar), _ptr(ws), ws_bytes, _stream()), "gcpnet_graph_build")
-        self._ws = ws  # keep alive until the stream has consumed it
-        self.struct = _cabi.Graph(self.N, E, _ptr(self.perm), _ptr(self.src), _ptr(self.dst), _ptr(self.dst_ptr),
+        self.dst_ptr, self.src_ptr = i32(N + 1), i32(N + 1)
+        self.fbar = torch.empty((N, 9), dtype=torch.float32, device=dev)
+        self.autoregressive = bool(autoregressive)
+        self.frames = frames  # what the message GCPs scalarise with (replaced by the masked copy below)
+        keep = []
+        if self.autoregressive:
+            self.gsrc, self.gdst = i32(E), i32(E)
+            self.vdst_ptr, self.vsrc_ptr = i32(2 * N + 1), i32(2 * N + 1)
+            ws_bytes = int(lib.gcpnet_graph_ar_workspace_bytes(E, N))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            _lib.check(lib.gcpnet_graph_build_autoregressive(
+                _ptr(edge_index), E, N, _ptr(frames), _ptr(self.perm), _ptr(self.src), _ptr(self.dst), _ptr(self.dst_ptr),
+                _ptr(self.src_pos), _ptr(self.src_ptr), _ptr(self.fbar), _ptr(self.gsrc), _ptr(self.gdst), _ptr(self.vdst_ptr),
+                _ptr(self.vsrc_ptr), _ptr(ws), ws_bytes, _stream()), "gcpnet_graph_build_autoregressive")
+        else:
+            ws_bytes = int(lib.gcpnet_graph_workspace_bytes(E, N))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            _lib.check(lib.gcpnet_graph_build(_ptr(edge_index), E, N, _ptr(frames), _ptr(self.perm), _ptr(self.src),
+                                              _ptr(self.dst), _ptr(self.dst_ptr), _ptr(self.src_pos), _ptr(self.src_ptr),
+                                              _ptr(self.fbar), _ptr(ws), ws_bytes, _stream()), "gcpnet_graph_build")
+        keep.append(ws)
+        self.struct = _cabi.Graph(N, E, _ptr(self.perm), _ptr(self.src), _ptr(self.dst), _ptr(self.dst_ptr),
                                   _ptr(self.src_pos), _ptr(self.src_ptr), _ptr(self.fbar))
+        if self.autoregressive:
+            g = self.struct
+            g.gsrc, g.gdst, g.vdst_ptr, g.vsrc_ptr, g.vsrc_pos = (_ptr(self.gsrc), _ptr(self.gdst), _ptr(self.vdst_ptr),
+                                                                  _ptr(self.vsrc_ptr), _ptr(self.src_pos))
+            g.num_gather_rows = 2 * N
+        self.mask = _mask_u8(node_mask, N, dev)
+        if self.mask is not None:
+            self.frames = torch.empty_like(frames)
+            self.fbar_ff = torch.empty_like(self.fbar)
+            self.fbar_pos = torch.empty_like(self.fbar)
+            ws2 = torch.empty(4 * (N + 1), dtype=torch.uint8, device=dev)
+            _lib.check(lib.gcpnet_graph_mask(_ptr(edge_index), E, N, _ptr(frames), _ptr(self.mask), C.byref(self.struct),
+                                             _ptr(self.frames), _ptr(self.fbar_ff), _ptr(self.fbar_pos), _ptr(ws2), 4 * (N + 1),
+                                             _stream()), "gcpnet_graph_mask")
+            keep.append(ws2)
+            self.struct.fbar = _ptr(self.fbar_ff)
+            self.struct.fbar_pos = _ptr(self.fbar_pos)
+            self.struct.node_mask = _ptr(self.mask)
+        self._ws = keep  # keep alive until the stream has consumed them
 
 
 _GRAPH_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
@@ -78,10 +125,11 @@ _GRAPH_CACHE_SIZE = 8
 _GRAPH_CACHE_MODE = [False]  # True while the entries were built under CUDA-graph capture
 
 
-def graph_views(edge_index: torch.Tensor, frames: torch.Tensor, num_nodes: int) -> GraphViews:
+def graph_views(edge_index: torch.Tensor, frames: torch.Tensor, num_nodes: int, autoregressive: bool = False,
+                node_mask: Optional[torch.Tensor] = None) -> GraphViews:
     """Build (or fetch) the graph views.  Frames are computed once per batch in the reference
     (gcpnet_nms_module.py:132) and every layer of the model sees the same tensors, so the key is
-    the identity + version of the two tensors; entries hold references to them so a pointer
+    the identity + version of the tensors; entries hold references to them so a pointer
     cannot be recycled while its entry lives.  The key relies on ``Tensor._version``: writes that do not bump it
     (``.data.copy_``, DLPack consumers, custom kernels) need ``clear_graph_cache()``.  Entries never cross a CUDA-graph
     capture boundary: views built under capture live in the graph's memory pool and are only valid inside that graph,
@@ -91,13 +139,14 @@ def graph_views(edge_index: torch.Tensor, frames: torch.Tensor, num_nodes: int) 
         _GRAPH_CACHE.clear()
         _GRAPH_CACHE_MODE[0] = capturing
     key = (edge_index.data_ptr(), edge_index._version, frames.data_ptr(), frames._version, int(num_nodes),
-           int(edge_index.shape[1]), edge_index.device.index, _stream())
+           int(edge_index.shape[1]), edge_index.device.index, _stream(), bool(autoregressive),
+           None if node_mask is None else (node_mask.data_ptr(), node_mask._version))
     hit = _GRAPH_CACHE.get(key)
     if hit is not None:
         _GRAPH_CACHE.move_to_end(key)
         return hit[0]
-    gv = GraphViews(edge_index, frames, num_nodes)
-    _GRAPH_CACHE[key] = (gv, edge_index, frames)
+    gv = GraphViews(edge_index, frames, num_nodes, autoregressive, node_mask)
+    _GRAPH_CACHE[key] = (gv, edge_index, frames, node_mask)
     while len(_GRAPH_CACHE) > _GRAPH_CACHE_SIZE:
         _GRAPH_CACHE.popitem(last=False)
     return gv
@@ -107,17 +156,57 @@ def clear_graph_cache() -> None:
     _GRAPH_CACHE.clear()
 
 
-def localize(pos: torch.Tensor, edge_index: torch.Tensor, norm_x_diff: bool = True) -> torch.Tensor:
-    """frames[E,3,3] = [x_diff; x_cross; x_vertical] (comp/__init__.py:220-269, no node mask)."""
+def localize(pos: torch.Tensor, edge_index: torch.Tensor, norm_x_diff: bool = True,
+             node_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """frames[E,3,3] = [x_diff; x_cross; x_vertical] (comp/__init__.py:220-269).  With ``node_mask`` the frames of edges
+    that touch a masked-out node are +inf, as in the reference (the masked layer path never reads them)."""
     _check_cuda(pos, "pos")
     if pos.dtype != torch.float32 or edge_index.dtype != torch.int64:
         raise TypeError("localize: pos must be float32 and edge_index int64")
     pos, edge_index = pos.contiguous(), edge_index.contiguous()
     E = int(edge_index.shape[1])
     frames = torch.empty((E, 3, 3), dtype=torch.float32, device=pos.device)
-    _lib.check(_lib.load().gcpnet_localize(_ptr(pos), _ptr(edge_index), E, int(norm_x_diff), _ptr(frames), _stream()),
-               "gcpnet_localize")
+    mask = _mask_u8(node_mask, int(pos.shape[0]), pos.device)
+    _lib.check(_lib.load().gcpnet_localize_masked(_ptr(pos), _ptr(edge_index), E, int(norm_x_diff), _ptr(mask), _ptr(frames),
+                                                  _stream()), "gcpnet_localize")
     return frames
+
+
+def centralize(batch, key: str, batch_index: torch.Tensor, node_mask: Optional[torch.Tensor] = None,
+               num_graphs: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``centralize`` (comp/__init__.py:170-200): (centroid[G,3], centered[N,3]) of ``batch[key]`` per graph; with a mask the
+    centroid averages the unmasked rows and masked rows of ``centered`` are +inf.  ``batch_index`` must be non-decreasing
+    (PyG batches are).  ``num_graphs`` avoids the host synchronisation the reference's ``scatter`` without ``dim_size``
+    implies (default: ``batch_index.max() + 1``)."""
+    x = batch[key]
+    _check_cuda(x, key)
+    if x.dtype != torch.float32 or x.dim() != 2 or x.shape[1] != 3 or batch_index.dtype != torch.int64:
+        raise TypeError("centralize: batch[key] must be float32 [N, 3] and batch_index int64 [N]")
+    x, batch_index = x.contiguous(), batch_index.contiguous()
+    N = int(x.shape[0])
+    mask = _mask_u8(node_mask, N, x.device)
+    if num_graphs is None:
+        sel = batch_index if mask is None else batch_index[mask.bool()]
+        num_graphs = int(sel.max().item()) + 1 if sel.numel() else 0
+    centroid = torch.zeros((num_graphs, 3), dtype=torch.float32, device=x.device)
+    centered = torch.empty_like(x)
+    _lib.check(_lib.load().gcpnet_centralize(_ptr(x), _ptr(batch_index), N, int(num_graphs), _ptr(mask), _ptr(centroid),
+                                             _ptr(centered), _stream()), "gcpnet_centralize")
+    return centroid, centered
+
+
+def decentralize(batch, key: str, batch_index: torch.Tensor, entities_centroid: torch.Tensor,
+                 node_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``decentralize`` (comp/__init__.py:203-217): ``batch[key] + centroid[batch_index]`` (masked rows: +inf)."""
+    x = batch[key]
+    _check_cuda(x, key)
+    x, batch_index, cen = x.contiguous(), batch_index.contiguous(), entities_centroid.contiguous()
+    N = int(x.shape[0])
+    mask = _mask_u8(node_mask, N, x.device)
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().gcpnet_decentralize(_ptr(x), _ptr(batch_index), N, _ptr(cen), _ptr(mask), _ptr(out), _stream()),
+               "gcpnet_decentralize")
+    return out
 
 
 def _check_cuda(t: torch.Tensor, name: str) -> None:
@@ -227,14 +316,16 @@ def _defer_join(tensors, after_join=None) -> None:
 # autograd bridge
 # ------------------------------------------------------------------------------------------
 class _LayerFn(torch.autograd.Function):
+    """One GCPInteractions layer.  `hg` / `chig`: the [2N] gather table of an autoregressive call (None otherwise)."""
+
     @staticmethod
-    def forward(ctx, mod: "GCPInteractions", gv: GraphViews, h, chi, e, xi, frames, pos, *params):
+    def forward(ctx, mod: "GCPInteractions", gv: GraphViews, h, chi, e, xi, frames, pos, hg, chig, *params):
         lib = _lib.load()
         spec = mod.spec
         N, E = gv.N, gv.E
         dev = h.device
         training = bool(mod.training and mod.dropout_p > 0.0)
-        layer = mod._layer_struct(params, training)
+        layer = mod._layer_struct(params, training, gv.autoregressive)
         plan = _cabi.Plan()
         _lib.check(lib.gcpnet_layer_plan(C.byref(layer), N, E, C.byref(plan)), "gcpnet_layer_plan")
         need_grad = mod._grad_mode and any(ctx.needs_input_grad)
@@ -244,22 +335,25 @@ class _LayerFn(torch.autograd.Function):
         msg = f32(plan.msg_floats)
         saved_edge = f32(plan.saved_edge_floats) if need_grad else None
         saved_node = f32(plan.saved_node_floats) if need_grad else None
+        prenorm = f32(plan.prenorm_floats) if spec.pre_norm else None
         pre = mod._prepacked
         mod._prepacked = None
-        if pre is not None and pre[0] == (N, E, training, tuple((p.data_ptr(), p._version) for p in params)) and pre[1].device == dev:
+        if pre is not None and pre[0] == (N, E, training, gv.autoregressive, tuple((p.data_ptr(), p._version) for p in params)) \
+                and pre[1].device == dev:
             packed, ready = pre[1], 1
             torch.cuda.current_stream().wait_event(pre[2])  # packed on the side stream at the start of the step
         else:
             packed, ready = f32(plan.packed_floats), 0
         io = _cabi.ForwardIO(_ptr(h), _ptr(chi), _ptr(e), _ptr(xi), _ptr(frames), _ptr(pos), _ptr(out_h), _ptr(out_chi),
-                             _ptr(out_pos), _ptr(msg), _ptr(saved_edge), _ptr(saved_node), _ptr(packed), ready, 0)
+                             _ptr(out_pos), _ptr(msg), _ptr(saved_edge), _ptr(saved_node), _ptr(packed), ready, 0,
+                             _ptr(hg), _ptr(chig), _ptr(prenorm))
         _lib.check(lib.gcpnet_layer_forward(C.byref(layer), C.byref(gv.struct), C.byref(plan), C.byref(io), _stream()),
                    "gcpnet_layer_forward")
         if training:
             mod._rng_counter.add_(1)
         ctx.mod, ctx.gv, ctx.plan, ctx.training = mod, gv, plan, training
         ctx.has_pos = spec.has_pos
-        ctx.save_for_backward(h, chi, e, xi, frames, saved_edge, saved_node, packed, *params)
+        ctx.save_for_backward(h, chi, e, xi, frames, saved_edge, saved_node, packed, hg, chig, prenorm, *params)
         if spec.has_pos:
             return out_h, out_chi, out_pos
         return out_h, out_chi
@@ -270,7 +364,7 @@ class _LayerFn(torch.autograd.Function):
         _side_stream_setup()
         mod, gv, plan = ctx.mod, ctx.gv, ctx.plan
         spec = mod.spec
-        h, chi, e, xi, frames, saved_edge, saved_node, packed, *params = ctx.saved_tensors
+        h, chi, e, xi, frames, saved_edge, saved_node, packed, hg, chig, prenorm, *params = ctx.saved_tensors
         if saved_node is None:
             raise RuntimeError("gcpnet_b200: backward called on a forward that ran without saved activations")
         dev = h.device
@@ -280,9 +374,12 @@ class _LayerFn(torch.autograd.Function):
         g_out_chi = torch.zeros_like(chi) if g_out_chi is None else g_out_chi.contiguous()
         if ctx.has_pos:
             g_out_pos = torch.zeros((gv.N, 3), dtype=torch.float32, device=dev) if g_out_pos is None else g_out_pos.contiguous()
-        layer = mod._layer_struct(params, ctx.training)
+        layer = mod._layer_struct(params, ctx.training, gv.autoregressive)
         f32 = lambda n: torch.empty(max(int(n), 1), dtype=torch.float32, device=dev)
         g_h, g_chi, g_e, g_xi = torch.empty_like(h), torch.empty_like(chi), torch.empty_like(e), torch.empty_like(xi)
+        g_hg = torch.empty_like(hg) if hg is not None else None
+        g_chig = torch.empty_like(chig) if chig is not None else None
+        ws_pre = f32(plan.prenorm_ws_floats) if spec.pre_norm else None
         sink = mod._grad_sink
         if sink is not None and (sink.numel() != spec.n_params or sink.device != dev or sink.dtype != torch.float32
                                  or not sink.is_contiguous()):
@@ -292,19 +389,23 @@ class _LayerFn(torch.autograd.Function):
         ws_ep, ws_np = f32(plan.edge_partial_floats), f32(plan.node_partial_floats)
         io = _cabi.BackwardIO(_ptr(h), _ptr(chi), _ptr(e), _ptr(xi), _ptr(frames), _ptr(saved_edge), _ptr(saved_node),
                               _ptr(g_out_h), _ptr(g_out_chi), _ptr(g_out_pos), _ptr(g_h), _ptr(g_chi), _ptr(g_e),
-                              _ptr(g_xi), _ptr(g_params), _ptr(ws_agg), _ptr(ws_edge), _ptr(ws_ep), _ptr(ws_np), _ptr(packed))
+                              _ptr(g_xi), _ptr(g_params), _ptr(ws_agg), _ptr(ws_edge), _ptr(ws_ep), _ptr(ws_np), _ptr(packed),
+                              _ptr(hg), _ptr(chig), _ptr(g_hg), _ptr(g_chig), _ptr(prenorm), _ptr(ws_pre))
         _lib.check(lib.gcpnet_layer_backward(C.byref(layer), C.byref(gv.struct), C.byref(plan), C.byref(io), _stream()),
                    "gcpnet_layer_backward")
         if gv.E == 0:
             g_e.zero_()
             g_xi.zero_()
         g_pos = g_out_pos if ctx.has_pos else None  # node_pos' = node_pos + update (gcpnet.py:1258)
+        if hg is not None:  # the direct cotangent of (h, chi) rides on the even rows of the gather table's cotangent
+            g_h = g_chi = None
+        head = (None, None, g_h, g_chi, g_e, g_xi, None, g_pos, g_hg, g_chig)
         if sink is not None:
             # nobody reads the parameter gradients during this backward pass: deferred join, side work overlaps
             hook = mod._grad_hook
-            _defer_join((ws_agg, ws_edge, ws_ep, ws_np, saved_edge, saved_node, packed, h, chi),
+            _defer_join((ws_agg, ws_edge, ws_ep, ws_np, saved_edge, saved_node, packed, h, chi, prenorm, ws_pre),
                         None if hook is None else hook(mod, sink))
-            return (None, None, g_h, g_chi, g_e, g_xi, None, g_pos) + (None,) * len(params)
+            return head + (None,) * len(params)
         # autograd (AccumulateGrad, tensor hooks, DDP reducer) may read the gradients as soon as this returns
         if _side()["stream"] is not None:
             _lib.check(lib.gcpnet_join(_stream()), "gcpnet_join")
@@ -316,7 +417,7 @@ class _LayerFn(torch.autograd.Function):
             for d in shp:
                 n *= d
             pgrads.append(g_params[o:o + n].view(shp))
-        return (None, None, g_h, g_chi, g_e, g_xi, None, g_pos, *pgrads)
+        return head + tuple(pgrads)
 
 
 # ------------------------------------------------------------------------------------------
@@ -508,30 +609,21 @@ class GCPInteractions(nn.Module):
             raise NotImplementedError(f"gcpnet_b200.GCPInteractions: {what} is not covered by the sm_100a kernels "
                                       "(and there is no eager fallback)")
 
-        sel = _get(cfg, "selected_GCP", None)
-        sel_name = getattr(getattr(sel, "func", sel), "__name__", None) or str(_get(sel, "_target_", "") or "")
-        if sel is not None and sel_name and not sel_name.endswith("GCP2"):
-            unsupported(f"selected_GCP={sel_name} (only GCP2)")
-        if autoregressive:
-            unsupported("autoregressive=True")
-        if self.pre_norm:
-            unsupported("layer_cfg.pre_norm=True")
+        _check_gcp_flags(cfg, "GCPInteractions")
         if int(_get(layer_cfg, "num_feedforward_layers", 2)) != 2:
             unsupported("num_feedforward_layers != 2")
-        if not bool(_get(cfg, "vector_gate", True)):
-            unsupported("vector_gate=False")
-        if int(_get(cfg, "scalar_gate", 0) or 0) > 0:
-            unsupported("scalar_gate > 0")
-        for flag in ("frame_gate", "sigma_frame_gate", "vector_frame_residual", "ablate_frame_updates", "ablate_scalars",
-                     "ablate_vectors", "enable_e3_equivariance"):
-            if bool(_get(cfg, flag, False)):
-                unsupported(f"cfg.{flag}=True")
+        if bool(_get(cfg, "enable_e3_equivariance", False)):
+            unsupported("cfg.enable_e3_equivariance=True")
         if self.updating_node_positions and not self.ablate_x_force_update:
             unsupported("ablate_x_force_update=False (force-based position update)")
-        nl = _get(cfg, "nonlinearities", None)
-        if nl is None:
-            nl = (_get(cfg, "scalar_nonlinearity", "relu"), _get(cfg, "vector_nonlinearity", None))
+        if self.autoregressive and self.pre_norm:
+            unsupported("autoregressive=True with pre_norm=True")
+        # (the reference's `nonlinearities` argument only reaches the MIDDLE feed-forward GCPs, gcpnet.py:1001-1002,1025-1029,
+        # which do not exist with two feed-forward layers)
+        nl = _nonlinearities(cfg)
         mp_cfg = _get(layer_cfg, "mp_cfg", None)
+        # reduce_function: "add" for autoregressive layers (gcpnet.py:984).  A call WITH node_rep_regressive divides the two
+        # summed passes by the in-degree (gcpnet.py:1099-1114) = a mean over the destination segment of the merged edge set.
         self.spec = _cabi.LayerSpec(
             node_dims, edge_dims,
             num_message_layers=int(_get(mp_cfg, "num_message_layers", 8)),
@@ -541,8 +633,9 @@ class GCPInteractions(nn.Module):
             scalar_nonlinearity=nl[0], vector_nonlinearity=nl[1],
             nonlinearity_slope=float(_get(layer_cfg, "nonlinearity_slope", 1e-2)),
             use_residual_message_gcp=bool(_get(mp_cfg, "use_residual_message_gcp", True)),
-            enable_e3_equivariance=False, reduce_function="mean",
-            updating_node_positions=self.updating_node_positions, node_positions_weight=self.node_positions_weight)
+            enable_e3_equivariance=False, reduce_function="add" if self.autoregressive else "mean",
+            updating_node_positions=self.updating_node_positions, node_positions_weight=self.node_positions_weight,
+            pre_norm=self.pre_norm)
         spec = self.spec
         for m in spec.message_mods + spec.ff_mods + ([spec.pos_mod] if spec.pos_mod else []):
             if not 1 <= m[5] <= 16:
@@ -555,7 +648,7 @@ class GCPInteractions(nn.Module):
         if spec.pos_mod:
             self.node_position_update_network = nn.ModuleList([GCP2Params(*spec.pos_mod[1:6])])
         self._param_list = None
-        self._struct_cache = None
+        self._struct_cache = {}
         self._prepacked = None
         self._grad_sink = None   # flat fp32 view the backward writes the parameter gradients into (gcpnet_b200.ddp)
         self._grad_hook = None   # hook(layer, sink) -> callable run after the end-of-backward join (or None)
@@ -572,18 +665,23 @@ class GCPInteractions(nn.Module):
 
     def _apply(self, fn, *a, **k):  # .to() / .cuda() replace parameter storage
         self._param_list = None
-        self._struct_cache = None
+        self._struct_cache = {}
         return super()._apply(fn, *a, **k)
 
-    def _layer_struct(self, params, training: bool) -> _cabi.Layer:
+    def _layer_struct(self, params, training: bool, ar_call: bool = False) -> _cabi.Layer:
         ptrs = tuple(p.data_ptr() for p in params)
-        key = (ptrs, training, self._rng_counter.data_ptr())
-        if self._struct_cache is not None and self._struct_cache[0] == key:
-            return self._struct_cache[1]
+        key = (ptrs, training, self._rng_counter.data_ptr(), ar_call)
+        hit = self._struct_cache.get(key)
+        if hit is not None:
+            return hit
         table = dict(zip(self.spec.names, ptrs))
         layer = self.spec.make_layer(lambda n: table[n], training=training, p_drop=self.dropout_p, seed=self._seed,
                                      rng_counter=self._rng_counter.data_ptr())
-        self._struct_cache = (key, layer)
+        if ar_call:  # two summed passes / in-degree = mean over the merged destination segment (gcpnet.py:1099-1114)
+            layer.autoregressive, layer.reduce_mean = 1, 1
+        if len(self._struct_cache) > 8:
+            self._struct_cache.clear()
+        self._struct_cache[key] = layer
         return layer
 
     def prepack(self, num_nodes: int, num_edges: int, stream: Optional[torch.cuda.Stream] = None) -> None:
@@ -596,7 +694,7 @@ class GCPInteractions(nn.Module):
         if not params[0].is_cuda:
             raise RuntimeError("gcpnet_b200: prepack needs the module on a CUDA device")
         training = bool(self.training and self.dropout_p > 0.0)
-        layer = self._layer_struct(params, training)
+        layer = self._layer_struct(params, training, False)
         plan = _cabi.Plan()
         _lib.check(lib.gcpnet_layer_plan(C.byref(layer), int(num_nodes), int(num_edges), C.byref(plan)), "gcpnet_layer_plan")
         packed = torch.empty(max(int(plan.packed_floats), 1), dtype=torch.float32, device=params[0].device)
@@ -611,8 +709,8 @@ class GCPInteractions(nn.Module):
             ev.record(side)
         if side is not cur and not torch.cuda.is_current_stream_capturing():
             packed.record_stream(side)  # allocated on the caller's stream, written on `side`
-        self._prepacked = ((int(num_nodes), int(num_edges), training, tuple((p.data_ptr(), p._version) for p in params)),
-                           packed, ev)
+        self._prepacked = ((int(num_nodes), int(num_edges), training, False,
+                            tuple((p.data_ptr(), p._version) for p in params)), packed, ev)
 
     # -- forward ----------------------------------------------------------------------------
     def forward(self, node_rep, edge_rep, edge_index, frames, node_rep_regressive=None, node_mask=None, node_pos=None):
@@ -620,10 +718,12 @@ class GCPInteractions(nn.Module):
         e, xi = edge_rep[0], edge_rep[1]
         s, v = self.node_dims
         se, ve = self.edge_dims
-        if node_rep_regressive is not None:
-            raise NotImplementedError("gcpnet_b200.GCPInteractions: autoregressive forward is not covered")
-        if node_mask is not None and not bool(node_mask.all()):
-            raise NotImplementedError("gcpnet_b200.GCPInteractions: a node_mask that drops nodes is not covered")
+        ar_call = node_rep_regressive is not None
+        if ar_call and self.pre_norm:
+            raise NotImplementedError("gcpnet_b200.GCPInteractions: node_rep_regressive with pre_norm=True is not covered")
+        if ar_call and not self.autoregressive:
+            # the reference would run the two passes with this layer's "mean" reduce and divide AGAIN by the in-degree
+            raise NotImplementedError("gcpnet_b200.GCPInteractions: node_rep_regressive needs a layer built with autoregressive=True")
         for t, name in ((h, "node scalars"), (chi, "node vectors"), (e, "edge scalars"), (xi, "edge vectors"),
                         (edge_index, "edge_index"), (frames, "frames")):
             _check_cuda(t, name)
@@ -657,9 +757,19 @@ class GCPInteractions(nn.Module):
         if N == 0:
             out = ScalarVector(h.clone(), chi.clone())
             return (out, node_pos.clone()) if self.updating_node_positions else out
-        gv = graph_views(edge_index, frames, N)
+        hg = chig = None
+        if ar_call:
+            # gather table of the two passes (gcpnet.py:1083-1097): row 2i = node_rep[i], row 2i+1 = node_rep_regressive[i]
+            h_ar, chi_ar = node_rep_regressive[0], node_rep_regressive[1]
+            shape(h_ar, (N, s), "autoregressive node scalars")
+            shape(chi_ar, (N, v, 3), "autoregressive node vectors")
+            hg = torch.stack((h, h_ar), dim=1).reshape(2 * N, s)
+            chig = torch.stack((chi, chi_ar), dim=1).reshape(2 * N, v, 3)
+        # views of the batch: CSR orders, mean frames; with a node mask the masked frames / subgraph mean frames (no host
+        # synchronisation: an all-true mask gives the unmasked numbers)
+        gv = graph_views(edge_index, frames, N, autoregressive=ar_call, node_mask=node_mask)
         self._grad_mode = torch.is_grad_enabled()  # Function.forward itself always runs with grad disabled
-        outs = _LayerFn.apply(self, gv, h, chi, e, xi, frames, node_pos, *self._params_in_order())
+        outs = _LayerFn.apply(self, gv, h, chi, e, xi, gv.frames, node_pos, hg, chig, *self._params_in_order())
         if self.updating_node_positions:
             return ScalarVector(outs[0], outs[1]), outs[2]
         return ScalarVector(outs[0], outs[1])

@@ -72,6 +72,9 @@ typedef struct gcpnet_layer {
   const float *ln0_w, *ln0_b, *ln1_w, *ln1_b; /* gcp_norm.{0,1}.scalar_norm.{weight,bias} */
   int32_t ln_grad_off[4];
   int32_t n_edge_params, n_node_params;
+  int32_t pre_norm;                /* layer_cfg.pre_norm (gcpnet.py:1188-1189,1223-1224,1245): gcp_norm.0 before the message
+                                      passing, gcp_norm.1 after the first residual, none at the end */
+  int32_t autoregressive;          /* 1: the graph carries gather ids (gcpnet_graph_build_autoregressive); FFMA edge kernels */
 } gcpnet_layer;
 
 /* Destination- and source-sorted views of one graph batch, built by gcpnet_graph_build and shared
@@ -84,7 +87,18 @@ typedef struct gcpnet_graph {
   const int32_t* dst_ptr;  /* [N+1] CSR pointer over `dst` */
   const int32_t* src_pos;  /* [E] sorted positions grouped by source node (stable) */
   const int32_t* src_ptr;  /* [N+1] CSR pointer over src_pos */
-  const float* fbar;       /* [N][9] mean frame over the edges leaving each node (0 if none) */
+  const float* fbar;       /* [N][9] mean frame over the edges leaving each node (0 if none): node-side scalarize of the
+                              feed-forward GCPs (comp/__init__.py:316-323); under a node mask the subgraph version */
+  /* ---- optional views (NULL / 0 when absent) ---- */
+  const float* fbar_pos;   /* [N][9] node mask: mean frame for the position-update GCP (full graph, masked edges give zero
+                              frames but count, comp/__init__.py:294-300,316-323); NULL = fbar */
+  const uint8_t* node_mask; /* [N] 1 = node takes part in the update (gcpnet.py:1202-1217,1249-1251); NULL = all */
+  const int32_t* gsrc;     /* [E] autoregressive: row of the gather table (2 * node + flag) holding the source features */
+  const int32_t* gdst;     /* [E] same for the destination features */
+  const int32_t* vdst_ptr; /* [2N+1] CSR over gather rows of the sorted positions (by gdst) */
+  const int32_t* vsrc_ptr; /* [2N+1] CSR over gather rows of vsrc_pos (by gsrc) */
+  const int32_t* vsrc_pos; /* [E] sorted positions grouped by gsrc */
+  int64_t num_gather_rows; /* 2N (autoregressive) or 0 */
 } gcpnet_graph;
 
 /* Sizes the caller must allocate for one layer on one graph (all in floats unless noted). */
@@ -101,6 +115,8 @@ typedef struct gcpnet_plan {
   int64_t packed_floats;         /* packed (chunked, padded) copy of the layer's weights, rewritten by every forward */
   int32_t tc_edge_path;          /* 1: this layer's edge kernels can run on the tcgen05 tensor-core path */
   int32_t reserved;
+  int64_t prenorm_floats;        /* pre_norm: N * (s+3v) normalised layer input (forward, kept for backward) */
+  int64_t prenorm_ws_floats;     /* pre_norm: backward workspace (cotangent of the normalised input, row statistics, partials) */
 } gcpnet_plan;
 
 typedef struct gcpnet_forward_io {
@@ -112,6 +128,9 @@ typedef struct gcpnet_forward_io {
   float* packed;       /* plan.packed_floats: written by the forward call, read by the matching backward */
   int32_t packed_ready; /* 1: `packed` already holds this layer's packed weights (gcpnet_layer_pack): skip the pack kernels */
   int32_t reserved;
+  const float *h_gather, *chi_gather; /* autoregressive: [2N][s], [2N][v][3] gather table, row 2i = node_rep[i], row 2i+1 =
+                                         node_rep_regressive[i] (gcpnet.py:1065-1116); NULL otherwise */
+  float* prenorm;       /* plan.prenorm_floats (pre_norm layers) */
 } gcpnet_forward_io;
 
 typedef struct gcpnet_backward_io {
@@ -122,6 +141,11 @@ typedef struct gcpnet_backward_io {
   float* g_params;                               /* [n_edge_params + n_node_params] flat parameter gradient (overwritten) */
   float *ws_agg, *ws_edge, *ws_edge_partial, *ws_node_partial; /* workspaces sized by the plan */
   const float* packed;                           /* the forward call's packed weights */
+  const float *h_gather, *chi_gather;            /* autoregressive: the forward's gather table */
+  float *g_h_gather, *g_chi_gather;              /* autoregressive: [2N] cotangent of the gather table; rows 2i additionally
+                                                    carry the direct cotangent of node i, g_h / g_chi are then scratch */
+  const float* prenorm;                          /* pre_norm: the forward's normalised input */
+  float* ws_prenorm;                             /* plan.prenorm_ws_floats */
 } gcpnet_backward_io;
 
 int gcpnet_version(void);
@@ -155,9 +179,41 @@ int gcpnet_graph_build(const int64_t* edge_index, int64_t num_edges, int64_t num
                        int32_t* perm, int32_t* src, int32_t* dst, int32_t* dst_ptr, int32_t* src_pos,
                        int32_t* src_ptr, float* fbar, void* workspace, size_t workspace_bytes, void* stream);
 
-/* frames = localize(x, edge_index) without node mask (comp/__init__.py:220-269). */
+/* Autoregressive layers (GCPInteractions.autoregressive_forward, gcpnet.py:1065-1116): edges with row < col read node_rep
+ * at both ends, the others node_rep_regressive; both message sets are summed per destination and divided by the in-degree
+ * (clamped at 1).  Same outputs as gcpnet_graph_build (sorted by destination; inside a destination, row < col edges
+ * first) plus the gather views of gcpnet_graph.  No boolean-mask indexing, no host synchronisation. */
+size_t gcpnet_graph_ar_workspace_bytes(int64_t num_edges, int64_t num_nodes);
+int gcpnet_graph_build_autoregressive(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes, const float* frames,
+                                      int32_t* perm, int32_t* src, int32_t* dst, int32_t* dst_ptr, int32_t* src_pos,
+                                      int32_t* src_ptr, float* fbar, int32_t* gsrc, int32_t* gdst, int32_t* vdst_ptr,
+                                      int32_t* vsrc_ptr, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Node mask (gcpnet.py:1202-1217; comp/__init__.py:294-300): from the views of gcpnet_graph_build and node_mask[N] derive
+ *   frames_eff[E][9]  frames with the rows of edges that touch a masked-out node zeroed (predicated: masked frames may
+ *                     hold inf, comp/__init__.py:232-236) -- what the message GCPs scalarise with,
+ *   fbar_ff[N][9]     mean frame of the feed-forward GCPs on the mask's subgraph, relabelled nodes indexing the ORIGINAL
+ *                     mask exactly as the reference does (gcpnet.py:1232-1239 passes node_mask to scalarize),
+ *   fbar_pos[N][9]    mean frame of the position-update GCP (full graph, masked edges contribute zero frames).
+ * workspace: (num_nodes + 1) * 4 bytes + gcpnet_graph_workspace_bytes. */
+int gcpnet_graph_mask(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes, const float* frames,
+                      const uint8_t* node_mask, const gcpnet_graph* graph, float* frames_eff, float* fbar_ff,
+                      float* fbar_pos, void* workspace, size_t workspace_bytes, void* stream);
+
+/* frames = localize(x, edge_index) (comp/__init__.py:220-269); node_mask may be NULL; with a mask the frames of edges that
+ * touch a masked-out node are +inf, as in the reference. */
 int gcpnet_localize(const float* pos, const int64_t* edge_index, int64_t num_edges, int norm_x_diff,
                     float* frames, void* stream);
+int gcpnet_localize_masked(const float* pos, const int64_t* edge_index, int64_t num_edges, int norm_x_diff,
+                           const uint8_t* node_mask, float* frames, void* stream);
+
+/* centralize / decentralize (comp/__init__.py:170-217): centroid[g] = mean of the (unmasked) rows of pos with
+ * batch_index == g; centered = pos - centroid[batch] (masked-out rows: +inf).  batch_index must be non-decreasing (a PyG
+ * Batch guarantees it).  decentralize adds the centroids back. */
+int gcpnet_centralize(const float* pos, const int64_t* batch_index, int64_t num_nodes, int64_t num_graphs,
+                      const uint8_t* node_mask, float* centroid, float* centered, void* stream);
+int gcpnet_decentralize(const float* pos, const int64_t* batch_index, int64_t num_nodes, const float* centroid,
+                        const uint8_t* node_mask, float* out, void* stream);
 
 /* Pack this layer's weights into `packed` (plan.packed_floats) ahead of time -- the weights are known at the start of a
  * step, so a caller can run all layers' packing on a side stream while the first layers compute, then pass

@@ -100,8 +100,9 @@ def safe_norm(x: Tensor, dim: int, eps: float = 1e-8) -> Tensor:
     return torch.sqrt((x * x).sum(dim=dim) + eps) + eps
 
 
-def localize(x: Tensor, edge_index: Tensor, norm_x_diff: bool = True) -> Tensor:
-    """comp:220-269 without node_mask: frames[e] = [x_diff; x_cross; x_vertical] (rows)."""
+def localize(x: Tensor, edge_index: Tensor, norm_x_diff: bool = True, node_mask: Optional[Tensor] = None) -> Tensor:
+    """comp:220-269: frames[e] = [x_diff; x_cross; x_vertical] (rows); with a node mask the frames of edges that touch a
+    masked-out node are +inf (comp:229-236,262-264)."""
     row, col = edge_index[0], edge_index[1]
     xr, xc = x[row], x[col]
     d = xr - xc
@@ -110,17 +111,61 @@ def localize(x: Tensor, edge_index: Tensor, norm_x_diff: bool = True) -> Tensor:
         d = d / (torch.sqrt((d * d).sum(dim=1, keepdim=True)) + 1)
         c = c / (torch.sqrt((c * c).sum(dim=1, keepdim=True)) + 1)
     v = torch.linalg.cross(d, c, dim=-1)
-    return torch.stack((d, c, v), dim=1)
+    f = torch.stack((d, c, v), dim=1)
+    if node_mask is not None:
+        em = node_mask[row] & node_mask[col]
+        f = torch.where(em.view(-1, 1, 1), f, torch.full_like(f, float("inf")))
+    return f
+
+
+def centralize(x: Tensor, batch_index: Tensor, node_mask: Optional[Tensor] = None):
+    """comp:170-200: (centroid per graph, centred entities); masked rows of the centred tensor are +inf."""
+    if node_mask is not None:
+        idx = batch_index[node_mask]
+        G = int(idx.max()) + 1 if idx.numel() else 0
+        cen = segment_reduce(x[node_mask], idx, G, "mean")
+        out = torch.full_like(x, float("inf"))
+        out[node_mask] = x[node_mask] - cen[batch_index][node_mask]
+        return cen, out
+    G = int(batch_index.max()) + 1 if batch_index.numel() else 0
+    cen = segment_reduce(x, batch_index, G, "mean")
+    return cen, x - cen[batch_index]
+
+
+def decentralize(x: Tensor, batch_index: Tensor, centroid: Tensor, node_mask: Optional[Tensor] = None) -> Tensor:
+    """comp:203-217."""
+    if node_mask is not None:
+        out = torch.full_like(x, float("inf"))
+        out[node_mask] = x[node_mask] + centroid[batch_index][node_mask]
+        return out
+    return x + centroid[batch_index]
+
+
+def subgraph(subset: Tensor, edge_index: Tensor, edge_attr: Tensor, num_nodes: int):
+    """torch_geometric.utils.subgraph 2.1.0 with relabel_nodes=True (call site gcpnet.py:1212-1217): keep the edges whose
+    two ends are in `subset`, relabel nodes to 0..k-1 in subset order."""
+    nm = torch.zeros(num_nodes, dtype=torch.bool)
+    nm[subset] = True
+    em = nm[edge_index[0]] & nm[edge_index[1]]
+    relabel = torch.zeros(num_nodes, dtype=torch.long)
+    relabel[subset] = torch.arange(subset.numel())
+    return relabel[edge_index[:, em]], edge_attr[em]
 
 
 def frame_scalars(D: Tensor, edge_index: Tensor, frames: Tensor, node_inputs: bool,
-                  e3: bool, dim_size: int) -> Tensor:
+                  e3: bool, dim_size: int, node_mask: Optional[Tensor] = None) -> Tensor:
     """comp:272-325 (scalarize).  D is [M, 3(xyz), 3(c)] = vector_down_frames output.
     q[m, 3c+a] = sum_xyz frames[edge, a, xyz] * D[src, xyz, c]; for node inputs the per-edge
-    values (gathered by SOURCE node) are averaged over SOURCE node (comp:316-323)."""
-    row = edge_index[0]
+    values (gathered by SOURCE node) are averaged over SOURCE node (comp:316-323).  With a node mask the rows of edges
+    whose two ends are not both unmasked are zero and their frames (possibly inf) are never read (comp:294-300)."""
+    row, col = edge_index[0], edge_index[1]
     Dm = D[row] if node_inputs else D
-    q = torch.einsum("eax,exc->eca", frames, Dm)  # [E, c, a]
+    if node_mask is not None:
+        em = node_mask[row] & node_mask[col]
+        q = torch.zeros((edge_index.shape[1], 3, 3), dtype=D.dtype)
+        q[em] = torch.einsum("eax,exc->eca", frames[em], Dm[em])
+    else:
+        q = torch.einsum("eax,exc->eca", frames, Dm)  # [E, c, a]
     if e3:
         q = torch.cat((q[:, :, :1], q[:, :, 1:2].abs(), q[:, :, 2:]), dim=2)  # comp:305-309
     q = q.reshape(q.shape[0], 9)
@@ -139,7 +184,7 @@ def gcp2_hidden_dim(vi: int, vo: int, bottleneck: int) -> int:
 
 def gcp2(p: Dict[str, Tensor], prefix: str, s: Tensor, V: Tensor, edge_index: Tensor,
          frames: Tensor, *, node_inputs: bool, act_s, act_v, vector_residual: bool, e3: bool,
-         vector_gate: bool = True):
+         vector_gate: bool = True, node_mask: Optional[Tensor] = None):
     """SURVEY Appendix A steps 1-11.  ``p[prefix + 'scalar_out.weight']`` etc.
     Returns (s', V') or s' if the module has no vector output (no ``vector_up``)."""
     Wd = p[prefix + "vector_down.weight"]  # [hd, vi]
@@ -149,7 +194,7 @@ def gcp2(p: Dict[str, Tensor], prefix: str, s: Tensor, V: Tensor, edge_index: Te
     H = Vt @ Wd.t()  # [M,3,hd]  (:420)
     n = safe_norm(H, dim=-2)  # [M,hd]    (:421)
     D = Vt @ Wdf.t()  # [M,3,3]   (:426)
-    q = frame_scalars(D, edge_index, frames, node_inputs, e3, V.shape[0])  # (:427-435)
+    q = frame_scalars(D, edge_index, frames, node_inputs, e3, V.shape[0], node_mask)  # (:427-435)
     z = torch.cat((s, n, q), dim=-1)  # (:422,436)
     t = z @ Ws.t() + bs  # (:441)
     if (prefix + "vector_up.weight") not in p:
@@ -171,7 +216,7 @@ def gcp2(p: Dict[str, Tensor], prefix: str, s: Tensor, V: Tensor, edge_index: Te
 # --------------------------------------------------------------------------------------
 def message_passing(p: Dict[str, Tensor], prefix: str, cfg: OracleConfig, h: Tensor, chi: Tensor,
                     e: Tensor, xi: Tensor, edge_index: Tensor, frames: Tensor,
-                    reduce: Optional[str] = None):
+                    reduce: Optional[str] = None, node_mask: Optional[Tensor] = None):
     row, col = edge_index[0], edge_index[1]
     L = cfg.num_message_layers
     a_s = activation(cfg.scalar_nonlinearity, cfg.nonlinearity_slope)
@@ -179,7 +224,7 @@ def message_passing(p: Dict[str, Tensor], prefix: str, cfg: OracleConfig, h: Ten
     ident = activation(None)
     ms = torch.cat((h[row], e, h[col]), dim=-1)  # (:911-917) order matters
     mV = torch.cat((chi[row], xi, chi[col]), dim=-2)
-    kw = dict(node_inputs=False, e3=cfg.enable_e3_equivariance, vector_gate=cfg.vector_gate)
+    kw = dict(node_inputs=False, e3=cfg.enable_e3_equivariance, vector_gate=cfg.vector_gate, node_mask=node_mask)
 
     def G(k, s, V):
         first_or_last = (k == 0) or (k == L - 1 and L > 1)
@@ -220,15 +265,32 @@ def gcp_layernorm(p: Dict[str, Tensor], prefix: str, cfg: OracleConfig, s: Tenso
 
 
 # --------------------------------------------------------------------------------------
-# GCPInteractions.forward (gcpnet.py:1160-1262), no node_mask, not autoregressive
+# GCPInteractions.forward (gcpnet.py:1160-1262)
 # --------------------------------------------------------------------------------------
+def autoregressive_message_passing(p, prefix, cfg, h, chi, e, xi, edge_index, frames, h_ar, chi_ar, node_mask=None):
+    """autoregressive_forward (gcpnet.py:1065-1116): edges with row < col see node_rep, the others node_rep_regressive (at
+    both ends); both passes reduce with "add"; the sum is divided by the in-degree over ALL edges, clamped at 1."""
+    row, col = edge_index[0], edge_index[1]
+    em = row < col
+    fs, fV = message_passing(p, prefix, cfg, h, chi, e[em], xi[em], edge_index[:, em], frames[em], reduce="add",
+                             node_mask=node_mask)
+    bs, bV = message_passing(p, prefix, cfg, h_ar, chi_ar, e[~em], xi[~em], edge_index[:, ~em], frames[~em], reduce="add",
+                             node_mask=node_mask)
+    cnt = torch.bincount(col, minlength=h.shape[0]).clamp(min=1).to(h.dtype)
+    return (fs + bs) / cnt.unsqueeze(-1), (fV + bV) / cnt.view(-1, 1, 1)
+
+
 def interactions_forward(p: Dict[str, Tensor], cfg: OracleConfig, h: Tensor, chi: Tensor,
                          e: Tensor, xi: Tensor, edge_index: Tensor, frames: Tensor,
                          node_pos: Optional[Tensor] = None, prefix: str = "",
-                         drop_masks: Optional[Sequence[Tuple[Tensor, Tensor]]] = None):
+                         drop_masks: Optional[Sequence[Tuple[Tensor, Tensor]]] = None,
+                         node_mask: Optional[Tensor] = None,
+                         node_rep_regressive: Optional[Tuple[Tensor, Tensor]] = None):
     """One GCPNet layer.  ``drop_masks`` = optional [(scalar_mask[N,s], vector_mask[N,v]) x 2]
     of already-scaled keep masks (value 0 or 1/(1-p)) to restate train-mode GCPDropout
-    (comp:97-135) with externally supplied randomness; None = eval mode."""
+    (comp:97-135) with externally supplied randomness; None = eval mode (with a node mask the rows of the
+    masks are those of the UNMASKED nodes, in order).  ``node_mask`` (bool[N]) and ``node_rep_regressive`` follow
+    gcpnet.py:1202-1217,1249-1251 and :1191-1195."""
     a_s = activation(cfg.scalar_nonlinearity, cfg.nonlinearity_slope)
     a_v = activation(cfg.vector_nonlinearity, cfg.nonlinearity_slope)
     ident = activation(None)
@@ -242,12 +304,22 @@ def interactions_forward(p: Dict[str, Tensor], cfg: OracleConfig, h: Tensor, chi
 
     if cfg.pre_norm:  # (:1188-1189)
         h, chi = gcp_layernorm(p, prefix + "gcp_norm.0.", cfg, h, chi)
-    ms, mV = message_passing(p, prefix + "interaction.", cfg, h, chi, e, xi, edge_index, frames)
+    if node_rep_regressive is not None:  # (:1191-1195)
+        ms, mV = autoregressive_message_passing(p, prefix + "interaction.", cfg, h, chi, e, xi, edge_index, frames,
+                                                node_rep_regressive[0], node_rep_regressive[1], node_mask=node_mask)
+    else:
+        ms, mV = message_passing(p, prefix + "interaction.", cfg, h, chi, e, xi, edge_index, frames, node_mask=node_mask)
+    res_h, res_chi = h, chi  # node_rep_residual (:1203)
+    ff_ei, ff_frames = edge_index, frames
+    if node_mask is not None:  # (:1202-1217)
+        h, chi, ms, mV = h[node_mask], chi[node_mask], ms[node_mask], mV[node_mask]
+        if not bool(node_mask.all()) and edge_index.shape[1] > 0:
+            ff_ei, ff_frames = subgraph(torch.where(node_mask)[0], edge_index, frames, node_mask.shape[0])
     ds, dV = drop(0, ms, mV)
     s, V = h + ds, chi + dV  # (:1220)
     s, V = gcp_layernorm(p, prefix + ("gcp_norm.1." if cfg.pre_norm else "gcp_norm.0."), cfg, s, V)  # (:1223-1226)
 
-    # feed-forward stack, node_inputs=True on the full edge_index (:1229-1239)
+    # feed-forward stack, node_inputs=True (:1229-1239); under a mask: on the subgraph, with the ORIGINAL [N] mask
     nff = cfg.num_feedforward_layers
     fs, fV = s, V
     for i in range(nff):
@@ -259,19 +331,22 @@ def interactions_forward(p: Dict[str, Tensor], cfg: OracleConfig, h: Tensor, chi
             acts = (a_s, a_v)
         # first and last FF GCP are built without vector residual (:1003-1004); middle ones use cfg's
         vres = cfg.vector_residual if 0 < i < nff - 1 else False
-        fs, fV = gcp2(p, f"{prefix}feedforward_network.{i}.", fs, fV, edge_index, frames,
+        fs, fV = gcp2(p, f"{prefix}feedforward_network.{i}.", fs, fV, ff_ei, ff_frames,
                       node_inputs=True, act_s=acts[0], act_v=acts[1], vector_residual=vres, e3=e3,
-                      vector_gate=cfg.vector_gate)
+                      vector_gate=cfg.vector_gate, node_mask=node_mask)
     ds, dV = drop(1, fs, fV)
     s, V = s + ds, V + dV  # (:1242)
     if not cfg.pre_norm:
         s, V = gcp_layernorm(p, prefix + "gcp_norm.1.", cfg, s, V)  # (:1245-1246)
+    if node_mask is not None:  # (:1249-1251) masked-out nodes keep the (pre-normalised) layer input
+        s = res_h.clone().index_put((torch.where(node_mask)[0],), s)
+        V = res_chi.clone().index_put((torch.where(node_mask)[0],), V)
     if not cfg.updating_node_positions:
         return (s, V)
     # derive_x_update (:1118-1158) with the force branch ablated (every shipped NMS config)
     _, pV = gcp2(p, f"{prefix}node_position_update_network.0.", s, V, edge_index, frames,
                  node_inputs=True, act_s=a_s, act_v=a_v, vector_residual=False, e3=e3,
-                 vector_gate=cfg.vector_gate)
+                 vector_gate=cfg.vector_gate, node_mask=node_mask)
     upd = (pV[:, 0, :] * cfg.node_positions_weight).clamp(min=-100, max=100)  # (:1156-1158)
     return (s, V), node_pos + upd  # (:1258)
 

@@ -41,6 +41,34 @@ CASES: Dict[str, dict] = {
     "tiny_one_message_layer": dict(cfg=dict(node_dims=(8, 4), edge_dims=(4, 2), num_message_layers=1,
                                              bottleneck=2, default_bottleneck=2),
                                    graph=("random", 10, 30), seed=16),
+    # ---- round 2: node mask (CPD encoder path, gcpnet.py:1202-1217,1249-1251), autoregressive layers (:1065-1116), pre_norm
+    # CPD hidden dims, kNN graph, ~8 % of the nodes masked out (frames of masked edges are +inf, as localize writes them)
+    "cpd_masked_knn": dict(cfg=dict(node_dims=(100, 16), edge_dims=(32, 4)), graph=("knn", 2, 40, 8), seed=17, mask_frac=0.08),
+    # NMS dims with position update under a mask: the position GCP runs on all nodes with its own masked mean frames
+    "nms_masked_pos": dict(cfg=dict(node_dims=(64, 16), edge_dims=(32, 4), updating_node_positions=True),
+                           graph=("nms", 6, 5), seed=18, mask_frac=0.2),
+    # small dims, random multigraph (self loops, duplicates, isolated nodes) under a mask
+    "tiny_masked_multigraph": dict(cfg=dict(node_dims=(8, 4), edge_dims=(4, 2), num_message_layers=2, bottleneck=2,
+                                            default_bottleneck=2, updating_node_positions=True),
+                                   graph=("random", 14, 60), seed=19, mask_frac=0.3),
+    # CPD decoder layer: autoregressive=True, node_rep_regressive = encoder embeddings, kNN graph (row<col split ~50/50)
+    "cpd_autoregressive": dict(cfg=dict(node_dims=(100, 16), edge_dims=(32, 4)), graph=("knn", 2, 30, 8), seed=20,
+                               autoregressive=True, regressive=True),
+    # the same with a node mask (GCPNetCPDLitModule passes both, gcpnet_cpd_module.py:196-207)
+    "tiny_autoregressive_masked": dict(cfg=dict(node_dims=(12, 4), edge_dims=(6, 2), num_message_layers=3, bottleneck=2,
+                                                default_bottleneck=2), graph=("random", 16, 70), seed=21,
+                                       autoregressive=True, regressive=True, mask_frac=0.25),
+    # an autoregressive layer called WITHOUT node_rep_regressive: plain message passing with reduce "add" (gcpnet.py:984)
+    "tiny_autoregressive_plain_call": dict(cfg=dict(node_dims=(8, 4), edge_dims=(4, 2), num_message_layers=2, bottleneck=2,
+                                                    default_bottleneck=2, reduce_function="add"),
+                                           graph=("random", 12, 40), seed=22, autoregressive=True),
+    # pre_norm (gcpnet.py:1188-1189,1223-1224,1245) with position update, and under a mask
+    "tiny_pre_norm": dict(cfg=dict(node_dims=(16, 4), edge_dims=(8, 2), num_message_layers=2, bottleneck=2,
+                                   default_bottleneck=2, pre_norm=True, updating_node_positions=True),
+                          graph=("knn", 2, 10, 4), seed=23),
+    "tiny_pre_norm_masked": dict(cfg=dict(node_dims=(16, 4), edge_dims=(8, 2), num_message_layers=2, bottleneck=2,
+                                          default_bottleneck=2, pre_norm=True), graph=("random", 15, 60), seed=24,
+                                 mask_frac=0.25),
 }
 
 
@@ -71,9 +99,23 @@ def build_graph(case: dict):
 
 
 def build_inputs(case: dict, dtype=torch.float32):
+    """Inputs of a case; round-2 cases add ``node_mask`` (bool[N]; the frames are then localize(..., node_mask): +inf on
+    masked edges) and ``regressive`` = (h_ar, chi_ar)."""
     cfg = build_cfg(case)
     ei, n, pos = build_graph(case)
-    return O.synthetic_layer_inputs(cfg, ei, n, seed=case["seed"], dtype=dtype, positions=pos)
+    inp = O.synthetic_layer_inputs(cfg, ei, n, seed=case["seed"], dtype=dtype, positions=pos)
+    g = torch.Generator().manual_seed(case["seed"] + 2000)
+    if case.get("mask_frac"):
+        mask = torch.rand(n, generator=g) >= case["mask_frac"]
+        mask[0] = False  # at least one masked-out node ...
+        mask[1] = True   # ... and one unmasked
+        inp["node_mask"] = mask
+        inp["frames"] = O.localize(inp["node_pos"].to(torch.float64), ei, node_mask=mask).to(dtype)
+    if case.get("regressive"):
+        s, v = cfg.node_dims
+        inp["regressive"] = (torch.randn(n, s, generator=g, dtype=torch.float64).to(dtype),
+                             torch.randn(n, v, 3, generator=g, dtype=torch.float64).to(dtype))
+    return inp
 
 
 def loss_weights(case: dict, cfg: O.OracleConfig, n: int, dtype=torch.float32):

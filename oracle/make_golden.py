@@ -45,7 +45,8 @@ def run_reference(name: str, case: dict):
     rcfg.default_bottleneck = cfg.default_bottleneck
     SV = ref.ScalarVector
     layer = ref.GCPInteractions(SV(*cfg.node_dims), SV(*cfg.edge_dims), cfg=rcfg, layer_cfg=rlayer,
-                                dropout=0.1, updating_node_positions=cfg.updating_node_positions)
+                                dropout=0.1, updating_node_positions=cfg.updating_node_positions,
+                                autoregressive=bool(case.get("autoregressive", False)))
     if "ckpt" in case:
         sd = ref_shim.load_checkpoint_state_dict(case["ckpt"][0])
         pre = f"interaction_layers.{case['ckpt'][1]}."
@@ -57,8 +58,17 @@ def run_reference(name: str, case: dict):
 
     inp = GC.build_inputs(case)
     leaves = {k: inp[k].clone().requires_grad_(True) for k in ("h", "chi", "e", "xi")}
-    out = layer((leaves["h"], leaves["chi"]), (leaves["e"], leaves["xi"]), inp["edge_index"],
-                inp["frames"], node_pos=inp["node_pos"] if cfg.updating_node_positions else None)
+    kw = {}
+    if "node_mask" in inp:
+        kw["node_mask"] = inp["node_mask"]
+    if "regressive" in inp:
+        leaves["h_ar"] = inp["regressive"][0].clone().requires_grad_(True)
+        leaves["chi_ar"] = inp["regressive"][1].clone().requires_grad_(True)
+        kw["node_rep_regressive"] = (leaves["h_ar"], leaves["chi_ar"])
+    # the masked path writes into its node_rep argument in place (gcpnet.py:1249-1251): hand it non-leaf tensors, as every
+    # caller in the reference does (the layer input is the embedding's / previous layer's output)
+    out = layer((leaves["h"] * 1.0, leaves["chi"] * 1.0), (leaves["e"], leaves["xi"]), inp["edge_index"],
+                inp["frames"], node_pos=inp["node_pos"] if cfg.updating_node_positions else None, **kw)
     n = inp["h"].shape[0]
     ch, cchi, cpos = GC.loss_weights(case, cfg, n)
     if cfg.updating_node_positions:
@@ -79,7 +89,8 @@ def run_reference(name: str, case: dict):
     for k, p in layer.named_parameters():
         rec["pgrad/" + k] = sample(p.grad if p.grad is not None else torch.zeros_like(p))
     rec["checksum_params"] = np.float64(sum(GC.checksum(v) for v in params.values()))
-    rec["checksum_inputs"] = np.float64(sum(GC.checksum(inp[k]) for k in ("h", "chi", "e", "xi", "frames")))
+    rec["checksum_inputs"] = np.float64(sum(GC.checksum(inp[k]) for k in ("h", "chi", "e", "xi")) + GC.checksum(
+        torch.nan_to_num(inp["frames"], posinf=3.0)))
     if "ckpt" in case:
         for k, v in params.items():
             rec["param/" + k] = v.numpy()

@@ -138,7 +138,8 @@ int emul_layer_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, con
   }
   if (g.num_edges > 0) {
     EdgeParams p = make_edge_params(l, g, lp.ops, lp.ef, false, io->packed);
-    p.h = io->h; p.chi = io->chi; p.e = io->e; p.xi = io->xi; p.frames = io->frames; p.msg = io->msg; p.saved = io->saved_edge;
+    p.h = io->h_gather ? io->h_gather : io->h; p.chi = io->chi_gather ? io->chi_gather : io->chi;
+    p.e = io->e; p.xi = io->xi; p.frames = io->frames; p.msg = io->msg; p.saved = io->saved_edge;
     int grid = lp.ef.grid; if (grid > 3) grid = 3;  // exercise the persistent loop
     int bad = 1;
     if (lp.ef.TE == 32) bad = by_slf(lp.ef.SLF, [&] { run_edge_fwd<32, 1>(p, grid); }, [&] { run_edge_fwd<32, 2>(p, grid); });
@@ -177,6 +178,7 @@ int emul_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, co
   const int W = l.s + 3 * l.v;
   NodeParams np = make_node_params(l, g, lp.ops, lp.nb, true, io->packed);
   np.saved = const_cast<float*>(io->saved_node);
+  np.h = io->h; np.chi = io->chi;
   np.g_out_h = io->g_out_h; np.g_out_chi = io->g_out_chi; np.g_out_pos = io->g_out_pos;
   np.g_x_h = io->g_h; np.g_x_chi = io->g_chi; np.g_agg = io->ws_agg; np.partial = io->ws_node_partial;
   const int ntn = (int)((g.num_nodes + lp.nb.TE - 1) / lp.nb.TE);
@@ -185,7 +187,8 @@ int emul_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, co
   else if (lp.nb.SLF == 4) run_node_bwd<4>(np, node_grid); else return fail("bad node tile");
   if (g.num_edges > 0) {
     EdgeParams ep = make_edge_params(l, g, lp.ops, lp.eb, true, io->packed);
-    ep.h = io->h; ep.chi = io->chi; ep.e = io->e; ep.xi = io->xi; ep.frames = io->frames;
+    ep.h = io->h_gather ? io->h_gather : io->h; ep.chi = io->chi_gather ? io->chi_gather : io->chi;
+    ep.e = io->e; ep.xi = io->xi; ep.frames = io->frames;
     ep.saved = const_cast<float*>(io->saved_edge); ep.gagg = io->ws_agg;
     ep.grow = io->ws_edge; ep.gcol = io->ws_edge + (size_t)g.num_edges * W; ep.ge = io->g_e; ep.gxi = io->g_xi;
     ep.partial = io->ws_edge_partial;
@@ -196,6 +199,16 @@ int emul_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, co
     if (lp.eb.TE == 48) bad = by_slf(lp.eb.SLF, [&] { run_edge_bwd<48, 1>(ep, edge_grid); }, [&] { run_edge_bwd<48, 2>(ep, edge_grid); });
     if (lp.eb.TE == 64) bad = by_slf(lp.eb.SLF, [&] { run_edge_bwd<64, 1>(ep, edge_grid); }, [&] { run_edge_bwd<64, 2>(ep, edge_grid); });
     if (bad) return fail("bad edge bwd tile");
+    if (g.gsrc != nullptr) {  // autoregressive: sums over the rows of the [2N] gather table (ar_cotangent_reduce_kernel)
+      for (int64_t u = 0; u < g.num_gather_rows; ++u)
+        for (int f = 0; f < W; ++f) {
+          float acc = 0.f;
+          if ((u & 1) == 0) acc = f < l.s ? io->g_h[(u >> 1) * l.s + f] : io->g_chi[(u >> 1) * 3 * l.v + (f - l.s)];
+          for (int q = g.vdst_ptr[u]; q < g.vdst_ptr[u + 1]; ++q) acc += ep.gcol[(size_t)q * W + f];
+          for (int q = g.vsrc_ptr[u]; q < g.vsrc_ptr[u + 1]; ++q) acc += ep.grow[(size_t)g.vsrc_pos[q] * W + f];
+          if (f < l.s) io->g_h_gather[u * l.s + f] = acc; else io->g_chi_gather[u * 3 * l.v + (f - l.s)] = acc;
+        }
+    } else
     for (int64_t i = 0; i < g.num_nodes; ++i)
       for (int f = 0; f < W; ++f) {
         float* out = f < l.s ? io->g_h + i * l.s + f : io->g_chi + i * 3 * l.v + (f - l.s);
@@ -211,6 +224,8 @@ int emul_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, co
     else for (int c = 0; c < node_grid; ++c) acc += io->ws_node_partial[(size_t)c * l.n_node_params + (i - l.n_edge_params)];
     io->g_params[i] = acc;
   }
+  if (l.pre_norm)  // gcp_norm.0 is applied (and differentiated) in front of the layer: the tiles never write these rows
+    for (int j = 0; j < 2 * l.s; ++j) io->g_params[l.ln_grad_off[0] + j] = 0.f;
   (void)plan;
   return 0;
 }

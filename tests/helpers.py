@@ -30,7 +30,7 @@ def load_case(name: str):
     inputs = GC.build_inputs(case)
     # RNG drift guard: regenerated weights/inputs must be the ones the reference saw
     cs_p = sum(GC.checksum(v) for v in params.values())
-    cs_i = sum(GC.checksum(inputs[k]) for k in ("h", "chi", "e", "xi", "frames"))
+    cs_i = sum(GC.checksum(inputs[k]) for k in ("h", "chi", "e", "xi")) + GC.checksum(torch.nan_to_num(inputs["frames"], posinf=3.0))
     assert abs(cs_p - float(fx["checksum_params"])) <= 1e-9 * max(1.0, abs(cs_p)), "weights regenerated differently"
     assert abs(cs_i - float(fx["checksum_inputs"])) <= 1e-9 * max(1.0, abs(cs_i)), "inputs regenerated differently"
     return case, cfg, params, inputs, fx
@@ -49,9 +49,16 @@ def oracle_forward_backward(case, cfg, params, inputs, dtype=torch.float32):
     p = {k: v.to(dtype).clone().requires_grad_(True) for k, v in params.items()}
     leaves = {k: inputs[k].to(dtype).clone().requires_grad_(True) for k in ("h", "chi", "e", "xi")}
     n = inputs["h"].shape[0]
+    kw = {}
+    if "node_mask" in inputs:
+        kw["node_mask"] = inputs["node_mask"]
+    if "regressive" in inputs:
+        leaves["h_ar"] = inputs["regressive"][0].to(dtype).clone().requires_grad_(True)
+        leaves["chi_ar"] = inputs["regressive"][1].to(dtype).clone().requires_grad_(True)
+        kw["node_rep_regressive"] = (leaves["h_ar"], leaves["chi_ar"])
     out = O.interactions_forward(p, cfg, leaves["h"], leaves["chi"], leaves["e"], leaves["xi"],
                                  inputs["edge_index"], inputs["frames"].to(dtype),
-                                 node_pos=inputs["node_pos"].to(dtype) if cfg.updating_node_positions else None)
+                                 node_pos=inputs["node_pos"].to(dtype) if cfg.updating_node_positions else None, **kw)
     ch, cchi, cpos = GC.loss_weights(case, cfg, n, dtype=dtype)
     if cfg.updating_node_positions:
         (oh, ochi), opos = out
@@ -108,13 +115,13 @@ def module_cfgs(cfg):
     return mcfg, lcfg
 
 
-def build_module(cfg, params=None, dropout=0.0, device="cuda"):
+def build_module(cfg, params=None, dropout=0.0, device="cuda", autoregressive=False):
     """gcpnet_b200.GCPInteractions for an OracleConfig, optionally loaded with reference-named weights."""
     import gcpnet_b200
 
     mcfg, lcfg = module_cfgs(cfg)
     layer = gcpnet_b200.GCPInteractions(cfg.node_dims, cfg.edge_dims, cfg=mcfg, layer_cfg=lcfg, dropout=dropout,
-                                        updating_node_positions=cfg.updating_node_positions)
+                                        updating_node_positions=cfg.updating_node_positions, autoregressive=autoregressive)
     if params is not None:
         layer.load_state_dict({k: v.detach().clone().float() for k, v in params.items()}, strict=True)
     return layer.to(device)
@@ -128,12 +135,19 @@ def module_forward_backward(layer, case, cfg, inputs, device="cuda"):
     frames = inputs["frames"].to(dev, torch.float32)
     n = inputs["h"].shape[0]
     ch, cchi, cpos = (t.to(dev) for t in GC.loss_weights(case, cfg, n))
+    kw = {}
+    if "node_mask" in inputs:
+        kw["node_mask"] = inputs["node_mask"].to(dev)
+    if "regressive" in inputs:
+        leaves["h_ar"] = inputs["regressive"][0].to(dev, torch.float32).clone().requires_grad_(True)
+        leaves["chi_ar"] = inputs["regressive"][1].to(dev, torch.float32).clone().requires_grad_(True)
+        kw["node_rep_regressive"] = (leaves["h_ar"], leaves["chi_ar"])
     if cfg.updating_node_positions:
         (oh, ochi), opos = layer((leaves["h"], leaves["chi"]), (leaves["e"], leaves["xi"]), ei, frames,
-                                 node_pos=inputs["node_pos"].to(dev, torch.float32))
+                                 node_pos=inputs["node_pos"].to(dev, torch.float32), **kw)
         loss = (oh * ch).sum() + (ochi * cchi).sum() + (opos * cpos).sum()
     else:
-        oh, ochi = layer((leaves["h"], leaves["chi"]), (leaves["e"], leaves["xi"]), ei, frames)
+        oh, ochi = layer((leaves["h"], leaves["chi"]), (leaves["e"], leaves["xi"]), ei, frames, **kw)
         opos = None
         loss = (oh * ch).sum() + (ochi * cchi).sum()
     layer.zero_grad(set_to_none=True)

@@ -34,6 +34,8 @@ def _check(L, res, cfg, case, n, reverse=False):
     assert rel_err(gchi, res["grad_chi"].numpy()) < TOL
     assert rel_err(ge, res["grad_e"].numpy()) < TOL
     assert rel_err(gxi, res["grad_xi"].numpy()) < TOL
+    if "grad_h_ar" in res:
+        assert rel_err(L.g_h_ar, res["grad_h_ar"].numpy()) < TOL and rel_err(L.g_chi_ar, res["grad_chi_ar"].numpy()) < TOL
     for k in L.spec.names:
         assert rel_err(L.param_grad(k), res["pgrad/" + k].numpy()) < TOL, k
     return oh.copy(), gp.copy()

@@ -22,7 +22,8 @@ def _compare(res, want, names, tol=TOL, exact=None, slack=4.0):
     max(tol, slack x the fp32 oracle's own distance to fp64): on large graphs ReLU units whose
     pre-activation is ~0 flip between any two fp32 evaluation orders (the reference's included),
     which moves individual gradient entries by more than 1e-4 of the tensor's range."""
-    keys = [k for k in ("out_h", "out_chi", "out_pos", "grad_h", "grad_chi", "grad_e", "grad_xi") if k in want]
+    keys = [k for k in ("out_h", "out_chi", "out_pos", "grad_h", "grad_chi", "grad_e", "grad_xi", "grad_h_ar", "grad_chi_ar")
+            if k in want]
     keys += ["pgrad/" + k for k in names]
     for key in keys:
         if exact is None:
@@ -37,11 +38,11 @@ def _compare(res, want, names, tol=TOL, exact=None, slack=4.0):
 def test_layer_matches_oracle_and_reference_fixture(name):
     case, cfg, params, inputs, fx = load_case(name)
     want = oracle_forward_backward(case, cfg, params, inputs)
-    layer = build_module(cfg, params).eval()
+    layer = build_module(cfg, params, autoregressive=bool(case.get("autoregressive", False))).eval()
     res = module_forward_backward(layer, case, cfg, inputs)
     _compare(res, want, [k for k, _ in layer.named_parameters()])
     # and against what the unmodified reference produced in the build container
-    for key in ("out_h", "out_chi", "out_pos", "grad_h", "grad_chi", "grad_e", "grad_xi"):
+    for key in ("out_h", "out_chi", "out_pos", "grad_h", "grad_chi", "grad_e", "grad_xi", "grad_h_ar", "grad_chi_ar"):
         if key in fx.files:
             assert rel_err(res[key].numpy(), fx[key]) < TOL, key
     for key in fx.files:
@@ -183,14 +184,16 @@ def test_inference_mode_and_no_saved_activations():
     oh, ochi = O.interactions_forward(params, cfg, inputs["h"], inputs["chi"], inputs["e"], inputs["xi"],
                                       inputs["edge_index"], inputs["frames"])
     assert rel_err(h0.cpu().numpy(), oh.numpy()) < TOL and rel_err(chi0.cpu().numpy(), ochi.numpy()) < TOL
-    # all-true node mask is the unmasked path (gcpnet.py:1202-1206)
+    # all-true node mask is the unmasked path (gcpnet.py:1202-1206): same numbers through the masked kernels' views
     with torch.no_grad():
-        h1, _ = layer(*args, node_mask=torch.ones(100, dtype=torch.bool, device=dev))
-    assert torch.equal(h0, h1)
-    with pytest.raises(NotImplementedError):
-        m = torch.ones(100, dtype=torch.bool, device=dev)
-        m[3] = False
-        layer(*args, node_mask=m)
+        h1, chi1 = layer(*args, node_mask=torch.ones(100, dtype=torch.bool, device=dev))
+    assert rel_err(h1.cpu().numpy(), h0.cpu().numpy()) < 1e-6 and rel_err(chi1.cpu().numpy(), chi0.cpu().numpy()) < 1e-6
+    # a masked-out node keeps its input row (gcpnet.py:1249-1251)
+    m = torch.ones(100, dtype=torch.bool, device=dev)
+    m[3] = False
+    with torch.no_grad():
+        h2, chi2 = layer(*args, node_mask=m)
+    assert torch.equal(h2[3].cpu(), inputs["h"][3]) and torch.equal(chi2[3].cpu(), inputs["chi"][3])
 
 
 def test_dropout_train_mode_statistics():
@@ -235,6 +238,90 @@ def test_localize_matches_oracle():
     ei = torch.randint(0, 500, (2, 4000), generator=g)
     got = gcpnet_b200.localize(x.cuda(), ei.cuda()).cpu()
     assert torch.allclose(got, O.localize(x, ei), rtol=1e-5, atol=1e-6)
+
+
+def test_masked_localize_centralize_decentralize_match_oracle():
+    """comp/__init__.py:170-269 with and without a node mask (+inf on masked edges / rows)."""
+    import gcpnet_b200
+    from gcpnet_b200.interactions import centralize, decentralize
+    g = torch.Generator().manual_seed(12)
+    n = 700
+    x = torch.randn(n, 3, generator=g)
+    ei = torch.randint(0, n, (2, 5000), generator=g)
+    mask = torch.rand(n, generator=g) > 0.15
+    batch_index = torch.sort(torch.randint(0, 9, (n,), generator=g)).values
+    for m in (None, mask):
+        got = gcpnet_b200.localize(x.cuda(), ei.cuda(), node_mask=None if m is None else m.cuda()).cpu()
+        want = O.localize(x, ei, node_mask=m)
+        fin = torch.isfinite(want)
+        assert torch.equal(torch.isfinite(got), fin) and torch.allclose(got[fin], want[fin], rtol=1e-5, atol=1e-6)
+        cen, cx = centralize({"x": x.cuda()}, "x", batch_index.cuda(), node_mask=None if m is None else m.cuda())
+        wcen, wcx = O.centralize(x, batch_index, node_mask=m)
+        fin = torch.isfinite(wcx)
+        assert torch.allclose(cen.cpu(), wcen, rtol=1e-5, atol=1e-6)
+        assert torch.equal(torch.isfinite(cx.cpu()), fin) and torch.allclose(cx.cpu()[fin], wcx[fin], rtol=1e-5, atol=1e-6)
+        back = decentralize({"x": cx}, "x", batch_index.cuda(), cen, node_mask=None if m is None else m.cuda()).cpu()
+        keep = fin.all(dim=1)
+        assert torch.allclose(back[keep], x[keep], rtol=1e-5, atol=1e-5)
+
+
+def test_autoregressive_and_masked_graph_views():
+    """Index work, bit-exact: the gather views of gcpnet_graph_build_autoregressive against numpy (sorted by
+    (destination, row >= col)), and the masked frames / mean frames of gcpnet_graph_mask against the restatement of
+    gcpnet.py:1202-1217 + comp/__init__.py:294-323 (relabelled subgraph edges indexing the ORIGINAL mask)."""
+    import gcpnet_b200
+    g = torch.Generator().manual_seed(13)
+    for n, E in ((300, 4000), (9000, 30000)):  # single-CTA build and radix-sort pipeline (2N > 12287)
+        ei = torch.randint(0, n - 3, (2, E), generator=g)
+        frames = torch.randn(E, 3, 3, generator=g)
+        mask = torch.rand(n, generator=g) > 0.1
+        frames_inf = torch.where((mask[ei[0]] & mask[ei[1]]).view(-1, 1, 1), frames, torch.full_like(frames, float("inf")))
+        gv = gcpnet_b200.graph_views(ei.cuda(), frames_inf.cuda(), n, autoregressive=True, node_mask=mask.cuda())
+        row, col = ei[0].numpy(), ei[1].numpy()
+        flag = (row >= col).astype(np.int64)
+        gs, gd = 2 * row + flag, 2 * col + flag
+        perm = np.argsort(gd, kind="stable")
+        assert np.array_equal(gv.perm.cpu().numpy(), perm.astype(np.int32))
+        assert np.array_equal(gv.gdst.cpu().numpy(), gd[perm].astype(np.int32))
+        assert np.array_equal(gv.gsrc.cpu().numpy(), gs[perm].astype(np.int32))
+        assert np.array_equal(gv.dst.cpu().numpy(), col[perm].astype(np.int32))
+        assert np.array_equal(gv.src.cpu().numpy(), row[perm].astype(np.int32))
+        assert np.array_equal(gv.vdst_ptr.cpu().numpy(), np.searchsorted(gd[perm], np.arange(2 * n + 1)).astype(np.int32))
+        assert np.array_equal(gv.dst_ptr.cpu().numpy(), np.searchsorted(col[perm], np.arange(n + 1)).astype(np.int32))
+        spos = np.argsort(gs[perm], kind="stable")
+        assert np.array_equal(gv.src_pos.cpu().numpy(), spos.astype(np.int32))
+        assert np.array_equal(gv.vsrc_ptr.cpu().numpy(), np.searchsorted(gs[perm][spos], np.arange(2 * n + 1)).astype(np.int32))
+        assert np.array_equal(gv.src_ptr.cpu().numpy(), np.searchsorted(row[perm][spos], np.arange(n + 1)).astype(np.int32))
+        # masked frames: zero rows on masked edges, never inf
+        em = (mask[ei[0]] & mask[ei[1]])
+        assert torch.equal(gv.frames.cpu(), torch.where(em.view(-1, 1, 1), frames, torch.zeros_like(frames)))
+        # mean frames of the position GCP: masked edges give zero frames but count (comp/__init__.py:296-300,316-323)
+        f0 = torch.where(em.view(-1, 1), frames.reshape(E, 9), torch.zeros(E, 9))
+        assert torch.allclose(gv.fbar_pos.cpu(), O.segment_reduce(f0, ei[0], n, "mean"), rtol=1e-5, atol=1e-6)
+        # feed-forward GCPs: subgraph of the mask, relabelled ids index the original mask (gcpnet.py:1232-1239)
+        sub_ei, sub_fr = O.subgraph(torch.where(mask)[0], ei, frames, n)
+        em2 = mask[sub_ei[0]] & mask[sub_ei[1]]
+        f1 = torch.where(em2.view(-1, 1), sub_fr.reshape(-1, 9), torch.zeros(sub_fr.shape[0], 9))
+        want = torch.zeros(n, 9)
+        want[mask] = O.segment_reduce(f1, sub_ei[0], int(mask.sum()), "mean")
+        assert torch.allclose(gv.fbar_ff.cpu(), want, rtol=1e-5, atol=1e-6)
+
+
+def test_graph_build_hub_nodes_and_bad_indices():
+    """A hub node that owns most of a small graph's edges (the single-CTA build ranks long segments cooperatively)."""
+    import gcpnet_b200
+    g = torch.Generator().manual_seed(14)
+    n, E = 500, 12000
+    ei = torch.randint(0, n, (2, E), generator=g)
+    ei[1, : E // 2] = 7      # 6 000 edges into node 7
+    ei[0, E // 3:] = 11      # 8 000 edges out of node 11
+    frames = torch.randn(E, 3, 3, generator=g)
+    gv = gcpnet_b200.graph_views(ei.cuda(), frames.cuda(), n)
+    row, col = ei[0].numpy(), ei[1].numpy()
+    perm = np.argsort(col, kind="stable")
+    assert np.array_equal(gv.perm.cpu().numpy(), perm.astype(np.int32))
+    spos = np.argsort(row[perm], kind="stable")
+    assert np.array_equal(gv.src_pos.cpu().numpy(), spos.astype(np.int32))
 
 
 def test_graph_build_matches_stable_sort():

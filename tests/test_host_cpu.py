@@ -81,10 +81,16 @@ def test_unsupported_configurations_raise():
         bad[key] = True
         with pytest.raises(NotImplementedError):
             gcpnet_b200.GCPInteractions((64, 16), (32, 4), cfg=bad, layer_cfg=lcfg)
+    # autoregressive and pre_norm layers construct (round 2); their combination does not
+    ar = gcpnet_b200.GCPInteractions((64, 16), (32, 4), cfg=mcfg, layer_cfg=lcfg, autoregressive=True)
+    assert ar.spec.reduce_mean is False  # reduce_function = "add" (gcpnet.py:984)
+    lpre = type(lcfg)(lcfg)
+    lpre["pre_norm"] = True
+    assert gcpnet_b200.GCPInteractions((64, 16), (32, 4), cfg=mcfg, layer_cfg=lpre).spec.pre_norm
     with pytest.raises(NotImplementedError):
-        gcpnet_b200.GCPInteractions((64, 16), (32, 4), cfg=mcfg, layer_cfg=lcfg, autoregressive=True)
+        gcpnet_b200.GCPInteractions((64, 16), (32, 4), cfg=mcfg, layer_cfg=lpre, autoregressive=True)
     lbad = type(lcfg)(lcfg)
-    lbad["pre_norm"] = True
+    lbad["num_feedforward_layers"] = 3
     with pytest.raises(NotImplementedError):
         gcpnet_b200.GCPInteractions((64, 16), (32, 4), cfg=mcfg, layer_cfg=lbad)
     with pytest.raises(AssertionError):  # same assertion text as gcpnet.py:295-297

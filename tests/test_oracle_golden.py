@@ -15,7 +15,7 @@ TOL = 1e-4
 def test_oracle_fp32_matches_reference_fixture(name):
     case, cfg, params, inputs, fx = load_case(name)
     res = oracle_forward_backward(case, cfg, params, inputs, dtype=torch.float32)
-    for key in ("out_h", "out_chi", "out_pos", "grad_h", "grad_chi", "grad_e", "grad_xi"):
+    for key in ("out_h", "out_chi", "out_pos", "grad_h", "grad_chi", "grad_e", "grad_xi", "grad_h_ar", "grad_chi_ar"):
         if key in fx.files:
             assert rel_err(res[key].numpy(), fx[key]) < TOL, key
     n_checked = 0

@@ -48,6 +48,33 @@ def test_localize_matches_reference():
     assert torch.allclose(O.localize(x, ei), ref.localize(x, ei), rtol=1e-6, atol=1e-7)
 
 
+def test_masked_localize_centralize_decentralize_match_reference():
+    """comp/__init__.py:170-269 with a node mask: +inf on masked edges / rows, centroids over the unmasked nodes."""
+    ref = ref_shim.load_reference()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(40, 3, generator=g)
+    ei = torch.randint(0, 40, (2, 300), generator=g)
+    mask = torch.rand(40, generator=g) > 0.2
+    assert torch.equal(O.localize(x, ei, node_mask=mask), ref.localize(x, ei, node_mask=mask))
+    batch_index = torch.sort(torch.randint(0, 5, (40,), generator=g)).values
+    bag = {"x": x}
+    for m in (None, mask):
+        rc, rx = ref.comp.centralize(bag, "x", batch_index, node_mask=m)
+        oc, ox = O.centralize(x, batch_index, node_mask=m)
+        assert torch.allclose(oc, rc, rtol=1e-6, atol=1e-7) and torch.allclose(ox, rx, rtol=1e-6, atol=1e-7)
+        od = O.decentralize(ox, batch_index, oc, node_mask=m)
+        if m is None:
+            rd = ref.comp.decentralize({"x": rx}, "x", batch_index, rc, node_mask=m)
+            assert torch.allclose(od, rd, rtol=1e-6, atol=1e-7)
+        else:
+            # the reference's masked decentralize adds an [N]-row gather to a [k]-row selection (comp/__init__.py:213) and
+            # raises unless the mask is all-true; no caller passes a mask.  The restatement adds the centroids on the
+            # unmasked rows (+inf elsewhere), which round-trips centralize.
+            with pytest.raises(RuntimeError):
+                ref.comp.decentralize({"x": rx}, "x", batch_index, rc, node_mask=m)
+            assert torch.allclose(od[m], x[m], rtol=1e-5, atol=1e-6) and bool(torch.isinf(od[~m]).all())
+
+
 def test_rotation_equivariance_of_oracle():
     """The property tests/test_gcpnet_equivariance.py:1773-1881 asserts (atol 1e-5, rtol 1e-4)."""
     cfg = O.OracleConfig(node_dims=(100, 16), edge_dims=(32, 4))
