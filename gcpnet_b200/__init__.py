@@ -5,7 +5,9 @@ Python host code over hand-written sm_100a kernels behind the C ABI of include/g
 from .scalar_vector import ScalarVector  # noqa: F401
 from .interactions import GCPInteractions, GCPMessagePassing, GCP2Params, localize, graph_views, clear_graph_cache  # noqa: F401
 from .graphs import GraphedStep, prepack  # noqa: F401
+from .interactions import centralize, decentralize  # noqa: F401
+from .modules import GCP2, GCPLayerNorm, GCPEmbedding, GCPNetNMS  # noqa: F401
 from . import ddp  # noqa: F401
 from .ddp import FlatGradients  # noqa: F401
 
-__all__ = ["GCPInteractions", "GCPMessagePassing", "GCP2Params", "ScalarVector", "localize", "graph_views", "clear_graph_cache", "GraphedStep", "prepack", "FlatGradients", "ddp"]
+__all__ = ["GCPInteractions", "GCPMessagePassing", "GCP2Params", "ScalarVector", "localize", "graph_views", "clear_graph_cache", "GraphedStep", "prepack", "FlatGradients", "ddp", "centralize", "decentralize", "GCP2", "GCPLayerNorm", "GCPEmbedding", "GCPNetNMS"]

@@ -66,6 +66,12 @@ class Plan(C.Structure):
     ]
 
 
+class Gcp2Plan(C.Structure):
+    _fields_ = [("tile", C.c_int32), ("grid", C.c_int32), ("smem_fwd_bytes", C.c_int32), ("smem_bwd_bytes", C.c_int32),
+                ("n_params", C.c_int32), ("reserved", C.c_int32), ("packed_floats", C.c_int64), ("saved_floats", C.c_int64),
+                ("partial_floats", C.c_int64)]
+
+
 class ForwardIO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("h", "chi", "e", "xi", "frames", "pos", "out_h", "out_chi", "out_pos", "msg", "saved_edge", "saved_node",
@@ -84,7 +90,8 @@ EXPORTS = (
     "gcpnet_version", "gcpnet_last_error", "gcpnet_launch_count", "gcpnet_profile_enable", "gcpnet_profile_read", "gcpnet_set_option", "gcpnet_debug_stamps", "gcpnet_set_side_stream", "gcpnet_join", "gcpnet_graph_workspace_bytes", "gcpnet_graph_build",
     "gcpnet_localize", "gcpnet_localize_masked", "gcpnet_graph_ar_workspace_bytes", "gcpnet_graph_build_autoregressive",
     "gcpnet_graph_mask", "gcpnet_centralize", "gcpnet_decentralize", "gcpnet_layer_plan", "gcpnet_layer_pack", "gcpnet_layer_forward", "gcpnet_layer_backward",
-    "gcpnet_message_passing_forward", "gcpnet_message_passing_backward",
+    "gcpnet_message_passing_forward", "gcpnet_message_passing_backward", "gcpnet_gcp2_plan_query", "gcpnet_gcp2_forward",
+    "gcpnet_gcp2_backward", "gcpnet_layernorm_forward", "gcpnet_layernorm_backward",
 )
 
 
@@ -140,6 +147,18 @@ def declare(lib: C.CDLL) -> None:
     lib.gcpnet_message_passing_forward.restype = C.c_int
     lib.gcpnet_message_passing_forward.argtypes = [C.POINTER(Layer), C.POINTER(Graph), C.POINTER(Plan),
                                                    C.POINTER(ForwardIO), C.c_void_p, C.c_void_p]
+    lib.gcpnet_gcp2_plan_query.restype = C.c_int
+    lib.gcpnet_gcp2_plan_query.argtypes = [C.POINTER(Gcp2), C.c_int64, C.POINTER(Gcp2Plan)]
+    lib.gcpnet_gcp2_forward.restype = C.c_int
+    lib.gcpnet_gcp2_forward.argtypes = [C.POINTER(Gcp2), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float] + \
+        [C.c_void_p] * 5
+    lib.gcpnet_gcp2_backward.restype = C.c_int
+    lib.gcpnet_gcp2_backward.argtypes = [C.POINTER(Gcp2), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float] + \
+        [C.c_void_p] * 10
+    lib.gcpnet_layernorm_forward.restype = C.c_int
+    lib.gcpnet_layernorm_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 5
+    lib.gcpnet_layernorm_backward.restype = C.c_int
+    lib.gcpnet_layernorm_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 9
     lib.gcpnet_message_passing_backward.restype = C.c_int
     lib.gcpnet_message_passing_backward.argtypes = [C.POINTER(Layer), C.POINTER(Graph), C.POINTER(Plan),
                                                     C.POINTER(BackwardIO), C.c_void_p, C.c_void_p]

@@ -95,6 +95,30 @@ __global__ void __launch_bounds__(NT, 1) node_bwd_kernel(const __grid_constant__
     node_bwd_tile<TE, NT, SLF, SLD>(p, smem, tile, wp, prow, tile != (int)blockIdx.x);
 }
 
+template <int TE, int NT, int SLF>
+__global__ void __launch_bounds__(NT, 1) gcp2op_fwd_kernel(const __grid_constant__ Gcp2OpParams p) {
+  extern __shared__ __align__(128) float smem[];
+  const int ntiles = (p.M + TE - 1) / TE;
+  const int mine = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (mine == 0) return;
+  WPipe wp = gcp2op_pipe(p, smem, mine);
+  wpipe_start<NT>(wp);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+    gcp2op_fwd_tile<TE, NT, SLF>(p, smem, tile, wp, tile == (int)blockIdx.x);
+}
+template <int TE, int NT, int SLF, int SLD>
+__global__ void __launch_bounds__(NT, 1) gcp2op_bwd_kernel(const __grid_constant__ Gcp2OpParams p) {
+  extern __shared__ __align__(128) float smem[];
+  const int ntiles = (p.M + TE - 1) / TE;
+  const int mine = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (mine == 0) return;
+  WPipe wp = gcp2op_pipe(p, smem, mine);
+  wpipe_start<NT>(wp);
+  float* prow = p.partial + (size_t)blockIdx.x * p.partial_stride;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+    gcp2op_bwd_tile<TE, NT, SLF, SLD>(p, smem, tile, wp, prow, tile != (int)blockIdx.x);
+}
+
 __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackParams p) {
   pack_gcp<256>(p.ops[blockIdx.x], p.blob, (int)blockIdx.y, (int)gridDim.y);
 }
@@ -715,6 +739,95 @@ static int layer_backward_body(const gcpnet_layer* layer, const gcpnet_graph* gr
   gcp_note_launches(1);
   CUDA_TRY(cudaGetLastError());
   if (launch_node_wgrad(l, g, lp, io->ws_node_partial, io->saved_node, io->g_params + l.n_edge_params, st)) return 1;
+  return 0;
+}
+
+// ---- GCP2 / GCPLayerNorm on their own ---------------------------------------------------------------------------------------
+int gcpnet_gcp2_plan_query(const gcpnet_gcp2* op, int64_t M, gcpnet_gcp2_plan* plan) {
+  if (!op || !plan) return fail("gcp2_plan: null argument");
+  const Gcp2OpPlan P = plan_gcp2_op(*op, M);
+  if (!P.error.empty()) return fail("gcp2_plan: " + P.error);
+  gcpnet_gcp2_plan q{};
+  q.tile = GCP2OP_TE; q.grid = P.grid; q.smem_fwd_bytes = P.smf.total * 4; q.smem_bwd_bytes = P.smb.total * 4;
+  q.n_params = P.n_params; q.packed_floats = P.packed_floats;
+  q.saved_floats = M * (long long)(op->so + op->vo); q.partial_floats = (long long)P.grid * P.n_params;
+  *plan = q;
+  return 0;
+}
+static Gcp2OpParams gcp2op_params(const Gcp2OpPlan& P, bool backward, int64_t M, const float* s_in, const float* v_in, const float* frames,
+                                  int e3, float slope, const float* blob) {
+  Gcp2OpParams p{};
+  p.M = (int)M; p.e3 = e3; p.slope = slope; p.s_in = s_in; p.v_in = v_in; p.frames = frames; p.blob = blob;
+  p.op = P.op; p.sm = backward ? P.smb : P.smf; p.seq = backward ? P.bwd : P.fwd;
+  return p;
+}
+int gcpnet_gcp2_forward(const gcpnet_gcp2* op, int64_t M, const float* s_in, const float* v_in, const float* frames, int e3, float slope,
+                        float* s_out, float* v_out, float* saved, float* packed, void* stream) {
+  if (!op || !s_in || !v_in || !frames || !s_out || !v_out || !packed) return fail("gcp2_forward: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Gcp2OpPlan P = plan_gcp2_op(*op, M);
+  if (!P.error.empty()) return fail("gcp2_forward: " + P.error);
+  if (M <= 0) return 0;
+  PackParams pp{};
+  pp.n = 1; pp.blob = packed; pp.ops[0] = P.op;
+  pack_kernel<<<dim3(1, 16), 256, 0, st>>>(pp);
+  gcp_note_launches(1);
+  Gcp2OpParams p = gcp2op_params(P, false, M, s_in, v_in, frames, e3, slope, packed);
+  p.s_out = s_out; p.v_out = v_out; p.saved = saved;
+  const int bytes = p.sm.total * 4;
+  if (P.slf == 1) return launch(gcp2op_fwd_kernel<GCP2OP_TE, GCP2OP_NT, 1>, p, P.grid, GCP2OP_NT, bytes, st);
+  return launch(gcp2op_fwd_kernel<GCP2OP_TE, GCP2OP_NT, 2>, p, P.grid, GCP2OP_NT, bytes, st);
+}
+int gcpnet_gcp2_backward(const gcpnet_gcp2* op, int64_t M, const float* s_in, const float* v_in, const float* frames, int e3, float slope,
+                         const float* saved, const float* packed, const float* g_s_out, const float* g_v_out, float* g_s_in,
+                         float* g_v_in, float* g_params, float* ws_partial, void* stream) {
+  if (!op || !s_in || !v_in || !frames || !saved || !packed || !g_s_out || !g_v_out || !g_s_in || !g_v_in || !g_params || !ws_partial)
+    return fail("gcp2_backward: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Gcp2OpPlan P = plan_gcp2_op(*op, M);
+  if (!P.error.empty()) return fail("gcp2_backward: " + P.error);
+  if (M <= 0) { CUDA_TRY(cudaMemsetAsync(g_params, 0, (size_t)P.n_params * sizeof(float), st)); return 0; }
+  Gcp2OpParams p = gcp2op_params(P, true, M, s_in, v_in, frames, e3, slope, packed);
+  p.saved = const_cast<float*>(saved); p.gs_out = g_s_out; p.gv_out = g_v_out; p.gs_in = g_s_in; p.gv_in = g_v_in;
+  p.partial = ws_partial; p.partial_stride = P.n_params;
+  const int bytes = p.sm.total * 4;
+  int rc;
+  if (P.slf == 1) rc = launch(gcp2op_bwd_kernel<GCP2OP_TE, GCP2OP_NT, 1, EDGE_SLD>, p, P.grid, GCP2OP_NT, bytes, st);
+  else rc = launch(gcp2op_bwd_kernel<GCP2OP_TE, GCP2OP_NT, 2, EDGE_SLD>, p, P.grid, GCP2OP_NT, bytes, st);
+  if (rc) return rc;
+  partial_reduce_kernel<<<(P.n_params + 255) / 256, 256, 0, st>>>(g_params, ws_partial, P.n_params, P.grid, nullptr, 0, 0, SkipRanges{});
+  gcp_note_launches(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int gcpnet_layernorm_forward(const float* h, const float* chi, int64_t N, int32_t s, int32_t v, const float* w, const float* b,
+                             float* out_h, float* out_chi, void* stream) {
+  if (N <= 0) return 0;
+  if ((s > 0 && (!h || !w || !b || !out_h)) || (v > 0 && (!chi || !out_chi))) return fail("layernorm_forward: null argument");
+  gcp_layernorm_fwd_kernel<<<(int)((N * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h, chi, (int)N, s, v, w, b, 1e-5f, 1e-8f, out_h, out_chi);
+  gcp_note_launches(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int gcpnet_layernorm_backward(const float* h, const float* chi, int64_t N, int32_t s, int32_t v, const float* w, const float* g_out_h,
+                              const float* g_out_chi, float* g_h, float* g_chi, float* g_w, float* g_b, float* workspace, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s > 0 && (!g_w || !g_b)) return fail("layernorm_backward: null argument");
+  if (N <= 0) {
+    if (s > 0) { CUDA_TRY(cudaMemsetAsync(g_w, 0, (size_t)s * sizeof(float), st)); CUDA_TRY(cudaMemsetAsync(g_b, 0, (size_t)s * sizeof(float), st)); }
+    return 0;
+  }
+  if (!workspace) return fail("layernorm_backward: workspace required");
+  float* stats = workspace;
+  float* partial = workspace + 2 * N;
+  gcp_layernorm_bwd_kernel<<<(int)((N * 32 + 255) / 256), 256, 0, st>>>(h, chi, (int)N, s, v, w, 1e-5f, 1e-8f, g_out_h, g_out_chi, g_h, g_chi, stats);
+  gcp_note_launches(1);
+  if (s > 0) {
+    gcp_layernorm_wgrad_kernel<<<LN_PARTS, 128, 0, st>>>(h, g_out_h, stats, (int)N, s, partial);
+    gcp_layernorm_wreduce_kernel<<<(2 * s + 127) / 128, 128, 0, st>>>(partial, LN_PARTS, s, g_w, g_b);
+    gcp_note_launches(2);
+  }
+  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 

@@ -8,6 +8,7 @@
 #include "../../include/gcpnet_b200.h"
 #include "edge_kernels.cuh"
 #include "node_kernels.cuh"
+#include "gcp2_op.cuh"
 #include "pack.cuh"
 #include "tc_setup.h"
 
@@ -227,6 +228,45 @@ inline bool pick_node_tile(const gcpnet_layer& l, LayerOps& ops, long long N, bo
     return true;
   }
   return false;
+}
+
+// ---- a GCP2 on its own (gcp2_op.cuh) ----------------------------------------------------------------------------------
+inline int gcp2_n_params(const gcpnet_gcp2& d) {
+  return d.hd * d.vi + 3 * d.vi + d.so * (d.si + d.hd + 9) + d.so + d.vo * d.hd + d.vo * d.so + d.vo;
+}
+inline Gcp2OpPlan plan_gcp2_op(const gcpnet_gcp2& d, long long M) {
+  Gcp2OpPlan P{};
+  P.error = check_gcp2(d, "gcp2");
+  if (!P.error.empty()) return P;
+  P.n_params = gcp2_n_params(d);
+  for (int i = 0; i < 7; ++i)
+    if (d.grad_off[i] < 0 || d.grad_off[i] >= P.n_params) { P.error = "gcp2: grad_off outside the module's flat gradient"; return P; }
+  P.slf = (round_up(d.so, 16) / 16 + 3) / 4;
+  if (P.slf > 2) { P.error = "gcp2: scalar output dim too wide for this build"; return P; }
+  const int caps[3] = {EDGE_CAP_FLOATS, 6144, 4096};
+  for (int ci = 0; ci < 3; ++ci) {
+    GcpOp op = to_op(d, 0);
+    int cursor = 0;
+    P.error = plan_gcp_pack(op, caps[ci], &cursor);
+    if (!P.error.empty()) continue;
+    WSeq f{}, b{};
+    seq_fwd(f, op); seq_bwd(b, op);
+    f.slot_floats = round_up(f.slot_floats, 32); b.slot_floats = round_up(b.slot_floats, 32);
+    bool ok = false;
+    for (int nslot = 3; nslot >= 1 && !ok; --nslot) {
+      const EdgeSmem mf = edge_plan_smem(GCP2OP_TE, d.so, d.vo, 0, 0, &op, 1, false, nslot, f.slot_floats);
+      const EdgeSmem mb = edge_plan_smem(GCP2OP_TE, d.so, d.vo, 0, 0, &op, 1, true, nslot, b.slot_floats);
+      if ((long long)mf.total * 4 <= SMEM_LIMIT_BYTES && (long long)mb.total * 4 <= SMEM_LIMIT_BYTES) {
+        f.nslot = nslot; b.nslot = nslot; P.smf = mf; P.smb = mb; ok = true;
+      }
+    }
+    if (!ok) { P.error = "gcp2: feature dims too large for the shared-memory tile plan of this build"; continue; }
+    P.op = op; P.fwd = f; P.bwd = b; P.packed_floats = round_up(cursor, 32); P.error.clear();
+    const long long tiles = (M + GCP2OP_TE - 1) / GCP2OP_TE;
+    P.grid = (int)(tiles < 1 ? 1 : (tiles > NUM_SMS ? NUM_SMS : tiles));
+    return P;
+  }
+  return P;
 }
 
 struct LayerPlan {

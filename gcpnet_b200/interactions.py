@@ -182,6 +182,8 @@ def centralize(batch, key: str, batch_index: torch.Tensor, node_mask: Optional[t
     _check_cuda(x, key)
     if x.dtype != torch.float32 or x.dim() != 2 or x.shape[1] != 3 or batch_index.dtype != torch.int64:
         raise TypeError("centralize: batch[key] must be float32 [N, 3] and batch_index int64 [N]")
+    if x.requires_grad and torch.is_grad_enabled():
+        raise NotImplementedError("gcpnet_b200.centralize: gradients w.r.t. the input positions are not covered")
     x, batch_index = x.contiguous(), batch_index.contiguous()
     N = int(x.shape[0])
     mask = _mask_u8(node_mask, N, x.device)
@@ -195,18 +197,33 @@ def centralize(batch, key: str, batch_index: torch.Tensor, node_mask: Optional[t
     return centroid, centered
 
 
+class _DecentralizeFn(torch.autograd.Function):
+    """x + centroid[batch]; differentiable in x (identity on the unmasked rows) -- the NMS loss reaches the layers' position
+    outputs through it (gcpnet_nms_module.py:149).  The centroids come from the input positions and carry no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, batch_index, cen, mask):
+        out = torch.empty_like(x)
+        _lib.check(_lib.load().gcpnet_decentralize(_ptr(x), _ptr(batch_index), int(x.shape[0]), _ptr(cen), _ptr(mask), _ptr(out),
+                                                   _stream()), "gcpnet_decentralize")
+        ctx.mask = mask
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.mask is not None:
+            g = g * ctx.mask.to(g.dtype).unsqueeze(-1)
+        return g, None, None, None
+
+
 def decentralize(batch, key: str, batch_index: torch.Tensor, entities_centroid: torch.Tensor,
                  node_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``decentralize`` (comp/__init__.py:203-217): ``batch[key] + centroid[batch_index]`` (masked rows: +inf)."""
     x = batch[key]
     _check_cuda(x, key)
-    x, batch_index, cen = x.contiguous(), batch_index.contiguous(), entities_centroid.contiguous()
-    N = int(x.shape[0])
-    mask = _mask_u8(node_mask, N, x.device)
-    out = torch.empty_like(x)
-    _lib.check(_lib.load().gcpnet_decentralize(_ptr(x), _ptr(batch_index), N, _ptr(cen), _ptr(mask), _ptr(out), _stream()),
-               "gcpnet_decentralize")
-    return out
+    x, batch_index, cen = x.contiguous(), batch_index.contiguous(), entities_centroid.detach().contiguous()
+    mask = _mask_u8(node_mask, int(x.shape[0]), x.device)
+    return _DecentralizeFn.apply(x, batch_index, cen, mask)
 
 
 def _check_cuda(t: torch.Tensor, name: str) -> None:

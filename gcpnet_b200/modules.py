@@ -1,0 +1,304 @@
+"""The callers either side of the interaction layers, on the same kernels: ``GCP2`` on its own, ``GCPLayerNorm``,
+``GCPEmbedding`` and the NMS model's ``forward(batch)``.
+
+Reference interfaces mirrored (src/models/components/gcpnet.py unless noted):
+``GCP2.__init__/forward`` :252-468, ``GCPLayerNorm`` comp/__init__.py:138-167, ``GCPEmbedding`` :703-823,
+``GCPNetNMSLitModule.forward`` src/models/gcpnet_nms_module.py:127-151.  Constructor arguments, ``state_dict`` names and
+return types are the reference's; anything the kernels do not cover raises ``NotImplementedError`` (no eager fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _cabi, _lib
+from .interactions import (GCP2Params, GCPInteractions, _check_cuda, _get, _mask_u8, _ptr, _stream, centralize, decentralize,
+                           graph_views, localize)
+from .scalar_vector import ScalarVector
+
+
+# ------------------------------------------------------------------------------------------
+# GCP2 on its own
+# ------------------------------------------------------------------------------------------
+class _Gcp2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod: "GCP2", s_in, v_in, frames9, *params):
+        lib = _lib.load()
+        M, dev = int(s_in.shape[0]), s_in.device
+        op = mod._op_struct(params)
+        plan = _cabi.Gcp2Plan()
+        _lib.check(lib.gcpnet_gcp2_plan_query(C.byref(op), M, C.byref(plan)), "gcpnet_gcp2_plan_query")
+        f32 = lambda n: torch.empty(max(int(n), 1), dtype=torch.float32, device=dev)
+        so, vo = mod.dims[2], mod.dims[3]
+        s_out = torch.empty((M, so), dtype=torch.float32, device=dev)
+        v_out = torch.empty((M, vo, 3), dtype=torch.float32, device=dev)
+        need_grad = mod._grad_mode and any(ctx.needs_input_grad)
+        saved = f32(plan.saved_floats) if need_grad else None
+        packed = f32(plan.packed_floats)
+        _lib.check(lib.gcpnet_gcp2_forward(C.byref(op), M, _ptr(s_in), _ptr(v_in), _ptr(frames9), int(mod.e3), mod.slope,
+                                           _ptr(s_out), _ptr(v_out), _ptr(saved), _ptr(packed), _stream()), "gcpnet_gcp2_forward")
+        ctx.mod, ctx.plan = mod, plan
+        ctx.save_for_backward(s_in, v_in, frames9, saved, packed, *params)
+        return s_out, v_out
+
+    @staticmethod
+    def backward(ctx, g_s, g_v):
+        lib = _lib.load()
+        mod, plan = ctx.mod, ctx.plan
+        s_in, v_in, frames9, saved, packed, *params = ctx.saved_tensors
+        if saved is None:
+            raise RuntimeError("gcpnet_b200: backward called on a forward that ran without saved activations")
+        M, dev = int(s_in.shape[0]), s_in.device
+        op = mod._op_struct(params)
+        f32 = lambda n: torch.empty(max(int(n), 1), dtype=torch.float32, device=dev)
+        g_s = torch.zeros((M, mod.dims[2]), dtype=torch.float32, device=dev) if g_s is None else g_s.contiguous()
+        g_v = torch.zeros((M, mod.dims[3], 3), dtype=torch.float32, device=dev) if g_v is None else g_v.contiguous()
+        g_s_in, g_v_in = torch.empty_like(s_in), torch.empty_like(v_in)
+        g_params, ws = f32(plan.n_params), f32(plan.partial_floats)
+        _lib.check(lib.gcpnet_gcp2_backward(C.byref(op), M, _ptr(s_in), _ptr(v_in), _ptr(frames9), int(mod.e3), mod.slope,
+                                            _ptr(saved), _ptr(packed), _ptr(g_s), _ptr(g_v), _ptr(g_s_in), _ptr(g_v_in),
+                                            _ptr(g_params), _ptr(ws), _stream()), "gcpnet_gcp2_backward")
+        pgrads = []
+        for name, (off, shp) in mod._layout.items():
+            n = 1
+            for d in shp:
+                n *= d
+            pgrads.append(g_params[off:off + n].view(shp))
+        return (None, g_s_in, g_v_in, None, *pgrads)
+
+
+class GCP2(GCP2Params):
+    """``GCP2`` (gcpnet.py:252-468), vector-gate path: reference constructor and ``forward(s_maybe_v, edge_index, frames,
+    node_inputs, node_mask)``; parameters under the reference's names (``vector_down``, ``scalar_out``,
+    ``vector_down_frames``, ``vector_up``, ``vector_out_scale``)."""
+
+    def __init__(self, input_dims, output_dims, nonlinearities: Optional[Tuple[Optional[str], Optional[str]]] = ("relu", "sigmoid"),
+                 scalar_gate: int = 0, vector_gate: bool = True, frame_gate: bool = False, sigma_frame_gate: bool = False,
+                 bottleneck: int = 1, vector_residual: bool = False, vector_frame_residual: bool = False,
+                 ablate_frame_updates: bool = False, ablate_scalars: bool = False, ablate_vectors: bool = False,
+                 enable_e3_equivariance: bool = False, scalarization_vectorization_output_dim: int = 3,
+                 nonlinearity_slope: float = 1e-2, **kwargs):
+        si, vi = int(input_dims[0]), int(input_dims[1])
+        so, vo = int(output_dims[0]), int(output_dims[1])
+
+        def unsupported(what):
+            raise NotImplementedError(f"gcpnet_b200.GCP2: {what} is not covered by the sm_100a kernels (no eager fallback)")
+
+        if vi <= 0 or vo <= 0:
+            unsupported("a GCP2 without vector inputs or outputs")
+        if scalar_gate or not vector_gate or frame_gate or sigma_frame_gate or vector_frame_residual:
+            unsupported("scalar_gate / frame gates / vector_gate=False")
+        if ablate_frame_updates or ablate_scalars or ablate_vectors or scalarization_vectorization_output_dim != 3:
+            unsupported("ablations")
+        if bottleneck > 1 and vi % bottleneck != 0:
+            raise AssertionError(f"Input channel of vector ({vi}) must be divisible with bottleneck factor ({bottleneck})")
+        hd = _cabi.gcp2_hidden_dim(vi, vo, int(bottleneck))
+        if not 1 <= hd <= 16:
+            unsupported(f"hidden vector dim {hd} (supported: 1..16)")
+        if so % 4:
+            unsupported("scalar output dims that are not multiples of 4")
+        super().__init__(si, vi, so, vo, hd)
+        nl = (None, None) if nonlinearities is None else nonlinearities
+        self.acts = (_cabi.ACT[_cabi._norm(nl[0])], _cabi.ACT[_cabi._norm(nl[1])])
+        self.vres, self.e3, self.slope = bool(vector_residual), bool(enable_e3_equivariance), float(nonlinearity_slope)
+        self.scalar_input_dim, self.vector_input_dim, self.scalar_output_dim, self.vector_output_dim = si, vi, so, vo
+        self._layout = {}
+        off = 0
+        for name, shp in _cabi.gcp2_shapes(si, vi, so, vo, hd).items():
+            self._layout[name] = (off, shp)
+            n = 1
+            for d in shp:
+                n *= d
+            off += n
+        self._cache = None
+
+    def _apply(self, fn, *a, **k):
+        self._cache = None
+        return super()._apply(fn, *a, **k)
+
+    def _params_in_order(self):
+        table = dict(self.named_parameters())
+        return [table[n] for n in self._layout]
+
+    def _op_struct(self, params) -> _cabi.Gcp2:
+        ptrs = tuple(p.data_ptr() for p in params)
+        if self._cache is not None and self._cache[0] == ptrs:
+            return self._cache[1]
+        op = _cabi.Gcp2()
+        op.si, op.vi, op.so, op.vo, op.hd = self.dims
+        op.act_s, op.act_v, op.vector_residual = self.acts[0], self.acts[1], int(self.vres)
+        for (name, (off, _)), ptr in zip(self._layout.items(), ptrs):
+            setattr(op, _cabi._PTR_FIELD[name], ptr)
+            op.grad_off[_cabi._GRAD_SLOT[name]] = off
+        self._cache = (ptrs, op)
+        return op
+
+    def forward(self, s_maybe_v, edge_index, frames, node_inputs: bool = False, node_mask=None):
+        s_in, v_in = s_maybe_v[0], s_maybe_v[1]
+        si, vi = self.dims[0], self.dims[1]
+        for t, name in ((s_in, "scalars"), (v_in, "vectors"), (edge_index, "edge_index"), (frames, "frames")):
+            _check_cuda(t, name)
+        M, E = int(s_in.shape[0]), int(edge_index.shape[1])
+        if tuple(s_in.shape) != (M, si) or tuple(v_in.shape) != (M, vi, 3) or s_in.dtype != torch.float32 or v_in.dtype != torch.float32:
+            raise TypeError(f"gcpnet_b200.GCP2: inputs must be float32 [{M}, {si}] and [{M}, {vi}, 3]")
+        if tuple(frames.shape) != (E, 3, 3) or edge_index.dtype != torch.int64:
+            raise TypeError("gcpnet_b200.GCP2: frames must be [E, 3, 3] and edge_index int64 [2, E]")
+        s_in, v_in, edge_index, frames = s_in.contiguous(), v_in.contiguous(), edge_index.contiguous(), frames.contiguous()
+        if node_inputs:
+            if self.e3:
+                raise NotImplementedError("gcpnet_b200.GCP2: enable_e3_equivariance with node_inputs=True is not covered")
+            # node-side scalarize = the node's D against the MEAN frame over its outgoing edges (comp/__init__.py:316-323)
+            gv = graph_views(edge_index, frames, M, node_mask=node_mask)
+            F = gv.fbar_pos if gv.mask is not None else gv.fbar
+        else:
+            if M != E:
+                raise TypeError("gcpnet_b200.GCP2: node_inputs=False needs one row per edge")
+            F = frames if node_mask is None else graph_views(edge_index, frames, int(node_mask.shape[0]), node_mask=node_mask).frames
+        if M == 0:
+            return ScalarVector(s_in.new_zeros((0, self.dims[2])), v_in.new_zeros((0, self.dims[3], 3)))
+        self._grad_mode = torch.is_grad_enabled()
+        s_out, v_out = _Gcp2Fn.apply(self, s_in, v_in, F.reshape(M, 9), *self._params_in_order())
+        return ScalarVector(s_out, v_out)
+
+
+# ------------------------------------------------------------------------------------------
+# GCPLayerNorm on its own
+# ------------------------------------------------------------------------------------------
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, chi, w, b):
+        lib = _lib.load()
+        N = int(h.shape[0]) if h is not None else int(chi.shape[0])
+        s = int(h.shape[1]) if h is not None else 0
+        v = int(chi.shape[1]) if chi is not None else 0
+        out_h = torch.empty_like(h) if h is not None else None
+        out_chi = torch.empty_like(chi) if chi is not None else None
+        _lib.check(lib.gcpnet_layernorm_forward(_ptr(h), _ptr(chi), N, s, v, _ptr(w), _ptr(b), _ptr(out_h), _ptr(out_chi), _stream()),
+                   "gcpnet_layernorm_forward")
+        ctx.save_for_backward(h, chi, w)
+        ctx.dims = (N, s, v)
+        return out_h, out_chi
+
+    @staticmethod
+    def backward(ctx, g_h, g_chi):
+        lib = _lib.load()
+        h, chi, w = ctx.saved_tensors
+        N, s, v = ctx.dims
+        dev = h.device if h is not None else chi.device
+        if h is not None and g_h is None:
+            g_h = torch.zeros_like(h)
+        if chi is not None and g_chi is None:
+            g_chi = torch.zeros_like(chi)
+        gi_h = torch.empty_like(h) if h is not None else None
+        gi_chi = torch.empty_like(chi) if chi is not None else None
+        g_w = torch.empty(s, dtype=torch.float32, device=dev) if s else None
+        g_b = torch.empty(s, dtype=torch.float32, device=dev) if s else None
+        ws = torch.empty(2 * N + 128 * max(s, 1), dtype=torch.float32, device=dev)
+        _lib.check(lib.gcpnet_layernorm_backward(_ptr(h), _ptr(chi), N, s, v, _ptr(w), _ptr(g_h.contiguous() if g_h is not None else None),
+                                                 _ptr(g_chi.contiguous() if g_chi is not None else None), _ptr(gi_h), _ptr(gi_chi),
+                                                 _ptr(g_w), _ptr(g_b), _ptr(ws), _stream()), "gcpnet_layernorm_backward")
+        return gi_h, gi_chi, g_w, g_b
+
+
+class GCPLayerNorm(nn.Module):
+    """``GCPLayerNorm`` (comp/__init__.py:138-167): ``scalar_norm`` = nn.LayerNorm over the scalars (the parameters live in a
+    real ``nn.LayerNorm`` so state_dicts match), vectors divided by the root mean clamped squared channel norm."""
+
+    def __init__(self, dims, eps: float = 1e-8):
+        super().__init__()
+        self.scalar_dims, self.vector_dims = int(dims[0]), int(dims[1])
+        self.scalar_norm = nn.LayerNorm(self.scalar_dims)
+        self.eps = eps
+        if eps != 1e-8:
+            raise NotImplementedError("gcpnet_b200.GCPLayerNorm: eps other than the reference's 1e-8")
+
+    def forward(self, x):
+        if not self.vector_dims:  # comp/__init__.py:160-161: scalars only
+            _check_cuda(x, "scalars")
+            out, _ = _LayerNormFn.apply(x.contiguous(), None, self.scalar_norm.weight, self.scalar_norm.bias)
+            return out
+        s, v = x[0], x[1]
+        _check_cuda(s, "scalars")
+        out_s, out_v = _LayerNormFn.apply(s.contiguous(), v.contiguous(), self.scalar_norm.weight, self.scalar_norm.bias)
+        return ScalarVector(out_s, out_v)
+
+
+# ------------------------------------------------------------------------------------------
+# GCPEmbedding
+# ------------------------------------------------------------------------------------------
+class GCPEmbedding(nn.Module):
+    """``GCPEmbedding`` (gcpnet.py:703-823): optional atom-type / ligand-flag embeddings (``nn.Embedding`` look-ups), input
+    (pre_norm) or output normalisation, an edge GCP2 with ``node_inputs=False`` and a node GCP2 with ``node_inputs=True``.
+    ``cfg.selected_GCP`` is ignored: the GCP2 of this package is used (other perceptrons raise in GCPInteractions)."""
+
+    def __init__(self, edge_input_dims, node_input_dims, edge_hidden_dims, node_hidden_dims, num_atom_types: int = 9,
+                 nonlinearities: Tuple[Optional[str], Optional[str]] = (None, None), num_lig_flags: int = 2, cfg: Any = None,
+                 pre_norm: bool = True):
+        super().__init__()
+        self.atom_embedding = nn.Embedding(num_atom_types, num_atom_types) if num_atom_types > 0 else None
+        self.concatenate_lig_flag = _get(cfg, "concatenate_lig_flag", None)
+        node_input_dims = ScalarVector(int(node_input_dims[0]), int(node_input_dims[1]))
+        if self.concatenate_lig_flag:
+            node_input_dims = ScalarVector(node_input_dims[0] + num_lig_flags, node_input_dims[1])
+            self.lig_flag_embedding = nn.Embedding(num_lig_flags, num_lig_flags)
+        self.pre_norm = bool(pre_norm)
+        self.edge_normalization = GCPLayerNorm(edge_input_dims if pre_norm else edge_hidden_dims)
+        self.node_normalization = GCPLayerNorm(node_input_dims if pre_norm else node_hidden_dims)
+        kw = dict(scalar_gate=_get(cfg, "scalar_gate", 0), vector_gate=_get(cfg, "vector_gate", True),
+                  frame_gate=_get(cfg, "frame_gate", False), sigma_frame_gate=_get(cfg, "sigma_frame_gate", False),
+                  vector_frame_residual=_get(cfg, "vector_frame_residual", False),
+                  ablate_frame_updates=_get(cfg, "ablate_frame_updates", False), ablate_scalars=_get(cfg, "ablate_scalars", False),
+                  ablate_vectors=_get(cfg, "ablate_vectors", False),
+                  enable_e3_equivariance=_get(cfg, "enable_e3_equivariance", False))
+        self.edge_embedding = GCP2(edge_input_dims, edge_hidden_dims, nonlinearities=nonlinearities, **kw)
+        self.node_embedding = GCP2(node_input_dims, node_hidden_dims, nonlinearities=(None, None), **kw)
+
+    def forward(self, batch):
+        h = self.atom_embedding(batch.h) if self.atom_embedding is not None else batch.h
+        if self.concatenate_lig_flag:
+            h = torch.cat((h, self.lig_flag_embedding(batch.lig_flag.long())), dim=-1)
+        node_rep, edge_rep = ScalarVector(h, batch.chi), ScalarVector(batch.e, batch.xi)
+        if self.pre_norm:
+            edge_rep, node_rep = self.edge_normalization(edge_rep), self.node_normalization(node_rep)
+        mask = getattr(batch, "mask", None)
+        edge_rep = self.edge_embedding(edge_rep, batch.edge_index, batch.f_ij, node_inputs=False, node_mask=mask)
+        node_rep = self.node_embedding(node_rep, batch.edge_index, batch.f_ij, node_inputs=True, node_mask=mask)
+        if not self.pre_norm:
+            edge_rep, node_rep = self.edge_normalization(edge_rep), self.node_normalization(node_rep)
+        return node_rep, edge_rep
+
+
+# ------------------------------------------------------------------------------------------
+# the NMS model's forward(batch) (src/models/gcpnet_nms_module.py:127-151)
+# ------------------------------------------------------------------------------------------
+class GCPNetNMS(nn.Module):
+    """Modules and ``forward(batch)`` of ``GCPNetNMSLitModule`` (gcpnet_nms_module.py:56-83,127-151) under the same
+    attribute names, so a shipped checkpoint's ``state_dict`` loads with ``strict=True``: centralize -> localize ->
+    GCPEmbedding -> L x GCPInteractions(updating_node_positions=True) -> decentralize, every step on this package's kernels."""
+
+    def __init__(self, model_cfg, module_cfg, layer_cfg):
+        super().__init__()
+        edge_in = ScalarVector(_get(model_cfg, "e_input_dim"), _get(model_cfg, "xi_input_dim"))
+        node_in = ScalarVector(_get(model_cfg, "h_input_dim"), _get(model_cfg, "chi_input_dim"))
+        self.edge_dims = ScalarVector(_get(model_cfg, "e_hidden_dim"), _get(model_cfg, "xi_hidden_dim"))
+        self.node_dims = ScalarVector(_get(model_cfg, "h_hidden_dim"), _get(model_cfg, "chi_hidden_dim"))
+        self.norm_x_diff = bool(_get(module_cfg, "norm_x_diff", True))
+        self.gcp_embedding = GCPEmbedding(edge_in, node_in, self.edge_dims, self.node_dims, num_atom_types=0, cfg=module_cfg)
+        self.interaction_layers = nn.ModuleList(
+            GCPInteractions(self.node_dims, self.edge_dims, cfg=module_cfg, layer_cfg=layer_cfg,
+                            dropout=float(_get(model_cfg, "dropout", 0.0)), updating_node_positions=True)
+            for _ in range(int(_get(model_cfg, "num_encoder_layers"))))
+
+    def forward(self, batch):
+        num_graphs = getattr(batch, "num_graphs", None)
+        x_centroid, batch.x = centralize(batch, "x", batch.batch, num_graphs=num_graphs)
+        batch.f_ij = localize(batch.x, batch.edge_index, norm_x_diff=self.norm_x_diff)
+        (h, chi), (e, xi) = self.gcp_embedding(batch)
+        for layer in self.interaction_layers:
+            (h, chi), batch.x = layer((h, chi), (e, xi), batch.edge_index, batch.f_ij, node_pos=batch.x)
+        batch.h, batch.chi, batch.e, batch.xi = h, chi, e, xi
+        batch.x = decentralize(batch, "x", batch.batch, x_centroid)
+        return batch, batch.x

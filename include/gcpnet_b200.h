@@ -232,6 +232,31 @@ int gcpnet_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, 
 int gcpnet_message_passing_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, const gcpnet_plan* plan,
                                    const gcpnet_forward_io* io, float* aggregate, void* stream);
 
+/* One GCP2 on its own (GCP2.forward, gcpnet.py:393-468), e.g. the edge / node embeddings of GCPEmbedding (gcpnet.py:735-823).
+ * Rows are entities: s_in[M][si], v_in[M][vi][3], frames[M][9] = the edge's frame (node_inputs=False) or the mean frame over
+ * the node's outgoing edges (node_inputs=True: gcpnet_graph.fbar / fbar_pos).  op->grad_off[] are offsets into this module's
+ * own flat gradient g_params[gcpnet_gcp2_plan.n_params]. */
+typedef struct gcpnet_gcp2_plan {
+  int32_t tile, grid, smem_fwd_bytes, smem_bwd_bytes, n_params, reserved;
+  int64_t packed_floats;   /* packed weights (written by the forward call, read by the matching backward) */
+  int64_t saved_floats;    /* M * (so + vo) activations kept for backward */
+  int64_t partial_floats;  /* grid * n_params per-CTA weight-gradient partials */
+} gcpnet_gcp2_plan;
+int gcpnet_gcp2_plan_query(const gcpnet_gcp2* op, int64_t num_rows, gcpnet_gcp2_plan* plan);
+int gcpnet_gcp2_forward(const gcpnet_gcp2* op, int64_t num_rows, const float* s_in, const float* v_in, const float* frames,
+                        int enable_e3, float slope, float* s_out, float* v_out, float* saved, float* packed, void* stream);
+int gcpnet_gcp2_backward(const gcpnet_gcp2* op, int64_t num_rows, const float* s_in, const float* v_in, const float* frames,
+                         int enable_e3, float slope, const float* saved, const float* packed, const float* g_s_out,
+                         const float* g_v_out, float* g_s_in, float* g_v_in, float* g_params, float* ws_partial, void* stream);
+
+/* GCPLayerNorm on its own (comp/__init__.py:138-167): scalars nn.LayerNorm(s) (w, b, eps 1e-5), vectors divided by
+ * sqrt(mean_c max(|v_c|^2, 1e-8)).  s == 0 or v == 0 drops that part.  Backward workspace: 2 N + 128 s floats. */
+int gcpnet_layernorm_forward(const float* h, const float* chi, int64_t num_rows, int32_t s, int32_t v, const float* w,
+                             const float* b, float* out_h, float* out_chi, void* stream);
+int gcpnet_layernorm_backward(const float* h, const float* chi, int64_t num_rows, int32_t s, int32_t v, const float* w,
+                              const float* g_out_h, const float* g_out_chi, float* g_h, float* g_chi, float* g_w, float* g_b,
+                              float* workspace, void* stream);
+
 /* Backward of GCPMessagePassing.forward alone: g_aggregate[N][s+3v] = cotangent of the aggregate.  Uses of `io`:
  * h, chi, e, xi, frames, saved_edge, packed (inputs); g_h, g_chi, g_e, g_xi (overwritten); g_params[0 .. n_edge_params)
  * (the message_fusion.* gradients); ws_edge, ws_edge_partial (workspaces).  The node-side fields are ignored. */

@@ -135,3 +135,50 @@ def checksum(t: torch.Tensor) -> float:
 
 def fixture_path(name: str) -> str:
     return os.path.join(GOLDEN_DIR, f"{name}.npz")
+
+
+# ------------------------------------------------------------------------------------------
+# whole-model case: GCPNetNMSLitModule.forward(batch) on the shipped NMS_Small checkpoint
+# ------------------------------------------------------------------------------------------
+NMS_CKPT = "checkpoints/NMS/NMS_Small/model_epoch_9977_mse_0_0070.ckpt"
+NMS_MODEL_FIXTURE = "nms_small_model"
+
+
+class Bag:
+    """Attribute bag standing in for a torch_geometric Batch (attribute and item access)."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def __getitem__(self, k):
+        return getattr(self, k)
+
+    def __setitem__(self, k, v):
+        setattr(self, k, v)
+
+
+def nms_raw_batch(num_graphs: int = 6, n: int = 5, seed: int = 31):
+    """Raw NMS inputs in the shapes of src/datamodules/components/nms_dataset.py:22-61,159-169: h = |velocity| [N,1],
+    chi = [velocity, forward, backward differences] [N,3,3], e = [charge product | 16 RBFs of the distance] [E,17],
+    xi = unit direction [E,1,3], x positions, fully connected directed 5-body graphs."""
+    g = torch.Generator().manual_seed(seed)
+    N = num_graphs * n
+    ei = O.nms_edge_index(num_graphs, n)
+    x = torch.randn(N, 3, generator=g) + torch.randn(num_graphs, 1, 3, generator=g).repeat_interleave(n, 0).reshape(N, 3) * 2.0
+    vel = torch.randn(N, 3, generator=g) * 0.5
+    charge = (torch.randint(0, 2, (N,), generator=g) * 2 - 1).float()
+    row, col = ei
+    d = x[row] - x[col]
+    dist = d.norm(dim=-1, keepdim=True)
+    mu = torch.linspace(0.0, 4.5, 16).view(1, -1)
+    rbf = torch.exp(-((dist - mu) / (4.5 / 16)) ** 2)
+    e = torch.cat(((charge[row] * charge[col]).unsqueeze(-1), rbf), dim=-1)
+    xi = (d / dist.clamp(min=1e-8)).unsqueeze(1)
+    idx = torch.arange(N).view(num_graphs, n)
+    fwd = (x.view(num_graphs, n, 3)[:, list(range(1, n)) + [0]] - x.view(num_graphs, n, 3)).reshape(N, 3)
+    bwd = (x.view(num_graphs, n, 3)[:, [n - 1] + list(range(n - 1))] - x.view(num_graphs, n, 3)).reshape(N, 3)
+    chi = torch.stack((vel, fwd, bwd), dim=1)
+    batch = torch.arange(num_graphs).repeat_interleave(n)
+    del idx
+    return dict(h=vel.norm(dim=-1, keepdim=True), chi=chi, e=e, xi=xi, x=x, edge_index=ei, batch=batch,
+                label=x + vel + 0.1 * torch.randn(N, 3, generator=g))

@@ -98,15 +98,44 @@ def run_reference(name: str, case: dict):
     print(f"{name}: N={n} E={inp['edge_index'].shape[1]} loss={loss.item():.6f} -> {GC.fixture_path(name)}")
 
 
+def run_nms_model():
+    """GCPNetNMSLitModule.forward(batch) + MSE loss on the shipped NMS_Small checkpoint (eval mode): predicted positions and
+    the gradients of the loss w.r.t. every parameter (sampled), through the reference's own LightningModule class."""
+    import types
+    ref, Lit = ref_shim.load_nms_litmodule()
+    model_cfg, module_cfg, layer_cfg = ref_shim.nms_model_cfgs(ref)
+    layer_class = lambda *a, **k: ref.GCPInteractions(*a, updating_node_positions=True, **k)
+    lit = Lit(layer_class=layer_class, optimizer=None, scheduler=None, model_cfg=model_cfg, module_cfg=module_cfg, layer_cfg=layer_cfg)
+    sd = ref_shim.load_checkpoint_state_dict(GC.NMS_CKPT)
+    missing, unexpected = lit.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    lit.eval()
+    raw = GC.nms_raw_batch()
+    b = GC.Bag(**{k: v.clone() for k, v in raw.items()})
+    _, preds = lit.forward(b)
+    loss = torch.nn.functional.mse_loss(preds, raw["label"])
+    loss.backward()
+    rec = {"preds": preds.detach().numpy(), "loss": np.float64(loss.item()), "out_h": b.h.detach().numpy(), "out_chi": b.chi.detach().numpy()}
+    for k, p in lit.named_parameters():
+        rec["pgrad/" + k] = sample(p.grad if p.grad is not None else torch.zeros_like(p))
+    for k, v in sd.items():
+        rec["param/" + k] = v.float().numpy()
+    np.savez_compressed(GC.fixture_path(GC.NMS_MODEL_FIXTURE), **rec)
+    print(f"{GC.NMS_MODEL_FIXTURE}: loss={loss.item():.6f} -> {GC.fixture_path(GC.NMS_MODEL_FIXTURE)}")
+
+
 def main(argv):
     if not ref_shim.reference_available():
         print("reference tree not available; nothing generated", file=sys.stderr)
         return 1
     torch.manual_seed(0)
     torch.set_num_threads(1)  # bitwise reproducible reductions
-    names = argv[1:] or list(GC.CASES)
+    names = argv[1:] or (list(GC.CASES) + [GC.NMS_MODEL_FIXTURE])
     for name in names:
-        run_reference(name, GC.CASES[name])
+        if name == GC.NMS_MODEL_FIXTURE:
+            run_nms_model()
+        else:
+            run_reference(name, GC.CASES[name])
     return 0
 
 

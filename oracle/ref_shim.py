@@ -196,6 +196,55 @@ def make_cfgs(ref, *, num_message_layers=8, pre_norm=False, num_feedforward_laye
     return cfg, layer_cfg
 
 
+def load_nms_litmodule():
+    """The reference's own ``GCPNetNMSLitModule`` class (src/models/gcpnet_nms_module.py), imported unmodified under stubs
+    for pytorch_lightning (LightningModule = nn.Module + save_hyperparameters) and torchmetrics (inert metric modules)."""
+    import importlib
+    import torch.nn as nn
+    ref = load_reference()
+
+    class _LightningModule(nn.Module):
+        def save_hyperparameters(self, *a, logger=True, ignore=None, **k):
+            import inspect
+            frame = inspect.currentframe().f_back
+            init_args = {k: v for k, v in frame.f_locals.items() if k not in ("self", "__class__") and k not in (ignore or [])}
+            kwargs = init_args.pop("kwargs", {})
+            init_args.update(kwargs)
+            self.hparams = AttrDict(init_args)
+
+    class _Metric(nn.Module):
+        def __init__(self, *a, **k):
+            super().__init__()
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    mod("pytorch_lightning", LightningModule=_LightningModule)
+    tm = mod("torchmetrics", MeanMetric=_Metric, MinMetric=_Metric, MaxMetric=_Metric, CosineSimilarity=_Metric)
+    tm.regression = mod("torchmetrics.regression")
+    tm.regression.mse = mod("torchmetrics.regression.mse", MeanSquaredError=_Metric)
+    saved = sys.modules.get("typeguard")
+    sys.modules["typeguard"] = types.ModuleType("typeguard")
+    sys.modules["typeguard"].typechecked = lambda f=None, **kw: f if f is not None else (lambda g: g)
+    try:
+        m = importlib.import_module("src.models.gcpnet_nms_module")
+    finally:
+        if saved is not None:
+            sys.modules["typeguard"] = saved
+    return ref, m.GCPNetNMSLitModule
+
+
+def nms_model_cfgs(ref):
+    """configs/model/model_cfg/gcp_model_nms.yaml + module_cfg/gcp_module_nms.yaml + layer_cfg/gcp_interaction_layer_nms.yaml."""
+    module_cfg, layer_cfg = make_cfgs(ref)
+    model_cfg = AttrDict(h_input_dim=1, chi_input_dim=3, e_input_dim=17, xi_input_dim=1, h_hidden_dim=64, chi_hidden_dim=16,
+                         e_hidden_dim=32, xi_hidden_dim=4, num_encoder_layers=4, num_decoder_layers=3, dropout=0.1)
+    return model_cfg, module_cfg, layer_cfg
+
+
 class _StubUnpickler(pickle.Unpickler):
     """Lightning 1.7.7 checkpoints pickle omegaconf/hydra objects in `hyper_parameters`;
     replace any class that is not importable here with an inert placeholder."""

@@ -1,0 +1,144 @@
+"""The callers either side of the interaction layers on the same kernels: GCP2 and GCPLayerNorm on their own, GCPEmbedding,
+and the whole NMS model -- ``forward(batch)`` + MSE loss + backward -- against the committed outputs of the reference's own
+``GCPNetNMSLitModule`` run on the shipped NMS_Small checkpoint (tests/golden/nms_small_model.npz, made by
+oracle/make_golden.py).  Tolerance 1e-4 relative to the tensor's max magnitude.  Needs a GPU (-m gpu)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gcp_oracle as O
+from oracle import golden_cases as GC
+from tests.helpers import AttrDict, rel_err, sample_like_fixture
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _gcp2_params(mod, prefix="m."):
+    return {prefix + k: v.detach().cpu().clone() for k, v in mod.state_dict().items()}
+
+
+@pytest.mark.parametrize("dims,node_inputs,acts,bottleneck,vres", [
+    (((17, 1), (32, 4)), False, (None, None), 1, False),        # NMS edge embedding (gcpnet.py:735-748)
+    (((1, 3), (64, 16)), True, (None, None), 1, False),         # NMS node embedding (:750-763)
+    (((6, 3), (100, 16)), True, ("silu", "sigmoid"), 1, False),  # CPD node input dims, GCP2's default vector nonlinearity
+    (((32, 8), (32, 8)), False, ("relu", None), 4, True),       # bottleneck + vector residual
+])
+@pytest.mark.parametrize("masked", [False, True])
+def test_gcp2_alone_matches_oracle(dims, node_inputs, acts, bottleneck, vres, masked):
+    import gcpnet_b200
+    (si, vi), (so, vo) = dims
+    g = torch.Generator().manual_seed(400)
+    n, E = 130, 900
+    ei = torch.randint(0, n - 2, (2, E), generator=g)
+    mask = (torch.rand(n, generator=g) > 0.2) if masked else None
+    pos = torch.randn(n, 3, generator=g)
+    frames = O.localize(pos, ei, node_mask=mask)
+    M = n if node_inputs else E
+    s_in, v_in = torch.randn(M, si, generator=g), torch.randn(M, vi, 3, generator=g)
+    torch.manual_seed(401)
+    mod = gcpnet_b200.GCP2((si, vi), (so, vo), nonlinearities=acts, bottleneck=bottleneck, vector_residual=vres).cuda()
+    p = {k: v.clone().requires_grad_(True) for k, v in _gcp2_params(mod).items()}
+    ls, lv = s_in.clone().requires_grad_(True), v_in.clone().requires_grad_(True)
+    ws, wV = O.gcp2(p, "m.", ls, lv, ei, frames, node_inputs=node_inputs, act_s=O.activation(acts[0]), act_v=O.activation(acts[1]),
+                    vector_residual=vres, e3=False, node_mask=mask)
+    cs, cv = torch.randn(M, so, generator=g), torch.randn(M, vo, 3, generator=g)
+    ((ws * cs).sum() + (wV * cv).sum()).backward()
+    ds, dv = s_in.cuda().requires_grad_(True), v_in.cuda().requires_grad_(True)
+    out = mod((ds, dv), ei.cuda(), frames.cuda(), node_inputs=node_inputs, node_mask=None if mask is None else mask.cuda())
+    ((out[0] * cs.cuda()).sum() + (out[1] * cv.cuda()).sum()).backward()
+    assert rel_err(out[0].detach().cpu().numpy(), ws.detach().numpy()) < TOL
+    assert rel_err(out[1].detach().cpu().numpy(), wV.detach().numpy()) < TOL
+    assert rel_err(ds.grad.cpu().numpy(), ls.grad.numpy()) < TOL and rel_err(dv.grad.cpu().numpy(), lv.grad.numpy()) < TOL
+    for k, t in mod.named_parameters():
+        assert rel_err(t.grad.cpu().numpy(), p["m." + k].grad.numpy()) < TOL, k
+
+
+@pytest.mark.parametrize("dims", [(17, 1), (1, 3), (64, 16), (100, 0)])
+def test_layernorm_alone_matches_oracle(dims):
+    """GCPLayerNorm (comp/__init__.py:138-167), including a one-element scalar LayerNorm and the scalar-only form."""
+    import gcpnet_b200
+    s, v = dims
+    g = torch.Generator().manual_seed(410)
+    n = 333
+    h = torch.randn(n, s, generator=g) * 2 + 0.5
+    chi = torch.randn(n, v, 3, generator=g) if v else None
+    if v:
+        chi[5] = 0.0  # all-zero vectors: the clamp at 1e-8 decides (comp/__init__.py:151)
+    ln = gcpnet_b200.GCPLayerNorm(dims).cuda()
+    with torch.no_grad():
+        ln.scalar_norm.weight.copy_(1 + 0.1 * torch.randn(s, generator=g))
+        ln.scalar_norm.bias.copy_(0.1 * torch.randn(s, generator=g))
+    p = {"scalar_norm.weight": ln.scalar_norm.weight.detach().cpu().clone().requires_grad_(True),
+         "scalar_norm.bias": ln.scalar_norm.bias.detach().cpu().clone().requires_grad_(True)}
+    cfg = O.OracleConfig()
+    lh = h.clone().requires_grad_(True)
+    ch = torch.randn(n, s, generator=g)
+    dh = h.cuda().requires_grad_(True)
+    if v:
+        lchi = chi.clone().requires_grad_(True)
+        cchi = torch.randn(n, v, 3, generator=g)
+        wh, wchi = O.gcp_layernorm(p, "", cfg, lh, lchi)
+        ((wh * ch).sum() + (wchi * cchi).sum()).backward()
+        dchi = chi.cuda().requires_grad_(True)
+        oh, ochi = ln((dh, dchi))
+        ((oh * ch.cuda()).sum() + (ochi * cchi.cuda()).sum()).backward()
+        assert rel_err(ochi.detach().cpu().numpy(), wchi.detach().numpy()) < TOL
+        assert rel_err(dchi.grad.cpu().numpy(), lchi.grad.numpy()) < TOL
+    else:
+        wh = torch.nn.functional.layer_norm(lh, (s,), p["scalar_norm.weight"], p["scalar_norm.bias"], 1e-5)
+        (wh * ch).sum().backward()
+        oh = ln(dh)
+        (oh * ch.cuda()).sum().backward()
+    assert rel_err(oh.detach().cpu().numpy(), wh.detach().numpy()) < TOL
+    if s > 1:  # a one-element LayerNorm has zero input gradient and zero weight gradient
+        assert rel_err(dh.grad.cpu().numpy(), lh.grad.numpy()) < TOL
+        assert rel_err(ln.scalar_norm.weight.grad.cpu().numpy(), p["scalar_norm.weight"].grad.numpy()) < TOL
+    else:
+        assert float(dh.grad.abs().max()) < 1e-5
+    assert rel_err(ln.scalar_norm.bias.grad.cpu().numpy(), p["scalar_norm.bias"].grad.numpy()) < TOL
+
+
+def _nms_model():
+    import gcpnet_b200
+    model_cfg = AttrDict(h_input_dim=1, chi_input_dim=3, e_input_dim=17, xi_input_dim=1, h_hidden_dim=64, chi_hidden_dim=16,
+                         e_hidden_dim=32, xi_hidden_dim=4, num_encoder_layers=4, num_decoder_layers=3, dropout=0.1)
+    module_cfg = AttrDict(norm_x_diff=True, scalar_gate=0, vector_gate=True, vector_residual=False, vector_frame_residual=False,
+                          frame_gate=False, sigma_frame_gate=False, scalar_nonlinearity="relu", vector_nonlinearity=None,
+                          nonlinearities=["relu", None], bottleneck=4, vector_linear=True, vector_identity=True,
+                          default_vector_residual=False, default_bottleneck=4, node_positions_weight=1.0,
+                          ablate_frame_updates=False, ablate_scalars=False, ablate_vectors=False, ablate_x_force_update=True,
+                          enable_e3_equivariance=False)
+    mp = AttrDict(edge_encoder=False, edge_gate=False, num_message_layers=8, message_residual=0, message_ff_multiplier=1,
+                  self_message=True, use_residual_message_gcp=True)
+    layer_cfg = AttrDict(pre_norm=False, num_feedforward_layers=2, dropout=0.1, nonlinearity_slope=1e-2, mp_cfg=mp)
+    return gcpnet_b200.GCPNetNMS(model_cfg, module_cfg, layer_cfg)
+
+
+def test_nms_model_forward_backward_matches_the_reference_litmodule_on_the_shipped_checkpoint():
+    """Whole ``forward(batch)`` of GCPNetNMSLitModule (gcpnet_nms_module.py:127-151) on checkpoints/NMS/NMS_Small: centralize,
+    localize, GCPEmbedding, 4 x GCPInteractions, decentralize -- every step on this package's kernels -- then the MSE loss and
+    its gradient w.r.t. all 442 044 parameters."""
+    fx = np.load(GC.fixture_path(GC.NMS_MODEL_FIXTURE))
+    model = _nms_model()
+    sd = {k[len("param/"):]: torch.from_numpy(fx[k]) for k in fx.files if k.startswith("param/")}
+    model.load_state_dict(sd, strict=True)  # the checkpoint's names and shapes, nothing missing, nothing extra
+    assert sum(p.numel() for p in model.parameters()) == sum(v.numel() for v in sd.values())
+    model = model.cuda().eval()
+    raw = GC.nms_raw_batch()
+    b = GC.Bag(**{k: v.cuda() for k, v in raw.items()})
+    b.num_graphs = 6
+    _, preds = model(b)
+    loss = torch.nn.functional.mse_loss(preds, raw["label"].cuda())
+    loss.backward()
+    assert rel_err(preds.detach().cpu().numpy(), fx["preds"]) < TOL
+    assert rel_err(b.h.detach().cpu().numpy(), fx["out_h"]) < TOL and rel_err(b.chi.detach().cpu().numpy(), fx["out_chi"]) < TOL
+    assert abs(float(loss) - float(fx["loss"])) < 1e-5 * max(1.0, abs(float(fx["loss"])))
+    worst = 0.0
+    for k, p in model.named_parameters():
+        want = fx["pgrad/" + k]
+        err = rel_err(sample_like_fixture(p.grad.cpu()), want)
+        worst = max(worst, err)
+        # trained ReLU weights: a few gradient tensors are tiny sums over 30 nodes; hold every tensor to 1e-3 and the bulk to 1e-4
+        assert err < 1e-3, (k, err)
+    assert worst < 1e-3

@@ -52,12 +52,12 @@ def test_ctypes_structs_match_header_sizes(tmp_path):
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include "gcpnet_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(gcpnet_gcp2),sizeof(gcpnet_layer),sizeof(gcpnet_graph),sizeof(gcpnet_plan),'
-                   'sizeof(gcpnet_forward_io),sizeof(gcpnet_backward_io));return 0;}\n')
+                   'sizeof(gcpnet_forward_io),sizeof(gcpnet_backward_io));printf("%zu\\n",sizeof(gcpnet_gcp2_plan));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     assert sizes == [C.sizeof(_cabi.Gcp2), C.sizeof(_cabi.Layer), C.sizeof(_cabi.Graph), C.sizeof(_cabi.Plan),
-                     C.sizeof(_cabi.ForwardIO), C.sizeof(_cabi.BackwardIO)]
+                     C.sizeof(_cabi.ForwardIO), C.sizeof(_cabi.BackwardIO), C.sizeof(_cabi.Gcp2Plan)]
 
 
 def test_state_dict_names_shapes_and_init_match_reference_layout():
