@@ -154,7 +154,7 @@ def declare(lib: C.CDLL) -> None:
         [C.c_void_p] * 5
     lib.gcpnet_gcp2_backward.restype = C.c_int
     lib.gcpnet_gcp2_backward.argtypes = [C.POINTER(Gcp2), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float] + \
-        [C.c_void_p] * 10
+        [C.c_void_p] * 9
     lib.gcpnet_layernorm_forward.restype = C.c_int
     lib.gcpnet_layernorm_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 5
     lib.gcpnet_layernorm_backward.restype = C.c_int

@@ -95,7 +95,7 @@ def test_layernorm_alone_matches_oracle(dims):
         assert rel_err(dh.grad.cpu().numpy(), lh.grad.numpy()) < TOL
         assert rel_err(ln.scalar_norm.weight.grad.cpu().numpy(), p["scalar_norm.weight"].grad.numpy()) < TOL
     else:
-        assert float(dh.grad.abs().max()) < 1e-5
+        assert float(dh.grad.abs().max()) < 1e-3  # (x - mean) = 0 up to rounding, times rstd = 1 / sqrt(eps) = 316
     assert rel_err(ln.scalar_norm.bias.grad.cpu().numpy(), p["scalar_norm.bias"].grad.numpy()) < TOL
 
 
@@ -137,6 +137,11 @@ def test_nms_model_forward_backward_matches_the_reference_litmodule_on_the_shipp
     worst = 0.0
     for k, p in model.named_parameters():
         want = fx["pgrad/" + k]
+        if float(np.abs(want).max()) < 1e-6:
+            # LayerNorm over ONE scalar (h_input_dim = 1): x - mean is exactly 0 in exact arithmetic, the weight gradient
+            # is rounding noise times rstd = 316 in the reference too -- nothing to be relative to
+            assert float(p.grad.abs().max()) < 1e-3, k
+            continue
         err = rel_err(sample_like_fixture(p.grad.cpu()), want)
         worst = max(worst, err)
         # trained ReLU weights: a few gradient tensors are tiny sums over 30 nodes; hold every tensor to 1e-3 and the bulk to 1e-4
