@@ -40,8 +40,13 @@ WORKLOADS = {
                  kind="knn", k=10, layers=6, node_dims=(100, 16), edge_dims=(32, 4), pos=False),
     "cfg4": dict(desc="NMS 20-body, 128 graphs per GPU, 4 layers", graphs=128, n=20, kind="nms", layers=4,
                  node_dims=(64, 16), edge_dims=(32, 4), pos=True),
-    "cfg5": dict(desc="CPD-like, 8 x 256 residues, kNN k=30, 6 encoder layers", graphs=8, n=256, kind="knn", k=30,
-                 layers=6, node_dims=(100, 16), edge_dims=(32, 4), pos=False),
+    "cfg5": dict(desc="CPD-like encoder, 8 x 256 residues, kNN k=30, 6 layers, 5 % of the nodes masked", graphs=8, n=256, kind="knn", k=30,
+                 layers=6, node_dims=(100, 16), edge_dims=(32, 4), pos=False, mask_frac=0.05),
+    "cfg5d": dict(desc="CPD-like decoder, 8 x 256 residues, kNN k=30, 6 autoregressive layers, 5 % masked", graphs=8, n=256, kind="knn",
+                  k=30, layers=6, node_dims=(100, 16), edge_dims=(32, 4), pos=False, mask_frac=0.05, autoregressive=True),
+    # BASELINE configs[3] as a STRONG-scaling case: 1 024 twenty-body graphs in total, sharded 1 024 / N per GPU
+    "cfg4s": dict(desc="NMS 20-body, 1024 graphs in total sharded by graph across the GPUs, 4 layers", graphs=1024, n=20, kind="nms",
+                  layers=4, node_dims=(64, 16), edge_dims=(32, 4), pos=True, strong=True),
 }
 
 
@@ -92,6 +97,10 @@ def make_batch(w, seed, rank=0):
     se, ve = w["edge_dims"]
     b = dict(h=torch.randn(N, s, generator=g), chi=torch.randn(N, v, 3, generator=g), e=torch.randn(E, se, generator=g),
              xi=torch.randn(E, ve, 3, generator=g), edge_index=ei.contiguous(), pos=pos.contiguous())
+    if w.get("mask_frac"):
+        b["mask"] = (torch.rand(N, generator=g) >= w["mask_frac"])
+    if w.get("autoregressive"):  # node_rep_regressive = the encoder's embeddings (gcpnet_cpd_module.py:196-207)
+        b["h_ar"], b["chi_ar"] = torch.randn(N, s, generator=g), torch.randn(N, v, 3, generator=g)
     return {k: t.pin_memory() if torch.cuda.is_available() else t for k, t in b.items()}, N, E
 
 
@@ -192,7 +201,10 @@ def cpu_steps(w, steps, warmup, threads=None):
     L = w["layers"]
     params = [{k: t.requires_grad_(True) for k, t in O.random_layer_params(cfg, seed=10 + i).items()} for i in range(L)]
     batch, N, E = make_batch(w, seed=0)
-    frames = O.localize(batch["pos"], batch["edge_index"])
+    mask = batch.get("mask")
+    frames = O.localize(batch["pos"], batch["edge_index"], node_mask=mask)
+    if w.get("autoregressive"):
+        cfg.reduce_function = "add"
     p_drop = 0.1
     times = []
     for it in range(warmup + steps):
@@ -202,10 +214,12 @@ def cpu_steps(w, steps, warmup, threads=None):
         pos = batch["pos"]
         s, v = cfg.node_dims
         for i in range(L):
-            masks = [((torch.rand(N, s) >= p_drop).float() / (1 - p_drop), (torch.rand(N, v) >= p_drop).float() / (1 - p_drop))
+            nk = N if mask is None else int(mask.sum())
+            masks = [((torch.rand(nk, s) >= p_drop).float() / (1 - p_drop), (torch.rand(nk, v) >= p_drop).float() / (1 - p_drop))
                      for _ in range(2)]
             out = O.interactions_forward(params[i], cfg, h, chi, e, xi, batch["edge_index"], frames,
-                                         node_pos=pos if w["pos"] else None, drop_masks=masks)
+                                         node_pos=pos if w["pos"] else None, drop_masks=masks, node_mask=mask,
+                                         node_rep_regressive=(batch["h_ar"], batch["chi_ar"]) if "h_ar" in batch else None)
             if w["pos"]:
                 (h, chi), pos = out
             else:
@@ -251,7 +265,8 @@ def build_stack(w, device):
     torch.manual_seed(0)
     layers = torch.nn.ModuleList([
         gcpnet_b200.GCPInteractions(w["node_dims"], w["edge_dims"], cfg=mcfg, layer_cfg=lcfg, dropout=0.1,
-                                    updating_node_positions=w["pos"]) for _ in range(w["layers"])]).to(device)
+                                    updating_node_positions=w["pos"], autoregressive=bool(w.get("autoregressive")))
+        for _ in range(w["layers"])]).to(device)
     layers.train()
     return layers
 
@@ -260,14 +275,21 @@ def loss_fn(layers, w, dev_batch):
     """frames + graph views + L x forward + loss, everything on the current stream."""
     import gcpnet_b200
     b = dev_batch
-    gcpnet_b200.prepack(layers, b["h"].shape[0], b["edge_index"].shape[1])  # all layers' weight packing, on a side stream
-    frames = gcpnet_b200.localize(b["pos"], b["edge_index"])
+    # all layers' weight packing, on a side stream
+    gcpnet_b200.prepack(layers, b["h"].shape[0], b["edge_index"].shape[1], autoregressive="h_ar" in b)
+    mask = b.get("mask")
+    frames = gcpnet_b200.localize(b["pos"], b["edge_index"], node_mask=mask)
     h, chi, e, xi, pos = b["h"], b["chi"], b["e"], b["xi"], b["pos"]
+    kw = {}
+    if mask is not None:
+        kw["node_mask"] = mask
+    if "h_ar" in b:
+        kw["node_rep_regressive"] = (b["h_ar"], b["chi_ar"])
     for layer in layers:
         if w["pos"]:
-            (h, chi), pos = layer((h, chi), (e, xi), b["edge_index"], frames, node_pos=pos)
+            (h, chi), pos = layer((h, chi), (e, xi), b["edge_index"], frames, node_pos=pos, **kw)
         else:
-            h, chi = layer((h, chi), (e, xi), b["edge_index"], frames)
+            h, chi = layer((h, chi), (e, xi), b["edge_index"], frames, **kw)
     return h.sum() + chi.sum() + (pos.sum() if w["pos"] else 0.0)
 
 
@@ -328,7 +350,9 @@ def run_ours(args, w):
     def to_dev_packed():
         dflat = hflat.to(dev, non_blocking=True)
         d = {k: dflat[seg[k]:seg[k] + host[k].numel()].view(host[k].shape) for k in fkeys}
-        d["edge_index"] = host["edge_index"].to(dev, non_blocking=True)
+        for k in host:
+            if k not in fkeys:  # edge_index, node mask
+                d[k] = host[k].to(dev, non_blocking=True)
         for k in ("h", "chi", "e", "xi"):
             d[k].requires_grad_(True)
         return d, dflat
@@ -426,7 +450,9 @@ def run_ours(args, w):
         if graphed is not None:
             # pinned host buffers -> the graph's static device buffers (two async copies), replay
             dflat.copy_(hflat, non_blocking=True)
-            dbatch["edge_index"].copy_(host["edge_index"], non_blocking=True)
+            for k in host:
+                if k not in fkeys:
+                    dbatch[k].copy_(host[k], non_blocking=True)
             loss = one_step(dbatch)
         else:
             loss = one_step(to_dev())
@@ -464,7 +490,7 @@ def run_ours(args, w):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
-    h2d = hflat.numel() * hflat.element_size() + host["edge_index"].numel() * host["edge_index"].element_size()  # bytes actually copied
+    h2d = hflat.numel() * hflat.element_size() + sum(host[k].numel() * host[k].element_size() for k in host if k not in fkeys)  # bytes actually copied
     if rank == 0:
         s, v = w["node_dims"]
         se, ve = w["edge_dims"]
@@ -507,7 +533,8 @@ def run_ours(args, w):
         _emit({
             "metric": "edges/s (fused GCP msg+aggregate fwd+bwd)", "value": world * units * args.steps / (dev_ms * 1e-3),
             "unit": "edge-layers/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if w.get("strong") else "weak",
+            "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": config_of(args, w, N, E, world),
             "method": {"l2": "flushed (256 MiB write) before every timed step", "timing": "CUDA events per step, summed, max over ranks",
@@ -558,7 +585,11 @@ def main():
     ap.add_argument("--option", action="append", default=[], metavar="NAME=0|1",
                     help="library switch for A/B runs (gcpnet_set_option): tc, post_fused, early_fork")
     args = ap.parse_args()
-    w = WORKLOADS[args.workload]
+    w = dict(WORKLOADS[args.workload])
+    if w.get("strong"):  # total work fixed: every rank takes graphs / world_size graphs of the bucket
+        world = int(os.environ.get("WORLD_SIZE", "1")) if args.impl != "reference" else 1
+        w["graphs_total"] = w["graphs"]
+        w["graphs"] = w["graphs"] // world
     if args.impl == "reference":
         run_reference(args, w)
     else:

@@ -15,6 +15,11 @@ that every replay overwrites).  With ``model=`` the gradients of all fused layer
 the per-layer NCCL all-reduces are captured inside the graph on the library's side stream, overlapping with the
 backward of the layers below.  ``optimizer.zero_grad(set_to_none=True)`` between replays is tolerated: every call
 re-attaches the captured gradient tensors.
+
+PyTorch pitfall (the engine warns about it): a loss tensor of an EARLIER eager or captured step that is still alive keeps
+the parameters' AccumulateGrad nodes -- which remember the stream they were created on -- alive, and a new capture that
+reuses them fails with "dependency created on uncaptured work in another stream".  Drop such tensors (or ``.detach()``
+them) before constructing a GraphedStep; this class itself only keeps the detached loss value.
 """
 from __future__ import annotations
 
@@ -30,14 +35,15 @@ from .interactions import clear_graph_cache
 _PACK_STREAM = {}
 
 
-def prepack(layers, num_nodes: int, num_edges: int) -> None:
-    """Pack the weights of all `layers` (gcpnet_b200.GCPInteractions) on a side stream at the start of a step."""
+def prepack(layers, num_nodes: int, num_edges: int, autoregressive: bool = False) -> None:
+    """Pack the weights of all `layers` (gcpnet_b200.GCPInteractions) on a side stream at the start of a step
+    (``autoregressive``: the layers will be called with ``node_rep_regressive``)."""
     dev = torch.cuda.current_device()
     st = _PACK_STREAM.get(dev)
     if st is None and not torch.cuda.is_current_stream_capturing():
         st = _PACK_STREAM[dev] = torch.cuda.Stream()
     for layer in layers:
-        layer.prepack(num_nodes, num_edges, st)
+        layer.prepack(num_nodes, num_edges, st, autoregressive)
 
 
 class GraphedStep:
@@ -51,7 +57,8 @@ class GraphedStep:
         self.flat = None
         if model is not None:
             from .ddp import FlatGradients
-            self.flat = FlatGradients(model, process_group=process_group)
+            # an existing FlatGradients is shared (several captured steps of one model: gcpnet_b200.bucketing)
+            self.flat = model if isinstance(model, FlatGradients) else FlatGradients(model, process_group=process_group)
             if not self.params:
                 self.params = [p for p, _ in self.flat._views]
         lib = _lib.load()
@@ -74,8 +81,15 @@ class GraphedStep:
         with torch.cuda.graph(self.graph, stream=cap):
             if self.flat is not None:
                 self.flat.zero_others()
-            self.loss = fn(self.batch)
-            self.loss.backward()
+            loss = fn(self.batch)
+            loss.backward()
+            # Keep only the VALUE (static graph memory).  Holding the tensor with its grad_fn would keep this capture's
+            # autograd graph -- and the parameters' AccumulateGrad nodes, which remember THIS capture stream -- alive; a later
+            # capture would then reuse those nodes, and with a gradient sink (no gradient ever flows into them, so their
+            # stream never joins the new capture) the engine's end-of-backward sync with that foreign stream is rejected
+            # as a dependency on uncaptured work.
+            self.loss = loss.detach()
+            del loss
             if self.flat is not None:
                 self.flat.all_reduce()  # parameters outside the fused layers (the layers' slices went per layer)
         clear_graph_cache()

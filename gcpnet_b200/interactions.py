@@ -355,10 +355,11 @@ class _LayerFn(torch.autograd.Function):
         prenorm = f32(plan.prenorm_floats) if spec.pre_norm else None
         pre = mod._prepacked
         mod._prepacked = None
+        if pre is not None:
+            torch.cuda.current_stream().wait_event(pre[2])  # packed on a side stream at the start of the step (always joined)
         if pre is not None and pre[0] == (N, E, training, gv.autoregressive, tuple((p.data_ptr(), p._version) for p in params)) \
                 and pre[1].device == dev:
             packed, ready = pre[1], 1
-            torch.cuda.current_stream().wait_event(pre[2])  # packed on the side stream at the start of the step
         else:
             packed, ready = f32(plan.packed_floats), 0
         io = _cabi.ForwardIO(_ptr(h), _ptr(chi), _ptr(e), _ptr(xi), _ptr(frames), _ptr(pos), _ptr(out_h), _ptr(out_chi),
@@ -701,7 +702,8 @@ class GCPInteractions(nn.Module):
         self._struct_cache[key] = layer
         return layer
 
-    def prepack(self, num_nodes: int, num_edges: int, stream: Optional[torch.cuda.Stream] = None) -> None:
+    def prepack(self, num_nodes: int, num_edges: int, stream: Optional[torch.cuda.Stream] = None,
+                autoregressive: bool = False) -> None:
         """Pack this layer's weights for a (num_nodes, num_edges) batch ahead of its forward call, on `stream` (forked from
         the current stream).  A step can call this for every layer first: the packing of layers 1..L-1 then overlaps with
         layer 0's kernels instead of sitting on each layer's critical path.  Consumed by the next forward call; repeat after
@@ -711,7 +713,7 @@ class GCPInteractions(nn.Module):
         if not params[0].is_cuda:
             raise RuntimeError("gcpnet_b200: prepack needs the module on a CUDA device")
         training = bool(self.training and self.dropout_p > 0.0)
-        layer = self._layer_struct(params, training, False)
+        layer = self._layer_struct(params, training, bool(autoregressive))
         plan = _cabi.Plan()
         _lib.check(lib.gcpnet_layer_plan(C.byref(layer), int(num_nodes), int(num_edges), C.byref(plan)), "gcpnet_layer_plan")
         packed = torch.empty(max(int(plan.packed_floats), 1), dtype=torch.float32, device=params[0].device)
@@ -726,7 +728,7 @@ class GCPInteractions(nn.Module):
             ev.record(side)
         if side is not cur and not torch.cuda.is_current_stream_capturing():
             packed.record_stream(side)  # allocated on the caller's stream, written on `side`
-        self._prepacked = ((int(num_nodes), int(num_edges), training, False,
+        self._prepacked = ((int(num_nodes), int(num_edges), training, bool(autoregressive),
                             tuple((p.data_ptr(), p._version) for p in params)), packed, ev)
 
     # -- forward ----------------------------------------------------------------------------

@@ -136,7 +136,7 @@ def load_reference():
     mod("torch_cluster")
 
     if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+        sys.path.append(REFERENCE_ROOT)  # at the END: the reference has its own `tests` package, which must not shadow ours
     # `src.utils` drags in lightning/hydra/rich: replace with the one symbol the path needs.
     import importlib
 
