@@ -547,7 +547,11 @@ def run_ours(args, w):
             "roofline": roof_out, "cpu_baseline": cpu, "clocks": clocks, "loss": losses[-1],
         })
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: destroy_process_group() was observed to hang (B200 x2, r2) while the captured step
+        # graph still references the communicator's kernels; a benchmark process has nothing to clean up.
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 _RESULT_FD = None
@@ -572,6 +576,13 @@ def _emit(line: dict):
         os.write(_RESULT_FD, data)
 
 
+def _watchdog(seconds):
+    """A multi-rank run that wedges in a collective must end by itself (the driver's clock is running)."""
+    t = threading.Timer(seconds, lambda: (sys.stderr.write("[bench] watchdog: run exceeded its time limit\n"), os._exit(3)))
+    t.daemon = True
+    t.start()
+
+
 def main():
     _protect_stdout()
     ap = argparse.ArgumentParser()
@@ -593,6 +604,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, w)
     else:
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            _watchdog(float(os.environ.get("GCPNET_BENCH_TIMEOUT", "600")))
         run_ours(args, w)
 
 

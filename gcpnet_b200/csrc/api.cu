@@ -481,6 +481,7 @@ static const char* check_variant(const gcpnet_layer& l, const gcpnet_graph& g, c
   if (ar && (!h_gather || !chi_gather)) return "autoregressive layers need the [2N] gather table";
   if (ar && l.pre_norm) return "pre_norm with an autoregressive gather table is not covered";
   if (l.pre_norm && !prenorm) return "pre_norm layers need the prenorm workspace";
+  if (l.enable_e3 && g.node_mask != nullptr) return "enable_e3_equivariance with a node mask is not covered";
   return nullptr;
 }
 
@@ -596,7 +597,7 @@ int gcpnet_layer_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, c
   }
   if (run_edge_forward(l, *graph, lp, f, st)) return 1;
   NodeParams p = make_node_params(l, *graph, lp.ops, lp.nf, false, f.packed);
-  p.h = f.h; p.chi = f.chi; p.msg = f.msg; p.pos = f.pos;
+  p.h = f.h; p.chi = f.chi; p.msg = f.msg; p.pos = f.pos; p.frames = f.frames;
   p.out_h = f.out_h; p.out_chi = f.out_chi; p.out_pos = f.out_pos; p.saved = f.saved_node;
   return launch_node_fwd(p, lp.nf, st);
 }
@@ -708,6 +709,7 @@ static int layer_backward_body(const gcpnet_layer* layer, const gcpnet_graph* gr
   np.dbg = g_tc_dbg.load(std::memory_order_relaxed);
   np.saved = const_cast<float*>(io->saved_node);
   np.h = io->h; np.chi = io->chi;  // node mask: masked-out nodes fed the layer input to the position GCP
+  np.frames = io->frames;
   np.g_out_h = io->g_out_h; np.g_out_chi = io->g_out_chi; np.g_out_pos = io->g_out_pos;
   np.g_x_h = io->g_h; np.g_x_chi = io->g_chi; np.g_agg = io->ws_agg;
   np.partial = io->ws_node_partial;

@@ -231,6 +231,15 @@ GCP_HDN void wpipe_start(WPipe& w) {
   w.head = 0;
 }
 
+// Node entities with enable_e3_equivariance: scalarize takes |.| of the x_cross projections PER EDGE before averaging over
+// the node's outgoing edges (comp/__init__.py:305-323), which the mean frame cannot express -> those three frame scalars
+// walk the node's outgoing edges (source CSR) instead.
+struct NodeE3 {
+  const int *src_ptr, *src_pos, *perm;
+  const float* frames;   // [E][9], caller's edge order
+  int row0, nrows;       // node range of the tile
+};
+
 // Shared-memory views used by one GCP2 evaluation on a tile.
 struct TileBufs {
   float* Z;   int ldz;   // [TE][ldz]  cols [0,si)=scalars in, [si,si+hd)=norms, [si+hd,si+hd+9)=frame scalars; pad cols zero
@@ -240,6 +249,7 @@ struct TileBufs {
   float* T;   int ldt;   // [TE][ldt]  pre-activation scalar_out
   float* SG;  int ldsg;  // [TE][ldsg] sigmoid gate per output vector channel
   float* WSM;            // persistent copy of the current GCP's small weights (backward): WdT | WU
+  const NodeE3* e3n = nullptr;  // node entities with e3 frames (see NodeE3); nullptr: F holds everything
 };
 constexpr int LDF = 9;
 
@@ -620,7 +630,22 @@ GCP_HD void gcp2_norm_scalarize(const GcpOp& op, const TileBufs& b, int e3, int 
       val = f[0] * hp[hdp + cc];
       val = fmaf(f[1], hp[cols + hdp + cc], val);
       val = fmaf(f[2], hp[2 * cols + hdp + cc], val);
-      if (e3 && a == 1) val = fabsf(val);  // comp:305-309
+      if (e3 && a == 1) {
+        if (b.e3n == nullptr) val = fabsf(val);  // comp:305-309 (edge entities: one frame per row)
+        else {  // node entities: mean over the outgoing edges of |x_cross . D|
+          const NodeE3& n3 = *b.e3n;
+          val = 0.f;
+          if (e < n3.nrows) {
+            const int i = n3.row0 + e, q0 = n3.src_ptr[i], q1 = n3.src_ptr[i + 1];
+            const float d0 = hp[hdp + cc], d1 = hp[cols + hdp + cc], d2 = hp[2 * cols + hdp + cc];
+            for (int q = q0; q < q1; ++q) {
+              const float* fe = n3.frames + (size_t)n3.perm[n3.src_pos[q]] * 9 + 3;
+              val += fabsf(fmaf(GCP_LDG(fe + 2), d2, fmaf(GCP_LDG(fe + 1), d1, GCP_LDG(fe) * d0)));
+            }
+            if (q1 > q0) val /= (float)(q1 - q0);
+          }
+        }
+      }
     }
     b.Z[e * b.ldz + op.si + j] = val;
   }
@@ -943,6 +968,22 @@ GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g,
       const int cc = kk - hdp;
       for (int a = 0; a < 3; ++a) {
         float gq = gnq[op.hd + 3 * cc + a];
+        if (e3 && a == 1 && b.e3n != nullptr) {
+          // node entities: d/dD[x] of mean_edges |F1 . D| = mean_edges sign(F1 . D) F1[x]
+          const NodeE3& n3 = *b.e3n;
+          if (e < n3.nrows) {
+            const int i = n3.row0 + e, q0 = n3.src_ptr[i], q1 = n3.src_ptr[i + 1];
+            const float d0 = hp[hdp + cc], d1 = hp[cols + hdp + cc], d2 = hp[2 * cols + hdp + cc];
+            float sx = 0.f;
+            for (int q = q0; q < q1; ++q) {
+              const float* fe = n3.frames + (size_t)n3.perm[n3.src_pos[q]] * 9 + 3;
+              const float pr = fmaf(GCP_LDG(fe + 2), d2, fmaf(GCP_LDG(fe + 1), d1, GCP_LDG(fe) * d0));
+              sx += pr > 0.f ? GCP_LDG(fe + x) : (pr < 0.f ? -GCP_LDG(fe + x) : 0.f);
+            }
+            if (q1 > q0) acc = fmaf(sx / (float)(q1 - q0), gq, acc);
+          }
+          continue;
+        }
         if (e3 && a == 1) {
           const float* f = b.F + e * LDF + 3;
           float q = f[0] * hp[hdp + cc];

@@ -389,6 +389,7 @@ inline NodeParams make_node_params(const gcpnet_layer& l, const gcpnet_graph& g,
   p.seed = l.seed; p.rng_ctr = (const long long*)l.rng_counter;
   p.fbar = g.fbar; p.dst_ptr = g.dst_ptr;
   p.fbar_pos = g.fbar_pos; p.mask = g.node_mask; p.pre_norm = l.pre_norm;
+  p.e3 = l.enable_e3; p.src_ptr = g.src_ptr; p.src_pos = g.src_pos; p.perm = g.perm;  // p.frames: set by the caller (io)
   p.ln0_w = l.ln0_w; p.ln0_b = l.ln0_b; p.ln1_w = l.ln1_w; p.ln1_b = l.ln1_b;
   p.blob = blob;
   p.ff0 = ops.ff0; p.ff1 = ops.ff1; p.pu = ops.pu;

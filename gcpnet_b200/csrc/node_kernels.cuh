@@ -40,6 +40,9 @@ struct NodeParams {
   const float* fbar_pos;        // node mask: mean frames of the position-update GCP (nullptr: fbar)
   const unsigned char* mask;    // node mask (nullptr: every node takes part): masked-out rows keep the layer input
   int pre_norm;                 // gcp_norm.1 after the first residual, no normalisation at the end (gcpnet.py:1223-1224,1245)
+  int e3;                       // enable_e3_equivariance: |x_cross projections| per outgoing edge (NodeE3)
+  const int *src_ptr, *src_pos, *perm;
+  const float* frames;
   const int* dst_ptr;
   const float *ln0_w, *ln0_b, *ln1_w, *ln1_b;
   const float* blob;
@@ -341,6 +344,7 @@ GCP_HDN void node_fwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
   constexpr int PARTS = NT / TE;
   const int row0 = tile * TE;
   const int nrows = (p.N - row0) < TE ? (p.N - row0) : TE;
+  const NodeE3 n3{p.src_ptr, p.src_pos, p.perm, p.frames, row0, nrows};
   const int s = p.s, v = p.v, v3 = 3 * p.v, W = s + v3, hs = p.hs, hv = p.hv, hv3 = 3 * p.hv;
   float* XS = sm + L.XS; float* XV = sm + L.XV; float* RED = sm + L.RED;
   const float keep_scale = 1.f / (1.f - p.p_drop);
@@ -381,8 +385,9 @@ GCP_HDN void node_fwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
   tile_layernorm_fwd<TE, NT>(XS, L.ldxs, XV, L.ldxv, s, v, lnA_w, lnA_b, p.ln_eps, p.vn_eps, RED);
   // FF0: (s, v) -> (hs, hv)
   {
-    const TileBufs b = node_bufs(p, sm, 0);
-    const float* gch = gcp2_fwd_tile_call<TE, NT, SLF>(p.ff0, b, wp, 0, p.slope, false);
+    TileBufs b = node_bufs(p, sm, 0);
+    if (p.e3) b.e3n = &n3;
+    const float* gch = gcp2_fwd_tile_call<TE, NT, SLF>(p.ff0, b, wp, p.e3, p.slope, false);
     const float* wu = gch + p.ff0.w.o_wu;
     float* ZB = sm + L.ZB; float* VB = sm + L.VB;
     GCP_PHASE_BEGIN(NT)
@@ -415,8 +420,9 @@ GCP_HDN void node_fwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
   }
   // FF1: (hs, hv) -> (s, v), then x2 = x1n + Dropout1(f)
   {
-    const TileBufs b = node_bufs(p, sm, 1);
-    const float* gch = gcp2_fwd_tile_call<TE, NT, SLF>(p.ff1, b, wp, 0, p.slope, true);
+    TileBufs b = node_bufs(p, sm, 1);
+    if (p.e3) b.e3n = &n3;
+    const float* gch = gcp2_fwd_tile_call<TE, NT, SLF>(p.ff1, b, wp, p.e3, p.slope, true);
     const float* wu = gch + p.ff1.w.o_wu;
     GCP_PHASE_BEGIN(NT)
     const int lane = tid & 31;
@@ -481,8 +487,9 @@ GCP_HDN void node_fwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
   tile_store_rows<TE, NT>(p.out_chi, row0, v3, XV, L.ldxv, nrows, tid);
   GCP_PHASE_END
   if (p.has_pos) {
-    const TileBufs b = node_bufs(p, sm, 2);
-    const float* gch = gcp2_fwd_tile_call<TE, NT, SLF>(p.pu, b, wp, 0, p.slope, false);
+    TileBufs b = node_bufs(p, sm, 2);
+    if (p.e3) b.e3n = &n3;
+    const float* gch = gcp2_fwd_tile_call<TE, NT, SLF>(p.pu, b, wp, p.e3, p.slope, false);
     const float* wu = gch + p.pu.w.o_wu;
     GCP_PHASE_BEGIN(NT)
     if (p.saved != nullptr) {
@@ -516,6 +523,7 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
   float* GXS = sm + L.GXS; float* GXV = sm + L.GXV; float* RED = sm + L.RED;
   const int ldgxs = L.ldgxs, ldgxv = L.ldgxv;
   auto rr = [=](int e) -> long long { return e < nrows ? row0 + e : -1; };
+  const NodeE3 n3{p.src_ptr, p.src_pos, p.perm, p.frames, row0, nrows};
   BwdBufs g;
   g.GU = sm + L.GU; g.ldgu = L.ldgu; g.GG = sm + L.GG; g.ldgg = L.ldgg; g.GNQ = sm + L.GNQ; g.ldnq = L.ldnq;
   g.GHD = sm + L.GHD; g.ldghd = L.ldghd;
@@ -560,7 +568,8 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
       }
       GCP_PHASE_END
     }
-    const TileBufs b = node_bufs(p, sm, 2);
+    TileBufs b = node_bufs(p, sm, 2);
+    if (p.e3) b.e3n = &n3;
     g.GS = sm + L.GS1; g.ldgs = L.ldgs1; g.GV = sm + L.GV1; g.ldgv = L.ldgv1;
     GCP_PHASE_BEGIN(NT)
     tile_load_rows<TE, NT>(b.T, b.ldt, p.saved + p.sv.TP, s, rr, tid);
@@ -580,7 +589,7 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
     GCP_PHASE_END
     set_spill(2);
     gcp2_bwd_tile_call<TE, NT, SLF, SLD>(
-        p.pu, b, g, wp, 0, p.slope, prow, accumulate, false, EmitTile{GXS, ldgxs, true}, EmitTile{GXV, ldgxv, true});
+        p.pu, b, g, wp, p.e3, p.slope, prow, accumulate, false, EmitTile{GXS, ldgxs, true}, EmitTile{GXV, ldgxv, true});
   }
   GCP_NSTAMP(2);
   if (p.mask != nullptr || pos_frames) {
@@ -609,8 +618,9 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
                                prow + p.o_ln1w, prow + p.o_ln1b, accumulate);
   GCP_NSTAMP(3);
   // ---- x2 = x1n + Dropout1(f): cotangent of f, reload x1 (raw copy + copy that becomes x1n), FF inputs
-  const TileBufs b1 = node_bufs(p, sm, 1);
-  const TileBufs b0 = node_bufs(p, sm, 0);
+  TileBufs b1 = node_bufs(p, sm, 1);
+  TileBufs b0 = node_bufs(p, sm, 0);
+  if (p.e3) { b1.e3n = &n3; b0.e3n = &n3; }
   float* GS1 = sm + L.GS1; float* GV1 = sm + L.GV1; float* GS0 = sm + L.GS0; float* GV0 = sm + L.GV0;
   GCP_PHASE_BEGIN(NT)
   const int lane = tid & 31;
@@ -648,7 +658,7 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
     const int ldgs0 = L.ldgs0, ldgv0 = L.ldgv0;
     set_spill(1);
     gcp2_bwd_tile_call<TE, NT, SLF, SLD>(
-        p.ff1, b1, g, wp, 0, p.slope, prow, accumulate, false, EmitTile{GS0, ldgs0, false}, EmitTile{GV0, ldgv0, false});
+        p.ff1, b1, g, wp, p.e3, p.slope, prow, accumulate, false, EmitTile{GS0, ldgs0, false}, EmitTile{GV0, ldgv0, false});
   }
   GCP_NSTAMP(6);
   // ---- FF0 backward: cotangents (GS0, GV0) -> accumulated into the cotangent of x1n
@@ -656,7 +666,7 @@ GCP_HDN void node_bwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
     g.GS = GS0; g.ldgs = L.ldgs0; g.GV = GV0; g.ldgv = L.ldgv0;
     set_spill(0);
     gcp2_bwd_tile_call<TE, NT, SLF, SLD>(
-        p.ff0, b0, g, wp, 0, p.slope, prow, accumulate, false, EmitTile{GXS, ldgxs, true}, EmitTile{GXV, ldgxv, true});
+        p.ff0, b0, g, wp, p.e3, p.slope, prow, accumulate, false, EmitTile{GXS, ldgxs, true}, EmitTile{GXV, ldgxv, true});
   }
   GCP_NSTAMP(7);
   // ---- backward of the normalisation after the first residual (input x1, kept raw in X2S/X2V)

@@ -630,8 +630,6 @@ class GCPInteractions(nn.Module):
         _check_gcp_flags(cfg, "GCPInteractions")
         if int(_get(layer_cfg, "num_feedforward_layers", 2)) != 2:
             unsupported("num_feedforward_layers != 2")
-        if bool(_get(cfg, "enable_e3_equivariance", False)):
-            unsupported("cfg.enable_e3_equivariance=True")
         if self.updating_node_positions and not self.ablate_x_force_update:
             unsupported("ablate_x_force_update=False (force-based position update)")
         if self.autoregressive and self.pre_norm:
@@ -651,7 +649,8 @@ class GCPInteractions(nn.Module):
             scalar_nonlinearity=nl[0], vector_nonlinearity=nl[1],
             nonlinearity_slope=float(_get(layer_cfg, "nonlinearity_slope", 1e-2)),
             use_residual_message_gcp=bool(_get(mp_cfg, "use_residual_message_gcp", True)),
-            enable_e3_equivariance=False, reduce_function="add" if self.autoregressive else "mean",
+            enable_e3_equivariance=bool(_get(cfg, "enable_e3_equivariance", False)),
+            reduce_function="add" if self.autoregressive else "mean",
             updating_node_positions=self.updating_node_positions, node_positions_weight=self.node_positions_weight,
             pre_norm=self.pre_norm)
         spec = self.spec
@@ -738,6 +737,8 @@ class GCPInteractions(nn.Module):
         s, v = self.node_dims
         se, ve = self.edge_dims
         ar_call = node_rep_regressive is not None
+        if node_mask is not None and self.spec.e3:
+            raise NotImplementedError("gcpnet_b200.GCPInteractions: enable_e3_equivariance with a node_mask is not covered")
         if ar_call and self.pre_norm:
             raise NotImplementedError("gcpnet_b200.GCPInteractions: node_rep_regressive with pre_norm=True is not covered")
         if ar_call and not self.autoregressive:

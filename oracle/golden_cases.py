@@ -66,6 +66,11 @@ CASES: Dict[str, dict] = {
     "tiny_pre_norm": dict(cfg=dict(node_dims=(16, 4), edge_dims=(8, 2), num_message_layers=2, bottleneck=2,
                                    default_bottleneck=2, pre_norm=True, updating_node_positions=True),
                           graph=("knn", 2, 10, 4), seed=23),
+    # enable_e3_equivariance (comp/__init__.py:305-309): |x_cross projections| per edge, also inside the node-side means
+    "tiny_e3": dict(cfg=dict(node_dims=(16, 4), edge_dims=(8, 2), num_message_layers=2, bottleneck=2, default_bottleneck=2,
+                             enable_e3_equivariance=True, updating_node_positions=True), graph=("random", 18, 80), seed=25),
+    "lba_e3_knn": dict(cfg=dict(node_dims=(100, 16), edge_dims=(32, 4), enable_e3_equivariance=True, scalar_nonlinearity="silu"),
+                       graph=("knn", 2, 24, 6), seed=26),
     "tiny_pre_norm_masked": dict(cfg=dict(node_dims=(16, 4), edge_dims=(8, 2), num_message_layers=2, bottleneck=2,
                                           default_bottleneck=2, pre_norm=True), graph=("random", 15, 60), seed=24,
                                  mask_frac=0.25),

@@ -159,7 +159,7 @@ int emul_layer_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, con
     return 0;
   }
   NodeParams p = make_node_params(l, g, lp.ops, lp.nf, false, io->packed);
-  p.h = io->h; p.chi = io->chi; p.msg = io->msg; p.pos = io->pos;
+  p.h = io->h; p.chi = io->chi; p.msg = io->msg; p.pos = io->pos; p.frames = io->frames;
   p.out_h = io->out_h; p.out_chi = io->out_chi; p.out_pos = io->out_pos; p.saved = io->saved_node;
   int grid = lp.nf.grid; if (grid > 2) grid = 2;
   if (lp.nf.SLF == 1) run_node_fwd<1>(p, grid); else if (lp.nf.SLF == 2) run_node_fwd<2>(p, grid);
@@ -178,7 +178,7 @@ int emul_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, co
   const int W = l.s + 3 * l.v;
   NodeParams np = make_node_params(l, g, lp.ops, lp.nb, true, io->packed);
   np.saved = const_cast<float*>(io->saved_node);
-  np.h = io->h; np.chi = io->chi;
+  np.h = io->h; np.chi = io->chi; np.frames = io->frames;
   np.g_out_h = io->g_out_h; np.g_out_chi = io->g_out_chi; np.g_out_pos = io->g_out_pos;
   np.g_x_h = io->g_h; np.g_x_chi = io->g_chi; np.g_agg = io->ws_agg; np.partial = io->ws_node_partial;
   const int ntn = (int)((g.num_nodes + lp.nb.TE - 1) / lp.nb.TE);

@@ -76,7 +76,7 @@ def test_unsupported_configurations_raise():
     import gcpnet_b200
     cfg = O.OracleConfig()
     mcfg, lcfg = module_cfgs(cfg)
-    for key in ("frame_gate", "ablate_frame_updates", "enable_e3_equivariance", "ablate_scalars"):
+    for key in ("frame_gate", "ablate_frame_updates", "ablate_scalars"):
         bad = type(mcfg)(mcfg)
         bad[key] = True
         with pytest.raises(NotImplementedError):
