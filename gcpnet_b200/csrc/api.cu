@@ -63,10 +63,17 @@ __global__ void __launch_bounds__(NT, 1) edge_bwd_kernel(const __grid_constant__
   const int mine = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   if (mine == 0) return;
   WPipe wp = edge_pipe(p, smem, mine);
+#if GCP_STAMPS
+  if (p.dbg != nullptr && blockIdx.x == 0) wp.dbg = p.dbg + 512;
+#endif
   wpipe_start<NT>(wp);
   float* prow = p.partial + (size_t)blockIdx.x * p.partial_stride;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     edge_bwd_tile<TE, NT, SLF, SLD>(p, smem, tile, wp, prow, tile != (int)blockIdx.x);
+#if GCP_STAMPS
+    wp.dbg = nullptr;  // first tile only
+#endif
+  }
 }
 
 template <int TE, int NT, int SLF>
@@ -645,6 +652,7 @@ static int run_ffma_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, 
   ep.grow = io.ws_edge; ep.gcol = io.ws_edge + (size_t)g.num_edges * W;
   ep.ge = io.g_e; ep.gxi = io.g_xi;
   ep.partial = io.ws_edge_partial;
+  ep.dbg = g_tc_dbg.load(std::memory_order_relaxed);
   *edge_grid = lp.eb.grid;
   if (launch_edge_bwd(ep, lp.eb, st)) return 1;
   GcpTimedScope timed(T_COT_REDUCE, st);

@@ -42,6 +42,7 @@ struct EdgeParams {
   EdgeSmem sm;
   GcpOp ops[MAX_MSG_LAYERS];
   WSeq seq;                                // chunk order of this kernel (forward or backward)
+  long long* dbg;                          // development aid (GCP_STAMPS builds): phase stamps of CTA 0's first tile
 };
 
 GCP_HD TileBufs edge_bufs(const EdgeParams& p, float* sm, int k) {

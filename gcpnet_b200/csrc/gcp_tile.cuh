@@ -815,7 +815,7 @@ GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g,
   const int K = gcp_k(op);
   float* wdt_sm = b.WSM;                    // [vi][cols]
   float* wu_sm = b.WSM + op.vi * cols;      // [vo][hdp]
-  constexpr int IW = (NT <= 256) ? 8 : 4;
+  constexpr int IW = 8;  // 4 x 8 blocks: 32 FMAs per 3 shared loads (4 x 4 blocks were shared-memory bound: r2 stage stamps, 23 k -> cycles per GCP)
   (void)hdp;
   // development aid: stamps 0..8 = phase boundaries, 9..14 = inside the first scalar_out chunk
 #if GCP_DEVICE_CODE && GCP_STAMPS
