@@ -183,9 +183,11 @@ def gcp2_hidden_dim(vi: int, vo: int, bottleneck: int) -> int:
 
 
 def gcp2_shapes(si: int, vi: int, so: int, vo: int, hd: int) -> Dict[str, Tuple[int, ...]]:
-    return {"vector_down.weight": (hd, vi), "scalar_out.weight": (so, si + hd + 9), "scalar_out.bias": (so,),
-            "vector_down_frames.weight": (3, vi), "vector_up.weight": (vo, hd),
-            "vector_out_scale.weight": (vo, so), "vector_out_scale.bias": (vo,)}
+    shapes = {"vector_down.weight": (hd, vi), "scalar_out.weight": (so, si + hd + 9), "scalar_out.bias": (so,),
+              "vector_down_frames.weight": (3, vi)}
+    if vo:  # gcpnet.py:310-322
+        shapes.update({"vector_up.weight": (vo, hd), "vector_out_scale.weight": (vo, so), "vector_out_scale.bias": (vo,)})
+    return shapes
 
 
 class LayerSpec:

@@ -482,8 +482,11 @@ static int run_tc_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, co
 
 // consistency of the optional variants (autoregressive gather views, pre_norm workspace)
 static const char* check_variant(const gcpnet_layer& l, const gcpnet_graph& g, const float* h_gather, const float* chi_gather, const float* prenorm) {
-  const bool ar = g.gsrc != nullptr;
-  if (ar != (l.autoregressive != 0)) return "autoregressive layers need the views of gcpnet_graph_build_autoregressive (and only they)";
+  const bool ar = g.num_gather_rows > 0;
+  if (ar != (l.autoregressive == 1)) return "autoregressive layers need the views of gcpnet_graph_build_autoregressive (and only they)";
+  // autoregressive == 2: aggregate_with_row (gcpnet.py:946): the graph was built on the flipped edge_index and the gather
+  // ids swap the two ends back (gsrc = dst, gdst = src)
+  if ((g.gsrc != nullptr && !ar) != (l.autoregressive == 2)) return "gather ids without gather rows need aggregate_with_row (autoregressive = 2)";
   if (ar && (!g.gdst || !g.vdst_ptr || !g.vsrc_ptr || !g.vsrc_pos || g.num_gather_rows != 2 * g.num_nodes)) return "incomplete autoregressive graph views";
   if (ar && (!h_gather || !chi_gather)) return "autoregressive layers need the [2N] gather table";
   if (ar && l.pre_norm) return "pre_norm with an autoregressive gather table is not covered";
@@ -612,6 +615,7 @@ int gcpnet_layer_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, c
 int gcpnet_message_passing_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, const gcpnet_plan* plan,
                                    const gcpnet_forward_io* io, float* aggregate, void* stream) {
   if (!layer || !graph || !plan || !io || !aggregate) return fail("message_passing_forward: null argument");
+  if (const char* m = check_variant(*layer, *graph, io->h_gather, io->chi_gather, io->prenorm)) return fail(std::string("message_passing_forward: ") + m);
   cudaStream_t st = (cudaStream_t)stream;
   if (!io->packed) return fail("message_passing_forward: packed-weight workspace required");
   LayerPlan lp;
@@ -635,7 +639,7 @@ static int run_ffma_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, 
   *edge_grid = 0;
   const int W = l.s + 3 * l.v;
   if (g.num_edges <= 0) {
-    if (g.gsrc != nullptr) {  // no edges: the gather-table cotangent is the direct part on the even rows
+    if (g.num_gather_rows > 0) {  // no edges: the gather-table cotangent is the direct part on the even rows
       const long long tot = g.num_gather_rows * W;
       ar_cotangent_reduce_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(
           io.g_h_gather, io.g_chi_gather, io.g_h, io.g_chi, nullptr, nullptr, g.vdst_ptr, g.vsrc_ptr, g.vsrc_pos, (int)g.num_gather_rows, l.s, 3 * l.v);
@@ -656,7 +660,12 @@ static int run_ffma_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, 
   *edge_grid = lp.eb.grid;
   if (launch_edge_bwd(ep, lp.eb, st)) return 1;
   GcpTimedScope timed(T_COT_REDUCE, st);
-  if (g.gsrc != nullptr) {
+  if (g.num_gather_rows == 0 && g.gsrc != nullptr) {
+    // aggregate_with_row: the "row" features were gathered by DESTINATION of the flipped graph and vice versa
+    const long long tot = g.num_nodes * W;
+    node_cotangent_reduce_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(
+        io.g_h, io.g_chi, ep.gcol, ep.grow, g.dst_ptr, g.src_ptr, g.src_pos, (int)g.num_nodes, l.s, 3 * l.v);
+  } else if (g.gsrc != nullptr) {
     const long long tot = g.num_gather_rows * W;
     ar_cotangent_reduce_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(
         io.g_h_gather, io.g_chi_gather, io.g_h, io.g_chi, ep.grow, ep.gcol, g.vdst_ptr, g.vsrc_ptr, g.vsrc_pos, (int)g.num_gather_rows, l.s, 3 * l.v);
@@ -773,7 +782,7 @@ static Gcp2OpParams gcp2op_params(const Gcp2OpPlan& P, bool backward, int64_t M,
 }
 int gcpnet_gcp2_forward(const gcpnet_gcp2* op, int64_t M, const float* s_in, const float* v_in, const float* frames, int e3, float slope,
                         float* s_out, float* v_out, float* saved, float* packed, void* stream) {
-  if (!op || !s_in || !v_in || !frames || !s_out || !v_out || !packed) return fail("gcp2_forward: null argument");
+  if (!op || !s_in || !v_in || !frames || !s_out || (!v_out && op->vo > 0) || !packed) return fail("gcp2_forward: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const Gcp2OpPlan P = plan_gcp2_op(*op, M);
   if (!P.error.empty()) return fail("gcp2_forward: " + P.error);
@@ -791,7 +800,7 @@ int gcpnet_gcp2_forward(const gcpnet_gcp2* op, int64_t M, const float* s_in, con
 int gcpnet_gcp2_backward(const gcpnet_gcp2* op, int64_t M, const float* s_in, const float* v_in, const float* frames, int e3, float slope,
                          const float* saved, const float* packed, const float* g_s_out, const float* g_v_out, float* g_s_in,
                          float* g_v_in, float* g_params, float* ws_partial, void* stream) {
-  if (!op || !s_in || !v_in || !frames || !saved || !packed || !g_s_out || !g_v_out || !g_s_in || !g_v_in || !g_params || !ws_partial)
+  if (!op || !s_in || !v_in || !frames || !saved || !packed || !g_s_out || (!g_v_out && op->vo > 0) || !g_s_in || !g_v_in || !g_params || !ws_partial)
     return fail("gcp2_backward: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const Gcp2OpPlan P = plan_gcp2_op(*op, M);

@@ -106,9 +106,9 @@ GCP_HDN void gcp2op_bwd_tile(const Gcp2OpParams& p, float* sm, int tile, WPipe& 
   auto rr = [=](int e) -> long long { return e < nrows ? row0 + e : -1; };
   gcp2op_load_inputs<TE, NT>(p, b, row0, nrows, tid);
   tile_load_rows<TE, NT>(g.GS, g.ldgs, p.gs_out, op.so, rr, tid);
-  tile_load_rows<TE, NT>(g.GV, g.ldgv, p.gv_out, 3 * op.vo, rr, tid);
+  if (op.vo > 0) tile_load_rows<TE, NT>(g.GV, g.ldgv, p.gv_out, 3 * op.vo, rr, tid);
   tile_load_rows<TE, NT>(b.T, b.ldt, p.saved, op.so, rr, tid);
-  tile_load_rows<TE, NT>(b.SG, b.ldsg, p.saved + (size_t)p.M * op.so, op.vo, rr, tid);
+  if (op.vo > 0) tile_load_rows<TE, NT>(b.SG, b.ldsg, p.saved + (size_t)p.M * op.so, op.vo, rr, tid);
   GCP_PHASE_END
   float* gs_in = p.gs_in; float* gv_in = p.gv_in;
   const int si = op.si, vi3 = 3 * op.vi;

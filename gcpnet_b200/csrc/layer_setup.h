@@ -36,7 +36,7 @@ inline GcpOp to_op(const gcpnet_gcp2& d, int grad_base) {
 
 inline std::string check_gcp2(const gcpnet_gcp2& d, const char* name) {
   auto err = [&](const std::string& m) { return std::string(name) + ": " + m; };
-  if (d.si <= 0 || d.vi <= 0 || d.so <= 0 || d.vo <= 0) return err("dims must be positive");
+  if (d.si <= 0 || d.vi <= 0 || d.so <= 0 || d.vo < 0) return err("dims must be positive (vo may be 0: scalar-only output, gcpnet.py:443-446)");
   if (d.so % 4 != 0) return err("scalar output dims must be multiples of 4 in this build");
   if (d.hd <= 0 || d.hd > 16) return err("hidden vector dim must be in [1,16] (bottleneck too small for this build)");
   if (d.vector_residual && d.vi != d.vo) return err("vector_residual needs vi == vo");
@@ -52,7 +52,7 @@ inline std::string check_layer(const gcpnet_layer& l) {
     const gcpnet_gcp2& g = l.message[k];
     std::string e = check_gcp2(g, "message_fusion");
     if (!e.empty()) return e;
-    if (g.so != l.s || g.vo != l.v) return "message GCP output dims must equal node dims";
+    if (g.so != l.s || g.vo != l.v || g.vo <= 0) return "message GCP output dims must equal node dims";
     if (k == 0 && (g.si != 2 * l.s + l.se || g.vi != 2 * l.v + l.ve)) return "message_fusion.0 input dims mismatch";
     if (k > 0 && (g.si != l.s || g.vi != l.v)) return "message_fusion.k input dims mismatch";
   }
@@ -95,7 +95,7 @@ inline std::string plan_gcp_pack(GcpOp& op, int cap_floats, int* cursor) {
   W.ws_floats = round_up(W.NP * W.ldk + W.NP, 4);
   W.ws_stride = round_up(W.ws_floats, 32);
   W.ws_off = *cursor; *cursor += W.nWS * W.ws_stride;
-  W.G = take(W.o_wu + op.vo * W.hdp);
+  W.G = take(W.o_wu + op.vo * W.hdp > 32 ? W.o_wu + op.vo * W.hdp : 32);  // never an empty chunk (vo = 0: 32 zero floats)
   if (W.G.floats > cap_floats) return "vector_out_scale is too wide for a weight-ring slot of this build";
   return "";
 }
@@ -240,7 +240,7 @@ inline Gcp2OpPlan plan_gcp2_op(const gcpnet_gcp2& d, long long M) {
   if (!P.error.empty()) return P;
   P.n_params = gcp2_n_params(d);
   for (int i = 0; i < 7; ++i)
-    if (d.grad_off[i] < 0 || d.grad_off[i] >= P.n_params) { P.error = "gcp2: grad_off outside the module's flat gradient"; return P; }
+    if (d.grad_off[i] < 0 || d.grad_off[i] >= P.n_params + (d.vo == 0 ? 1 : 0)) { P.error = "gcp2: grad_off outside the module's flat gradient"; return P; }
   P.slf = (round_up(d.so, 16) / 16 + 3) / 4;
   if (P.slf > 2) { P.error = "gcp2: scalar output dim too wide for this build"; return P; }
   const int caps[3] = {EDGE_CAP_FLOATS, 6144, 4096};

@@ -244,8 +244,9 @@ class GCP2Params(nn.Module):
         self.vector_down = nn.Linear(vi, hd, bias=False)
         self.scalar_out = nn.Linear(hd + si + 9, so)
         self.vector_down_frames = nn.Linear(vi, 3, bias=False)
-        self.vector_up = nn.Linear(hd, vo, bias=False)
-        self.vector_out_scale = nn.Linear(so, vo)
+        if vo:  # gcpnet.py:310-322: no vector_up / vector_out_scale without vector outputs
+            self.vector_up = nn.Linear(hd, vo, bias=False)
+            self.vector_out_scale = nn.Linear(so, vo)
 
     def forward(self, *a, **k):  # pragma: no cover
         raise RuntimeError("GCP2Params only holds parameters; the fused layer kernels evaluate it")
@@ -467,6 +468,20 @@ def _check_gcp_flags(cfg, who: str) -> None:
             unsupported(f"cfg.{flag}=True")
 
 
+class _SwappedViews:
+    """Graph views of the flipped edge_index with gather ids that swap the two ends back (aggregate_with_row)."""
+
+    def __init__(self, gv: GraphViews):
+        self.base, self.N, self.E, self.autoregressive = gv, gv.N, gv.E, False
+        g = gv.struct
+        self.struct = _cabi.Graph(g.num_nodes, g.num_edges, g.perm, g.src, g.dst, g.dst_ptr, g.src_pos, g.src_ptr, g.fbar)
+        self.struct.gsrc, self.struct.gdst = g.dst, g.src
+
+
+def _swapped_gather(gv: GraphViews) -> "_SwappedViews":
+    return _SwappedViews(gv)
+
+
 class _MPFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod: "GCPMessagePassing", gv: GraphViews, h, chi, e, xi, frames, *params):
@@ -533,9 +548,10 @@ class GCPMessagePassing(nn.Module):
         node_dims = ScalarVector(int(input_dims[0]), int(input_dims[1]))
         if tuple(int(d) for d in output_dims) != tuple(node_dims):
             raise NotImplementedError("gcpnet_b200.GCPMessagePassing: output_dims != input_dims is not covered")
-        if use_scalar_message_attention or aggregate_with_row:
-            raise NotImplementedError("gcpnet_b200.GCPMessagePassing: use_scalar_message_attention / aggregate_with_row "
-                                      "(GCPInteractions2 only) are not covered")
+        if use_scalar_message_attention:
+            raise NotImplementedError("gcpnet_b200.GCPMessagePassing: use_scalar_message_attention (GCPInteractions2 only) "
+                                      "is not covered")
+        self.aggregate_with_row = bool(aggregate_with_row)
         if reduce_function not in ("mean", "add", "sum"):
             raise NotImplementedError(f"gcpnet_b200.GCPMessagePassing: reduce_function={reduce_function!r}")
         _check_gcp_flags(cfg, "GCPMessagePassing")
@@ -576,6 +592,8 @@ class GCPMessagePassing(nn.Module):
             return self._struct_cache[1]
         table = dict(zip(self.spec.names, ptrs))  # message_fusion.* come first in the flat layout
         layer = self.spec.make_layer(lambda n: table.get(n, 0))
+        if self.aggregate_with_row:
+            layer.autoregressive = 2
         self._struct_cache = (ptrs, layer)
         return layer
 
@@ -598,7 +616,13 @@ class GCPMessagePassing(nn.Module):
         if N == 0:
             return ScalarVector(h.clone(), chi.clone())
         edge_index, frames = edge_index.contiguous(), frames.contiguous()
-        gv = graph_views(edge_index, frames, N)
+        if self.aggregate_with_row:
+            # scatter over `row` (gcpnet.py:946): the views of the FLIPPED edge_index sort by row; the gather ids hand the
+            # message GCPs the original (row, col) ends (edge features and frames stay aligned with the caller's edge ids)
+            gv = graph_views(edge_index.flip(0).contiguous(), frames, N)
+            gv = _swapped_gather(gv)
+        else:
+            gv = graph_views(edge_index, frames, N)
         self._grad_mode = torch.is_grad_enabled()
         agg = _MPFn.apply(self, gv, h, chi, e, xi, frames, *self._params_in_order())
         return ScalarVector.recover(agg, v)

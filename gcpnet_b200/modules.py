@@ -34,7 +34,7 @@ class _Gcp2Fn(torch.autograd.Function):
         f32 = lambda n: torch.empty(max(int(n), 1), dtype=torch.float32, device=dev)
         so, vo = mod.dims[2], mod.dims[3]
         s_out = torch.empty((M, so), dtype=torch.float32, device=dev)
-        v_out = torch.empty((M, vo, 3), dtype=torch.float32, device=dev)
+        v_out = torch.empty((M, vo, 3), dtype=torch.float32, device=dev) if vo else None
         need_grad = mod._grad_mode and any(ctx.needs_input_grad)
         saved = f32(plan.saved_floats) if need_grad else None
         packed = f32(plan.packed_floats)
@@ -42,6 +42,9 @@ class _Gcp2Fn(torch.autograd.Function):
                                            _ptr(s_out), _ptr(v_out), _ptr(saved), _ptr(packed), _stream()), "gcpnet_gcp2_forward")
         ctx.mod, ctx.plan = mod, plan
         ctx.save_for_backward(s_in, v_in, frames9, saved, packed, *params)
+        if not vo:
+            ctx.mark_non_differentiable()
+            return s_out, None
         return s_out, v_out
 
     @staticmethod
@@ -55,7 +58,10 @@ class _Gcp2Fn(torch.autograd.Function):
         op = mod._op_struct(params)
         f32 = lambda n: torch.empty(max(int(n), 1), dtype=torch.float32, device=dev)
         g_s = torch.zeros((M, mod.dims[2]), dtype=torch.float32, device=dev) if g_s is None else g_s.contiguous()
-        g_v = torch.zeros((M, mod.dims[3], 3), dtype=torch.float32, device=dev) if g_v is None else g_v.contiguous()
+        if mod.dims[3]:
+            g_v = torch.zeros((M, mod.dims[3], 3), dtype=torch.float32, device=dev) if g_v is None else g_v.contiguous()
+        else:
+            g_v = None
         g_s_in, g_v_in = torch.empty_like(s_in), torch.empty_like(v_in)
         g_params, ws = f32(plan.n_params), f32(plan.partial_floats)
         _lib.check(lib.gcpnet_gcp2_backward(C.byref(op), M, _ptr(s_in), _ptr(v_in), _ptr(frames9), int(mod.e3), mod.slope,
@@ -87,8 +93,17 @@ class GCP2(GCP2Params):
         def unsupported(what):
             raise NotImplementedError(f"gcpnet_b200.GCP2: {what} is not covered by the sm_100a kernels (no eager fallback)")
 
-        if vi <= 0 or vo <= 0:
-            unsupported("a GCP2 without vector inputs or outputs")
+        self._scalar_only = vi <= 0
+        if vi <= 0:
+            # gcpnet.py:323-324,447-449: no vector inputs -> scalar_out is a plain Linear over the scalars and the vector
+            # output is zeros; a library GEMM (torch.nn.functional.linear), exactly the reference's own op
+            nn.Module.__init__(self)
+            self.dims = (si, 0, so, vo, 0)
+            self.scalar_out = nn.Linear(si, so)
+            nl = (None, None) if nonlinearities is None else nonlinearities
+            self.acts = (_cabi._norm(nl[0]), _cabi._norm(nl[1]))
+            self.slope = float(nonlinearity_slope)
+            return
         if scalar_gate or not vector_gate or frame_gate or sigma_frame_gate or vector_frame_residual:
             unsupported("scalar_gate / frame gates / vector_gate=False")
         if ablate_frame_updates or ablate_scalars or ablate_vectors or scalarization_vectorization_output_dim != 3:
@@ -137,6 +152,17 @@ class GCP2(GCP2Params):
         return op
 
     def forward(self, s_maybe_v, edge_index, frames, node_inputs: bool = False, node_mask=None):
+        if self._scalar_only:
+            s_in = s_maybe_v if torch.is_tensor(s_maybe_v) else s_maybe_v[0]
+            _check_cuda(s_in, "scalars")
+            t = torch.nn.functional.linear(s_in, self.scalar_out.weight, self.scalar_out.bias)
+            a = self.acts[0]
+            if a is not None:
+                t = {"relu": torch.relu, "silu": torch.nn.functional.silu, "sigmoid": torch.sigmoid, "selu": torch.selu,
+                     "leakyrelu": lambda x: torch.nn.functional.leaky_relu(x, self.slope)}[a](t)
+            if not self.dims[3]:
+                return t
+            return ScalarVector(t, t.new_zeros((t.shape[0], self.dims[3], 3)))
         s_in, v_in = s_maybe_v[0], s_maybe_v[1]
         si, vi = self.dims[0], self.dims[1]
         for t, name in ((s_in, "scalars"), (v_in, "vectors"), (edge_index, "edge_index"), (frames, "frames")):
@@ -158,9 +184,12 @@ class GCP2(GCP2Params):
                 raise TypeError("gcpnet_b200.GCP2: node_inputs=False needs one row per edge")
             F = frames if node_mask is None else graph_views(edge_index, frames, int(node_mask.shape[0]), node_mask=node_mask).frames
         if M == 0:
-            return ScalarVector(s_in.new_zeros((0, self.dims[2])), v_in.new_zeros((0, self.dims[3], 3)))
+            z = s_in.new_zeros((0, self.dims[2]))
+            return ScalarVector(z, v_in.new_zeros((0, self.dims[3], 3))) if self.dims[3] else z
         self._grad_mode = torch.is_grad_enabled()
         s_out, v_out = _Gcp2Fn.apply(self, s_in, v_in, F.reshape(M, 9), *self._params_in_order())
+        if not self.dims[3]:
+            return s_out  # no vector outputs: the scalar features alone (gcpnet.py:443-446)
         return ScalarVector(s_out, v_out)
 
 

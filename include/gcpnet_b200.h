@@ -74,7 +74,9 @@ typedef struct gcpnet_layer {
   int32_t n_edge_params, n_node_params;
   int32_t pre_norm;                /* layer_cfg.pre_norm (gcpnet.py:1188-1189,1223-1224,1245): gcp_norm.0 before the message
                                       passing, gcp_norm.1 after the first residual, none at the end */
-  int32_t autoregressive;          /* 1: the graph carries gather ids (gcpnet_graph_build_autoregressive); FFMA edge kernels */
+  int32_t autoregressive;          /* 1: the graph carries the gather views of gcpnet_graph_build_autoregressive; 2: aggregate_with_row
+                                      (gcpnet.py:946): graph built on the flipped edge_index, gsrc = dst / gdst = src swap the
+                                      ends back, num_gather_rows = 0.  Both run the FFMA edge kernels. */
 } gcpnet_layer;
 
 /* Destination- and source-sorted views of one graph batch, built by gcpnet_graph_build and shared

@@ -216,7 +216,7 @@ def gcp2(p: Dict[str, Tensor], prefix: str, s: Tensor, V: Tensor, edge_index: Te
 # --------------------------------------------------------------------------------------
 def message_passing(p: Dict[str, Tensor], prefix: str, cfg: OracleConfig, h: Tensor, chi: Tensor,
                     e: Tensor, xi: Tensor, edge_index: Tensor, frames: Tensor,
-                    reduce: Optional[str] = None, node_mask: Optional[Tensor] = None):
+                    reduce: Optional[str] = None, node_mask: Optional[Tensor] = None, aggregate_with_row: bool = False):
     row, col = edge_index[0], edge_index[1]
     L = cfg.num_message_layers
     a_s = activation(cfg.scalar_nonlinearity, cfg.nonlinearity_slope)
@@ -248,7 +248,7 @@ def message_passing(p: Dict[str, Tensor], prefix: str, cfg: OracleConfig, h: Ten
         for k in range(L):
             rs, rV = G(k, rs, rV)
     flat = torch.cat((rs, rV.reshape(rV.shape[0], 3 * rV.shape[1])), dim=-1)  # flatten (comp:61-63)
-    agg = segment_reduce(flat, col, h.shape[0], reduce or cfg.reduce_function)  # (:946)
+    agg = segment_reduce(flat, row if aggregate_with_row else col, h.shape[0], reduce or cfg.reduce_function)  # (:946)
     so = rs.shape[1]
     return agg[:, :so], agg[:, so:].reshape(agg.shape[0], (agg.shape[1] - so) // 3, 3)  # recover (comp:65-69)
 

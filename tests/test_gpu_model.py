@@ -54,6 +54,41 @@ def test_gcp2_alone_matches_oracle(dims, node_inputs, acts, bottleneck, vres, ma
         assert rel_err(t.grad.cpu().numpy(), p["m." + k].grad.numpy()) < TOL, k
 
 
+def test_gcp2_scalar_only_output_and_scalar_only_input():
+    """The invariant projection heads ((s, v) -> (s', 0): the GCP returns its scalars, gcpnet.py:443-446;
+    gcpnet_lba_module.py:176-184) and GCPs without vector inputs (LBA node embedding (9, 0) -> (s, v): a Linear, zero
+    vectors, gcpnet.py:323-324,447-449)."""
+    import gcpnet_b200
+    g = torch.Generator().manual_seed(420)
+    n, E = 90, 600
+    ei = torch.randint(0, n, (2, E), generator=g)
+    frames = O.localize(torch.randn(n, 3, generator=g), ei)
+    torch.manual_seed(421)
+    head = gcpnet_b200.GCP2((100, 16), (100, 0), nonlinearities=("relu", None), bottleneck=4).cuda()
+    assert set(head.state_dict()) == {"vector_down.weight", "scalar_out.weight", "scalar_out.bias", "vector_down_frames.weight"}
+    s_in, v_in = torch.randn(n, 100, generator=g), torch.randn(n, 16, 3, generator=g)
+    p = {k: v.clone().requires_grad_(True) for k, v in _gcp2_params(head).items()}
+    ls, lv = s_in.clone().requires_grad_(True), v_in.clone().requires_grad_(True)
+    want = O.gcp2(p, "m.", ls, lv, ei, frames, node_inputs=True, act_s=O.activation("relu"), act_v=O.activation(None),
+                  vector_residual=False, e3=False)
+    c = torch.randn(n, 100, generator=g)
+    (want * c).sum().backward()
+    ds, dv = s_in.cuda().requires_grad_(True), v_in.cuda().requires_grad_(True)
+    out = head((ds, dv), ei.cuda(), frames.cuda(), node_inputs=True)
+    assert torch.is_tensor(out) and out.shape == (n, 100)
+    (out * c.cuda()).sum().backward()
+    assert rel_err(out.detach().cpu().numpy(), want.detach().numpy()) < TOL
+    assert rel_err(ds.grad.cpu().numpy(), ls.grad.numpy()) < TOL and rel_err(dv.grad.cpu().numpy(), lv.grad.numpy()) < TOL
+    for k, t in head.named_parameters():
+        assert rel_err(t.grad.cpu().numpy(), p["m." + k].grad.numpy()) < TOL, k
+    emb = gcpnet_b200.GCP2((9, 0), (100, 16), nonlinearities=(None, None)).cuda()
+    assert set(emb.state_dict()) == {"scalar_out.weight", "scalar_out.bias"}
+    x = torch.randn(n, 9, generator=g).cuda()
+    so, vo = emb(x, ei.cuda(), frames.cuda(), node_inputs=True)
+    assert torch.allclose(so, torch.nn.functional.linear(x, emb.scalar_out.weight, emb.scalar_out.bias)) and vo.shape == (n, 16, 3)
+    assert float(vo.abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("dims", [(17, 1), (1, 3), (64, 16), (100, 0)])
 def test_layernorm_alone_matches_oracle(dims):
     """GCPLayerNorm (comp/__init__.py:138-167), including a one-element scalar LayerNorm and the scalar-only form."""

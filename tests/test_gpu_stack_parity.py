@@ -177,6 +177,37 @@ def test_message_passing_alone_forward_and_backward(dims, tc, reduce):
         assert rel_err(t.grad.cpu().numpy(), p["interaction." + k].grad.numpy()) < TOL, k
 
 
+@pytest.mark.parametrize("dims", [(64, 16), (100, 16)])
+def test_message_passing_aggregate_with_row(dims):
+    """aggregate_with_row=True (gcpnet.py:946: scatter over `row`): the message GCPs still see (row, col) ends."""
+    import gcpnet_b200
+    from tests.helpers import module_cfgs
+    cfg = O.OracleConfig(node_dims=dims, edge_dims=(32, 4), reduce_function="sum", scalar_nonlinearity="silu")
+    g = torch.Generator().manual_seed(335)
+    n, E = 140, 1000
+    ei = torch.randint(0, n - 3, (2, E), generator=g)
+    inputs = O.synthetic_layer_inputs(cfg, ei, n, seed=336)
+    params = {k: v for k, v in O.random_layer_params(cfg, seed=337).items() if k.startswith("interaction.")}
+    mcfg, lcfg = module_cfgs(cfg)
+    mp = gcpnet_b200.GCPMessagePassing(dims, dims, (32, 4), cfg=mcfg, mp_cfg=lcfg.mp_cfg, reduce_function="sum", aggregate_with_row=True)
+    mp.load_state_dict({k[len("interaction."):]: v for k, v in params.items()}, strict=True)
+    mp = mp.cuda()
+    cots = _cots(n, dims[0], dims[1], 338)
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    lv = {k: inputs[k].clone().requires_grad_(True) for k in ("h", "chi", "e", "xi")}
+    ws, wV = O.message_passing(p, "interaction.", cfg, lv["h"], lv["chi"], lv["e"], lv["xi"], ei, inputs["frames"], aggregate_with_row=True)
+    ((ws * cots[0]).sum() + (wV * cots[1]).sum()).backward()
+    dv = {k: inputs[k].cuda().requires_grad_(True) for k in ("h", "chi", "e", "xi")}
+    out = mp((dv["h"], dv["chi"]), (dv["e"], dv["xi"]), ei.cuda(), inputs["frames"].cuda())
+    ((out[0] * cots[0].cuda()).sum() + (out[1] * cots[1].cuda()).sum()).backward()
+    assert rel_err(out[0].detach().cpu().numpy(), ws.detach().numpy()) < TOL
+    assert rel_err(out[1].detach().cpu().numpy(), wV.detach().numpy()) < TOL
+    for k in ("h", "chi", "e", "xi"):
+        assert rel_err(dv[k].grad.cpu().numpy(), lv[k].grad.numpy()) < TOL, k
+    for k, t in mp.named_parameters():
+        assert rel_err(t.grad.cpu().numpy(), p["interaction." + k].grad.numpy()) < TOL, k
+
+
 @pytest.mark.parametrize("act", ["leakyrelu", "selu", "sigmoid", "silu"])
 @pytest.mark.parametrize("dims", [(64, 16), (100, 16)])
 def test_other_scalar_nonlinearities(act, dims):
