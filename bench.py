@@ -387,6 +387,9 @@ def run_ours(args, w):
                                               model=layers, process_group=None)
             graphed.flat.group, graphed.flat.overlap = group, False
             allreduce_mode = "one eager NCCL all-reduce (mean) of the flat gradient buffer after the graph replay"
+        if world > 1 and graphed.flat.overlap:
+            allreduce_mode = ("per-layer one-shot all-reduce (mean) over NVLink peer memory (csrc/p2p.cu)" if graphed.flat.transport == "p2p"
+                              else "per-layer NCCL all-reduce (mean)") + ", captured in the step graph on the side stream"
         launches_per_step = (lib.gcpnet_launch_count() - l0) // (max(args.warmup, 3) + 1)
     eager_flat = None
 

@@ -91,7 +91,8 @@ EXPORTS = (
     "gcpnet_localize", "gcpnet_localize_masked", "gcpnet_graph_ar_workspace_bytes", "gcpnet_graph_build_autoregressive",
     "gcpnet_graph_mask", "gcpnet_centralize", "gcpnet_decentralize", "gcpnet_layer_plan", "gcpnet_layer_pack", "gcpnet_layer_forward", "gcpnet_layer_backward",
     "gcpnet_message_passing_forward", "gcpnet_message_passing_backward", "gcpnet_gcp2_plan_query", "gcpnet_gcp2_forward",
-    "gcpnet_gcp2_backward", "gcpnet_layernorm_forward", "gcpnet_layernorm_backward",
+    "gcpnet_gcp2_backward", "gcpnet_layernorm_forward", "gcpnet_layernorm_backward", "gcpnet_p2p_create", "gcpnet_p2p_connect",
+    "gcpnet_p2p_allreduce_mean", "gcpnet_p2p_destroy",
 )
 
 
@@ -159,6 +160,14 @@ def declare(lib: C.CDLL) -> None:
     lib.gcpnet_layernorm_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 5
     lib.gcpnet_layernorm_backward.restype = C.c_int
     lib.gcpnet_layernorm_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 9
+    lib.gcpnet_p2p_create.restype = C.c_int
+    lib.gcpnet_p2p_create.argtypes = [C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
+    lib.gcpnet_p2p_connect.restype = C.c_int
+    lib.gcpnet_p2p_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gcpnet_p2p_allreduce_mean.restype = C.c_int
+    lib.gcpnet_p2p_allreduce_mean.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+    lib.gcpnet_p2p_destroy.restype = C.c_int
+    lib.gcpnet_p2p_destroy.argtypes = [C.c_void_p]
     lib.gcpnet_message_passing_backward.restype = C.c_int
     lib.gcpnet_message_passing_backward.argtypes = [C.POINTER(Layer), C.POINTER(Graph), C.POINTER(Plan),
                                                     C.POINTER(BackwardIO), C.c_void_p, C.c_void_p]

@@ -259,6 +259,17 @@ int gcpnet_layernorm_backward(const float* h, const float* chi, int64_t num_rows
                               const float* g_out_h, const float* g_out_chi, float* g_h, float* g_chi, float* g_w, float* g_b,
                               float* workspace, void* stream);
 
+/* Mean of the flat parameter gradient over the ranks of ONE node, over NVLink peer memory (csrc/p2p.cu): the path's only
+ * exchange step (Lightning DDP / NCCL in the reference).  create: allocates this rank's IPC buffer
+ * (num_floats gradient floats + flags), returns its device pointer (the layers' gradient sink) and its 64-byte CUDA IPC
+ * handle; the caller exchanges the handles (any transport), then connect() maps the peers.  allreduce_mean enqueues one
+ * kernel on `stream`: out[offset .. offset + count) = mean over ranks of their buffers' [offset .. offset + count).  Every
+ * rank must issue the same sequence of calls.  No allocation or synchronisation per call: CUDA-graph capturable. */
+int gcpnet_p2p_create(int rank, int world, int64_t num_floats, void** handle_out, void** data_out, unsigned char ipc_handle[64]);
+int gcpnet_p2p_connect(void* handle, const unsigned char* all_handles, float* out);
+int gcpnet_p2p_allreduce_mean(void* handle, int64_t offset, int64_t count, void* stream);
+int gcpnet_p2p_destroy(void* handle);
+
 /* Backward of GCPMessagePassing.forward alone: g_aggregate[N][s+3v] = cotangent of the aggregate.  Uses of `io`:
  * h, chi, e, xi, frames, saved_edge, packed (inputs); g_h, g_chi, g_e, g_xi (overwritten); g_params[0 .. n_edge_params)
  * (the message_fusion.* gradients); ws_edge, ws_edge_partial (workspaces).  The node-side fields are ignored. */

@@ -100,8 +100,8 @@ def test_gloo_two_ranks_average_equals_union_batch(tmp_path):
         assert rel_err(got[k].numpy(), v.numpy()) < 1e-5, k
 
 
-def _nccl_worker(rank, world, port, out):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+def _nccl_worker(rank, world, port, out, transport):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), GCPNET_DDP_TRANSPORT=transport)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -110,6 +110,7 @@ def _nccl_worker(rank, world, port, out):
         plist = [O.random_layer_params(cfg, seed=511 + i) for i in range(2)]
         layers = torch.nn.ModuleList([build_module(cfg, p, device=f"cuda:{rank}").eval() for p in plist])
         fg = ddp.FlatGradients(layers, process_group=dist.group.WORLD, overlap=True)
+        assert fg.transport == transport, (fg.transport, transport)
         b = _graph_batch(cfg, list(ddp.shard_graphs(GRAPHS, rank, world)))
         dev = torch.device("cuda", rank)
         for rep in range(2):  # second pass: side stream exists, per-layer collectives overlap with the backward
@@ -127,11 +128,14 @@ def _nccl_worker(rank, world, port, out):
 
 
 @pytest.mark.gpu
-def test_nccl_two_ranks_average_equals_union_batch(tmp_path):
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
+def test_nccl_two_ranks_average_equals_union_batch(tmp_path, transport):
+    """Both transports of the gradient mean: this package's one-shot all-reduce over NVLink peer memory (csrc/p2p.cu) and
+    the NCCL collective; per-layer, on the side stream, overlapping the backward of the layers below."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     out = str(tmp_path / "avg.pt")
-    mp.spawn(_nccl_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_nccl_worker, args=(2, _free_port(), out, transport), nprocs=2, join=True)
     got = torch.load(out)
     cfg = O.OracleConfig(node_dims=(64, 16), edge_dims=(32, 4), updating_node_positions=True, scalar_nonlinearity="silu")
     plist = [O.random_layer_params(cfg, seed=511 + i) for i in range(2)]
