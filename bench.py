@@ -522,10 +522,21 @@ def run_ours(args, w):
             traffic = tr.get(args.workload, {}).get(dom)
         except Exception:
             pass
+        # FLOP side of the same kernel (fwd = sum of gcp2 terms, bwd ~ 2 x fwd), against the measured dense bf16
+        # tensor peak and against what 3xTF32 can reach of it (tf32 = 1/2 bf16 rate, three products per term)
+        def gcp2_flops(si, vi, so, vo, hd):
+            return 6 * vi * hd + 8 * hd + 18 * vi + 54 + 2 * (si + hd + 9) * so + 6 * hd * vo + 2 * so * vo + 7 * vo + so
+        hd0, hdk = (2 * v + ve) // 4, v // 4
+        fwd_flops = gcp2_flops(2 * s + se, 2 * v + ve, s, v, hd0) + 7 * gcp2_flops(s, v, s, v, hdk) + 7 * (s + 3 * v)
+        kflops = (2 * fwd_flops if dom == "edge_bwd" else fwd_flops) * E
+        tfs = kflops / (us * 1e-6) / 1e12 if us > 0 else 0.0
+        tpeak = float(peaks.get("bf16_tflops", 1632.8))
         roof_out = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": gbs, "peak": peak, "unit": "GB/s",
                     "frac": gbs / peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured, burst copy)" if peaks else "of fallback 6.65 TB/s",
                     "algorithmic_bytes_per_launch": alg, "us_per_launch": us, "launches_timed": cnt,
+                    "flop_side": {"algorithmic_flops_per_launch": kflops, "achieved_tflops": tfs, "bf16_dense_peak_tflops": tpeak,
+                                  "frac_of_bf16_peak": tfs / tpeak, "frac_of_3xtf32_ceiling": tfs / (tpeak / 6.0)},
                     "kernel_share_of_step": tot_ms / dev_ms,
                     "kernel_share_of_kernel_time": tot_ms / max(sum(t for t, _ in kernel_ms.values()), 1e-9),
                     "kernel_timing": "CUDA events around every launch of the kernel in an eager pass of the same steps "
