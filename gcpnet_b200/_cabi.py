@@ -58,7 +58,7 @@ class Plan(C.Structure):
         ("node_tile", C.c_int32), ("node_grid_fwd", C.c_int32), ("node_grid_bwd", C.c_int32),
         ("edge_smem_fwd_bytes", C.c_int32), ("edge_smem_bwd_bytes", C.c_int32),
         ("node_smem_fwd_bytes", C.c_int32), ("node_smem_bwd_bytes", C.c_int32),
-        ("msg_floats", C.c_int64), ("saved_edge_floats", C.c_int64), ("saved_node_floats", C.c_int64),
+        ("agg_floats", C.c_int64), ("saved_edge_floats", C.c_int64), ("saved_node_floats", C.c_int64),
         ("edge_partial_floats", C.c_int64), ("node_partial_floats", C.c_int64),
         ("edge_cotangent_floats", C.c_int64), ("agg_cotangent_floats", C.c_int64), ("packed_floats", C.c_int64),
         ("tc_edge_path", C.c_int32), ("reserved", C.c_int32),
@@ -74,7 +74,7 @@ class Gcp2Plan(C.Structure):
 
 class ForwardIO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
-                ("h", "chi", "e", "xi", "frames", "pos", "out_h", "out_chi", "out_pos", "msg", "saved_edge", "saved_node",
+                ("h", "chi", "e", "xi", "frames", "pos", "out_h", "out_chi", "out_pos", "agg", "saved_edge", "saved_node",
                  "packed")] + [("packed_ready", C.c_int32), ("reserved", C.c_int32)] + \
         [(n, C.c_void_p) for n in ("h_gather", "chi_gather", "prenorm")]
 

@@ -130,15 +130,15 @@ __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackP
   pack_gcp<256>(p.ops[blockIdx.x], p.blob, (int)blockIdx.y, (int)gridDim.y);
 }
 
-// aggregate only (GCPMessagePassing.forward): out[i] = mean/sum over the destination segment
-__global__ void aggregate_kernel(const float* __restrict__ msg, const int* __restrict__ dst_ptr, int N, int W,
+// aggregate only (GCPMessagePassing.forward): out[i] = mean/sum over the destination segment, from the sums the edge
+// kernel's tiles left behind (segment_total, gcp_tile.cuh)
+__global__ void aggregate_kernel(const float* __restrict__ agg, const int* __restrict__ dst_ptr, int N, int W, int edge_rows,
                                  int reduce_mean, float* __restrict__ out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)N * W) return;
   const int i = (int)(idx / W), f = (int)(idx - (long long)i * W);
   const int a = dst_ptr[i], b = dst_ptr[i + 1];
-  float acc = 0.f;
-  for (int q = a; q < b; ++q) acc += __ldg(msg + (size_t)q * W + f);
+  float acc = segment_total(agg, N, W, edge_rows, dst_ptr, i, f);
   if (reduce_mean && b - a > 1) acc /= (float)(b - a);
   out[idx] = acc;
 }
@@ -330,7 +330,7 @@ static void fill_tc_common(tc::TcEdgeParams& p, const gcpnet_graph& g, const Lay
                            const float* xi, const float* frames, const float* packed) {
   p.N = (int)g.num_nodes; p.E = (int)g.num_edges;
   p.h = h; p.chi = chi; p.e = e; p.xi = xi; p.frames = frames;
-  p.perm = g.perm; p.src = g.src; p.dst = g.dst;
+  p.perm = g.perm; p.src = g.src; p.dst = g.dst; p.dst_ptr = g.dst_ptr;
   p.blob = packed + lp.v2_packed_floats;
   const float* pq = packed + lp.v2_packed_floats + tc::rup(lp.tc.blob_floats, 32);  // per-node products of message GCP 0
   p.P = pq; p.Q = pq + (size_t)p.N * 2 * p.pw;
@@ -339,7 +339,7 @@ static int launch_tc_edge_fwd(const gcpnet_graph& g, const LayerPlan& lp, const 
   GcpTimedScope timed(T_EDGE_FWD, st);
   tc::TcEdgeParams p = lp.tc.proto;
   fill_tc_common(p, g, lp, io.h, io.chi, io.e, io.xi, io.frames, io.packed);
-  p.msg = io.msg; p.saved = saved;
+  p.agg = io.agg; p.saved = saved;
   p.dbg = g_tc_dbg.load(std::memory_order_relaxed);
   if (gcp_tc_launch_node_pre(p, const_cast<float*>(p.P), const_cast<float*>(p.Q), st)) return 1;
   return gcp_tc_launch_edge_fwd(p, lp.tc.grid, st);
@@ -424,7 +424,7 @@ static int run_tc_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, co
     tc::TcBwdParams b = T.bproto;
     fill_tc_common(b.f, g, lp, io.h, io.chi, io.e, io.xi, io.frames, io.packed);
     b.f.saved = const_cast<float*>(io.saved_edge);
-    b.f.msg = nullptr; b.f.dbg = g_tc_dbg.load(std::memory_order_relaxed);
+    b.f.agg = nullptr; b.f.dbg = g_tc_dbg.load(std::memory_order_relaxed);
     b.gagg = gagg; b.dst_ptr = g.dst_ptr;
     b.ge = io.g_e; b.gxi = io.g_xi; b.Y = Y; b.partial = io.ws_edge_partial;
     if (gcp_tc_launch_edge_bwd(b, T.grid, st)) return 1;
@@ -568,7 +568,7 @@ static int run_edge_forward(const gcpnet_layer& l, const gcpnet_graph& g, const 
   EdgeParams p = make_edge_params(l, g, lp.ops, lp.ef, false, io.packed);
   p.h = io.h_gather ? io.h_gather : io.h; p.chi = io.chi_gather ? io.chi_gather : io.chi;
   p.e = io.e; p.xi = io.xi; p.frames = io.frames;
-  p.msg = io.msg; p.saved = io.saved_edge;
+  p.agg = io.agg; p.saved = io.saved_edge;
   return launch_edge_fwd(p, lp.ef, st);
 }
 
@@ -607,7 +607,8 @@ int gcpnet_layer_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, c
   }
   if (run_edge_forward(l, *graph, lp, f, st)) return 1;
   NodeParams p = make_node_params(l, *graph, lp.ops, lp.nf, false, f.packed);
-  p.h = f.h; p.chi = f.chi; p.msg = f.msg; p.pos = f.pos; p.frames = f.frames;
+  p.h = f.h; p.chi = f.chi; p.agg = f.agg; p.pos = f.pos; p.frames = f.frames;
+  p.edge_rows = edge_tile_rows(lp);
   p.out_h = f.out_h; p.out_chi = f.out_chi; p.out_pos = f.out_pos; p.saved = f.saved_node;
   return launch_node_fwd(p, lp.nf, st);
 }
@@ -626,8 +627,8 @@ int gcpnet_message_passing_forward(const gcpnet_layer* layer, const gcpnet_graph
   if (run_edge_forward(*layer, *graph, lp, *io, st)) return 1;
   const int W = layer->s + 3 * layer->v;
   const long long tot = graph->num_nodes * W;
-  aggregate_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(io->msg, graph->dst_ptr, (int)graph->num_nodes, W,
-                                                            layer->reduce_mean, aggregate);
+  aggregate_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(io->agg, graph->dst_ptr, (int)graph->num_nodes, W,
+                                                            edge_tile_rows(lp), layer->reduce_mean, aggregate);
   gcp_note_launches(1);
   CUDA_TRY(cudaGetLastError());
   return 0;

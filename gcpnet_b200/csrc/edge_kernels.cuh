@@ -30,7 +30,7 @@ struct EdgeParams {
                                            // rows of the [2N] gather table, gcpnet.py:1065-1116)
   const int* dst_ptr;                      // [N+1] CSR row pointer of the destination-sorted order
   const float* blob;                       // packed weights of the layer (pack.cuh)
-  float* msg;                              // [E][s+3v] final messages, sorted order
+  float* agg;                              // [N][s+3v] per-destination sums + [tiles][2][s+3v] carries (segment_total, gcp_tile.cuh)
   float* saved;                            // activations kept for backward (nullptr: inference)
   long long offT[MAX_MSG_LAYERS], offG[MAX_MSG_LAYERS], offS[MAX_MSG_LAYERS], offV[MAX_MSG_LAYERS];
   // backward
@@ -125,7 +125,6 @@ GCP_HDN void edge_fwd_tile(const EdgeParams& p, float* sm, int tile, WPipe& wp, 
         if (e < nrows) {
           if (sT) sT[q * s + j] = t;
           if (sS) sS[q * s + j] = r;
-          if (last) p.msg[q * (s + v3) + j] = r;
         }
       }
       if (sG && e < nrows) for (int o = lane; o < v; o += 32) sG[q * v + o] = b.SG[e * b.ldsg + o];
@@ -144,7 +143,6 @@ GCP_HDN void edge_fwd_tile(const EdgeParams& p, float* sm, int tile, WPipe& wp, 
           *vp = r;
           if (e < nrows) {
             if (sV) sV[q * v3 + 3 * o + x] = r;
-            if (last) p.msg[q * (s + v3) + s + 3 * o + x] = r;
           }
         }
       }
@@ -152,6 +150,26 @@ GCP_HDN void edge_fwd_tile(const EdgeParams& p, float* sm, int tile, WPipe& wp, 
     GCP_PHASE_END
     wp.head++;  // G chunk released; the next phase (next GCP or next tile) refills its slot
   }
+  // ---- aggregate (gcpnet.py:938-947) straight out of shared memory: the thread of a segment's FIRST row in the tile sums
+  //      that destination's rows (fixed order), per column part
+  GCP_PHASE_BEGIN(NT)
+  const int e = tid % TE, part = tid / TE, W = s + v3;
+  if (e < nrows) {
+    const int q = row0 + e, d = p.dst[q];
+    if (e == 0 || p.dst[q - 1] != d) {
+      int e1 = e + 1;
+      while (e1 < nrows && p.dst[row0 + e1] == d) ++e1;
+      const int a = p.dst_ptr[d], b = p.dst_ptr[d + 1];
+      float* out = (a >= row0 && b <= row0 + TE) ? p.agg + (size_t)d * W
+                                                 : p.agg + (size_t)p.N * W + ((size_t)tile * 2 + (a < row0 ? 0 : 1)) * W;
+      for (int f = part; f < W; f += NT / TE) {
+        float acc = 0.f;
+        for (int r = e; r < e1; ++r) acc += f < s ? Zs[r * L.ldz + f] : Vs[r * L.ldv + (f - s)];
+        out[f] = acc;
+      }
+    }
+  }
+  GCP_PHASE_END
 }
 
 template <int TE, int NT, int SLF, int SLD>

@@ -548,6 +548,27 @@ GCP_HD void GCP_WGRAD_NAME(const float* G, int ldg, int J, const float* Zin, int
 }
 
 // ------------------------------------------------------------------------------------------
+// segment reduction fused into the edge kernels (GCPMessagePassing.aggregate, gcpnet.py:938-947)
+// ------------------------------------------------------------------------------------------
+// The edge kernels never write per-edge messages: edges are sorted by destination, so a tile sums the rows of every
+// destination it holds in shared memory (fixed row order) and emits
+//   buf[d][W]                   the segment's sum, when the whole segment lies inside ONE tile (t0 == t1 below), or
+//   carry[tile][0 | 1][W]       the partial sum of the tile's first (started in an earlier tile) / last (continues in the
+//                               next tile) segment,  carry = buf + N * W.
+// A destination whose segment spans tiles t0 < ... < t1 is the last segment of t0 and the first of every later tile:
+// consumers add those partials in tile order -- still a fixed order, still no atomics.
+GCP_HD float segment_total(const float* buf, long long N, int W, int R, const int* dst_ptr, int i, int f) {
+  const int a = dst_ptr[i], b = dst_ptr[i + 1];
+  if (a == b) return 0.f;
+  const int t0 = a / R, t1 = (b - 1) / R;
+  if (t0 == t1) return GCP_LDG(buf + (size_t)i * W + f);
+  const float* carry = buf + (size_t)N * W;
+  float acc = GCP_LDG(carry + ((size_t)t0 * 2 + 1) * W + f);
+  for (int t = t0 + 1; t <= t1; ++t) acc += GCP_LDG(carry + ((size_t)t * 2) * W + f);
+  return acc;
+}
+
+// ------------------------------------------------------------------------------------------
 // cooperative row copies: warp per row, lane per column (coalesced, no integer division)
 // ------------------------------------------------------------------------------------------
 // dst (smem, row stride ldd) <- rows of a global matrix with `len` contiguous floats per row,

@@ -276,6 +276,8 @@ struct LayerPlan {
   tc::TcPlan tc;      // tensor-core edge path (tc_edge.cuh); tc.ok == false -> FFMA tiles only
   int v2_packed_floats;
 };
+// rows per tile of the edge forward kernel this plan launches (layout of the segment sums, segment_total in gcp_tile.cuh)
+inline int edge_tile_rows(const LayerPlan& lp) { return lp.tc.ok ? lp.tc.proto.rows : lp.ef.TE; }
 
 // Spill area of the node backward (behind the per-CTA partial rows in ws_node_partial): per GCP dense row matrices
 // gT [N][so -> 4], Z [N][K -> 4], gg [N][vo -> 4]  (BwdBufs::sp_*, node_wgrad.cuh).
@@ -336,7 +338,10 @@ inline std::string make_layer_plan(const gcpnet_layer& l, long long N, long long
     p.edge_smem_fwd_bytes = lp->ef.sm.total * 4; p.edge_smem_bwd_bytes = lp->eb.sm.total * 4;
     p.node_smem_fwd_bytes = lp->nf.sm.total * 4; p.node_smem_bwd_bytes = lp->nb.sm.total * 4;
     const long long W = l.s + 3 * l.v;
-    p.msg_floats = E * W;
+    {  // per-destination sums + two carry rows per edge tile (segment_total, gcp_tile.cuh)
+      const long long rows = edge_tile_rows(*lp);
+      p.agg_floats = N * W + 2 * ((E + rows - 1) / rows) * W;
+    }
     long long offT[MAX_MSG_LAYERS], offG[MAX_MSG_LAYERS], offS[MAX_MSG_LAYERS], offV[MAX_MSG_LAYERS], tot;
     edge_saved_offsets(l, E, offT, offG, offS, offV, &tot);
     p.saved_edge_floats = tot;

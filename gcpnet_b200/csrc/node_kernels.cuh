@@ -36,7 +36,7 @@ struct NodeParams {
   float slope, ln_eps, vn_eps, pos_weight, p_drop;
   unsigned long long seed;
   const long long* rng_ctr;     // device counter, advanced by the host side once per training forward
-  const float *h, *chi, *msg, *fbar, *pos;
+  const float *h, *chi, *agg, *fbar, *pos;
   const float* fbar_pos;        // node mask: mean frames of the position-update GCP (nullptr: fbar)
   const unsigned char* mask;    // node mask (nullptr: every node takes part): masked-out rows keep the layer input
   int pre_norm;                 // gcp_norm.1 after the first residual, no normalisation at the end (gcpnet.py:1223-1224,1245)
@@ -44,6 +44,7 @@ struct NodeParams {
   const int *src_ptr, *src_pos, *perm;
   const float* frames;
   const int* dst_ptr;
+  int edge_rows;                // rows per edge tile of the kernel that produced `agg` (segment_total)
   const float *ln0_w, *ln0_b, *ln1_w, *ln1_b;
   const float* blob;
   float *out_h, *out_chi, *out_pos;
@@ -358,8 +359,7 @@ GCP_HDN void node_fwd_tile(const NodeParams& p, float* sm, int tile, WPipe& wp, 
       const int i = row0 + e;
       const int a = p.dst_ptr[i], bnd = p.dst_ptr[i + 1];
       for (int f = lane; f < W; f += 32) {
-        float acc = 0.f;
-        for (int q = a; q < bnd; ++q) acc += GCP_LDG(p.msg + (size_t)q * W + f);
+        float acc = segment_total(p.agg, p.N, W, p.edge_rows, p.dst_ptr, i, f);  // summed by the edge kernel's tiles
         if (p.reduce_mean && bnd - a > 1) acc = acc / (float)(bnd - a);
         if (p.train) {
           // scalar channels: elementwise; vector channels: one draw per (node, channel) shared by xyz (comp:113)

@@ -73,7 +73,8 @@ struct TcEdgeParams {
   const float* blob;
   const float *P, *Q;                 // [N][2 * (sop + 16)], [N][2 * 96]
   int pw;                             // sop + 16
-  float* msg;                         // [E][s + 3v]
+  float* agg;                         // [N][s + 3v] per-destination sums + [tiles][2][s + 3v] carries (segment_total)
+  const int* dst_ptr;                 // [N + 1] CSR row pointer of the destination-sorted order
   float* saved;                       // per tile: (L-1) x [S image | V image]; nullptr = inference
   long long* dbg;                     // optional [L][16] clock64 stamps of CTA 0's first tile (development aid)
   long long saved_tile_stride; int s_img, v_img;  // floats

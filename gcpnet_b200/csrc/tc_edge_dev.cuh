@@ -308,7 +308,6 @@ __device__ __forceinline__ void epilogue_b(const TcEdgeParams& p, const TcGcp& g
   float* V = sm + p.VBUF;
   const float* bs = smc + g.o_b;
   const float* bg = smc + g.o_b + g.sop;
-  const int W = p.s + 3 * p.v;
   // scalars: S' = (S +) act_s(T + b)   (gcpnet.py:441,465; residual stack :920-924)
   for (int cg = w.part; 16 * cg < g.so; cg += CS) {
     float t[16];
@@ -334,7 +333,6 @@ __device__ __forceinline__ void epilogue_b(const TcEdgeParams& p, const TcGcp& g
         }
         sv[0] += old.x; sv[1] += old.y; sv[2] += old.z; sv[3] += old.w;
         put4(Z, w.tl + (uint32_t)p.ZLO, w.r, c, sv[0], sv[1], sv[2], sv[3]);
-        if (last && live) *reinterpret_cast<float4*>(p.msg + q * W + c) = make_float4(sv[0], sv[1], sv[2], sv[3]);
       }
     }
   }
@@ -372,15 +370,52 @@ __device__ __forceinline__ void epilogue_b(const TcEdgeParams& p, const TcGcp& g
     }
 #pragma unroll
     for (int x = 0; x < 3; ++x) put4(V + x * PLANE, w.tl + (uint32_t)(p.VLO + PW * x), w.r, 4 * gi, nv[x][0], nv[x][1], nv[x][2], nv[x][3]);
-    if (last && live && 4 * gi < g.vo) {
-      float* mp = p.msg + q * W + p.s + 12 * gi;  // [channel][xyz], xyz fastest; vo % 4 == 0
-      float f[12];
+  }
+}
+
+// ---- aggregate (gcpnet.py:938-947) straight out of the Z / V tiles: the threads of a destination's rows in the tile share
+//      its 4-column groups; each sums its group over the segment's rows, starting at its own row and wrapping around (a fixed
+//      order per output element; the threads of a warp read different rows -> no bank conflicts).  Complete segments go to
+//      agg[dst], the tile's open ends to its two carry rows (segment_total, gcp_tile.cuh).  The per-edge messages never go
+//      to HBM.
+template <int CS>
+__device__ __forceinline__ void segment_sums(const TcEdgeParams& p, const float* Z, const float* V, const Who& w, int tile,
+                                             int dst, bool live) {
+  if (!live) return;
+  const long long row0 = (long long)tile * p.rows;
+  const long long a = p.dst_ptr[dst], b = p.dst_ptr[dst + 1];
+  const int r0 = a > row0 ? (int)(a - row0) : 0;                                  // rows [r0, r1) of the tile belong to dst
+  const int r1 = (int)((b < row0 + p.rows ? b : row0 + p.rows) - row0);
+  const int n = r1 - r0, j = w.r - r0, W = p.s + 3 * p.v;
+  float* out = (a >= row0 && b <= row0 + p.rows) ? p.agg + (size_t)dst * W
+                                                 : p.agg + (size_t)p.N * W + ((size_t)tile * 2 + (a < row0 ? 0 : 1)) * W;
+  const int gs = p.s >> 2, gv = p.v >> 2;  // 4-column groups of the scalars / of the vector channels
+  for (int g = j * CS + w.part; g < gs + gv; g += n * CS) {
+    if (g < gs) {
+      float4 acc = get4(Z, w.r, 4 * g);
+      for (int i = 1, r = w.r + 1; i < n; ++i, ++r) {
+        if (r == r1) r = r0;
+        const float4 t = get4(Z, r, 4 * g);
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
+      *reinterpret_cast<float4*>(out + 4 * g) = acc;
+    } else {
+      const int gi = g - gs;
+      float4 acc[3];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int x = 0; x < 3; ++x) acc[x] = get4(V + x * PLANE, w.r, 4 * gi);
+      for (int i = 1, r = w.r + 1; i < n; ++i, ++r) {
+        if (r == r1) r = r0;
 #pragma unroll
-        for (int x = 0; x < 3; ++x) f[3 * i + x] = nv[x][i];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) *reinterpret_cast<float4*>(mp + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        for (int x = 0; x < 3; ++x) {
+          const float4 t = get4(V + x * PLANE, r, 4 * gi);
+          acc[x].x += t.x; acc[x].y += t.y; acc[x].z += t.z; acc[x].w += t.w;
+        }
+      }
+      float* mp = out + p.s + 12 * gi;  // [channel][xyz], xyz fastest; v % 4 == 0
+      *reinterpret_cast<float4*>(mp) = make_float4(acc[0].x, acc[1].x, acc[2].x, acc[0].y);
+      *reinterpret_cast<float4*>(mp + 4) = make_float4(acc[1].y, acc[2].y, acc[0].z, acc[1].z);
+      *reinterpret_cast<float4*>(mp + 8) = make_float4(acc[2].z, acc[0].w, acc[1].w, acc[2].w);
     }
   }
 }
@@ -562,6 +597,8 @@ __global__ void __launch_bounds__(128 * CS, 1) tc_edge_fwd_kernel(const __grid_c
                            &smc);
       rs.head += 1;
     }
+    __syncthreads();  // the last GCP's epilogue B wrote the final messages into the Z / V tiles
+    segment_sums<CS>(p, Z, V, c.w, tile, dst, live);
   }
   if (c.uwarp == 0 && elect_one()) bulk_store_wait_all();
   fence_before_sync();

@@ -350,7 +350,7 @@ class _LayerFn(torch.autograd.Function):
         f32 = lambda n: torch.empty(max(int(n), 1), dtype=torch.float32, device=dev)
         out_h, out_chi = torch.empty_like(h), torch.empty_like(chi)
         out_pos = torch.empty_like(pos) if spec.has_pos else None
-        msg = f32(plan.msg_floats)
+        agg = f32(plan.agg_floats)
         saved_edge = f32(plan.saved_edge_floats) if need_grad else None
         saved_node = f32(plan.saved_node_floats) if need_grad else None
         prenorm = f32(plan.prenorm_floats) if spec.pre_norm else None
@@ -364,7 +364,7 @@ class _LayerFn(torch.autograd.Function):
         else:
             packed, ready = f32(plan.packed_floats), 0
         io = _cabi.ForwardIO(_ptr(h), _ptr(chi), _ptr(e), _ptr(xi), _ptr(frames), _ptr(pos), _ptr(out_h), _ptr(out_chi),
-                             _ptr(out_pos), _ptr(msg), _ptr(saved_edge), _ptr(saved_node), _ptr(packed), ready, 0,
+                             _ptr(out_pos), _ptr(agg), _ptr(saved_edge), _ptr(saved_node), _ptr(packed), ready, 0,
                              _ptr(hg), _ptr(chig), _ptr(prenorm))
         _lib.check(lib.gcpnet_layer_forward(C.byref(layer), C.byref(gv.struct), C.byref(plan), C.byref(io), _stream()),
                    "gcpnet_layer_forward")
@@ -495,9 +495,9 @@ class _MPFn(torch.autograd.Function):
         f32 = lambda n: torch.empty(max(int(n), 1), dtype=torch.float32, device=dev)
         W = spec.s + 3 * spec.v
         agg = torch.empty((N, W), dtype=torch.float32, device=dev)
-        msg, packed = f32(plan.msg_floats), f32(plan.packed_floats)
+        sums, packed = f32(plan.agg_floats), f32(plan.packed_floats)  # the edge tiles' segment sums; `agg` = reduced output
         saved_edge = f32(plan.saved_edge_floats) if need_grad else None
-        io = _cabi.ForwardIO(_ptr(h), _ptr(chi), _ptr(e), _ptr(xi), _ptr(frames), None, None, None, None, _ptr(msg),
+        io = _cabi.ForwardIO(_ptr(h), _ptr(chi), _ptr(e), _ptr(xi), _ptr(frames), None, None, None, None, _ptr(sums),
                              _ptr(saved_edge), None, _ptr(packed), 0, 0)
         _lib.check(lib.gcpnet_message_passing_forward(C.byref(layer), C.byref(gv.struct), C.byref(plan), C.byref(io), _ptr(agg),
                                                       _stream()), "gcpnet_message_passing_forward")

@@ -107,7 +107,8 @@ typedef struct gcpnet_graph {
 typedef struct gcpnet_plan {
   int32_t edge_tile, edge_grid_fwd, edge_grid_bwd, node_tile, node_grid_fwd, node_grid_bwd;
   int32_t edge_smem_fwd_bytes, edge_smem_bwd_bytes, node_smem_fwd_bytes, node_smem_bwd_bytes;
-  int64_t msg_floats;            /* [E][s+3v] final messages */
+  int64_t agg_floats;            /* per-destination message sums [N][s+3v] + two carry rows per edge tile (the per-edge
+                                    messages are summed inside the edge kernel's tiles and never written) */
   int64_t saved_edge_floats;     /* activations kept for backward (0 in inference) */
   int64_t saved_node_floats;
   int64_t edge_partial_floats;   /* edge_grid_bwd * n_edge_params */
@@ -124,7 +125,7 @@ typedef struct gcpnet_plan {
 typedef struct gcpnet_forward_io {
   const float *h, *chi, *e, *xi, *frames, *pos;  /* pos may be NULL when !has_pos */
   float *out_h, *out_chi, *out_pos;
-  float* msg;          /* plan.msg_floats */
+  float* agg;          /* plan.agg_floats: segment sums of the messages, written by the edge kernel */
   float* saved_edge;   /* plan.saved_edge_floats or NULL (inference) */
   float* saved_node;   /* plan.saved_node_floats or NULL (inference) */
   float* packed;       /* plan.packed_floats: written by the forward call, read by the matching backward */

@@ -139,7 +139,7 @@ int emul_layer_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, con
   if (g.num_edges > 0) {
     EdgeParams p = make_edge_params(l, g, lp.ops, lp.ef, false, io->packed);
     p.h = io->h_gather ? io->h_gather : io->h; p.chi = io->chi_gather ? io->chi_gather : io->chi;
-    p.e = io->e; p.xi = io->xi; p.frames = io->frames; p.msg = io->msg; p.saved = io->saved_edge;
+    p.e = io->e; p.xi = io->xi; p.frames = io->frames; p.agg = io->agg; p.saved = io->saved_edge;
     int grid = lp.ef.grid; if (grid > 3) grid = 3;  // exercise the persistent loop
     int bad = 1;
     if (lp.ef.TE == 32) bad = by_slf(lp.ef.SLF, [&] { run_edge_fwd<32, 1>(p, grid); }, [&] { run_edge_fwd<32, 2>(p, grid); });
@@ -151,15 +151,15 @@ int emul_layer_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, con
   if (mp_only) {
     for (int64_t i = 0; i < g.num_nodes; ++i)
       for (int f = 0; f < W; ++f) {
-        float acc = 0.f;
-        for (int q = g.dst_ptr[i]; q < g.dst_ptr[i + 1]; ++q) acc += io->msg[(size_t)q * W + f];
+        float acc = segment_total(io->agg, g.num_nodes, W, lp.ef.TE, g.dst_ptr, (int)i, f);
         if (l.reduce_mean && g.dst_ptr[i + 1] - g.dst_ptr[i] > 1) acc /= (float)(g.dst_ptr[i + 1] - g.dst_ptr[i]);
         aggregate[i * W + f] = acc;
       }
     return 0;
   }
   NodeParams p = make_node_params(l, g, lp.ops, lp.nf, false, io->packed);
-  p.h = io->h; p.chi = io->chi; p.msg = io->msg; p.pos = io->pos; p.frames = io->frames;
+  p.h = io->h; p.chi = io->chi; p.agg = io->agg; p.pos = io->pos; p.frames = io->frames;
+  p.edge_rows = lp.ef.TE;
   p.out_h = io->out_h; p.out_chi = io->out_chi; p.out_pos = io->out_pos; p.saved = io->saved_node;
   int grid = lp.nf.grid; if (grid > 2) grid = 2;
   if (lp.nf.SLF == 1) run_node_fwd<1>(p, grid); else if (lp.nf.SLF == 2) run_node_fwd<2>(p, grid);

@@ -158,12 +158,13 @@ class EmulLayer:
         N = self.N
         nan = lambda *shape: np.full(shape, np.nan, dtype=np.float32)
         self.out_h, self.out_chi, self.out_pos = nan(N, s), nan(N, v, 3), nan(N, 3)
-        self.msg = nan(max(int(self.plan.msg_floats), 1))
+        # segment sums [N][W] + two carry rows per edge tile; sized for the smallest tile a test may force (32 rows)
+        self.agg = nan(max(int(self.plan.agg_floats), (N + 2 * (self.E // 32 + 1)) * (s + 3 * v), 1))
         self.saved_edge = nan(max(int(self.plan.saved_edge_floats), 1)) if save else None
         self.saved_node = nan(max(int(self.plan.saved_node_floats), 1)) if save else None
         self.packed = nan(max(int(self.plan.packed_floats), 1))
         io = _cabi.ForwardIO(_p(self.h), _p(self.chi), _p(self.e), _p(self.xi), _p(self.frames), _p(self.pos),
-                             _p(self.out_h), _p(self.out_chi), _p(self.out_pos), _p(self.msg),
+                             _p(self.out_h), _p(self.out_chi), _p(self.out_pos), _p(self.agg),
                              _p(self.saved_edge) if save else None, _p(self.saved_node) if save else None,
                              _p(self.packed), 0, 0, _p(self.hg) if self.hg is not None else None,
                              _p(self.chig) if self.chig is not None else None, None)

@@ -84,6 +84,33 @@ def test_emulated_multi_tile_ragged(lib, edge_tile, node_tile):
         assert rel_err(L.param_grad(k), res["pgrad/" + k].numpy()) < TOL, k
 
 
+@pytest.mark.parametrize("edge_tile", [32, 64])
+def test_emulated_segments_spanning_several_edge_tiles(lib, edge_tile):
+    """Per-destination sums are formed inside the edge tiles: hub destinations (in-degree > tile height) are assembled from
+    the carry rows of several tiles, in tile order (segment_total, gcp_tile.cuh).  Node 0 starts on a tile boundary."""
+    from tests import emul_harness as EH
+    cfg = O.OracleConfig(node_dims=(16, 4), edge_dims=(8, 2), num_message_layers=2, updating_node_positions=True,
+                         bottleneck=2, default_bottleneck=2)
+    params = O.random_layer_params(cfg, seed=41)
+    g = torch.Generator().manual_seed(7)
+    n = 23
+    parts = [torch.randint(0, n, (2, 60), generator=g)]
+    for node, deg in {0: 2 * edge_tile + 5, 9: 3 * edge_tile, 10: edge_tile + 1, 22: 70}.items():
+        parts.append(torch.stack((torch.randint(0, n, (deg,), generator=g), torch.full((deg,), node, dtype=torch.long))))
+    ei = torch.cat(parts, dim=1)
+    ei = ei[:, torch.randperm(ei.shape[1], generator=g)]
+    inputs = O.synthetic_layer_inputs(cfg, ei, n, seed=42)
+    case = dict(seed=43)
+    res = oracle_forward_backward(case, cfg, params, inputs)
+    L = EH.EmulLayer(lib, cfg, params, inputs)
+    oh, ochi, opos = L.forward(edge_tile=edge_tile)
+    assert rel_err(oh, res["out_h"].numpy()) < TOL and rel_err(ochi, res["out_chi"].numpy()) < TOL
+    assert rel_err(opos, res["out_pos"].numpy()) < TOL
+    agg = L.forward(edge_tile=edge_tile, mp_only=True)
+    ms, mV = O.message_passing(params, "interaction.", cfg, inputs["h"], inputs["chi"], inputs["e"], inputs["xi"], ei, inputs["frames"])
+    assert rel_err(agg, torch.cat((ms, mV.reshape(n, -1)), dim=1).numpy()) < TOL
+
+
 def test_emulated_message_passing_only(lib):
     """GCPMessagePassing.forward alone, reduce='add' (autoregressive layers, gcpnet.py:984)."""
     from tests import emul_harness as EH

@@ -403,6 +403,39 @@ def test_tensor_core_and_ffma_paths_agree_and_match_oracle(graph):
         assert rel_err(res[1][key].numpy(), res[0][key].numpy()) < 2e-5, key
 
 
+def _hub_edge_index(n, hubs, extra, seed):
+    """Random edges plus hub destinations: `hubs` = {node: in-degree}; source nodes random."""
+    g = torch.Generator().manual_seed(seed)
+    parts = [torch.randint(0, n, (2, extra), generator=g)]
+    for node, deg in hubs.items():
+        parts.append(torch.stack((torch.randint(0, n, (deg,), generator=g), torch.full((deg,), node, dtype=torch.long))))
+    ei = torch.cat(parts, dim=1)
+    return ei[:, torch.randperm(ei.shape[1], generator=g)]
+
+
+@pytest.mark.parametrize("dims", [(64, 16), (16, 4)])
+def test_segment_sums_of_destinations_that_span_several_edge_tiles(dims):
+    """The edge kernels sum the messages per destination inside their tiles (no per-edge message rows in HBM): a destination
+    with more incoming edges than a tile has rows is assembled from the carry rows of several tiles.  Node 0's segment starts
+    on a tile boundary; the others start mid-tile, one of them right behind another hub.  (Reduce 'add' over hubs:
+    test_message_passing_alone_forward_and_backward.)"""
+    big = dims[0] >= 64
+    cfg = O.OracleConfig(node_dims=dims, edge_dims=(32, 4) if big else (4, 2), bottleneck=4 if big else 2,
+                         default_bottleneck=4 if big else 2, updating_node_positions=True)
+    n = 97
+    ei = _hub_edge_index(n, {0: 300, 1: 5, 40: 700, 41: 129, 96: 260}, extra=600, seed=71)
+    inputs = O.synthetic_layer_inputs(cfg, ei, n, seed=72)
+    case = dict(seed=73)
+    params = O.random_layer_params(cfg, seed=70)
+    want = oracle_forward_backward(case, cfg, params, inputs)
+    exact = oracle_forward_backward(case, cfg, params, inputs, dtype=torch.float64)
+    layer = build_module(cfg, params).eval()
+    names = [k for k, _ in layer.named_parameters()]
+    for tc in ((0, 1) if big else (0,)):
+        res = _with_tc(tc, lambda: module_forward_backward(layer, case, cfg, inputs))
+        _compare(res, want, names, exact=exact)
+
+
 def test_tensor_core_path_nonresidual_vector_residual_and_silu():
     """Flag combinations of the message stack on the tensor-core path (NMS dims)."""
     for kw in (dict(use_residual_message_gcp=False), dict(vector_residual=True), dict(scalar_nonlinearity="silu"),

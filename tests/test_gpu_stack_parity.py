@@ -149,6 +149,11 @@ def test_message_passing_alone_forward_and_backward(dims, tc, reduce):
     g = torch.Generator().manual_seed(330)
     n, E = 150, 1100
     ei = torch.randint(0, n - 3, (2, E), generator=g)
+    # two hub destinations: their segments span several edge tiles (per-destination sums are formed inside the tiles)
+    hubs = [torch.stack((torch.randint(0, n, (deg,), generator=g), torch.full((deg,), node, dtype=torch.long)))
+            for node, deg in ((17, 300), (18, 140))]
+    ei = torch.cat([ei] + hubs, dim=1)
+    ei = ei[:, torch.randperm(ei.shape[1], generator=g)]
     inputs = O.synthetic_layer_inputs(cfg, ei, n, seed=331)
     params = {k: v for k, v in O.random_layer_params(cfg, seed=332).items() if k.startswith("interaction.")}
     mcfg, lcfg = module_cfgs(cfg)
