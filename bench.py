@@ -42,8 +42,12 @@ WORKLOADS = {
                  node_dims=(64, 16), edge_dims=(32, 4), pos=True),
     "cfg5": dict(desc="CPD-like encoder, 8 x 256 residues, kNN k=30, 6 layers, 5 % of the nodes masked", graphs=8, n=256, kind="knn", k=30,
                  layers=6, node_dims=(100, 16), edge_dims=(32, 4), pos=False, mask_frac=0.05),
-    "cfg5d": dict(desc="CPD-like decoder, 8 x 256 residues, kNN k=30, 6 autoregressive layers, 5 % masked", graphs=8, n=256, kind="knn",
-                  k=30, layers=6, node_dims=(100, 16), edge_dims=(32, 4), pos=False, mask_frac=0.05, autoregressive=True),
+    # decoder layers as GCPNetCPDLitModule builds them (gcpnet_cpd_module.py:95-111): autoregressive, vector_gate=False,
+    # ablate_frame_updates=True
+    "cfg5d": dict(desc="CPD-like decoder, 8 x 256 residues, kNN k=30, 6 autoregressive GCP-Baseline layers (no frame scalars, "
+                       "no vector gate), 5 % masked", graphs=8, n=256, kind="knn",
+                  k=30, layers=6, node_dims=(100, 16), edge_dims=(32, 4), pos=False, mask_frac=0.05, autoregressive=True,
+                  vector_gate=False, ablate_frame_updates=True),
     # BASELINE configs[3] as a STRONG-scaling case: 1 024 twenty-body graphs in total, sharded 1 024 / N per GPU
     "cfg4s": dict(desc="NMS 20-body, 1024 graphs in total sharded by graph across the GPUs, 4 layers", graphs=1024, n=20, kind="nms",
                   layers=4, node_dims=(64, 16), edge_dims=(32, 4), pos=True, strong=True),
@@ -106,7 +110,8 @@ def make_batch(w, seed, rank=0):
 
 def oracle_cfg(w):
     from oracle import gcp_oracle as O  # CPU arm only
-    return O.OracleConfig(node_dims=w["node_dims"], edge_dims=w["edge_dims"], updating_node_positions=w["pos"])
+    return O.OracleConfig(node_dims=w["node_dims"], edge_dims=w["edge_dims"], updating_node_positions=w["pos"],
+                          vector_gate=w.get("vector_gate", True), ablate_frame_updates=w.get("ablate_frame_updates", False))
 
 
 class AttrDict(dict):
@@ -118,12 +123,14 @@ class AttrDict(dict):
         return AttrDict(self)
 
 
-def module_cfgs():
+def module_cfgs(w=None):
     """configs/model/module_cfg/gcp_module_nms.yaml + layer_cfg/gcp_interaction_layer_nms.yaml + mp_cfg/gcp_mp_nms.yaml."""
-    mcfg = AttrDict(norm_x_diff=True, scalar_gate=0, vector_gate=True, vector_residual=False, vector_frame_residual=False,
+    w = w or {}
+    mcfg = AttrDict(norm_x_diff=True, scalar_gate=0, vector_gate=w.get("vector_gate", True), vector_residual=False, vector_frame_residual=False,
                     frame_gate=False, sigma_frame_gate=False, scalar_nonlinearity="relu", vector_nonlinearity=None,
                     nonlinearities=["relu", None], bottleneck=4, vector_linear=True, vector_identity=True,
-                    default_vector_residual=False, default_bottleneck=4, node_positions_weight=1.0, ablate_frame_updates=False,
+                    default_vector_residual=False, default_bottleneck=4, node_positions_weight=1.0,
+                    ablate_frame_updates=w.get("ablate_frame_updates", False),
                     ablate_scalars=False, ablate_vectors=False, ablate_x_force_update=True, enable_e3_equivariance=False)
     mp = AttrDict(edge_encoder=False, edge_gate=False, num_message_layers=8, message_residual=0, message_ff_multiplier=1,
                   self_message=True, use_residual_message_gcp=True)
@@ -261,7 +268,7 @@ def run_reference(args, w):
 # ------------------------------------------------------------------------------------------
 def build_stack(w, device):
     import gcpnet_b200
-    mcfg, lcfg = module_cfgs()
+    mcfg, lcfg = module_cfgs(w)
     torch.manual_seed(0)
     layers = torch.nn.ModuleList([
         gcpnet_b200.GCPInteractions(w["node_dims"], w["edge_dims"], cfg=mcfg, layer_cfg=lcfg, dropout=0.1,

@@ -23,7 +23,7 @@ class Gcp2(C.Structure):
         ("vector_down", C.c_void_p), ("vector_down_frames", C.c_void_p), ("scalar_out_w", C.c_void_p),
         ("scalar_out_b", C.c_void_p), ("vector_up", C.c_void_p), ("vector_out_scale_w", C.c_void_p),
         ("vector_out_scale_b", C.c_void_p),
-        ("grad_off", C.c_int32 * 7), ("reserved", C.c_int32),
+        ("grad_off", C.c_int32 * 7), ("flags", C.c_int32),
     ]
 
 
@@ -191,11 +191,23 @@ def gcp2_hidden_dim(vi: int, vo: int, bottleneck: int) -> int:
     return vi // bottleneck if bottleneck > 1 else max(vi, vo)
 
 
-def gcp2_shapes(si: int, vi: int, so: int, vo: int, hd: int) -> Dict[str, Tuple[int, ...]]:
-    shapes = {"vector_down.weight": (hd, vi), "scalar_out.weight": (so, si + hd + 9), "scalar_out.bias": (so,),
-              "vector_down_frames.weight": (3, vi)}
+GCP2_NO_FRAMES, GCP2_NO_GATE = 1, 2  # include/gcpnet_b200.h: GCPNET_GCP2_NO_FRAMES / _NO_GATE
+
+
+def gcp2_flags(ablate_frame_updates: bool = False, vector_gate: bool = True) -> int:
+    return (GCP2_NO_FRAMES if ablate_frame_updates else 0) | (0 if vector_gate else GCP2_NO_GATE)
+
+
+def gcp2_shapes(si: int, vi: int, so: int, vo: int, hd: int, flags: int = 0) -> Dict[str, Tuple[int, ...]]:
+    """Parameters of one GCP2 in state_dict order (gcpnet.py:298-322)."""
+    frames = not (flags & GCP2_NO_FRAMES)
+    shapes = {"vector_down.weight": (hd, vi), "scalar_out.weight": (so, si + hd + (9 if frames else 0)), "scalar_out.bias": (so,)}
+    if frames:  # gcpnet.py:307-309
+        shapes["vector_down_frames.weight"] = (3, vi)
     if vo:  # gcpnet.py:310-322
-        shapes.update({"vector_up.weight": (vo, hd), "vector_out_scale.weight": (vo, so), "vector_out_scale.bias": (vo,)})
+        shapes["vector_up.weight"] = (vo, hd)
+        if not (flags & GCP2_NO_GATE):
+            shapes.update({"vector_out_scale.weight": (vo, so), "vector_out_scale.bias": (vo,)})
     return shapes
 
 
@@ -207,8 +219,9 @@ class LayerSpec:
                  vector_residual=False, default_vector_residual=False, scalar_nonlinearity="relu",
                  vector_nonlinearity=None, nonlinearity_slope=1e-2, use_residual_message_gcp=True,
                  enable_e3_equivariance=False, reduce_function="mean", updating_node_positions=False,
-                 node_positions_weight=1.0, pre_norm=False, autoregressive=False):
+                 node_positions_weight=1.0, pre_norm=False, autoregressive=False, ablate_frame_updates=False, vector_gate=True):
         self.s, self.v = int(node_dims[0]), int(node_dims[1])
+        self.gcp_flags = gcp2_flags(ablate_frame_updates, vector_gate)  # every GCP of a layer is built from one cfg
         self.se, self.ve = int(edge_dims[0]), int(edge_dims[1])
         self.L = int(num_message_layers)
         self.residual = bool(use_residual_message_gcp)
@@ -264,14 +277,14 @@ class LayerSpec:
             off += n
 
         for m in mods:
-            for pn, shp in gcp2_shapes(*m[1:6]).items():
+            for pn, shp in gcp2_shapes(*m[1:6], self.gcp_flags).items():
                 add(m[0] + pn, shp)
         self.n_edge_params = off
         for i in range(2):
             add(f"gcp_norm.{i}.scalar_norm.weight", (s,))
             add(f"gcp_norm.{i}.scalar_norm.bias", (s,))
         for m in self.ff_mods + ([self.pos_mod] if self.pos_mod else []):
-            for pn, shp in gcp2_shapes(*m[1:6]).items():
+            for pn, shp in gcp2_shapes(*m[1:6], self.gcp_flags).items():
                 add(m[0] + pn, shp)
         self.n_params = off
         self.n_node_params = off - self.n_edge_params
@@ -280,9 +293,11 @@ class LayerSpec:
         prefix, si, vi, so, vo, hd, act_s, act_v, vres = mod
         dst.si, dst.vi, dst.so, dst.vo, dst.hd = si, vi, so, vo, hd
         dst.act_s, dst.act_v, dst.vector_residual = act_s, act_v, vres
+        dst.flags = self.gcp_flags
         for pn in GCP2_PARAM_ORDER:
-            setattr(dst, _PTR_FIELD[pn], ptr(prefix + pn))
-            dst.grad_off[_GRAD_SLOT[pn]] = self.offsets[prefix + pn]
+            if prefix + pn in self.offsets:  # GCP-Baseline variants lack vector_down_frames / vector_out_scale
+                setattr(dst, _PTR_FIELD[pn], ptr(prefix + pn))
+                dst.grad_off[_GRAD_SLOT[pn]] = self.offsets[prefix + pn]
 
     def make_layer(self, ptr: Callable[[str], int], *, training=False, p_drop=0.0, seed=0, rng_counter=0) -> Layer:
         l = Layer()

@@ -210,7 +210,7 @@ static SkipRanges node_wgrad_ranges(const gcpnet_layer& l, const LayerPlan& lp) 
     if (op[k] == nullptr) continue;
     const GcpOp& o = *op[k];
     add(o.o_Ws, o.so * gcp_k(o)); add(o.o_bs, o.so);
-    if (o.vo > 0) { add(o.o_Wg, o.vo * o.so); add(o.o_bg, o.vo); }
+    if (o.vo > 0 && gcp_gated(o)) { add(o.o_Wg, o.vo * o.so); add(o.o_bg, o.vo); }
   }
   return s;
 }
@@ -401,7 +401,7 @@ static int launch_node_wgrad(const gcpnet_layer& l, const gcpnet_graph& g, const
     if (op[k] == nullptr) continue;
     const GcpOp& o = *op[k];
     add(spill + sp.gT[k], sp.ldg[k], o.so, spill + sp.Z[k], sp.ldz[k], gcp_k(o), ACT_NONE, g_node_params + o.o_Ws, g_node_params + o.o_bs);
-    if (o.vo > 0)
+    if (o.vo > 0 && gcp_gated(o))
       add(spill + sp.GG[k], sp.ldgg[k], o.vo, saved_node + tsaved[k], o.so, o.so, o.act_v, g_node_params + o.o_Wg, g_node_params + o.o_bg);
   }
   node_wgrad_kernel<<<cta, 256, 0, st>>>(p);

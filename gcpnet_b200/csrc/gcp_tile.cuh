@@ -147,10 +147,13 @@ struct GcpOp {
   int act_s, act_v, vres;
   const float *Wd, *Wdf, *Ws, *bs, *Wu, *Wg, *bg;
   int o_Wd, o_Wdf, o_Ws, o_bs, o_Wu, o_Wg, o_bg;
-  int pad_;
+  int flags;  // GCP2_NO_FRAMES | GCP2_NO_GATE (GCP-Baseline variants, gcpnet.py:302-322,344-350,424-437)
   GcpW w;
 };
-GCP_HD int gcp_k(const GcpOp& op) { return op.si + op.hd + 9; }
+constexpr int GCP2_NO_FRAMES = 1, GCP2_NO_GATE = 2;
+GCP_HD int gcp_nfs(const GcpOp& op) { return (op.flags & GCP2_NO_FRAMES) ? 0 : 9; }  // frame scalars read by scalar_out
+GCP_HD bool gcp_gated(const GcpOp& op) { return (op.flags & GCP2_NO_GATE) == 0; }
+GCP_HD int gcp_k(const GcpOp& op) { return op.si + op.hd + gcp_nfs(op); }
 GCP_HD int gcp_kpad(const GcpOp& op) { return op.w.nWS * op.w.kc; }  // columns the GEMM reads from Z
 
 struct WSeq {  // the order in which one kernel consumes chunks, per tile
@@ -635,7 +638,7 @@ GCP_HD void gcp2_vec_down(const GcpOp& op, const TileBufs& b, const float* wdt, 
 template <int TE, int NT>
 GCP_HD void gcp2_norm_scalarize(const GcpOp& op, const TileBufs& b, int e3, int tid) {
   const int cols = op.w.cols, hdp = op.w.hdp;
-  const int nq = op.hd + 9, kpad = gcp_kpad(op), K = op.si + nq;
+  const int nq = op.hd + gcp_nfs(op), kpad = gcp_kpad(op), K = op.si + nq;
   const int ncol = kpad - op.si;  // nq real columns + zero padding
   for (int item = tid; item < TE * ncol; item += NT) {
     const int e = item % TE, j = item / TE;
@@ -776,6 +779,9 @@ GCP_HDN const float* gcp2_fwd_tile(const GcpOp& op, const TileBufs& b, WPipe& wp
   // thread = (e, o-group): e = tid % TE, o = tid / TE + (NT/TE) * j
   const int e = tid % TE;
   const float* tp = b.T + e * b.ldt;
+  if (!gcp_gated(op)) {  // vector_gate=False, identity vector nonlinearity: V' = U (gcpnet.py:344-350)
+    for (int o = tid / TE; o < op.vo; o += NT / TE) b.SG[e * b.ldsg + o] = 1.f;
+  } else
   for (int o0 = tid / TE; o0 < op.vo; o0 += 2 * (NT / TE)) {
     const int o1 = o0 + NT / TE;
     const bool has1 = o1 < op.vo;
@@ -886,7 +892,8 @@ GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g,
   GCP_BSTAMP();
   // ---- vector_out_scale / vector_up weight gradients (read ALL of T = pre-activations: own phase)
   GCP_PHASE_BEGIN(NT)
-  if (g.sp_GG != nullptr)
+  if (!gcp_gated(op)) { }  // no vector_out_scale (sg = 1 -> gg = 0 above)
+  else if (g.sp_GG != nullptr)
     tile_store_rows<TE, NT>(g.sp_GG, g.sp_row0, round_up(op.vo, 4), g.GG, g.ldgg, g.sp_nrows, tid);
   else
     tile_wgrad<TE, NT, 1, 4>(g.GG, g.ldgg, op.vo, T, ldt, op.so, prow + op.o_Wg, prow + op.o_bg, accumulate,
@@ -984,7 +991,7 @@ GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g,
       const float root = sqrtf(fmaf(a, a, fmaf(bb, bb, c * c)) + SAFE_NORM_EPS);
       acc = gnq[kk] * hp[x * cols + kk] / root;
       for (int o = 0; o < op.vo; ++o) acc = fmaf(g.GU[e * g.ldgu + 3 * o + x], wu_sm[o * hdp + kk], acc);
-    } else if (kk >= hdp && kk < hdp + 3) {
+    } else if (kk >= hdp && kk < hdp + 3 && gcp_nfs(op) != 0) {
       // frame scalars: q[3cc+a] = sum_x F[a][x] D[x][cc]  (|.| on a==1 when e3)
       const int cc = kk - hdp;
       for (int a = 0; a < 3; ++a) {
@@ -1022,7 +1029,7 @@ GCP_HDN void gcp2_bwd_tile(const GcpOp& op, const TileBufs& b, const BwdBufs& g,
   // ---- vector_down / vector_down_frames weight gradients; vector input cotangent
   GCP_PHASE_BEGIN(NT)
   // gWdT[c][k] = sum_{e,x} gHD[e][x][k] * V[e][c][x]
-  for (int item = tid; item < op.vi * (op.hd + 3); item += NT) {
+  for (int item = tid; item < op.vi * (op.hd + gcp_nfs(op) / 3); item += NT) {
     const int kk = item / op.vi, c = item - kk * op.vi;  // kk < hd: Wd row kk ; else Wdf row kk-hd
     const int col = kk < op.hd ? kk : hdp + (kk - op.hd);
     float s = 0.f;

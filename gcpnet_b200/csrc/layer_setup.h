@@ -31,6 +31,7 @@ inline GcpOp to_op(const gcpnet_gcp2& d, int grad_base) {
   o.o_Wd = d.grad_off[0] - grad_base; o.o_Wdf = d.grad_off[1] - grad_base; o.o_Ws = d.grad_off[2] - grad_base;
   o.o_bs = d.grad_off[3] - grad_base; o.o_Wu = d.grad_off[4] - grad_base; o.o_Wg = d.grad_off[5] - grad_base;
   o.o_bg = d.grad_off[6] - grad_base;
+  o.flags = d.flags;
   return o;
 }
 
@@ -41,6 +42,9 @@ inline std::string check_gcp2(const gcpnet_gcp2& d, const char* name) {
   if (d.hd <= 0 || d.hd > 16) return err("hidden vector dim must be in [1,16] (bottleneck too small for this build)");
   if (d.vector_residual && d.vi != d.vo) return err("vector_residual needs vi == vo");
   if (d.act_s < 0 || d.act_s > 5 || d.act_v < 0 || d.act_v > 5) return err("unknown nonlinearity");
+  if (d.flags & ~(GCPNET_GCP2_NO_FRAMES | GCPNET_GCP2_NO_GATE)) return err("unknown flags");
+  if ((d.flags & GCPNET_GCP2_NO_GATE) && d.vo > 0 && d.act_v != 0)
+    return err("vector_gate=False with a vector nonlinearity (norm gating, gcpnet.py:349-350) is not built");
   return "";
 }
 
@@ -232,7 +236,8 @@ inline bool pick_node_tile(const gcpnet_layer& l, LayerOps& ops, long long N, bo
 
 // ---- a GCP2 on its own (gcp2_op.cuh) ----------------------------------------------------------------------------------
 inline int gcp2_n_params(const gcpnet_gcp2& d) {
-  return d.hd * d.vi + 3 * d.vi + d.so * (d.si + d.hd + 9) + d.so + d.vo * d.hd + d.vo * d.so + d.vo;
+  const int nfs = (d.flags & GCPNET_GCP2_NO_FRAMES) ? 0 : 9, gate = (d.flags & GCPNET_GCP2_NO_GATE) ? 0 : 1;
+  return d.hd * d.vi + (nfs / 3) * d.vi + d.so * (d.si + d.hd + nfs) + d.so + d.vo * d.hd + gate * (d.vo * d.so + d.vo);
 }
 inline Gcp2OpPlan plan_gcp2_op(const gcpnet_gcp2& d, long long M) {
   Gcp2OpPlan P{};

@@ -19,7 +19,7 @@ GCP_HD float pack_S(const GcpOp& op, int idx) {
   const int c = idx / cols, k = idx - c * cols;
   if (c >= op.vi) return 0.f;
   if (k < op.hd) return GCP_LDG(op.Wd + k * op.vi + c);
-  if (k >= hdp && k < hdp + 3) return GCP_LDG(op.Wdf + (k - hdp) * op.vi + c);
+  if (k >= hdp && k < hdp + 3 && gcp_nfs(op) != 0) return GCP_LDG(op.Wdf + (k - hdp) * op.vi + c);
   return 0.f;
 }
 // G chunk: WG[vo][ldg] | bg[round_up(vo,4)] | WU[vo][hdp]
@@ -27,9 +27,9 @@ GCP_HD float pack_G(const GcpOp& op, int idx) {
   const GcpW& W = op.w;
   if (idx < W.o_bg) {
     const int o = idx / W.ldg, n = idx - o * W.ldg;
-    return (o < op.vo && n < op.so) ? GCP_LDG(op.Wg + o * op.so + n) : 0.f;
+    return (o < op.vo && n < op.so && gcp_gated(op)) ? GCP_LDG(op.Wg + o * op.so + n) : 0.f;
   }
-  if (idx < W.o_wu) { const int o = idx - W.o_bg; return o < op.vo ? GCP_LDG(op.bg + o) : 0.f; }
+  if (idx < W.o_wu) { const int o = idx - W.o_bg; return (o < op.vo && gcp_gated(op)) ? GCP_LDG(op.bg + o) : 0.f; }
   const int r = idx - W.o_wu;
   const int o = r / W.hdp, k = r - o * W.hdp;
   return (o < op.vo && k < op.hd) ? GCP_LDG(op.Wu + o * op.hd + k) : 0.f;

@@ -74,6 +74,7 @@ inline TcPlan make_tc_plan(const gcpnet_layer& l, long long N, long long E) {
     g.si = d.si; g.vi = d.vi; g.so = d.so; g.vo = d.vo; g.hd = d.hd;
     g.act_s = d.act_s; g.vres = d.vector_residual;
     if (d.act_v != 0) return no("vector nonlinearity is not the identity (gate not composable)");
+    if (d.flags != 0) return no("GCP-Baseline variants (no frame scalars / no vector gate) run the FFMA edge kernels");
     if (d.hd < 1 || d.hd > NSLOT) return no("hidden vector width beyond 12");
     if (d.so != s || d.vo != v) return no("message GCP output dims differ from node dims");
     if (k == 0 && (d.si != 2 * s + se || d.vi != 2 * v + ve || d.vector_residual)) return no("unexpected message GCP 0 shape");

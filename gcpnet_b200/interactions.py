@@ -238,15 +238,18 @@ class GCP2Params(nn.Module):
     """Parameter holder for one GCP2 (gcpnet.py:298-322); construction order = the reference's, so the
     same torch seed gives the same initial weights."""
 
-    def __init__(self, si: int, vi: int, so: int, vo: int, hd: int):
+    def __init__(self, si: int, vi: int, so: int, vo: int, hd: int, flags: int = 0):
         super().__init__()
         self.dims = (si, vi, so, vo, hd)
+        frames = not (flags & _cabi.GCP2_NO_FRAMES)
         self.vector_down = nn.Linear(vi, hd, bias=False)
-        self.scalar_out = nn.Linear(hd + si + 9, so)
-        self.vector_down_frames = nn.Linear(vi, 3, bias=False)
+        self.scalar_out = nn.Linear(hd + si + (9 if frames else 0), so)
+        if frames:  # gcpnet.py:307-309
+            self.vector_down_frames = nn.Linear(vi, 3, bias=False)
         if vo:  # gcpnet.py:310-322: no vector_up / vector_out_scale without vector outputs
             self.vector_up = nn.Linear(hd, vo, bias=False)
-            self.vector_out_scale = nn.Linear(so, vo)
+            if not (flags & _cabi.GCP2_NO_GATE):
+                self.vector_out_scale = nn.Linear(so, vo)
 
     def forward(self, *a, **k):  # pragma: no cover
         raise RuntimeError("GCP2Params only holds parameters; the fused layer kernels evaluate it")
@@ -255,9 +258,9 @@ class GCP2Params(nn.Module):
 class _MessageParams(nn.Module):
     """``interaction.message_fusion.{k}`` of a GCPInteractions layer (the fused layer kernels evaluate the stack)."""
 
-    def __init__(self, mods):
+    def __init__(self, mods, flags: int = 0):
         super().__init__()
-        self.message_fusion = nn.ModuleList([GCP2Params(*m[1:6]) for m in mods])
+        self.message_fusion = nn.ModuleList([GCP2Params(*m[1:6], flags) for m in mods])
 
 
 class _LayerNormParams(nn.Module):
@@ -449,8 +452,10 @@ def _nonlinearities(cfg):
     return nl
 
 
-def _check_gcp_flags(cfg, who: str) -> None:
-    """Flag combinations of the reference's GCP2 the kernels do not cover raise (no eager fallback)."""
+def _check_gcp_flags(cfg, who: str) -> dict:
+    """Flag combinations of the reference's GCP2 the kernels do not cover raise (no eager fallback).  Returns the two
+    GCP-Baseline switches the kernels do cover -- what GCPNetCPDLitModule builds its decoder layers with
+    (gcpnet_cpd_module.py:95-97): ``ablate_frame_updates`` (no frame scalars) and ``vector_gate=False`` (ungated vectors)."""
     def unsupported(what):
         raise NotImplementedError(f"gcpnet_b200.{who}: {what} is not covered by the sm_100a kernels "
                                   "(and there is no eager fallback)")
@@ -458,14 +463,15 @@ def _check_gcp_flags(cfg, who: str) -> None:
     sel_name = getattr(getattr(sel, "func", sel), "__name__", None) or str(_get(sel, "_target_", "") or "")
     if sel is not None and sel_name and not sel_name.endswith("GCP2"):
         unsupported(f"selected_GCP={sel_name} (only GCP2)")
-    if not bool(_get(cfg, "vector_gate", True)):
-        unsupported("vector_gate=False")
+    vector_gate = bool(_get(cfg, "vector_gate", True))
+    if not vector_gate and _nonlinearities(cfg)[1] is not None:
+        unsupported("vector_gate=False with a vector nonlinearity (norm gating, gcpnet.py:349-350)")
     if int(_get(cfg, "scalar_gate", 0) or 0) > 0:
         unsupported("scalar_gate > 0")
-    for flag in ("frame_gate", "sigma_frame_gate", "vector_frame_residual", "ablate_frame_updates", "ablate_scalars",
-                 "ablate_vectors"):
+    for flag in ("frame_gate", "sigma_frame_gate", "vector_frame_residual", "ablate_scalars", "ablate_vectors"):
         if bool(_get(cfg, flag, False)):
             unsupported(f"cfg.{flag}=True")
+    return dict(ablate_frame_updates=bool(_get(cfg, "ablate_frame_updates", False)), vector_gate=vector_gate)
 
 
 class _SwappedViews:
@@ -554,7 +560,7 @@ class GCPMessagePassing(nn.Module):
         self.aggregate_with_row = bool(aggregate_with_row)
         if reduce_function not in ("mean", "add", "sum"):
             raise NotImplementedError(f"gcpnet_b200.GCPMessagePassing: reduce_function={reduce_function!r}")
-        _check_gcp_flags(cfg, "GCPMessagePassing")
+        variant = _check_gcp_flags(cfg, "GCPMessagePassing")
         self.node_dims = node_dims
         self.edge_dims = ScalarVector(int(edge_dims[0]), int(edge_dims[1]))
         self.reduce_function = reduce_function
@@ -566,12 +572,13 @@ class GCPMessagePassing(nn.Module):
             default_vector_residual=bool(_get(cfg, "default_vector_residual", False)),
             scalar_nonlinearity=nl[0], vector_nonlinearity=nl[1], nonlinearity_slope=float(nonlinearity_slope),
             use_residual_message_gcp=bool(_get(mp_cfg, "use_residual_message_gcp", True)),
-            enable_e3_equivariance=bool(_get(cfg, "enable_e3_equivariance", False)), reduce_function=reduce_function)
+            enable_e3_equivariance=bool(_get(cfg, "enable_e3_equivariance", False)), reduce_function=reduce_function,
+            **variant)
         for m in self.spec.message_mods:
             if not 1 <= m[5] <= 16:
                 raise NotImplementedError(f"gcpnet_b200.GCPMessagePassing: hidden vector dim {m[5]} (supported: 1..16)")
-        self.message_fusion = nn.ModuleList([GCP2Params(*m[1:6]) for m in self.spec.message_mods])
-        self._names = [n[len("interaction."):] for n in self.spec.names[:7 * self.spec.L]]
+        self.message_fusion = nn.ModuleList([GCP2Params(*m[1:6], self.spec.gcp_flags) for m in self.spec.message_mods])
+        self._names = [n[len("interaction."):] for n in self.spec.names if n.startswith("interaction.")]
         self._param_list = None
         self._struct_cache = None
 
@@ -651,7 +658,7 @@ class GCPInteractions(nn.Module):
             raise NotImplementedError(f"gcpnet_b200.GCPInteractions: {what} is not covered by the sm_100a kernels "
                                       "(and there is no eager fallback)")
 
-        _check_gcp_flags(cfg, "GCPInteractions")
+        variant = _check_gcp_flags(cfg, "GCPInteractions")
         if int(_get(layer_cfg, "num_feedforward_layers", 2)) != 2:
             unsupported("num_feedforward_layers != 2")
         if self.updating_node_positions and not self.ablate_x_force_update:
@@ -676,18 +683,18 @@ class GCPInteractions(nn.Module):
             enable_e3_equivariance=bool(_get(cfg, "enable_e3_equivariance", False)),
             reduce_function="add" if self.autoregressive else "mean",
             updating_node_positions=self.updating_node_positions, node_positions_weight=self.node_positions_weight,
-            pre_norm=self.pre_norm)
+            pre_norm=self.pre_norm, **variant)
         spec = self.spec
         for m in spec.message_mods + spec.ff_mods + ([spec.pos_mod] if spec.pos_mod else []):
             if not 1 <= m[5] <= 16:
                 unsupported(f"hidden vector dim {m[5]} of {m[0]} (supported: 1..16)")
 
         # parameters, in the reference's registration order and under its names
-        self.interaction = _MessageParams(spec.message_mods)
+        self.interaction = _MessageParams(spec.message_mods, spec.gcp_flags)
         self.gcp_norm = nn.ModuleList([_LayerNormParams(node_dims.scalar) for _ in range(2)])
-        self.feedforward_network = nn.ModuleList([GCP2Params(*m[1:6]) for m in spec.ff_mods])
+        self.feedforward_network = nn.ModuleList([GCP2Params(*m[1:6], spec.gcp_flags) for m in spec.ff_mods])
         if spec.pos_mod:
-            self.node_position_update_network = nn.ModuleList([GCP2Params(*spec.pos_mod[1:6])])
+            self.node_position_update_network = nn.ModuleList([GCP2Params(*spec.pos_mod[1:6], spec.gcp_flags)])
         self._param_list = None
         self._struct_cache = {}
         self._prepacked = None

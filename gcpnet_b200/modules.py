@@ -104,10 +104,15 @@ class GCP2(GCP2Params):
             self.acts = (_cabi._norm(nl[0]), _cabi._norm(nl[1]))
             self.slope = float(nonlinearity_slope)
             return
-        if scalar_gate or not vector_gate or frame_gate or sigma_frame_gate or vector_frame_residual:
-            unsupported("scalar_gate / frame gates / vector_gate=False")
-        if ablate_frame_updates or ablate_scalars or ablate_vectors or scalarization_vectorization_output_dim != 3:
-            unsupported("ablations")
+        if scalar_gate or frame_gate or sigma_frame_gate or vector_frame_residual:
+            unsupported("scalar_gate / frame gates")
+        if ablate_scalars or ablate_vectors or scalarization_vectorization_output_dim != 3:
+            unsupported("ablate_scalars / ablate_vectors")
+        nl = (None, None) if nonlinearities is None else nonlinearities
+        if not vector_gate and vo and _cabi._norm(nl[1]) is not None:
+            unsupported("vector_gate=False with a vector nonlinearity (norm gating, gcpnet.py:349-350)")
+        # GCP-Baseline variants (what the CPD decoder and its invariant projection are built with, gcpnet_cpd_module.py:95-97)
+        flags = _cabi.gcp2_flags(bool(ablate_frame_updates), bool(vector_gate))
         if bottleneck > 1 and vi % bottleneck != 0:
             raise AssertionError(f"Input channel of vector ({vi}) must be divisible with bottleneck factor ({bottleneck})")
         hd = _cabi.gcp2_hidden_dim(vi, vo, int(bottleneck))
@@ -115,14 +120,14 @@ class GCP2(GCP2Params):
             unsupported(f"hidden vector dim {hd} (supported: 1..16)")
         if so % 4:
             unsupported("scalar output dims that are not multiples of 4")
-        super().__init__(si, vi, so, vo, hd)
-        nl = (None, None) if nonlinearities is None else nonlinearities
+        super().__init__(si, vi, so, vo, hd, flags)
+        self.flags = flags
         self.acts = (_cabi.ACT[_cabi._norm(nl[0])], _cabi.ACT[_cabi._norm(nl[1])])
         self.vres, self.e3, self.slope = bool(vector_residual), bool(enable_e3_equivariance), float(nonlinearity_slope)
         self.scalar_input_dim, self.vector_input_dim, self.scalar_output_dim, self.vector_output_dim = si, vi, so, vo
         self._layout = {}
         off = 0
-        for name, shp in _cabi.gcp2_shapes(si, vi, so, vo, hd).items():
+        for name, shp in _cabi.gcp2_shapes(si, vi, so, vo, hd, flags).items():
             self._layout[name] = (off, shp)
             n = 1
             for d in shp:
@@ -145,6 +150,7 @@ class GCP2(GCP2Params):
         op = _cabi.Gcp2()
         op.si, op.vi, op.so, op.vo, op.hd = self.dims
         op.act_s, op.act_v, op.vector_residual = self.acts[0], self.acts[1], int(self.vres)
+        op.flags = self.flags
         for (name, (off, _)), ptr in zip(self._layout.items(), ptrs):
             setattr(op, _cabi._PTR_FIELD[name], ptr)
             op.grad_off[_cabi._GRAD_SLOT[name]] = off

@@ -35,6 +35,14 @@ enum gcpnet_act { GCPNET_ACT_NONE = 0, GCPNET_ACT_RELU = 1, GCPNET_ACT_LEAKYRELU
  * scalar_out.weight[so][si+hd+9] (+bias[so]), vector_up.weight[vo][hd],
  * vector_out_scale.weight[vo][so] (+bias[vo]).  grad_off[i] = offset (floats) of the i-th block's
  * gradient inside the layer's flat gradient, in the order listed. */
+/* gcpnet_gcp2.flags (the GCP-Baseline variants the CPD decoder is built with, gcpnet_cpd_module.py:95-97):
+ *   NO_FRAMES  ablate_frame_updates=True (gcpnet.py:302-309,424-437): no vector_down_frames, scalar_out reads [s | norms] only;
+ *   NO_GATE    vector_gate=False with an identity vector nonlinearity (gcpnet.py:344-350): V' = vector_up(H) (+ V), no
+ *              vector_out_scale.  The pointers (and gradient slots) of the absent parameters are ignored.
+ * Both run the FFMA tile kernels. */
+#define GCPNET_GCP2_NO_FRAMES 1
+#define GCPNET_GCP2_NO_GATE 2
+
 typedef struct gcpnet_gcp2 {
   int32_t si, vi, so, vo, hd;
   int32_t act_s, act_v, vector_residual;
@@ -46,7 +54,7 @@ typedef struct gcpnet_gcp2 {
   const float* vector_out_scale_w;
   const float* vector_out_scale_b;
   int32_t grad_off[7]; /* vector_down, vector_down_frames, scalar_out_w, scalar_out_b, vector_up, vector_out_scale_w, vector_out_scale_b */
-  int32_t reserved;
+  int32_t flags;       /* GCPNET_GCP2_NO_FRAMES | GCPNET_GCP2_NO_GATE */
 } gcpnet_gcp2;
 
 /* One GCPInteractions layer (gcpnet.py:963-1063): message stack, two LayerNorms, two feed-forward

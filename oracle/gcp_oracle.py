@@ -46,6 +46,7 @@ class OracleConfig:
     vector_residual: bool = False
     default_vector_residual: bool = False
     vector_gate: bool = True
+    ablate_frame_updates: bool = False  # GCP-Baseline (gcpnet.py:302-309,424-437): no frame scalars, no vector_down_frames
     enable_e3_equivariance: bool = False
     num_message_layers: int = 8
     use_residual_message_gcp: bool = True
@@ -188,14 +189,16 @@ def gcp2(p: Dict[str, Tensor], prefix: str, s: Tensor, V: Tensor, edge_index: Te
     """SURVEY Appendix A steps 1-11.  ``p[prefix + 'scalar_out.weight']`` etc.
     Returns (s', V') or s' if the module has no vector output (no ``vector_up``)."""
     Wd = p[prefix + "vector_down.weight"]  # [hd, vi]
-    Wdf = p[prefix + "vector_down_frames.weight"]  # [3, vi]
     Ws, bs = p[prefix + "scalar_out.weight"], p[prefix + "scalar_out.bias"]
     Vt = V.transpose(-1, -2)  # [M,3,vi]  (gcpnet.py:418)
     H = Vt @ Wd.t()  # [M,3,hd]  (:420)
     n = safe_norm(H, dim=-2)  # [M,hd]    (:421)
-    D = Vt @ Wdf.t()  # [M,3,3]   (:426)
-    q = frame_scalars(D, edge_index, frames, node_inputs, e3, V.shape[0], node_mask)  # (:427-435)
-    z = torch.cat((s, n, q), dim=-1)  # (:422,436)
+    z = torch.cat((s, n), dim=-1)  # (:422)
+    if (prefix + "vector_down_frames.weight") in p:  # absent with ablate_frame_updates (:307-309,424)
+        Wdf = p[prefix + "vector_down_frames.weight"]  # [3, vi]
+        D = Vt @ Wdf.t()  # [M,3,3]   (:426)
+        q = frame_scalars(D, edge_index, frames, node_inputs, e3, V.shape[0], node_mask)  # (:427-435)
+        z = torch.cat((z, q), dim=-1)  # (:436)
     t = z @ Ws.t() + bs  # (:441)
     if (prefix + "vector_up.weight") not in p:
         return act_s(t)  # (:443-446)
@@ -354,18 +357,21 @@ def interactions_forward(p: Dict[str, Tensor], cfg: OracleConfig, h: Tensor, chi
 # --------------------------------------------------------------------------------------
 # parameter construction with the reference's names and shapes
 # --------------------------------------------------------------------------------------
-def gcp2_param_shapes(si, vi, so, vo, bottleneck):
+def gcp2_param_shapes(si, vi, so, vo, bottleneck, frames: bool = True, gate: bool = True):
+    """gcpnet.py:298-322; `frames` = not ablate_frame_updates, `gate` = vector_gate."""
     hd = gcp2_hidden_dim(vi, vo, bottleneck)
     shapes = {
         "vector_down.weight": (hd, vi),
-        "scalar_out.weight": (so, si + hd + 9),
+        "scalar_out.weight": (so, si + hd + (9 if frames else 0)),
         "scalar_out.bias": (so,),
-        "vector_down_frames.weight": (3, vi),
     }
+    if frames:
+        shapes["vector_down_frames.weight"] = (3, vi)
     if vo:
         shapes["vector_up.weight"] = (vo, hd)
-        shapes["vector_out_scale.weight"] = (vo, so)
-        shapes["vector_out_scale.bias"] = (vo,)
+        if gate:
+            shapes["vector_out_scale.weight"] = (vo, so)
+            shapes["vector_out_scale.bias"] = (vo,)
     return shapes
 
 
@@ -374,6 +380,7 @@ def layer_param_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
     se, ve = cfg.edge_dims
     L = cfg.num_message_layers
     out: Dict[str, Tuple[int, ...]] = {}
+    var = dict(frames=not cfg.ablate_frame_updates, gate=cfg.vector_gate)
 
     def add(prefix, shapes):
         for k, shp in shapes.items():
@@ -383,9 +390,9 @@ def layer_param_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
         primary = k == 0 or k == L - 1
         bn = cfg.default_bottleneck if primary else cfg.bottleneck
         if k == 0:
-            add("interaction.message_fusion.0.", gcp2_param_shapes(2 * s + se, 2 * v + ve, s, v, bn))
+            add("interaction.message_fusion.0.", gcp2_param_shapes(2 * s + se, 2 * v + ve, s, v, bn, **var))
         else:
-            add(f"interaction.message_fusion.{k}.", gcp2_param_shapes(s, v, s, v, bn))
+            add(f"interaction.message_fusion.{k}.", gcp2_param_shapes(s, v, s, v, bn, **var))
     for i in range(2):
         out[f"gcp_norm.{i}.scalar_norm.weight"] = (s,)
         out[f"gcp_norm.{i}.scalar_norm.bias"] = (s,)
@@ -393,9 +400,9 @@ def layer_param_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
     hid = (4 * s, 2 * v)
     dims = [(s, v)] + [hid] * (cfg.num_feedforward_layers - 1) + [(s, v)]
     for i in range(cfg.num_feedforward_layers):
-        add(f"feedforward_network.{i}.", gcp2_param_shapes(*dims[i], *dims[i + 1], cfg.bottleneck))
+        add(f"feedforward_network.{i}.", gcp2_param_shapes(*dims[i], *dims[i + 1], cfg.bottleneck, **var))
     if cfg.updating_node_positions:
-        add("node_position_update_network.0.", gcp2_param_shapes(s, v, s, 1, cfg.bottleneck))
+        add("node_position_update_network.0.", gcp2_param_shapes(s, v, s, 1, cfg.bottleneck, **var))
     return out
 
 

@@ -71,6 +71,18 @@ CASES: Dict[str, dict] = {
                              enable_e3_equivariance=True, updating_node_positions=True), graph=("random", 18, 80), seed=25),
     "lba_e3_knn": dict(cfg=dict(node_dims=(100, 16), edge_dims=(32, 4), enable_e3_equivariance=True, scalar_nonlinearity="silu"),
                        graph=("knn", 2, 24, 6), seed=26),
+    # GCP-Baseline variants: what GCPNetCPDLitModule builds its decoder layers with (gcpnet_cpd_module.py:95-97:
+    # vector_gate = frame_gate = False, ablate_frame_updates = True) -- no frame scalars, no vector_out_scale, V' = vector_up(H)
+    "cpd_decoder_variant": dict(cfg=dict(node_dims=(100, 16), edge_dims=(32, 4), num_message_layers=4, reduce_function="add",
+                                         vector_gate=False, ablate_frame_updates=True),
+                                graph=("knn", 2, 24, 6), seed=27, autoregressive=True, regressive=True, mask_frac=0.1),
+    "tiny_no_frame_scalars": dict(cfg=dict(node_dims=(16, 4), edge_dims=(8, 2), num_message_layers=2, bottleneck=2,
+                                           default_bottleneck=2, ablate_frame_updates=True, updating_node_positions=True),
+                                  graph=("random", 14, 50), seed=28),
+    "tiny_no_vector_gate": dict(cfg=dict(node_dims=(16, 4), edge_dims=(8, 2), num_message_layers=3, bottleneck=2,
+                                         default_bottleneck=2, vector_gate=False, vector_residual=True,
+                                         updating_node_positions=True),
+                                graph=("random", 14, 50), seed=29),
     "tiny_pre_norm_masked": dict(cfg=dict(node_dims=(16, 4), edge_dims=(8, 2), num_message_layers=2, bottleneck=2,
                                           default_bottleneck=2, pre_norm=True), graph=("random", 15, 60), seed=24,
                                  mask_frac=0.25),

@@ -41,7 +41,8 @@ def run_reference(name: str, case: dict):
         scalar_nonlinearity=cfg.scalar_nonlinearity, vector_nonlinearity=cfg.vector_nonlinearity,
         bottleneck=cfg.bottleneck, vector_residual=cfg.vector_residual,
         enable_e3_equivariance=cfg.enable_e3_equivariance,
-        use_residual_message_gcp=cfg.use_residual_message_gcp)
+        use_residual_message_gcp=cfg.use_residual_message_gcp,
+        vector_gate=cfg.vector_gate, ablate_frame_updates=cfg.ablate_frame_updates)
     rcfg.default_bottleneck = cfg.default_bottleneck
     SV = ref.ScalarVector
     layer = ref.GCPInteractions(SV(*cfg.node_dims), SV(*cfg.edge_dims), cfg=rcfg, layer_cfg=rlayer,

@@ -174,17 +174,18 @@ def load_reference():
 
 def make_cfgs(ref, *, num_message_layers=8, pre_norm=False, num_feedforward_layers=2,
               scalar_nonlinearity="relu", vector_nonlinearity=None, bottleneck=4,
-              vector_residual=False, enable_e3_equivariance=False, use_residual_message_gcp=True):
+              vector_residual=False, enable_e3_equivariance=False, use_residual_message_gcp=True,
+              vector_gate=True, ablate_frame_updates=False):
     """cfg / layer_cfg mirroring configs/model/module_cfg/gcp_module_nms.yaml:1-37,
     layer_cfg/gcp_interaction_layer_nms.yaml:1-8 and mp_cfg/gcp_mp_nms.yaml:1-7."""
     cfg = AttrDict(
-        selected_GCP=ref.GCP2, norm_x_diff=True, scalar_gate=0, vector_gate=True,
+        selected_GCP=ref.GCP2, norm_x_diff=True, scalar_gate=0, vector_gate=vector_gate,
         vector_residual=vector_residual, vector_frame_residual=False, frame_gate=False,
         sigma_frame_gate=False, scalar_nonlinearity=scalar_nonlinearity,
         vector_nonlinearity=vector_nonlinearity,
         nonlinearities=[scalar_nonlinearity, vector_nonlinearity], bottleneck=bottleneck,
         vector_linear=True, vector_identity=True, default_vector_residual=False,
-        default_bottleneck=bottleneck, node_positions_weight=1.0, ablate_frame_updates=False,
+        default_bottleneck=bottleneck, node_positions_weight=1.0, ablate_frame_updates=ablate_frame_updates,
         ablate_scalars=False, ablate_vectors=False, ablate_x_force_update=True,
         enable_e3_equivariance=enable_e3_equivariance,
     )

@@ -55,7 +55,8 @@ def spec_from_oracle_cfg(cfg) -> _cabi.LayerSpec:
         vector_nonlinearity=cfg.vector_nonlinearity, nonlinearity_slope=cfg.nonlinearity_slope,
         use_residual_message_gcp=cfg.use_residual_message_gcp, enable_e3_equivariance=cfg.enable_e3_equivariance,
         reduce_function=cfg.reduce_function, updating_node_positions=cfg.updating_node_positions,
-        node_positions_weight=cfg.node_positions_weight, pre_norm=cfg.pre_norm)
+        node_positions_weight=cfg.node_positions_weight, pre_norm=cfg.pre_norm,
+        ablate_frame_updates=cfg.ablate_frame_updates, vector_gate=cfg.vector_gate)
 
 
 class EmulLayer:

@@ -106,7 +106,7 @@ def module_cfgs(cfg):
         nonlinearities=[cfg.scalar_nonlinearity, cfg.vector_nonlinearity], bottleneck=cfg.bottleneck,
         vector_linear=True, vector_identity=True, default_vector_residual=cfg.default_vector_residual,
         default_bottleneck=cfg.default_bottleneck, node_positions_weight=cfg.node_positions_weight,
-        ablate_frame_updates=False, ablate_scalars=False, ablate_vectors=False, ablate_x_force_update=True,
+        ablate_frame_updates=cfg.ablate_frame_updates, ablate_scalars=False, ablate_vectors=False, ablate_x_force_update=True,
         enable_e3_equivariance=cfg.enable_e3_equivariance)
     mp = AttrDict(edge_encoder=False, edge_gate=False, num_message_layers=cfg.num_message_layers, message_residual=0,
                   message_ff_multiplier=1, self_message=True, use_residual_message_gcp=cfg.use_residual_message_gcp)

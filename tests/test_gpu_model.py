@@ -89,6 +89,48 @@ def test_gcp2_scalar_only_output_and_scalar_only_input():
     assert float(vo.abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("vector_gate,ablate,dims", [(False, True, ((100, 16), (20, 0))), (False, True, ((100, 16), (100, 16))),
+                                                     (True, True, ((64, 16), (64, 16))), (False, False, ((64, 16), (32, 8)))])
+def test_gcp2_baseline_variants_match_oracle(vector_gate, ablate, dims):
+    """GCP-Baseline switches of GCP2: ablate_frame_updates (scalar_out reads [s | norms] only, gcpnet.py:302-309,424-437) and
+    vector_gate=False (V' = vector_up(H), gcpnet.py:344-350) -- what GCPNetCPDLitModule builds its decoder layers and its
+    invariant node projection (100, 16) -> (20, 0) with (gcpnet_cpd_module.py:95-97,114-127)."""
+    import gcpnet_b200
+    (si, vi), (so, vo) = dims
+    g = torch.Generator().manual_seed(430)
+    n, E = 77, 500
+    ei = torch.randint(0, n, (2, E), generator=g)
+    frames = O.localize(torch.randn(n, 3, generator=g), ei)
+    torch.manual_seed(431)
+    mod = gcpnet_b200.GCP2((si, vi), (so, vo), nonlinearities=("silu", None), bottleneck=4, vector_gate=vector_gate,
+                           ablate_frame_updates=ablate).cuda()
+    keys = set(mod.state_dict())
+    assert ("vector_down_frames.weight" in keys) == (not ablate)
+    assert ("vector_out_scale.weight" in keys) == (vector_gate and vo > 0)
+    assert mod.scalar_out.weight.shape[1] == si + vi // 4 + (0 if ablate else 9)
+    s_in, v_in = torch.randn(n, si, generator=g), torch.randn(n, vi, 3, generator=g)
+    p = {k: v.clone().requires_grad_(True) for k, v in _gcp2_params(mod).items()}
+    ls, lv = s_in.clone().requires_grad_(True), v_in.clone().requires_grad_(True)
+    want = O.gcp2(p, "m.", ls, lv, ei, frames, node_inputs=True, act_s=O.activation("silu"), act_v=O.activation(None),
+                  vector_residual=False, e3=False, vector_gate=vector_gate)
+    ds, dv = s_in.cuda().requires_grad_(True), v_in.cuda().requires_grad_(True)
+    out = mod((ds, dv), ei.cuda(), frames.cuda(), node_inputs=True)
+    cs = torch.randn(n, so, generator=g)
+    if vo:
+        cv = torch.randn(n, vo, 3, generator=g)
+        ((want[0] * cs).sum() + (want[1] * cv).sum()).backward()
+        ((out[0] * cs.cuda()).sum() + (out[1] * cv.cuda()).sum()).backward()
+        assert rel_err(out[0].detach().cpu().numpy(), want[0].detach().numpy()) < TOL
+        assert rel_err(out[1].detach().cpu().numpy(), want[1].detach().numpy()) < TOL
+    else:
+        (want * cs).sum().backward()
+        (out * cs.cuda()).sum().backward()
+        assert rel_err(out.detach().cpu().numpy(), want.detach().numpy()) < TOL
+    assert rel_err(ds.grad.cpu().numpy(), ls.grad.numpy()) < TOL and rel_err(dv.grad.cpu().numpy(), lv.grad.numpy()) < TOL
+    for k, t in mod.named_parameters():
+        assert rel_err(t.grad.cpu().numpy(), p["m." + k].grad.numpy()) < TOL, k
+
+
 @pytest.mark.parametrize("dims", [(17, 1), (1, 3), (64, 16), (100, 0)])
 def test_layernorm_alone_matches_oracle(dims):
     """GCPLayerNorm (comp/__init__.py:138-167), including a one-element scalar LayerNorm and the scalar-only form."""

@@ -78,11 +78,22 @@ def test_unsupported_configurations_raise():
     import gcpnet_b200
     cfg = O.OracleConfig()
     mcfg, lcfg = module_cfgs(cfg)
-    for key in ("frame_gate", "ablate_frame_updates", "ablate_scalars"):
+    for key in ("frame_gate", "ablate_scalars", "vector_frame_residual"):
         bad = type(mcfg)(mcfg)
         bad[key] = True
         with pytest.raises(NotImplementedError):
             gcpnet_b200.GCPInteractions((64, 16), (32, 4), cfg=bad, layer_cfg=lcfg)
+    # the CPD decoder's GCP-Baseline variant constructs (gcpnet_cpd_module.py:95-97) with the reference's parameter set ...
+    dec = type(mcfg)(mcfg)
+    dec["vector_gate"], dec["ablate_frame_updates"] = False, True
+    layer = gcpnet_b200.GCPInteractions((100, 16), (32, 4), cfg=dec, layer_cfg=lcfg, autoregressive=True)
+    names = [k for k, _ in layer.named_parameters()]
+    assert not any("vector_down_frames" in k or "vector_out_scale" in k for k in names)
+    assert tuple(layer.interaction.message_fusion[1].scalar_out.weight.shape) == (100, 100 + 4)
+    # ... ungated vectors with a vector nonlinearity (norm gating) do not
+    dec["nonlinearities"] = ["relu", "sigmoid"]
+    with pytest.raises(NotImplementedError):
+        gcpnet_b200.GCPInteractions((100, 16), (32, 4), cfg=dec, layer_cfg=lcfg)
     # autoregressive and pre_norm layers construct (round 2); their combination does not
     ar = gcpnet_b200.GCPInteractions((64, 16), (32, 4), cfg=mcfg, layer_cfg=lcfg, autoregressive=True)
     assert ar.spec.reduce_mean is False  # reduce_function = "add" (gcpnet.py:984)
