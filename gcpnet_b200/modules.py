@@ -337,3 +337,94 @@ class GCPNetNMS(nn.Module):
         batch.h, batch.chi, batch.e, batch.xi = h, chi, e, xi
         batch.x = decentralize(batch, "x", batch.batch, x_centroid)
         return batch, batch.x
+
+
+# ------------------------------------------------------------------------------------------
+# the CPD model's forward(batch) (src/models/gcpnet_cpd_module.py:43-246)
+# ------------------------------------------------------------------------------------------
+class GCPMLPDecoder(nn.Module):
+    """``GCPMLPDecoder`` (gcpnet.py:1454-1491): the dense read-out over invariant node features, ``(logits, log_probs)``.
+    Plain ``nn.Linear`` layers -- library GEMMs, exactly the reference's own ops (a task head, not part of the hot path)."""
+
+    def __init__(self, hidden_dim: int, vocab_size: int = 20, num_layers: int = 1, residual_updates: bool = False):
+        super().__init__()
+        self.residual_updates = bool(residual_updates)
+        layers = [nn.Linear(hidden_dim, hidden_dim) for _ in range(num_layers - 1)] + [nn.Linear(hidden_dim, vocab_size)]
+        self.readout = nn.ModuleList(layers) if self.residual_updates else nn.Sequential(*layers)
+
+    def forward(self, h):
+        if self.residual_updates:
+            for layer in self.readout[:-1]:
+                h = h + layer(h)
+            logits = self.readout[-1](h)
+        else:
+            logits = self.readout(h)
+        return logits, torch.nn.functional.log_softmax(logits, dim=-1)
+
+
+class GCPNetCPD(nn.Module):
+    """Modules and ``forward(batch)`` of ``GCPNetCPDLitModule`` (gcpnet_cpd_module.py:43-132,178-246) under the same attribute
+    names (the shipped checkpoint's ``state_dict`` loads with ``strict=True``): masked centralize -> masked localize ->
+    GCPEmbedding -> encoder GCPInteractions layers under the node mask -> (``autoregressive_decoder``: sequence embedding on
+    the ``row < col`` edges, autoregressive GCP-Baseline decoder layers) -> invariant node projection (-> dense decoder).
+    Like the reference's constructor (:95-97), ``autoregressive_decoder=True`` rewrites ``module_cfg`` in place before the
+    decoder layers and the projection are built: ``vector_gate = frame_gate``, ``frame_gate = False``,
+    ``ablate_frame_updates = True``."""
+
+    def __init__(self, node_input_dims, edge_input_dims, model_cfg, module_cfg, layer_cfg, dropout: float = 0.1,
+                 autoregressive_decoder: bool = False):
+        super().__init__()
+        self.node_dims = ScalarVector(_get(model_cfg, "h_hidden_dim"), _get(model_cfg, "chi_hidden_dim"))
+        self.edge_dims = ScalarVector(_get(model_cfg, "e_hidden_dim"), _get(model_cfg, "xi_hidden_dim"))
+        edge_hidden_dims = ScalarVector(self.edge_dims[0] + 20, self.edge_dims[1])
+        out_dim = int(_get(model_cfg, "output_dim"))
+        self.autoregressive_decoder = bool(autoregressive_decoder)
+        self.norm_x_diff = bool(_get(module_cfg, "norm_x_diff", True))
+        self.gcp_embedding = GCPEmbedding(edge_input_dims, node_input_dims, self.edge_dims, self.node_dims, num_atom_types=0,
+                                          cfg=module_cfg, pre_norm=False)
+        self.encoder_layers = nn.ModuleList(
+            GCPInteractions(self.node_dims, self.edge_dims, cfg=module_cfg, layer_cfg=layer_cfg, dropout=dropout)
+            for _ in range(int(_get(model_cfg, "num_encoder_layers"))))
+        if self.autoregressive_decoder:
+            module_cfg["vector_gate"] = _get(module_cfg, "frame_gate", False)
+            module_cfg["frame_gate"] = False
+            module_cfg["ablate_frame_updates"] = True
+            self.atom_embedding = nn.Embedding(out_dim, out_dim)
+            self.decoder_layers = nn.ModuleList(
+                GCPInteractions(self.node_dims, edge_hidden_dims, cfg=module_cfg, layer_cfg=layer_cfg, dropout=dropout,
+                                autoregressive=True)
+                for _ in range(int(_get(model_cfg, "num_decoder_layers"))))
+        proj_dim = out_dim if self.autoregressive_decoder else self.node_dims[0]
+        self.invariant_node_projection = GCP2(
+            self.node_dims, (proj_dim, 0), nonlinearities=(None, None), scalar_gate=_get(module_cfg, "scalar_gate", 0),
+            vector_gate=_get(module_cfg, "vector_gate", True), frame_gate=_get(module_cfg, "frame_gate", False),
+            sigma_frame_gate=_get(module_cfg, "sigma_frame_gate", False),
+            vector_frame_residual=_get(module_cfg, "vector_frame_residual", False),
+            ablate_frame_updates=_get(module_cfg, "ablate_frame_updates", False),
+            ablate_scalars=_get(module_cfg, "ablate_scalars", False), ablate_vectors=_get(module_cfg, "ablate_vectors", False),
+            enable_e3_equivariance=_get(module_cfg, "enable_e3_equivariance", False))
+        if not self.autoregressive_decoder:
+            self.decoder = GCPMLPDecoder(proj_dim, vocab_size=out_dim, num_layers=int(_get(model_cfg, "num_decoder_layers")),
+                                         residual_updates=bool(_get(model_cfg, "decoder_residual_updates", False)))
+
+    def forward(self, batch):
+        mask = batch.mask
+        _, batch.x = centralize(batch, "x", batch.batch, node_mask=mask, num_graphs=getattr(batch, "num_graphs", None))
+        batch.f_ij = localize(batch.x, batch.edge_index, norm_x_diff=self.norm_x_diff, node_mask=mask)
+        (h, chi), (e, xi) = self.gcp_embedding(batch)
+        for layer in self.encoder_layers:
+            h, chi = layer((h, chi), (e, xi), batch.edge_index, batch.f_ij, node_mask=mask)
+        if self.autoregressive_decoder:
+            encoder_embedding = (h, chi)
+            row, col = batch.edge_index[0], batch.edge_index[1]
+            # the sequence is visible along edges from earlier residues only (gcpnet_cpd_module.py:200-204)
+            seq = self.atom_embedding(batch.seq)[row] * (row < col).unsqueeze(-1).to(e.dtype)
+            e = torch.cat((e, seq), dim=-1)
+            for layer in self.decoder_layers:
+                h, chi = layer((h, chi), (e, xi), batch.edge_index, batch.f_ij, node_rep_regressive=encoder_embedding,
+                               node_mask=mask)
+        batch.h, batch.chi, batch.e, batch.xi = h, chi, e, xi
+        out = self.invariant_node_projection((h, chi), batch.edge_index, batch.f_ij, node_inputs=True, node_mask=mask)
+        if not self.autoregressive_decoder:
+            out = self.decoder(out)
+        return batch, out

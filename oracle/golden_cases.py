@@ -11,6 +11,7 @@ from __future__ import annotations
 import os
 from typing import Dict
 
+import numpy as np
 import torch
 
 from . import gcp_oracle as O
@@ -199,3 +200,67 @@ def nms_raw_batch(num_graphs: int = 6, n: int = 5, seed: int = 31):
     del idx
     return dict(h=vel.norm(dim=-1, keepdim=True), chi=chi, e=e, xi=xi, x=x, edge_index=ei, batch=batch,
                 label=x + vel + 0.1 * torch.randn(N, 3, generator=g))
+
+
+# ------------------------------------------------------------------------------------------
+# whole-model cases: GCPNetCPDLitModule.forward(batch)
+# ------------------------------------------------------------------------------------------
+CPD_CKPT = ("checkpoints/CPD/model_epoch_735_shortppl_8_22_singlechainppl_8_60_allppl_6_06_shortrecov_33_33_"
+            "singlechainrecov_32_86_allrecov_40_32.ckpt")
+# the shipped (direct-shot) model cut to its first two encoder layers -- the fixture carries the trained weights it uses
+CPD_CKPT_FIXTURE, CPD_CKPT_ENCODER_LAYERS = "cpd_ckpt_model", 2
+# autoregressive decoder (GCP-Baseline decoder layers), seeded weights, 2 + 2 layers
+CPD_AR_FIXTURE, CPD_AR_LAYERS = "cpd_ar_model", (2, 2)
+
+
+def cpd_raw_batch(num_graphs: int = 2, n: int = 40, k: int = 8, seed: int = 41):
+    """Raw CPD inputs in the shapes of configs/model/gcpnet_cpd.yaml (node_input_dims [6, 3], edge_input_dims [32, 1]):
+    h = sin/cos of three dihedral-like angles [N,6], chi = three unit-ish orientation vectors [N,3,3], e = 16 RBFs of the
+    distance + 16 positional encodings of the sequence offset [E,32], xi = unit direction [E,1,3], x = backbone-like random
+    walk, seq = residue ids, mask = residues with coordinates (a few masked out), kNN edges by destination."""
+    g = torch.Generator().manual_seed(seed)
+    N = num_graphs * n
+    step = torch.randn(num_graphs, n, 3, generator=g)
+    x = (3.8 * step / step.norm(dim=-1, keepdim=True)).cumsum(dim=1) * 0.6
+    d = torch.cdist(x, x) + torch.eye(n).unsqueeze(0) * 1e9
+    nbr = d.topk(k, dim=-1, largest=False).indices  # [G, n, k] sources of each destination
+    dst = torch.arange(n).view(1, n, 1).expand(num_graphs, n, k)
+    off = (torch.arange(num_graphs) * n).view(num_graphs, 1, 1)
+    ei = torch.stack(((nbr + off).reshape(-1), (dst + off).reshape(-1)))
+    x = x.reshape(N, 3) + torch.randn(num_graphs, 1, 3, generator=g).repeat_interleave(n, 0).reshape(N, 3) * 5.0
+    row, col = ei
+    dv = x[row] - x[col]
+    dist = dv.norm(dim=-1, keepdim=True)
+    mu = torch.linspace(0.0, 20.0, 16).view(1, -1)
+    rbf = torch.exp(-((dist - mu) / (20.0 / 16)) ** 2)
+    freq = torch.exp(torch.arange(0, 16, 2).float() * -(np.log(10000.0) / 16))
+    ang = (row - col).float().unsqueeze(-1) * freq
+    e = torch.cat((rbf, torch.cos(ang), torch.sin(ang)), dim=-1)
+    xi = (dv / dist.clamp(min=1e-8)).unsqueeze(1)
+    phi = torch.rand(N, 3, generator=g) * 6.2831853 - 3.14159265
+    h = torch.cat((torch.cos(phi), torch.sin(phi)), dim=-1)
+    chi = torch.randn(N, 3, 3, generator=g)
+    chi = chi / chi.norm(dim=-1, keepdim=True)
+    mask = torch.rand(N, generator=g) >= 0.08
+    mask[3], mask[4] = False, True
+    return dict(h=h, chi=chi, e=e, xi=xi, x=x, edge_index=ei, batch=torch.arange(num_graphs).repeat_interleave(n),
+                seq=torch.randint(0, 20, (N,), generator=g), mask=mask)
+
+
+def seeded_state_dict(shapes, seed: int):
+    """Deterministic weights for a name -> shape table (names visited in sorted order): LayerNorm weights near 1, biases small,
+    matrices uniform in +-1/sqrt(fan_in), embeddings standard normal."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for name in sorted(shapes):
+        shp = tuple(shapes[name])
+        if "scalar_norm.weight" in name:
+            t = 1 + 0.1 * torch.randn(shp, generator=g)
+        elif name.endswith(".bias"):
+            t = 0.1 * torch.randn(shp, generator=g)
+        elif "atom_embedding" in name:
+            t = torch.randn(shp, generator=g)
+        else:
+            t = (torch.rand(shp, generator=g) * 2 - 1) / (shp[-1] ** 0.5)
+        out[name] = t
+    return out

@@ -125,16 +125,53 @@ def run_nms_model():
     print(f"{GC.NMS_MODEL_FIXTURE}: loss={loss.item():.6f} -> {GC.fixture_path(GC.NMS_MODEL_FIXTURE)}")
 
 
+def run_cpd_model(name: str):
+    """GCPNetCPDLitModule.forward(batch) + cross-entropy on the unmasked residues (training_step, gcpnet_cpd_module.py:248-251),
+    eval mode, through the reference's own LightningModule class: the shipped direct-shot checkpoint cut to its first encoder
+    layers (trained weights), and the autoregressive-decoder variant with seeded weights."""
+    ref, Lit = ref_shim.load_cpd_litmodule()
+    ar = name == GC.CPD_AR_FIXTURE
+    n_enc, n_dec = GC.CPD_AR_LAYERS if ar else (GC.CPD_CKPT_ENCODER_LAYERS, 3)
+    model_cfg, module_cfg, layer_cfg = ref_shim.cpd_model_cfgs(ref, n_enc, n_dec)
+    lit = Lit(layer_class=ref.GCPInteractions, optimizer=None, scheduler=None, node_input_dims=[6, 3], edge_input_dims=[32, 1],
+              model_cfg=model_cfg, module_cfg=module_cfg, layer_cfg=layer_cfg, autoregressive_decoder=ar)
+    if ar:
+        sd = GC.seeded_state_dict({k: v.shape for k, v in lit.state_dict().items()}, seed=51)
+    else:
+        full = ref_shim.load_checkpoint_state_dict(GC.CPD_CKPT)
+        keep = lambda k: not k.startswith("encoder_layers.") or int(k.split(".")[1]) < n_enc
+        sd = {k: v.float() for k, v in full.items() if keep(k)}
+    lit.load_state_dict(sd, strict=True)
+    lit.eval()
+    raw = GC.cpd_raw_batch()
+    b = GC.Bag(**{k: v.clone() for k, v in raw.items()})
+    _, out = lit.forward(b)
+    logits = out if ar else out[0]
+    loss = torch.nn.functional.cross_entropy(logits[raw["mask"]], raw["seq"][raw["mask"]])
+    loss.backward()
+    rec = {"logits": logits.detach().numpy(), "loss": np.float64(loss.item()), "out_h": b.h.detach().numpy(),
+           "out_chi": b.chi.detach().numpy()}
+    for k, p in lit.named_parameters():
+        rec["pgrad/" + k] = sample(p.grad if p.grad is not None else torch.zeros_like(p))
+    if not ar:
+        for k, v in sd.items():
+            rec["param/" + k] = v.numpy()
+    np.savez_compressed(GC.fixture_path(name), **rec)
+    print(f"{name}: loss={loss.item():.6f} params={sum(v.numel() for v in sd.values())} -> {GC.fixture_path(name)}")
+
+
 def main(argv):
     if not ref_shim.reference_available():
         print("reference tree not available; nothing generated", file=sys.stderr)
         return 1
     torch.manual_seed(0)
     torch.set_num_threads(1)  # bitwise reproducible reductions
-    names = argv[1:] or (list(GC.CASES) + [GC.NMS_MODEL_FIXTURE])
+    names = argv[1:] or (list(GC.CASES) + [GC.NMS_MODEL_FIXTURE, GC.CPD_CKPT_FIXTURE, GC.CPD_AR_FIXTURE])
     for name in names:
         if name == GC.NMS_MODEL_FIXTURE:
             run_nms_model()
+        elif name in (GC.CPD_CKPT_FIXTURE, GC.CPD_AR_FIXTURE):
+            run_cpd_model(name)
         else:
             run_reference(name, GC.CASES[name])
     return 0

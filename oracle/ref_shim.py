@@ -124,7 +124,7 @@ def load_reference():
     mod("torch_scatter", scatter=_scatter)
     tg = mod("torch_geometric")
     tg.data = mod("torch_geometric.data", Batch=_Bag, Data=_Bag)
-    tg.utils = mod("torch_geometric.utils", subgraph=_subgraph)
+    tg.utils = mod("torch_geometric.utils", subgraph=_subgraph, unbatch=None)  # unbatch: only the CPD sampling loop calls it
     mod("torchtyping", TensorType=_TensorType, patch_typeguard=lambda: None)
     mod("typeguard", typechecked=lambda f=None, **kw: f if f is not None else (lambda g: g))
     mod("omegaconf", DictConfig=AttrDict, OmegaConf=types.SimpleNamespace(
@@ -200,6 +200,25 @@ def make_cfgs(ref, *, num_message_layers=8, pre_norm=False, num_feedforward_laye
 def load_nms_litmodule():
     """The reference's own ``GCPNetNMSLitModule`` class (src/models/gcpnet_nms_module.py), imported unmodified under stubs
     for pytorch_lightning (LightningModule = nn.Module + save_hyperparameters) and torchmetrics (inert metric modules)."""
+    return _load_litmodule("src.models.gcpnet_nms_module", "GCPNetNMSLitModule")
+
+
+def load_cpd_litmodule():
+    """The reference's own ``GCPNetCPDLitModule`` class (src/models/gcpnet_cpd_module.py), imported the same way."""
+    return _load_litmodule("src.models.gcpnet_cpd_module", "GCPNetCPDLitModule")
+
+
+def cpd_model_cfgs(ref, num_encoder_layers=9, num_decoder_layers=3):
+    """configs/model/gcpnet_cpd.yaml + model_cfg/gcp_model_cpd.yaml + module_cfg/gcp_module_cpd.yaml +
+    layer_cfg/gcp_interaction_layer_cpd.yaml (+ mp_cfg/gcp_mp_cpd.yaml)."""
+    module_cfg, layer_cfg = make_cfgs(ref)
+    model_cfg = AttrDict(h_input_dim=6, chi_input_dim=2, e_input_dim=16, xi_input_dim=1, h_hidden_dim=100, chi_hidden_dim=16,
+                         e_hidden_dim=32, xi_hidden_dim=4, output_dim=20, num_encoder_layers=num_encoder_layers,
+                         num_decoder_layers=num_decoder_layers, dropout=0.2, decoder_residual_updates=True)
+    return model_cfg, module_cfg, layer_cfg
+
+
+def _load_litmodule(module_name: str, class_name: str):
     import importlib
     import torch.nn as nn
     ref = load_reference()
@@ -224,18 +243,18 @@ def load_nms_litmodule():
         return m
 
     mod("pytorch_lightning", LightningModule=_LightningModule)
-    tm = mod("torchmetrics", MeanMetric=_Metric, MinMetric=_Metric, MaxMetric=_Metric, CosineSimilarity=_Metric)
+    tm = mod("torchmetrics", MeanMetric=_Metric, MinMetric=_Metric, MaxMetric=_Metric, CosineSimilarity=_Metric, CatMetric=_Metric)
     tm.regression = mod("torchmetrics.regression")
     tm.regression.mse = mod("torchmetrics.regression.mse", MeanSquaredError=_Metric)
     saved = sys.modules.get("typeguard")
     sys.modules["typeguard"] = types.ModuleType("typeguard")
     sys.modules["typeguard"].typechecked = lambda f=None, **kw: f if f is not None else (lambda g: g)
     try:
-        m = importlib.import_module("src.models.gcpnet_nms_module")
+        m = importlib.import_module(module_name)
     finally:
         if saved is not None:
             sys.modules["typeguard"] = saved
-    return ref, m.GCPNetNMSLitModule
+    return ref, getattr(m, class_name)
 
 
 def nms_model_cfgs(ref):

@@ -224,3 +224,61 @@ def test_nms_model_forward_backward_matches_the_reference_litmodule_on_the_shipp
         # trained ReLU weights: a few gradient tensors are tiny sums over 30 nodes; hold every tensor to 1e-3 and the bulk to 1e-4
         assert err < 1e-3, (k, err)
     assert worst < 1e-3
+
+
+def _cpd_model(n_enc, n_dec, autoregressive_decoder):
+    import gcpnet_b200
+    model_cfg = AttrDict(h_input_dim=6, chi_input_dim=2, e_input_dim=16, xi_input_dim=1, h_hidden_dim=100, chi_hidden_dim=16,
+                         e_hidden_dim=32, xi_hidden_dim=4, output_dim=20, num_encoder_layers=n_enc, num_decoder_layers=n_dec,
+                         dropout=0.2, decoder_residual_updates=True)
+    module_cfg = AttrDict(norm_x_diff=True, scalar_gate=0, vector_gate=True, vector_residual=False, vector_frame_residual=False,
+                          frame_gate=False, sigma_frame_gate=False, scalar_nonlinearity="relu", vector_nonlinearity=None,
+                          nonlinearities=["relu", None], bottleneck=4, vector_linear=True, vector_identity=True,
+                          default_vector_residual=False, default_bottleneck=4, ablate_frame_updates=False, ablate_scalars=False,
+                          ablate_vectors=False, enable_e3_equivariance=False)
+    mp = AttrDict(edge_encoder=False, edge_gate=False, num_message_layers=8, message_residual=0, message_ff_multiplier=1,
+                  self_message=True, use_residual_message_gcp=True)
+    layer_cfg = AttrDict(pre_norm=False, num_feedforward_layers=2, dropout=0.1, nonlinearity_slope=1e-2, mp_cfg=mp)
+    model = gcpnet_b200.GCPNetCPD([6, 3], [32, 1], model_cfg, module_cfg, layer_cfg, dropout=0.2,
+                                  autoregressive_decoder=autoregressive_decoder)
+    if autoregressive_decoder:  # the constructor rewrites module_cfg exactly as the reference's does (gcpnet_cpd_module.py:95-97)
+        assert module_cfg.vector_gate is False and module_cfg.ablate_frame_updates is True
+    return model
+
+
+@pytest.mark.parametrize("which", ["checkpoint", "autoregressive"])
+def test_cpd_model_forward_backward_matches_the_reference_litmodule(which):
+    """Whole ``forward(batch)`` of GCPNetCPDLitModule (gcpnet_cpd_module.py:178-246) + the training step's cross-entropy on the
+    unmasked residues, against fixtures produced by the reference's own class: masked centralize / localize, GCPEmbedding,
+    masked encoder layers, invariant projection and (a) the shipped checkpoint's trained weights (direct-shot model cut to
+    its first two encoder layers, dense decoder), (b) the autoregressive decoder: sequence embedding on row < col edges and
+    two autoregressive GCP-Baseline layers (no frame scalars, no vector gate), seeded weights."""
+    ar = which == "autoregressive"
+    fx = np.load(GC.fixture_path(GC.CPD_AR_FIXTURE if ar else GC.CPD_CKPT_FIXTURE))
+    n_enc, n_dec = GC.CPD_AR_LAYERS if ar else (GC.CPD_CKPT_ENCODER_LAYERS, 3)
+    model = _cpd_model(n_enc, n_dec, ar)
+    if ar:
+        sd = GC.seeded_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=51)
+    else:
+        sd = {k[len("param/"):]: torch.from_numpy(fx[k]) for k in fx.files if k.startswith("param/")}
+    model.load_state_dict(sd, strict=True)  # the reference's names and shapes, nothing missing, nothing extra
+    model = model.cuda().eval()
+    raw = GC.cpd_raw_batch()
+    b = GC.Bag(**{k: v.cuda() for k, v in raw.items()})
+    b.num_graphs = 2
+    _, out = model(b)
+    logits = out if ar else out[0]
+    mask = raw["mask"].cuda()
+    loss = torch.nn.functional.cross_entropy(logits[mask], raw["seq"].cuda()[mask])
+    loss.backward()
+    # masked-out residues keep whatever the embedding gave them; every row is compared
+    assert rel_err(logits.detach().cpu().numpy(), fx["logits"]) < TOL
+    assert rel_err(b.h.detach().cpu().numpy(), fx["out_h"]) < TOL and rel_err(b.chi.detach().cpu().numpy(), fx["out_chi"]) < TOL
+    assert abs(float(loss) - float(fx["loss"])) < 1e-5 * max(1.0, abs(float(fx["loss"])))
+    for k, p in model.named_parameters():
+        want = fx["pgrad/" + k]
+        got = sample_like_fixture(p.grad.cpu()) if p.grad is not None else np.zeros_like(want)
+        if float(np.abs(want).max()) < 1e-6:
+            assert float(np.abs(got).max()) < 1e-3, k
+            continue
+        assert rel_err(got, want) < 1e-3, (k, rel_err(got, want))
