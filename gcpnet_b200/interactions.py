@@ -642,8 +642,15 @@ class GCPInteractions(nn.Module):
     """One GCPNet layer (message passing + node update), reference signature (gcpnet.py:963-974)."""
 
     def __init__(self, node_dims, edge_dims, cfg, layer_cfg, dropout: float = 0.1, autoregressive: bool = False,
-                 nonlinearities: Optional[Tuple[Any, Any]] = None, updating_node_positions: bool = False):
+                 nonlinearities: Optional[Tuple[Any, Any]] = None, updating_node_positions: bool = False,
+                 inplace_masked_update: bool = False):
         super().__init__()
+        # The reference's masked path writes the updated rows INTO THE CALLER'S node_rep tensors when pre_norm is off and
+        # returns those same tensors (gcpnet.py:1203,1249-1251).  GCPNetCPDLitModule relies on it: its `encoder_embedding`
+        # aliases the tensors the decoder layers keep updating (gcpnet_cpd_module.py:198-216).  Off by default (inputs are
+        # borrowed and not mutated); switch it on -- e.g. `model.layer_class.inplace_masked_update=true` under Hydra -- when
+        # this class replaces the reference layer inside a caller that depends on the alias.
+        self.inplace_masked_update = bool(inplace_masked_update)
         node_dims = ScalarVector(int(node_dims[0]), int(node_dims[1]))
         edge_dims = ScalarVector(int(edge_dims[0]), int(edge_dims[1]))
         self.node_dims, self.edge_dims = node_dims, edge_dims
@@ -820,7 +827,14 @@ class GCPInteractions(nn.Module):
         # synchronisation: an all-true mask gives the unmasked numbers)
         gv = graph_views(edge_index, frames, N, autoregressive=ar_call, node_mask=node_mask)
         self._grad_mode = torch.is_grad_enabled()  # Function.forward itself always runs with grad disabled
+        write_back = node_mask is not None and self.inplace_masked_update and not self.pre_norm
+        if write_back:  # the kernels re-read the layer input in backward: keep a private copy of what is about to be overwritten
+            h, chi = h.clone(), chi.clone()
         outs = _LayerFn.apply(self, gv, h, chi, e, xi, gv.frames, node_pos, hg, chig, *self._params_in_order())
+        if write_back:
+            node_rep[0].copy_(outs[0])
+            node_rep[1].copy_(outs[1])
+            outs = (node_rep[0], node_rep[1]) + tuple(outs[2:])
         if self.updating_node_positions:
             return ScalarVector(outs[0], outs[1]), outs[2]
         return ScalarVector(outs[0], outs[1])

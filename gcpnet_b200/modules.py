@@ -366,7 +366,8 @@ class GCPNetCPD(nn.Module):
     """Modules and ``forward(batch)`` of ``GCPNetCPDLitModule`` (gcpnet_cpd_module.py:43-132,178-246) under the same attribute
     names (the shipped checkpoint's ``state_dict`` loads with ``strict=True``): masked centralize -> masked localize ->
     GCPEmbedding -> encoder GCPInteractions layers under the node mask -> (``autoregressive_decoder``: sequence embedding on
-    the ``row < col`` edges, autoregressive GCP-Baseline decoder layers) -> invariant node projection (-> dense decoder).
+    the ``row < col`` edges, autoregressive GCP-Baseline decoder layers whose ``node_rep_regressive`` follows the decoder's
+    own updates, as the reference's aliasing makes it) -> invariant node projection (-> dense decoder).
     Like the reference's constructor (:95-97), ``autoregressive_decoder=True`` rewrites ``module_cfg`` in place before the
     decoder layers and the projection are built: ``vector_gate = frame_gate``, ``frame_gate = False``,
     ``ablate_frame_updates = True``."""
@@ -415,14 +416,16 @@ class GCPNetCPD(nn.Module):
         for layer in self.encoder_layers:
             h, chi = layer((h, chi), (e, xi), batch.edge_index, batch.f_ij, node_mask=mask)
         if self.autoregressive_decoder:
-            encoder_embedding = (h, chi)
             row, col = batch.edge_index[0], batch.edge_index[1]
             # the sequence is visible along edges from earlier residues only (gcpnet_cpd_module.py:200-204)
             seq = self.atom_embedding(batch.seq)[row] * (row < col).unsqueeze(-1).to(e.dtype)
             e = torch.cat((e, seq), dim=-1)
             for layer in self.decoder_layers:
-                h, chi = layer((h, chi), (e, xi), batch.edge_index, batch.f_ij, node_rep_regressive=encoder_embedding,
-                               node_mask=mask)
+                # The reference binds `encoder_embedding = (h, chi)` once (:198), but under a node mask every reference layer
+                # writes its result into the tensors it was given and returns them (gcpnet.py:1203,1249-1251): the tuple
+                # aliases the tensors the decoder keeps updating, so each decoder layer sees the CURRENT (h, chi) as
+                # node_rep_regressive -- values and gradients.  Stated here without in-place writes.
+                h, chi = layer((h, chi), (e, xi), batch.edge_index, batch.f_ij, node_rep_regressive=(h, chi), node_mask=mask)
         batch.h, batch.chi, batch.e, batch.xi = h, chi, e, xi
         out = self.invariant_node_projection((h, chi), batch.edge_index, batch.f_ij, node_inputs=True, node_mask=mask)
         if not self.autoregressive_decoder:

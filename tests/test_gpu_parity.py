@@ -576,3 +576,43 @@ def test_library_switches_give_the_same_gradients():
             if k in base:
                 assert torch.equal(r[k], base[k]), (key, k)
     assert lib.gcpnet_set_option(b"no_such_option", 1) == -1
+
+
+def test_inplace_masked_update_writes_into_the_callers_tensors_like_the_reference():
+    """gcpnet.py:1203,1249-1251: under a node mask (pre_norm off) the reference writes the updated rows into the caller's
+    node_rep tensors and returns them.  Off by default here; with ``inplace_masked_update=True`` the returned tensors ARE
+    the inputs, values and all gradients equal the default mode's."""
+    import gcpnet_b200
+    from tests.helpers import module_cfgs
+    cfg = O.OracleConfig(node_dims=(16, 4), edge_dims=(8, 2), num_message_layers=2, bottleneck=2, default_bottleneck=2)
+    g = torch.Generator().manual_seed(90)
+    n, E = 40, 200
+    ei = torch.randint(0, n, (2, E), generator=g)
+    mask = torch.rand(n, generator=g) > 0.2
+    inputs = O.synthetic_layer_inputs(cfg, ei, n, seed=91)
+    frames = O.localize(inputs["node_pos"].double(), ei, node_mask=mask).float()
+    params = O.random_layer_params(cfg, seed=92)
+    mcfg, lcfg = module_cfgs(cfg)
+    res = {}
+    for flag in (False, True):
+        layer = gcpnet_b200.GCPInteractions(cfg.node_dims, cfg.edge_dims, cfg=mcfg, layer_cfg=lcfg, dropout=0.0,
+                                            inplace_masked_update=flag)
+        layer.load_state_dict(params, strict=True)
+        layer = layer.cuda().eval()
+        leaf_h, leaf_chi = inputs["h"].cuda().requires_grad_(True), inputs["chi"].cuda().requires_grad_(True)
+        h_in, chi_in = leaf_h * 1.0, leaf_chi * 1.0  # non-leaf, as every caller hands them over
+        before = h_in.detach().clone()
+        out = layer((h_in, chi_in), (inputs["e"].cuda(), inputs["xi"].cuda()), ei.cuda(), frames.cuda(), node_mask=mask.cuda())
+        if flag:
+            assert out[0].data_ptr() == h_in.data_ptr() and out[1].data_ptr() == chi_in.data_ptr()
+            assert not torch.equal(h_in.detach(), before)
+            assert torch.equal(h_in.detach()[~mask.cuda()], before[~mask.cuda()])  # masked-out rows keep the input
+        else:
+            assert out[0].data_ptr() != h_in.data_ptr() and torch.equal(h_in.detach(), before)
+        ((out[0] * out[0]).sum() + out[1].sum()).backward()
+        res[flag] = (out[0].detach().clone(), out[1].detach().clone(), leaf_h.grad.clone(), leaf_chi.grad.clone(),
+                     [p.grad.clone() for p in layer.parameters()])
+    for a, b in zip(res[False][:4], res[True][:4]):
+        assert torch.equal(a, b)
+    for a, b in zip(res[False][4], res[True][4]):
+        assert torch.equal(a, b)
