@@ -179,7 +179,11 @@ class GCP2(GCP2Params):
         if tuple(frames.shape) != (E, 3, 3) or edge_index.dtype != torch.int64:
             raise TypeError("gcpnet_b200.GCP2: frames must be [E, 3, 3] and edge_index int64 [2, E]")
         s_in, v_in, edge_index, frames = s_in.contiguous(), v_in.contiguous(), edge_index.contiguous(), frames.contiguous()
-        if node_inputs:
+        if self.flags & _cabi.GCP2_NO_FRAMES:
+            # ablate_frame_updates: the frames (and with them edge_index / node_mask) are never read (gcpnet.py:424-437,450-452);
+            # the reference's sampling loop relies on that when it projects a handful of rows against the full graph
+            F = s_in.new_zeros((M, 9))
+        elif node_inputs:
             if self.e3:
                 raise NotImplementedError("gcpnet_b200.GCP2: enable_e3_equivariance with node_inputs=True is not covered")
             # node-side scalarize = the node's D against the MEAN frame over its outgoing edges (comp/__init__.py:316-323)
@@ -431,3 +435,69 @@ class GCPNetCPD(nn.Module):
         if not self.autoregressive_decoder:
             out = self.decoder(out)
         return batch, out
+
+    @torch.no_grad()
+    def autoregressively_generate_samples(self, node_rep, edge_rep, edge_index, frames, encoder_node_mask, num_samples: int,
+                                          temperature: float = 0.1, sampler=None, return_logits: bool = False):
+        """``GCPNetCPDLitModule.autoregressively_generate_samples`` (gcpnet_cpd_module.py:275-363): encode once, tile the
+        graph ``num_samples`` times, then decode residue by residue -- position ``i`` of every sample runs the decoder layers
+        on the edges that END at ``i`` (sequence visible along ``row < col`` edges only), projects to logits and draws the
+        residue; returns ``int32 [num_samples, N]``.  ``sampler(logits / temperature) -> ids`` defaults to the reference's
+        ``Categorical(logits=...).sample()``.  The per-position edge sets come from ONE sort of the tiled edges by destination
+        position (one host read) instead of a boolean mask + ``nonzero`` per position.  The reference's layers write their
+        result into the cache tensors they are given (gcpnet.py:1249-1251), so layer ``j`` also updates ``node_rep_cache[j]``
+        (and ``node_rep_cache[0]`` is what every layer reads as ``node_rep_regressive``): stated here by rebinding."""
+        if not self.autoregressive_decoder:
+            raise RuntimeError("gcpnet_b200.GCPNetCPD: the model was built without an autoregressive decoder")
+        if sampler is None:
+            sampler = lambda scaled: torch.distributions.Categorical(logits=scaled).sample()
+        emb = self.gcp_embedding
+        N, S = int(node_rep[0].shape[0]), int(num_samples)
+        dev = node_rep[0].device
+        edge_rep = emb.edge_normalization(emb.edge_embedding(edge_rep, edge_index, frames, node_inputs=False,
+                                                             node_mask=encoder_node_mask))
+        node_rep = emb.node_normalization(emb.node_embedding(node_rep, edge_index, frames, node_inputs=True,
+                                                             node_mask=encoder_node_mask))
+        h, chi = node_rep[0], node_rep[1]
+        for layer in self.encoder_layers:
+            h, chi = layer((h, chi), edge_rep, edge_index, frames, node_mask=encoder_node_mask)
+        h, chi = h.repeat(S, 1), chi.repeat(S, 1, 1)
+        e, xi = edge_rep[0].repeat(S, 1), edge_rep[1].repeat(S, 1, 1)
+        E = int(edge_index.shape[1])
+        ei = torch.cat([edge_index + k * N for k in range(S)], dim=1)
+        fr = frames.repeat(S, 1, 1)
+        # edges grouped by the position their destination decodes at (stable: the reference's boolean mask keeps edge order)
+        order = torch.argsort(ei[1] % N, stable=True)
+        start = torch.searchsorted((ei[1] % N)[order].contiguous(), torch.arange(N + 1, device=dev)).tolist()
+        visible = (ei[0] < ei[1]).unsqueeze(-1).to(e.dtype)
+        enc_mask = encoder_node_mask.repeat(S)
+        enc_host = encoder_node_mask.tolist()
+        seq = torch.zeros(S * N, dtype=torch.int32, device=dev)
+        seq_emb = torch.zeros(S * N, self.atom_embedding.embedding_dim, dtype=e.dtype, device=dev)
+        cache = [(h.clone(), chi.clone()) for _ in self.decoder_layers]
+        trace = []
+        for i in range(N):
+            if not enc_host[i]:
+                # the reference assigns the (empty) selection of masked-out rows into a num_samples-row slice and fails
+                raise RuntimeError(f"gcpnet_b200.GCPNetCPD: residue {i} is masked out; the sampling loop needs every residue "
+                                   "(the reference fails at this point too, gcpnet_cpd_module.py:345-349)")
+            idx = order[start[i]:start[i + 1]]
+            ei_, fr_, xi_ = ei[:, idx].contiguous(), fr[idx].contiguous(), xi[idx].contiguous()
+            e_ = torch.cat((e[idx], seq_emb[ei[0][idx]] * visible[idx]), dim=-1)
+            node_mask = torch.zeros(S * N, dtype=torch.bool, device=dev)
+            node_mask[i::N] = True
+            node_mask &= enc_mask
+            for j, layer in enumerate(self.decoder_layers):
+                out = layer(cache[j], (e_, xi_), ei_, fr_, node_rep_regressive=cache[0], node_mask=node_mask)
+                cache[j] = (out[0], out[1])  # the reference's write-back into the tensors it was given
+                rows = (out[0][i::N], out[1][i::N])
+                if j < len(self.decoder_layers) - 1:  # (the cache tensors are this method's own)
+                    cache[j + 1][0][i::N], cache[j + 1][1][i::N] = rows[0], rows[1]
+            logits = self.invariant_node_projection((rows[0].contiguous(), rows[1].contiguous()), ei_, fr_, node_inputs=True,
+                                                    node_mask=node_mask)
+            if return_logits:
+                trace.append(logits)
+            seq[i::N] = sampler(logits / temperature).to(torch.int32)
+            seq_emb[i::N] = self.atom_embedding(seq[i::N].long())
+        out_seq = seq.reshape(S, N)
+        return (out_seq, torch.stack(trace)) if return_logits else out_seq

@@ -247,6 +247,23 @@ def cpd_raw_batch(num_graphs: int = 2, n: int = 40, k: int = 8, seed: int = 41):
                 seq=torch.randint(0, 20, (N,), generator=g), mask=mask)
 
 
+CPD_SAMPLING_FIXTURE = "cpd_ar_sampling"   # the sampling loop on one 24-residue chain, 3 samples
+
+
+def cpd_sampling_datum():
+    """One chain for GCPNetCPDLitModule.autoregressively_generate_samples: every residue has coordinates."""
+    raw = cpd_raw_batch(num_graphs=1, n=24, k=6, seed=43)
+    raw["mask"] = torch.ones_like(raw["mask"])
+    return raw
+
+
+def ranked_choice(scaled_logits: torch.Tensor) -> torch.Tensor:
+    """Deterministic stand-in for the sampler of the decode test: row k takes the class with the (k+1)-th largest logit."""
+    order = scaled_logits.argsort(dim=-1, descending=True)
+    k = torch.arange(order.shape[0], device=order.device) % order.shape[1]
+    return order[torch.arange(order.shape[0], device=order.device), k]
+
+
 def seeded_state_dict(shapes, seed: int):
     """Deterministic weights for a name -> shape table (names visited in sorted order): LayerNorm weights near 1, biases small,
     matrices uniform in +-1/sqrt(fan_in), embeddings standard normal."""

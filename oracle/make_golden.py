@@ -160,18 +160,60 @@ def run_cpd_model(name: str):
     print(f"{name}: loss={loss.item():.6f} params={sum(v.numel() for v in sd.values())} -> {GC.fixture_path(name)}")
 
 
+def run_cpd_sampling():
+    """GCPNetCPDLitModule.autoregressively_generate_samples (gcpnet_cpd_module.py:275-363), unmodified, on the seeded
+    autoregressive model -- only the random draw is replaced: the module's ``Categorical`` is swapped for a recorder that
+    keeps the scaled logits of every position and returns, for sample k, the class with the (k+1)-th largest logit
+    (golden_cases.ranked_choice): the decode is deterministic and the samples differ from each other."""
+    import importlib
+    ref, Lit = ref_shim.load_cpd_litmodule()
+    n_enc, n_dec = GC.CPD_AR_LAYERS
+    model_cfg, module_cfg, layer_cfg = ref_shim.cpd_model_cfgs(ref, n_enc, n_dec)
+    lit = Lit(layer_class=ref.GCPInteractions, optimizer=None, scheduler=None, node_input_dims=[6, 3], edge_input_dims=[32, 1],
+              model_cfg=model_cfg, module_cfg=module_cfg, layer_cfg=layer_cfg, autoregressive_decoder=True)
+    lit.load_state_dict(GC.seeded_state_dict({k: v.shape for k, v in lit.state_dict().items()}, seed=51), strict=True)
+    lit.eval()
+    trace = []
+
+    class _ArgmaxRecorder:
+        def __init__(self, logits):
+            self.logits = logits
+            trace.append(logits.detach().clone())
+
+        def sample(self):
+            return GC.ranked_choice(self.logits)
+
+    mod = importlib.import_module("src.models.gcpnet_cpd_module")
+    saved = mod.Categorical
+    mod.Categorical = _ArgmaxRecorder
+    try:
+        raw = GC.cpd_sampling_datum()
+        _, x = ref.comp.centralize(GC.Bag(**raw), key="x", batch_index=raw["batch"], node_mask=raw["mask"])
+        frames = ref.localize(x, raw["edge_index"], norm_x_diff=True, node_mask=raw["mask"])
+        SV = ref.ScalarVector
+        samples = lit.autoregressively_generate_samples(SV(raw["h"], raw["chi"]), SV(raw["e"], raw["xi"]), raw["edge_index"],
+                                                        frames, encoder_node_mask=raw["mask"], num_samples=3, temperature=0.1)
+    finally:
+        mod.Categorical = saved
+    rec = {"samples": samples.numpy(), "scaled_logits": torch.stack(trace).numpy(), "frames": frames.numpy()}
+    np.savez_compressed(GC.fixture_path(GC.CPD_SAMPLING_FIXTURE), **rec)
+    print(f"{GC.CPD_SAMPLING_FIXTURE}: samples {tuple(samples.shape)} -> {GC.fixture_path(GC.CPD_SAMPLING_FIXTURE)}")
+
+
 def main(argv):
     if not ref_shim.reference_available():
         print("reference tree not available; nothing generated", file=sys.stderr)
         return 1
     torch.manual_seed(0)
     torch.set_num_threads(1)  # bitwise reproducible reductions
-    names = argv[1:] or (list(GC.CASES) + [GC.NMS_MODEL_FIXTURE, GC.CPD_CKPT_FIXTURE, GC.CPD_AR_FIXTURE])
+    names = argv[1:] or (list(GC.CASES) + [GC.NMS_MODEL_FIXTURE, GC.CPD_CKPT_FIXTURE, GC.CPD_AR_FIXTURE, GC.CPD_SAMPLING_FIXTURE])
     for name in names:
         if name == GC.NMS_MODEL_FIXTURE:
             run_nms_model()
         elif name in (GC.CPD_CKPT_FIXTURE, GC.CPD_AR_FIXTURE):
             run_cpd_model(name)
+        elif name == GC.CPD_SAMPLING_FIXTURE:
+            run_cpd_sampling()
         else:
             run_reference(name, GC.CASES[name])
     return 0
