@@ -39,6 +39,7 @@ class Layer(C.Structure):
         ("ln0_w", C.c_void_p), ("ln0_b", C.c_void_p), ("ln1_w", C.c_void_p), ("ln1_b", C.c_void_p),
         ("ln_grad_off", C.c_int32 * 4), ("n_edge_params", C.c_int32), ("n_node_params", C.c_int32),
         ("pre_norm", C.c_int32), ("autoregressive", C.c_int32),
+        ("attn_w", C.c_void_p), ("attn_b", C.c_void_p), ("attn_grad_off", C.c_int32 * 2),
     ]
 
 
@@ -219,7 +220,8 @@ class LayerSpec:
                  vector_residual=False, default_vector_residual=False, scalar_nonlinearity="relu",
                  vector_nonlinearity=None, nonlinearity_slope=1e-2, use_residual_message_gcp=True,
                  enable_e3_equivariance=False, reduce_function="mean", updating_node_positions=False,
-                 node_positions_weight=1.0, pre_norm=False, autoregressive=False, ablate_frame_updates=False, vector_gate=True):
+                 node_positions_weight=1.0, pre_norm=False, autoregressive=False, ablate_frame_updates=False, vector_gate=True,
+                 message_attention=False):
         self.s, self.v = int(node_dims[0]), int(node_dims[1])
         self.gcp_flags = gcp2_flags(ablate_frame_updates, vector_gate)  # every GCP of a layer is built from one cfg
         self.se, self.ve = int(edge_dims[0]), int(edge_dims[1])
@@ -279,6 +281,10 @@ class LayerSpec:
         for m in mods:
             for pn, shp in gcp2_shapes(*m[1:6], self.gcp_flags).items():
                 add(m[0] + pn, shp)
+        self.message_attention = bool(message_attention)
+        if self.message_attention:  # GCPMessagePassing.scalar_message_attention = Sequential(Linear(s, 1), Sigmoid) (gcpnet.py:893-897)
+            add("interaction.scalar_message_attention.0.weight", (1, s))
+            add("interaction.scalar_message_attention.0.bias", (1,))
         self.n_edge_params = off
         for i in range(2):
             add(f"gcp_norm.{i}.scalar_norm.weight", (s,))
@@ -326,6 +332,10 @@ class LayerSpec:
             l.ln_grad_off[i] = self.offsets[n]
         l.n_edge_params, l.n_node_params = self.n_edge_params, self.n_node_params
         l.pre_norm, l.autoregressive = int(self.pre_norm), int(self.autoregressive)
+        if self.message_attention:
+            wn, bn = "interaction.scalar_message_attention.0.weight", "interaction.scalar_message_attention.0.bias"
+            l.attn_w, l.attn_b = ptr(wn), ptr(bn)
+            l.attn_grad_off[0], l.attn_grad_off[1] = self.offsets[wn], self.offsets[bn]
         return l
 
 

@@ -30,6 +30,8 @@ struct EdgeParams {
                                            // rows of the [2N] gather table, gcpnet.py:1065-1116)
   const int* dst_ptr;                      // [N+1] CSR row pointer of the destination-sorted order
   const float* blob;                       // packed weights of the layer (pack.cuh)
+  const float *attn_w, *attn_b;            // scalar message attention (gcpnet.py:931-934): m_s *= sigmoid(attn_w . m_s + attn_b); nullptr: off
+  int o_attn_w, o_attn_b;                  // their gradient offsets inside a per-CTA partial row
   float* agg;                              // [N][s+3v] per-destination sums + [tiles][2][s+3v] carries (segment_total, gcp_tile.cuh)
   float* saved;                            // activations kept for backward (nullptr: inference)
   long long offT[MAX_MSG_LAYERS], offG[MAX_MSG_LAYERS], offS[MAX_MSG_LAYERS], offV[MAX_MSG_LAYERS];
@@ -150,6 +152,18 @@ GCP_HDN void edge_fwd_tile(const EdgeParams& p, float* sm, int tile, WPipe& wp, 
     GCP_PHASE_END
     wp.head++;  // G chunk released; the next phase (next GCP or next tile) refills its slot
   }
+  // ---- scalar message attention (gcpnet.py:931-934): one thread per row
+  if (p.attn_w != nullptr) {
+    GCP_PHASE_BEGIN(NT)
+    if (tid < TE) {
+      float* zp = Zs + tid * L.ldz;
+      float a = GCP_LDG(p.attn_b);
+      for (int j = 0; j < s; ++j) a = fmaf(GCP_LDG(p.attn_w + j), zp[j], a);
+      a = sigmoidf_(a);
+      for (int j = 0; j < s; ++j) zp[j] *= a;
+    }
+    GCP_PHASE_END
+  }
   // ---- aggregate (gcpnet.py:938-947) straight out of shared memory: the thread of a segment's FIRST row in the tile sums
   //      that destination's rows (fixed order), per column part
   GCP_PHASE_BEGIN(NT)
@@ -216,6 +230,41 @@ GCP_HDN void edge_bwd_tile(const EdgeParams& p, float* sm, int tile, WPipe& wp, 
     tile_load_rows<TE, NT>(b.T, b.ldt, p.saved + p.offT[k], s, rr, tid);
     tile_load_rows<TE, NT>(b.SG, b.ldsg, p.saved + p.offG[k], v, rr, tid);
     GCP_PHASE_END
+    if (k == p.L - 1 && p.attn_w != nullptr) {
+      // ---- scalar message attention backward.  The un-gated final scalars are r = (S_{L-2} +) act_s(T_{L-1}): both tiles
+      //      were just loaded.  a = sigmoid(w . r + b); the message was r * a:
+      //        g_r = g_m * a + (g_m . r) a (1 - a) w ;  g_w += (g_m . r) a (1 - a) r ;  g_b += (g_m . r) a (1 - a)
+      const bool add = k > 0 && p.residual != 0;
+      const int act = op.act_s;
+      const float slope = p.slope;
+      GCP_PHASE_BEGIN(NT)
+      if (tid < TE) {
+        const float* zp = b.Z + tid * b.ldz; const float* tp = b.T + tid * b.ldt;
+        float* gs = g.GS + tid * g.ldgs;
+        float a = GCP_LDG(p.attn_b), ga = 0.f;
+        for (int j = 0; j < s; ++j) {
+          const float r = (add ? zp[j] : 0.f) + act_fwd(act, tp[j], slope);
+          a = fmaf(GCP_LDG(p.attn_w + j), r, a);
+          ga = fmaf(gs[j], r, ga);
+        }
+        a = sigmoidf_(a);
+        const float da = ga * a * (1.f - a);
+        for (int j = 0; j < s; ++j) gs[j] = fmaf(gs[j], a, da * GCP_LDG(p.attn_w + j));
+        g.GG[tid * g.ldgg] = da;  // (GG is scratch until the gate backward of this GCP)
+      }
+      GCP_PHASE_END
+      GCP_PHASE_BEGIN(NT)
+      for (int j = tid; j <= s; j += NT) {  // j == s: the bias
+        float sum = 0.f;
+        for (int e = 0; e < TE; ++e) {
+          const float da = g.GG[e * g.ldgg];
+          sum += j == s ? da : da * ((add ? b.Z[e * b.ldz + j] : 0.f) + act_fwd(act, b.T[e * b.ldt + j], slope));
+        }
+        float* dst = prow + (j == s ? p.o_attn_b : p.o_attn_w + j);
+        *dst = (accumulate ? *dst : 0.f) + sum;
+      }
+      GCP_PHASE_END
+    }
     // (gcp2_bwd_tile refills every chunk it releases, so nothing is pending on the ring here)
     const bool refill_first = false;
     if (k > 0) {

@@ -380,6 +380,7 @@ inline EdgeParams make_edge_params(const gcpnet_layer& l, const gcpnet_graph& g,
   p.perm = g.perm; p.src = g.src; p.dst = g.dst; p.dst_ptr = g.dst_ptr;
   p.gsrc = g.gsrc != nullptr ? g.gsrc : g.src; p.gdst = g.gdst != nullptr ? g.gdst : g.dst;
   p.blob = blob;
+  p.attn_w = l.attn_w; p.attn_b = l.attn_b; p.o_attn_w = l.attn_grad_off[0]; p.o_attn_b = l.attn_grad_off[1];
   for (int k = 0; k < p.L; ++k) p.ops[k] = ops.msg[k];
   long long tot;
   edge_saved_offsets(l, g.num_edges, p.offT, p.offG, p.offS, p.offV, &tot);

@@ -59,6 +59,7 @@ inline TcPlan make_tc_plan(const gcpnet_layer& l, long long N, long long E) {
   if (v > PW || ve > 8) return no("vector channels beyond 16 / 8");
   if (L < 1) return no("no message layers");
   if (l.autoregressive) return no("autoregressive layers gather from two node tables (FFMA edge kernels)");
+  if (l.attn_w != nullptr) return no("scalar message attention runs in the FFMA edge kernels");
   TcEdgeParams& p = P.proto;
   p.L = L; p.s = s; p.v = v; p.se = se; p.ve = ve;
   p.residual = l.residual_messages; p.e3 = l.enable_e3; p.slope = l.slope;

@@ -461,8 +461,10 @@ def _check_gcp_flags(cfg, who: str) -> dict:
                                   "(and there is no eager fallback)")
     sel = _get(cfg, "selected_GCP", None)
     sel_name = getattr(getattr(sel, "func", sel), "__name__", None) or str(_get(sel, "_target_", "") or "")
-    if sel is not None and sel_name and not sel_name.endswith("GCP2"):
-        unsupported(f"selected_GCP={sel_name} (only GCP2)")
+    # GCP3's forward is GCP2's (gcpnet.py:625-700 vs :393-468); its one extra, feedforward_out, is only ever requested by
+    # GCPInteractions2 for its own feed-forward GCPs (gcpnet_b200.GCP3)
+    if sel is not None and sel_name and not sel_name.endswith(("GCP2", "GCP3")):
+        unsupported(f"selected_GCP={sel_name} (only GCP2 / GCP3)")
     vector_gate = bool(_get(cfg, "vector_gate", True))
     if not vector_gate and _nonlinearities(cfg)[1] is not None:
         unsupported("vector_gate=False with a vector nonlinearity (norm gating, gcpnet.py:349-350)")
@@ -554,9 +556,7 @@ class GCPMessagePassing(nn.Module):
         node_dims = ScalarVector(int(input_dims[0]), int(input_dims[1]))
         if tuple(int(d) for d in output_dims) != tuple(node_dims):
             raise NotImplementedError("gcpnet_b200.GCPMessagePassing: output_dims != input_dims is not covered")
-        if use_scalar_message_attention:
-            raise NotImplementedError("gcpnet_b200.GCPMessagePassing: use_scalar_message_attention (GCPInteractions2 only) "
-                                      "is not covered")
+        self.use_scalar_message_attention = bool(use_scalar_message_attention)
         self.aggregate_with_row = bool(aggregate_with_row)
         if reduce_function not in ("mean", "add", "sum"):
             raise NotImplementedError(f"gcpnet_b200.GCPMessagePassing: reduce_function={reduce_function!r}")
@@ -573,11 +573,13 @@ class GCPMessagePassing(nn.Module):
             scalar_nonlinearity=nl[0], vector_nonlinearity=nl[1], nonlinearity_slope=float(nonlinearity_slope),
             use_residual_message_gcp=bool(_get(mp_cfg, "use_residual_message_gcp", True)),
             enable_e3_equivariance=bool(_get(cfg, "enable_e3_equivariance", False)), reduce_function=reduce_function,
-            **variant)
+            message_attention=self.use_scalar_message_attention, **variant)
         for m in self.spec.message_mods:
             if not 1 <= m[5] <= 16:
                 raise NotImplementedError(f"gcpnet_b200.GCPMessagePassing: hidden vector dim {m[5]} (supported: 1..16)")
         self.message_fusion = nn.ModuleList([GCP2Params(*m[1:6], self.spec.gcp_flags) for m in self.spec.message_mods])
+        if self.use_scalar_message_attention:  # gcpnet.py:893-897 (the Sigmoid of the Sequential runs inside the edge kernel)
+            self.scalar_message_attention = nn.Sequential(nn.Linear(node_dims[0], 1), nn.Sigmoid())
         self._names = [n[len("interaction."):] for n in self.spec.names if n.startswith("interaction.")]
         self._param_list = None
         self._struct_cache = None
@@ -605,8 +607,6 @@ class GCPMessagePassing(nn.Module):
         return layer
 
     def forward(self, node_rep, edge_rep, edge_index, frames, node_mask=None):
-        if node_mask is not None:
-            raise NotImplementedError("gcpnet_b200.GCPMessagePassing: node_mask goes through GCPInteractions")
         h, chi, e, xi = node_rep[0].contiguous(), node_rep[1].contiguous(), edge_rep[0].contiguous(), edge_rep[1].contiguous()
         for t, name in ((h, "node scalars"), (chi, "node vectors"), (e, "edge scalars"), (xi, "edge vectors"),
                         (edge_index, "edge_index"), (frames, "frames")):
@@ -626,10 +626,12 @@ class GCPMessagePassing(nn.Module):
         if self.aggregate_with_row:
             # scatter over `row` (gcpnet.py:946): the views of the FLIPPED edge_index sort by row; the gather ids hand the
             # message GCPs the original (row, col) ends (edge features and frames stay aligned with the caller's edge ids)
-            gv = graph_views(edge_index.flip(0).contiguous(), frames, N)
+            gv = graph_views(edge_index.flip(0).contiguous(), frames, N, node_mask=node_mask)
+            frames = gv.frames  # under a node mask: zero rows on the masked edges (scalarize, comp/__init__.py:294-300)
             gv = _swapped_gather(gv)
         else:
-            gv = graph_views(edge_index, frames, N)
+            gv = graph_views(edge_index, frames, N, node_mask=node_mask)
+            frames = gv.frames
         self._grad_mode = torch.is_grad_enabled()
         agg = _MPFn.apply(self, gv, h, chi, e, xi, frames, *self._params_in_order())
         return ScalarVector.recover(agg, v)

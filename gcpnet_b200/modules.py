@@ -501,3 +501,211 @@ class GCPNetCPD(nn.Module):
             seq_emb[i::N] = self.atom_embedding(seq[i::N].long())
         out_seq = seq.reshape(S, N)
         return (out_seq, torch.stack(trace)) if return_logits else out_seq
+
+
+# ------------------------------------------------------------------------------------------
+# GCP3 and GCPInteractions2: the EQ / AR tasks' perceptron and layer, composed from the kernels above
+# ------------------------------------------------------------------------------------------
+class _Gcp2Op:
+    """What ``_Gcp2Fn`` needs to know about one GCP2 evaluation whose parameters are handed over as plain tensors."""
+
+    def __init__(self, dims, acts, flags, vres, e3, slope):
+        self.dims, self.acts, self.flags, self.vres, self.e3, self.slope = dims, acts, int(flags), bool(vres), bool(e3), slope
+        self._layout = {}
+        off = 0
+        for name, shp in _cabi.gcp2_shapes(*dims, self.flags).items():
+            self._layout[name] = (off, shp)
+            n = 1
+            for d in shp:
+                n *= d
+            off += n
+        self._grad_mode = True
+
+    def _op_struct(self, params) -> _cabi.Gcp2:
+        op = _cabi.Gcp2()
+        op.si, op.vi, op.so, op.vo, op.hd = self.dims
+        op.act_s, op.act_v, op.vector_residual, op.flags = self.acts[0], self.acts[1], int(self.vres), self.flags
+        for (name, (off, _)), p in zip(self._layout.items(), params):
+            setattr(op, _cabi._PTR_FIELD[name], p.data_ptr())
+            op.grad_off[_cabi._GRAD_SLOT[name]] = off
+        return op
+
+    def __call__(self, s_in, v_in, frames9, params):
+        self._grad_mode = torch.is_grad_enabled()
+        return _Gcp2Fn.apply(self, s_in, v_in, frames9, *[p.contiguous() for p in params])
+
+
+class GCP3(GCP2):
+    """``GCP3`` (gcpnet.py:471-700): GCP2's forward (the two classes' ``forward`` are line-for-line the same) with default
+    nonlinearities ("silu", "silu") and, with ``feedforward_out=True``, ``scalar_out`` = Linear -> ``scalar_out_nonlinearity``
+    -> Linear (state_dict names ``scalar_out.0.*`` / ``scalar_out.2.*``).  The two-layer form runs as TWO passes of the GCP2
+    kernel: pass A evaluates ``u = act_out(scalar_out.0([s | norms | frame scalars]))`` (a GCP2 with no vector output),
+    pass B a frame-less GCP2 on ``(u, V)`` whose scalar_out is ``[scalar_out.2 | 0]`` (zero weights on the norm columns) --
+    ``vector_down`` is shared, autograd adds its two gradients."""
+
+    def __init__(self, input_dims, output_dims, nonlinearities: Optional[Tuple[Optional[str], Optional[str]]] = ("silu", "silu"),
+                 scalar_out_nonlinearity: Optional[str] = "silu", scalar_gate: int = 0, vector_gate: bool = True,
+                 frame_gate: bool = False, sigma_frame_gate: bool = False, feedforward_out: bool = False, bottleneck: int = 1,
+                 vector_residual: bool = False, vector_frame_residual: bool = False, ablate_frame_updates: bool = False,
+                 ablate_scalars: bool = False, ablate_vectors: bool = False, enable_e3_equivariance: bool = False,
+                 scalarization_vectorization_output_dim: int = 3, nonlinearity_slope: float = 1e-2, **kwargs):
+        super().__init__(input_dims, output_dims, nonlinearities=nonlinearities, scalar_gate=scalar_gate, vector_gate=vector_gate,
+                         frame_gate=frame_gate, sigma_frame_gate=sigma_frame_gate, bottleneck=bottleneck,
+                         vector_residual=vector_residual, vector_frame_residual=vector_frame_residual,
+                         ablate_frame_updates=ablate_frame_updates, ablate_scalars=ablate_scalars, ablate_vectors=ablate_vectors,
+                         enable_e3_equivariance=enable_e3_equivariance,
+                         scalarization_vectorization_output_dim=scalarization_vectorization_output_dim,
+                         nonlinearity_slope=nonlinearity_slope)
+        self.feedforward_out = bool(feedforward_out)
+        if not self.feedforward_out:
+            return
+        if self._scalar_only:
+            raise NotImplementedError("gcpnet_b200.GCP3: feedforward_out without vector inputs is not covered")
+        si, vi, so, vo, hd = self.dims
+        first = self.scalar_out
+        # same registration order as the reference: vector_down, scalar_out (0, 2), vector_down_frames, vector_up, vector_out_scale
+        rest = {k: self._modules.pop(k) for k in ("vector_down_frames", "vector_up", "vector_out_scale") if k in self._modules}
+        del self._modules["scalar_out"]
+        self.scalar_out = nn.Sequential(first, nn.SiLU() if _cabi._norm(scalar_out_nonlinearity) == "silu" else nn.Identity(),
+                                        nn.Linear(so, so))
+        for k, m in rest.items():
+            self._modules[k] = m
+        act_out = _cabi.ACT[_cabi._norm(scalar_out_nonlinearity)]
+        self._stage_a = _Gcp2Op((si, vi, so, 0, hd), (act_out, 0), self.flags & _cabi.GCP2_NO_FRAMES, False, self.e3, self.slope)
+        self._stage_b = _Gcp2Op((so, vi, so, vo, hd), self.acts, self.flags | _cabi.GCP2_NO_FRAMES, self.vres, False, self.slope)
+
+    def forward(self, s_maybe_v, edge_index, frames, node_inputs: bool = False, node_mask=None):
+        if not self.feedforward_out:
+            return super().forward(s_maybe_v, edge_index, frames, node_inputs=node_inputs, node_mask=node_mask)
+        s_in, v_in = s_maybe_v[0].contiguous(), s_maybe_v[1].contiguous()
+        si, vi, so, vo, hd = self.dims
+        for t, name in ((s_in, "scalars"), (v_in, "vectors"), (edge_index, "edge_index"), (frames, "frames")):
+            _check_cuda(t, name)
+        M, E = int(s_in.shape[0]), int(edge_index.shape[1])
+        if tuple(s_in.shape) != (M, si) or tuple(v_in.shape) != (M, vi, 3) or s_in.dtype != torch.float32 or v_in.dtype != torch.float32:
+            raise TypeError(f"gcpnet_b200.GCP3: inputs must be float32 [{M}, {si}] and [{M}, {vi}, 3]")
+        if M == 0:
+            z = s_in.new_zeros((0, so))
+            return ScalarVector(z, v_in.new_zeros((0, vo, 3))) if vo else z
+        edge_index, frames = edge_index.contiguous(), frames.contiguous()
+        if self.flags & _cabi.GCP2_NO_FRAMES:
+            F = s_in.new_zeros((M, 9))
+        elif node_inputs:
+            if self.e3:
+                raise NotImplementedError("gcpnet_b200.GCP3: enable_e3_equivariance with node_inputs=True is not covered")
+            gv = graph_views(edge_index, frames, M, node_mask=node_mask)
+            F = (gv.fbar_pos if gv.mask is not None else gv.fbar).reshape(M, 9)
+        else:
+            if M != E:
+                raise TypeError("gcpnet_b200.GCP3: node_inputs=False needs one row per edge")
+            F = (frames if node_mask is None else graph_views(edge_index, frames, int(node_mask.shape[0]), node_mask=node_mask).frames)
+            F = F.reshape(M, 9)
+        lin0, lin2 = self.scalar_out[0], self.scalar_out[2]
+        pa = [self.vector_down.weight, lin0.weight, lin0.bias]
+        if not (self.flags & _cabi.GCP2_NO_FRAMES):
+            pa.append(self.vector_down_frames.weight)
+        u, _ = self._stage_a(s_in, v_in, F, pa)
+        if not vo:
+            t = torch.nn.functional.linear(u, lin2.weight, lin2.bias)
+            return _apply_act(self.acts[0], t, self.slope)
+        w2 = torch.cat((lin2.weight, lin2.weight.new_zeros((so, hd))), dim=1)  # no weight on the norm columns of pass B
+        pb = [self.vector_down.weight, w2, lin2.bias, self.vector_up.weight]
+        if not (self.flags & _cabi.GCP2_NO_GATE):
+            pb += [self.vector_out_scale.weight, self.vector_out_scale.bias]
+        s_out, v_out = self._stage_b(u, v_in, s_in.new_zeros((M, 9)), pb)
+        return ScalarVector(s_out, v_out)
+
+
+def _apply_act(code: int, t: torch.Tensor, slope: float) -> torch.Tensor:
+    name = {v: k for k, v in _cabi.ACT.items()}[code]
+    if name is None:
+        return t
+    return {"relu": torch.relu, "silu": torch.nn.functional.silu, "sigmoid": torch.sigmoid, "selu": torch.selu,
+            "leakyrelu": lambda x: torch.nn.functional.leaky_relu(x, slope)}[name](t)
+
+
+class GCPDropout(nn.Module):
+    """``GCPDropout`` (comp/__init__.py:97-135) for the composed layer below: ``nn.Dropout`` on the scalars, one Bernoulli
+    draw per (node, channel) shared by x, y, z on the vectors, scaled by 1 / (1 - p); identity in eval mode.  (The fused
+    GCPInteractions layer draws its masks inside the node kernel instead.)"""
+
+    def __init__(self, drop_rate: float):
+        super().__init__()
+        self.p = float(drop_rate)
+
+    def forward(self, x):
+        if not self.training or self.p <= 0.0:
+            return x
+        s, v = x[0], x[1]
+        keep_s = (torch.rand_like(s) >= self.p).to(s.dtype) / (1.0 - self.p)
+        keep_v = (torch.rand(v.shape[:-1], device=v.device) >= self.p).to(v.dtype).unsqueeze(-1) / (1.0 - self.p)
+        return ScalarVector(s * keep_s, v * keep_v)
+
+
+class GCPInteractions2(nn.Module):
+    """``GCPInteractions2`` (gcpnet.py:1265-1451), the layer of the EQ / AR configs, with the reference's constructor,
+    ``forward`` signature and ``state_dict`` names: GCPMessagePassing (reduce "sum", scalar message attention,
+    aggregate_with_row) -> concat with the layer input -> feed-forward GCPs on the full graph, the last with
+    ``feedforward_out`` -> dropout, residual, one GCPLayerNorm -> masked rows zeroed -> optional position update.
+    A composition of this package's kernels (message passing, GCP2, GCPLayerNorm) -- not one fused layer kernel like
+    GCPInteractions; concat / residual / mask products are elementwise torch ops."""
+
+    def __init__(self, node_dims, edge_dims, cfg, layer_cfg, dropout: float = 0.1,
+                 nonlinearities: Optional[Tuple[Any, Any]] = None, updating_node_positions: bool = False):
+        super().__init__()
+        from .interactions import GCPMessagePassing, _check_gcp_flags, _nonlinearities
+        node_dims = ScalarVector(int(node_dims[0]), int(node_dims[1]))
+        edge_dims = ScalarVector(int(edge_dims[0]), int(edge_dims[1]))
+        self.node_dims, self.edge_dims = node_dims, edge_dims
+        cfg_nl = tuple(_nonlinearities(cfg))
+        nonlinearities = cfg_nl if nonlinearities is None else tuple(nonlinearities)
+        self.pre_norm = bool(_get(layer_cfg, "pre_norm", False))
+        self.updating_node_positions = bool(updating_node_positions)
+        self.node_positions_weight = float(_get(cfg, "node_positions_weight", 1.0))
+        variant = _check_gcp_flags(cfg, "GCPInteractions2")
+        slope = float(_get(layer_cfg, "nonlinearity_slope", 1e-2))
+        self.interaction = GCPMessagePassing(
+            node_dims, node_dims, edge_dims, cfg=cfg, mp_cfg=_get(layer_cfg, "mp_cfg", None), reduce_function="sum",
+            use_scalar_message_attention=bool(_get(layer_cfg, "use_scalar_message_attention", False)),
+            aggregate_with_row=bool(_get(layer_cfg, "aggregate_with_row", False)), nonlinearity_slope=slope)
+        kw = dict(vector_gate=variant["vector_gate"], ablate_frame_updates=variant["ablate_frame_updates"],
+                  bottleneck=int(_get(cfg, "bottleneck", 1)), enable_e3_equivariance=bool(_get(cfg, "enable_e3_equivariance", False)),
+                  nonlinearity_slope=slope)
+        self.gcp_norm = nn.ModuleList([GCPLayerNorm(node_dims)])
+        self.gcp_dropout = nn.ModuleList([GCPDropout(dropout)])
+        nff = int(_get(layer_cfg, "num_feedforward_layers", 1))
+        s, v = node_dims
+        hidden = (s, v) if nff == 1 else (4 * s, 2 * v)
+        layers = [GCP3((2 * s, 2 * v), hidden, nonlinearities=(None, None) if nff == 1 else cfg_nl, feedforward_out=nff == 1,
+                       vector_residual=False, **kw)]
+        layers += [GCP3(hidden, hidden, nonlinearities=nonlinearities, vector_residual=bool(_get(cfg, "vector_residual", False)), **kw)
+                   for _ in range(nff - 2)]
+        if nff > 1:
+            layers.append(GCP3(hidden, (s, v), nonlinearities=(None, None), feedforward_out=True, vector_residual=False, **kw))
+        self.feedforward_network = nn.ModuleList(layers)
+        if self.updating_node_positions:
+            self.node_position_update_gcp = GCP3((s, v), (s, 1), nonlinearities=cfg_nl, vector_residual=False, **kw)
+
+    def forward(self, node_rep, edge_rep, edge_index, frames, node_mask=None, node_pos=None):
+        h, chi = node_rep[0], node_rep[1]
+        node_rep = ScalarVector(h, chi)
+        if self.pre_norm:
+            node_rep = self.gcp_norm[0](node_rep)
+        hidden = self.interaction(node_rep, edge_rep, edge_index, frames, node_mask=node_mask)
+        hidden = ScalarVector(torch.cat((hidden[0], node_rep[0]), dim=-1), torch.cat((hidden[1], node_rep[1]), dim=-2))
+        for module in self.feedforward_network:
+            hidden = module(hidden, edge_index, frames, node_inputs=True, node_mask=node_mask)
+        hidden = self.gcp_dropout[0](hidden)
+        node_rep = ScalarVector(node_rep[0] + hidden[0], node_rep[1] + hidden[1])
+        if not self.pre_norm:
+            node_rep = self.gcp_norm[0](node_rep)
+        if node_mask is not None:
+            m = node_mask.to(node_rep[0].dtype)
+            node_rep = ScalarVector(node_rep[0] * m[:, None], node_rep[1] * m[:, None, None])
+        if not self.updating_node_positions:
+            return node_rep
+        upd = self.node_position_update_gcp(node_rep, edge_index, frames, node_inputs=True, node_mask=node_mask)
+        node_pos = node_pos + upd[1].squeeze(1) * self.node_positions_weight
+        if node_mask is not None:
+            node_pos = node_pos * node_mask.to(node_pos.dtype).unsqueeze(-1)
+        return node_rep, node_pos

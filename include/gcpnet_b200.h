@@ -85,6 +85,12 @@ typedef struct gcpnet_layer {
   int32_t autoregressive;          /* 1: the graph carries the gather views of gcpnet_graph_build_autoregressive; 2: aggregate_with_row
                                       (gcpnet.py:946): graph built on the flipped edge_index, gsrc = dst / gdst = src swap the
                                       ends back, num_gather_rows = 0.  Both run the FFMA edge kernels. */
+  /* GCPMessagePassing(use_scalar_message_attention=True) (gcpnet.py:893-897,931-934; the EQ / AR layers): the scalar
+   * messages are scaled by sigmoid(attn_w . m_s + attn_b) before the aggregation.  NULL = off.  attn_grad_off = offsets
+   * of the two gradients inside the edge block of the flat gradient (they count in n_edge_params).  FFMA edge kernels. */
+  const float* attn_w;             /* interaction.scalar_message_attention.0.weight [1][s] */
+  const float* attn_b;             /* interaction.scalar_message_attention.0.bias [1] */
+  int32_t attn_grad_off[2];
 } gcpnet_layer;
 
 /* Destination- and source-sorted views of one graph batch, built by gcpnet_graph_build and shared

@@ -189,7 +189,10 @@ def gcp2(p: Dict[str, Tensor], prefix: str, s: Tensor, V: Tensor, edge_index: Te
     """SURVEY Appendix A steps 1-11.  ``p[prefix + 'scalar_out.weight']`` etc.
     Returns (s', V') or s' if the module has no vector output (no ``vector_up``)."""
     Wd = p[prefix + "vector_down.weight"]  # [hd, vi]
-    Ws, bs = p[prefix + "scalar_out.weight"], p[prefix + "scalar_out.bias"]
+    if (prefix + "scalar_out.weight") in p:
+        Ws, bs = p[prefix + "scalar_out.weight"], p[prefix + "scalar_out.bias"]
+    else:  # feedforward_out: an nn.Sequential, its first Linear is scalar_out.0
+        Ws, bs = p[prefix + "scalar_out.0.weight"], p[prefix + "scalar_out.0.bias"]
     Vt = V.transpose(-1, -2)  # [M,3,vi]  (gcpnet.py:418)
     H = Vt @ Wd.t()  # [M,3,hd]  (:420)
     n = safe_norm(H, dim=-2)  # [M,hd]    (:421)
@@ -200,6 +203,9 @@ def gcp2(p: Dict[str, Tensor], prefix: str, s: Tensor, V: Tensor, edge_index: Te
         q = frame_scalars(D, edge_index, frames, node_inputs, e3, V.shape[0], node_mask)  # (:427-435)
         z = torch.cat((z, q), dim=-1)  # (:436)
     t = z @ Ws.t() + bs  # (:441)
+    if (prefix + "scalar_out.2.weight") in p:
+        # GCP3 with feedforward_out (gcpnet.py:529-533): scalar_out = Linear -> scalar_out_nonlinearity (SiLU) -> Linear
+        t = F.silu(t) @ p[prefix + "scalar_out.2.weight"].t() + p[prefix + "scalar_out.2.bias"]
     if (prefix + "vector_up.weight") not in p:
         return act_s(t)  # (:443-446)
     Wu = p[prefix + "vector_up.weight"]  # [vo, hd]
@@ -250,6 +256,9 @@ def message_passing(p: Dict[str, Tensor], prefix: str, cfg: OracleConfig, h: Ten
         rs, rV = ms, mV
         for k in range(L):
             rs, rV = G(k, rs, rV)
+    if (prefix + "scalar_message_attention.0.weight") in p:  # learnable gate on the scalar messages (:931-934)
+        aw, ab = p[prefix + "scalar_message_attention.0.weight"], p[prefix + "scalar_message_attention.0.bias"]
+        rs = rs * torch.sigmoid(rs @ aw.t() + ab)
     flat = torch.cat((rs, rV.reshape(rV.shape[0], 3 * rV.shape[1])), dim=-1)  # flatten (comp:61-63)
     agg = segment_reduce(flat, row if aggregate_with_row else col, h.shape[0], reduce or cfg.reduce_function)  # (:946)
     so = rs.shape[1]
@@ -352,6 +361,113 @@ def interactions_forward(p: Dict[str, Tensor], cfg: OracleConfig, h: Tensor, chi
                  vector_gate=cfg.vector_gate, node_mask=node_mask)
     upd = (pV[:, 0, :] * cfg.node_positions_weight).clamp(min=-100, max=100)  # (:1156-1158)
     return (s, V), node_pos + upd  # (:1258)
+
+
+# --------------------------------------------------------------------------------------
+# GCPInteractions2.forward (gcpnet.py:1265-1451): the EQ / AR tasks' layer
+# --------------------------------------------------------------------------------------
+def interactions2_forward(p: Dict[str, Tensor], cfg: OracleConfig, h: Tensor, chi: Tensor, e: Tensor, xi: Tensor,
+                          edge_index: Tensor, frames: Tensor, node_pos: Optional[Tensor] = None, prefix: str = "",
+                          node_mask: Optional[Tensor] = None, aggregate_with_row: bool = False,
+                          drop_mask: Optional[Tuple[Tensor, Tensor]] = None):
+    """Message passing with reduce "sum" (:1284) (+ scalar message attention, + aggregate_with_row) -> concat with the layer
+    input (:1406) -> feed-forward GCPs on the FULL graph (:1409-1416), the last one with feedforward_out (:1316-1344) ->
+    dropout, residual, ONE GCPLayerNorm (:1419-1423) -> masked rows zeroed (:1426-1427) -> optional position update, masked
+    (:1433-1441).  ``drop_mask`` = already-scaled keep masks (scalars [N,s], vectors [N,v]) for train mode."""
+    a_s = activation(cfg.scalar_nonlinearity, cfg.nonlinearity_slope)
+    a_v = activation(cfg.vector_nonlinearity, cfg.nonlinearity_slope)
+    ident = activation(None)
+    e3 = cfg.enable_e3_equivariance
+    s, V = h, chi
+    if cfg.pre_norm:
+        s, V = gcp_layernorm(p, prefix + "gcp_norm.0.", cfg, s, V)
+    ms, mV = message_passing(p, prefix + "interaction.", cfg, s, V, e, xi, edge_index, frames, reduce="sum",
+                             node_mask=node_mask, aggregate_with_row=aggregate_with_row)
+    fs, fV = torch.cat((ms, s), dim=-1), torch.cat((mV, V), dim=-2)  # hidden_residual.concat((node_rep,)) (:1406)
+    nff = cfg.num_feedforward_layers
+    for i in range(nff):
+        first, last = i == 0, i == nff - 1
+        if first:
+            acts = (ident, ident) if nff == 1 else (a_s, a_v)  # (:1321)
+        elif last:
+            acts = (ident, ident)  # (:1338)
+        else:
+            acts = (a_s, a_v)
+        vres = cfg.vector_residual if not (first or last) else False  # ff_without_res_cfg (:1305-1306)
+        fs, fV = gcp2(p, f"{prefix}feedforward_network.{i}.", fs, fV, edge_index, frames, node_inputs=True,
+                      act_s=acts[0], act_v=acts[1], vector_residual=vres, e3=e3, vector_gate=cfg.vector_gate, node_mask=node_mask)
+    if drop_mask is not None:
+        fs, fV = fs * drop_mask[0], fV * drop_mask[1].unsqueeze(-1)
+    s, V = s + fs, V + fV  # (:1419)
+    if not cfg.pre_norm:
+        s, V = gcp_layernorm(p, prefix + "gcp_norm.0.", cfg, s, V)  # (:1422-1423)
+    if node_mask is not None:
+        m = node_mask.to(s.dtype)
+        s, V = s * m[:, None], V * m[:, None, None]  # ScalarVector.mask (:1427)
+    if not cfg.updating_node_positions:
+        return (s, V)
+    _, pV = gcp2(p, f"{prefix}node_position_update_gcp.", s, V, edge_index, frames, node_inputs=True, act_s=a_s, act_v=a_v,
+                 vector_residual=False, e3=e3, vector_gate=cfg.vector_gate, node_mask=node_mask)
+    pos = node_pos + pV[:, 0, :] * cfg.node_positions_weight  # derive_x_update (:1357-1378): no clamp here
+    if node_mask is not None:
+        pos = pos * node_mask.to(pos.dtype).unsqueeze(-1)  # (:1441)
+    return (s, V), pos
+
+
+def layer2_param_shapes(cfg: OracleConfig, message_attention: bool = True) -> Dict[str, Tuple[int, ...]]:
+    """Parameters of a GCPInteractions2 layer in state_dict order (gcpnet.py:1290-1356)."""
+    s, v = cfg.node_dims
+    se, ve = cfg.edge_dims
+    L = cfg.num_message_layers
+    var = dict(frames=not cfg.ablate_frame_updates, gate=cfg.vector_gate)
+    out: Dict[str, Tuple[int, ...]] = {}
+
+    def add(prefix, shapes, ffout=False):
+        for k, shp in shapes.items():
+            if ffout and k.startswith("scalar_out."):
+                k = k.replace("scalar_out.", "scalar_out.0.")
+            out[prefix + k] = shp
+            if ffout and k == "scalar_out.0.bias":
+                out[prefix + "scalar_out.2.weight"] = (shp[0], shp[0])
+                out[prefix + "scalar_out.2.bias"] = (shp[0],)
+
+    for k in range(L):
+        primary = k == 0 or k == L - 1
+        bn = cfg.default_bottleneck if primary else cfg.bottleneck
+        dims = (2 * s + se, 2 * v + ve) if k == 0 else (s, v)
+        add(f"interaction.message_fusion.{k}.", gcp2_param_shapes(*dims, s, v, bn, **var))
+    if message_attention:
+        out["interaction.scalar_message_attention.0.weight"] = (1, s)
+        out["interaction.scalar_message_attention.0.bias"] = (1,)
+    out["gcp_norm.0.scalar_norm.weight"] = (s,)
+    out["gcp_norm.0.scalar_norm.bias"] = (s,)
+    nff = cfg.num_feedforward_layers
+    hid = (s, v) if nff == 1 else (4 * s, 2 * v)
+    dims = [(2 * s, 2 * v)] + [hid] * (nff - 1) + [(s, v)]
+    for i in range(nff):
+        ffout = (i == 0 and nff == 1) or (i == nff - 1 and nff > 1)
+        add(f"feedforward_network.{i}.", gcp2_param_shapes(*dims[i], *dims[i + 1], cfg.bottleneck, **var), ffout=ffout)
+    if cfg.updating_node_positions:
+        add("node_position_update_gcp.", gcp2_param_shapes(s, v, s, 1, cfg.bottleneck, **var))
+    return out
+
+
+def random_params_for(shapes: Dict[str, Tuple[int, ...]], seed: int = 0, dtype=torch.float32) -> Dict[str, Tensor]:
+    """Seeded parameters for a name -> shape table (same distributions as random_layer_params)."""
+    g = torch.Generator().manual_seed(seed)
+    p: Dict[str, Tensor] = {}
+    for name, shp in shapes.items():
+        if "scalar_norm.weight" in name:
+            p[name] = (1 + 0.1 * torch.randn(shp, generator=g, dtype=torch.float64)).to(dtype)
+        elif "scalar_norm.bias" in name:
+            p[name] = (0.1 * torch.randn(shp, generator=g, dtype=torch.float64)).to(dtype)
+        elif name.endswith(".weight"):
+            bound = 1.0 / (shp[1] ** 0.5)
+            p[name] = ((torch.rand(shp, generator=g, dtype=torch.float64) * 2 - 1) * bound).to(dtype)
+        else:
+            fan_in = shapes[name.replace(".bias", ".weight")][1]
+            p[name] = ((torch.rand(shp, generator=g, dtype=torch.float64) * 2 - 1) / (fan_in ** 0.5)).to(dtype)
+    return p
 
 
 # --------------------------------------------------------------------------------------

@@ -281,3 +281,24 @@ def seeded_state_dict(shapes, seed: int):
             t = (torch.rand(shp, generator=g) * 2 - 1) / (shp[-1] ** 0.5)
         out[name] = t
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# GCPInteractions2 (gcpnet.py:1265-1451): the EQ / AR configs' layer, selected_GCP = GCP3
+# ------------------------------------------------------------------------------------------
+LAYER2_CASES: Dict[str, dict] = {
+    # configs/model/gcpnet_eq.yaml: (100, 16) / (32, 4), 8 message layers, ONE feed-forward GCP with feedforward_out, scalar
+    # message attention, aggregate_with_row, node mask (gcpnet_eq_module.py:205-214)
+    "eq_layer2": dict(cfg=dict(node_dims=(100, 16), edge_dims=(32, 4), num_feedforward_layers=1, reduce_function="sum"),
+                      graph=("knn", 2, 24, 6), seed=71, mask_frac=0.1, attention=True, aggregate_with_row=True),
+    # three feed-forward GCPs (first / middle with vector residual / last with feedforward_out), position update, no attention
+    "tiny_layer2_ff3_pos": dict(cfg=dict(node_dims=(16, 4), edge_dims=(8, 2), num_message_layers=2, bottleneck=2,
+                                         default_bottleneck=2, num_feedforward_layers=3, updating_node_positions=True,
+                                         vector_residual=True, scalar_nonlinearity="silu", reduce_function="sum"),
+                                graph=("random", 18, 90), seed=72, attention=False, aggregate_with_row=False),
+}
+
+
+def layer2_params(case: dict) -> Dict[str, torch.Tensor]:
+    cfg = build_cfg(case)
+    return O.random_params_for(O.layer2_param_shapes(cfg, message_attention=case["attention"]), seed=case["seed"])

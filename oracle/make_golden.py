@@ -160,6 +160,52 @@ def run_cpd_model(name: str):
     print(f"{name}: loss={loss.item():.6f} params={sum(v.numel() for v in sd.values())} -> {GC.fixture_path(name)}")
 
 
+def run_layer2(name: str, case: dict):
+    """The reference's GCPInteractions2 with selected_GCP = GCP3 (configs/model/gcpnet_eq.yaml), eval mode: outputs and ALL
+    gradients."""
+    ref = ref_shim.load_reference()
+    cfg = GC.build_cfg(case)
+    rcfg, rlayer = ref_shim.make_cfgs(
+        ref, num_message_layers=cfg.num_message_layers, pre_norm=cfg.pre_norm, num_feedforward_layers=cfg.num_feedforward_layers,
+        scalar_nonlinearity=cfg.scalar_nonlinearity, vector_nonlinearity=cfg.vector_nonlinearity, bottleneck=cfg.bottleneck,
+        vector_residual=cfg.vector_residual, enable_e3_equivariance=cfg.enable_e3_equivariance,
+        use_residual_message_gcp=cfg.use_residual_message_gcp, vector_gate=cfg.vector_gate,
+        ablate_frame_updates=cfg.ablate_frame_updates)
+    rcfg.default_bottleneck = cfg.default_bottleneck
+    rcfg.selected_GCP = ref.gcpnet.GCP3
+    rlayer.use_scalar_message_attention = bool(case["attention"])
+    rlayer.aggregate_with_row = bool(case["aggregate_with_row"])
+    SV = ref.ScalarVector
+    layer = ref.gcpnet.GCPInteractions2(SV(*cfg.node_dims), SV(*cfg.edge_dims), cfg=rcfg, layer_cfg=rlayer, dropout=0.1,
+                                        updating_node_positions=cfg.updating_node_positions)
+    params = GC.layer2_params(case)
+    assert list(params) == list(layer.state_dict()), "parameter names / order differ from the reference's state_dict"
+    layer.load_state_dict(params, strict=True)
+    layer.eval()
+    inp = GC.build_inputs(case)
+    leaves = {k: inp[k].clone().requires_grad_(True) for k in ("h", "chi", "e", "xi")}
+    out = layer((leaves["h"], leaves["chi"]), (leaves["e"], leaves["xi"]), inp["edge_index"], inp["frames"],
+                node_mask=inp.get("node_mask"), node_pos=inp["node_pos"] if cfg.updating_node_positions else None)
+    n = inp["h"].shape[0]
+    ch, cchi, cpos = GC.loss_weights(case, cfg, n)
+    if cfg.updating_node_positions:
+        (oh, ochi), opos = out
+        loss = (oh * ch).sum() + (ochi * cchi).sum() + (opos * cpos).sum()
+    else:
+        (oh, ochi), opos = out, None
+        loss = (oh * ch).sum() + (ochi * cchi).sum()
+    loss.backward()
+    rec = {"out_h": oh.detach().numpy(), "out_chi": ochi.detach().numpy(), "loss": np.float64(loss.item())}
+    if opos is not None:
+        rec["out_pos"] = opos.detach().numpy()
+    for k, t in leaves.items():
+        rec["grad_" + k] = t.grad.numpy()
+    for k, p in layer.named_parameters():
+        rec["pgrad/" + k] = sample(p.grad if p.grad is not None else torch.zeros_like(p))
+    np.savez_compressed(GC.fixture_path(name), **rec)
+    print(f"{name}: N={n} E={inp['edge_index'].shape[1]} loss={loss.item():.6f} -> {GC.fixture_path(name)}")
+
+
 def run_cpd_sampling():
     """GCPNetCPDLitModule.autoregressively_generate_samples (gcpnet_cpd_module.py:275-363), unmodified, on the seeded
     autoregressive model -- only the random draw is replaced: the module's ``Categorical`` is swapped for a recorder that
@@ -206,7 +252,8 @@ def main(argv):
         return 1
     torch.manual_seed(0)
     torch.set_num_threads(1)  # bitwise reproducible reductions
-    names = argv[1:] or (list(GC.CASES) + [GC.NMS_MODEL_FIXTURE, GC.CPD_CKPT_FIXTURE, GC.CPD_AR_FIXTURE, GC.CPD_SAMPLING_FIXTURE])
+    names = argv[1:] or (list(GC.CASES) + list(GC.LAYER2_CASES) +
+                         [GC.NMS_MODEL_FIXTURE, GC.CPD_CKPT_FIXTURE, GC.CPD_AR_FIXTURE, GC.CPD_SAMPLING_FIXTURE])
     for name in names:
         if name == GC.NMS_MODEL_FIXTURE:
             run_nms_model()
@@ -214,6 +261,8 @@ def main(argv):
             run_cpd_model(name)
         elif name == GC.CPD_SAMPLING_FIXTURE:
             run_cpd_sampling()
+        elif name in GC.LAYER2_CASES:
+            run_layer2(name, GC.LAYER2_CASES[name])
         else:
             run_reference(name, GC.CASES[name])
     return 0

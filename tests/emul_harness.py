@@ -47,7 +47,7 @@ def _p(a: np.ndarray) -> int:
     return a.ctypes.data
 
 
-def spec_from_oracle_cfg(cfg) -> _cabi.LayerSpec:
+def spec_from_oracle_cfg(cfg, message_attention: bool = False) -> _cabi.LayerSpec:
     return _cabi.LayerSpec(
         cfg.node_dims, cfg.edge_dims, num_message_layers=cfg.num_message_layers, bottleneck=cfg.bottleneck,
         default_bottleneck=cfg.default_bottleneck, vector_residual=cfg.vector_residual,
@@ -56,7 +56,7 @@ def spec_from_oracle_cfg(cfg) -> _cabi.LayerSpec:
         use_residual_message_gcp=cfg.use_residual_message_gcp, enable_e3_equivariance=cfg.enable_e3_equivariance,
         reduce_function=cfg.reduce_function, updating_node_positions=cfg.updating_node_positions,
         node_positions_weight=cfg.node_positions_weight, pre_norm=cfg.pre_norm,
-        ablate_frame_updates=cfg.ablate_frame_updates, vector_gate=cfg.vector_gate)
+        ablate_frame_updates=cfg.ablate_frame_updates, vector_gate=cfg.vector_gate, message_attention=message_attention)
 
 
 class EmulLayer:
@@ -65,7 +65,7 @@ class EmulLayer:
     def __init__(self, lib, cfg, params: Dict[str, torch.Tensor], inputs: Dict[str, torch.Tensor], *,
                  training=False, p_drop=0.0, seed=0):
         self.lib, self.cfg = lib, cfg
-        self.spec = spec_from_oracle_cfg(cfg)
+        self.spec = spec_from_oracle_cfg(cfg, "interaction.scalar_message_attention.0.weight" in params)
         self.flat = np.zeros(self.spec.n_params, dtype=np.float32)
         for name in self.spec.names:
             t = params[name].detach().to(torch.float32).numpy().reshape(-1)

@@ -255,3 +255,33 @@ def module_stack(layers, cfg, inputs, cots, device="cuda"):
         for k, p in layer.named_parameters():
             res[f"pgrad/{li}/{k}"] = p.grad.cpu() if p.grad is not None else torch.zeros_like(p).cpu()
     return res
+
+
+def oracle_layer2_forward_backward(case, dtype=torch.float32):
+    """GCPInteractions2 case of oracle/golden_cases.LAYER2_CASES through the oracle: outputs, input gradients, parameter
+    gradients (same loss as oracle/make_golden.run_layer2)."""
+    from oracle import golden_cases as GC
+    cfg = GC.build_cfg(case)
+    inp = GC.build_inputs(case)
+    params = {k: v.to(dtype).requires_grad_(True) for k, v in GC.layer2_params(case).items()}
+    lv = {k: inp[k].to(dtype).clone().requires_grad_(True) for k in ("h", "chi", "e", "xi")}
+    out = O.interactions2_forward(params, cfg, lv["h"], lv["chi"], lv["e"], lv["xi"], inp["edge_index"], inp["frames"].to(dtype),
+                                  node_pos=inp["node_pos"].to(dtype) if cfg.updating_node_positions else None,
+                                  node_mask=inp.get("node_mask"), aggregate_with_row=case["aggregate_with_row"])
+    n = inp["h"].shape[0]
+    ch, cchi, cpos = GC.loss_weights(case, cfg, n, dtype=dtype)
+    res = {}
+    if cfg.updating_node_positions:
+        (oh, ochi), opos = out
+        loss = (oh * ch).sum() + (ochi * cchi).sum() + (opos * cpos).sum()
+        res["out_pos"] = opos.detach()
+    else:
+        oh, ochi = out
+        loss = (oh * ch).sum() + (ochi * cchi).sum()
+    loss.backward()
+    res.update(out_h=oh.detach(), out_chi=ochi.detach(), loss=float(loss))
+    for k, t in lv.items():
+        res["grad_" + k] = t.grad
+    for k, t in params.items():
+        res["pgrad/" + k] = t.grad if t.grad is not None else torch.zeros_like(t)
+    return res

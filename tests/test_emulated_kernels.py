@@ -111,6 +111,28 @@ def test_emulated_segments_spanning_several_edge_tiles(lib, edge_tile):
     assert rel_err(agg, torch.cat((ms, mV.reshape(n, -1)), dim=1).numpy()) < TOL
 
 
+@pytest.mark.parametrize("residual,layers", [(True, 3), (False, 2), (True, 1)])
+def test_emulated_scalar_message_attention(lib, residual, layers):
+    """GCPMessagePassing(use_scalar_message_attention=True) (gcpnet.py:893-897,931-934): the scalar messages are scaled by
+    sigmoid(w . m_s + b) inside the edge kernels; forward, input gradients and the gradients of w and b against the oracle
+    (the oracle applies the attention whenever the two parameters are present)."""
+    from tests import emul_harness as EH
+    cfg = O.OracleConfig(node_dims=(16, 4), edge_dims=(8, 2), num_message_layers=layers, bottleneck=2, default_bottleneck=2,
+                         use_residual_message_gcp=residual, scalar_nonlinearity="silu")
+    params = O.random_layer_params(cfg, seed=61)
+    g = torch.Generator().manual_seed(8)
+    params["interaction.scalar_message_attention.0.weight"] = torch.randn(1, 16, generator=g) * 0.5
+    params["interaction.scalar_message_attention.0.bias"] = torch.randn(1, generator=g) * 0.5
+    n, E = 30, 170
+    ei = torch.randint(0, n, (2, E), generator=g)
+    inputs = O.synthetic_layer_inputs(cfg, ei, n, seed=62)
+    case = dict(seed=63)
+    res = oracle_forward_backward(case, cfg, params, inputs)
+    L = EH.EmulLayer(lib, cfg, params, inputs)
+    assert L.spec.names.index("interaction.scalar_message_attention.0.weight") == 7 * layers  # right behind message_fusion.*
+    _check(L, res, cfg, case, n)
+
+
 def test_emulated_message_passing_only(lib):
     """GCPMessagePassing.forward alone, reduce='add' (autoregressive layers, gcpnet.py:984)."""
     from tests import emul_harness as EH

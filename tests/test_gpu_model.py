@@ -312,3 +312,54 @@ def test_cpd_autoregressive_sampling_loop_matches_the_reference():
     drawn = model.autoregressively_generate_samples((raw["h"], raw["chi"]), (raw["e"], raw["xi"]), raw["edge_index"], frames,
                                                     raw["mask"], num_samples=2)
     assert tuple(drawn.shape) == (2, 24) and int(drawn.min()) >= 0 and int(drawn.max()) < 20
+
+
+@pytest.mark.parametrize("name", list(GC.LAYER2_CASES))
+def test_interactions2_layer_matches_the_reference_fixture_and_the_oracle(name):
+    """``GCPInteractions2`` with ``GCP3`` (gcpnet.py:1265-1451; configs/model/gcpnet_eq.yaml): message passing with reduce
+    "sum", scalar message attention and aggregate_with_row in the edge kernels, the feedforward_out GCP as two passes of the
+    GCP2 kernel, one GCPLayerNorm, masked rows zeroed, optional position update -- outputs and all gradients against the
+    reference's fixture."""
+    import gcpnet_b200
+    from tests.helpers import module_cfgs, oracle_layer2_forward_backward
+    case = GC.LAYER2_CASES[name]
+    cfg = GC.build_cfg(case)
+    fx = np.load(GC.fixture_path(name))
+    mcfg, lcfg = module_cfgs(cfg)
+    lcfg["use_scalar_message_attention"], lcfg["aggregate_with_row"] = case["attention"], case["aggregate_with_row"]
+    layer = gcpnet_b200.GCPInteractions2(cfg.node_dims, cfg.edge_dims, cfg=mcfg, layer_cfg=lcfg, dropout=0.1,
+                                         updating_node_positions=cfg.updating_node_positions)
+    layer.load_state_dict(GC.layer2_params(case), strict=True)
+    layer = layer.cuda().eval()
+    inp = GC.build_inputs(case)
+    lv = {k: inp[k].cuda().requires_grad_(True) for k in ("h", "chi", "e", "xi")}
+    mask = inp.get("node_mask")
+    out = layer((lv["h"], lv["chi"]), (lv["e"], lv["xi"]), inp["edge_index"].cuda(), inp["frames"].cuda(),
+                node_mask=None if mask is None else mask.cuda(), node_pos=inp["node_pos"].cuda() if cfg.updating_node_positions else None)
+    n = inp["h"].shape[0]
+    ch, cchi, cpos = (t.cuda() for t in GC.loss_weights(case, cfg, n))
+    if cfg.updating_node_positions:
+        (oh, ochi), opos = out
+        loss = (oh * ch).sum() + (ochi * cchi).sum() + (opos * cpos).sum()
+        assert rel_err(opos.detach().cpu().numpy(), fx["out_pos"]) < TOL
+    else:
+        oh, ochi = out
+        loss = (oh * ch).sum() + (ochi * cchi).sum()
+    loss.backward()
+    assert rel_err(oh.detach().cpu().numpy(), fx["out_h"]) < TOL and rel_err(ochi.detach().cpu().numpy(), fx["out_chi"]) < TOL
+    assert abs(float(loss) - float(fx["loss"])) < 1e-4 * max(1.0, abs(float(fx["loss"])))
+    for k in ("h", "chi", "e", "xi"):
+        assert rel_err(lv[k].grad.cpu().numpy(), fx["grad_" + k]) < TOL, k
+    want = oracle_layer2_forward_backward(case)
+    for k, p in layer.named_parameters():
+        assert p.grad is not None, k
+        assert rel_err(sample_like_fixture(p.grad.cpu()), fx["pgrad/" + k]) < TOL, k
+        assert rel_err(p.grad.cpu().numpy(), want["pgrad/" + k].numpy()) < TOL, k
+    # train mode runs (GCPDropout draws on the device) and keeps masked rows at zero
+    layer.train()
+    out = layer((lv["h"], lv["chi"]), (lv["e"], lv["xi"]), inp["edge_index"].cuda(), inp["frames"].cuda(),
+                node_mask=None if mask is None else mask.cuda(), node_pos=inp["node_pos"].cuda() if cfg.updating_node_positions else None)
+    th = out[0][0] if cfg.updating_node_positions else out[0]
+    assert torch.isfinite(th).all()
+    if mask is not None:
+        assert float(th[~mask.cuda()].abs().max()) == 0.0

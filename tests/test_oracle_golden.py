@@ -56,3 +56,20 @@ def test_safe_norm_double_eps():
     z = torch.zeros(2, 3, 4)
     n = safe_norm(z, dim=-2)
     assert torch.allclose(n, torch.full((2, 4), 1e-4 + 1e-8), rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("name", list(GC.LAYER2_CASES))
+def test_oracle_layer2_matches_reference_fixture(name):
+    """GCPInteractions2 with GCP3 (the EQ / AR configs' layer): the oracle against the reference's outputs and gradients."""
+    from tests.helpers import oracle_layer2_forward_backward
+    fx = np.load(GC.fixture_path(name))
+    res = oracle_layer2_forward_backward(GC.LAYER2_CASES[name])
+    for key in ("out_h", "out_chi", "out_pos", "grad_h", "grad_chi", "grad_e", "grad_xi"):
+        if key in fx.files:
+            assert rel_err(res[key].numpy(), fx[key]) < TOL, key
+    n_checked = 0
+    for key in fx.files:
+        if key.startswith("pgrad/"):
+            assert rel_err(sample_like_fixture(res[key]), fx[key]) < TOL, key
+            n_checked += 1
+    assert n_checked >= 20
