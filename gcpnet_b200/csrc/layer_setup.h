@@ -39,7 +39,7 @@ inline std::string check_gcp2(const gcpnet_gcp2& d, const char* name) {
   auto err = [&](const std::string& m) { return std::string(name) + ": " + m; };
   if (d.si <= 0 || d.vi <= 0 || d.so <= 0 || d.vo < 0) return err("dims must be positive (vo may be 0: scalar-only output, gcpnet.py:443-446)");
   if (d.so % 4 != 0) return err("scalar output dims must be multiples of 4 in this build");
-  if (d.hd <= 0 || d.hd > 16) return err("hidden vector dim must be in [1,16] (bottleneck too small for this build)");
+  if (d.hd <= 0 || d.hd > 32) return err("hidden vector dim must be in [1,32] (bottleneck too small for this build)");
   if (d.vector_residual && d.vi != d.vo) return err("vector_residual needs vi == vo");
   if (d.act_s < 0 || d.act_s > 5 || d.act_v < 0 || d.act_v > 5) return err("unknown nonlinearity");
   if (d.flags & ~(GCPNET_GCP2_NO_FRAMES | GCPNET_GCP2_NO_GATE)) return err("unknown flags");

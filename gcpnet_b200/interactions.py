@@ -575,8 +575,8 @@ class GCPMessagePassing(nn.Module):
             enable_e3_equivariance=bool(_get(cfg, "enable_e3_equivariance", False)), reduce_function=reduce_function,
             message_attention=self.use_scalar_message_attention, **variant)
         for m in self.spec.message_mods:
-            if not 1 <= m[5] <= 16:
-                raise NotImplementedError(f"gcpnet_b200.GCPMessagePassing: hidden vector dim {m[5]} (supported: 1..16)")
+            if not 1 <= m[5] <= 32:
+                raise NotImplementedError(f"gcpnet_b200.GCPMessagePassing: hidden vector dim {m[5]} (supported: 1..32)")
         self.message_fusion = nn.ModuleList([GCP2Params(*m[1:6], self.spec.gcp_flags) for m in self.spec.message_mods])
         if self.use_scalar_message_attention:  # gcpnet.py:893-897 (the Sigmoid of the Sequential runs inside the edge kernel)
             self.scalar_message_attention = nn.Sequential(nn.Linear(node_dims[0], 1), nn.Sigmoid())
@@ -695,8 +695,8 @@ class GCPInteractions(nn.Module):
             pre_norm=self.pre_norm, **variant)
         spec = self.spec
         for m in spec.message_mods + spec.ff_mods + ([spec.pos_mod] if spec.pos_mod else []):
-            if not 1 <= m[5] <= 16:
-                unsupported(f"hidden vector dim {m[5]} of {m[0]} (supported: 1..16)")
+            if not 1 <= m[5] <= 32:
+                unsupported(f"hidden vector dim {m[5]} of {m[0]} (supported: 1..32)")
 
         # parameters, in the reference's registration order and under its names
         self.interaction = _MessageParams(spec.message_mods, spec.gcp_flags)

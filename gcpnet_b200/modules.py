@@ -116,8 +116,8 @@ class GCP2(GCP2Params):
         if bottleneck > 1 and vi % bottleneck != 0:
             raise AssertionError(f"Input channel of vector ({vi}) must be divisible with bottleneck factor ({bottleneck})")
         hd = _cabi.gcp2_hidden_dim(vi, vo, int(bottleneck))
-        if not 1 <= hd <= 16:
-            unsupported(f"hidden vector dim {hd} (supported: 1..16)")
+        if not 1 <= hd <= 32:
+            unsupported(f"hidden vector dim {hd} (supported: 1..32)")
         if so % 4:
             unsupported("scalar output dims that are not multiples of 4")
         super().__init__(si, vi, so, vo, hd, flags)

@@ -291,6 +291,9 @@ LAYER2_CASES: Dict[str, dict] = {
     # message attention, aggregate_with_row, node mask (gcpnet_eq_module.py:205-214)
     "eq_layer2": dict(cfg=dict(node_dims=(100, 16), edge_dims=(32, 4), num_feedforward_layers=1, reduce_function="sum"),
                       graph=("knn", 2, 24, 6), seed=71, mask_frac=0.1, attention=True, aggregate_with_row=True),
+    # configs/model/gcpnet_ar.yaml dims: (100, 32) / (16, 4) -- the first message GCP has 68 vector inputs, hd = 17
+    "ar_layer2": dict(cfg=dict(node_dims=(100, 32), edge_dims=(16, 4), num_feedforward_layers=1, reduce_function="sum"),
+                      graph=("knn", 2, 20, 5), seed=73, attention=True, aggregate_with_row=True),
     # three feed-forward GCPs (first / middle with vector residual / last with feedforward_out), position update, no attention
     "tiny_layer2_ff3_pos": dict(cfg=dict(node_dims=(16, 4), edge_dims=(8, 2), num_message_layers=2, bottleneck=2,
                                          default_bottleneck=2, num_feedforward_layers=3, updating_node_positions=True,

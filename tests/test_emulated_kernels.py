@@ -133,6 +133,24 @@ def test_emulated_scalar_message_attention(lib, residual, layers):
     _check(L, res, cfg, case, n)
 
 
+def test_emulated_wide_hidden_vector_channels(lib):
+    """Hidden vector widths above 16 (bottleneck 1: hd = max(vi, vo); the AR config's first message GCP has hd = 17):
+    message GCP 0 with hd = 18, the feed-forward GCPs with hd = 16."""
+    from tests import emul_harness as EH
+    cfg = O.OracleConfig(node_dims=(20, 8), edge_dims=(4, 2), num_message_layers=2, bottleneck=1, default_bottleneck=1,
+                         updating_node_positions=True, scalar_nonlinearity="silu")
+    params = O.random_layer_params(cfg, seed=81)
+    assert params["interaction.message_fusion.0.vector_down.weight"].shape == (18, 18)
+    g = torch.Generator().manual_seed(9)
+    n, E = 26, 120
+    ei = torch.randint(0, n, (2, E), generator=g)
+    inputs = O.synthetic_layer_inputs(cfg, ei, n, seed=82)
+    case = dict(seed=83)
+    res = oracle_forward_backward(case, cfg, params, inputs)
+    L = EH.EmulLayer(lib, cfg, params, inputs)
+    _check(L, res, cfg, case, n)
+
+
 def test_emulated_message_passing_only(lib):
     """GCPMessagePassing.forward alone, reduce='add' (autoregressive layers, gcpnet.py:984)."""
     from tests import emul_harness as EH
