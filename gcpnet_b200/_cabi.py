@@ -221,7 +221,7 @@ class LayerSpec:
                  vector_nonlinearity=None, nonlinearity_slope=1e-2, use_residual_message_gcp=True,
                  enable_e3_equivariance=False, reduce_function="mean", updating_node_positions=False,
                  node_positions_weight=1.0, pre_norm=False, autoregressive=False, ablate_frame_updates=False, vector_gate=True,
-                 message_attention=False):
+                 message_attention=False, ff_hidden_dims=None):
         self.s, self.v = int(node_dims[0]), int(node_dims[1])
         self.gcp_flags = gcp2_flags(ablate_frame_updates, vector_gate)  # every GCP of a layer is built from one cfg
         self.se, self.ve = int(edge_dims[0]), int(edge_dims[1])
@@ -252,7 +252,9 @@ class LayerSpec:
                 raise AssertionError(f"Input channel of vector ({vi}) must be divisible with bottleneck factor ({bn})")
             mods.append((f"interaction.message_fusion.{k}.", si, vi, s, v, gcp2_hidden_dim(vi, v, bn), acts[0], acts[1], int(vres)))
         self.message_mods = mods
-        hs, hv = 4 * s, 2 * v  # gcpnet.py:1014 with num_feedforward_layers == 2
+        # gcpnet.py:1014 with num_feedforward_layers == 2.  (GCPMessagePassing on its own has no feed-forward GCPs: it passes
+        # the node dims so that the plan's node side stays small whatever the message dims are.)
+        hs, hv = (4 * s, 2 * v) if ff_hidden_dims is None else (int(ff_hidden_dims[0]), int(ff_hidden_dims[1]))
         self.hs, self.hv = hs, hv
         if bottleneck > 1 and (v % bottleneck != 0 or hv % bottleneck != 0):
             raise AssertionError("vector channels must be divisible by the bottleneck factor")

@@ -573,7 +573,7 @@ class GCPMessagePassing(nn.Module):
             scalar_nonlinearity=nl[0], vector_nonlinearity=nl[1], nonlinearity_slope=float(nonlinearity_slope),
             use_residual_message_gcp=bool(_get(mp_cfg, "use_residual_message_gcp", True)),
             enable_e3_equivariance=bool(_get(cfg, "enable_e3_equivariance", False)), reduce_function=reduce_function,
-            message_attention=self.use_scalar_message_attention, **variant)
+            message_attention=self.use_scalar_message_attention, ff_hidden_dims=node_dims, **variant)
         for m in self.spec.message_mods:
             if not 1 <= m[5] <= 32:
                 raise NotImplementedError(f"gcpnet_b200.GCPMessagePassing: hidden vector dim {m[5]} (supported: 1..32)")
