@@ -34,7 +34,7 @@ int gcp_tc_launch_pack(const tc::TcPackProg& prog, cudaStream_t st) {
 }
 
 int gcp_tc_launch_node_pre(const tc::TcEdgeParams& p, float* P, float* Q, cudaStream_t st) {
-  const long long total = (long long)p.N * (2 * p.pw + 192);
+  const long long total = (long long)((p.N + tc::PRE_NODES - 1) / tc::PRE_NODES) * (2 * p.pw + 192);  // PRE_NODES nodes per thread
   if (total <= 0) return 0;
   tc::tc_node_pre_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(p.h, p.chi, p.blob, p.nt, p.N, p.s, p.v, p.pw, P, Q);
   gcp_note_launches(1);

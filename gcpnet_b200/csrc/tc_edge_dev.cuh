@@ -77,40 +77,61 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const __grid_constant__ Tc
 // ------------------------------------------------------------------------------------------------
 // per-node pre-products of message GCP 0:  P[i] = [src | dst] x (T-part, g-part),  Q[i] = [src | dst] x 3 planes x 32
 // ------------------------------------------------------------------------------------------------
+constexpr int PRE_NODES = 4;  // nodes per thread: every weight load feeds four accumulators (the kernel is L1-bandwidth bound)
 __global__ void __launch_bounds__(256) tc_node_pre_kernel(const float* __restrict__ h, const float* __restrict__ chi,
                                                           const float* __restrict__ blob, TcNodeTiles nt, int N, int s, int v, int pw,
                                                           float* __restrict__ P, float* __restrict__ Q) {
   const int per = 2 * pw + 192;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= (long long)N * per) return;
-  const int i = (int)(idx / per), o = (int)(idx - (long long)i * per);
-  float acc = 0.f;
+  const int groups = (N + PRE_NODES - 1) / PRE_NODES;
+  if (idx >= (long long)groups * per) return;
+  const int grp = (int)(idx / per), o = (int)(idx - (long long)grp * per);
+  const int i0 = grp * PRE_NODES;
+  int row[PRE_NODES];
+#pragma unroll
+  for (int r = 0; r < PRE_NODES; ++r) row[r] = i0 + r < N ? i0 + r : N - 1;  // clamped loads; stores are guarded
+  float acc[PRE_NODES];
+#pragma unroll
+  for (int r = 0; r < PRE_NODES; ++r) acc[r] = 0.f;
   if (o < 2 * pw) {
     const int side = o / pw, c = o - side * pw;
     const float* B = blob + (side ? nt.pd : nt.ps);  // [pw][s] slab, pitch pw
-    const float* hp = h + (size_t)i * s;
-    // s % 16 == 0 on this path: 16-byte loads, four columns per step; ONE accumulator in column order (the summation
-    // order is part of the pinned numerics: ReLU units at ~0 flip with it, tests/test_gpu_parity.py)
-#pragma unroll 4
+    // s % 16 == 0 on this path: 16-byte loads, four columns per step; ONE accumulator per output in column order (the
+    // summation order is part of the pinned numerics: ReLU units at ~0 flip with it, tests/test_gpu_parity.py)
+#pragma unroll 2
     for (int j4 = 0; j4 < (s >> 2); ++j4) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(B + (j4 * pw + c) * 4));
-      const float4 x = __ldg(reinterpret_cast<const float4*>(hp) + j4);
-      acc = fmaf(b.x, x.x, acc); acc = fmaf(b.y, x.y, acc); acc = fmaf(b.z, x.z, acc); acc = fmaf(b.w, x.w, acc);
+#pragma unroll
+      for (int r = 0; r < PRE_NODES; ++r) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(h + (size_t)row[r] * s) + j4);
+        acc[r] = fmaf(b.x, x.x, acc[r]); acc[r] = fmaf(b.y, x.y, acc[r]); acc[r] = fmaf(b.z, x.z, acc[r]); acc[r] = fmaf(b.w, x.w, acc[r]);
+      }
     }
-    P[(size_t)i * 2 * pw + o] = acc;
+#pragma unroll
+    for (int r = 0; r < PRE_NODES; ++r)
+      if (i0 + r < N) P[(size_t)(i0 + r) * 2 * pw + o] = acc[r];
   } else {
     const int o2 = o - 2 * pw;
     const int side = o2 / 96, x = (o2 - side * 96) / 32, c = o2 & 31;
     const float* B = blob + (side ? nt.qd : nt.qs);  // [32][v8] slab, pitch 32
-    const float* cp = chi + (size_t)i * 3 * v + x;
     int ch = 0;
     for (; ch + 4 <= v; ch += 4) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(B + ((ch >> 2) * 32 + c) * 4));
-      acc = fmaf(b.x, __ldg(cp + 3 * ch), acc); acc = fmaf(b.y, __ldg(cp + 3 * ch + 3), acc);
-      acc = fmaf(b.z, __ldg(cp + 3 * ch + 6), acc); acc = fmaf(b.w, __ldg(cp + 3 * ch + 9), acc);
+#pragma unroll
+      for (int r = 0; r < PRE_NODES; ++r) {
+        const float* cp = chi + (size_t)row[r] * 3 * v + x;
+        acc[r] = fmaf(b.x, __ldg(cp + 3 * ch), acc[r]); acc[r] = fmaf(b.y, __ldg(cp + 3 * ch + 3), acc[r]);
+        acc[r] = fmaf(b.z, __ldg(cp + 3 * ch + 6), acc[r]); acc[r] = fmaf(b.w, __ldg(cp + 3 * ch + 9), acc[r]);
+      }
     }
-    for (; ch < v; ++ch) acc = fmaf(__ldg(B + ((ch >> 2) * 32 + c) * 4 + (ch & 3)), __ldg(cp + 3 * ch), acc);
-    Q[(size_t)i * 192 + o2] = acc;
+    for (; ch < v; ++ch) {
+      const float b = __ldg(B + ((ch >> 2) * 32 + c) * 4 + (ch & 3));
+#pragma unroll
+      for (int r = 0; r < PRE_NODES; ++r) acc[r] = fmaf(b, __ldg(chi + (size_t)row[r] * 3 * v + x + 3 * ch), acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < PRE_NODES; ++r)
+      if (i0 + r < N) Q[(size_t)(i0 + r) * 192 + o2] = acc[r];
   }
 }
 
