@@ -63,7 +63,7 @@ class Plan(C.Structure):
         ("edge_partial_floats", C.c_int64), ("node_partial_floats", C.c_int64),
         ("edge_cotangent_floats", C.c_int64), ("agg_cotangent_floats", C.c_int64), ("packed_floats", C.c_int64),
         ("tc_edge_path", C.c_int32), ("reserved", C.c_int32),
-        ("prenorm_floats", C.c_int64), ("prenorm_ws_floats", C.c_int64),
+        ("prenorm_floats", C.c_int64), ("prenorm_ws_floats", C.c_int64), ("edge_spill_floats", C.c_int64),
     ]
 
 
@@ -84,7 +84,7 @@ class BackwardIO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("h", "chi", "e", "xi", "frames", "saved_edge", "saved_node", "g_out_h", "g_out_chi", "g_out_pos",
                  "g_h", "g_chi", "g_e", "g_xi", "g_params", "ws_agg", "ws_edge", "ws_edge_partial", "ws_node_partial",
-                 "packed", "h_gather", "chi_gather", "g_h_gather", "g_chi_gather", "prenorm", "ws_prenorm")]
+                 "packed", "h_gather", "chi_gather", "g_h_gather", "g_chi_gather", "prenorm", "ws_prenorm", "ws_edge_spill")]
 
 
 EXPORTS = (

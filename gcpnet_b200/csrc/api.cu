@@ -180,14 +180,18 @@ __global__ void ar_cotangent_reduce_kernel(float* __restrict__ g_hg, float* __re
 // flat parameter gradient = fixed-order sum of the per-CTA partial rows
 // `skip`: ranges of the NODE part that the tiles did not produce (their operands were spilled for node_wgrad_kernel, which
 // writes those gradients itself): neither read nor written here
-struct SkipRanges { int n; int off[14], len[14]; };
+struct SkipRanges { int n; int off[2 * MAX_MSG_LAYERS + 2], len[2 * MAX_MSG_LAYERS + 2]; };
 __global__ void partial_reduce_kernel(float* __restrict__ out, const float* __restrict__ pe, int ne, int ge,
-                                      const float* __restrict__ pn, int nn, int gn, const SkipRanges skip) {
+                                      const float* __restrict__ pn, int nn, int gn, const SkipRanges skip,
+                                      const SkipRanges eskip = SkipRanges{}) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= ne + nn) return;
   float acc = 0.f;
-  if (idx < ne) { for (int g = 0; g < ge; ++g) acc += __ldg(pe + (size_t)g * ne + idx); }
-  else {
+  if (idx < ne) {
+    for (int r = 0; r < eskip.n; ++r)  // produced by the off-tile product over all edges (launch_edge_wgrad)
+      if (idx >= eskip.off[r] && idx < eskip.off[r] + eskip.len[r]) return;
+    for (int g = 0; g < ge; ++g) acc += __ldg(pe + (size_t)g * ne + idx);
+  } else {
     const int j = idx - ne;
     for (int r = 0; r < skip.n; ++r)
       if (j >= skip.off[r] && j < skip.off[r] + skip.len[r]) return;
@@ -201,7 +205,7 @@ static SkipRanges node_wgrad_ranges(const gcpnet_layer& l, const LayerPlan& lp) 
   const GcpOp* op[3] = {&lp.ops.ff0, &lp.ops.ff1, l.has_pos ? &lp.ops.pu : nullptr};
   auto add = [&](int off, int len) {  // merge with the previous range when contiguous (weight followed by its bias)
     if (s.n > 0 && s.off[s.n - 1] + s.len[s.n - 1] == off) { s.len[s.n - 1] += len; return; }
-    if (s.n < 14) { s.off[s.n] = off; s.len[s.n] = len; ++s.n; }
+    if (s.n < 2 * MAX_MSG_LAYERS + 2) { s.off[s.n] = off; s.len[s.n] = len; ++s.n; }
   };
   if (l.pre_norm) {  // gcp_norm.0 belongs to the standalone normalisation in front of the layer (run_prenorm_backward)
     add(l.ln_grad_off[0] - l.n_edge_params, l.s); add(l.ln_grad_off[1] - l.n_edge_params, l.s);
@@ -407,6 +411,52 @@ static int launch_node_wgrad(const gcpnet_layer& l, const gcpnet_graph& g, const
   node_wgrad_kernel<<<cta, 256, 0, st>>>(p);
   gcp_note_launches(1);
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// FFMA edge backward with spilled operands: scalar_out / vector_out_scale weight gradients of every message GCP as one
+// output-parallel product over all edges, written straight into the flat gradient
+static SkipRanges edge_wgrad_ranges(const LayerPlan& lp) {
+  SkipRanges s{};
+  for (int k = 0; k < lp.ops.L; ++k) {
+    const GcpOp& o = lp.ops.msg[k];
+    s.off[s.n] = o.o_Ws; s.len[s.n] = o.so * gcp_k(o) + o.so; ++s.n;  // weight followed by its bias
+    if (gcp_gated(o)) { s.off[s.n] = o.o_Wg; s.len[s.n] = o.vo * o.so + o.vo; ++s.n; }
+  }
+  return s;
+}
+static int launch_edge_wgrad(const gcpnet_layer& l, const gcpnet_graph& g, const LayerPlan& lp, float* spill, const float* saved_edge,
+                             float* g_edge_params, cudaStream_t st) {
+  const long long E = g.num_edges;
+  const EdgeSpill sp = edge_spill_layout(E, lp.ops);
+  long long offT[MAX_MSG_LAYERS], offG[MAX_MSG_LAYERS], offS[MAX_MSG_LAYERS], offV[MAX_MSG_LAYERS], tot;
+  edge_saved_offsets(l, E, offT, offG, offS, offV, &tot);
+  NodeWgradParams p{};
+  p.N = (int)E; p.slope = l.slope;
+  p.chunk_rows = EDGE_WGRAD_CHUNK_ROWS; p.nchunks = sp.nchunks; p.out_total = sp.out_total; p.scratch = spill + sp.scratch;
+  int cta = 0, out0 = 0;
+  auto add = [&](const float* G, int ldg, int J, const float* Z, int ldz, int I, int act, float* outW, float* outb) {
+    NodeWgradJob& j = p.job[p.njobs++];
+    j.G = G; j.ldg = ldg; j.J = J; j.Z = Z; j.ldz = ldz; j.I = I; j.act = act; j.outW = outW; j.outb = outb;
+    j.JB = (J + 15) / 16; j.IG = ((I + 7) / 8 + 3) / 4; j.cta0 = cta; j.out0 = out0;
+    cta += j.JB * j.IG;
+    out0 += J * I + J;
+  };
+  for (int k = 0; k < lp.ops.L; ++k) {
+    const GcpOp& o = lp.ops.msg[k];
+    add(spill + sp.gT[k], sp.ldg[k], o.so, spill + sp.Z[k], sp.ldz[k], gcp_k(o), ACT_NONE, g_edge_params + o.o_Ws, g_edge_params + o.o_bs);
+    if (gcp_gated(o))  // vector_out_scale reads act_v(T): the saved pre-activations of the forward pass
+      add(spill + sp.GG[k], sp.ldgg[k], o.vo, saved_edge + offT[k], o.so, o.so, o.act_v, g_edge_params + o.o_Wg, g_edge_params + o.o_bg);
+  }
+  if (out0 != sp.out_total) return fail("edge_wgrad: output layout mismatch");
+  node_wgrad_kernel<<<dim3(cta, p.nchunks), 256, 0, st>>>(p);
+  gcp_note_launches(1);
+  CUDA_TRY(cudaGetLastError());
+  if (p.nchunks > 1) {
+    wgrad_chunk_reduce_kernel<<<(p.out_total + 255) / 256, 256, 0, st>>>(p);
+    gcp_note_launches(1);
+    CUDA_TRY(cudaGetLastError());
+  }
   return 0;
 }
 
@@ -657,6 +707,11 @@ static int run_ffma_edge_backward(const gcpnet_layer& l, const gcpnet_graph& g, 
   ep.grow = io.ws_edge; ep.gcol = io.ws_edge + (size_t)g.num_edges * W;
   ep.ge = io.g_e; ep.gxi = io.g_xi;
   ep.partial = io.ws_edge_partial;
+  if (io.ws_edge_spill != nullptr) {
+    const EdgeSpill sp = edge_spill_layout(g.num_edges, lp.ops);
+    ep.spill = io.ws_edge_spill;
+    for (int k = 0; k < lp.ops.L; ++k) { ep.sp_gT[k] = sp.gT[k]; ep.sp_Z[k] = sp.Z[k]; ep.sp_GG[k] = sp.GG[k]; }
+  }
   ep.dbg = g_tc_dbg.load(std::memory_order_relaxed);
   *edge_grid = lp.eb.grid;
   if (launch_edge_bwd(ep, lp.eb, st)) return 1;
@@ -753,12 +808,20 @@ static int layer_backward_body(const gcpnet_layer* layer, const gcpnet_graph* gr
   int edge_grid = 0;
   if (run_ffma_edge_backward(l, g, lp, *io, io->ws_agg, st, &edge_grid)) return 1;
   const int np_tot = l.n_edge_params + l.n_node_params;
-  GcpTimedScope timed(T_PARTIAL_REDUCE, st);
-  partial_reduce_kernel<<<(np_tot + 255) / 256, 256, 0, st>>>(io->g_params, io->ws_edge_partial, l.n_edge_params, edge_grid,
-                                                           io->ws_node_partial, l.n_node_params, lp.nb.grid, node_wgrad_ranges(l, lp));
-  gcp_note_launches(1);
-  CUDA_TRY(cudaGetLastError());
-  if (launch_node_wgrad(l, g, lp, io->ws_node_partial, io->saved_node, io->g_params + l.n_edge_params, st)) return 1;
+  const bool spilled = io->ws_edge_spill != nullptr && g.num_edges > 0;
+  // everything below only feeds the parameter gradient: side stream when the caller gave one
+  cudaStream_t ps = fork_side(st);
+  {
+    GcpTimedScope timed(T_PARTIAL_REDUCE, ps);
+    partial_reduce_kernel<<<(np_tot + 255) / 256, 256, 0, ps>>>(io->g_params, io->ws_edge_partial, l.n_edge_params, edge_grid,
+                                                             io->ws_node_partial, l.n_node_params, lp.nb.grid, node_wgrad_ranges(l, lp),
+                                                             spilled ? edge_wgrad_ranges(lp) : SkipRanges{});
+    gcp_note_launches(1);
+    CUDA_TRY(cudaGetLastError());
+    if (launch_node_wgrad(l, g, lp, io->ws_node_partial, io->saved_node, io->g_params + l.n_edge_params, ps)) return 1;
+    if (spilled && launch_edge_wgrad(l, g, lp, io->ws_edge_spill, io->saved_edge, io->g_params, ps)) return 1;
+  }
+  if (ps != st && side_done(ps, st)) return 1;
   return 0;
 }
 

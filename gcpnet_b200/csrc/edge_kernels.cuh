@@ -41,6 +41,11 @@ struct EdgeParams {
   float *ge, *gxi;                         // [E][se], [E][3ve] caller's edge order
   float* partial;                          // [grid][partial_stride] per-CTA weight-gradient partials
   int partial_stride;
+  // off-tile weight gradients of scalar_out / vector_out_scale: the tiles spill their rows of gT [so -> 4], Z [K -> 4] and
+  // gg [vo -> 4] per message GCP (dense rows, sorted edge order) and edge_wgrad (node_wgrad.cuh) forms the products over ALL
+  // edges -- instead of read-modify-writing 12 k partial sums per tile and GCP.  nullptr: the tiles form them.
+  float* spill;
+  long long sp_gT[MAX_MSG_LAYERS], sp_Z[MAX_MSG_LAYERS], sp_GG[MAX_MSG_LAYERS];
   EdgeSmem sm;
   GcpOp ops[MAX_MSG_LAYERS];
   WSeq seq;                                // chunk order of this kernel (forward or backward)
@@ -198,6 +203,10 @@ GCP_HDN void edge_bwd_tile(const EdgeParams& p, float* sm, int tile, WPipe& wp, 
   for (int k = p.L - 1; k >= 0; --k) {
     const GcpOp& op = p.ops[k];
     const TileBufs b = edge_bufs(p, sm, k);
+    if (p.spill != nullptr) {
+      g.sp_gT = p.spill + p.sp_gT[k]; g.sp_Z = p.spill + p.sp_Z[k]; g.sp_GG = p.spill + p.sp_GG[k];
+      g.sp_row0 = row0; g.sp_nrows = nrows;
+    }
     GCP_PHASE_BEGIN(NT)
     const int lane = tid & 31;
     if (k == p.L - 1) {

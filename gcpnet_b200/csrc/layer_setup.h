@@ -284,6 +284,35 @@ struct LayerPlan {
 // rows per tile of the edge forward kernel this plan launches (layout of the segment sums, segment_total in gcp_tile.cuh)
 inline int edge_tile_rows(const LayerPlan& lp) { return lp.tc.ok ? lp.tc.proto.rows : lp.ef.TE; }
 
+// Spill area of the FFMA edge backward (ws_edge_spill): per message GCP dense row matrices gT [E][so -> 4], Z [E][K -> 4],
+// gg [E][vo -> 4] in sorted edge order (EdgeParams::spill, node_wgrad.cuh).  Beyond EDGE_SPILL_MAX_FLOATS the tiles keep
+// forming the products themselves.
+constexpr long long EDGE_SPILL_MAX_FLOATS = 1ll << 31;  // 8 GB
+constexpr int EDGE_WGRAD_CHUNK_ROWS = 4096;            // rows (edges) per CTA of the product kernel
+struct EdgeSpill {
+  long long gT[MAX_MSG_LAYERS], Z[MAX_MSG_LAYERS], GG[MAX_MSG_LAYERS], total;
+  int ldg[MAX_MSG_LAYERS], ldz[MAX_MSG_LAYERS], ldgg[MAX_MSG_LAYERS];
+  long long scratch; int nchunks, out_total;  // partial blocks of the row chunks: [nchunks][out_total] behind the operand rows
+};
+inline EdgeSpill edge_spill_layout(long long E, const LayerOps& ops) {
+  EdgeSpill sp{};
+  long long off = 0;
+  for (int k = 0; k < ops.L; ++k) {
+    const GcpOp& op = ops.msg[k];
+    sp.ldg[k] = round_up(op.so, 4); sp.ldz[k] = round_up(gcp_k(op), 4); sp.ldgg[k] = round_up(op.vo, 4);
+    sp.gT[k] = off; off += E * sp.ldg[k];
+    sp.Z[k] = off; off += E * sp.ldz[k];
+    sp.GG[k] = off; off += E * sp.ldgg[k];
+    sp.out_total += op.so * gcp_k(op) + op.so + (gcp_gated(op) ? op.vo * op.so + op.vo : 0);
+  }
+  sp.nchunks = (int)((E + EDGE_WGRAD_CHUNK_ROWS - 1) / EDGE_WGRAD_CHUNK_ROWS);
+  if (sp.nchunks < 1) sp.nchunks = 1;
+  sp.scratch = off;
+  if (sp.nchunks > 1) off += (long long)sp.nchunks * sp.out_total;
+  sp.total = off;
+  return sp;
+}
+
 // Spill area of the node backward (behind the per-CTA partial rows in ws_node_partial): per GCP dense row matrices
 // gT [N][so -> 4], Z [N][K -> 4], gg [N][vo -> 4]  (BwdBufs::sp_*, node_wgrad.cuh).
 struct NodeSpill { long long gT[3], Z[3], GG[3], total; int ldg[3], ldz[3], ldgg[3]; };
@@ -354,6 +383,10 @@ inline std::string make_layer_plan(const gcpnet_layer& l, long long N, long long
     p.saved_node_floats = node_saved_layout((int)N, l.s, l.v, l.ff0.so, l.ff0.vo, l.has_pos != 0, l.training != 0).total;
     p.edge_partial_floats = (long long)p.edge_grid_bwd * l.n_edge_params;
     if (lp->tc.ok) p.edge_partial_floats = lp->tc.partial_floats;
+    {
+      const long long sp = edge_spill_layout(E, lp->ops).total;
+      p.edge_spill_floats = (!lp->tc.ok && E > 0 && sp <= EDGE_SPILL_MAX_FLOATS) ? sp : 0;
+    }
     p.node_partial_floats = node_spill_offset(p.node_grid_bwd, l.n_node_params) + node_spill_layout(N, lp->ops, l.has_pos != 0).total;
     p.edge_cotangent_floats = 2 * E * W;
     if (lp->tc.ok)  // [Y | A | G | Gn | node partials]

@@ -11,17 +11,22 @@
 
 namespace gcp {
 
-constexpr int NODE_WGRAD_MAX_JOBS = 6;
+constexpr int NODE_WGRAD_MAX_JOBS = 2 * MAX_MSG_LAYERS;  // node update: <= 6; FFMA edge backward: two per message GCP
 struct NodeWgradJob {
   const float* G; const float* Z;  // [N][ldg], [N][ldz]
   float* outW; float* outb;        // [J][I], [J]
   int ldg, J, ldz, I;
   int act;                         // activation applied to Z on the fly (vector_out_scale reads act_v(T))
   int cta0, JB, IG;                // first CTA of the job, 16-row blocks of J, 32-column groups of I
+  int out0;                        // chunked mode: offset of this job's [J][I] | [J] block inside one scratch row
 };
+// Many rows (the edge path: rows = edges): grid.y row chunks of `chunk_rows` rows each write their partial blocks into
+// scratch[chunk][out_total]; wgrad_chunk_reduce_kernel adds the chunks in order.  nchunks == 1: results go straight to outW / outb.
 struct NodeWgradParams {
   int N, njobs;
   float slope;
+  int chunk_rows, nchunks, out_total;
+  float* scratch;
   NodeWgradJob job[NODE_WGRAD_MAX_JOBS];
 };
 
@@ -34,7 +39,11 @@ __global__ void __launch_bounds__(256) node_wgrad_kernel(const __grid_constant__
   const int local = (int)blockIdx.x - jb.cta0;
   const int ig = local / jb.JB, jblk = local - ig * jb.JB;
   const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int J = jb.J, I = jb.I, N = p.N;
+  const int J = jb.J, I = jb.I;
+  const int nbeg = p.nchunks > 1 ? (int)blockIdx.y * p.chunk_rows : 0;
+  const int N = p.nchunks > 1 ? (nbeg + p.chunk_rows < p.N ? nbeg + p.chunk_rows : p.N) : p.N;  // rows [nbeg, N)
+  float* outW = p.nchunks > 1 ? p.scratch + (size_t)blockIdx.y * p.out_total + jb.out0 : jb.outW;
+  float* outb = p.nchunks > 1 ? outW + (size_t)J * I : jb.outb;
   const int IB = (I + 7) >> 3;
   const int nb = IB - 4 * ig < 4 ? IB - 4 * ig : 4;
   const int j0 = 16 * jblk + g;
@@ -50,7 +59,7 @@ __global__ void __launch_bounds__(256) node_wgrad_kernel(const __grid_constant__
   const int act = jb.act;
   const float slope = p.slope;
 #pragma unroll 2
-  for (int n0 = 8 * warp; n0 < N; n0 += 64) {
+  for (int n0 = nbeg + 8 * warp; n0 < N; n0 += 64) {
     const int r0 = n0 + t, r1 = n0 + t + 4;
     const bool v0 = r0 < N, v1 = r1 < N;
     const float* g0 = jb.G + (size_t)(v0 ? r0 : 0) * jb.ldg;
@@ -95,7 +104,7 @@ __global__ void __launch_bounds__(256) node_wgrad_kernel(const __grid_constant__
     const int bb = slot >> 2, q = slot & 3;
     const int j = 16 * jblk + (ln >> 2) + 8 * (q >> 1);
     const int i = 8 * (4 * ig + bb) + 2 * (ln & 3) + (q & 1);
-    if (bb < nb && j < J && i < I) jb.outW[(size_t)j * I + i] = s;
+    if (bb < nb && j < J && i < I) outW[(size_t)j * I + i] = s;
   }
   if (ig == 0 && jb.outb != nullptr) {  // bias gradient of this block's 16 rows of J: 16 row-partitions, fixed-order sum
     __syncthreads();
@@ -103,16 +112,32 @@ __global__ void __launch_bounds__(256) node_wgrad_kernel(const __grid_constant__
     const int j = 16 * jblk + jj;
     float s = 0.f;
     if (j < J)
-      for (int n = part; n < N; n += 16) s += __ldg(jb.G + (size_t)n * jb.ldg + j);
+      for (int n = nbeg + part; n < N; n += 16) s += __ldg(jb.G + (size_t)n * jb.ldg + j);
     red[0][part][jj] = s;
     __syncthreads();
     if (tid < 16 && 16 * jblk + tid < J) {
       float a = 0.f;
 #pragma unroll
       for (int q = 0; q < 16; ++q) a += red[0][q][tid];
-      jb.outb[16 * jblk + tid] = a;
+      outb[16 * jblk + tid] = a;
     }
   }
+#endif
+}
+
+// chunked mode: out = sum over the row chunks, in chunk order (deterministic)
+__global__ void __launch_bounds__(256) wgrad_chunk_reduce_kernel(const __grid_constant__ NodeWgradParams p) {
+#if GCP_DEVICE_CODE
+  const int idx = (int)(blockIdx.x * 256 + threadIdx.x);
+  if (idx >= p.out_total) return;
+  int jn = 0;
+  while (jn + 1 < p.njobs && idx >= p.job[jn + 1].out0) ++jn;
+  const NodeWgradJob& jb = p.job[jn];
+  const int local = idx - jb.out0, nw = jb.J * jb.I;
+  float s = 0.f;
+  for (int c = 0; c < p.nchunks; ++c) s += __ldg(p.scratch + (size_t)c * p.out_total + idx);
+  if (local < nw) jb.outW[local] = s;
+  else if (jb.outb != nullptr) jb.outb[local - nw] = s;
 #endif
 }
 

@@ -409,10 +409,12 @@ class _LayerFn(torch.autograd.Function):
         g_params = sink if sink is not None else f32(spec.n_params)
         ws_agg, ws_edge = f32(plan.agg_cotangent_floats), f32(plan.edge_cotangent_floats)
         ws_ep, ws_np = f32(plan.edge_partial_floats), f32(plan.node_partial_floats)
+        # FFMA edge kernels: operand rows of the off-tile weight-gradient product over all edges
+        ws_spill = f32(plan.edge_spill_floats) if plan.edge_spill_floats > 0 else None
         io = _cabi.BackwardIO(_ptr(h), _ptr(chi), _ptr(e), _ptr(xi), _ptr(frames), _ptr(saved_edge), _ptr(saved_node),
                               _ptr(g_out_h), _ptr(g_out_chi), _ptr(g_out_pos), _ptr(g_h), _ptr(g_chi), _ptr(g_e),
                               _ptr(g_xi), _ptr(g_params), _ptr(ws_agg), _ptr(ws_edge), _ptr(ws_ep), _ptr(ws_np), _ptr(packed),
-                              _ptr(hg), _ptr(chig), _ptr(g_hg), _ptr(g_chig), _ptr(prenorm), _ptr(ws_pre))
+                              _ptr(hg), _ptr(chig), _ptr(g_hg), _ptr(g_chig), _ptr(prenorm), _ptr(ws_pre), _ptr(ws_spill))
         _lib.check(lib.gcpnet_layer_backward(C.byref(layer), C.byref(gv.struct), C.byref(plan), C.byref(io), _stream()),
                    "gcpnet_layer_backward")
         if gv.E == 0:
@@ -425,7 +427,7 @@ class _LayerFn(torch.autograd.Function):
         if sink is not None:
             # nobody reads the parameter gradients during this backward pass: deferred join, side work overlaps
             hook = mod._grad_hook
-            _defer_join((ws_agg, ws_edge, ws_ep, ws_np, saved_edge, saved_node, packed, h, chi, prenorm, ws_pre),
+            _defer_join((ws_agg, ws_edge, ws_ep, ws_np, saved_edge, saved_node, packed, h, chi, prenorm, ws_pre, ws_spill),
                         None if hook is None else hook(mod, sink))
             return head + (None,) * len(params)
         # autograd (AccumulateGrad, tensor hooks, DDP reducer) may read the gradients as soon as this returns

@@ -134,6 +134,7 @@ typedef struct gcpnet_plan {
   int32_t reserved;
   int64_t prenorm_floats;        /* pre_norm: N * (s+3v) normalised layer input (forward, kept for backward) */
   int64_t prenorm_ws_floats;     /* pre_norm: backward workspace (cotangent of the normalised input, row statistics, partials) */
+  int64_t edge_spill_floats;     /* FFMA edge backward: operand rows of the off-tile weight-gradient product (0: not used) */
 } gcpnet_plan;
 
 typedef struct gcpnet_forward_io {
@@ -163,6 +164,10 @@ typedef struct gcpnet_backward_io {
                                                     carry the direct cotangent of node i, g_h / g_chi are then scratch */
   const float* prenorm;                          /* pre_norm: the forward's normalised input */
   float* ws_prenorm;                             /* plan.prenorm_ws_floats */
+  float* ws_edge_spill;                          /* plan.edge_spill_floats (FFMA edge kernels): per message GCP the rows of gT, Z and
+                                                    gg of every edge; one output-parallel product over all edges then forms the
+                                                    scalar_out / vector_out_scale weight gradients instead of a read-modify-write
+                                                    of per-CTA partials per tile.  NULL: the tiles form them (slower) */
 } gcpnet_backward_io;
 
 int gcpnet_version(void);
