@@ -58,7 +58,9 @@ __global__ void __launch_bounds__(256) node_wgrad_kernel(const __grid_constant__
     for (int q = 0; q < 4; ++q) c[bb][q] = 0.f;
   const int act = jb.act;
   const float slope = p.slope;
-#pragma unroll 2
+  const bool do_bias = ig == 0 && jb.outb != nullptr;  // bias gradient = column sums of G: rides on the A fragments
+  float ba = 0.f, bc = 0.f;
+#pragma unroll 4
   for (int n0 = nbeg + 8 * warp; n0 < N; n0 += 64) {
     const int r0 = n0 + t, r1 = n0 + t + 4;
     const bool v0 = r0 < N, v1 = r1 < N;
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(256) node_wgrad_kernel(const __grid_constant__
       fb[bb][0] = (v0 && bb < nb) ? __ldg(z0 + ii[bb]) : 0.f;
       fb[bb][1] = (v1 && bb < nb) ? __ldg(z1 + ii[bb]) : 0.f;
     }
+    if (do_bias) { ba += fa[0] + fa[2]; bc += fa[1] + fa[3]; }
     uint32_t ah[4], al[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) { ah[q] = __float_as_uint(fa[q]) & 0xffffe000u; al[q] = __float_as_uint(fa[q] - __uint_as_float(ah[q])); }
@@ -106,19 +109,18 @@ __global__ void __launch_bounds__(256) node_wgrad_kernel(const __grid_constant__
     const int i = 8 * (4 * ig + bb) + 2 * (ln & 3) + (q & 1);
     if (bb < nb && j < J && i < I) outW[(size_t)j * I + i] = s;
   }
-  if (ig == 0 && jb.outb != nullptr) {  // bias gradient of this block's 16 rows of J: 16 row-partitions, fixed-order sum
+  if (do_bias) {  // bias gradient of this block's 16 rows of J: per-thread column sums -> fixed-order sum over warps and row lanes
     __syncthreads();
-    const int jj = tid & 15, part = tid >> 4;
-    const int j = 16 * jblk + jj;
-    float s = 0.f;
-    if (j < J)
-      for (int n = nbeg + part; n < N; n += 16) s += __ldg(jb.G + (size_t)n * jb.ldg + j);
-    red[0][part][jj] = s;
+    red[warp][0][lane] = ba;  // column j0 = 16 jblk + g      (lane = 4 g + t)
+    red[warp][1][lane] = bc;  // column j0 + 8
     __syncthreads();
     if (tid < 16 && 16 * jblk + tid < J) {
+      const int gg = tid & 7, half = tid >> 3;
       float a = 0.f;
 #pragma unroll
-      for (int q = 0; q < 16; ++q) a += red[0][q][tid];
+      for (int w = 0; w < 8; ++w)
+#pragma unroll
+        for (int tt = 0; tt < 4; ++tt) a += red[w][half][4 * gg + tt];
       outb[16 * jblk + tid] = a;
     }
   }
