@@ -132,3 +132,32 @@ def test_scalar_vector_algebra():
     assert s.shape == (4, 6) and v.shape == (4, 4, 3)
     h, chi = b
     assert h is b.scalar and isinstance(b, tuple)
+
+
+def test_model_classes_carry_the_reference_state_dict_names():
+    """Host side only: GCPNetCPD and GCPInteractions2 register exactly the parameters of the reference classes -- the CPD
+    fixture holds the shipped checkpoint's names and shapes, oracle.layer2_param_shapes is asserted against the reference's
+    GCPInteractions2.state_dict() when the fixtures are made (oracle/make_golden.run_layer2)."""
+    import numpy as np
+    import gcpnet_b200
+    from oracle import golden_cases as GC
+    from tests.test_gpu_model import _cpd_model
+    fx = np.load(GC.fixture_path(GC.CPD_CKPT_FIXTURE))
+    want = {k[len("param/"):]: tuple(fx[k].shape) for k in fx.files if k.startswith("param/")}
+    model = _cpd_model(GC.CPD_CKPT_ENCODER_LAYERS, 3, False)
+    got = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert got == want
+    ar = _cpd_model(2, 2, True)
+    keys = list(ar.state_dict())
+    assert "atom_embedding.weight" in keys and "decoder_layers.1.interaction.message_fusion.7.vector_up.weight" in keys
+    assert not any(k.startswith("decoder_layers.") and ("vector_down_frames" in k or "vector_out_scale" in k) for k in keys)
+    assert any(k.startswith("encoder_layers.") and "vector_out_scale" in k for k in keys)  # the encoder keeps the full GCP2
+    assert tuple(ar.state_dict()["invariant_node_projection.scalar_out.weight"].shape) == (20, 116)
+    for name, case in GC.LAYER2_CASES.items():
+        cfg = GC.build_cfg(case)
+        mcfg, lcfg = module_cfgs(cfg)
+        lcfg["use_scalar_message_attention"], lcfg["aggregate_with_row"] = case["attention"], case["aggregate_with_row"]
+        layer = gcpnet_b200.GCPInteractions2(cfg.node_dims, cfg.edge_dims, cfg=mcfg, layer_cfg=lcfg,
+                                             updating_node_positions=cfg.updating_node_positions)
+        shapes = O.layer2_param_shapes(cfg, message_attention=case["attention"])
+        assert [(k, tuple(v.shape)) for k, v in layer.state_dict().items()] == [(k, tuple(s)) for k, s in shapes.items()], name
