@@ -91,3 +91,77 @@ def test_rotation_equivariance_of_oracle():
     rh, rchi = O.interactions_forward(params, cfg, inp["h"], inp["chi"] @ Q, inp["e"], inp["xi"] @ Q, ei, fr)
     assert torch.allclose(rh, oh, rtol=1e-4, atol=1e-5)
     assert torch.allclose(rchi, ochi @ Q, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("nff,pos,masked,attention,with_row", [(1, False, True, True, True), (2, True, False, True, False),
+                                                               (3, False, False, False, True)])
+def test_interactions2_matches_reference(nff, pos, masked, attention, with_row):
+    """GCPInteractions2 with GCP3 (gcpnet.py:1265-1451, :471-700): state_dict names / order / shapes, outputs and every
+    gradient of oracle.interactions2_forward against the imported reference."""
+    ref = ref_shim.load_reference()
+    cfg = O.OracleConfig(node_dims=(16, 4), edge_dims=(8, 2), num_message_layers=3, bottleneck=2, default_bottleneck=2,
+                         num_feedforward_layers=nff, updating_node_positions=pos, reduce_function="sum", vector_residual=nff == 3)
+    rcfg, rlayer = ref_shim.make_cfgs(ref, num_message_layers=3, num_feedforward_layers=nff, bottleneck=2, vector_residual=nff == 3)
+    rcfg.selected_GCP = ref.gcpnet.GCP3
+    rlayer.use_scalar_message_attention, rlayer.aggregate_with_row = attention, with_row
+    SV = ref.ScalarVector
+    layer = ref.gcpnet.GCPInteractions2(SV(16, 4), SV(8, 2), cfg=rcfg, layer_cfg=rlayer, dropout=0.1, updating_node_positions=pos)
+    shapes = O.layer2_param_shapes(cfg, message_attention=attention)
+    assert [(k, tuple(v.shape)) for k, v in layer.state_dict().items()] == [(k, tuple(s)) for k, s in shapes.items()]
+    params = O.random_params_for(shapes, seed=5)
+    layer.load_state_dict(params, strict=True)
+    layer.eval()
+    g = torch.Generator().manual_seed(3)
+    n, E = 20, 90
+    ei = torch.randint(0, n, (2, E), generator=g)
+    inp = O.synthetic_layer_inputs(cfg, ei, n, seed=4)
+    mask = (torch.rand(n, generator=g) > 0.2) if masked else None
+    frames = O.localize(inp["node_pos"].double(), ei, node_mask=mask).float() if masked else inp["frames"]
+    lr = {k: inp[k].clone().requires_grad_(True) for k in ("h", "chi", "e", "xi")}
+    lo = {k: inp[k].clone().requires_grad_(True) for k in ("h", "chi", "e", "xi")}
+    P = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    out = layer((lr["h"], lr["chi"]), (lr["e"], lr["xi"]), ei, frames, node_mask=mask, node_pos=inp["node_pos"] if pos else None)
+    mine = O.interactions2_forward(P, cfg, lo["h"], lo["chi"], lo["e"], lo["xi"], ei, frames, node_pos=inp["node_pos"] if pos else None,
+                                   node_mask=mask, aggregate_with_row=with_row)
+    if pos:
+        (rh, rchi), rp = out
+        (mh, mchi), mp = mine
+        assert torch.allclose(mp, rp, rtol=1e-5, atol=1e-6)
+        ((rh ** 2).sum() + rchi.sum() + (rp * rp).sum()).backward()
+        ((mh ** 2).sum() + mchi.sum() + (mp * mp).sum()).backward()
+    else:
+        (rh, rchi), (mh, mchi) = out, mine
+        ((rh ** 2).sum() + rchi.sum()).backward()
+        ((mh ** 2).sum() + mchi.sum()).backward()
+    assert torch.allclose(mh, rh, rtol=1e-5, atol=1e-6) and torch.allclose(mchi, rchi, rtol=1e-5, atol=1e-6)
+    for k in lr:
+        assert torch.allclose(lo[k].grad, lr[k].grad, rtol=1e-4, atol=1e-5), k
+    for k, q in layer.named_parameters():
+        assert torch.allclose(P[k].grad, q.grad, rtol=1e-4, atol=1e-5), k
+
+
+def test_gcp_baseline_variants_match_reference():
+    """ablate_frame_updates / vector_gate=False (what GCPNetCPDLitModule builds its decoder with): oracle vs the reference
+    layer, autoregressive call under a node mask."""
+    ref = ref_shim.load_reference()
+    cfg = O.OracleConfig(node_dims=(12, 4), edge_dims=(6, 2), num_message_layers=3, bottleneck=2, default_bottleneck=2,
+                         vector_gate=False, ablate_frame_updates=True, reduce_function="add")
+    rcfg, rlayer = ref_shim.make_cfgs(ref, num_message_layers=3, bottleneck=2, vector_gate=False, ablate_frame_updates=True)
+    SV = ref.ScalarVector
+    layer = ref.GCPInteractions(SV(12, 4), SV(6, 2), cfg=rcfg, layer_cfg=rlayer, dropout=0.0, autoregressive=True)
+    params = O.random_layer_params(cfg, seed=7)
+    layer.load_state_dict(params, strict=True)
+    layer.eval()
+    g = torch.Generator().manual_seed(8)
+    n, E = 16, 70
+    ei = torch.randint(0, n, (2, E), generator=g)
+    inp = O.synthetic_layer_inputs(cfg, ei, n, seed=9)
+    mask = torch.rand(n, generator=g) > 0.25
+    frames = O.localize(inp["node_pos"].double(), ei, node_mask=mask).float()
+    reg = (torch.randn(n, 12, generator=g), torch.randn(n, 4, 3, generator=g))
+    with torch.no_grad():
+        rh, rchi = layer((inp["h"].clone(), inp["chi"].clone()), (inp["e"], inp["xi"]), ei, frames, node_rep_regressive=reg,
+                         node_mask=mask)
+        oh, ochi = O.interactions_forward(params, cfg, inp["h"], inp["chi"], inp["e"], inp["xi"], ei, frames, node_mask=mask,
+                                          node_rep_regressive=reg)
+    assert torch.allclose(oh, rh, rtol=1e-5, atol=1e-6) and torch.allclose(ochi, rchi, rtol=1e-5, atol=1e-6)
