@@ -938,10 +938,12 @@ int gcpnet_message_passing_backward(const gcpnet_layer* layer, const gcpnet_grap
   int edge_grid = 0;
   if (run_ffma_edge_backward(l, g, lp, *io, g_aggregate, st, &edge_grid)) return 1;
   GcpTimedScope timed(T_PARTIAL_REDUCE, st);
+  const bool spilled = io->ws_edge_spill != nullptr;
   partial_reduce_kernel<<<(l.n_edge_params + 255) / 256, 256, 0, st>>>(io->g_params, io->ws_edge_partial, l.n_edge_params, edge_grid,
-                                                                        nullptr, 0, 0, SkipRanges{});
+                                                                        nullptr, 0, 0, SkipRanges{}, spilled ? edge_wgrad_ranges(lp) : SkipRanges{});
   gcp_note_launches(1);
   CUDA_TRY(cudaGetLastError());
+  if (spilled && launch_edge_wgrad(l, g, lp, io->ws_edge_spill, io->saved_edge, io->g_params, st)) return 1;
   return 0;
 }
 

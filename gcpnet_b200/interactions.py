@@ -530,9 +530,11 @@ class _MPFn(torch.autograd.Function):
         g_h, g_chi, g_e, g_xi = torch.empty_like(h), torch.empty_like(chi), torch.zeros_like(e), torch.zeros_like(xi)
         g_params = f32(spec.n_edge_params)
         ws_edge, ws_ep = f32(plan.edge_cotangent_floats), f32(plan.edge_partial_floats)
+        ws_spill = f32(plan.edge_spill_floats) if plan.edge_spill_floats > 0 else None  # FFMA kernels: off-tile weight gradients
         io = _cabi.BackwardIO(_ptr(h), _ptr(chi), _ptr(e), _ptr(xi), _ptr(frames), _ptr(saved_edge), None, None, None, None,
                               _ptr(g_h), _ptr(g_chi), _ptr(g_e), _ptr(g_xi), _ptr(g_params), None, _ptr(ws_edge), _ptr(ws_ep),
                               None, _ptr(packed))
+        io.ws_edge_spill = _ptr(ws_spill)
         _lib.check(lib.gcpnet_message_passing_backward(C.byref(layer), C.byref(gv.struct), C.byref(plan), C.byref(io),
                                                        _ptr(g_agg.contiguous()), _stream()), "gcpnet_message_passing_backward")
         if _side()["stream"] is not None:
