@@ -616,3 +616,44 @@ def test_inplace_masked_update_writes_into_the_callers_tensors_like_the_referenc
         assert torch.equal(a, b)
     for a, b in zip(res[False][4], res[True][4]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("which", ["tc", "ffma_nms", "ffma_lba_chunked", "masked", "autoregressive_baseline"])
+def test_deterministic_mode_with_nan_filled_workspaces(which):
+    """``torch.use_deterministic_algorithms(True)`` must not throw -- and in that mode ``torch.empty`` fills new
+    memory with NaN, so every workspace the kernels read before writing (partial rows, carry rows of the in-tile segment
+    sums, spill / chunk scratch of the off-tile weight gradients, gather tables) would poison the result."""
+    import gcpnet_b200
+    from tests.helpers import module_cfgs
+    kw = dict(node_dims=(64, 16), edge_dims=(32, 4), scalar_nonlinearity="silu")
+    mask = reg = None
+    ar = False
+    if which in ("tc", "ffma_nms"):
+        cfg = O.OracleConfig(updating_node_positions=True, **kw)
+        case, inputs = _random_case(cfg, n=400, E=0, seed=81, graph="nms", k=20)  # 7 600 edges: several tiles per CTA on FFMA
+    elif which == "ffma_lba_chunked":
+        cfg = O.OracleConfig(node_dims=(100, 16), edge_dims=(32, 4), scalar_nonlinearity="silu", num_message_layers=3)
+        case, inputs = _random_case(cfg, n=640, E=0, seed=82, graph="knn", k=14)  # 8 960 edges: three row chunks of the product
+    else:
+        cfg = O.OracleConfig(node_dims=(100, 16), edge_dims=(32, 4), scalar_nonlinearity="silu", num_message_layers=3,
+                             **(dict(vector_gate=False, ablate_frame_updates=True, reduce_function="add") if which != "masked" else {}))
+        case, inputs = _random_case(cfg, n=256, E=0, seed=83, graph="knn", k=10)
+        g = torch.Generator().manual_seed(84)
+        mask = torch.rand(256, generator=g) > 0.1
+        inputs["node_mask"] = mask
+        inputs["frames"] = O.localize(inputs["node_pos"].double(), inputs["edge_index"], node_mask=mask).float()
+        if which != "masked":
+            ar = True
+            inputs["regressive"] = (torch.randn(256, 100, generator=g), torch.randn(256, 16, 3, generator=g))
+    params = O.random_layer_params(cfg, seed=80)
+    want = oracle_forward_backward(case, cfg, params, inputs)
+    layer = build_module(cfg, params, autoregressive=ar).eval()
+    torch.use_deterministic_algorithms(True)
+    try:
+        probe = torch.empty(8, device="cuda")
+        if not bool(torch.isnan(probe).all()):
+            pytest.skip("this PyTorch does not fill uninitialised memory in deterministic mode")
+        res = _with_tc(0 if which != "tc" else 1, lambda: module_forward_backward(layer, case, cfg, inputs))
+    finally:
+        torch.use_deterministic_algorithms(False)
+    _compare(res, want, [k for k, _ in layer.named_parameters()])
