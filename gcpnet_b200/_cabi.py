@@ -6,7 +6,7 @@ the CPU emulation the non-GPU tests drive (tests/emul, host pointers).
 from __future__ import annotations
 
 import ctypes as C
-from typing import Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Callable, Dict, List, Optional, Tuple
 
 MAX_MESSAGE_LAYERS = 12
 ACT = {None: 0, "none": 0, "relu": 1, "leakyrelu": 2, "silu": 3, "sigmoid": 4, "selu": 5}

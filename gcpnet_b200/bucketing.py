@@ -13,7 +13,7 @@ pockets, CATH proteins) replay ONE captured CUDA graph per bucket instead of lau
 from __future__ import annotations
 
 import random
-from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Callable, Dict, Iterable, List, Sequence, Tuple
 
 import numpy as np
 import torch

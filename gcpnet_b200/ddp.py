@@ -26,7 +26,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import Iterable, List, Optional, Sequence, Tuple, Union
+from typing import List, Optional, Sequence, Tuple, Union
 
 import torch
 from torch import nn

@@ -15,7 +15,7 @@ import torch
 from torch import nn
 
 from . import _cabi, _lib
-from .interactions import (GCP2Params, GCPInteractions, _check_cuda, _get, _mask_u8, _ptr, _stream, centralize, decentralize,
+from .interactions import (GCP2Params, GCPInteractions, _check_cuda, _get, _ptr, _stream, centralize, decentralize,
                            graph_views, localize)
 from .scalar_vector import ScalarVector
 

@@ -22,7 +22,7 @@ Reference line numbers cite ``src/models/components/gcpnet.py`` (``gcpnet.py``) 
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, Optional, Sequence, Tuple
 
 import torch

@@ -102,7 +102,6 @@ def run_reference(name: str, case: dict):
 def run_nms_model():
     """GCPNetNMSLitModule.forward(batch) + MSE loss on the shipped NMS_Small checkpoint (eval mode): predicted positions and
     the gradients of the loss w.r.t. every parameter (sampled), through the reference's own LightningModule class."""
-    import types
     ref, Lit = ref_shim.load_nms_litmodule()
     model_cfg, module_cfg, layer_cfg = ref_shim.nms_model_cfgs(ref)
     layer_class = lambda *a, **k: ref.GCPInteractions(*a, updating_node_positions=True, **k)
