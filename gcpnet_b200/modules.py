@@ -709,3 +709,58 @@ class GCPInteractions2(nn.Module):
         if node_mask is not None:
             node_pos = node_pos * node_mask.to(node_pos.dtype).unsqueeze(-1)
         return node_rep, node_pos
+
+
+# ------------------------------------------------------------------------------------------
+# the LBA model's forward(batch) (src/models/gcpnet_lba_module.py:41-200; the PSR / RS modules share its shape)
+# ------------------------------------------------------------------------------------------
+class GCPNetLBA(nn.Module):
+    """Modules and ``forward(batch)`` of ``GCPNetLBALitModule`` (gcpnet_lba_module.py:61-106,153-184) under the same attribute
+    names (the shipped checkpoints load with ``strict=True``): centralize -> localize -> GCPEmbedding (atom-type embedding,
+    input normalisation) -> GCPInteractions layers -> GCPLayerNorm + invariant node projection (a GCP2 without vector
+    outputs on node entities) -> mean over the nodes of each graph -> dense head.  The pooling is a segment mean over the
+    (sorted) batch index and the head two ``nn.Linear`` layers -- library ops, as in the reference."""
+
+    def __init__(self, model_cfg, module_cfg, layer_cfg, num_atom_types: int = 9):
+        super().__init__()
+        edge_in = ScalarVector(_get(model_cfg, "e_input_dim"), _get(model_cfg, "xi_input_dim"))
+        node_in = ScalarVector(num_atom_types, _get(model_cfg, "chi_input_dim"))
+        self.edge_dims = ScalarVector(_get(model_cfg, "e_hidden_dim"), _get(model_cfg, "xi_hidden_dim"))
+        self.node_dims = ScalarVector(_get(model_cfg, "h_hidden_dim"), _get(model_cfg, "chi_hidden_dim"))
+        self.norm_x_diff = bool(_get(module_cfg, "norm_x_diff", True))
+        self.gcp_embedding = GCPEmbedding(edge_in, node_in, self.edge_dims, self.node_dims, num_atom_types=num_atom_types,
+                                          cfg=module_cfg)
+        self.interaction_layers = nn.ModuleList(
+            GCPInteractions(self.node_dims, self.edge_dims, cfg=module_cfg, layer_cfg=layer_cfg,
+                            dropout=float(_get(model_cfg, "dropout", 0.0)))
+            for _ in range(int(_get(model_cfg, "num_encoder_layers"))))
+        nl = _get(module_cfg, "nonlinearities", None)
+        if nl is None:
+            nl = (_get(module_cfg, "scalar_nonlinearity", "relu"), _get(module_cfg, "vector_nonlinearity", None))
+        self.invariant_node_projection = nn.ModuleList([
+            GCPLayerNorm(self.node_dims),
+            GCP2(self.node_dims, (self.node_dims[0], 0), nonlinearities=tuple(nl), scalar_gate=_get(module_cfg, "scalar_gate", 0),
+                 vector_gate=_get(module_cfg, "vector_gate", True), frame_gate=_get(module_cfg, "frame_gate", False),
+                 sigma_frame_gate=_get(module_cfg, "sigma_frame_gate", False),
+                 vector_frame_residual=_get(module_cfg, "vector_frame_residual", False),
+                 ablate_frame_updates=_get(module_cfg, "ablate_frame_updates", False),
+                 enable_e3_equivariance=_get(module_cfg, "enable_e3_equivariance", False))])
+        s, k = self.node_dims[0], int(_get(model_cfg, "output_scale_factor", 2))
+        self.dense = nn.Sequential(nn.Linear(s, s * k), nn.ReLU(inplace=True), nn.Dropout(float(_get(model_cfg, "dense_dropout", 0.0))),
+                                   nn.Linear(s * k, int(_get(model_cfg, "output_dim", 1))))
+
+    def forward(self, batch):
+        num_graphs = getattr(batch, "num_graphs", None)
+        _, batch.x = centralize(batch, "x", batch.batch, num_graphs=num_graphs)
+        batch.f_ij = localize(batch.x, batch.edge_index, norm_x_diff=self.norm_x_diff)
+        (h, chi), (e, xi) = self.gcp_embedding(batch)
+        for layer in self.interaction_layers:
+            h, chi = layer((h, chi), (e, xi), batch.edge_index, batch.f_ij)
+        batch.h, batch.chi, batch.e, batch.xi = h, chi, e, xi
+        out = self.invariant_node_projection[0]((h, chi))
+        out = self.invariant_node_projection[1](out, batch.edge_index, batch.f_ij, node_inputs=True)
+        # scatter(out, batch.batch, reduce="mean") (gcpnet_lba_module.py:180): PyG batches are sorted by graph
+        G = int(num_graphs) if num_graphs is not None else int(batch.batch.max().item()) + 1
+        counts = torch.bincount(batch.batch, minlength=G)
+        out = torch.segment_reduce(out, "mean", lengths=counts, unsafe=True, initial=0.0)  # empty graph -> 0, as scatter
+        return batch, self.dense(out).squeeze()

@@ -247,6 +247,36 @@ def cpd_raw_batch(num_graphs: int = 2, n: int = 40, k: int = 8, seed: int = 41):
                 seq=torch.randint(0, 20, (N,), generator=g), mask=mask)
 
 
+# GCPNetLBALitModule.forward(batch): the shipped LBA checkpoint cut to its first two of eight layers
+LBA_CKPT = "checkpoints/LBA/model_1_epoch_205_rmse_1_352_pearson_0_612_spearman_0_609.ckpt"
+LBA_CKPT_FIXTURE, LBA_CKPT_LAYERS = "lba_ckpt_model", 2
+
+
+def lba_raw_batch(num_graphs: int = 3, n: int = 30, k: int = 8, seed: int = 45):
+    """Raw LBA inputs in the shapes of configs/model/model_cfg/gcp_model_lba.yaml: h = atom type ids [N] (9 types), chi = two
+    orientation vectors [N,2,3], e = 16 RBFs of the distance [E,16], xi = unit direction [E,1,3], x = atom positions, kNN
+    edges per complex, one label per complex."""
+    g = torch.Generator().manual_seed(seed)
+    N = num_graphs * n
+    x = torch.randn(num_graphs, n, 3, generator=g) * 4.0
+    d = torch.cdist(x, x) + torch.eye(n).unsqueeze(0) * 1e9
+    nbr = d.topk(k, dim=-1, largest=False).indices
+    dst = torch.arange(n).view(1, n, 1).expand(num_graphs, n, k)
+    off = (torch.arange(num_graphs) * n).view(num_graphs, 1, 1)
+    ei = torch.stack(((nbr + off).reshape(-1), (dst + off).reshape(-1)))
+    x = x.reshape(N, 3) + torch.randn(num_graphs, 1, 3, generator=g).repeat_interleave(n, 0).reshape(N, 3) * 10.0
+    row, col = ei
+    dv = x[row] - x[col]
+    dist = dv.norm(dim=-1, keepdim=True)
+    mu = torch.linspace(0.0, 4.5, 16).view(1, -1)
+    e = torch.exp(-((dist - mu) / (4.5 / 16)) ** 2)
+    xi = (dv / dist.clamp(min=1e-8)).unsqueeze(1)
+    chi = torch.randn(N, 2, 3, generator=g)
+    chi = chi / chi.norm(dim=-1, keepdim=True)
+    return dict(h=torch.randint(0, 9, (N,), generator=g), chi=chi, e=e, xi=xi, x=x, edge_index=ei,
+                batch=torch.arange(num_graphs).repeat_interleave(n), label=torch.randn(num_graphs, generator=g) * 2 + 6)
+
+
 CPD_SAMPLING_FIXTURE = "cpd_ar_sampling"   # the sampling loop on one 24-residue chain, 3 samples
 
 

@@ -159,6 +159,32 @@ def run_cpd_model(name: str):
     print(f"{name}: loss={loss.item():.6f} params={sum(v.numel() for v in sd.values())} -> {GC.fixture_path(name)}")
 
 
+def run_lba_model():
+    """GCPNetLBALitModule.forward(batch) + MSE loss (gcpnet_lba_module.py:153-191) on the shipped LBA checkpoint cut to its
+    first two layers, eval mode, through the reference's own LightningModule class."""
+    ref, Lit = ref_shim.load_lba_litmodule()
+    model_cfg, module_cfg, layer_cfg = ref_shim.lba_model_cfgs(ref, GC.LBA_CKPT_LAYERS)
+    lit = Lit(layer_class=ref.GCPInteractions, optimizer=None, scheduler=None, model_cfg=model_cfg, module_cfg=module_cfg,
+              layer_cfg=layer_cfg)
+    full = ref_shim.load_checkpoint_state_dict(GC.LBA_CKPT)
+    keep = lambda k: not k.startswith("interaction_layers.") or int(k.split(".")[1]) < GC.LBA_CKPT_LAYERS
+    sd = {k: v.float() for k, v in full.items() if keep(k)}
+    lit.load_state_dict(sd, strict=True)
+    lit.eval()
+    raw = GC.lba_raw_batch()
+    b = GC.Bag(**{k: v.clone() for k, v in raw.items()})
+    _, preds = lit.forward(b)
+    loss = torch.nn.functional.mse_loss(preds, raw["label"])
+    loss.backward()
+    rec = {"preds": preds.detach().numpy(), "loss": np.float64(loss.item()), "out_h": b.h.detach().numpy(), "out_chi": b.chi.detach().numpy()}
+    for k, p in lit.named_parameters():
+        rec["pgrad/" + k] = sample(p.grad if p.grad is not None else torch.zeros_like(p))
+    for k, v in sd.items():
+        rec["param/" + k] = v.numpy()
+    np.savez_compressed(GC.fixture_path(GC.LBA_CKPT_FIXTURE), **rec)
+    print(f"{GC.LBA_CKPT_FIXTURE}: loss={loss.item():.6f} params={sum(v.numel() for v in sd.values())} -> {GC.fixture_path(GC.LBA_CKPT_FIXTURE)}")
+
+
 def run_layer2(name: str, case: dict):
     """The reference's GCPInteractions2 with selected_GCP = GCP3 (configs/model/gcpnet_eq.yaml), eval mode: outputs and ALL
     gradients."""
@@ -252,7 +278,7 @@ def main(argv):
     torch.manual_seed(0)
     torch.set_num_threads(1)  # bitwise reproducible reductions
     names = argv[1:] or (list(GC.CASES) + list(GC.LAYER2_CASES) +
-                         [GC.NMS_MODEL_FIXTURE, GC.CPD_CKPT_FIXTURE, GC.CPD_AR_FIXTURE, GC.CPD_SAMPLING_FIXTURE])
+                         [GC.NMS_MODEL_FIXTURE, GC.CPD_CKPT_FIXTURE, GC.CPD_AR_FIXTURE, GC.CPD_SAMPLING_FIXTURE, GC.LBA_CKPT_FIXTURE])
     for name in names:
         if name == GC.NMS_MODEL_FIXTURE:
             run_nms_model()
@@ -260,6 +286,8 @@ def main(argv):
             run_cpd_model(name)
         elif name == GC.CPD_SAMPLING_FIXTURE:
             run_cpd_sampling()
+        elif name == GC.LBA_CKPT_FIXTURE:
+            run_lba_model()
         elif name in GC.LAYER2_CASES:
             run_layer2(name, GC.LAYER2_CASES[name])
         else:

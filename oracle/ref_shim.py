@@ -208,6 +208,22 @@ def load_cpd_litmodule():
     return _load_litmodule("src.models.gcpnet_cpd_module", "GCPNetCPDLitModule")
 
 
+def load_lba_litmodule():
+    """The reference's own ``GCPNetLBALitModule`` class (src/models/gcpnet_lba_module.py), imported the same way."""
+    return _load_litmodule("src.models.gcpnet_lba_module", "GCPNetLBALitModule")
+
+
+def lba_model_cfgs(ref, num_encoder_layers=8):
+    """configs/model/gcpnet_lba.yaml + model_cfg/gcp_model_lba.yaml + module_cfg/gcp_module_lba.yaml +
+    layer_cfg/gcp_interaction_layer_lba.yaml."""
+    module_cfg, layer_cfg = make_cfgs(ref)
+    module_cfg["concatenate_lig_flag"] = False
+    model_cfg = AttrDict(chi_input_dim=2, e_input_dim=16, xi_input_dim=1, h_hidden_dim=100, chi_hidden_dim=16, e_hidden_dim=32,
+                         xi_hidden_dim=4, output_dim=1, output_scale_factor=2, num_encoder_layers=num_encoder_layers,
+                         num_decoder_layers=3, dropout=0.1, dense_dropout=0.1)
+    return model_cfg, module_cfg, layer_cfg
+
+
 def cpd_model_cfgs(ref, num_encoder_layers=9, num_decoder_layers=3):
     """configs/model/gcpnet_cpd.yaml + model_cfg/gcp_model_cpd.yaml + module_cfg/gcp_module_cpd.yaml +
     layer_cfg/gcp_interaction_layer_cpd.yaml (+ mp_cfg/gcp_mp_cpd.yaml)."""
@@ -243,7 +259,8 @@ def _load_litmodule(module_name: str, class_name: str):
         return m
 
     mod("pytorch_lightning", LightningModule=_LightningModule)
-    tm = mod("torchmetrics", MeanMetric=_Metric, MinMetric=_Metric, MaxMetric=_Metric, CosineSimilarity=_Metric, CatMetric=_Metric)
+    tm = mod("torchmetrics", MeanMetric=_Metric, MinMetric=_Metric, MaxMetric=_Metric, CosineSimilarity=_Metric, CatMetric=_Metric,
+             PearsonCorrCoef=_Metric, SpearmanCorrCoef=_Metric)
     tm.regression = mod("torchmetrics.regression")
     tm.regression.mse = mod("torchmetrics.regression.mse", MeanSquaredError=_Metric)
     saved = sys.modules.get("typeguard")

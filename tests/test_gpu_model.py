@@ -363,3 +363,46 @@ def test_interactions2_layer_matches_the_reference_fixture_and_the_oracle(name):
     assert torch.isfinite(th).all()
     if mask is not None:
         assert float(th[~mask.cuda()].abs().max()) == 0.0
+
+
+def _lba_model(n_layers):
+    import gcpnet_b200
+    model_cfg = AttrDict(chi_input_dim=2, e_input_dim=16, xi_input_dim=1, h_hidden_dim=100, chi_hidden_dim=16, e_hidden_dim=32,
+                         xi_hidden_dim=4, output_dim=1, output_scale_factor=2, num_encoder_layers=n_layers, num_decoder_layers=3,
+                         dropout=0.1, dense_dropout=0.1)
+    module_cfg = AttrDict(norm_x_diff=True, concatenate_lig_flag=False, scalar_gate=0, vector_gate=True, vector_residual=False,
+                          vector_frame_residual=False, frame_gate=False, sigma_frame_gate=False, scalar_nonlinearity="relu",
+                          vector_nonlinearity=None, nonlinearities=["relu", None], bottleneck=4, vector_linear=True,
+                          vector_identity=True, default_vector_residual=False, default_bottleneck=4, ablate_frame_updates=False,
+                          ablate_scalars=False, ablate_vectors=False, enable_e3_equivariance=False)
+    mp = AttrDict(edge_encoder=False, edge_gate=False, num_message_layers=8, message_residual=0, message_ff_multiplier=1,
+                  self_message=True, use_residual_message_gcp=True)
+    layer_cfg = AttrDict(pre_norm=False, num_feedforward_layers=2, dropout=0.1, nonlinearity_slope=1e-2, mp_cfg=mp)
+    return gcpnet_b200.GCPNetLBA(model_cfg, module_cfg, layer_cfg)
+
+
+def test_lba_model_forward_backward_matches_the_reference_litmodule_on_the_shipped_checkpoint():
+    """Whole ``forward(batch)`` of GCPNetLBALitModule (gcpnet_lba_module.py:153-184) on checkpoints/LBA (cut to its first two
+    layers so that the fixture can carry the weights): atom-type embedding, input normalisation, edge / node embedding GCPs,
+    two (100,16) layers, GCPLayerNorm + invariant projection, per-complex mean, dense head; MSE loss and all gradients."""
+    fx = np.load(GC.fixture_path(GC.LBA_CKPT_FIXTURE))
+    model = _lba_model(GC.LBA_CKPT_LAYERS)
+    sd = {k[len("param/"):]: torch.from_numpy(fx[k]) for k in fx.files if k.startswith("param/")}
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    raw = GC.lba_raw_batch()
+    b = GC.Bag(**{k: v.cuda() for k, v in raw.items()})
+    b.num_graphs = 3
+    _, preds = model(b)
+    loss = torch.nn.functional.mse_loss(preds, raw["label"].cuda())
+    loss.backward()
+    assert rel_err(preds.detach().cpu().numpy(), fx["preds"]) < TOL
+    assert rel_err(b.h.detach().cpu().numpy(), fx["out_h"]) < TOL and rel_err(b.chi.detach().cpu().numpy(), fx["out_chi"]) < TOL
+    assert abs(float(loss) - float(fx["loss"])) < 1e-4 * max(1.0, abs(float(fx["loss"])))
+    for k, p in model.named_parameters():
+        want = fx["pgrad/" + k]
+        got = sample_like_fixture(p.grad.cpu()) if p.grad is not None else np.zeros_like(want)
+        if float(np.abs(want).max()) < 1e-6:
+            assert float(np.abs(got).max()) < 1e-3, k
+            continue
+        assert rel_err(got, want) < 1e-3, (k, rel_err(got, want))
