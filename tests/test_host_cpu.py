@@ -141,7 +141,11 @@ def test_model_classes_carry_the_reference_state_dict_names():
     import numpy as np
     import gcpnet_b200
     from oracle import golden_cases as GC
-    from tests.test_gpu_model import _cpd_model
+    from tests.test_gpu_model import _cpd_model, _lba_model
+    lfx = np.load(GC.fixture_path(GC.LBA_CKPT_FIXTURE))
+    lba = _lba_model(GC.LBA_CKPT_LAYERS)
+    assert {k: tuple(v.shape) for k, v in lba.state_dict().items()} == \
+        {k[len("param/"):]: tuple(lfx[k].shape) for k in lfx.files if k.startswith("param/")}
     fx = np.load(GC.fixture_path(GC.CPD_CKPT_FIXTURE))
     want = {k[len("param/"):]: tuple(fx[k].shape) for k in fx.files if k.startswith("param/")}
     model = _cpd_model(GC.CPD_CKPT_ENCODER_LAYERS, 3, False)
