@@ -168,6 +168,13 @@ int emul_layer_forward(const gcpnet_layer* layer, const gcpnet_graph* graph, con
   return 0;
 }
 
+// floats of the spill area of the off-tile weight-gradient product (0 on error)
+long long emul_edge_spill_floats(const gcpnet_layer* layer, long long N, long long E) {
+  LayerPlan lp;
+  if (!make_layer_plan(*layer, N, E, &lp, nullptr, false).empty()) return 0;
+  return edge_spill_layout(E, lp.ops).total;
+}
+
 int emul_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, const gcpnet_plan* plan,
                         const gcpnet_backward_io* io, int force_node_tile, int edge_grid, int node_grid) {
   const gcpnet_layer& l = *layer; const gcpnet_graph& g = *graph;
@@ -192,6 +199,11 @@ int emul_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, co
     ep.saved = const_cast<float*>(io->saved_edge); ep.gagg = io->ws_agg;
     ep.grow = io->ws_edge; ep.gcol = io->ws_edge + (size_t)g.num_edges * W; ep.ge = io->g_e; ep.gxi = io->g_xi;
     ep.partial = io->ws_edge_partial;
+    if (io->ws_edge_spill != nullptr) {  // off-tile weight gradients: the tiles spill gT / Z / gg rows (layer_setup.h: EdgeSpill)
+      const EdgeSpill sp = edge_spill_layout(g.num_edges, lp.ops);
+      ep.spill = io->ws_edge_spill;
+      for (int k = 0; k < lp.ops.L; ++k) { ep.sp_gT[k] = sp.gT[k]; ep.sp_Z[k] = sp.Z[k]; ep.sp_GG[k] = sp.GG[k]; }
+    }
     const int nte = (int)((g.num_edges + lp.eb.TE - 1) / lp.eb.TE);
     if (edge_grid > nte) edge_grid = nte;
     int bad = 1;
@@ -223,6 +235,33 @@ int emul_layer_backward(const gcpnet_layer* layer, const gcpnet_graph* graph, co
     if (i < l.n_edge_params) for (int c = 0; c < edge_grid; ++c) acc += io->ws_edge_partial[(size_t)c * l.n_edge_params + i];
     else for (int c = 0; c < node_grid; ++c) acc += io->ws_node_partial[(size_t)c * l.n_node_params + (i - l.n_edge_params)];
     io->g_params[i] = acc;
+  }
+  if (io->ws_edge_spill != nullptr && g.num_edges > 0) {
+    // host restatement of launch_edge_wgrad (api.cu): dW[j][i] = sum_e G[e][j] * act(Z[e][i]), db[j] = sum_e G[e][j] over the
+    // spilled rows, written over the (unwritten) partial sums of those parameters
+    const long long E = g.num_edges;
+    const EdgeSpill sp = edge_spill_layout(E, lp.ops);
+    long long offT[MAX_MSG_LAYERS], offG[MAX_MSG_LAYERS], offS[MAX_MSG_LAYERS], offV[MAX_MSG_LAYERS], tot;
+    edge_saved_offsets(l, E, offT, offG, offS, offV, &tot);
+    auto product = [&](const float* G, int ldg, int J, const float* Z, int ldz, int I, int act, float* outW, float* outb) {
+      for (int j = 0; j < J; ++j) {
+        double b = 0.0;
+        for (long long n = 0; n < E; ++n) b += G[n * ldg + j];
+        outb[j] = (float)b;
+        for (int i = 0; i < I; ++i) {
+          double a = 0.0;
+          for (long long n = 0; n < E; ++n) a += (double)G[n * ldg + j] * (double)act_fwd(act, Z[n * ldz + i], l.slope);
+          outW[(size_t)j * I + i] = (float)a;
+        }
+      }
+    };
+    for (int k = 0; k < lp.ops.L; ++k) {
+      const GcpOp& o = lp.ops.msg[k];
+      const float* spill = io->ws_edge_spill;
+      product(spill + sp.gT[k], sp.ldg[k], o.so, spill + sp.Z[k], sp.ldz[k], gcp_k(o), ACT_NONE, io->g_params + o.o_Ws, io->g_params + o.o_bs);
+      if (gcp_gated(o))
+        product(spill + sp.GG[k], sp.ldgg[k], o.vo, io->saved_edge + offT[k], o.so, o.so, o.act_v, io->g_params + o.o_Wg, io->g_params + o.o_bg);
+    }
   }
   if (l.pre_norm)  // gcp_norm.0 is applied (and differentiated) in front of the layer: the tiles never write these rows
     for (int j = 0; j < 2 * l.s; ++j) io->g_params[l.ln_grad_off[0] + j] = 0.f;

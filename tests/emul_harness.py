@@ -177,7 +177,7 @@ class EmulLayer:
             return agg
         return self.out_h, self.out_chi, self.out_pos
 
-    def backward(self, g_h, g_chi, g_pos=None, *, node_tile=0, edge_grid=3, node_grid=2):
+    def backward(self, g_h, g_chi, g_pos=None, *, node_tile=0, edge_grid=3, node_grid=2, spill=False):
         s, v = self.cfg.node_dims
         se, ve = self.cfg.edge_dims
         N, E = self.N, self.E
@@ -195,6 +195,13 @@ class EmulLayer:
                               _p(self.saved_node), _p(g_h), _p(g_chi), _p(g_pos) if g_pos is not None else None,
                               _p(self.g_h), _p(self.g_chi), _p(self.g_e), _p(self.g_xi), _p(self.g_params),
                               _p(ws_agg), _p(ws_edge), _p(ws_ep), _p(ws_np), _p(self.packed))
+        if spill:  # off-tile weight gradients of the FFMA edge backward: the tiles spill their operand rows
+            self.lib.emul_edge_spill_floats.restype = C.c_longlong
+            self.lib.emul_edge_spill_floats.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong]
+            n_spill = int(self.lib.emul_edge_spill_floats(C.byref(self.layer), N, E))
+            assert n_spill > 0
+            ws_spill = nan(n_spill)
+            io.ws_edge_spill = _p(ws_spill)
         if self.hg is not None:
             self.g_hg, self.g_chig = nan(2 * N, s), nan(2 * N, v, 3)
             io.h_gather, io.chi_gather, io.g_h_gather, io.g_chi_gather = _p(self.hg), _p(self.chig), _p(self.g_hg), _p(self.g_chig)

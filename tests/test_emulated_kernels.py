@@ -151,6 +151,42 @@ def test_emulated_wide_hidden_vector_channels(lib):
     _check(L, res, cfg, case, n)
 
 
+@pytest.mark.parametrize("variant", ["default", "baseline", "autoregressive"])
+def test_emulated_off_tile_weight_gradients(lib, variant):
+    """FFMA edge backward with spilled operand rows (ws_edge_spill): the tiles store gT / Z / gg per message GCP instead of
+    forming the scalar_out / vector_out_scale gradients, the product over all edges (host restatement of launch_edge_wgrad)
+    fills them in -- same gradients as the in-tile path and as the oracle; everything else NaN-initialised."""
+    from tests import emul_harness as EH
+    kw = dict(node_dims=(16, 4), edge_dims=(8, 2), num_message_layers=3, bottleneck=2, default_bottleneck=2,
+              scalar_nonlinearity="silu", updating_node_positions=variant == "default")
+    if variant == "baseline":
+        kw.update(vector_gate=False, ablate_frame_updates=True)
+    if variant == "autoregressive":
+        kw.update(reduce_function="add")
+    cfg = O.OracleConfig(**kw)
+    params = O.random_layer_params(cfg, seed=91)
+    g = torch.Generator().manual_seed(10)
+    n, E = 28, 150
+    ei = torch.randint(0, n, (2, E), generator=g)
+    inputs = O.synthetic_layer_inputs(cfg, ei, n, seed=92)
+    if variant == "autoregressive":
+        inputs["regressive"] = (torch.randn(n, 16, generator=g), torch.randn(n, 4, 3, generator=g))
+    case = dict(seed=93)
+    res = oracle_forward_backward(case, cfg, params, inputs)
+    L = EH.EmulLayer(lib, cfg, params, inputs)
+    L.forward()
+    ch, cchi, cpos = GC.loss_weights(case, cfg, n)
+    cp = cpos.numpy() if cfg.updating_node_positions else None
+    _, _, _, _, gp_tiles = L.backward(ch.numpy(), cchi.numpy(), cp)
+    gp_tiles = gp_tiles.copy()
+    gh, gchi, ge, gxi, gp = L.backward(ch.numpy(), cchi.numpy(), cp, spill=True)
+    assert np.isfinite(gp).all()
+    assert rel_err(gh, res["grad_h"].numpy()) < TOL and rel_err(ge, res["grad_e"].numpy()) < TOL
+    for k in L.spec.names:
+        assert rel_err(L.param_grad(k), res["pgrad/" + k].numpy()) < TOL, k
+    assert rel_err(gp, gp_tiles) < 1e-5
+
+
 def test_emulated_message_passing_only(lib):
     """GCPMessagePassing.forward alone, reduce='add' (autoregressive layers, gcpnet.py:984)."""
     from tests import emul_harness as EH
