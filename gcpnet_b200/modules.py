@@ -724,7 +724,8 @@ class GCPNetLBA(nn.Module):
     def __init__(self, model_cfg, module_cfg, layer_cfg, num_atom_types: int = 9):
         super().__init__()
         edge_in = ScalarVector(_get(model_cfg, "e_input_dim"), _get(model_cfg, "xi_input_dim"))
-        node_in = ScalarVector(num_atom_types, _get(model_cfg, "chi_input_dim"))
+        # atom-type ids through an embedding (LBA, PSR) or ready-made node scalars (RS: num_atom_types = 0, gcpnet_rs_module.py:62-76)
+        node_in = ScalarVector(num_atom_types if num_atom_types > 0 else _get(model_cfg, "h_input_dim"), _get(model_cfg, "chi_input_dim"))
         self.edge_dims = ScalarVector(_get(model_cfg, "e_hidden_dim"), _get(model_cfg, "xi_hidden_dim"))
         self.node_dims = ScalarVector(_get(model_cfg, "h_hidden_dim"), _get(model_cfg, "chi_hidden_dim"))
         self.norm_x_diff = bool(_get(module_cfg, "norm_x_diff", True))
@@ -764,3 +765,16 @@ class GCPNetLBA(nn.Module):
         counts = torch.bincount(batch.batch, minlength=G)
         out = torch.segment_reduce(out, "mean", lengths=counts, unsafe=True, initial=0.0)  # empty graph -> 0, as scatter
         return batch, self.dense(out).squeeze()
+
+
+class GCPNetPSR(GCPNetLBA):
+    """``GCPNetPSRLitModule`` (src/models/gcpnet_psr_module.py:43-192): the same modules and ``forward(batch)`` as the LBA module
+    (its config has five layers)."""
+
+
+class GCPNetRS(GCPNetLBA):
+    """``GCPNetRSLitModule`` (src/models/gcpnet_rs_module.py:43-200): the LBA module's ``forward(batch)`` with ready-made node
+    scalars instead of atom-type ids (``num_atom_types=0``, node input dims ``(h_input_dim, chi_input_dim)``)."""
+
+    def __init__(self, model_cfg, module_cfg, layer_cfg):
+        super().__init__(model_cfg, module_cfg, layer_cfg, num_atom_types=0)

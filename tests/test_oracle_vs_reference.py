@@ -165,3 +165,57 @@ def test_gcp_baseline_variants_match_reference():
         oh, ochi = O.interactions_forward(params, cfg, inp["h"], inp["chi"], inp["e"], inp["xi"], ei, frames, node_mask=mask,
                                           node_rep_regressive=reg)
     assert torch.allclose(oh, rh, rtol=1e-5, atol=1e-6) and torch.allclose(ochi, rchi, rtol=1e-5, atol=1e-6)
+
+
+def _attr(**kw):
+    from tests.helpers import AttrDict
+    return AttrDict(**kw)
+
+
+def _module_layer_cfgs():
+    module_cfg = _attr(norm_x_diff=True, concatenate_lig_flag=False, scalar_gate=0, vector_gate=True, vector_residual=False,
+                       vector_frame_residual=False, frame_gate=False, sigma_frame_gate=False, scalar_nonlinearity="relu",
+                       vector_nonlinearity=None, nonlinearities=["relu", None], bottleneck=4, vector_linear=True,
+                       vector_identity=True, default_vector_residual=False, default_bottleneck=4, node_positions_weight=1.0,
+                       ablate_frame_updates=False, ablate_scalars=False, ablate_vectors=False, ablate_x_force_update=True,
+                       enable_e3_equivariance=False)
+    mp = _attr(edge_encoder=False, edge_gate=False, num_message_layers=8, message_residual=0, message_ff_multiplier=1,
+               self_message=True, use_residual_message_gcp=True)
+    return module_cfg, _attr(pre_norm=False, num_feedforward_layers=2, dropout=0.1, nonlinearity_slope=1e-2, mp_cfg=mp)
+
+
+@pytest.mark.parametrize("family", ["NMS", "LBA", "PSR", "RS", "CPD"])
+def test_shipped_checkpoints_load_strict_into_the_model_classes(family):
+    """Every shipped checkpoint of the GCPInteractions model families (checkpoints/{NMS,LBA,PSR,RS,CPD}) loads with
+    ``strict=True`` into the corresponding gcpnet_b200 model class built from the reference's configs/model/*.yaml values:
+    same parameter names, same shapes, nothing missing, nothing extra (host side only)."""
+    import glob
+    import os
+    import gcpnet_b200
+    module_cfg, layer_cfg = _module_layer_cfgs()
+    hid = dict(h_hidden_dim=100, chi_hidden_dim=16, e_hidden_dim=32, xi_hidden_dim=4)
+    if family == "NMS":
+        build = lambda: gcpnet_b200.GCPNetNMS(_attr(h_input_dim=1, chi_input_dim=3, e_input_dim=17, xi_input_dim=1, h_hidden_dim=64,
+                                                     chi_hidden_dim=16, e_hidden_dim=32, xi_hidden_dim=4, num_encoder_layers=4,
+                                                     num_decoder_layers=3, dropout=0.1), module_cfg, layer_cfg)
+    elif family == "LBA":
+        build = lambda: gcpnet_b200.GCPNetLBA(_attr(chi_input_dim=2, e_input_dim=16, xi_input_dim=1, output_dim=1, output_scale_factor=2,
+                                                     num_encoder_layers=8, dropout=0.1, dense_dropout=0.1, **hid), module_cfg, layer_cfg)
+    elif family == "PSR":
+        build = lambda: gcpnet_b200.GCPNetPSR(_attr(chi_input_dim=2, e_input_dim=16, xi_input_dim=1, output_dim=1, output_scale_factor=2,
+                                                     num_encoder_layers=5, dropout=0.1, dense_dropout=0.1, **hid), module_cfg, layer_cfg)
+    elif family == "RS":
+        build = lambda: gcpnet_b200.GCPNetRS(_attr(h_input_dim=52, chi_input_dim=2, e_input_dim=30, xi_input_dim=1, output_dim=1,
+                                                    output_scale_factor=2, num_encoder_layers=8, dropout=0.1, dense_dropout=0.1, **hid),
+                                             module_cfg, layer_cfg)
+    else:
+        build = lambda: gcpnet_b200.GCPNetCPD([6, 3], [32, 1], _attr(output_dim=20, num_encoder_layers=9, num_decoder_layers=3,
+                                                                     dropout=0.2, decoder_residual_updates=True, **hid),
+                                              module_cfg, layer_cfg, dropout=0.2, autoregressive_decoder=False)
+    paths = sorted(glob.glob(os.path.join(ref_shim.REFERENCE_ROOT, "checkpoints", family, "**", "*.ckpt"), recursive=True))
+    assert paths, family
+    for path in paths:
+        sd = ref_shim.load_checkpoint_state_dict(os.path.relpath(path, ref_shim.REFERENCE_ROOT))
+        model = build()
+        model.load_state_dict({k: v.float() for k, v in sd.items()}, strict=True)
+        assert sum(p.numel() for p in model.parameters()) == sum(v.numel() for k, v in sd.items())
