@@ -219,3 +219,25 @@ def test_shipped_checkpoints_load_strict_into_the_model_classes(family):
         model = build()
         model.load_state_dict({k: v.float() for k, v in sd.items()}, strict=True)
         assert sum(p.numel() for p in model.parameters()) == sum(v.numel() for k, v in sd.items())
+
+
+def test_shipped_eq_checkpoints_load_strict_into_interactions2_layers():
+    """checkpoints/EQ (configs/model/gcpnet_eq.yaml: GCPInteractions2 + GCP3, scalar message attention, aggregate_with_row, one
+    feed-forward GCP with feedforward_out): every layer of every shipped checkpoint loads ``strict=True`` into
+    gcpnet_b200.GCPInteractions2 -- same parameter names and shapes (host side only; the layer's numerics are pinned by the
+    eq_layer2 fixture)."""
+    import glob
+    import os
+    import gcpnet_b200
+    module_cfg, layer_cfg = _module_layer_cfgs()
+    layer_cfg["num_feedforward_layers"], layer_cfg["use_scalar_message_attention"], layer_cfg["aggregate_with_row"] = 1, True, True
+    paths = sorted(glob.glob(os.path.join(ref_shim.REFERENCE_ROOT, "checkpoints", "EQ", "*.ckpt")))
+    assert paths
+    for path in paths:
+        sd = ref_shim.load_checkpoint_state_dict(os.path.relpath(path, ref_shim.REFERENCE_ROOT))
+        n_layers = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("interaction_layers."))
+        assert n_layers == 5  # configs/model/model_cfg/gcp_model_eq.yaml
+        for i in range(n_layers):
+            pre = f"interaction_layers.{i}."
+            layer = gcpnet_b200.GCPInteractions2((100, 16), (32, 4), cfg=module_cfg, layer_cfg=layer_cfg, dropout=0.1)
+            layer.load_state_dict({k[len(pre):]: v.float() for k, v in sd.items() if k.startswith(pre)}, strict=True)
